@@ -1,0 +1,269 @@
+"""ctypes binding of libb200phys.so (include/b200phys.h) + numpy dtypes that mirror the boundary structs.
+
+This is plumbing only: every call forwards to the C ABI. If the CUDA library is missing or cannot be loaded this module
+raises -- there is no CPU fallback anywhere in the product path.
+"""
+import ctypes as C
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200phys.so")
+
+# ---- struct mirrors (include/b200phys.h) --------------------------------------------------------------------------
+body_dtype = np.dtype([
+    ("rotation", "f4", 4), ("position", "f4", 3), ("localCOGPosition", "f4", 3), ("invMass", "f4"),
+    ("invInertia", "f4", 9), ("gravityFactor", "f4"), ("linearDamping", "f4"), ("angularDamping", "f4"),
+    ("linearVelocity", "f4", 3), ("angularVelocity", "f4", 3), ("forceAccumulator", "f4", 3), ("torqueAccumulator", "f4", 3)])
+body_state_dtype = np.dtype([("rotation", "f4", 4), ("position", "f4", 3), ("linearVelocity", "f4", 3), ("angularVelocity", "f4", 3)])
+transform_dtype = np.dtype([("rotation", "f4", 4), ("position", "f4", 3), ("reserved", "f4")])
+collider_dtype = np.dtype([
+    ("shape", "f4", 10), ("restitution", "f4"), ("friction", "f4"), ("density", "f4"),
+    ("type", "u1"), ("objectType", "u1"), ("reserved", "u2"), ("objectIndex", "u4"), ("parentTransform", "u4")])
+pair_dtype = np.dtype([("a", "u4"), ("b", "u4")])
+body_pair_dtype = np.dtype([("rbA", "u4"), ("rbB", "u4")])
+contact_dtype = np.dtype([("point", "f4", 3), ("penetrationDepth", "f4"), ("normal", "f4", 3), ("friction_restitution", "u4")])
+
+distance_joint_dtype = np.dtype([("localAnchorA", "f4", 3), ("localAnchorB", "f4", 3), ("globalLength", "f4")])
+ball_joint_dtype = np.dtype([("localAnchorA", "f4", 3), ("localAnchorB", "f4", 3)])
+fixed_joint_dtype = np.dtype([("initialInvRotationDifference", "f4", 4), ("localAnchorA", "f4", 3), ("localAnchorB", "f4", 3), ("reserved", "f4", 2)])
+hinge_joint_dtype = np.dtype([
+    ("localAnchorA", "f4", 3), ("localAnchorB", "f4", 3), ("localHingeAxisA", "f4", 3), ("localHingeAxisB", "f4", 3),
+    ("minRotationLimit", "f4"), ("maxRotationLimit", "f4"), ("maxMotorTorque", "f4"), ("motorType", "i4"),
+    ("motorVelocityOrTargetAngle", "f4"), ("localHingeTangentA", "f4", 3), ("localHingeBitangentA", "f4", 3), ("localHingeTangentB", "f4", 3)])
+cone_twist_joint_dtype = np.dtype([
+    ("localAnchorA", "f4", 3), ("localAnchorB", "f4", 3), ("localLimitAxisA", "f4", 3), ("localLimitAxisB", "f4", 3),
+    ("localLimitTangentA", "f4", 3), ("localLimitBitangentA", "f4", 3), ("localLimitTangentB", "f4", 3),
+    ("swingLimit", "f4"), ("twistLimit", "f4"), ("swingMotorType", "i4"), ("swingMotorVelocityOrTargetAngle", "f4"),
+    ("maxSwingMotorTorque", "f4"), ("swingMotorAxis", "f4"), ("twistMotorType", "i4"), ("twistMotorVelocityOrTargetAngle", "f4"),
+    ("maxTwistMotorTorque", "f4")])
+slider_joint_dtype = np.dtype([
+    ("initialInvRotationDifference", "f4", 4), ("localAnchorA", "f4", 3), ("localAnchorB", "f4", 3), ("localAxisA", "f4", 3),
+    ("negDistanceLimit", "f4"), ("posDistanceLimit", "f4"), ("maxMotorForce", "f4"), ("motorType", "i4"),
+    ("motorVelocityOrTargetDistance", "f4"), ("reserved", "f4", 2)])
+JOINT_DTYPES = [distance_joint_dtype, ball_joint_dtype, fixed_joint_dtype, hinge_joint_dtype, cone_twist_joint_dtype, slider_joint_dtype]
+
+assert body_dtype.itemsize == 140 and collider_dtype.itemsize == 64 and body_state_dtype.itemsize == 52
+assert hinge_joint_dtype.itemsize == 104 and cone_twist_joint_dtype.itemsize == 120 and fixed_joint_dtype.itemsize == 48 and slider_joint_dtype.itemsize == 80
+
+SPHERE, CAPSULE, CYLINDER, AABB, OBB, HULL = range(6)
+OBJ_RIGID_BODY, OBJ_STATIC, OBJ_FORCE_FIELD, OBJ_TRIGGER = range(4)
+NO_TRANSFORM = 0xFFFFFFFF
+STEP_FAST, STEP_EXACT_ORDER = 0, 1
+
+
+class Config(C.Structure):
+    _fields_ = [("device", C.c_int32), ("maxBodies", C.c_uint32), ("maxColliders", C.c_uint32), ("maxTransforms", C.c_uint32),
+                ("maxPairs", C.c_uint32), ("maxManifolds", C.c_uint32), ("maxJointsPerKind", C.c_uint32), ("maxGridCells", C.c_uint32),
+                ("cellSize", C.c_float), ("bigFactor", C.c_float), ("maxContacts", C.c_uint32), ("reserved", C.c_uint32 * 5)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("numBodies", C.c_uint32), ("numColliders", C.c_uint32), ("numBroadphaseOverlaps", C.c_uint32), ("numCollisions", C.c_uint32),
+                ("numContacts", C.c_uint32), ("numBigColliders", C.c_uint32), ("numGridCells", C.c_uint32), ("numColors", C.c_uint32 * 7),
+                ("overflowPairs", C.c_uint32), ("overflowManifolds", C.c_uint32), ("overflowGrid", C.c_uint32), ("epaOverflows", C.c_uint32),
+                ("gjkIterationCaps", C.c_uint32), ("assertCount", C.c_uint32), ("cellSize", C.c_float),
+                ("msWorld", C.c_float), ("msBroad", C.c_float), ("msNarrow", C.c_float), ("msInit", C.c_float), ("msSolve", C.c_float),
+                ("msIntegrate", C.c_float), ("msTotal", C.c_float), ("kernelLaunches", C.c_uint32), ("reserved", C.c_uint32 * 7)]
+
+    def as_dict(self):
+        d = {}
+        for name, _ in self._fields_:
+            v = getattr(self, name)
+            d[name] = list(v) if hasattr(v, "__len__") else v
+        return d
+
+
+# every symbol include/b200phys.h declares (tests check that the library exports all of them)
+EXPORTS = [
+    "b200phys_version", "b200phys_error_string", "b200phys_create", "b200phys_destroy", "b200phys_set_stream", "b200phys_enable_timing",
+    "b200phys_host_alloc", "b200phys_host_free",
+    "b200phys_set_hulls", "b200phys_upload_bodies", "b200phys_upload_transforms", "b200phys_upload_colliders", "b200phys_upload_joints",
+    "b200phys_upload_forces", "b200phys_step", "b200phys_synchronize", "b200phys_download_bodies", "b200phys_get_stats",
+    "b200phys_download_aabbs", "b200phys_download_pairs", "b200phys_download_contacts", "b200phys_download_collisions",
+    "b200phys_download_solve_order", "b200phys_halo_pack", "b200phys_halo_unpack", "b200phys_halo_clear", "b200phys_halo_record_bytes",
+]
+
+_lib = None
+
+
+def load_library():
+    """Loads the CUDA library; raises if it has not been built (python __graft_entry__.py build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("libb200phys.so is missing: build it with `make -C d3d12renderer_b200/csrc` (there is no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    vp, u32, i32, f32 = C.c_void_p, C.c_uint32, C.c_int, C.c_float
+    lib.b200phys_version.restype = i32
+    lib.b200phys_error_string.restype = C.c_char_p; lib.b200phys_error_string.argtypes = [i32]
+    lib.b200phys_create.argtypes = [C.POINTER(Config), C.POINTER(vp)]
+    lib.b200phys_destroy.argtypes = [vp]
+    lib.b200phys_set_stream.argtypes = [vp, vp]
+    lib.b200phys_enable_timing.argtypes = [vp, i32]
+    lib.b200phys_host_alloc.restype = vp; lib.b200phys_host_alloc.argtypes = [C.c_size_t]
+    lib.b200phys_host_free.restype = None; lib.b200phys_host_free.argtypes = [vp]
+    lib.b200phys_set_hulls.argtypes = [vp, vp, vp, u32]
+    lib.b200phys_upload_bodies.argtypes = [vp, vp, u32]
+    lib.b200phys_upload_transforms.argtypes = [vp, vp, u32]
+    lib.b200phys_upload_colliders.argtypes = [vp, vp, u32]
+    lib.b200phys_upload_joints.argtypes = [vp, i32, vp, vp, u32]
+    lib.b200phys_upload_forces.argtypes = [vp, vp, u32]
+    lib.b200phys_step.argtypes = [vp, f32, u32, u32]
+    lib.b200phys_synchronize.argtypes = [vp]
+    lib.b200phys_download_bodies.argtypes = [vp, vp, u32]
+    lib.b200phys_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    lib.b200phys_download_aabbs.argtypes = [vp, vp, C.POINTER(u32)]
+    lib.b200phys_download_pairs.argtypes = [vp, vp, C.POINTER(u32)]
+    lib.b200phys_download_contacts.argtypes = [vp, vp, vp, C.POINTER(u32)]
+    lib.b200phys_download_collisions.argtypes = [vp, vp, vp, C.POINTER(u32)]
+    lib.b200phys_download_solve_order.argtypes = [vp, i32, vp, C.POINTER(u32)]
+    lib.b200phys_halo_pack.argtypes = [vp, i32, f32, f32, C.POINTER(vp), C.POINTER(u32), C.POINTER(u32)]
+    lib.b200phys_halo_unpack.argtypes = [vp, vp, u32]
+    lib.b200phys_halo_clear.argtypes = [vp]
+    lib.b200phys_halo_record_bytes.restype = u32
+    _lib = lib
+    return lib
+
+
+class B200PhysError(RuntimeError):
+    pass
+
+
+def _check(lib, code, what):
+    if code != 0:
+        raise B200PhysError("%s failed: %d (%s)" % (what, code, lib.b200phys_error_string(code).decode()))
+
+
+def _ptr(arr):
+    return arr.ctypes.data_as(C.c_void_p) if arr is not None else None
+
+
+class PinnedArray:
+    """numpy view over page-locked memory from b200phys_host_alloc (direct DMA uploads/downloads)."""
+
+    def __init__(self, dtype, count):
+        self.lib = load_library()
+        self.nbytes = max(1, np.dtype(dtype).itemsize * count)
+        self.ptr = self.lib.b200phys_host_alloc(self.nbytes)
+        if not self.ptr:
+            raise B200PhysError("b200phys_host_alloc failed")
+        buf = (C.c_char * self.nbytes).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=dtype, count=count)
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            self.lib.b200phys_host_free(self.ptr)
+            self.ptr = None
+
+
+class Stepper:
+    """Thin object wrapper over one b200phys_context (one per GPU / rank)."""
+
+    def __init__(self, max_bodies, max_colliders, max_transforms=16, device=0, max_pairs=0, max_manifolds=0, max_contacts=0,
+                 max_joints=0, max_grid_cells=0, cell_size=0.0, big_factor=0.0):
+        self.lib = load_library()
+        cfg = Config()
+        cfg.device = device; cfg.maxBodies = max_bodies; cfg.maxColliders = max_colliders; cfg.maxTransforms = max_transforms
+        cfg.maxPairs = max_pairs; cfg.maxManifolds = max_manifolds; cfg.maxContacts = max_contacts; cfg.maxJointsPerKind = max_joints
+        cfg.maxGridCells = max_grid_cells; cfg.cellSize = cell_size; cfg.bigFactor = big_factor
+        self.ctx = C.c_void_p()
+        _check(self.lib, self.lib.b200phys_create(C.byref(cfg), C.byref(self.ctx)), "b200phys_create")
+        self.num_bodies = 0
+
+    def close(self):
+        if self.ctx:
+            self.lib.b200phys_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream_ptr):
+        _check(self.lib, self.lib.b200phys_set_stream(self.ctx, C.c_void_p(cuda_stream_ptr)), "set_stream")
+
+    def enable_timing(self, on=True):
+        _check(self.lib, self.lib.b200phys_enable_timing(self.ctx, 1 if on else 0), "enable_timing")
+
+    def set_hulls(self, vertices, offsets):
+        v = np.ascontiguousarray(vertices, dtype=np.float32); o = np.ascontiguousarray(offsets, dtype=np.uint32)
+        _check(self.lib, self.lib.b200phys_set_hulls(self.ctx, _ptr(v), _ptr(o), len(o) - 1), "set_hulls")
+
+    def upload_bodies(self, bodies):
+        assert bodies.dtype == body_dtype and bodies.flags.c_contiguous
+        _check(self.lib, self.lib.b200phys_upload_bodies(self.ctx, _ptr(bodies), len(bodies)), "upload_bodies")
+        self.num_bodies = len(bodies)
+
+    def upload_transforms(self, transforms):
+        assert transforms.dtype == transform_dtype and transforms.flags.c_contiguous
+        _check(self.lib, self.lib.b200phys_upload_transforms(self.ctx, _ptr(transforms), len(transforms)), "upload_transforms")
+
+    def upload_colliders(self, colliders):
+        assert colliders.dtype == collider_dtype and colliders.flags.c_contiguous
+        _check(self.lib, self.lib.b200phys_upload_colliders(self.ctx, _ptr(colliders), len(colliders)), "upload_colliders")
+
+    def upload_joints(self, kind, joints, pairs):
+        assert joints.dtype == JOINT_DTYPES[kind] and pairs.dtype == body_pair_dtype
+        _check(self.lib, self.lib.b200phys_upload_joints(self.ctx, kind, _ptr(np.ascontiguousarray(joints)), _ptr(np.ascontiguousarray(pairs)), len(joints)), "upload_joints")
+
+    def upload_forces(self, force_torque):
+        ft = np.ascontiguousarray(force_torque, dtype=np.float32)
+        _check(self.lib, self.lib.b200phys_upload_forces(self.ctx, _ptr(ft), ft.shape[0]), "upload_forces")
+
+    def step(self, dt, iterations, flags=STEP_FAST):
+        _check(self.lib, self.lib.b200phys_step(self.ctx, dt, iterations, flags), "step")
+
+    def synchronize(self):
+        _check(self.lib, self.lib.b200phys_synchronize(self.ctx), "synchronize")
+
+    def download_bodies(self, out=None):
+        if out is None:
+            out = np.empty(self.num_bodies, dtype=body_state_dtype)
+        _check(self.lib, self.lib.b200phys_download_bodies(self.ctx, _ptr(out), len(out)), "download_bodies")
+        return out
+
+    def stats(self, check=True):
+        st = Stats()
+        code = self.lib.b200phys_get_stats(self.ctx, C.byref(st))
+        if check:
+            _check(self.lib, code, "get_stats")
+        return st
+
+    def _count_then_fetch(self, fn, dtypes, name):
+        n = C.c_uint32(0)
+        nulls = [None] * len(dtypes)
+        _check(self.lib, fn(self.ctx, *nulls, C.byref(n)), name)
+        outs = [np.empty(n.value, dtype=dt) for dt in dtypes]
+        if n.value:
+            _check(self.lib, fn(self.ctx, *[_ptr(o) for o in outs], C.byref(n)), name)
+        return outs
+
+    def download_aabbs(self):
+        n = C.c_uint32(0)
+        _check(self.lib, self.lib.b200phys_download_aabbs(self.ctx, None, C.byref(n)), "download_aabbs")
+        out = np.empty((n.value, 6), dtype=np.float32)
+        if n.value:
+            _check(self.lib, self.lib.b200phys_download_aabbs(self.ctx, _ptr(out), C.byref(n)), "download_aabbs")
+        return out
+
+    def download_pairs(self):
+        return self._count_then_fetch(self.lib.b200phys_download_pairs, [pair_dtype], "download_pairs")[0]
+
+    def download_contacts(self):
+        return self._count_then_fetch(self.lib.b200phys_download_contacts, [contact_dtype, body_pair_dtype], "download_contacts")
+
+    def download_collisions(self):
+        return self._count_then_fetch(self.lib.b200phys_download_collisions, [pair_dtype, np.dtype("u1")], "download_collisions")
+
+    def download_solve_order(self, kind):
+        n = C.c_uint32(0)
+        _check(self.lib, self.lib.b200phys_download_solve_order(self.ctx, kind, None, C.byref(n)), "download_solve_order")
+        out = np.empty(n.value, dtype=np.uint32)
+        if n.value:
+            _check(self.lib, self.lib.b200phys_download_solve_order(self.ctx, kind, _ptr(out), C.byref(n)), "download_solve_order")
+        return out

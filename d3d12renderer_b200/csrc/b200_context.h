@@ -1,0 +1,178 @@
+// b200_context.h -- device-side data layout of one b200phys_context (see DESIGN.md "Data layout in HBM").
+//
+// Everything a step needs lives in HBM between steps; the host only uploads what gameplay code mutates and downloads
+// poses/velocities. All counts that kernels consume (pairs, manifolds, contacts, colours, grid size) stay ON THE DEVICE in
+// DeviceCounts: kernels are grid-stride loops bounded by those counters, so a step is a fixed launch sequence with no
+// host round trip in the middle.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/b200phys.h"
+
+namespace b200 {
+
+static const uint32_t kMaxBig = 1024;          // colliders too large for the grid (brute-forced)
+static const uint32_t kNumBuckets = 21;        // upper-triangular 6x6 type pairs (collision_narrow.cpp:2411-2421)
+static const uint32_t kBucketDropped = 21;     // pruned pair (no rigid body / same body)
+static const uint32_t kBucketOverlap = 22;     // trigger / force-field overlap test only
+static const uint32_t kNumPairKeys = 23;
+static const uint32_t kMaxColors = 64;         // fast mode: 64-bit colour masks
+static const uint32_t kMaxLevels = 1u << 16;   // exact mode: wavefront levels
+static const uint32_t kNumGroups = 7;          // 6 joint kinds + contacts (constraints.cpp:3748-3772 order)
+
+struct GridParams
+{
+    float cellSize, invCellSize;
+    float origin[3];
+    int32_t dims[3];
+    uint32_t numCells;
+    float bigThreshold;
+};
+
+// device-resident scalars produced and consumed by kernels
+struct DeviceCounts
+{
+    uint32_t numPairs;                  // broad-phase overlaps (clamped to capacity)
+    uint32_t numPairsWanted;            // what the scan produced (overflow detection)
+    uint32_t keyStart[kNumPairKeys + 1];// bucket ranges of the classified pair list
+    uint32_t numManifolds, numManifoldsWanted;
+    uint32_t numContacts;
+    uint32_t numColors[kNumGroups];
+    uint32_t numJoints[6];
+    uint32_t colorStart[kNumGroups][kMaxColors + 1]; // fast mode unit ranges per colour
+    uint32_t numBig;
+    uint32_t remaining;                 // colouring work counter
+    uint32_t overflowPairs, overflowManifolds, overflowGrid, overflowColors, overflowBig;
+    uint32_t epaOverflows, gjkIterationCaps, assertCount;
+    unsigned long long extentSumFixed;  // sum of AABB extents, 2^-16 fixed point (deterministic mean)
+    uint32_t extentCount;
+    uint32_t maxSmallExtentBits;        // float bits (non-negative floats order like uints)
+    uint32_t centreMinBits[3], centreMaxBits[3]; // sortable-uint encoded floats
+    GridParams grid;
+    uint32_t barrier[8];                // grid barrier words of the cooperative kernels
+};
+
+template <typename T> struct DevBuf { T* p = nullptr; size_t n = 0; };
+
+struct Context
+{
+    b200phys_config cfg;
+    int device = 0;
+    int numSMs = 148;
+    cudaStream_t stream = nullptr;      // the stream every kernel of this context is launched on
+    cudaStream_t ownStream = nullptr;
+    bool timing = false;
+    cudaEvent_t ev[8] = {};
+
+    uint32_t numBodies = 0, numColliders = 0, numTransforms = 0, numHulls = 0;
+    uint32_t numJoints[6] = {};
+    bool stepped = false;
+    uint32_t launches = 0;
+
+    // ---- bodies (persistent, SoA float4 planes; N+1 entries where the last is the static dummy, physics.cpp:1279)
+    float4* bRot = nullptr;     // rotation
+    float4* bPos = nullptr;     // position.xyz, invMass
+    float4* bCog = nullptr;     // localCOG.xyz, gravityFactor
+    float4* bInvI = nullptr;    // 3 planes: local invInertia columns + (linearDamping, angularDamping, 0)
+    float4* bVel = nullptr;     // linearVelocity.xyz
+    float4* bAng = nullptr;     // angularVelocity.xyz
+    float4* bForce = nullptr;   // forceAccumulator.xyz
+    float4* bTorque = nullptr;  // torqueAccumulator.xyz
+    // ---- per-step body global state (rigid_body_global_state, rigid_body.h:6-16)
+    float4* gVel = nullptr;     // AoS 32 B: (v.xyz, invMass), (w.xyz, 0)  -- the only record the solver iterations touch
+    float4* gPos = nullptr;     // world COG position
+    float4* gInvI = nullptr;    // AoS 48 B: world inverse inertia rows
+
+    // ---- colliders
+    float4* cLocal = nullptr;   // uploaded b200phys_collider records (4 x float4)
+    float4* xforms = nullptr;   // uploaded b200phys_transform records (2 x float4)
+    float4* wCol = nullptr;     // world colliders, AoS 64 B (gather target of the narrow phase)
+    float4* aabbMin = nullptr;  // world AABB min.xyz
+    float4* aabbMax = nullptr;  // world AABB max.xyz
+    float4* hullVerts = nullptr;   // all hull vertices (xyz, 0)
+    uint32_t* hullOffsets = nullptr;
+    float4* hullAabb = nullptr;    // 2 per hull
+
+    // ---- broad phase (uniform grid)
+    uint32_t* cellOf = nullptr;       // per collider: cell index, 0xFFFFFFFF = big
+    uint32_t* rankInCell = nullptr;
+    uint32_t* cellCount = nullptr;    // maxGridCells + 1
+    uint32_t* cellStart = nullptr;    // maxGridCells + 1
+    float4* sortedMin = nullptr;      // AABBs in cell order: (min.xyz, collider id bits)
+    float4* sortedMax = nullptr;
+    uint32_t* bigList = nullptr;
+    uint32_t* pairCount = nullptr;    // per collider
+    uint32_t* pairStart = nullptr;    // C + 1
+    uint2* pairs = nullptr;           // canonical: a < b, sorted by (a, b)
+
+    // ---- narrow phase
+    uint8_t* pairKey = nullptr;       // bucket per pair
+    uint2* pairsTyped = nullptr;      // type-ordered (collision_narrow.cpp:2374), not yet bucketed
+    uint32_t* pairDst = nullptr;      // destination slot of the stable bucket sort
+    uint2* pairsSorted = nullptr;     // bucketed, stable
+    float4* manTmp = nullptr;         // 5 planes x maxPairs: (normal, count), 4 x (point, depth)
+    unsigned long long* manScan = nullptr; // per pair (contacts << 32 | collided) and its exclusive scan
+    unsigned long long* manScanOut = nullptr;
+    uint2* collisions = nullptr;      // colliding collider pairs (one per manifold)
+    uint4* manifolds = nullptr;       // (bodyA, bodyB, contactStart, contactCount)
+    float4* contacts = nullptr;       // 2 x float4 per contact: (point, depth), (normal, friction_restitution bits)
+    uint2* contactBodies = nullptr;
+
+    // ---- solver
+    uint32_t* unitColor[kNumGroups] = {};   // colour / level per unit
+    uint32_t* unitOrder[kNumGroups] = {};   // units sorted by colour (solve order)
+    uint32_t* adjStart = nullptr;           // N + 2
+    uint32_t* adjFill = nullptr;
+    uint32_t* adjList = nullptr;            // 2 * max units
+    uint32_t* levelStart = nullptr;         // 7 x (kMaxLevels + 1): colour ranges per group
+    uint32_t* levelFill = nullptr;          // 3 x (kMaxLevels + 1): per-round progress, colour histogram, scatter cursors
+    uint32_t* slotOfContact = nullptr;      // solve slot -> canonical contact index
+    uint32_t* unitSlotStart = nullptr;      // per sorted manifold: first solve slot
+    float4* rows = nullptr;                 // 8 planes x maxContacts
+    float2* rowImp = nullptr;               // accumulated (normal, tangent) impulse per slot
+    void* jointIn[6] = {};                  // uploaded joint structs
+    uint2* jointBodies[6] = {};
+    void* jointRows[6] = {};                // solver rows per kind (structs in k_joints.cuh)
+
+    // ---- scratch
+    uint32_t* scanTmp = nullptr;            // block sums of the scan utility
+    unsigned long long* scanTmp64 = nullptr;
+    uint32_t* sortHist = nullptr;           // numKeys x numWarps histograms of the stable small-key sort
+    uint8_t* staging = nullptr;             // host<->device staging (device side)
+    size_t stagingBytes = 0;
+    void* hostStaging = nullptr;            // pinned
+    size_t hostStagingBytes = 0;
+
+    DeviceCounts* counts = nullptr;         // device
+    DeviceCounts* hostCounts = nullptr;     // pinned mirror (filled by get_stats / downloads)
+
+    // capacities
+    uint32_t maxPairs = 0, maxManifolds = 0, maxContacts = 0, maxJoints = 0, maxCells = 0;
+
+    // halo (multi-GPU)
+    uint8_t* haloBuf = nullptr; uint32_t haloCap = 0;
+    uint32_t numGhostBodies = 0, numGhostColliders = 0;
+};
+
+// launch geometry shared by every grid-stride kernel: a multiple of the SM count (148 on B200)
+static inline int gridFor(const Context* c, int blocksPerSM = 8) { return c->numSMs * blocksPerSM; }
+
+// ---- stage launchers (one per .cu file) ------------------------------------------------------------------------
+void launchUnpackBodies(Context* c, const void* devStaging, uint32_t count);
+void launchUnpackForces(Context* c, const void* devStaging, uint32_t count);
+void launchPackBodyStates(Context* c, void* devStaging, uint32_t count);
+void launchIntegrateForces(Context* c, float dt);
+void launchWorldColliders(Context* c);
+void launchIntegrateVelocities(Context* c, float dt);
+void launchBroadphase(Context* c);
+void launchNarrowphase(Context* c);
+void launchSolver(Context* c, float dt, uint32_t iterations, uint32_t flags);
+void launchPackAabbs(Context* c, float* devOut);
+
+// utilities (b200_util.cu)
+void scanExclusiveU32(Context* c, const uint32_t* in, uint32_t* out, const uint32_t* devCount, uint32_t maxCount, uint32_t* totalOut /*device, may be null*/);
+void scanExclusiveU64(Context* c, const unsigned long long* in, unsigned long long* out, const uint32_t* devCount, uint32_t maxCount, unsigned long long* totalOut);
+// stable counting sort of n (device count) elements by small keys (< numKeys <= 64): dst[i] = destination slot, keyStart[k] = ranges
+void stableSmallKeySort(Context* c, const uint8_t* keys, const uint32_t* devCount, uint32_t maxCount, uint32_t numKeys, uint32_t* dst, uint32_t* keyStart);
+
+} // namespace b200

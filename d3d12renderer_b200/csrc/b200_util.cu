@@ -1,0 +1,217 @@
+// b200_util.cu -- device-wide primitives used by the broad phase, narrow phase and solver set-up:
+//   * exclusive scan (u32 / u64) over a DEVICE-side element count: reduce -> spine -> apply, contiguous chunk per CTA
+//   * stable counting sort for small key ranges (<= 64 keys): contiguous chunk per WARP, __match_any_sync ranking
+// Both are hand-written (no CUB/thrust) and sized as multiples of the SM count.
+#include "b200_context.h"
+#include "b200_util.cuh"
+
+namespace b200 {
+
+static const int kScanThreads = 256;
+static const int kScanItems = 4;                 // per thread per tile
+static const int kScanTile = kScanThreads * kScanItems;
+
+B200_D uint32_t chunkSize(uint32_t n, uint32_t parts, uint32_t align)
+{
+    uint32_t c = (n + parts - 1) / parts;
+    return ((c + align - 1) / align) * align;
+}
+
+template <typename T>
+B200_D T blockReduceSum(T v, T* smem)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (laneId() == 0) smem[threadIdx.x >> 5] = v;
+    __syncthreads();
+    T r = 0;
+    if (threadIdx.x < 32)
+    {
+        r = (threadIdx.x < (blockDim.x >> 5)) ? smem[threadIdx.x] : (T)0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) r += __shfl_down_sync(0xffffffffu, r, o);
+    }
+    __syncthreads();
+    return r; // valid in thread 0
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kScanThreads) scanReduceKernel(const T* __restrict__ in, const uint32_t* __restrict__ devCount, uint32_t hostCount, T* __restrict__ blockSums)
+{
+    __shared__ T red[kScanThreads / 32];
+    const uint32_t n = devCount ? *devCount : hostCount;
+    const uint32_t chunk = chunkSize(n, gridDim.x, kScanTile);
+    const uint32_t begin = min(n, blockIdx.x * chunk), end = min(n, begin + chunk);
+    T sum = 0;
+    for (uint32_t i = begin + threadIdx.x; i < end; i += kScanThreads) sum += in[i];
+    sum = blockReduceSum(sum, red);
+    if (threadIdx.x == 0) blockSums[blockIdx.x] = sum;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(1024) scanSpineKernel(T* __restrict__ blockSums, uint32_t numBlocks, T* __restrict__ totalOut)
+{
+    // numBlocks <= 2048: two elements per thread, Hillis-Steele in shared memory
+    __shared__ T s[2048];
+    for (uint32_t i = threadIdx.x; i < 2048; i += blockDim.x) s[i] = (i < numBlocks) ? blockSums[i] : (T)0;
+    __syncthreads();
+    for (uint32_t off = 1; off < 2048; off <<= 1)
+    {
+        T a0 = 0, a1 = 0; uint32_t i0 = threadIdx.x, i1 = threadIdx.x + 1024;
+        if (i0 >= off) a0 = s[i0 - off];
+        if (i1 >= off) a1 = s[i1 - off];
+        __syncthreads();
+        s[i0] += a0; s[i1] += a1;
+        __syncthreads();
+    }
+    for (uint32_t i = threadIdx.x; i < numBlocks; i += blockDim.x) blockSums[i] = (i == 0) ? (T)0 : s[i - 1];
+    if (threadIdx.x == 0 && totalOut) *totalOut = s[numBlocks - 1];
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kScanThreads) scanApplyKernel(const T* __restrict__ in, T* __restrict__ out, const uint32_t* __restrict__ devCount, uint32_t hostCount,
+                                                                const T* __restrict__ blockSums, const T* __restrict__ total)
+{
+    __shared__ T warpSums[kScanThreads / 32];
+    __shared__ T carryS;
+    const uint32_t n = devCount ? *devCount : hostCount;
+    const uint32_t chunk = chunkSize(n, gridDim.x, kScanTile);
+    const uint32_t begin = min(n, blockIdx.x * chunk), end = min(n, begin + chunk);
+    T carry = blockSums[blockIdx.x];
+    for (uint32_t tile = begin; tile < end; tile += kScanTile)
+    {
+        const uint32_t base = tile + threadIdx.x * kScanItems;
+        T v[kScanItems]; T local = 0;
+#pragma unroll
+        for (int k = 0; k < kScanItems; ++k) { v[k] = (base + k < end) ? in[base + k] : (T)0; local += v[k]; }
+        // warp inclusive scan of the per-thread sums
+        T incl = local;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { T t = __shfl_up_sync(0xffffffffu, incl, o); if (laneId() >= (uint32_t)o) incl += t; }
+        if (laneId() == 31) warpSums[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        if (threadIdx.x < 32)
+        {
+            T w = (threadIdx.x < kScanThreads / 32) ? warpSums[threadIdx.x] : (T)0;
+            T wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { T t = __shfl_up_sync(0xffffffffu, wi, o); if (laneId() >= (uint32_t)o) wi += t; }
+            if (threadIdx.x < kScanThreads / 32) warpSums[threadIdx.x] = wi - w;   // exclusive warp offsets
+            if (threadIdx.x == kScanThreads / 32 - 1) carryS = wi;                 // tile total
+        }
+        __syncthreads();
+        T excl = carry + warpSums[threadIdx.x >> 5] + (incl - local);
+#pragma unroll
+        for (int k = 0; k < kScanItems; ++k) { if (base + k < end) out[base + k] = excl; excl += v[k]; }
+        carry += carryS;
+        __syncthreads();
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && total) out[n] = *total;   // out has n + 1 entries
+}
+
+template <typename T>
+static void scanExclusive(Context* c, const T* in, T* out, const uint32_t* devCount, uint32_t maxCount, T* tmp, T* totalOut)
+{
+    if (maxCount == 0) return;
+    int blocks = gridFor(c, 8);
+    if (blocks > 2048) blocks = 2048;
+    uint32_t maxBlocks = (maxCount + kScanTile - 1) / kScanTile;
+    if ((uint32_t)blocks > maxBlocks) blocks = (int)maxBlocks;
+    if (blocks < 1) blocks = 1;
+    T* total = tmp + 2048;
+    scanReduceKernel<T><<<blocks, kScanThreads, 0, c->stream>>>(in, devCount, maxCount, tmp);
+    scanSpineKernel<T><<<1, 1024, 0, c->stream>>>(tmp, (uint32_t)blocks, total);
+    scanApplyKernel<T><<<blocks, kScanThreads, 0, c->stream>>>(in, out, devCount, maxCount, tmp, total);
+    if (totalOut) cudaMemcpyAsync(totalOut, total, sizeof(T), cudaMemcpyDeviceToDevice, c->stream);
+    c->launches += 3;
+}
+
+void scanExclusiveU32(Context* c, const uint32_t* in, uint32_t* out, const uint32_t* devCount, uint32_t maxCount, uint32_t* totalOut)
+{
+    scanExclusive<uint32_t>(c, in, out, devCount, maxCount, c->scanTmp, totalOut);
+}
+void scanExclusiveU64(Context* c, const unsigned long long* in, unsigned long long* out, const uint32_t* devCount, uint32_t maxCount, unsigned long long* totalOut)
+{
+    scanExclusive<unsigned long long>(c, in, out, devCount, maxCount, c->scanTmp64, totalOut);
+}
+
+// ------------------------------------------------------------------------------------------ stable small-key sort
+static const int kSortThreads = 256;
+static const int kSortWarps = kSortThreads / 32;
+
+__global__ void __launch_bounds__(kSortThreads) sksHistKernel(const uint8_t* __restrict__ keys, const uint32_t* __restrict__ devCount, uint32_t numKeys,
+                                                              uint32_t* __restrict__ hist /* [numKeys][totalWarps] */)
+{
+    __shared__ uint32_t h[kSortWarps][64];
+    const uint32_t n = *devCount;
+    const uint32_t warp = threadIdx.x >> 5, lane = laneId();
+    const uint32_t totalWarps = gridDim.x * kSortWarps, gw = blockIdx.x * kSortWarps + warp;
+    for (uint32_t k = lane; k < 64; k += 32) h[warp][k] = 0;
+    __syncwarp();
+    const uint32_t chunk = chunkSize(n, totalWarps, 32);
+    const uint32_t begin = min(n, gw * chunk), end = min(n, begin + chunk);
+    for (uint32_t g = begin; g < end; g += 32)       // warp-uniform trip count
+    {
+        const uint32_t i = g + lane;
+        const bool valid = i < end;
+        const uint32_t key = valid ? keys[i] : 63u;
+        const uint32_t peers = __match_any_sync(0xffffffffu, valid ? key : 0x100u);
+        if (valid && (peers & laneMaskLt()) == 0) h[warp][key] += __popc(peers);
+        __syncwarp();
+    }
+    __syncwarp();
+    for (uint32_t k = lane; k < numKeys; k += 32) hist[k * totalWarps + gw] = h[warp][k];
+}
+
+__global__ void __launch_bounds__(kSortThreads) sksScatterKernel(const uint8_t* __restrict__ keys, const uint32_t* __restrict__ devCount, uint32_t numKeys,
+                                                                 const uint32_t* __restrict__ histScan, uint32_t* __restrict__ dst)
+{
+    __shared__ uint32_t base[kSortWarps][64];
+    const uint32_t n = *devCount;
+    const uint32_t warp = threadIdx.x >> 5, lane = laneId();
+    const uint32_t totalWarps = gridDim.x * kSortWarps, gw = blockIdx.x * kSortWarps + warp;
+    for (uint32_t k = lane; k < numKeys; k += 32) base[warp][k] = histScan[k * totalWarps + gw];
+    __syncwarp();
+    const uint32_t chunk = chunkSize(n, totalWarps, 32);
+    const uint32_t begin = min(n, gw * chunk), end = min(n, begin + chunk);
+    for (uint32_t g = begin; g < end; g += 32)       // warp-uniform trip count
+    {
+        const uint32_t i = g + lane;
+        const bool valid = i < end;
+        const uint32_t key = valid ? keys[i] : 63u;
+        const uint32_t peers = __match_any_sync(0xffffffffu, valid ? key : 0x100u);
+        uint32_t b = 0;
+        if (valid) b = base[warp][key];
+        __syncwarp();
+        if (valid)
+        {
+            dst[i] = b + __popc(peers & laneMaskLt());
+            if ((peers & laneMaskLt()) == 0) base[warp][key] = b + __popc(peers);
+        }
+        __syncwarp();
+    }
+}
+
+__global__ void sksKeyStartKernel(const uint32_t* __restrict__ histScan, uint32_t numKeys, uint32_t totalWarps, const uint32_t* __restrict__ devCount, uint32_t* __restrict__ keyStart)
+{
+    uint32_t k = threadIdx.x;
+    if (k < numKeys) keyStart[k] = histScan[k * totalWarps];
+    if (k == numKeys) keyStart[k] = *devCount;
+}
+
+void stableSmallKeySort(Context* c, const uint8_t* keys, const uint32_t* devCount, uint32_t maxCount, uint32_t numKeys, uint32_t* dst, uint32_t* keyStart)
+{
+    if (maxCount == 0) return;
+    const int blocks = gridFor(c, 4);
+    const uint32_t totalWarps = (uint32_t)blocks * kSortWarps;
+    uint32_t* hist = c->sortHist;                       // numKeys * totalWarps (+1)
+    uint32_t* histScan = hist + 64 * totalWarps + 64;
+    sksHistKernel<<<blocks, kSortThreads, 0, c->stream>>>(keys, devCount, numKeys, hist);
+    c->launches += 1;
+    scanExclusiveU32(c, hist, histScan, nullptr, numKeys * totalWarps, nullptr);
+    sksScatterKernel<<<blocks, kSortThreads, 0, c->stream>>>(keys, devCount, numKeys, histScan, dst);
+    sksKeyStartKernel<<<1, 64, 0, c->stream>>>(histScan, numKeys, totalWarps, devCount, keyStart);
+    c->launches += 2;
+}
+
+} // namespace b200

@@ -1,0 +1,404 @@
+// b200phys_api.cu -- the C ABI of libb200phys.so (include/b200phys.h): context lifetime, scene upload, step, downloads.
+// Host side only orchestrates: allocate HBM once (replaces the reference's per-step arena scratch, physics.cpp:1205-1230),
+// enqueue the fixed kernel sequence of one physicsStepInternal (physics.cpp:1180-1362) on the context's stream, copy results.
+// There is no CPU implementation of any stage in this library: without a CUDA device b200phys_create fails.
+#include "b200_context.h"
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+using namespace b200;
+
+struct b200phys_context { Context c; };
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return -(int)e_; } while (0)
+
+namespace {
+
+template <typename T> cudaError_t devAlloc(T*& p, size_t n) { p = nullptr; if (n == 0) n = 1; return cudaMalloc((void**)&p, n * sizeof(T)); }
+
+int allocateAll(Context& c)
+{
+    const b200phys_config& g = c.cfg;
+    const size_t N1 = (size_t)g.maxBodies + 1, C = g.maxColliders ? g.maxColliders : 1, T = g.maxTransforms ? g.maxTransforms : 1;
+    c.maxPairs = g.maxPairs ? g.maxPairs : 16u * (uint32_t)C;
+    c.maxManifolds = g.maxManifolds ? g.maxManifolds : c.maxPairs;
+    if (c.maxManifolds > c.maxPairs) c.maxManifolds = c.maxPairs;
+    c.maxContacts = g.maxContacts ? g.maxContacts : 2u * c.maxManifolds + 1024u;
+    c.maxJoints = g.maxJointsPerKind ? g.maxJointsPerKind : g.maxBodies;
+    c.maxCells = g.maxGridCells ? g.maxGridCells : (1u << 24);
+    const size_t P = c.maxPairs, M = c.maxManifolds, K = c.maxContacts, J = c.maxJoints;
+
+    CK(devAlloc(c.bRot, N1)); CK(devAlloc(c.bPos, N1)); CK(devAlloc(c.bCog, N1)); CK(devAlloc(c.bInvI, 3 * N1));
+    CK(devAlloc(c.bVel, N1)); CK(devAlloc(c.bAng, N1)); CK(devAlloc(c.bForce, N1)); CK(devAlloc(c.bTorque, N1));
+    CK(devAlloc(c.gVel, 2 * N1)); CK(devAlloc(c.gPos, N1)); CK(devAlloc(c.gInvI, 3 * N1));
+    CK(devAlloc(c.cLocal, 4 * C)); CK(devAlloc(c.xforms, 2 * T)); CK(devAlloc(c.wCol, 4 * C)); CK(devAlloc(c.aabbMin, C)); CK(devAlloc(c.aabbMax, C));
+    CK(devAlloc(c.hullVerts, 1)); CK(devAlloc(c.hullOffsets, 2)); CK(devAlloc(c.hullAabb, 2));
+    CK(devAlloc(c.cellOf, C)); CK(devAlloc(c.rankInCell, C)); CK(devAlloc(c.cellCount, (size_t)c.maxCells + 2)); CK(devAlloc(c.cellStart, (size_t)c.maxCells + 2));
+    CK(devAlloc(c.sortedMin, C)); CK(devAlloc(c.sortedMax, C)); CK(devAlloc(c.bigList, kMaxBig));
+    CK(devAlloc(c.pairCount, C + 2)); CK(devAlloc(c.pairStart, C + 2)); CK(devAlloc(c.pairs, P));
+    CK(devAlloc(c.pairKey, P)); CK(devAlloc(c.pairsTyped, P)); CK(devAlloc(c.pairDst, P + 2)); CK(devAlloc(c.pairsSorted, P));
+    CK(devAlloc(c.manTmp, 5 * P)); CK(devAlloc(c.manScan, P + 2)); CK(devAlloc(c.manScanOut, P + 2));
+    CK(devAlloc(c.collisions, M)); CK(devAlloc(c.manifolds, M)); CK(devAlloc(c.contacts, 2 * K)); CK(devAlloc(c.contactBodies, K));
+    for (uint32_t gI = 0; gI < kNumGroups; ++gI)
+    {
+        const size_t units = (gI == 6) ? M : J;
+        CK(devAlloc(c.unitColor[gI], units)); CK(devAlloc(c.unitOrder[gI], units));
+    }
+    CK(devAlloc(c.adjStart, N1 + 2)); CK(devAlloc(c.adjFill, N1 + 2)); CK(devAlloc(c.adjList, 2 * (M > J ? M : J)));
+    CK(devAlloc(c.levelStart, (size_t)kNumGroups * (kMaxLevels + 1))); CK(devAlloc(c.levelFill, (size_t)3 * (kMaxLevels + 1)));
+    CK(devAlloc(c.slotOfContact, K)); CK(devAlloc(c.unitSlotStart, M + 2)); CK(devAlloc(c.rows, 8 * K)); CK(devAlloc(c.rowImp, K));
+    static const size_t inBytes[6] = { sizeof(b200phys_distance_joint), sizeof(b200phys_ball_joint), sizeof(b200phys_fixed_joint),
+                                       sizeof(b200phys_hinge_joint), sizeof(b200phys_cone_twist_joint), sizeof(b200phys_slider_joint) };
+    for (int k = 0; k < 6; ++k)
+    {
+        uint8_t* p = nullptr; CK(devAlloc(p, J * inBytes[k])); c.jointIn[k] = p;
+        CK(devAlloc(c.jointBodies[k], J));
+        uint8_t* r = nullptr; CK(devAlloc(r, J * 512)); c.jointRows[k] = r;   // every row struct is < 512 bytes (static_assert in k_solver.cu)
+    }
+    CK(devAlloc(c.scanTmp, 4096)); CK(devAlloc(c.scanTmp64, 4096));
+    const size_t totalWarps = (size_t)c.numSMs * 4 * 8;
+    CK(devAlloc(c.sortHist, 2 * (64 * totalWarps + 64) + 64));
+    c.stagingBytes = (size_t)g.maxBodies * sizeof(b200phys_body);
+    if (c.stagingBytes < C * 24) c.stagingBytes = C * 24;
+    if (c.stagingBytes < 1024) c.stagingBytes = 1024;
+    CK(devAlloc(c.staging, c.stagingBytes));
+    CK(devAlloc(c.counts, 1));
+    CK(cudaMemset(c.counts, 0, sizeof(DeviceCounts)));
+    CK(cudaHostAlloc((void**)&c.hostCounts, sizeof(DeviceCounts), cudaHostAllocDefault));
+    memset(c.hostCounts, 0, sizeof(DeviceCounts));
+    // the dummy body slot and all planes start zeroed
+    CK(cudaMemset(c.bRot, 0, N1 * 16)); CK(cudaMemset(c.bPos, 0, N1 * 16)); CK(cudaMemset(c.bCog, 0, N1 * 16)); CK(cudaMemset(c.bInvI, 0, 3 * N1 * 16));
+    CK(cudaMemset(c.bVel, 0, N1 * 16)); CK(cudaMemset(c.bAng, 0, N1 * 16)); CK(cudaMemset(c.bForce, 0, N1 * 16)); CK(cudaMemset(c.bTorque, 0, N1 * 16));
+    CK(cudaMemset(c.hullOffsets, 0, 8));
+    for (int i = 0; i < 8; ++i) CK(cudaEventCreate(&c.ev[i]));
+    return 0;
+}
+
+void freeAll(Context& c)
+{
+    void* ptrs[] = { c.bRot, c.bPos, c.bCog, c.bInvI, c.bVel, c.bAng, c.bForce, c.bTorque, c.gVel, c.gPos, c.gInvI, c.cLocal, c.xforms, c.wCol, c.aabbMin, c.aabbMax,
+        c.hullVerts, c.hullOffsets, c.hullAabb, c.cellOf, c.rankInCell, c.cellCount, c.cellStart, c.sortedMin, c.sortedMax, c.bigList, c.pairCount, c.pairStart, c.pairs,
+        c.pairKey, c.pairsTyped, c.pairDst, c.pairsSorted, c.manTmp, c.manScan, c.manScanOut, c.collisions, c.manifolds, c.contacts, c.contactBodies,
+        c.adjStart, c.adjFill, c.adjList, c.levelStart, c.levelFill, c.slotOfContact, c.unitSlotStart, c.rows, c.rowImp, c.scanTmp, c.scanTmp64, c.sortHist, c.staging, c.counts, c.haloBuf };
+    for (void* p : ptrs) if (p) cudaFree(p);
+    for (uint32_t g = 0; g < kNumGroups; ++g) { if (c.unitColor[g]) cudaFree(c.unitColor[g]); if (c.unitOrder[g]) cudaFree(c.unitOrder[g]); }
+    for (int k = 0; k < 6; ++k) { if (c.jointIn[k]) cudaFree(c.jointIn[k]); if (c.jointBodies[k]) cudaFree(c.jointBodies[k]); if (c.jointRows[k]) cudaFree(c.jointRows[k]); }
+    if (c.hostCounts) cudaFreeHost(c.hostCounts);
+    for (int i = 0; i < 8; ++i) if (c.ev[i]) cudaEventDestroy(c.ev[i]);
+    if (c.ownStream) cudaStreamDestroy(c.ownStream);
+}
+
+int fetchCounts(Context& c)
+{
+    CK(cudaMemcpyAsync(c.hostCounts, c.counts, sizeof(DeviceCounts), cudaMemcpyDeviceToHost, c.stream));
+    CK(cudaStreamSynchronize(c.stream));
+    return 0;
+}
+
+} // namespace
+
+extern "C" {
+
+int b200phys_version(void) { return B200PHYS_VERSION; }
+
+const char* b200phys_error_string(int code)
+{
+    if (code == 0) return "ok";
+    if (code < 0) return cudaGetErrorString((cudaError_t)(-code));
+    switch (code)
+    {
+    case B200PHYS_E_INVALID: return "invalid argument";
+    case B200PHYS_E_CAPACITY: return "device buffer capacity exceeded (see b200phys_stats overflow counters)";
+    case B200PHYS_E_NOT_READY: return "not ready (nothing uploaded / no step yet)";
+    default: return "unknown error";
+    }
+}
+
+void* b200phys_host_alloc(size_t bytes) { void* p = nullptr; if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) return nullptr; return p; }
+void b200phys_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+int b200phys_create(const b200phys_config* config, b200phys_context** out)
+{
+    if (!config || !out) return B200PHYS_E_INVALID;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess) return -(int)e;
+    if (count == 0) return -(int)cudaErrorNoDevice;
+    if (config->device < 0 || config->device >= count) return B200PHYS_E_INVALID;
+    CK(cudaSetDevice(config->device));
+    b200phys_context* ctx = new (std::nothrow) b200phys_context();
+    if (!ctx) return B200PHYS_E_INVALID;
+    Context& c = ctx->c;
+    c.cfg = *config; c.device = config->device;
+    cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, c.device));
+    c.numSMs = prop.multiProcessorCount;
+    if (!prop.cooperativeLaunch) { delete ctx; return -(int)cudaErrorNotSupported; }
+    CK(cudaStreamCreateWithFlags(&c.ownStream, cudaStreamNonBlocking));
+    c.stream = c.ownStream;
+    int r = allocateAll(c);
+    if (r != 0) { freeAll(c); delete ctx; return r; }
+    *out = ctx;
+    return 0;
+}
+
+int b200phys_destroy(b200phys_context* ctx)
+{
+    if (!ctx) return B200PHYS_E_INVALID;
+    cudaSetDevice(ctx->c.device);
+    cudaDeviceSynchronize();
+    freeAll(ctx->c);
+    delete ctx;
+    return 0;
+}
+
+int b200phys_set_stream(b200phys_context* ctx, void* cudaStream)
+{
+    if (!ctx) return B200PHYS_E_INVALID;
+    ctx->c.stream = cudaStream ? (cudaStream_t)cudaStream : ctx->c.ownStream;
+    return 0;
+}
+
+int b200phys_enable_timing(b200phys_context* ctx, int enabled) { if (!ctx) return B200PHYS_E_INVALID; ctx->c.timing = enabled != 0; return 0; }
+
+int b200phys_set_hulls(b200phys_context* ctx, const float* vertices, const uint32_t* vertexOffsets, uint32_t numHulls)
+{
+    if (!ctx || (numHulls && (!vertices || !vertexOffsets))) return B200PHYS_E_INVALID;
+    Context& c = ctx->c; CK(cudaSetDevice(c.device));
+    CK(cudaStreamSynchronize(c.stream));
+    const uint32_t nv = numHulls ? vertexOffsets[numHulls] : 0;
+    if (c.hullVerts) cudaFree(c.hullVerts); if (c.hullOffsets) cudaFree(c.hullOffsets); if (c.hullAabb) cudaFree(c.hullAabb);
+    CK(devAlloc(c.hullVerts, (size_t)nv + 1)); CK(devAlloc(c.hullOffsets, (size_t)numHulls + 2)); CK(devAlloc(c.hullAabb, 2 * (size_t)numHulls + 2));
+    float4* hv = new float4[nv + 1]; float4* ha = new float4[2 * numHulls + 2];
+    for (uint32_t h = 0; h < numHulls; ++h)
+    {   // local aabb like hullFromMesh (bounding_volumes.cpp:1385-1397): grow() over the vertices
+        float mn[3] = { 3.402823466e+38f, 3.402823466e+38f, 3.402823466e+38f }, mx[3] = { -3.402823466e+38f, -3.402823466e+38f, -3.402823466e+38f };
+        for (uint32_t v = vertexOffsets[h]; v < vertexOffsets[h + 1]; ++v)
+        {
+            const float* p = vertices + 3 * (size_t)v;
+            hv[v] = make_float4(p[0], p[1], p[2], 0.f);
+            for (int a = 0; a < 3; ++a) { mn[a] = mn[a] < p[a] ? mn[a] : p[a]; mx[a] = mx[a] < p[a] ? p[a] : mx[a]; }
+        }
+        ha[2 * h] = make_float4(mn[0], mn[1], mn[2], 0.f); ha[2 * h + 1] = make_float4(mx[0], mx[1], mx[2], 0.f);
+    }
+    cudaError_t e1 = cudaMemcpy(c.hullVerts, hv, sizeof(float4) * nv, cudaMemcpyHostToDevice);
+    cudaError_t e2 = cudaMemcpy(c.hullOffsets, vertexOffsets, sizeof(uint32_t) * ((size_t)numHulls + (numHulls ? 1 : 0)), cudaMemcpyHostToDevice);
+    cudaError_t e3 = cudaMemcpy(c.hullAabb, ha, sizeof(float4) * 2 * numHulls, cudaMemcpyHostToDevice);
+    delete[] hv; delete[] ha;
+    CK(e1); CK(e2); CK(e3);
+    c.numHulls = numHulls;
+    return 0;
+}
+
+int b200phys_upload_bodies(b200phys_context* ctx, const b200phys_body* bodies, uint32_t count)
+{
+    if (!ctx || (count && !bodies) || count > ctx->c.cfg.maxBodies) return B200PHYS_E_INVALID;
+    Context& c = ctx->c; CK(cudaSetDevice(c.device));
+    if (count)
+    {
+        CK(cudaMemcpyAsync(c.staging, bodies, sizeof(b200phys_body) * (size_t)count, cudaMemcpyHostToDevice, c.stream));
+        launchUnpackBodies(&c, c.staging, count);
+    }
+    c.numBodies = count;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int b200phys_upload_forces(b200phys_context* ctx, const float* forceTorque6, uint32_t count)
+{
+    if (!ctx || (count && !forceTorque6) || count != ctx->c.numBodies) return B200PHYS_E_INVALID;
+    Context& c = ctx->c; CK(cudaSetDevice(c.device));
+    if (count)
+    {
+        CK(cudaMemcpyAsync(c.staging, forceTorque6, 24 * (size_t)count, cudaMemcpyHostToDevice, c.stream));
+        launchUnpackForces(&c, c.staging, count);
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int b200phys_upload_transforms(b200phys_context* ctx, const b200phys_transform* transforms, uint32_t count)
+{
+    if (!ctx || (count && !transforms) || count > (ctx->c.cfg.maxTransforms ? ctx->c.cfg.maxTransforms : 1)) return B200PHYS_E_INVALID;
+    Context& c = ctx->c; CK(cudaSetDevice(c.device));
+    if (count) CK(cudaMemcpyAsync(c.xforms, transforms, sizeof(b200phys_transform) * (size_t)count, cudaMemcpyHostToDevice, c.stream));
+    c.numTransforms = count;
+    return 0;
+}
+
+int b200phys_upload_colliders(b200phys_context* ctx, const b200phys_collider* colliders, uint32_t count)
+{
+    if (!ctx || (count && !colliders) || count > ctx->c.cfg.maxColliders) return B200PHYS_E_INVALID;
+    Context& c = ctx->c; CK(cudaSetDevice(c.device));
+    if (count) CK(cudaMemcpyAsync(c.cLocal, colliders, sizeof(b200phys_collider) * (size_t)count, cudaMemcpyHostToDevice, c.stream));
+    c.numColliders = count;
+    return 0;
+}
+
+int b200phys_upload_joints(b200phys_context* ctx, int kind, const void* joints, const b200phys_body_pair* pairs, uint32_t count)
+{
+    if (!ctx || kind < 0 || kind >= 6 || (count && (!joints || !pairs)) || count > ctx->c.maxJoints) return B200PHYS_E_INVALID;
+    static const size_t inBytes[6] = { sizeof(b200phys_distance_joint), sizeof(b200phys_ball_joint), sizeof(b200phys_fixed_joint),
+                                       sizeof(b200phys_hinge_joint), sizeof(b200phys_cone_twist_joint), sizeof(b200phys_slider_joint) };
+    Context& c = ctx->c; CK(cudaSetDevice(c.device));
+    if (count)
+    {
+        CK(cudaMemcpyAsync(c.jointIn[kind], joints, inBytes[kind] * (size_t)count, cudaMemcpyHostToDevice, c.stream));
+        CK(cudaMemcpyAsync(c.jointBodies[kind], pairs, sizeof(b200phys_body_pair) * (size_t)count, cudaMemcpyHostToDevice, c.stream));
+    }
+    c.numJoints[kind] = count;
+    return 0;
+}
+
+int b200phys_step(b200phys_context* ctx, float dt, uint32_t numSolverIterations, uint32_t flags)
+{
+    if (!ctx || !(dt > 0.f)) return B200PHYS_E_INVALID;
+    Context& c = ctx->c; CK(cudaSetDevice(c.device));
+    c.launches = 0;
+    if (c.timing) cudaEventRecord(c.ev[0], c.stream);
+    launchWorldColliders(&c);                               // physics.cpp:1217
+    if (c.timing) cudaEventRecord(c.ev[1], c.stream);
+    launchBroadphase(&c);                                   // physics.cpp:1222
+    if (c.timing) cudaEventRecord(c.ev[2], c.stream);
+    launchNarrowphase(&c);                                  // physics.cpp:1233
+    if (c.timing) cudaEventRecord(c.ev[3], c.stream);
+    launchIntegrateForces(&c, dt);                          // physics.cpp:1266-1279
+    launchSolver(&c, dt, numSolverIterations, flags);       // physics.cpp:1316-1334 (records ev[4] before the iterations)
+    if (c.timing) cudaEventRecord(c.ev[5], c.stream);
+    launchIntegrateVelocities(&c, dt);                      // physics.cpp:1338-1348
+    if (c.timing) cudaEventRecord(c.ev[6], c.stream);
+    c.stepped = true;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int b200phys_synchronize(b200phys_context* ctx)
+{
+    if (!ctx) return B200PHYS_E_INVALID;
+    CK(cudaSetDevice(ctx->c.device));
+    CK(cudaStreamSynchronize(ctx->c.stream));
+    return 0;
+}
+
+int b200phys_download_bodies(b200phys_context* ctx, b200phys_body_state* out, uint32_t count)
+{
+    if (!ctx || !out || count > ctx->c.numBodies) return B200PHYS_E_INVALID;
+    Context& c = ctx->c; CK(cudaSetDevice(c.device));
+    if (!count) return 0;
+    launchPackBodyStates(&c, c.staging, count);
+    CK(cudaMemcpyAsync(out, c.staging, sizeof(b200phys_body_state) * (size_t)count, cudaMemcpyDeviceToHost, c.stream));
+    CK(cudaStreamSynchronize(c.stream));
+    return 0;
+}
+
+int b200phys_get_stats(b200phys_context* ctx, b200phys_stats* out)
+{
+    if (!ctx || !out) return B200PHYS_E_INVALID;
+    Context& c = ctx->c; CK(cudaSetDevice(c.device));
+    int r = fetchCounts(c); if (r) return r;
+    const DeviceCounts& d = *c.hostCounts;
+    memset(out, 0, sizeof(*out));
+    out->numBodies = c.numBodies; out->numColliders = c.numColliders;
+    out->numBroadphaseOverlaps = d.numPairs; out->numCollisions = d.numManifolds; out->numContacts = d.numContacts;
+    out->numBigColliders = d.numBig; out->numGridCells = d.grid.numCells;
+    for (int g = 0; g < 7; ++g) out->numColors[g] = d.numColors[g];
+    out->overflowPairs = d.overflowPairs; out->overflowManifolds = d.overflowManifolds; out->overflowGrid = d.overflowGrid | d.overflowBig | (d.overflowColors << 8);
+    out->epaOverflows = d.epaOverflows; out->gjkIterationCaps = d.gjkIterationCaps; out->assertCount = d.assertCount;
+    out->cellSize = d.grid.cellSize;
+    out->kernelLaunches = c.launches;
+    if (c.timing && c.stepped)
+    {
+        float ms[6] = {};
+        for (int i = 0; i < 6; ++i) cudaEventElapsedTime(&ms[i], c.ev[i], c.ev[i + 1]);
+        out->msWorld = ms[0]; out->msBroad = ms[1]; out->msNarrow = ms[2]; out->msInit = ms[3]; out->msSolve = ms[4]; out->msIntegrate = ms[5];
+        cudaEventElapsedTime(&out->msTotal, c.ev[0], c.ev[6]);
+    }
+    if (d.overflowPairs || d.overflowManifolds || d.overflowGrid || d.overflowBig || d.overflowColors) return B200PHYS_E_CAPACITY;
+    return 0;
+}
+
+int b200phys_download_aabbs(b200phys_context* ctx, float* outMinMax6, uint32_t* count)
+{
+    if (!ctx || !count) return B200PHYS_E_INVALID;
+    Context& c = ctx->c; CK(cudaSetDevice(c.device));
+    if (!c.stepped) return B200PHYS_E_NOT_READY;
+    *count = c.numColliders;
+    if (!outMinMax6 || !c.numColliders) return 0;
+    launchPackAabbs(&c, (float*)c.staging);
+    CK(cudaMemcpyAsync(outMinMax6, c.staging, 24 * (size_t)c.numColliders, cudaMemcpyDeviceToHost, c.stream));
+    CK(cudaStreamSynchronize(c.stream));
+    return 0;
+}
+
+int b200phys_download_pairs(b200phys_context* ctx, b200phys_collider_pair* out, uint32_t* count)
+{
+    if (!ctx || !count) return B200PHYS_E_INVALID;
+    Context& c = ctx->c; CK(cudaSetDevice(c.device));
+    if (!c.stepped) return B200PHYS_E_NOT_READY;
+    int r = fetchCounts(c); if (r) return r;
+    *count = c.hostCounts->numPairs;
+    if (out && *count) { CK(cudaMemcpyAsync(out, c.pairs, sizeof(uint2) * (size_t)*count, cudaMemcpyDeviceToHost, c.stream)); CK(cudaStreamSynchronize(c.stream)); }
+    return 0;
+}
+
+int b200phys_download_contacts(b200phys_context* ctx, b200phys_contact* outContacts, b200phys_body_pair* outBodyPairs, uint32_t* count)
+{
+    if (!ctx || !count) return B200PHYS_E_INVALID;
+    Context& c = ctx->c; CK(cudaSetDevice(c.device));
+    if (!c.stepped) return B200PHYS_E_NOT_READY;
+    int r = fetchCounts(c); if (r) return r;
+    *count = c.hostCounts->numContacts;
+    if (*count)
+    {
+        if (outContacts) CK(cudaMemcpyAsync(outContacts, c.contacts, sizeof(b200phys_contact) * (size_t)*count, cudaMemcpyDeviceToHost, c.stream));
+        if (outBodyPairs) CK(cudaMemcpyAsync(outBodyPairs, c.contactBodies, sizeof(uint2) * (size_t)*count, cudaMemcpyDeviceToHost, c.stream));
+        CK(cudaStreamSynchronize(c.stream));
+    }
+    return 0;
+}
+
+int b200phys_download_collisions(b200phys_context* ctx, b200phys_collider_pair* outPairs, uint8_t* outContactCounts, uint32_t* count)
+{
+    if (!ctx || !count) return B200PHYS_E_INVALID;
+    Context& c = ctx->c; CK(cudaSetDevice(c.device));
+    if (!c.stepped) return B200PHYS_E_NOT_READY;
+    int r = fetchCounts(c); if (r) return r;
+    const uint32_t n = c.hostCounts->numManifolds;
+    *count = n;
+    if (n && outPairs) { CK(cudaMemcpyAsync(outPairs, c.collisions, sizeof(uint2) * (size_t)n, cudaMemcpyDeviceToHost, c.stream)); }
+    if (n && outContactCounts)
+    {
+        uint4* tmp = new uint4[n];
+        cudaError_t e = cudaMemcpyAsync(tmp, c.manifolds, sizeof(uint4) * (size_t)n, cudaMemcpyDeviceToHost, c.stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c.stream);
+        if (e == cudaSuccess) for (uint32_t i = 0; i < n; ++i) outContactCounts[i] = (uint8_t)tmp[i].w;
+        delete[] tmp;
+        CK(e);
+    }
+    CK(cudaStreamSynchronize(c.stream));
+    return 0;
+}
+
+int b200phys_download_solve_order(b200phys_context* ctx, int kind, uint32_t* outOrder, uint32_t* count)
+{
+    if (!ctx || !count || kind < 0 || kind > 6) return B200PHYS_E_INVALID;
+    Context& c = ctx->c; CK(cudaSetDevice(c.device));
+    if (!c.stepped) return B200PHYS_E_NOT_READY;
+    int r = fetchCounts(c); if (r) return r;
+    if (kind == 6)
+    {
+        *count = c.hostCounts->numContacts;
+        if (outOrder && *count) { CK(cudaMemcpyAsync(outOrder, c.slotOfContact, 4 * (size_t)*count, cudaMemcpyDeviceToHost, c.stream)); CK(cudaStreamSynchronize(c.stream)); }
+    }
+    else
+    {
+        *count = c.numJoints[kind];
+        if (outOrder && *count) { CK(cudaMemcpyAsync(outOrder, c.unitOrder[kind], 4 * (size_t)*count, cudaMemcpyDeviceToHost, c.stream)); CK(cudaStreamSynchronize(c.stream)); }
+    }
+    return 0;
+}
+
+/* multi-GPU halo entry points are implemented in k_halo.cu */
+
+} // extern "C"

@@ -1,0 +1,226 @@
+// k_narrow.cu -- narrow phase driver on the device (reference src/physics/collision_narrow.cpp:2328-2603):
+//   classify   : prune (no rigid body / same body), order each pair by collider type (strict <, :2374), bucket id
+//   bucket sort: stable counting sort into the 21 upper-triangular type buckets (:2399-2453) -> warps are type-uniform
+//   collide    : one thread per pair, three kernels by cost class (closed form / SAT+clip / GJK+EPA)
+//   compact    : exclusive scan of (contacts, collided) -> dense contact + manifold arrays in canonical order
+//                (bucket, colliderA, colliderB, slot); material combine and 16+16 bit packing as in :2221-2253
+#include "b200_context.h"
+#include "k_narrow_shapes.cuh"
+
+namespace b200 {
+
+static const int kThreads = 256;
+
+B200_D uint32_t bucketOf(uint32_t ta, uint32_t tb) { return ta * 6u - (ta * (ta - 1u)) / 2u + (tb - ta); }
+
+__global__ void __launch_bounds__(kThreads) npClassifyKernel(const uint2* __restrict__ pairs, const float4* __restrict__ wCol, uint8_t* __restrict__ pairKey, uint2* __restrict__ typed,
+                                                             const DeviceCounts* __restrict__ cnt)
+{
+    const uint32_t n = cnt->numPairs;
+    for (uint32_t p = blockIdx.x * kThreads + threadIdx.x; p < n; p += gridDim.x * kThreads)
+    {
+        uint2 pr = pairs[p];
+        const float4 ma = wCol[4 * pr.x + 3], mb = wCol[4 * pr.y + 3];
+        const uint32_t twa = __float_as_uint(ma.x), twb = __float_as_uint(mb.x);
+        uint32_t ta = twa & 0xFFu, tb = twb & 0xFFu; const uint32_t oa = twa >> 8, ob = twb >> 8;
+        const uint32_t ba = __float_as_uint(ma.y), bb = __float_as_uint(mb.y);
+        uint32_t key;
+        if (oa != B200PHYS_OBJ_RIGID_BODY && ob != B200PHYS_OBJ_RIGID_BODY) key = kBucketDropped;                       // :2358-2362
+        else if (oa == B200PHYS_OBJ_RIGID_BODY && ob == B200PHYS_OBJ_RIGID_BODY && ba == bb) key = kBucketDropped;      // :2364-2369
+        else
+        {
+            if (!(ta < tb)) { uint32_t t = pr.x; pr.x = pr.y; pr.y = t; t = ta; ta = tb; tb = t; }                     // equal types swap too (:2374)
+            const bool collision = (oa == B200PHYS_OBJ_RIGID_BODY && ob == B200PHYS_OBJ_RIGID_BODY) || oa == B200PHYS_OBJ_STATIC || ob == B200PHYS_OBJ_STATIC; // :2378-2379
+            key = collision ? bucketOf(ta, tb) : kBucketOverlap;
+        }
+        pairKey[p] = (uint8_t)key;
+        typed[p] = pr;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) npPermuteKernel(const uint2* __restrict__ typed, const uint32_t* __restrict__ dst, uint2* __restrict__ sorted, const DeviceCounts* __restrict__ cnt)
+{
+    const uint32_t n = cnt->numPairs;
+    for (uint32_t p = blockIdx.x * kThreads + threadIdx.x; p < n; p += gridDim.x * kThreads) sorted[dst[p]] = typed[p];
+}
+
+// ------------------------------------------------------------------------------------------------- shape loading
+struct ColRec { float4 r0, r1, r2, r3; };
+B200_D ColRec loadCol(const float4* __restrict__ wCol, uint32_t i) { ColRec c; c.r0 = wCol[4 * i]; c.r1 = wCol[4 * i + 1]; c.r2 = wCol[4 * i + 2]; c.r3 = wCol[4 * i + 3]; return c; }
+B200_D SphereS asSphere(const ColRec& c) { SphereS s; s.c = mk3(c.r0.x, c.r0.y, c.r0.z); s.r = c.r0.w; return s; }
+B200_D CapS asCap(const ColRec& c) { CapS s; s.a = mk3(c.r0.x, c.r0.y, c.r0.z); s.b = mk3(c.r0.w, c.r1.x, c.r1.y); s.r = c.r1.z; return s; }
+B200_D BoxS asBox(const ColRec& c) { BoxS s; s.mn = mk3(c.r0.x, c.r0.y, c.r0.z); s.mx = mk3(c.r0.w, c.r1.x, c.r1.y); return s; }
+B200_D ObbS asObb(const ColRec& c) { ObbS s; s.q = mkq(c.r0.x, c.r0.y, c.r0.z, c.r0.w); s.c = mk3(c.r1.x, c.r1.y, c.r1.z); s.r = mk3(c.r1.w, c.r2.x, c.r2.y); return s; }
+B200_D HullS asHull(const ColRec& c, const float4* hullVerts, const uint32_t* hullOffsets)
+{
+    HullS h; h.q = mkq(c.r0.x, c.r0.y, c.r0.z, c.r0.w); h.p = mk3(c.r1.x, c.r1.y, c.r1.z);
+    const uint32_t g = __float_as_uint(c.r3.z);
+    const uint32_t o0 = hullOffsets[g], o1 = hullOffsets[g + 1];
+    h.verts = hullVerts + o0; h.n = o1 - o0;
+    return h;
+}
+B200_D SupportD supportFor(uint32_t type, const ColRec& c, const float4* hullVerts, const uint32_t* hullOffsets)
+{
+    switch (type)
+    {
+    case B200PHYS_SPHERE: return supSphere(asSphere(c));
+    case B200PHYS_CAPSULE: return supCapsule(asCap(c));
+    case B200PHYS_CYLINDER: return supCylinder(asCap(c));
+    case B200PHYS_AABB: return supBox(asBox(c));
+    case B200PHYS_OBB: return supObb(asObb(c));
+    default: return supHull(asHull(c, hullVerts, hullOffsets));
+    }
+}
+
+B200_D void storeManifold(float4* __restrict__ manTmp, unsigned long long* __restrict__ manScan, uint32_t q, uint32_t maxPairs, bool hit, const Man& m)
+{
+    const uint32_t cnt = hit ? m.cnt : 0u;
+    manScan[q] = ((unsigned long long)cnt << 32) | (cnt ? 1ull : 0ull);
+    if (cnt)
+    {
+        manTmp[q] = make_float4(m.n.x, m.n.y, m.n.z, 0.f);
+        for (uint32_t k = 0; k < cnt; ++k) manTmp[(size_t)(k + 1) * maxPairs + q] = make_float4(m.p[k].x, m.p[k].y, m.p[k].z, m.d[k]);
+    }
+}
+
+B200_D void flushCounters(const NarrowCounters& nc, DeviceCounts* cnt)
+{
+    if (nc.epaOverflow) atomicAdd(&cnt->epaOverflows, nc.epaOverflow);
+    if (nc.gjkCap) atomicAdd(&cnt->gjkIterationCaps, nc.gjkCap);
+    if (nc.asserts) atomicAdd(&cnt->assertCount, nc.asserts);
+}
+
+// cost class 0: closed-form pairs (buckets 0,1,2,3,4,6,7,15); class 1: SAT + clipping (16,18); class 2: GJK + EPA (the rest)
+template <int CLASS>
+__global__ void __launch_bounds__(CLASS == 0 ? 256 : 128) npCollideKernel(const uint2* __restrict__ sorted, const float4* __restrict__ wCol, const float4* __restrict__ hullVerts,
+    const uint32_t* __restrict__ hullOffsets, float4* __restrict__ manTmp, unsigned long long* __restrict__ manScan, uint32_t maxPairs, DeviceCounts* cnt)
+{
+    constexpr uint32_t list0[8] = { 0, 1, 2, 3, 4, 6, 7, 15 };
+    constexpr uint32_t list1[2] = { 16, 18 };
+    constexpr uint32_t list2[11] = { 5, 8, 9, 10, 11, 12, 13, 14, 17, 19, 20 };
+    constexpr int nList = CLASS == 0 ? 8 : (CLASS == 1 ? 2 : 11);
+    NarrowCounters nc; nc.epaOverflow = nc.gjkCap = nc.asserts = 0;
+    for (int li = 0; li < nList; ++li)
+    {
+        const uint32_t bucket = CLASS == 0 ? list0[li] : (CLASS == 1 ? list1[li] : list2[li]);
+        const uint32_t q0 = cnt->keyStart[bucket], q1 = cnt->keyStart[bucket + 1];
+        for (uint32_t q = q0 + blockIdx.x * blockDim.x + threadIdx.x; q < q1; q += gridDim.x * blockDim.x)
+        {
+            const uint2 pr = sorted[q];
+            const ColRec A = loadCol(wCol, pr.x), B = loadCol(wCol, pr.y);
+            Man m; m.cnt = 0;
+            bool hit = false;
+            if (CLASS == 0)
+            {
+                switch (bucket)
+                {
+                case 0: hit = sphereSphere(asSphere(A), asSphere(B), m, nc); break;
+                case 1: hit = sphereCapsule(asSphere(A), asCap(B), m, nc); break;
+                case 2: hit = sphereCylinder(asSphere(A), asCap(B), m, nc); break;
+                case 3: hit = sphereBox(asSphere(A), asBox(B), m); break;
+                case 4: hit = sphereObb(asSphere(A), asObb(B), m); break;
+                case 6: hit = capsuleVsSegmentShape(asCap(A), asCap(B), false, m, nc); break;
+                case 7: hit = capsuleVsSegmentShape(asCap(A), asCap(B), true, m, nc); break;
+                default: hit = boxBox(asBox(A), asBox(B), m); break;
+                }
+            }
+            else if (CLASS == 1)
+            {
+                if (bucket == 16) { const BoxS bx = asBox(A); ObbS o; o.q = qIdentity(); o.c = boxCenter(bx); o.r = boxRadius(bx); hit = obbObb(o, asObb(B), m); } // :1142-1148
+                else hit = obbObb(asObb(A), asObb(B), m);
+            }
+            else
+            {
+                switch (bucket)
+                {
+                case 8:  hit = segmentShapeBox(asCap(A), false, asBox(B), m, nc); break;
+                case 9:  hit = segmentShapeObb(asCap(A), false, asObb(B), m, nc); break;
+                case 11: hit = cylinderCylinder(asCap(A), asCap(B), m, nc); break;
+                case 12: hit = segmentShapeBox(asCap(A), true, asBox(B), m, nc); break;
+                case 13: hit = segmentShapeObb(asCap(A), true, asObb(B), m, nc); break;
+                default:
+                {   // anything vs hull: 5 sphere, 10 capsule, 14 cylinder, 17 aabb, 19 obb, 20 hull (:496-520,792-818,1045-1071,1150-1176,1529-1584)
+                    const uint32_t ta = __float_as_uint(A.r3.x) & 0xFFu;
+                    hit = gjkEpa(supportFor(ta, A, hullVerts, hullOffsets), supHull(asHull(B, hullVerts, hullOffsets)), m, nc);
+                } break;
+                }
+            }
+            storeManifold(manTmp, manScan, q, maxPairs, hit, m);
+        }
+    }
+    flushCounters(nc, cnt);
+}
+
+// pruned / overlap-only slots produce no manifold
+__global__ void __launch_bounds__(kThreads) npClearTailKernel(unsigned long long* __restrict__ manScan, const DeviceCounts* __restrict__ cnt)
+{
+    const uint32_t q0 = cnt->keyStart[kBucketDropped], q1 = cnt->numPairs;
+    for (uint32_t q = q0 + blockIdx.x * kThreads + threadIdx.x; q < q1; q += gridDim.x * kThreads) manScan[q] = 0ull;
+}
+
+__global__ void npTotalsKernel(const unsigned long long* __restrict__ scanOut, uint32_t maxManifolds, uint32_t maxContacts, DeviceCounts* cnt)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0)
+    {
+        const unsigned long long t = scanOut[cnt->numPairs];
+        const uint32_t nm = (uint32_t)(t & 0xFFFFFFFFull), nk = (uint32_t)(t >> 32);
+        cnt->numManifoldsWanted = nm;
+        cnt->numManifolds = min(nm, maxManifolds);
+        cnt->numContacts = min(nk, maxContacts);
+        if (nm > maxManifolds || nk > maxContacts) cnt->overflowManifolds = 1;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) npCompactKernel(const uint2* __restrict__ sorted, const float4* __restrict__ wCol, const float4* __restrict__ manTmp,
+    const unsigned long long* __restrict__ manScan, const unsigned long long* __restrict__ scanOut, uint32_t maxPairs, uint32_t maxManifolds, uint32_t maxContacts,
+    uint2* __restrict__ collisions, uint4* __restrict__ manifolds, float4* __restrict__ contacts, uint2* __restrict__ contactBodies, const DeviceCounts* __restrict__ cnt)
+{
+    const uint32_t n = cnt->keyStart[kBucketDropped];   // collision buckets come first
+    for (uint32_t q = blockIdx.x * kThreads + threadIdx.x; q < n; q += gridDim.x * kThreads)
+    {
+        const unsigned long long self = manScan[q];
+        const uint32_t count = (uint32_t)(self >> 32);
+        if (!count) continue;
+        const unsigned long long ex = scanOut[q];
+        const uint32_t mi = (uint32_t)(ex & 0xFFFFFFFFull), cs = (uint32_t)(ex >> 32);
+        if (mi >= maxManifolds || cs + count > maxContacts) continue;
+        const uint2 pr = sorted[q];
+        const float4 a2 = wCol[4 * pr.x + 2], a3 = wCol[4 * pr.x + 3], b2 = wCol[4 * pr.y + 2], b3 = wCol[4 * pr.y + 3];
+        // writeScalarContact (collision_narrow.cpp:2228-2237): truncating 16+16 bit packing
+        const float friction = clamp01(sqrtf(a2.w * b2.w));
+        const float restitution = clamp01(fmax2(a2.z, b2.z));
+        const uint32_t fr = ((uint32_t)(friction * 0xFFFF) << 16) | (uint32_t)(restitution * 0xFFFF);
+        const uint32_t rbA = __float_as_uint(a3.y), rbB = __float_as_uint(b3.y);
+        collisions[mi] = pr;
+        manifolds[mi] = make_uint4(rbA, rbB, cs, count);
+        const float4 nrm = manTmp[q];
+        for (uint32_t k = 0; k < count; ++k)
+        {
+            contacts[2 * (cs + k)] = manTmp[(size_t)(k + 1) * maxPairs + q];
+            contacts[2 * (cs + k) + 1] = make_float4(nrm.x, nrm.y, nrm.z, __uint_as_float(fr));
+            contactBodies[cs + k] = make_uint2(rbA, rbB);
+        }
+    }
+}
+
+void launchNarrowphase(Context* c)
+{
+    DeviceCounts* cnt = c->counts;
+    const int G = gridFor(c, 8);
+    npClassifyKernel<<<G, kThreads, 0, c->stream>>>(c->pairs, c->wCol, c->pairKey, c->pairsTyped, cnt);
+    c->launches += 1;
+    stableSmallKeySort(c, c->pairKey, &cnt->numPairs, c->maxPairs, kNumPairKeys, c->pairDst, cnt->keyStart);
+    npPermuteKernel<<<G, kThreads, 0, c->stream>>>(c->pairsTyped, c->pairDst, c->pairsSorted, cnt);
+    npCollideKernel<0><<<G, 256, 0, c->stream>>>(c->pairsSorted, c->wCol, c->hullVerts, c->hullOffsets, c->manTmp, c->manScan, c->maxPairs, cnt);
+    npCollideKernel<1><<<gridFor(c, 4), 128, 0, c->stream>>>(c->pairsSorted, c->wCol, c->hullVerts, c->hullOffsets, c->manTmp, c->manScan, c->maxPairs, cnt);
+    npCollideKernel<2><<<gridFor(c, 4), 128, 0, c->stream>>>(c->pairsSorted, c->wCol, c->hullVerts, c->hullOffsets, c->manTmp, c->manScan, c->maxPairs, cnt);
+    npClearTailKernel<<<G, kThreads, 0, c->stream>>>(c->manScan, cnt);
+    c->launches += 5;
+    scanExclusiveU64(c, c->manScan, c->manScanOut, &cnt->numPairs, c->maxPairs, nullptr);
+    npTotalsKernel<<<1, 32, 0, c->stream>>>(c->manScanOut, c->maxManifolds, c->maxContacts, cnt);
+    npCompactKernel<<<G, kThreads, 0, c->stream>>>(c->pairsSorted, c->wCol, c->manTmp, c->manScan, c->manScanOut, c->maxPairs, c->maxManifolds, c->maxContacts,
+                                                   c->collisions, c->manifolds, c->contacts, c->contactBodies, cnt);
+    c->launches += 2;
+}
+
+} // namespace b200

@@ -1,0 +1,842 @@
+// k_narrow_shapes.cuh -- per-pair contact generation on the device: the 21 shape-pair routines of the reference's
+// scalar narrow phase (src/physics/collision_narrow.cpp:374-1584) with their helpers (:56-369), the GJK boolean test
+// (collision_gjk.h:184-238, collision_gjk.cpp:6-212) and EPA (collision_epa.h:96-168, collision_epa.cpp:5-239).
+// One thread owns one pair; simplex / polytope state lives in registers and thread-local memory. Arithmetic order follows
+// the reference so that contacts agree with the CPU oracle to the last bits (the library is built with -fmad=false).
+#pragma once
+#include "b200_util.cuh"
+#include "../../include/b200phys.h"
+
+namespace b200 {
+
+struct Man { f3 p[4]; float d[4]; f3 n; uint32_t cnt; };
+
+struct SphereS { f3 c; float r; };
+struct CapS { f3 a, b; float r; };          // capsule and cylinder
+struct BoxS { f3 mn, mx; };
+struct ObbS { q4 q; f3 c, r; };
+struct HullS { q4 q; f3 p; const float4* verts; uint32_t n; };
+
+struct NarrowCounters { uint32_t epaOverflow, gjkCap, asserts; };
+
+// ------------------------------------------------------------------------------------------------------- helpers
+B200_D f3 closestPointSegment(f3 q, f3 a, f3 b)
+{   // bounding_volumes.h:365-371
+    f3 ab = b - a;
+    float t = dot(q - a, ab) / sqLen(ab);
+    t = clampf(t, 0.f, 1.f);
+    return a + t * ab;
+}
+B200_D f3 closestPointBox(f3 q, const BoxS& b)
+{   // bounding_volumes.h:373-384
+    f3 r;
+    float v = q.x; if (v < b.mn.x) v = b.mn.x; if (v > b.mx.x) v = b.mx.x; r.x = v;
+    v = q.y; if (v < b.mn.y) v = b.mn.y; if (v > b.mx.y) v = b.mx.y; r.y = v;
+    v = q.z; if (v < b.mn.z) v = b.mn.z; if (v > b.mx.z) v = b.mx.z; r.z = v;
+    return r;
+}
+B200_D float closestSegmentSegment(f3 p1, f3 q1, f3 p2, f3 q2, f3& c1, f3& c2)
+{   // bounding_volumes.cpp:1251-1318
+    float s, t;
+    f3 d1 = q1 - p1, d2 = q2 - p2, r = p1 - p2;
+    float a = dot(d1, d1), e = dot(d2, d2), f = dot(d2, r);
+    if (a <= B200_EPS && e <= B200_EPS) { c1 = p1; c2 = p2; return dot(c1 - c2, c1 - c2); }
+    if (a <= B200_EPS) { s = 0.f; t = f / e; t = clampf(t, 0.f, 1.f); }
+    else
+    {
+        float c = dot(d1, r);
+        if (e <= B200_EPS) { t = 0.f; s = clampf(-c / a, 0.f, 1.f); }
+        else
+        {
+            float b = dot(d1, d2);
+            float denom = a * e - b * b;
+            if (denom != 0.f) s = clampf((b * f - c * e) / denom, 0.f, 1.f); else s = 0.f;
+            t = (b * s + f) / e;
+            if (t < 0.f) { t = 0.f; s = clampf(-c / a, 0.f, 1.f); }
+            else if (t > 1.f) { t = 1.f; s = clampf((b - c) / a, 0.f, 1.f); }
+        }
+    }
+    c1 = p1 + d1 * s; c2 = p2 + d2 * t;
+    return sqLen(c1 - c2);
+}
+struct PlaneS { f3 n; float d; };
+B200_D PlaneS createPlane(f3 point, f3 normal) { PlaneS p; p.n = normal; p.d = -dot(normal, point); return p; }
+// dot(vec4(p,1), plane) with the reference's horizontal-add order (x+y)+(z+w)
+B200_D float signedDistance(f3 p, const PlaneS& pl) { return (p.x * pl.n.x + p.y * pl.n.y) + (p.z * pl.n.z + 1.f * pl.d); }
+B200_D f3 boxCenter(const BoxS& b) { return (b.mn + b.mx) * 0.5f; }
+B200_D f3 boxRadius(const BoxS& b) { return (b.mx - b.mn) * 0.5f; }
+
+// ------------------------------------------------------------------------------------------------ analytic pairs
+// collision_narrow.cpp:374-400
+B200_D bool sphereSphere(const SphereS& s1, const SphereS& s2, Man& m, NarrowCounters& nc)
+{
+    f3 n = s2.c - s1.c;
+    float rs = s2.r + s1.r;
+    float sq = sqLen(n);
+    if (sq <= rs * rs)
+    {
+        float dist;
+        if (sq == 0.f) { dist = 0.f; m.n = mk3(0.f, 1.f, 0.f); }
+        else { dist = sqrtf(sq); m.n = n / dist; }
+        m.cnt = 1;
+        m.d[0] = rs - dist;
+        if (!(m.d[0] >= 0.f)) ++nc.asserts;
+        m.p[0] = 0.5f * (s1.c + s1.r * m.n + s2.c - s2.r * m.n);
+        return true;
+    }
+    return false;
+}
+// collision_narrow.cpp:402-406
+B200_D bool sphereCapsule(const SphereS& s, const CapS& c, Man& m, NarrowCounters& nc)
+{
+    SphereS o; o.c = closestPointSegment(s.c, c.a, c.b); o.r = c.r;
+    return sphereSphere(s, o, m, nc);
+}
+// collision_narrow.cpp:408-449
+B200_D bool sphereCylinder(const SphereS& s, const CapS& c, Man& m, NarrowCounters& nc)
+{
+    f3 ab = c.b - c.a;
+    float t = dot(s.c - c.a, ab) / sqLen(ab);
+    if (t >= 0.f && t <= 1.f) { SphereS o; o.c = lerp(c.a, c.b, t); o.r = c.r; return sphereSphere(s, o, m, nc); }
+    f3 p = (t <= 0.f) ? c.a : c.b;
+    f3 up = (t <= 0.f) ? -ab : ab;
+    f3 proj = normalize(cross(cross(up, s.c - p), up));
+    f3 endA = p + proj * c.r, endB = p - proj * c.r;
+    f3 closest = closestPointSegment(s.c, endA, endB);
+    f3 normal = closest - s.c;
+    float sq = sqLen(normal);
+    if (sq <= s.r * s.r)
+    {
+        float dist;
+        if (sq == 0.f) { dist = 0.f; m.n = -normalize(up); }
+        else { dist = sqrtf(sq); m.n = normal / dist; }
+        m.cnt = 1;
+        m.d[0] = s.r - dist;
+        if (!(m.d[0] >= 0.f)) ++nc.asserts;
+        m.p[0] = closest + 0.5f * m.d[0] * normal;
+        return true;
+    }
+    return false;
+}
+// collision_narrow.cpp:451-478
+B200_D bool sphereBox(const SphereS& s, const BoxS& a, Man& m)
+{
+    f3 p = closestPointBox(s.c, a);
+    f3 n = p - s.c;
+    float sq = sqLen(n);
+    if (sq <= s.r * s.r)
+    {
+        float dist = 0.f;
+        if (sq > 0.f) { dist = sqrtf(sq); n /= dist; } else { n = mk3(0.f, 1.f, 0.f); }
+        m.cnt = 1; m.n = n;
+        m.d[0] = s.r - dist;
+        m.p[0] = 0.5f * (p + s.c + n * s.r);
+        return true;
+    }
+    return false;
+}
+// collision_narrow.cpp:480-494
+B200_D bool sphereObb(const SphereS& s, const ObbS& o, Man& m)
+{
+    BoxS bb; bb.mn = o.c - o.r; bb.mx = o.c + o.r;
+    SphereS s_; s_.c = conjugate(o.q) * (s.c - o.c) + o.c; s_.r = s.r;
+    if (sphereBox(s_, bb, m))
+    {
+        m.n = o.q * m.n;
+        m.p[0] = o.q * (m.p[0] - o.c) + o.c;
+        return true;
+    }
+    return false;
+}
+// capsule-capsule (:523-612) and capsule-cylinder (:614-703)
+B200_D bool capsuleVsSegmentShape(const CapS& a, const CapS& b, bool bIsCylinder, Man& m, NarrowCounters& nc)
+{
+    f3 aDir = a.b - a.a;
+    f3 bDir = normalize(b.b - b.a);
+    float aLen = len(aDir);
+    aDir *= 1.f / aLen;
+    float parallel = dot(aDir, bDir);
+    if (fabsf(parallel) > 0.99f)
+    {
+        f3 pAa = a.a, pAb = a.b, pBa = b.a, pBb = b.b;
+        if (parallel < 0.f) { f3 t = pBa; pBa = pBb; pBb = t; }
+        f3 ref = a.a;
+        float a0 = 0.f, a1 = aLen;
+        float b0 = dot(aDir, pBa - ref), b1 = dot(aDir, pBb - ref);
+        if (!(b1 > b0)) ++nc.asserts;
+        float left = fmax2(a0, b0), right = fmin2(a1, b1);
+        if (right < left)
+        {
+            SphereS sa; sa.r = a.r; sa.c = (a0 > b1) ? pAa : pAb;
+            if (bIsCylinder) return sphereCylinder(sa, b, m, nc);
+            SphereS sb; sb.r = b.r; sb.c = (a0 > b1) ? pBb : pBa;
+            return sphereSphere(sa, sb, m, nc);
+        }
+        f3 cA0 = ref + left * aDir, cA1 = ref + right * aDir;
+        f3 cB0 = closestPointSegment(cA0, pBa, pBb);
+        f3 cB1 = cB0 + (right - left) * aDir;
+        f3 normal = cB0 - cA0;
+        float d = len(normal);
+        if (d < B200_EPS) { d = 0.f; normal = mk3(0.f, 1.f, 0.f); } else { normal /= d; }
+        float rs = a.r + b.r;
+        float pen = rs - d;
+        if (pen < 0.f) return false;
+        m.n = normal; m.cnt = 2;
+        m.d[0] = pen; m.p[0] = (cA0 + cB0) * 0.5f;
+        m.d[1] = pen; m.p[1] = (cA1 + cB1) * 0.5f;
+        return true;
+    }
+    f3 c1, c2;
+    closestSegmentSegment(a.a, a.b, b.a, b.b, c1, c2);
+    SphereS sa; sa.c = c1; sa.r = a.r;
+    if (bIsCylinder) return sphereCylinder(sa, b, m, nc);
+    SphereS sb; sb.c = c2; sb.r = b.r;
+    return sphereSphere(sa, sb, m, nc);
+}
+// collision_narrow.cpp:1074-1140 (depth keeps the sign of the separation direction)
+B200_D bool boxBox(const BoxS& a, const BoxS& b, Man& m)
+{
+    f3 cA = boxCenter(a), cB = boxCenter(b), rA = boxRadius(a), rB = boxRadius(b);
+    f3 d = cB - cA;
+    f3 p = (rB + rA) - vabs(d);
+    if (p.x < 0.f || p.y < 0.f || p.z < 0.f) return false;
+    int me = (p.x < p.y) ? ((p.x < p.z) ? 0 : 2) : ((p.y < p.z) ? 1 : 2);
+    float s = comp(d, me) < 0.f ? -1.f : 1.f;
+    float pen = comp(p, me) * s;
+    f3 normal = mk3(0.f); setComp(normal, me, s);
+    m.n = normal; m.cnt = 4;
+    int a0 = (me + 1) % 3, a1 = (me + 2) % 3;
+    float min0 = fmax2(comp(a.mn, a0), comp(b.mn, a0)), min1 = fmax2(comp(a.mn, a1), comp(b.mn, a1));
+    float max0 = fmin2(comp(a.mx, a0), comp(b.mx, a0)), max1 = fmin2(comp(a.mx, a1), comp(b.mx, a1));
+    float depth = comp(cA, me) + comp(rA, me) - pen * 0.5f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+    {
+        m.d[i] = pen; m.p[i] = mk3(0.f);
+        setComp(m.p[i], a0, (i < 2) ? min0 : max0); setComp(m.p[i], a1, (i & 1) ? max1 : min1); setComp(m.p[i], me, depth);
+    }
+    return true;
+}
+
+// --------------------------------------------------------------------------------- manifold reduction and clipping
+struct VPd { f3 v; float depth; };
+struct PolyD { VPd p[16]; uint32_t n; };
+
+// collision_narrow.cpp:56-146
+B200_D void stableManifold(const VPd* v, uint32_t n, f3 normal, Man& out)
+{
+    if (n > 4)
+    {
+        f3 search = getTangent(normal);
+        float best = dot(search, v[0].v); uint32_t ri = 0;
+        for (uint32_t i = 1; i < n; ++i) { float d = dot(search, v[i].v); if (d > best) { ri = i; best = d; } }
+        out.d[0] = v[ri].depth; out.p[0] = v[ri].v;
+        best = 0.f; ri = 0;
+        for (uint32_t i = 0; i < n; ++i) { float d = sqLen(v[i].v - out.p[0]); if (d > best) { ri = i; best = d; } }
+        out.d[1] = v[ri].depth; out.p[1] = v[ri].v;
+        best = 0.f; ri = 0;
+        for (uint32_t i = 0; i < n; ++i)
+        {
+            f3 qa = out.p[0] - v[i].v, qb = out.p[1] - v[i].v;
+            float area = 0.5f * dot(cross(qa, qb), normal);
+            if (area > best) { ri = i; best = area; }
+        }
+        out.d[2] = v[ri].depth; out.p[2] = v[ri].v;
+        best = 0.f; ri = 0;
+        for (uint32_t i = 0; i < n; ++i)
+        {
+            f3 qa = out.p[0] - v[i].v, qb = out.p[1] - v[i].v, qc = out.p[2] - v[i].v;
+            float a1 = 0.5f * dot(cross(qa, qb), normal);
+            float a2 = 0.5f * dot(cross(qb, qc), normal);
+            float a3 = 0.5f * dot(cross(qc, qa), normal);
+            float area = fmax2(fmax2(a1, a2), a3);
+            if (area > best) { ri = i; best = area; }
+        }
+        out.d[3] = v[ri].depth; out.p[3] = v[ri].v;
+        out.cnt = 4;
+    }
+    else
+    {
+        out.cnt = n;
+        for (uint32_t i = 0; i < n; ++i) { out.d[i] = v[i].depth; out.p[i] = v[i].v; }
+    }
+}
+// collision_narrow.cpp:154-163
+B200_D VPd clipEdge(VPd a, VPd b, float aDist, float bDist)
+{
+    aDist = fabsf(aDist); bDist = fabsf(bDist);
+    float total = aDist + bDist;
+    float t = aDist / total;
+    VPd r; r.v = lerp(a.v, b.v, t); r.depth = lerpf(a.depth, b.depth, t);
+    return r;
+}
+// collision_narrow.cpp:166-222
+B200_D void clipPolygon(PolyD& input, const PlaneS* planes, uint32_t nPlanes, PolyD& output)
+{
+    PolyD* in = &input; PolyD* out = &output;
+    uint32_t ci = 0;
+    for (; ci < nPlanes; ++ci)
+    {
+        PlaneS pl = planes[ci];
+        out->n = 0;
+        if (in->n == 0) break;
+        VPd start = in->p[in->n - 1];
+        for (uint32_t i = 0; i < in->n; ++i)
+        {
+            VPd end = in->p[i];
+            float sd = signedDistance(start.v, pl), ed = signedDistance(end.v, pl);
+            bool sIn = sd > 0.f, eIn = ed > 0.f;
+            if (sIn && eIn) out->p[out->n++] = end;
+            else if (sIn) out->p[out->n++] = clipEdge(start, end, sd, ed);
+            else if (!sIn && eIn) { out->p[out->n++] = clipEdge(start, end, sd, ed); out->p[out->n++] = end; }
+            start = end;
+        }
+        PolyD* tmp = in; in = out; out = tmp;
+    }
+    if (ci % 2 == 0) { for (uint32_t i = 0; i < input.n; ++i) output.p[i] = input.p[i]; output.n = input.n; }
+}
+B200_D int maxAbsAxis(f3 n) { f3 p = vabs(n); return (p.x > p.y) ? ((p.x > p.z) ? 0 : 2) : ((p.y > p.z) ? 1 : 2); }
+// collision_narrow.cpp:225-254
+B200_D void boxClipPlanes(f3 radius, f3 normal, f3* pts, f3* nrm)
+{
+    int me = maxAbsAxis(normal), a0 = (me + 1) % 3, a1 = (me + 2) % 3;
+    f3 n;
+    n = mk3(0.f); setComp(n, a0, 1.f);  nrm[0] = n; pts[0] = -radius;
+    n = mk3(0.f); setComp(n, a1, 1.f);  nrm[1] = n; pts[1] = -radius;
+    n = mk3(0.f); setComp(n, a0, -1.f); nrm[2] = n; pts[2] = radius;
+    n = mk3(0.f); setComp(n, a1, -1.f); nrm[3] = n; pts[3] = radius;
+}
+// collision_narrow.cpp:257-289
+B200_D void boxIncidentVerts(f3 radius, f3 normal, PolyD& poly)
+{
+    int me = maxAbsAxis(normal), a0 = (me + 1) % 3, a1 = (me + 2) % 3;
+    float s = comp(normal, me) < 0.f ? 1.f : -1.f;
+    float d = comp(radius, me) * s;
+    float min0 = -comp(radius, a0), min1 = -comp(radius, a1), max0 = comp(radius, a0), max1 = comp(radius, a1);
+    poly.n = 4;
+    for (int i = 0; i < 4; ++i)
+    {
+        setComp(poly.p[i].v, me, d);
+        setComp(poly.p[i].v, a0, (i == 0 || i == 3) ? min0 : max0);
+        setComp(poly.p[i].v, a1, (i < 2) ? min1 : max1);
+    }
+}
+// collision_narrow.cpp:291-299
+B200_D PlaneS boxReferencePlane(const BoxS& b, f3 normal)
+{
+    f3 pt = mk3((normal.x < 0.f) ? b.mn.x : b.mx.x, (normal.y < 0.f) ? b.mn.y : b.mx.y, (normal.z < 0.f) ? b.mn.z : b.mx.z);
+    return createPlane(pt, normal);
+}
+// collision_narrow.cpp:301-336
+B200_D void boxIncidentEdge(f3 r, f3 normal, f3& oa, f3& ob)
+{
+    f3 p = vabs(normal);
+    oa = r;
+    if (p.x > p.y) { if (p.y > p.z) ob = mk3(r.x, r.y, -r.z); else ob = mk3(r.x, -r.y, r.z); }
+    else { if (p.x > p.z) ob = mk3(r.x, r.y, -r.z); else ob = mk3(-r.x, r.y, r.z); }
+    f3 s = mk3(normal.x < 0.f ? -1.f : 1.f, normal.y < 0.f ? -1.f : 1.f, normal.z < 0.f ? -1.f : 1.f);
+    oa = oa * s; ob = ob * s;
+}
+// collision_narrow.cpp:339-369
+B200_D bool clipAndBuild(PolyD& poly, const PlaneS* planes, uint32_t nPlanes, const PlaneS& ref, Man& out)
+{
+    PolyD cl; cl.n = 0;
+    clipPolygon(poly, planes, nPlanes, cl);
+    if (cl.n > 0)
+    {
+        for (uint32_t i = 0; i < cl.n; ++i)
+        {
+            if (cl.p[i].depth < 0.f) { cl.p[i] = cl.p[cl.n - 1]; --cl.n; --i; }
+            else { cl.p[i].v += ref.n * cl.p[i].depth; }
+        }
+        if (cl.n > 0) { stableManifold(cl.p, cl.n, out.n, out); return true; }
+    }
+    return false;
+}
+
+// ----------------------------------------------------------------------------------------------- support mappings
+struct SupportD
+{
+    int type;
+    f3 a, b; float r;     // sphere: a = centre; capsule/cylinder: a, b; aabb: a = min, b = max
+    q4 q; f3 c, rad;      // obb: q, c, rad; hull: q, c = position
+    const float4* verts; uint32_t nv;
+
+    B200_D f3 eval(f3 dir) const
+    {
+        switch (type)
+        {
+        case B200PHYS_SPHERE: return normalize(dir) * r + a;                    // collision_gjk.h:6-14
+        case B200PHYS_CAPSULE:                                                  // collision_gjk.h:16-27
+        {
+            float dA = dot(dir, a), dB = dot(dir, b);
+            f3 far = dA > dB ? a : b;
+            return normalize(dir) * r + far;
+        }
+        case B200PHYS_CYLINDER:                                                 // collision_gjk.h:29-44
+        {
+            float dA = dot(dir, a), dB = dot(dir, b);
+            f3 far = dA > dB ? a : b;
+            f3 n = a - b;
+            f3 proj = noz(cross(cross(n, dir), n));
+            return far + proj * r;
+        }
+        case B200PHYS_AABB:                                                     // collision_gjk.h:46-58
+            return mk3((dir.x < 0.f) ? a.x : b.x, (dir.y < 0.f) ? a.y : b.y, (dir.z < 0.f) ? a.z : b.z);
+        case B200PHYS_OBB:                                                      // collision_gjk.h:60-75
+        {
+            f3 d = conjugate(q) * dir;
+            f3 rr = mk3(d.x < 0.f ? -rad.x : rad.x, d.y < 0.f ? -rad.y : rad.y, d.z < 0.f ? -rad.z : rad.z);
+            return c + q * rr;
+        }
+        default:                                                                // hull, collision_gjk.h:77-100
+        {
+            f3 d = conjugate(q) * dir;
+            f3 best = mk3(0.f);
+            float maxDist = -FLT_MAX;
+            for (uint32_t i = 0; i < nv; ++i)
+            {
+                float4 v4 = verts[i];
+                f3 v = mk3(v4.x, v4.y, v4.z);
+                float t = dot(d, v);
+                if (t > maxDist) { maxDist = t; best = v; }
+            }
+            return c + q * best;
+        }
+        }
+    }
+};
+B200_D SupportD supSphere(const SphereS& s) { SupportD r; r.type = B200PHYS_SPHERE; r.a = s.c; r.r = s.r; return r; }
+B200_D SupportD supCapsule(const CapS& s) { SupportD r; r.type = B200PHYS_CAPSULE; r.a = s.a; r.b = s.b; r.r = s.r; return r; }
+B200_D SupportD supCylinder(const CapS& s) { SupportD r; r.type = B200PHYS_CYLINDER; r.a = s.a; r.b = s.b; r.r = s.r; return r; }
+B200_D SupportD supBox(const BoxS& s) { SupportD r; r.type = B200PHYS_AABB; r.a = s.mn; r.b = s.mx; return r; }
+B200_D SupportD supObb(const ObbS& s) { SupportD r; r.type = B200PHYS_OBB; r.q = s.q; r.c = s.c; r.rad = s.r; return r; }
+B200_D SupportD supHull(const HullS& s) { SupportD r; r.type = B200PHYS_HULL; r.q = s.q; r.c = s.p; r.verts = s.verts; r.nv = s.n; return r; }
+
+// ------------------------------------------------------------------------------------------------------------ GJK
+struct SupPt { f3 a, b, m; };
+struct SimplexD { SupPt a, b, c, d; uint32_t n; };
+B200_D SupPt minkowski(const SupportD& A, const SupportD& B, f3 dir) { SupPt p; p.a = A.eval(dir); p.b = B.eval(-dir); p.m = p.a - p.b; return p; }
+B200_D f3 crossABA(f3 a, f3 b) { return cross(cross(a, b), a); }
+
+#define B200_GJK_STOP 0
+#define B200_GJK_CONTINUE 1
+#define B200_GJK_ERROR 2
+#define B200_GJK_MAX_ROUNDS 64
+
+// collision_gjk.cpp:6-212 (the reference's goto web between the three face regions, written as a small state machine)
+B200_D int updateSimplex(SimplexD& s, const SupPt& a, f3& dir)
+{
+    if (s.n == 2)
+    {
+        f3 ao = -a.m, ab = s.b.m - a.m, ac = s.c.m - a.m;
+        f3 abc = cross(ab, ac);
+        f3 abp = cross(ab, abc);
+        if (dot(ao, abp) > 0.f) { s.c = a; dir = crossABA(ab, ao); return B200_GJK_CONTINUE; }
+        f3 acp = cross(abc, ac);
+        if (dot(ao, acp) > 0.f) { s.b = a; dir = crossABA(ac, ao); return B200_GJK_CONTINUE; }
+        if (dot(ao, abc) >= 0.f) { s.d = s.b; s.b = a; s.n = 3; dir = abc; return B200_GJK_CONTINUE; }
+        if (dot(ao, -abc) >= 0.f) { s.d = s.c; s.c = s.b; s.b = a; s.n = 3; dir = -abc; return B200_GJK_CONTINUE; }
+        return B200_GJK_ERROR;
+    }
+    if (s.n != 3) return B200_GJK_ERROR;
+
+    f3 ao = -a.m, ab = s.b.m - a.m, ac = s.c.m - a.m, ad = s.d.m - a.m;
+    f3 bcd = cross(s.c.m - s.b.m, s.d.m - s.b.m);
+    if (dot(bcd, dir) > 0.00001f || dot(bcd, s.b.m) < -0.00001f) return B200_GJK_ERROR;
+    f3 abc = cross(ac, ab), abd = cross(ab, ad), adc = cross(ad, ac);
+    int flags = 0;
+    flags |= (dot(abc, ao) > 0.f) ? 1 : 0;
+    flags |= (dot(abd, ao) > 0.f) ? 2 : 0;
+    flags |= (dot(adc, ao) > 0.f) ? 4 : 0;
+    if (flags == 7) return B200_GJK_ERROR;
+    if (flags == 0) return B200_GJK_STOP;
+
+    // states: 1 = overABC1, 2 = overABC2, 3 = overABD1, 4 = overABD2, 5 = overADC1, 6 = overADC2
+    int state;
+    if (flags == 1) state = 1;
+    else if (flags == 2) state = 3;
+    else if (flags == 4) state = 5;
+    else if (flags == 3) state = (dot(cross(abc, ab), ao) > 0.f) ? 3 : 2;
+    else if (flags == 6) state = (dot(cross(abd, ad), ao) > 0.f) ? 5 : 4;
+    else state = (dot(cross(adc, ac), ao) > 0.f) ? 1 : 6;   // flags == 5
+
+    for (;;)
+    {
+        switch (state)
+        {
+        case 1: if (dot(cross(abc, ab), ao) > 0.f) { s.c = a; s.n = 2; dir = crossABA(ab, ao); return B200_GJK_CONTINUE; } state = 2; break;
+        case 2: if (dot(cross(ac, abc), ao) > 0.f) { s.b = a; s.n = 2; dir = crossABA(ac, ao); return B200_GJK_CONTINUE; }
+                s.d = a; dir = abc; return B200_GJK_CONTINUE;
+        case 3: if (dot(cross(abd, ad), ao) > 0.f) { s.b = s.d; s.c = a; s.n = 2; dir = crossABA(ad, ao); return B200_GJK_CONTINUE; } state = 4; break;
+        case 4: if (dot(cross(ab, abd), ao) > 0.f) { s.c = a; s.n = 2; dir = crossABA(ab, ao); return B200_GJK_CONTINUE; }
+                s.c = a; dir = abd; return B200_GJK_CONTINUE;
+        case 5: if (dot(cross(adc, ac), ao) > 0.f) { s.b = a; s.n = 2; dir = crossABA(ac, ao); return B200_GJK_CONTINUE; } state = 6; break;
+        default: if (dot(cross(ad, adc), ao) > 0.f) { s.b = a; s.c = s.d; s.n = 2; dir = crossABA(ad, ao); return B200_GJK_CONTINUE; }
+                s.b = a; dir = adc; return B200_GJK_CONTINUE;
+        }
+    }
+}
+
+// collision_gjk.h:184-238 (+ a 64-round cap the reference lacks; hits are counted)
+B200_D bool gjk(const SupportD& A, const SupportD& B, SimplexD& s, NarrowCounters& nc)
+{
+    f3 dir = mk3(1.f, 0.1f, -0.2f);
+    s.c = minkowski(A, B, dir);
+    if (dot(s.c.m, dir) < 0.f) return false;
+    dir = -s.c.m;
+    s.b = minkowski(A, B, dir);
+    if (dot(s.b.m, dir) < 0.f) return false;
+    dir = crossABA(s.c.m - s.b.m, -s.b.m);
+    s.n = 2;
+    for (int round = 0; ; ++round)
+    {
+        if (round >= B200_GJK_MAX_ROUNDS) { ++nc.gjkCap; return false; }
+        if (sqLen(dir) < 0.0001f) return false;
+        SupPt a = minkowski(A, B, dir);
+        if (dot(a.m, dir) < 0.f) return false;
+        int r = updateSimplex(s, a, dir);
+        if (r == B200_GJK_STOP) { s.a = a; s.n = 4; break; }
+        if (r == B200_GJK_ERROR) return false;
+    }
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------------------ EPA
+// Append-only polytope like the reference (inactive triangles are never reclaimed, collision_epa.cpp:21-33) with
+// device-sized capacities: <= 20 iterations add <= 20 points; triangle / edge arrays that run full behave like the
+// reference's "out of memory" exit (best result so far) and are counted in stats.epaOverflows.
+#define B200_EPA_MAX_POINTS 24
+#define B200_EPA_MAX_TRIS 160
+#define B200_EPA_MAX_EDGES 240
+#define B200_EPA_MAX_BORDER 64
+
+struct EpaTri { uint16_t a, b, c, eA, eB, eC; float nx, ny, nz, dist; };
+struct EpaEdge { uint16_t a, b, t0, t1; };
+
+struct EpaPoly
+{
+    SupPt pts[B200_EPA_MAX_POINTS];
+    EpaTri tris[B200_EPA_MAX_TRIS];
+    EpaEdge edges[B200_EPA_MAX_EDGES];
+    uint32_t active[(B200_EPA_MAX_TRIS + 31) / 32];
+    uint8_t refs[B200_EPA_MAX_EDGES];
+    uint16_t newEdgePerPoint[B200_EPA_MAX_POINTS];
+    uint32_t nT, nP, nE;
+
+    B200_D bool isActive(uint32_t i) const { return (active[i >> 5] >> (i & 31)) & 1u; }
+    B200_D void setActive(uint32_t i, bool on) { if (on) active[i >> 5] |= (1u << (i & 31)); else active[i >> 5] &= ~(1u << (i & 31)); }
+    B200_D static void triInfo(const SupPt& a, const SupPt& b, const SupPt& c, f3& n, float& d)
+    {   // collision_epa.cpp:5-11
+        n = normalize(cross(b.m - a.m, c.m - a.m));
+        d = dot(n, a.m);
+    }
+    B200_D int pushPoint(const SupPt& p) { if (nP >= B200_EPA_MAX_POINTS) return -1; pts[nP] = p; return (int)nP++; }
+    B200_D int pushTri(uint16_t a, uint16_t b, uint16_t c, uint16_t eA, uint16_t eB, uint16_t eC, f3 n, float d)
+    {
+        if (nT >= B200_EPA_MAX_TRIS) return -1;
+        EpaTri& t = tris[nT]; t.a = a; t.b = b; t.c = c; t.eA = eA; t.eB = eB; t.eC = eC; t.nx = n.x; t.ny = n.y; t.nz = n.z; t.dist = d;
+        setActive(nT, true); return (int)nT++;
+    }
+    B200_D int pushEdge(uint16_t a, uint16_t b, uint16_t t0, uint16_t t1)
+    {
+        if (nE >= B200_EPA_MAX_EDGES) return -1;
+        EpaEdge& e = edges[nE]; e.a = a; e.b = b; e.t0 = t0; e.t1 = t1; return (int)nE++;
+    }
+    B200_D uint32_t closest() const
+    {   // collision_epa.cpp:94-112
+        uint32_t best = 0xFFFFFFFFu; float mind = FLT_MAX;
+        for (uint32_t i = 0; i < nT; ++i) if (isActive(i) && tris[i].dist < mind) { mind = tris[i].dist; best = i; }
+        return best;
+    }
+    // collision_epa.cpp:114-239
+    B200_D bool addPoint(const SupPt& np)
+    {
+        for (uint32_t i = 0; i < nE; ++i) refs[i] = 0;
+        for (uint32_t i = 0; i < nT; ++i)
+        {
+            if (!isActive(i)) continue;
+            const EpaTri& t = tris[i];
+            float d = dot(mk3(t.nx, t.ny, t.nz), np.m - pts[t.a].m);
+            if (d > 0.f) { ++refs[t.eA]; ++refs[t.eB]; ++refs[t.eC]; setActive(i, false); }
+        }
+        uint16_t border[B200_EPA_MAX_BORDER]; uint32_t nBorder = 0;
+        for (uint32_t i = 0; i < nE; ++i)
+            if (refs[i] == 1) { if (nBorder >= B200_EPA_MAX_BORDER) return false; border[nBorder++] = (uint16_t)i; }
+        int npi = pushPoint(np);
+        if (npi < 0) return false;
+        const uint16_t triOffset = (uint16_t)nT;
+        for (uint32_t i = 0; i < nBorder; ++i)
+        {
+            const uint16_t ei = border[i];
+            EpaEdge e = edges[ei];
+            const bool aAct = isActive(e.t0), bAct = isActive(e.t1);
+            const uint16_t connect = bAct ? e.a : e.b;
+            const uint16_t triIndex = (uint16_t)nT;
+            int ne = pushEdge(connect, (uint16_t)npi, 0xFFFF, (uint16_t)nT);
+            if (ne < 0) return false;
+            newEdgePerPoint[connect] = (uint16_t)ne;
+            const uint16_t bI = connect, cI = bAct ? e.b : e.a;
+            f3 n; float d; triInfo(np, pts[bI], pts[cI], n, d);
+            int ti = pushTri((uint16_t)npi, bI, cI, ei, 0xFFFF, (uint16_t)ne, n, d);
+            if (ti < 0) return false;
+            if (aAct) edges[ei].t1 = triIndex; else edges[ei].t0 = triIndex;
+        }
+        for (uint32_t i = 0; i < nBorder; ++i)
+        {
+            const EpaEdge e = edges[border[i]];
+            const bool bNew = e.t1 >= triOffset;
+            const uint16_t connect = bNew ? e.a : e.b;
+            const uint16_t other = newEdgePerPoint[connect];
+            const uint16_t triIndex = (uint16_t)(i + triOffset);
+            tris[triIndex].eB = other;
+            edges[other].t0 = triIndex;
+        }
+        return true;
+    }
+};
+
+// collision_epa.h:96-168 ; result used even when not converged (collision_narrow.cpp:508-512)
+B200_D void epa(const SimplexD& g, const SupportD& A, const SupportD& B, f3& outPoint, f3& outNormal, float& outDepth, NarrowCounters& nc)
+{
+    EpaPoly P;
+    P.nT = P.nP = P.nE = 0;
+    for (uint32_t i = 0; i < (B200_EPA_MAX_TRIS + 31) / 32; ++i) P.active[i] = 0;
+    P.pushPoint(g.a); P.pushPoint(g.b); P.pushPoint(g.c); P.pushPoint(g.d);
+    f3 n; float d;
+    EpaPoly::triInfo(g.a, g.b, g.d, n, d); P.pushTri(0, 1, 3, 4, 3, 0, n, d);
+    EpaPoly::triInfo(g.b, g.c, g.d, n, d); P.pushTri(1, 2, 3, 5, 4, 1, n, d);
+    EpaPoly::triInfo(g.c, g.a, g.d, n, d); P.pushTri(2, 0, 3, 3, 5, 2, n, d);
+    EpaPoly::triInfo(g.a, g.c, g.b, n, d); P.pushTri(0, 2, 1, 1, 0, 2, n, d);
+    P.pushEdge(0, 1, 0, 3); P.pushEdge(1, 2, 1, 3); P.pushEdge(2, 0, 2, 3);
+    P.pushEdge(0, 3, 2, 0); P.pushEdge(1, 3, 0, 1); P.pushEdge(2, 3, 1, 2);
+
+    uint32_t ci = 0;
+    for (uint32_t it = 0; it < 20; ++it)
+    {
+        ci = P.closest();
+        if (ci == 0xFFFFFFFFu) { ++nc.asserts; ci = 0; break; }
+        const EpaTri& t = P.tris[ci];
+        const f3 tn = mk3(t.nx, t.ny, t.nz);
+        SupPt a = minkowski(A, B, tn);
+        float dd = dot(a.m, tn);
+        if (dd - t.dist < 0.01f) break;
+        if (!P.addPoint(a)) { ++nc.epaOverflow; break; }
+    }
+    const EpaTri& t = P.tris[ci];
+    const f3 tn = mk3(t.nx, t.ny, t.nz);
+    const SupPt& a = P.pts[t.a]; const SupPt& b = P.pts[t.b]; const SupPt& c = P.pts[t.c];
+    f3 bc = barycentric(a.m, b.m, c.m, tn * t.dist);
+    f3 pA = bc.x * a.a + bc.y * b.a + bc.z * c.a;
+    f3 pB = bc.x * a.b + bc.y * b.b + bc.z * c.b;
+    outPoint = 0.5f * (pA + pB);
+    outNormal = tn;
+    outDepth = t.dist;
+}
+
+B200_D bool gjkEpa(const SupportD& A, const SupportD& B, Man& m, NarrowCounters& nc)
+{
+    SimplexD s;
+    if (!gjk(A, B, s, nc)) return false;
+    f3 p, n; float d;
+    epa(s, A, B, p, n, d, nc);
+    m.n = n; m.cnt = 1; m.d[0] = d; m.p[0] = p;
+    return true;
+}
+
+// ------------------------------------------------------------------------------------- GJK/EPA-based shape pairs
+// capsule-aabb (:705-769) / cylinder-aabb (:953-1022)
+B200_D bool segmentShapeBox(const CapS& c, bool isCylinder, const BoxS& a, Man& m, NarrowCounters& nc)
+{
+    SupportD A = isCylinder ? supCylinder(c) : supCapsule(c);
+    SupportD B = supBox(a);
+    if (!gjkEpa(A, B, m, nc)) return false;
+    f3 normal = m.n;
+    if (fabsf(normal.x) > 0.99f || fabsf(normal.y) > 0.99f || fabsf(normal.z) > 0.99f)
+    {
+        f3 axis = normalize(c.b - c.a);
+        if (fabsf(dot(normal, axis)) < 0.01f)
+        {
+            f3 cpp[4], cpn[4]; PlaneS planes[4];
+            f3 boxNormal = -normal;
+            PlaneS ref = boxReferencePlane(a, boxNormal);
+            PolyD poly; poly.n = 2;
+            f3 pa = c.a + normal * c.r, pb = c.b + normal * c.r;
+            poly.p[0].v = pa; poly.p[0].depth = -signedDistance(pa, ref);
+            poly.p[1].v = pb; poly.p[1].depth = -signedDistance(pb, ref);
+            f3 ac = boxCenter(a);
+            boxClipPlanes(boxRadius(a), boxNormal, cpp, cpn);
+            for (int i = 0; i < 4; ++i) { cpp[i] = cpp[i] + ac; planes[i] = createPlane(cpp[i], cpn[i]); }
+            clipAndBuild(poly, planes, 4, ref, m);
+        }
+    }
+    return true;
+}
+// capsule-obb (:771-790) / cylinder-obb (:1024-1043)
+B200_D bool segmentShapeObb(const CapS& c, bool isCylinder, const ObbS& o, Man& m, NarrowCounters& nc)
+{
+    BoxS bb; bb.mn = o.c - o.r; bb.mx = o.c + o.r;
+    CapS c_; c_.a = conjugate(o.q) * (c.a - o.c) + o.c; c_.b = conjugate(o.q) * (c.b - o.c) + o.c; c_.r = c.r;
+    if (segmentShapeBox(c_, isCylinder, bb, m, nc))
+    {
+        m.n = o.q * m.n;
+        for (uint32_t i = 0; i < m.cnt; ++i) m.p[i] = o.q * (m.p[i] - o.c) + o.c;
+        return true;
+    }
+    return false;
+}
+// collision_narrow.cpp:821-951
+B200_D bool cylinderCylinder(const CapS& a, const CapS& b, Man& m, NarrowCounters& nc)
+{
+    f3 aDir = a.b - a.a;
+    f3 bDir = normalize(b.b - b.a);
+    float aLen = len(aDir);
+    aDir *= 1.f / aLen;
+    float parallel = dot(aDir, bDir);
+    if (fabsf(parallel) > 0.99f)
+    {
+        f3 pBa = b.a, pBb = b.b;
+        if (parallel < 0.f) { f3 t = pBa; pBa = pBb; pBb = t; }
+        f3 ref = a.a;
+        float a0 = 0.f, a1 = aLen;
+        float b0 = dot(aDir, pBa - ref), b1 = dot(aDir, pBb - ref);
+        if (!(b1 > b0)) ++nc.asserts;
+        float left = fmax2(a0, b0), right = fmin2(a1, b1);
+        if (right < left) return false;
+        f3 cA0 = ref + left * aDir, cA1 = ref + right * aDir;
+        f3 cB0 = closestPointSegment(cA0, pBa, pBb);
+        f3 cB1 = cB0 + (right - left) * aDir;
+        f3 normal = cB0 - cA0;
+        float d = len(normal);
+        float rs = a.r + b.r;
+        float pen = rs - d;
+        if (pen < 0.f) return false;
+        float capPen = right - left;
+        if (!(capPen > 0.f)) ++nc.asserts;
+        if (capPen < pen)
+        {
+            m.cnt = 1; m.d[0] = capPen;
+            if (b0 > a0) { m.n = aDir; m.p[0] = a.b - mk3(capPen * 0.5f); }      // scalar broadcast, SURVEY quirk B2
+            else { m.n = -aDir; m.p[0] = a.a + mk3(capPen * 0.5f); }
+        }
+        else
+        {
+            if (d < B200_EPS) { d = 0.f; normal = mk3(0.f, 1.f, 0.f); } else { normal /= d; }
+            m.n = normal; m.cnt = 2;
+            m.d[0] = pen; m.p[0] = (cA0 + cB0) * 0.5f;
+            m.d[1] = pen; m.p[1] = (cA1 + cB1) * 0.5f;
+        }
+        return true;
+    }
+    return gjkEpa(supCylinder(a), supCylinder(b), m, nc);
+}
+
+// ------------------------------------------------------------------------------------------------------ OBB - OBB
+// collision_narrow.cpp:1179-1527 : 15-axis SAT in A's frame, then face clipping or edge-edge closest points
+B200_D bool obbObb(const ObbS& a, const ObbS& b, Man& m)
+{
+    f3 axA[3] = { a.q * mk3(1.f, 0.f, 0.f), a.q * mk3(0.f, 1.f, 0.f), a.q * mk3(0.f, 0.f, 1.f) };
+    f3 axB[3] = { b.q * mk3(1.f, 0.f, 0.f), b.q * mk3(0.f, 1.f, 0.f), b.q * mk3(0.f, 0.f, 1.f) };
+    m3 r;
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+#pragma unroll
+        for (int i = 0; i < 3; ++i) matRef(r, i, j) = dot(axA[i], axB[j]);
+    f3 tw = b.c - a.c;
+    f3 t = conjugate(a.q) * tw;
+    bool parallel = false;
+    m3 absR;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) { absR.m[i] = fabsf(r.m[i]) + B200_EPS; if (absR.m[i] >= 0.99f) parallel = true; }
+
+    float ra, rb, minPen = FLT_MAX;
+    f3 normal = mk3(0.f);
+    bool bFace = false;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+    {
+        ra = comp(a.r, i); rb = dot(m3Row(absR, i), b.r);
+        float pen = ra + rb - fabsf(comp(t, i));
+        if (pen < 0.f) return false;
+        if (pen < minPen) { minPen = pen; normal = mk3(0.f); setComp(normal, i, 1.f); }
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+    {
+        ra = dot(m3Col(absR, i), a.r); rb = comp(b.r, i);
+        float d = dot(m3Col(r, i), t);
+        float pen = ra + rb - fabsf(d);
+        if (pen < 0.f) return false;
+        if (pen < minPen) { minPen = pen; normal = mk3(0.f); setComp(normal, i, 1.f); bFace = true; }
+    }
+    bool edgeCol = false; f3 edgeN = mk3(0.f);
+    if (!parallel)
+    {
+        // edge axis a_i x b_j, i-major like the reference (:1275-1408); i1 = (i+1)%3, i2 = (i+2)%3 and likewise for j
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+        {
+            const int i1 = (i + 1) % 3, i2 = (i + 2) % 3;
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+            {
+                const int j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+                // ra = a.r[i1] * |R[i2][j]| + a.r[i2] * |R[i1][j]| ; rb = b.r[jlo] * |R[i][jhi]| + b.r[jhi] * |R[i][jlo]| with (jlo < jhi) = the two axes != j
+                const int jlo = (j1 < j2) ? j1 : j2, jhi = (j1 < j2) ? j2 : j1;
+                const int ilo = (i1 < i2) ? i1 : i2, ihi = (i1 < i2) ? i2 : i1;
+                ra = comp(a.r, ilo) * mat(absR, ihi, j) + comp(a.r, ihi) * mat(absR, ilo, j);
+                rb = comp(b.r, jlo) * mat(absR, i, jhi) + comp(b.r, jhi) * mat(absR, i, jlo);
+                // |t[i2] * R[i1][j] - t[i1] * R[i2][j]|
+                float dist = fabsf(comp(t, i2) * mat(r, i1, j) - comp(t, i1) * mat(r, i2, j));
+                float pen = ra + rb - dist;
+                if (pen < 0.f) return false;
+                f3 n = mk3(0.f); setComp(n, i1, -mat(r, i2, j)); setComp(n, i2, mat(r, i1, j));
+                float l = 1.f / len(n);
+                pen *= l;
+                if (pen < minPen) { minPen = pen; edgeN = n * l; edgeCol = true; }
+            }
+        }
+    }
+    const bool faceCol = !edgeCol;
+    if (faceCol) { if (bFace) normal = r * normal; } else { normal = edgeN; }
+    normal = a.q * normal;
+    if (dot(normal, tw) < 0.f) normal = -normal;
+    m.n = normal;
+
+    if (faceCol)
+    {
+        f3 cpp[4], cpn[4]; PolyD poly; PlaneS plane;
+        if (!bFace)
+        {
+            boxClipPlanes(a.r, conjugate(a.q) * normal, cpp, cpn);
+            boxIncidentVerts(b.r, conjugate(b.q) * normal, poly);
+            for (int i = 0; i < 4; ++i) { cpp[i] = a.q * cpp[i] + a.c; cpn[i] = a.q * cpn[i]; poly.p[i].v = b.q * poly.p[i].v + b.c; }
+            f3 refPt = supObb(a).eval(normal);
+            plane = createPlane(refPt, normal);
+        }
+        else
+        {
+            boxClipPlanes(b.r, conjugate(b.q) * -normal, cpp, cpn);
+            boxIncidentVerts(a.r, conjugate(a.q) * -normal, poly);
+            for (int i = 0; i < 4; ++i) { cpp[i] = b.q * cpp[i] + b.c; cpn[i] = b.q * cpn[i]; poly.p[i].v = a.q * poly.p[i].v + a.c; }
+            f3 refPt = supObb(b).eval(-normal);
+            plane = createPlane(refPt, -normal);
+        }
+        PlaneS planes[4];
+        for (int i = 0; i < 4; ++i) { planes[i] = createPlane(cpp[i], cpn[i]); poly.p[i].depth = -signedDistance(poly.p[i].v, plane); }
+        if (!clipAndBuild(poly, planes, 4, plane, m)) return false;
+    }
+    else
+    {
+        f3 a0, a1, b0, b1;
+        boxIncidentEdge(a.r, conjugate(a.q) * normal, a0, a1);
+        boxIncidentEdge(b.r, conjugate(b.q) * -normal, b0, b1);
+        a0 = a.q * a0 + a.c; a1 = a.q * a1 + a.c; b0 = b.q * b0 + b.c; b1 = b.q * b1 + b.c;
+        f3 pa, pb;
+        float sq = closestSegmentSegment(a0, a1, b0, b1, pa, pb);
+        m.cnt = 1; m.d[0] = sqrtf(sq); m.p[0] = (pa + pb) * 0.5f;
+    }
+    return true;
+}
+
+} // namespace b200

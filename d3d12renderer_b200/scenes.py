@@ -1,0 +1,144 @@
+"""Synthetic scene generators for the BASELINE.json configurations.
+
+Host-side set-up code (not on the per-step hot path): produces the flat boundary arrays (abi.body_dtype, abi.collider_dtype,
+abi.transform_dtype, joints) that both the CUDA stepper and the parity oracle consume. All randomness comes from the
+reference's xorshift64 generator (src/core/random.h:5-50) so scenes are reproducible from their seed alone.
+Mass properties follow collider_union::calculatePhysicsProperties (src/physics/physics.cpp:1416-1588) in float32.
+"""
+import numpy as np
+from . import abi
+
+F = np.float32
+M_PI = F(3.14159265359)  # reference src/core/math.h:13
+
+
+class Xorshift64:
+    """random_number_generator (reference src/core/random.h:5-50)."""
+
+    def __init__(self, seed):
+        self.state = seed & 0xFFFFFFFFFFFFFFFF
+
+    def u64(self):
+        x = self.state
+        x ^= (x << 13) & 0xFFFFFFFFFFFFFFFF
+        x ^= x >> 7
+        x ^= (x << 17) & 0xFFFFFFFFFFFFFFFF
+        self.state = x
+        return x
+
+    def f01(self):
+        return F(F(self.u64() & 0xFFFFFFFF) / F(4294967295.0))
+
+    def between(self, lo, hi):
+        t = F((self.f01() - F(0)) / (F(1) - F(0)))
+        return F(F(lo) + t * (F(hi) - F(lo)))
+
+
+def xorshift_floats01(seed, count):
+    """count values of randomFloat01() as a float32 array (vectorised output, sequential generator)."""
+    out = np.empty(count, dtype=np.float64)
+    x = seed & 0xFFFFFFFFFFFFFFFF
+    mask = 0xFFFFFFFFFFFFFFFF
+    for i in range(count):
+        x ^= (x << 13) & mask
+        x ^= x >> 7
+        x ^= (x << 17) & mask
+        out[i] = x & 0xFFFFFFFF
+    return (out.astype(np.float32) / F(4294967295.0)).astype(np.float32)
+
+
+def sphere_mass(radius, density):
+    r = F(radius)
+    sq = F(r * r); sq_pi = F(M_PI * sq)
+    volume = F(F(F(4.0) / F(3.0)) * sq_pi * r)
+    mass = F(volume * F(density))
+    inertia = F(F(F(F(2.0) / F(5.0)) * mass) * r * r)
+    return mass, inertia
+
+
+def new_bodies(n):
+    b = np.zeros(n, dtype=abi.body_dtype)
+    b["rotation"][:, 3] = 1.0
+    b["gravityFactor"] = 1.0
+    b["linearDamping"] = 0.4   # rigid_body.h:21 defaults
+    b["angularDamping"] = 0.4
+    return b
+
+
+def set_sphere_bodies(bodies, idx, radius, density):
+    mass, inertia = sphere_mass(radius, density)
+    bodies["invMass"][idx] = F(1.0) / mass
+    inv_i = F(1.0) / inertia
+    for k in (0, 4, 8):
+        bodies["invInertia"][idx, k] = inv_i
+
+
+def static_box(colliders, i, center, radius, transform_index, restitution=0.1, friction=1.0, density=4.0):
+    c = np.asarray(center, dtype=np.float32); r = np.asarray(radius, dtype=np.float32)
+    colliders["shape"][i, 0:3] = c - r
+    colliders["shape"][i, 3:6] = c + r
+    colliders["restitution"][i] = restitution; colliders["friction"][i] = friction; colliders["density"][i] = density
+    colliders["type"][i] = abi.AABB; colliders["objectType"][i] = abi.OBJ_STATIC
+    colliders["objectIndex"][i] = 0; colliders["parentTransform"][i] = transform_index
+
+
+def spheres_on_ground(n_side=32, spacing=1.25, mode="drop", seed=15681923, radius=0.5):
+    """BASELINE config 1: n_side^2 dynamic spheres over the reference's ground box (application.cpp:215,248-251).
+    mode 'drop': y = 0.5 + rand[0,10] (free fall, few contacts); mode 'rest': y = 0.45 (every sphere penetrates 0.05)."""
+    n = n_side * n_side
+    bodies = new_bodies(n)
+    ix, iz = np.meshgrid(np.arange(n_side), np.arange(n_side), indexing="ij")
+    half = F((n_side - 1) * spacing * 0.5)
+    bodies["position"][:, 0] = (ix.ravel().astype(np.float32) * F(spacing) - half)
+    bodies["position"][:, 2] = (iz.ravel().astype(np.float32) * F(spacing) - half)
+    if mode == "drop":
+        r = xorshift_floats01(seed, n)
+        bodies["position"][:, 1] = F(0.5) + r * F(10.0)
+    else:
+        bodies["position"][:, 1] = F(0.45)
+    set_sphere_bodies(bodies, slice(None), radius, 1.0)
+    colliders = np.zeros(n + 1, dtype=abi.collider_dtype)
+    colliders["shape"][:n, 3] = radius
+    colliders["restitution"][:n] = 0.1; colliders["friction"][:n] = 0.5; colliders["density"][:n] = 1.0
+    colliders["type"][:n] = abi.SPHERE; colliders["objectType"][:n] = abi.OBJ_RIGID_BODY
+    colliders["objectIndex"][:n] = np.arange(n, dtype=np.uint32); colliders["parentTransform"][:n] = abi.NO_TRANSFORM
+    transforms = np.zeros(1, dtype=abi.transform_dtype)
+    transforms["rotation"][0, 3] = 1.0; transforms["position"][0] = (0.0, -4.0, 0.0)
+    extent = max(30.0, float(half) + 2.0)
+    static_box(colliders, n, (0, 0, 0), (extent, 4.0, extent), 0)
+    return {"bodies": bodies, "colliders": colliders, "transforms": transforms, "name": "spheres_on_ground_%d_%s" % (n, mode)}
+
+
+def sphere_box_drop(nx=64, ny=64, nz=64, spacing=1.02, jitter=0.005, seed=519431, radius=0.5, base_y=0.6, walls=True):
+    """BASELINE config 2: nx*ny*nz spheres on a jittered lattice inside an open box of 5 static AABBs (floor + 4 walls)."""
+    n = nx * ny * nz
+    bodies = new_bodies(n)
+    ix, iy, iz = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
+    rng = np.random.default_rng(seed)          # jitter only: bulk generator for large N (seed recorded with the scene)
+    j = rng.uniform(-jitter, jitter, size=(n, 3)).astype(np.float32)
+    hx = F((nx - 1) * spacing * 0.5); hz = F((nz - 1) * spacing * 0.5)
+    bodies["position"][:, 0] = ix.ravel().astype(np.float32) * F(spacing) - hx + j[:, 0]
+    bodies["position"][:, 1] = iy.ravel().astype(np.float32) * F(spacing) + F(base_y) + j[:, 1]
+    bodies["position"][:, 2] = iz.ravel().astype(np.float32) * F(spacing) - hz + j[:, 2]
+    set_sphere_bodies(bodies, slice(None), radius, 1.0)
+    ns = 5 if walls else 1
+    colliders = np.zeros(n + ns, dtype=abi.collider_dtype)
+    colliders["shape"][:n, 3] = radius
+    colliders["restitution"][:n] = 0.1; colliders["friction"][:n] = 0.5; colliders["density"][:n] = 1.0
+    colliders["type"][:n] = abi.SPHERE; colliders["objectType"][:n] = abi.OBJ_RIGID_BODY
+    colliders["objectIndex"][:n] = np.arange(n, dtype=np.uint32); colliders["parentTransform"][:n] = abi.NO_TRANSFORM
+    transforms = np.zeros(1, dtype=abi.transform_dtype)
+    transforms["rotation"][0, 3] = 1.0
+    ex = float(hx) + radius + 0.6; ez = float(hz) + radius + 0.6; h = float(ny * spacing) + 4.0
+    static_box(colliders, n, (0, -4.0, 0), (ex + 8.0, 4.0, ez + 8.0), 0)
+    if walls:
+        static_box(colliders, n + 1, (-(ex + 2.0), h * 0.5, 0), (2.0, h * 0.5 + 2.0, ez + 4.0), 0)
+        static_box(colliders, n + 2, ((ex + 2.0), h * 0.5, 0), (2.0, h * 0.5 + 2.0, ez + 4.0), 0)
+        static_box(colliders, n + 3, (0, h * 0.5, -(ez + 2.0)), (ex + 4.0, h * 0.5 + 2.0, 2.0), 0)
+        static_box(colliders, n + 4, (0, h * 0.5, (ez + 2.0)), (ex + 4.0, h * 0.5 + 2.0, 2.0), 0)
+    return {"bodies": bodies, "colliders": colliders, "transforms": transforms, "name": "sphere_box_drop_%dx%dx%d" % (nx, ny, nz)}
+
+
+def sphere_pile_settled(nx=16, ny=16, nz=16, spacing=0.96, jitter=0.01, seed=7, radius=0.5):
+    """Dense overlapping lattice (every sphere touches its neighbours): exercises sphere-sphere contacts + colouring."""
+    return sphere_box_drop(nx, ny, nz, spacing=spacing, jitter=jitter, seed=seed, radius=radius, base_y=0.48, walls=True)

@@ -1,0 +1,248 @@
+/*
+ * b200phys.h -- thin C ABI of the B200-native rigid-body stepper (libb200phys.so).
+ *
+ * Drop-in boundary for ONE path of pkurth/D3D12Renderer: physicsStepInternal()
+ * (reference src/physics/physics.cpp:1180-1362): world-space colliders -> broad phase ->
+ * narrow phase -> constraint init -> sequential-impulse iterations -> velocity integration.
+ * The host side (C++ mirror of physicsStep(), d3d12renderer_b200/host/) gathers the
+ * reference's component pools into the flat arrays declared here, exactly like the
+ * reference's own "Physics-Lib" DLL precedent (src/learning/learned_locomotion.cpp:395-488).
+ *
+ * Conventions
+ *  - plain C structs, caller-owned HOST memory, no torch / C++ types in any signature
+ *  - every call returns int: 0 = ok, <0 = CUDA error (-(cudaError_t)), >0 = B200PHYS_E_*
+ *  - all indices are 32 bit (the reference uses uint16: collision_broad.h:8-13, constraints.h:53-56)
+ *  - mat3 is column-major like the reference (src/core/math.h:389-403): m[0..2] is column 0
+ *  - quaternions are (x, y, z, w) (src/core/math.h:292-297)
+ *  - there is NO CPU fallback: without a CUDA device b200phys_create fails with <0
+ */
+#ifndef B200PHYS_H
+#define B200PHYS_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200PHYS_VERSION 1
+
+/* error codes (>0) */
+#define B200PHYS_E_INVALID        1   /* bad argument */
+#define B200PHYS_E_CAPACITY       2   /* a device buffer overflowed during the step; see b200phys_stats.overflow_* */
+#define B200PHYS_E_NOT_READY      3   /* download before the first step / before upload */
+
+/* collider_type (reference src/physics/physics.h:59-70; the ORDER is load-bearing for pair bucketing) */
+enum { B200PHYS_SPHERE = 0, B200PHYS_CAPSULE = 1, B200PHYS_CYLINDER = 2, B200PHYS_AABB = 3, B200PHYS_OBB = 4, B200PHYS_HULL = 5,
+       B200PHYS_COLLIDER_TYPE_COUNT = 6 };
+
+/* physics_object_type (reference src/physics/physics.h:49-57) */
+enum { B200PHYS_OBJ_RIGID_BODY = 0, B200PHYS_OBJ_STATIC = 1, B200PHYS_OBJ_FORCE_FIELD = 2, B200PHYS_OBJ_TRIGGER = 3 };
+
+/* constraint_type (reference src/physics/constraints.h:14-28); also the per-iteration kind order (constraints.cpp:3748-3772) */
+enum { B200PHYS_JOINT_DISTANCE = 0, B200PHYS_JOINT_BALL = 1, B200PHYS_JOINT_FIXED = 2, B200PHYS_JOINT_HINGE = 3,
+       B200PHYS_JOINT_CONE_TWIST = 4, B200PHYS_JOINT_SLIDER = 5, B200PHYS_JOINT_KIND_COUNT = 6 };
+
+/* constraint_motor_type (constraints.h:41-45) */
+enum { B200PHYS_MOTOR_VELOCITY = 0, B200PHYS_MOTOR_POSITION = 1 };
+
+#define B200PHYS_NO_TRANSFORM 0xFFFFFFFFu
+
+/* step flags */
+#define B200PHYS_STEP_EXACT_ORDER 1u /* wavefront levels: reproduces Gauss-Seidel in canonical array order exactly (parity mode) */
+#define B200PHYS_STEP_FAST        0u /* conflict-free colouring (the reference's AVX2 path also re-orders: constraints.cpp:51-184) */
+
+/* rigid_body_component + physics_transform1_component (reference src/physics/rigid_body.h:18-58). 35 floats. */
+typedef struct b200phys_body {
+    float rotation[4];          /* physics_transform1.rotation */
+    float position[3];          /* physics_transform1.position */
+    float localCOGPosition[3];
+    float invMass;              /* 0 = kinematic */
+    float invInertia[9];        /* local space, column-major */
+    float gravityFactor;
+    float linearDamping;
+    float angularDamping;
+    float linearVelocity[3];
+    float angularVelocity[3];
+    float forceAccumulator[3];
+    float torqueAccumulator[3];
+} b200phys_body;
+
+/* what a step changes on a body (rigid_body.cpp:126-142): pose + velocities; accumulators are cleared. 13 floats. */
+typedef struct b200phys_body_state {
+    float rotation[4];
+    float position[3];
+    float linearVelocity[3];
+    float angularVelocity[3];
+} b200phys_body_state;
+
+/* pose of a collider parent that is NOT a rigid body (transform_component of a static / trigger / force-field entity,
+ * physics.cpp:645-647) */
+typedef struct b200phys_transform {
+    float rotation[4];
+    float position[3];
+    float reserved;
+} b200phys_transform;
+
+/* collider_union in the PARENT's local space (reference src/physics/physics.h:84-106), 64 bytes.
+ * shape[] by type (bounding_volumes.h:30-231):
+ *   sphere   : center.xyz, radius
+ *   capsule  : positionA.xyz, positionB.xyz, radius
+ *   cylinder : positionA.xyz, positionB.xyz, radius
+ *   aabb     : minCorner.xyz, maxCorner.xyz
+ *   obb      : rotation.xyzw, center.xyz, radius.xyz
+ *   hull     : rotation.xyzw, position.xyz, geometryIndex (uint32 bit pattern in shape[7]) */
+typedef struct b200phys_collider {
+    float    shape[10];
+    float    restitution;
+    float    friction;
+    float    density;
+    uint8_t  type;              /* B200PHYS_SPHERE ... */
+    uint8_t  objectType;        /* B200PHYS_OBJ_* */
+    uint16_t reserved;
+    uint32_t objectIndex;       /* rigid body index if objectType == RIGID_BODY, force-field / trigger index otherwise */
+    uint32_t parentTransform;   /* for non-rigid-body parents: index into the uploaded transforms, or B200PHYS_NO_TRANSFORM */
+} b200phys_collider;
+
+/* bounding_hull_geometry (bounding_volumes.h:208-218) flattened: vertices of hull g are
+ * vertices[3*vertexOffsets[g] .. 3*vertexOffsets[g+1]); its local aabb is computed on upload (bounding_volumes.cpp:1393-1397). */
+
+/* --- joints: field order identical to the reference structs (constraints.h) ------------------------------------ */
+typedef struct b200phys_distance_joint {    /* distance_constraint, constraints.h:73-80 */
+    float localAnchorA[3], localAnchorB[3], globalLength;
+} b200phys_distance_joint;
+
+typedef struct b200phys_ball_joint {        /* ball_constraint, constraints.h:129-135 */
+    float localAnchorA[3], localAnchorB[3];
+} b200phys_ball_joint;
+
+typedef struct b200phys_fixed_joint {       /* fixed_constraint, constraints.h:175-183 */
+    float initialInvRotationDifference[4];
+    float localAnchorA[3], localAnchorB[3];
+    float reserved[2];
+} b200phys_fixed_joint;
+
+typedef struct b200phys_hinge_joint {       /* hinge_constraint, constraints.h:229-257; 26 x 4 bytes */
+    float localAnchorA[3], localAnchorB[3], localHingeAxisA[3], localHingeAxisB[3];
+    float minRotationLimit, maxRotationLimit;
+    float maxMotorTorque;
+    int32_t motorType;
+    float motorVelocityOrTargetAngle;
+    float localHingeTangentA[3], localHingeBitangentA[3], localHingeTangentB[3];
+} b200phys_hinge_joint;
+
+typedef struct b200phys_cone_twist_joint {  /* cone_twist_constraint, constraints.h:346-380; 30 x 4 bytes */
+    float localAnchorA[3], localAnchorB[3];
+    float localLimitAxisA[3], localLimitAxisB[3];
+    float localLimitTangentA[3], localLimitBitangentA[3], localLimitTangentB[3];
+    float swingLimit, twistLimit;
+    int32_t swingMotorType;
+    float swingMotorVelocityOrTargetAngle;
+    float maxSwingMotorTorque;
+    float swingMotorAxis;
+    int32_t twistMotorType;
+    float twistMotorVelocityOrTargetAngle;
+    float maxTwistMotorTorque;
+} b200phys_cone_twist_joint;
+
+typedef struct b200phys_slider_joint {      /* slider_constraint, constraints.h:497-520 */
+    float initialInvRotationDifference[4];
+    float localAnchorA[3], localAnchorB[3], localAxisA[3];
+    float negDistanceLimit, posDistanceLimit;
+    float maxMotorForce;
+    int32_t motorType;
+    float motorVelocityOrTargetDistance;
+    float reserved[2];
+} b200phys_slider_joint;
+
+/* constraint_body_pair with 32-bit indices (constraints.h:53-56) */
+typedef struct b200phys_body_pair { uint32_t rbA, rbB; } b200phys_body_pair;
+
+/* collider_pair with 32-bit indices (collision_broad.h:8-13). Broad-phase output is canonical: a < b, sorted by (a, b). */
+typedef struct b200phys_collider_pair { uint32_t a, b; } b200phys_collider_pair;
+
+/* collision_contact (physics.h:347-354) */
+typedef struct b200phys_contact {
+    float    point[3];
+    float    penetrationDepth;
+    float    normal[3];             /* from collider A to collider B of the (type-ordered) pair */
+    uint32_t friction_restitution;  /* (uint16 friction << 16) | uint16 restitution, truncating (collision_narrow.cpp:2237) */
+} b200phys_contact;
+
+typedef struct b200phys_config {
+    int32_t  device;                /* CUDA device ordinal */
+    uint32_t maxBodies;
+    uint32_t maxColliders;
+    uint32_t maxTransforms;
+    uint32_t maxPairs;              /* broad-phase pair capacity   (0: 16 * maxColliders) */
+    uint32_t maxManifolds;          /* colliding pairs capacity    (0: maxPairs) */
+    uint32_t maxJointsPerKind;      /* 0: maxBodies */
+    uint32_t maxGridCells;          /* uniform grid cell budget    (0: 1<<24) */
+    float    cellSize;              /* 0: automatic (largest small-collider AABB extent) */
+    float    bigFactor;             /* colliders whose AABB extent exceeds bigFactor * mean extent skip the grid (0: 3) */
+    uint32_t maxContacts;           /* contact capacity            (0: 2 * maxManifolds + 1024) */
+    uint32_t reserved[5];
+} b200phys_config;
+
+/* the five counters the reference publishes (physics.cpp:1258-1262) + capacities + per-stage device times */
+typedef struct b200phys_stats {
+    uint32_t numBodies, numColliders;
+    uint32_t numBroadphaseOverlaps, numCollisions, numContacts;
+    uint32_t numBigColliders, numGridCells, numColors[7]; /* colours/levels per constraint kind, [6] = contacts */
+    uint32_t overflowPairs, overflowManifolds, overflowGrid, epaOverflows, gjkIterationCaps, assertCount;
+    float    cellSize;
+    float    msWorld, msBroad, msNarrow, msInit, msSolve, msIntegrate, msTotal; /* only when timing is enabled */
+    uint32_t kernelLaunches;        /* kernels launched by the last step */
+    uint32_t reserved[7];
+} b200phys_stats;
+
+typedef struct b200phys_context b200phys_context;
+
+/* lifetime ------------------------------------------------------------------------------------------------------ */
+int b200phys_version(void);
+const char* b200phys_error_string(int code);
+int b200phys_create(const b200phys_config* config, b200phys_context** out);  /* replaces arena scratch (physics.cpp:1205-1212) */
+int b200phys_destroy(b200phys_context* ctx);
+int b200phys_set_stream(b200phys_context* ctx, void* cudaStream);            /* run on the caller's stream (0 = own stream) */
+int b200phys_enable_timing(b200phys_context* ctx, int enabled);
+/* page-locked host memory: uploads / downloads from such buffers are direct DMA transfers (optional, any host memory works) */
+void* b200phys_host_alloc(size_t bytes);
+void b200phys_host_free(void* p);
+
+/* scene upload (host -> device): replaces the EnTT pool walks of physics.cpp:631-756, 789-805, 1266-1276 ------------ */
+int b200phys_set_hulls(b200phys_context* ctx, const float* vertices, const uint32_t* vertexOffsets, uint32_t numHulls);
+int b200phys_upload_bodies(b200phys_context* ctx, const b200phys_body* bodies, uint32_t count);
+int b200phys_upload_transforms(b200phys_context* ctx, const b200phys_transform* transforms, uint32_t count);
+int b200phys_upload_colliders(b200phys_context* ctx, const b200phys_collider* colliders, uint32_t count);
+int b200phys_upload_joints(b200phys_context* ctx, int kind, const void* joints, const b200phys_body_pair* pairs, uint32_t count);
+/* accumulators only (what gameplay code mutates between steps: physics.cpp:626-627); count must equal the uploaded body count */
+int b200phys_upload_forces(b200phys_context* ctx, const float* forceTorque6, uint32_t count);
+
+/* the step: physicsStepInternal (physics.cpp:1180-1362) ------------------------------------------------------------- */
+int b200phys_step(b200phys_context* ctx, float dt, uint32_t numSolverIterations, uint32_t flags);
+int b200phys_synchronize(b200phys_context* ctx);
+
+/* results (device -> host) --------------------------------------------------------------------------------------- */
+int b200phys_download_bodies(b200phys_context* ctx, b200phys_body_state* out, uint32_t count);
+int b200phys_get_stats(b200phys_context* ctx, b200phys_stats* out);
+/* parity / event-layer taps (each returns the element count through *count; out may be NULL to query the count) */
+int b200phys_download_aabbs(b200phys_context* ctx, float* outMinMax6, uint32_t* count);
+int b200phys_download_pairs(b200phys_context* ctx, b200phys_collider_pair* out, uint32_t* count);
+int b200phys_download_contacts(b200phys_context* ctx, b200phys_contact* outContacts, b200phys_body_pair* outBodyPairs, uint32_t* count);
+int b200phys_download_collisions(b200phys_context* ctx, b200phys_collider_pair* outPairs, uint8_t* outContactCounts, uint32_t* count);
+/* order in which the solver visited contacts / joints of one kind inside an iteration (kind 6 = contacts) */
+int b200phys_download_solve_order(b200phys_context* ctx, int kind, uint32_t* outOrder, uint32_t* count);
+
+/* multi-GPU (one context per rank; transport is the caller's: NCCL send/recv on these device buffers) ----------- */
+/* packs bodies+colliders whose AABB reaches into [lo, hi) along `axis` into a device buffer; returns device ptr + count */
+int b200phys_halo_pack(b200phys_context* ctx, int axis, float lo, float hi, void** outDevicePtr, uint32_t* outCount, uint32_t* outBytes);
+/* appends `count` ghost records (received from a neighbour, device memory) as kinematic read-only bodies for the next step */
+int b200phys_halo_unpack(b200phys_context* ctx, const void* devicePtr, uint32_t count);
+int b200phys_halo_clear(b200phys_context* ctx);
+uint32_t b200phys_halo_record_bytes(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200PHYS_H */

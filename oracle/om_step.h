@@ -1,0 +1,79 @@
+// oracle/om_step.h -- TEST INFRASTRUCTURE ONLY (parity oracle). Never included by the product path.
+// State and stage functions of the CPU restatement of physicsStepInternal (reference src/physics/physics.cpp:1180-1362).
+#pragma once
+#include "om_shapes.h"
+#include "../include/b200phys.h"   // boundary POD structs only (no product code)
+#include <vector>
+
+namespace orc {
+
+// rigid_body_global_state (rigid_body.h:6-16)
+struct BodyG { Q4 rotation; V3 localCOG; V3 position; M3 invInertia; float invMass; V3 v; V3 w; };
+
+struct Contact { V3 point; float depth; V3 normal; uint32_t fr; };  // collision_contact (physics.h:347-354)
+struct Pair { uint32_t a, b; };
+
+// collision_constraint (constraints.h:615-631)
+struct ContactRow
+{
+    V3 rA, rB, tangent;
+    V3 tAngA, tAngB, nAngA, nAngB;
+    float impN, impT, massN, massT, bias;
+};
+
+enum PairOrder { ORDER_REFERENCE_SAP = 0, ORDER_CANONICAL = 1 };
+
+struct SapEndpoint { float value; uint32_t collider; bool start; };
+
+struct Oracle
+{
+    // scene (host-order arrays exactly as passed through the C ABI)
+    std::vector<b200phys_body> bodies;
+    std::vector<b200phys_transform> transforms;
+    std::vector<b200phys_collider> colliders;
+    std::vector<HullGeom> hulls;
+    std::vector<uint8_t> joints[6];                 // raw structs per kind
+    std::vector<b200phys_body_pair> jointPairs[6];
+
+    // persistent broad-phase state (sap_context, collision_broad.cpp:20-24)
+    std::vector<SapEndpoint> endpoints;
+    uint32_t sortingAxis = 0;
+    uint32_t sapColliderCount = 0;
+
+    // per-step outputs
+    std::vector<WCol> wcol;
+    std::vector<Box> aabbs;
+    std::vector<Pair> pairs;            // broad phase, in the order selected by `pairOrder`
+    std::vector<Pair> collisions;       // colliding collider pairs (type-ordered), one per manifold
+    std::vector<uint8_t> contactCount;  // per collision
+    std::vector<Contact> contacts;
+    std::vector<b200phys_body_pair> contactBodies;
+    std::vector<BodyG> g;               // numBodies + 1 (dummy)
+    std::vector<ContactRow> rows;
+    NarrowStats nstats;
+    uint32_t numNonCollisionInteractions = 0;
+
+    int pairOrder = ORDER_CANONICAL;
+    // timing of the last step by reference stage name (ms)
+    double msWorld = 0, msBroad = 0, msNarrow = 0, msForces = 0, msInit = 0, msSolve = 0, msIntegrate = 0;
+
+    void worldColliders();                               // physics.cpp:631-756
+    void broadphaseSAP();                                // collision_broad.cpp:297-447 + :87-166
+    void broadphaseBrute(std::vector<Pair>& out) const;  // all-pairs, same predicate
+    void narrowphase();                                  // collision_narrow.cpp:2328-2603
+    void integrateForces(float dt);                      // rigid_body.cpp:95-124 over physics.cpp:1266-1279
+    void initContacts(float dt);                         // constraints.cpp:3307-3379
+    void solveContacts(const uint32_t* order, uint32_t n); // constraints.cpp:3381-3449
+    void integrateVelocities(float dt);                  // rigid_body.cpp:126-142
+
+    // joints (om_joints.cpp)
+    void initJoints(float dt);
+    void solveJoints(int kind, const uint32_t* order);
+    std::vector<uint8_t> jointRows[6];
+
+    // one physicsStepInternal. contactOrder / jointOrder[k]: optional visiting order inside an iteration (the analogue of
+    // the reference's AVX2 re-batching, constraints.cpp:51-184); null = array order.
+    void step(float dt, uint32_t iterations, const uint32_t* contactOrder, const uint32_t* const jointOrder[6]);
+};
+
+} // namespace orc

@@ -1,0 +1,131 @@
+"""GPU parity tests: the CUDA stepper (through the C ABI, libb200phys.so) against the CPU oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star): broad-phase pair indices bit-exact; positions / velocities within 1e-4 relative after one
+step. Because the library is built without FMA contraction and follows the reference's operation order, most quantities
+are compared far tighter than that (tolerances are written next to each assert).
+"""
+import numpy as np
+import pytest
+
+from d3d12renderer_b200 import abi, scenes
+import oracle_lib
+
+pytestmark = pytest.mark.gpu
+
+DT = np.float32(1.0 / 120.0)
+
+
+def make_stepper(scene, **kw):
+    nb, nc = len(scene["bodies"]), len(scene["colliders"])
+    nj = max([len(j[0]) for j in scene.get("joints", {}).values()] + [1])
+    st = abi.Stepper(max_bodies=nb, max_colliders=nc, max_transforms=max(1, len(scene["transforms"])), max_joints=nj, **kw)
+    if "hull_vertices" in scene:
+        st.set_hulls(scene["hull_vertices"], scene["hull_offsets"])
+    st.upload_bodies(np.ascontiguousarray(scene["bodies"]))
+    st.upload_transforms(np.ascontiguousarray(scene["transforms"]))
+    st.upload_colliders(np.ascontiguousarray(scene["colliders"]))
+    for kind, (joints, pairs) in scene.get("joints", {}).items():
+        st.upload_joints(kind, joints, pairs)
+    return st
+
+
+def rel_err(a, b):
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b) / np.maximum(1.0, np.abs(b)))) if a.size else 0.0
+
+
+def assert_states_close(gpu, ref, tol):
+    for f in ("position", "rotation", "linearVelocity", "angularVelocity"):
+        e = rel_err(gpu[f], ref[f])
+        assert e <= tol, "%s differs: %g > %g" % (f, e, tol)
+
+
+def run_both(scene, iterations=10, flags=abi.STEP_FAST, steps=1):
+    """Steps GPU and oracle; the oracle replays the GPU's solve order (like the reference's AVX2 path, any conflict-free
+    re-ordering is a legal Gauss-Seidel order; exact mode uses canonical array order on both sides)."""
+    st = make_stepper(scene)
+    orc = oracle_lib.Oracle(scene, canonical=True)
+    out = None
+    for _ in range(steps):
+        st.step(DT, iterations, flags)
+        stats = st.stats()
+        gpu_pairs = st.download_pairs()
+        gpu_contacts, gpu_cbodies = st.download_contacts()
+        order = st.download_solve_order(6)
+        joint_orders = {k: st.download_solve_order(k) for k in scene.get("joints", {})}
+        gpu_states = st.download_bodies()
+        if flags == abi.STEP_EXACT_ORDER:
+            orc.step(DT, iterations)
+        else:
+            orc.step(DT, iterations, contact_order=order, joint_orders=joint_orders)
+        out = dict(stats=stats, gpu_pairs=gpu_pairs, gpu_contacts=gpu_contacts, gpu_cbodies=gpu_cbodies, order=order, gpu_states=gpu_states,
+                   ref_pairs=orc.pairs(), ref_contacts=orc.contacts(), ref_states=orc.body_states(), ref_aabbs=orc.aabbs(), gpu_aabbs=st.download_aabbs(),
+                   oracle=orc, stepper=st)
+    return out
+
+
+def check_detection(r, contact_tol=0.0):
+    assert np.array_equal(r["gpu_aabbs"].view(np.uint32), r["ref_aabbs"].view(np.uint32)), "world AABBs must be bit-identical"
+    assert len(r["gpu_pairs"]) == len(r["ref_pairs"])
+    assert np.array_equal(r["gpu_pairs"], r["ref_pairs"]), "broad-phase pair list must be bit-exact (canonical order)"
+    rc, rb = r["ref_contacts"]
+    assert len(r["gpu_contacts"]) == len(rc)
+    assert np.array_equal(r["gpu_cbodies"], rb)
+    assert np.array_equal(r["gpu_contacts"]["friction_restitution"], rc["friction_restitution"])
+    for f in ("point", "normal", "penetrationDepth"):
+        e = rel_err(r["gpu_contacts"][f], rc[f])
+        assert e <= contact_tol, "contact %s differs: %g" % (f, e)
+
+
+def test_known_answer_single_sphere():
+    """one sphere 0.05 deep in the ground; hand-derived fp32 values."""
+    sc = scenes.spheres_on_ground(1, mode="rest")
+    sc["bodies"]["position"][0] = (0, 0.45, 0)
+    r = run_both(sc)
+    check_detection(r)
+    c = r["gpu_contacts"][0]
+    assert c["friction_restitution"] == 0xB5041999
+    assert abs(float(c["penetrationDepth"]) - 0.050000012) < 1e-8 and tuple(c["normal"]) == (0.0, -1.0, 0.0)
+    s = r["gpu_states"][0]
+    assert abs(float(s["linearVelocity"][1]) - 0.59614736) < 1e-7
+    assert abs(float(s["position"][1]) - 0.4549679) < 1e-7
+    assert tuple(s["rotation"]) == (0.0, 0.0, 0.0, 1.0)
+    assert_states_close(r["gpu_states"], r["ref_states"], 0.0)
+
+
+@pytest.mark.parametrize("mode", ["rest", "drop"])
+def test_config1_spheres_on_ground(mode):
+    """BASELINE config 1: 1024 spheres over the ground box, 10 PGS iterations."""
+    sc = scenes.spheres_on_ground(32, mode=mode)
+    r = run_both(sc, iterations=10)
+    check_detection(r)
+    if mode == "rest":
+        assert r["stats"].numContacts == 1024 and r["stats"].numBroadphaseOverlaps == 1024
+    # every contact is sphere-vs-static: order independent, expected bit-identical; the gate is 1e-4
+    assert_states_close(r["gpu_states"], r["ref_states"], 1e-6)
+
+
+@pytest.mark.parametrize("flags", [abi.STEP_FAST, abi.STEP_EXACT_ORDER])
+def test_sphere_pile_order_modes(flags):
+    """Dense pile with body-body contacts: fast mode is checked against the oracle replaying the GPU's colour order, exact
+    mode against the oracle's canonical Gauss-Seidel order."""
+    sc = scenes.sphere_pile_settled(8, 8, 8)
+    r = run_both(sc, iterations=10, flags=flags)
+    check_detection(r)
+    assert r["stats"].numContacts > 1000
+    assert_states_close(r["gpu_states"], r["ref_states"], 1e-5)
+
+
+def test_multi_step_trajectory():
+    """20 consecutive steps of a small drop scene stay within the gate (detection exact each step)."""
+    sc = scenes.spheres_on_ground(8, mode="rest")
+    r = run_both(sc, iterations=10, steps=20)
+    check_detection(r)
+    assert_states_close(r["gpu_states"], r["ref_states"], 1e-4)
+
+
+def test_pairs_match_brute_force():
+    sc = scenes.sphere_pile_settled(10, 6, 10)
+    r = run_both(sc, iterations=1)
+    brute = r["oracle"].brute_pairs()
+    assert np.array_equal(np.sort(brute, order=["a", "b"]), r["gpu_pairs"])
