@@ -1,0 +1,265 @@
+#!/usr/bin/env python
+"""bench.py -- physics steps/sec of the B200-native rigid-body stepper on BASELINE.json's single-GPU headline configuration
+(configs[1]: 262 144 spheres box-drop pile, 10 PGS iterations), one process per GPU.
+
+  python bench.py --gpus 1 --steps K --warmup W                   # our arm (CUDA path through the C ABI)
+  python bench.py --impl reference --gpus 1 --steps K --warmup W  # the reference's CPU algorithm (oracle restatement; the reference
+                                                                  # itself is MSVC/Windows-only and does not compile here)
+A step = one physicsStepInternal (world colliders -> broad phase -> narrow phase -> PGS iterations -> integration) over all bodies.
+`value` is device-resident throughput (inputs already in HBM); `e2e` includes the per-step host->device upload of every
+body record from pinned memory and the device->host download of every pose/velocity through the public C ABI calls.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+
+METRIC = "physics steps/sec at N rigid bodies (value = bodies x steps/s, whole job)"
+ITERATIONS = 10
+DT = np.float32(1.0 / 120.0)
+# algorithmic bytes: per contact and solver iteration: row 120 + 2 x 28 read, 8 + 2 x 24 written
+B_KITER = 232.0
+B_GRID, B_PAIR_OUT = 136.0, 8.0
+CPU_SAMPLE_DIMS = (32, 16, 32)   # 16 384 spheres: the largest pile the reference's uint16 collider indices allow (<= 32 767)
+
+
+def measured_hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True); self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+def build_scene(rank):
+    """configs[1]: 262 144 spheres (64^3 jittered lattice, spacing 0.96 r=0.5: a settled pile, ~3 contacts per body) in an
+    open box of 5 static AABBs. Every rank owns one such pile (weak scaling, piles are independent)."""
+    from d3d12renderer_b200 import scenes
+    return scenes.sphere_pile_settled(64, 64, 64, seed=519431 + rank)
+
+
+def cpu_reference_sample(steps, warmup):
+    """The reference's scalar CPU algorithm (oracle restatement) on a pile it can address (uint16 collider indices),
+    same lattice and density as the GPU workload; 1 thread like the reference's step."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+    from d3d12renderer_b200 import scenes
+    sc = scenes.sphere_pile_settled(*CPU_SAMPLE_DIMS, seed=519431)
+    n = len(sc["bodies"])
+    orc = oracle_lib.Oracle(sc, canonical=False)    # reference SAP order: no canonicalisation work on the clock
+    for _ in range(warmup):
+        orc.step(DT, ITERATIONS)
+    stage = np.zeros(7)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        orc.step(DT, ITERATIONS)
+        stage += orc.stage_ms()
+    t = time.perf_counter() - t0
+    names = ["world_colliders", "broad_phase", "narrow_phase", "integrate_forces", "initialize_constraints", "solve_constraints", "integrate_velocities"]
+    return {"bodies": n, "steps": steps, "seconds": t, "steps_per_s": steps / t, "body_steps_per_s": n * steps / t,
+            "contacts": len(orc.contacts()[0]), "stage_ms": {k: float(v / steps) for k, v in zip(names, stage)}}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 40)); warmup = max(1, min(args.warmup, 3))
+    s = cpu_reference_sample(steps, warmup)
+    total_bodies = 262144 * args.gpus
+    line = {
+        "impl": "reference", "metric": METRIC, "value": s["body_steps_per_s"], "unit": "body-steps/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+        "ms_per_step": 1000.0 * s["seconds"] / steps * (262144.0 / s["bodies"]), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "262144-sphere settled pile (BASELINE configs[1]), 10 PGS iterations, dt 1/120", "bodies": total_bodies, "iterations": ITERATIONS},
+        "cpu_baseline": {"value": s["body_steps_per_s"], "unit": "body-steps/s", "cores": 1, "kind": "port",
+                         "sample": "%d-sphere pile of the same lattice (the reference's uint16 indices cap colliders at 32767), %d steps, scalar oracle restatement, 1 thread; %d contacts; stage ms %s"
+                                   % (s["bodies"], steps, s["contacts"], json.dumps(s["stage_ms"]))},
+        "e2e": {"value": s["body_steps_per_s"], "unit": "body-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0")); local_rank = int(os.environ.get("LOCAL_RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from d3d12renderer_b200 import abi
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    W = max(3, args.warmup); K = args.steps
+
+    sc = build_scene(rank)
+    n_bodies = len(sc["bodies"]); n_col = len(sc["colliders"])
+    st = abi.Stepper(max_bodies=n_bodies, max_colliders=n_col, max_transforms=4, device=local_rank)
+    stream = torch.cuda.current_stream()
+    st.set_stream(stream.cuda_stream)
+    host_bodies = abi.PinnedArray(abi.body_dtype, n_bodies); host_bodies.array[:] = sc["bodies"]
+    host_states = abi.PinnedArray(abi.body_state_dtype, n_bodies)
+    st.upload_transforms(sc["transforms"]); st.upload_colliders(sc["colliders"]); st.upload_bodies(host_bodies.array)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world > 1:
+            t = torch.tensor([x], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); return float(t.item())
+        return x
+
+    # ---- device-resident throughput -----------------------------------------------------------------------------
+    for _ in range(W):
+        st.step(DT, ITERATIONS, abi.STEP_FAST)
+    barrier()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for _ in range(K):
+        st.step(DT, ITERATIONS, abi.STEP_FAST)
+    ev1.record(stream)
+    barrier()
+    ms_dev = max_over_ranks(ev0.elapsed_time(ev1))
+    clock_info = clocks.stop() if rank == 0 else None
+    stats = st.stats()
+    launches_per_step = stats.kernelLaunches
+
+    # ---- per-kernel device times for the roofline (CUDA events on the launching stream, live) --------------------
+    st.enable_timing(True)
+    acc = np.zeros(7); contacts = 0; pairs = 0; cells = 0
+    R = 10
+    for _ in range(R):
+        st.step(DT, ITERATIONS, abi.STEP_FAST)
+        s = st.stats()
+        acc += np.array([s.msWorld, s.msBroad, s.msNarrow, s.msInit, s.msSolve, s.msIntegrate, s.msTotal]); contacts += s.numContacts; pairs += s.numBroadphaseOverlaps
+    st.enable_timing(False)
+    acc /= R; contacts /= R; pairs /= R
+    peak, peak_src = measured_hbm_peak()
+    solve_bytes = contacts * ITERATIONS * B_KITER
+    solve_gbs = solve_bytes / (acc[4] * 1e-3) / 1e9 if acc[4] > 0 else 0.0
+    broad_bytes = n_col * B_GRID + pairs * B_PAIR_OUT
+    broad_gbs = broad_bytes / (acc[1] * 1e-3) / 1e9 if acc[1] > 0 else 0.0
+
+    # ---- end to end through the public API: H2D of every body record + step + D2H of every pose/velocity ----------
+    hb = host_bodies.array; hs = host_states.array
+    st.download_bodies(hs)
+    for _ in range(2):
+        st.upload_bodies(hb); st.step(DT, ITERATIONS, abi.STEP_FAST); st.download_bodies(hs)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        st.upload_bodies(hb)                       # pinned host -> HBM, 140 B per body
+        st.step(DT, ITERATIONS, abi.STEP_FAST)
+        st.download_bodies(hs)                     # HBM -> pinned host, 52 B per body (synchronises)
+        hb["rotation"] = hs["rotation"]; hb["position"] = hs["position"]            # what the host mirror scatters back into its components
+        hb["linearVelocity"] = hs["linearVelocity"]; hb["angularVelocity"] = hs["angularVelocity"]
+    barrier()
+    ms_e2e = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    checksum = float(np.sum(hs["position"][:, 1].astype(np.float64)))
+
+    total_bodies = n_bodies * world
+    value = total_bodies * K / (ms_dev * 1e-3)
+    e2e_value = total_bodies * K / (ms_e2e * 1e-3)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        s = cpu_reference_sample(20, 2)
+        cpu = {"value": s["body_steps_per_s"], "unit": "body-steps/s", "cores": 1, "kind": "port",
+               "sample": "%d-sphere pile of the same lattice (reference uint16 collider limit), %d steps in %.1f s, scalar oracle restatement, 1 thread" % (s["bodies"], s["steps"], s["seconds"])}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "body-steps/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "262144-sphere settled pile per GPU (BASELINE configs[1]), 10 PGS iterations, dt 1/120, fast (coloured) solver order",
+                       "bodies": total_bodies, "bodies_per_gpu": n_bodies, "iterations": ITERATIONS, "contacts_per_gpu": contacts, "pairs_per_gpu": pairs,
+                       "steps_per_s": K / (ms_dev * 1e-3), "parallelism": "1 pile per GPU (independent shards, no halo)" if world > 1 else "single GPU",
+                       "l2_policy": "per-step working set (rows, pair and manifold scratch, body planes) > 126 MB L2; no explicit flush",
+                       "state_checksum_y": checksum},
+            "e2e": {"value": e2e_value, "unit": "body-steps/s", "ms_per_step": ms_e2e / K, "h2d_bytes_per_step": int(n_bodies * abi.body_dtype.itemsize),
+                    "d2h_bytes_per_step": int(n_bodies * abi.body_state_dtype.itemsize)},
+            "gpu_launches": int(launches_per_step * K),
+            "roofline": {"bound": "hbm", "kernel": "solveKernel (PGS iterations)", "achieved": solve_gbs, "peak": peak, "unit": "GB/s", "frac": solve_gbs / peak,
+                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": solve_bytes, "launch_ms": acc[4],
+                         "broad_phase": {"achieved": broad_gbs, "frac": broad_gbs / peak, "algorithmic_bytes": broad_bytes, "ms": acc[1]}},
+            "stage_ms": {"world": acc[0], "broad": acc[1], "narrow": acc[2], "init": acc[3], "solve": acc[4], "integrate": acc[5], "total": acc[6]},
+            "clocks": clock_info,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    st.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
