@@ -79,7 +79,7 @@ EXPORTS = [
     "b200phys_version", "b200phys_error_string", "b200phys_create", "b200phys_destroy", "b200phys_set_stream", "b200phys_enable_timing",
     "b200phys_host_alloc", "b200phys_host_free",
     "b200phys_set_hulls", "b200phys_upload_bodies", "b200phys_upload_transforms", "b200phys_upload_colliders", "b200phys_upload_joints",
-    "b200phys_upload_forces", "b200phys_step", "b200phys_synchronize", "b200phys_download_bodies", "b200phys_get_stats",
+    "b200phys_upload_forces", "b200phys_upload_body_states", "b200phys_step", "b200phys_synchronize", "b200phys_download_bodies", "b200phys_get_stats",
     "b200phys_download_aabbs", "b200phys_download_pairs", "b200phys_download_contacts", "b200phys_download_collisions",
     "b200phys_download_solve_order", "b200phys_halo_pack", "b200phys_halo_unpack", "b200phys_halo_clear", "b200phys_halo_record_bytes",
 ]
@@ -110,6 +110,7 @@ def load_library():
     lib.b200phys_upload_colliders.argtypes = [vp, vp, u32]
     lib.b200phys_upload_joints.argtypes = [vp, i32, vp, vp, u32]
     lib.b200phys_upload_forces.argtypes = [vp, vp, u32]
+    lib.b200phys_upload_body_states.argtypes = [vp, vp, u32]
     lib.b200phys_step.argtypes = [vp, f32, u32, u32]
     lib.b200phys_synchronize.argtypes = [vp]
     lib.b200phys_download_bodies.argtypes = [vp, vp, u32]
@@ -210,6 +211,10 @@ class Stepper:
     def upload_joints(self, kind, joints, pairs):
         assert joints.dtype == JOINT_DTYPES[kind] and pairs.dtype == body_pair_dtype
         _check(self.lib, self.lib.b200phys_upload_joints(self.ctx, kind, _ptr(np.ascontiguousarray(joints)), _ptr(np.ascontiguousarray(pairs)), len(joints)), "upload_joints")
+
+    def upload_body_states(self, states):
+        assert states.dtype == body_state_dtype and states.flags.c_contiguous
+        _check(self.lib, self.lib.b200phys_upload_body_states(self.ctx, _ptr(states), len(states)), "upload_body_states")
 
     def upload_forces(self, force_torque):
         ft = np.ascontiguousarray(force_torque, dtype=np.float32)

@@ -49,7 +49,7 @@ struct DeviceCounts
     uint32_t maxSmallExtentBits;        // float bits (non-negative floats order like uints)
     uint32_t centreMinBits[3], centreMaxBits[3]; // sortable-uint encoded floats
     GridParams grid;
-    uint32_t barrier[8];                // grid barrier words of the cooperative kernels
+    uint32_t barrier[8][32];            // grid barrier words of the cooperative kernels ([0] arrivals, [16] release flag)
 };
 
 template <typename T> struct DevBuf { T* p = nullptr; size_t n = 0; };
@@ -121,6 +121,10 @@ struct Context
     // ---- solver
     uint32_t* unitColor[kNumGroups] = {};   // colour / level per unit
     uint32_t* unitOrder[kNumGroups] = {};   // units sorted by colour (solve order)
+    uint32_t* unitPending = nullptr;        // colouring: unresolved higher-ranked neighbours per unit
+    unsigned long long* unitForbid = nullptr; // colouring: colour mask (fast) / level lower bound (exact) per unit
+    uint32_t* nbrCount = nullptr;           // colouring: number of units waiting for this unit
+    uint32_t* nbrList = nullptr;            // colouring: 16 explicit waiting units per unit
     uint32_t* adjStart = nullptr;           // N + 2
     uint32_t* adjFill = nullptr;
     uint32_t* adjList = nullptr;            // 2 * max units
@@ -128,6 +132,7 @@ struct Context
     uint32_t* levelFill = nullptr;          // 3 x (kMaxLevels + 1): per-round progress, colour histogram, scatter cursors
     uint32_t* slotOfContact = nullptr;      // solve slot -> canonical contact index
     uint32_t* unitSlotStart = nullptr;      // per sorted manifold: first solve slot
+    uint4* unitInfo = nullptr;              // per sorted manifold: (bodyA, bodyB, first slot, contact count)
     float4* rows = nullptr;                 // 8 planes x maxContacts
     float2* rowImp = nullptr;               // accumulated (normal, tangent) impulse per slot
     void* jointIn[6] = {};                  // uploaded joint structs
@@ -160,6 +165,7 @@ static inline int gridFor(const Context* c, int blocksPerSM = 8) { return c->num
 // ---- stage launchers (one per .cu file) ------------------------------------------------------------------------
 void launchUnpackBodies(Context* c, const void* devStaging, uint32_t count);
 void launchUnpackForces(Context* c, const void* devStaging, uint32_t count);
+void launchUnpackBodyStates(Context* c, const void* devStaging, uint32_t count);
 void launchPackBodyStates(Context* c, void* devStaging, uint32_t count);
 void launchIntegrateForces(Context* c, float dt);
 void launchWorldColliders(Context* c);

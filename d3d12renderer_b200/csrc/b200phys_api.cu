@@ -45,9 +45,10 @@ int allocateAll(Context& c)
         const size_t units = (gI == 6) ? M : J;
         CK(devAlloc(c.unitColor[gI], units)); CK(devAlloc(c.unitOrder[gI], units));
     }
+    CK(devAlloc(c.unitPending, (M > J ? M : J))); CK(devAlloc(c.nbrCount, (M > J ? M : J))); CK(devAlloc(c.nbrList, 16 * (M > J ? M : J))); CK(devAlloc(c.unitForbid, (M > J ? M : J)));
     CK(devAlloc(c.adjStart, N1 + 2)); CK(devAlloc(c.adjFill, N1 + 2)); CK(devAlloc(c.adjList, 2 * (M > J ? M : J)));
     CK(devAlloc(c.levelStart, (size_t)kNumGroups * (kMaxLevels + 1))); CK(devAlloc(c.levelFill, (size_t)3 * (kMaxLevels + 1)));
-    CK(devAlloc(c.slotOfContact, K)); CK(devAlloc(c.unitSlotStart, M + 2)); CK(devAlloc(c.rows, 8 * K)); CK(devAlloc(c.rowImp, K));
+    CK(devAlloc(c.slotOfContact, K)); CK(devAlloc(c.unitSlotStart, M + 2)); CK(devAlloc(c.unitInfo, M)); CK(devAlloc(c.rows, 8 * K)); CK(devAlloc(c.rowImp, K));
     static const size_t inBytes[6] = { sizeof(b200phys_distance_joint), sizeof(b200phys_ball_joint), sizeof(b200phys_fixed_joint),
                                        sizeof(b200phys_hinge_joint), sizeof(b200phys_cone_twist_joint), sizeof(b200phys_slider_joint) };
     for (int k = 0; k < 6; ++k)
@@ -80,7 +81,7 @@ void freeAll(Context& c)
     void* ptrs[] = { c.bRot, c.bPos, c.bCog, c.bInvI, c.bVel, c.bAng, c.bForce, c.bTorque, c.gVel, c.gPos, c.gInvI, c.cLocal, c.xforms, c.wCol, c.aabbMin, c.aabbMax,
         c.hullVerts, c.hullOffsets, c.hullAabb, c.cellOf, c.rankInCell, c.cellCount, c.cellStart, c.sortedMin, c.sortedMax, c.bigList, c.pairCount, c.pairStart, c.pairs,
         c.pairKey, c.pairsTyped, c.pairDst, c.pairsSorted, c.manTmp, c.manScan, c.manScanOut, c.collisions, c.manifolds, c.contacts, c.contactBodies,
-        c.adjStart, c.adjFill, c.adjList, c.levelStart, c.levelFill, c.slotOfContact, c.unitSlotStart, c.rows, c.rowImp, c.scanTmp, c.scanTmp64, c.sortHist, c.staging, c.counts, c.haloBuf };
+        c.unitPending, c.unitForbid, c.nbrCount, c.nbrList, c.adjStart, c.adjFill, c.adjList, c.levelStart, c.levelFill, c.slotOfContact, c.unitSlotStart, c.unitInfo, c.rows, c.rowImp, c.scanTmp, c.scanTmp64, c.sortHist, c.staging, c.counts, c.haloBuf };
     for (void* p : ptrs) if (p) cudaFree(p);
     for (uint32_t g = 0; g < kNumGroups; ++g) { if (c.unitColor[g]) cudaFree(c.unitColor[g]); if (c.unitOrder[g]) cudaFree(c.unitOrder[g]); }
     for (int k = 0; k < 6; ++k) { if (c.jointIn[k]) cudaFree(c.jointIn[k]); if (c.jointBodies[k]) cudaFree(c.jointBodies[k]); if (c.jointRows[k]) cudaFree(c.jointRows[k]); }
@@ -205,6 +206,19 @@ int b200phys_upload_bodies(b200phys_context* ctx, const b200phys_body* bodies, u
     return 0;
 }
 
+int b200phys_upload_body_states(b200phys_context* ctx, const b200phys_body_state* states, uint32_t count)
+{
+    if (!ctx || (count && !states) || count != ctx->c.numBodies) return B200PHYS_E_INVALID;
+    Context& c = ctx->c; CK(cudaSetDevice(c.device));
+    if (count)
+    {
+        CK(cudaMemcpyAsync(c.staging, states, sizeof(b200phys_body_state) * (size_t)count, cudaMemcpyHostToDevice, c.stream));
+        launchUnpackBodyStates(&c, c.staging, count);
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
 int b200phys_upload_forces(b200phys_context* ctx, const float* forceTorque6, uint32_t count)
 {
     if (!ctx || (count && !forceTorque6) || count != ctx->c.numBodies) return B200PHYS_E_INVALID;
@@ -307,6 +321,7 @@ int b200phys_get_stats(b200phys_context* ctx, b200phys_stats* out)
     out->epaOverflows = d.epaOverflows; out->gjkIterationCaps = d.gjkIterationCaps; out->assertCount = d.assertCount;
     out->cellSize = d.grid.cellSize;
     out->kernelLaunches = c.launches;
+    out->reserved[0] = d.remaining;   // colouring rounds of the last group (diagnostic)
     if (c.timing && c.stepped)
     {
         float ms[6] = {};

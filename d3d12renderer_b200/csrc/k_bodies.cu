@@ -53,6 +53,30 @@ __global__ void __launch_bounds__(kThreads) unpackForcesKernel(const float* __re
     }
 }
 
+__global__ void __launch_bounds__(kThreads) unpackBodyStatesKernel(const float* __restrict__ src, uint32_t count,
+    float4* __restrict__ bRot, float4* __restrict__ bPos, float4* __restrict__ bVel, float4* __restrict__ bAng)
+{
+    __shared__ float s[kThreads * 13];
+    for (uint32_t base = blockIdx.x * kThreads; base < count; base += gridDim.x * kThreads)
+    {
+        const uint32_t nHere = min((uint32_t)kThreads, count - base);
+        const float* g = src + (size_t)base * 13;
+        for (uint32_t k = threadIdx.x; k < nHere * 13; k += kThreads) s[k] = g[k];
+        __syncthreads();
+        if (threadIdx.x < nHere)
+        {
+            const float* b = s + threadIdx.x * 13;
+            const uint32_t i = base + threadIdx.x;
+            bRot[i] = make_float4(b[0], b[1], b[2], b[3]);
+            const float invMass = bPos[i].w;
+            bPos[i] = make_float4(b[4], b[5], b[6], invMass);
+            bVel[i] = make_float4(b[7], b[8], b[9], 0.f);
+            bAng[i] = make_float4(b[10], b[11], b[12], 0.f);
+        }
+        __syncthreads();
+    }
+}
+
 __global__ void __launch_bounds__(kThreads) packBodyStatesKernel(float* __restrict__ dst, uint32_t count,
     const float4* __restrict__ bRot, const float4* __restrict__ bPos, const float4* __restrict__ bVel, const float4* __restrict__ bAng)
 {
@@ -267,6 +291,12 @@ void launchUnpackForces(Context* c, const void* dev, uint32_t count)
 {
     if (!count) return;
     unpackForcesKernel<<<gridFor(c, 4), kThreads, 0, c->stream>>>((const float*)dev, count, c->bForce, c->bTorque);
+    c->launches++;
+}
+void launchUnpackBodyStates(Context* c, const void* dev, uint32_t count)
+{
+    if (!count) return;
+    unpackBodyStatesKernel<<<gridFor(c, 4), kThreads, 0, c->stream>>>((const float*)dev, count, c->bRot, c->bPos, c->bVel, c->bAng);
     c->launches++;
 }
 void launchPackBodyStates(Context* c, void* dev, uint32_t count)

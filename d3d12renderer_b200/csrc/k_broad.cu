@@ -17,6 +17,7 @@
 namespace b200 {
 
 static const int kThreads = 256;
+static const uint32_t kLocalPartners = 48;
 
 B200_D bool overlapInclusive(float4 amn, float4 amx, float4 bmn, float4 bmx)
 {   // bounding_volumes.h:352-358
@@ -187,11 +188,12 @@ __global__ void __launch_bounds__(kThreads) bpQueryKernel(const float4* __restri
     {
         const uint32_t e = (r * gridDim.x + blockIdx.x) * kThreads + threadIdx.x;
         const bool active = e < numBinned;
-        float4 amn = make_float4(0, 0, 0, 0), amx = amn; uint32_t id = 0, count = 0, base = 0;
+        float4 amn = make_float4(0, 0, 0, 0), amx = amn; uint32_t id = 0, count = 0, base = 0, expected = 0;
+        uint32_t part[kLocalPartners];   // FILL: partners are collected and sorted in thread-local memory, then written once
         if (active)
         {
             amn = sortedMin[e]; amx = sortedMax[e]; id = __float_as_uint(amn.w);
-            if (FILL) base = pairStart[id];
+            if (FILL) { base = pairStart[id]; expected = pairStart[id + 1] - base; }
             // cells that can hold the centre of an overlapping small collider
             const float slackX = halfE + halfE * 1e-3f + fabsf(amn.x) * 1e-6f + fabsf(amx.x) * 1e-6f;
             const float slackY = halfE + halfE * 1e-3f + fabsf(amn.y) * 1e-6f + fabsf(amx.y) * 1e-6f;
@@ -210,7 +212,7 @@ __global__ void __launch_bounds__(kThreads) bpQueryKernel(const float4* __restri
                         const uint32_t jd = __float_as_uint(bmn.w);
                         if (jd <= id) continue;
                         if (!overlapInclusive(amn, amx, bmn, sortedMax[f])) continue;
-                        if (FILL) { if (base + count < maxPairs) pairs[base + count] = make_uint2(id, jd); else cnt->overflowPairs = 1; }
+                        if (FILL) { if (expected <= kLocalPartners) part[count] = jd; else if (base + count < maxPairs) pairs[base + count] = make_uint2(id, jd); else cnt->overflowPairs = 1; }
                         ++count;
                     }
                 }
@@ -228,15 +230,26 @@ __global__ void __launch_bounds__(kThreads) bpQueryKernel(const float4* __restri
                     const uint32_t jd = sBigId[k];
                     if (jd <= id) continue;
                     if (!overlapInclusive(amn, amx, sBigMin[k], sBigMax[k])) continue;
-                    if (FILL) { if (base + count < maxPairs) pairs[base + count] = make_uint2(id, jd); else cnt->overflowPairs = 1; }
+                    if (FILL) { if (expected <= kLocalPartners) part[count] = jd; else if (base + count < maxPairs) pairs[base + count] = make_uint2(id, jd); else cnt->overflowPairs = 1; }
                     ++count;
                 }
         }
         if (active)
         {
             if (!FILL) pairCount[id] = count;
+            else if (expected <= kLocalPartners)
+            {   // ascending partner order: insertion sort in local memory, then one sequential write of the segment
+                for (uint32_t a = 1; a < count; ++a)
+                {
+                    const uint32_t key = part[a];
+                    uint32_t b = a;
+                    while (b > 0 && part[b - 1] > key) { part[b] = part[b - 1]; --b; }
+                    part[b] = key;
+                }
+                for (uint32_t a = 0; a < count; ++a) { if (base + a < maxPairs) pairs[base + a] = make_uint2(id, part[a]); else cnt->overflowPairs = 1; }
+            }
             else
-            {   // ascending partner order inside the collider's own segment (short: insertion sort in place)
+            {   // rare: more partners than the local buffer -> insertion sort in place in global memory
                 const uint32_t n = (base + count <= maxPairs) ? count : (base < maxPairs ? maxPairs - base : 0);
                 for (uint32_t a = 1; a < n; ++a)
                 {

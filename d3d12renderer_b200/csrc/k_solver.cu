@@ -17,12 +17,15 @@
 #include "b200_context.h"
 #include "b200_util.cuh"
 #include "k_joints.cuh"
+#include <cstdlib>
 
 namespace b200 {
 
 static_assert(sizeof(ConeTwistRowD) <= 512 && sizeof(SliderRowD) <= 512 && sizeof(HingeRowD) <= 512 && sizeof(FixedRowD) <= 512, "joint rows are allocated 512 bytes each");
 
 static const int kThreads = 256;
+static const int kColorThreads = 1024;   // fat CTAs: fewer arrivals per grid barrier
+static const int kSolveThreads = 512;
 static const uint32_t kUncolored = 0xFFFFFFFFu;
 
 B200_D bool bodyIsDynamic(const float4* __restrict__ gVel, uint32_t b, uint32_t N) { return b < N && gVel[2 * b].w > 0.f; }
@@ -52,84 +55,159 @@ __global__ void __launch_bounds__(kThreads) adjFillKernel(const uint2* __restric
 }
 
 // ------------------------------------------------------------------------------------------- colouring / levelling
-// One cooperative kernel: rounds of "colour every unit whose higher-priority neighbours are coloured", then a counting
-// sort of the units by colour (colour histogram -> scan by CTA 0 -> scatter). roundDone[r] is written only in round r,
-// so every CTA reads the same finished value after the barrier and takes the same exit decision.
-__global__ void __launch_bounds__(kThreads) colorKernel(int exact, uint32_t group, const uint2* __restrict__ unitBodies, const uint32_t* __restrict__ numUnitsPtr,
+// One cooperative kernel, "push" formulation of Jones-Plassmann:
+//   pending[u]  = number of neighbours that must be coloured before u (higher hash priority; exact mode: smaller index)
+//   forbid[u]   = fast: bit mask of colours taken by those neighbours; exact: 1 + max level of those neighbours
+// A unit with pending == 0 takes the lowest free colour (or its level), ORs/maxes it into its lower-ranked neighbours and
+// only then decrements their pending counters (release: __threadfence between, acquire on the reader's side), so the
+// result does not depend on timing: every unit decides from exactly the colours of its higher-ranked neighbours.
+// Work is proportional to 3 traversals of each unit's neighbourhood in total, independent of the number of rounds.
+// Afterwards the units are counting-sorted by colour (histogram -> scan by CTA 0 -> scatter).
+B200_D bool ranksBefore(int exact, uint32_t v, uint32_t pv, uint32_t u, uint32_t pu)
+{   // true if v must be coloured before u
+    return exact ? (v < u) : (pv > pu || (pv == pu && v > u));
+}
+
+static const uint32_t kNbrStride = 16;   // explicit "who waits for me" list per unit (falls back to adjacency traversal above this)
+
+// visits every neighbour v != u of unit u (units sharing a dynamic body); 4 adjacency entries are loaded per trip so the
+// loads overlap (the lists are short: latency, not bandwidth, is what costs here)
+template <typename F>
+B200_D void forEachNeighbour(uint32_t u, uint2 b, const float4* __restrict__ gVel, uint32_t N, const uint32_t* __restrict__ adjStart, const uint32_t* __restrict__ adjList, F&& f)
+{
+#pragma unroll
+    for (int side = 0; side < 2; ++side)
+    {
+        const uint32_t body = side ? b.y : b.x;
+        if (side && b.y == b.x) break;
+        if (!bodyIsDynamic(gVel, body, N)) continue;
+        const uint32_t a0 = adjStart[body], a1 = adjStart[body + 1];
+        for (uint32_t a = a0; a < a1; a += 4)
+        {
+            uint32_t v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = (a + j < a1) ? adjList[a + j] : u;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) if (v[j] != u) f(v[j]);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kColorThreads) colorKernel(int exact, uint32_t group, const uint2* __restrict__ unitBodies, const uint32_t* __restrict__ numUnitsPtr,
     const float4* __restrict__ gVel, uint32_t N, const uint32_t* __restrict__ adjStart, const uint32_t* __restrict__ adjList,
-    uint32_t* __restrict__ color, uint32_t* __restrict__ order, uint32_t* __restrict__ roundDone, uint32_t* __restrict__ colorCount /* kMaxLevels+1 */,
+    uint32_t* __restrict__ color, uint32_t* __restrict__ order, uint32_t* __restrict__ pending, unsigned long long* __restrict__ forbid,
+    uint32_t* __restrict__ nbrCount, uint32_t* __restrict__ nbrList,
+    uint32_t* __restrict__ roundDone, uint32_t* __restrict__ colorCount /* kMaxLevels+1 */,
     uint32_t* __restrict__ colorStartOut /* kMaxLevels+1 */, uint32_t* __restrict__ colorFill, DeviceCounts* cnt, uint32_t barrierSlot)
 {
-    __shared__ uint32_t sRed[kThreads / 32];
+    __shared__ uint32_t sRed[kColorThreads / 32];
+    __shared__ uint32_t sHist[kMaxColors], sBase[kMaxColors];   // fast mode: per-CTA colour histogram / scatter bases (no same-address global atomics)
     uint32_t epoch = 0;
-    uint32_t* bar = &cnt->barrier[barrierSlot];
+    uint32_t* bar = cnt->barrier[barrierSlot];
     const uint32_t n = *numUnitsPtr;
     const uint32_t maxColors = exact ? kMaxLevels : kMaxColors;
-    const uint32_t tid = blockIdx.x * kThreads + threadIdx.x, stride = gridDim.x * kThreads;
+    const uint32_t tid = blockIdx.x * kColorThreads + threadIdx.x, stride = gridDim.x * kColorThreads;
+    if (threadIdx.x < kMaxColors) sHist[threadIdx.x] = 0;
+    __syncthreads();
 
-    for (uint32_t u = tid; u < n; u += stride) color[u] = kUncolored;
+    // ---- phase 0: dependency counts + the list of units that wait for u
+    for (uint32_t u = tid; u < n; u += stride)
+    {
+        const uint2 b = unitBodies[u];
+        const uint32_t pu = hashPriority(u);
+        uint32_t pend = 0, nw = 0;
+        forEachNeighbour(u, b, gVel, N, adjStart, adjList, [&](uint32_t v)
+        {
+            const uint32_t pv = hashPriority(v);
+            if (ranksBefore(exact, v, pv, u, pu)) ++pend;
+            else { if (nw < kNbrStride) nbrList[(size_t)u * kNbrStride + nw] = v; ++nw; }
+        });
+        // fast mode packs both into ONE 64-bit word (pending << 48 | colour mask): the notifier's OR and its decrement go to the
+        // same address, which the memory model keeps in program order, so no fence is needed on either side
+        if (exact) { pending[u] = pend; forbid[u] = 0ull; } else forbid[u] = (unsigned long long)pend << 48;
+        color[u] = kUncolored; nbrCount[u] = nw;
+    }
     gridBarrier(bar, epoch);
 
-    uint32_t total = 0, localMax = 0;
+    uint32_t total = 0, localMax = 0, doneMask = 0;
     for (uint32_t round = 0; round < kMaxLevels && total < n; ++round)
     {
         uint32_t colouredHere = 0;
         for (uint32_t u = tid; u < n; u += stride)
         {
-            if (ldCgU32(color + u) != kUncolored) continue;
-            const uint2 b = unitBodies[u];
-            const uint32_t pu = hashPriority(u);
-            unsigned long long mask = 0ull; uint32_t level = 0; bool wait = false;
-            for (int side = 0; side < 2 && !wait; ++side)
+            const uint32_t k = (u - tid) / stride;                 // this thread's k-th unit: done bits live in a register
+            if (k < 32 ? ((doneMask >> k) & 1u) : (color[u] != kUncolored)) continue;
+            unsigned long long f;
+            if (exact)
             {
-                const uint32_t body = side ? b.y : b.x;
-                if (side && b.y == b.x) break;
-                if (!bodyIsDynamic(gVel, body, N)) continue;
-                const uint32_t a0 = adjStart[body], a1 = adjStart[body + 1];
-                for (uint32_t a = a0; a < a1; ++a)
-                {
-                    const uint32_t v = adjList[a];
-                    if (v == u) continue;
-                    if (exact)
-                    {
-                        if (v > u) continue;                       // only earlier units constrain the level
-                        const uint32_t cv = ldCgU32(color + v);
-                        if (cv == kUncolored) { wait = true; break; }
-                        level = max(level, cv + 1u);
-                    }
-                    else
-                    {
-                        const uint32_t cv = ldCgU32(color + v);
-                        if (cv == kUncolored)
-                        {
-                            const uint32_t pv = hashPriority(v);
-                            if (pv > pu || (pv == pu && v > u)) { wait = true; break; }
-                        }
-                        else mask |= (1ull << cv);
-                    }
-                }
+                if (ldCgU32(pending + u) != 0) continue;
+                __threadfence();                                   // acquire: the notifiers' level updates precede their pending decrements
+                asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(f) : "l"(forbid + u) : "memory");
             }
-            if (wait) continue;
-            uint32_t c = exact ? level : (uint32_t)(__ffsll((long long)~mask) - 1);
-            if (c >= maxColors) { c = maxColors - 1; cnt->overflowColors = 1; }
-            asm volatile("st.global.cg.u32 [%0], %1;" :: "l"(color + u), "r"(c) : "memory");
-            atomicAdd(&colorCount[c], 1u);
+            else
+            {
+                asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(f) : "l"(forbid + u) : "memory");
+                if ((f >> 48) != 0ull) continue;
+                f |= 0xFFFF000000000000ull;                        // only 48 colours are representable in fast mode
+            }
+            if (k < 32) doneMask |= (1u << k);
+            uint32_t c = exact ? (uint32_t)f : (uint32_t)(__ffsll((long long)~f) - 1);
+            if (c >= (exact ? maxColors : 48u)) { c = (exact ? maxColors : 48u) - 1; cnt->overflowColors = 1; }
+            color[u] = c;
+            if (exact) atomicAdd(&colorCount[c], 1u); else atomicAdd(&sHist[c], 1u);
             localMax = max(localMax, c + 1u);
             ++colouredHere;
+            const uint32_t nw = nbrCount[u];
+            if (nw <= kNbrStride)
+            {   // the waiting units are listed explicitly: 4 independent 128-bit loads, then fire-and-forget atomics
+                uint32_t w[kNbrStride];
+                const uint4* L = reinterpret_cast<const uint4*>(nbrList + (size_t)u * kNbrStride);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { const uint4 q = (4u * j < nw) ? L[j] : make_uint4(0, 0, 0, 0); w[4 * j] = q.x; w[4 * j + 1] = q.y; w[4 * j + 2] = q.z; w[4 * j + 3] = q.w; }
+                if (exact)
+                {
+#pragma unroll
+                    for (int j = 0; j < (int)kNbrStride; ++j) if ((uint32_t)j < nw) atomicMax(&forbid[w[j]], (unsigned long long)(c + 1u));
+                    __threadfence();
+#pragma unroll
+                    for (int j = 0; j < (int)kNbrStride; ++j) if ((uint32_t)j < nw) atomicSub(&pending[w[j]], 1u);
+                }
+                else
+                {
+#pragma unroll
+                    for (int j = 0; j < (int)kNbrStride; ++j) if ((uint32_t)j < nw) { atomicOr(&forbid[w[j]], 1ull << c); atomicAdd(&forbid[w[j]], 0xFFFF000000000000ull); }   // += -(1 << 48)
+                }
+            }
+            else
+            {
+                const uint2 b = unitBodies[u];
+                const uint32_t pu = hashPriority(u);
+                forEachNeighbour(u, b, gVel, N, adjStart, adjList, [&](uint32_t v)
+                { if (ranksBefore(exact, u, pu, v, hashPriority(v))) { if (exact) atomicMax(&forbid[v], (unsigned long long)(c + 1u)); else { atomicOr(&forbid[v], 1ull << c); atomicAdd(&forbid[v], 0xFFFF000000000000ull); } } });
+                if (exact)
+                {
+                    __threadfence();
+                    forEachNeighbour(u, b, gVel, N, adjStart, adjList, [&](uint32_t v)
+                    { if (ranksBefore(exact, u, pu, v, hashPriority(v))) atomicSub(&pending[v], 1u); });
+                }
+            }
         }
-        // block-reduce the progress counter, one atomic per CTA into this round's private slot
         uint32_t v = colouredHere;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
         if (laneId() == 0) sRed[threadIdx.x >> 5] = v;
         __syncthreads();
-        if (threadIdx.x == 0) { uint32_t t = 0; for (int w = 0; w < kThreads / 32; ++w) t += sRed[w]; if (t) atomicAdd(&roundDone[round], t); }
+        if (threadIdx.x == 0) { uint32_t t = 0; for (int w = 0; w < kColorThreads / 32; ++w) t += sRed[w]; if (t) atomicAdd(&roundDone[round], t); }
         gridBarrier(bar, epoch);
         const uint32_t done = ldCgU32(roundDone + round);
         if (done == 0 && total < n) { if (tid == 0) cnt->overflowColors = 2; break; }   // no progress: refuse to spin
         total += done;
+        if (tid == 0) cnt->remaining = round + 1;   // diagnostic: colouring rounds of the last group
     }
-    if (localMax) atomicMax(&cnt->numColors[group], localMax);
+    localMax = __reduce_max_sync(0xffffffffu, localMax);
+    if (laneId() == 0 && localMax) atomicMax(&cnt->numColors[group], localMax);
+    __syncthreads();
+    if (!exact && threadIdx.x < kMaxColors && sHist[threadIdx.x]) atomicAdd(&colorCount[threadIdx.x], sHist[threadIdx.x]);
     gridBarrier(bar, epoch);
 
     // counting sort by colour: exclusive scan of the histogram (one CTA; <= 65536 entries), then scatter
@@ -139,7 +217,7 @@ __global__ void __launch_bounds__(kThreads) colorKernel(int exact, uint32_t grou
         __shared__ uint32_t carry;
         if (threadIdx.x == 0) carry = 0;
         __syncthreads();
-        for (uint32_t base = 0; base < numColors; base += kThreads)
+        for (uint32_t base = 0; base < numColors; base += kColorThreads)
         {
             const uint32_t i = base + threadIdx.x;
             const uint32_t x = (i < numColors) ? ldCgU32(colorCount + i) : 0u;
@@ -152,22 +230,39 @@ __global__ void __launch_bounds__(kThreads) colorKernel(int exact, uint32_t grou
             const uint32_t c0 = carry;
             if (i < numColors) { colorStartOut[i] = c0 + woff + incl - x; if (!exact && i <= kMaxColors) cnt->colorStart[group][i] = c0 + woff + incl - x; }
             __syncthreads();
-            if (threadIdx.x == kThreads - 1) carry = c0 + woff + incl;
+            if (threadIdx.x == kColorThreads - 1) carry = c0 + woff + incl;
             __syncthreads();
         }
         if (threadIdx.x == 0) { colorStartOut[numColors] = carry; if (!exact && numColors <= kMaxColors) cnt->colorStart[group][numColors] = carry; }
     }
     gridBarrier(bar, epoch);
-    for (uint32_t u = tid; u < n; u += stride)
+    if (exact)
     {
-        const uint32_t c = min(ldCgU32(color + u), maxColors - 1);
-        const uint32_t pos = ldCgU32(colorStartOut + c) + atomicAdd(&colorFill[c], 1u);
-        order[pos] = u;
+        for (uint32_t u = tid; u < n; u += stride)
+        {
+            const uint32_t c = min(color[u], maxColors - 1);
+            const uint32_t pos = ldCgU32(colorStartOut + c) + atomicAdd(&colorFill[c], 1u);
+            order[pos] = u;
+        }
+    }
+    else
+    {   // each CTA reserves one range per colour (its histogram from the rounds above), then ranks inside it in shared memory
+        if (threadIdx.x < kMaxColors)
+        {
+            const uint32_t h = sHist[threadIdx.x];
+            sBase[threadIdx.x] = h ? (ldCgU32(colorStartOut + threadIdx.x) + atomicAdd(&colorFill[threadIdx.x], h)) : 0u;
+        }
+        __syncthreads();
+        for (uint32_t u = tid; u < n; u += stride)
+        {
+            const uint32_t c = min(color[u], maxColors - 1);
+            order[atomicAdd(&sBase[c], 1u)] = u;
+        }
     }
 }
 
 // ------------------------------------------------------------------------------------------------ contact rows
-// row planes (float4 each, plane stride = maxContacts), indexed by solve slot:
+// row planes (float4 each, plane stride = maxContacts; a warp reads 512 contiguous bytes per plane), indexed by solve slot:
 //  0: rA.xyz, massN   1: rB.xyz, massT   2: normal.xyz, bias   3: tangent.xyz, friction
 //  4: nAngA.xyz       5: nAngB.xyz       6: tAngA.xyz          7: tAngB.xyz
 __global__ void __launch_bounds__(kThreads) slotCountKernel(const uint32_t* __restrict__ order, const uint4* __restrict__ manifolds, uint32_t* __restrict__ slotCount, const DeviceCounts* __restrict__ cnt)
@@ -189,7 +284,7 @@ B200_D m3 loadInvInertia(const float4* __restrict__ gInvI, uint32_t b)
 // initializeCollisionVelocityConstraints (constraints.cpp:3307-3379)
 __global__ void __launch_bounds__(kThreads) initContactRowsKernel(const uint32_t* __restrict__ order, const uint32_t* __restrict__ unitSlotStart, const uint4* __restrict__ manifolds,
     const float4* __restrict__ contacts, const float4* __restrict__ gVel, const float4* __restrict__ gPos, const float4* __restrict__ gInvI,
-    float4* __restrict__ rows, float2* __restrict__ rowImp, uint32_t* __restrict__ slotOfContact, uint32_t maxContacts, float dt, const DeviceCounts* __restrict__ cnt)
+    float4* __restrict__ rows, float2* __restrict__ rowImp, uint32_t* __restrict__ slotOfContact, uint4* __restrict__ unitInfo, uint32_t maxContacts, float dt, const DeviceCounts* __restrict__ cnt)
 {
     const uint32_t n = cnt->numManifolds;
     const float invDt = 1.f / dt;
@@ -197,6 +292,7 @@ __global__ void __launch_bounds__(kThreads) initContactRowsKernel(const uint32_t
     {
         const uint4 man = manifolds[order[p]];
         const uint32_t slot0 = unitSlotStart[p];
+        unitInfo[p] = make_uint4(man.x, man.y, slot0, man.w);   // solve-order record: one 128-bit load per manifold and iteration
         const float4 vA4 = gVel[2 * man.x], wA4 = gVel[2 * man.x + 1], vB4 = gVel[2 * man.y], wB4 = gVel[2 * man.y + 1];
         const f3 posA = xyz(gPos[man.x]), posB = xyz(gPos[man.y]);
         const m3 IA = loadInvInertia(gInvI, man.x), IB = loadInvInertia(gInvI, man.y);
@@ -244,46 +340,54 @@ __global__ void __launch_bounds__(kThreads) initContactRowsKernel(const uint32_t
     }
 }
 
-// solveCollisionVelocityConstraints (constraints.cpp:3381-3449) for one manifold
-B200_D void solveManifold(uint32_t p, const uint32_t* __restrict__ order, const uint32_t* __restrict__ unitSlotStart, const uint4* __restrict__ manifolds,
-                          const float4* __restrict__ rows, float2* __restrict__ rowImp, float4* __restrict__ gVel, uint32_t maxContacts)
+// solveCollisionVelocityConstraints (constraints.cpp:3381-3449): one contact row applied to the two body velocity records
+struct RowRegs { float4 r[8]; float2 imp; };
+B200_D void loadRow(RowRegs& R, const float4* __restrict__ rows, const float2* __restrict__ rowImp, uint32_t slot, uint32_t maxContacts)
 {
-    const uint4 man = manifolds[order[p]];
-    const uint32_t slot0 = unitSlotStart[p];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) R.r[j] = ldStream(rows + (size_t)j * maxContacts + slot);
+    R.imp = rowImp[slot];
+}
+B200_D void applyRow(RowRegs& R, float imA, float imB, f3& vA, f3& wA, f3& vB, f3& wB)
+{
+    const f3 rA = xyz(R.r[0]), rB = xyz(R.r[1]), normal = xyz(R.r[2]), tangent = xyz(R.r[3]);
+    {   // tangent (friction) row first, clamped by the normal impulse of the PREVIOUS iteration (:3404-3424)
+        const f3 rel = (vB + cross(wB, rB)) - (vA + cross(wA, rA));
+        const float vt = dot(rel, tangent);
+        float lambda = -R.r[1].w * vt;
+        const float maxF = R.r[3].w * R.imp.x;
+        const float ni = clampf(R.imp.y + lambda, -maxF, maxF);
+        lambda = ni - R.imp.y; R.imp.y = ni;
+        const f3 P = lambda * tangent;
+        vA -= imA * P; wA -= xyz(R.r[6]) * lambda;
+        vB += imB * P; wB += xyz(R.r[7]) * lambda;
+    }
+    {   // normal row (:3426-3442)
+        const f3 rel = (vB + cross(wB, rB)) - (vA + cross(wA, rA));
+        const float vn = dot(rel, normal);
+        float lambda = -R.r[0].w * (vn - R.r[2].w);
+        const float ni = fmax2(R.imp.x + lambda, 0.f);
+        lambda = ni - R.imp.x; R.imp.x = ni;
+        const f3 P = lambda * normal;
+        vA -= imA * P; wA -= xyz(R.r[4]) * lambda;
+        vB += imB * P; wB += xyz(R.r[5]) * lambda;
+    }
+}
+
+// one manifold: `first` already holds the rows of its first contact (prefetched before the grid barrier)
+B200_D void solveManifold(const uint4 man, RowRegs& first, const float4* __restrict__ rows, float2* __restrict__ rowImp, float4* __restrict__ gVel, uint32_t maxContacts)
+{
     const float4 a0 = ldCg(gVel + 2 * man.x), a1 = ldCg(gVel + 2 * man.x + 1), b0 = ldCg(gVel + 2 * man.y), b1 = ldCg(gVel + 2 * man.y + 1);
     const float imA = a0.w, imB = b0.w;
     if (imA == 0.f && imB == 0.f) return;                        // :3394
     f3 vA = xyz(a0), wA = xyz(a1), vB = xyz(b0), wB = xyz(b1);
-    for (uint32_t k = 0; k < man.w; ++k)
+    applyRow(first, imA, imB, vA, wA, vB, wB);
+    rowImp[man.z] = first.imp;
+    for (uint32_t k = 1; k < man.w; ++k)
     {
-        const uint32_t slot = slot0 + k;
-        const float4 r0 = ldStream(rows + slot), r1 = ldStream(rows + (size_t)maxContacts + slot), r2 = ldStream(rows + (size_t)2 * maxContacts + slot),
-                     r3 = ldStream(rows + (size_t)3 * maxContacts + slot), r4 = ldStream(rows + (size_t)4 * maxContacts + slot), r5 = ldStream(rows + (size_t)5 * maxContacts + slot),
-                     r6 = ldStream(rows + (size_t)6 * maxContacts + slot), r7 = ldStream(rows + (size_t)7 * maxContacts + slot);
-        float2 imp = rowImp[slot];
-        const f3 rA = xyz(r0), rB = xyz(r1), normal = xyz(r2), tangent = xyz(r3);
-        {   // tangent (friction) row first, clamped by the normal impulse of the PREVIOUS iteration (:3404-3424)
-            const f3 rel = (vB + cross(wB, rB)) - (vA + cross(wA, rA));
-            const float vt = dot(rel, tangent);
-            float lambda = -r1.w * vt;
-            const float maxF = r3.w * imp.x;
-            const float ni = clampf(imp.y + lambda, -maxF, maxF);
-            lambda = ni - imp.y; imp.y = ni;
-            const f3 P = lambda * tangent;
-            vA -= imA * P; wA -= xyz(r6) * lambda;
-            vB += imB * P; wB += xyz(r7) * lambda;
-        }
-        {   // normal row (:3426-3442)
-            const f3 rel = (vB + cross(wB, rB)) - (vA + cross(wA, rA));
-            const float vn = dot(rel, normal);
-            float lambda = -r0.w * (vn - r2.w);
-            const float ni = fmax2(imp.x + lambda, 0.f);
-            lambda = ni - imp.x; imp.x = ni;
-            const f3 P = lambda * normal;
-            vA -= imA * P; wA -= xyz(r4) * lambda;
-            vB += imB * P; wB += xyz(r5) * lambda;
-        }
-        rowImp[slot] = imp;
+        RowRegs R; loadRow(R, rows, rowImp, man.z + k, maxContacts);
+        applyRow(R, imA, imB, vA, wA, vB, wB);
+        rowImp[man.z + k] = R.imp;
     }
     if (imA != 0.f) { stCg(gVel + 2 * man.x, mk4(vA, imA)); stCg(gVel + 2 * man.x + 1, mk4(wA, 0.f)); }
     if (imB != 0.f) { stCg(gVel + 2 * man.y, mk4(vB, imB)); stCg(gVel + 2 * man.y + 1, mk4(wB, 0.f)); }
@@ -291,24 +395,33 @@ B200_D void solveManifold(uint32_t p, const uint32_t* __restrict__ order, const 
 
 struct SolveArgs
 {
-    // contacts
-    const uint32_t* order; const uint32_t* unitSlotStart; const uint4* manifolds; const float4* rows; float2* rowImp; uint32_t maxContacts;
+    const uint4* unitInfo; const float4* rows; float2* rowImp; uint32_t maxContacts;
     const uint32_t* colorStart;      // contacts: per-colour unit ranges (kMaxLevels + 1)
     JointSolveArgs joints;
     float4* gVel; const float4* gInvI;
     DeviceCounts* cnt; uint32_t iterations; uint32_t barrierSlot;
 };
 
-// the persistent PGS kernel: iterations x (joint kinds in reference order, then contacts) x colours, grid barrier between colours
-__global__ void __launch_bounds__(kThreads) solveKernel(SolveArgs A)
+// The persistent PGS kernel: iterations x (joint kinds in reference order, then contacts) x colours, grid barrier between
+// colours; one fat CTA per SM (148 arrivals per barrier). Software pipelining across the barrier: the manifold record and
+// the 128-byte row a thread needs FIRST in the next colour do not depend on other CTAs, so they are loaded into registers
+// BEFORE the barrier; after it only the two 32-byte body records are on the critical path.
+template <bool JOINTS>
+__global__ void __launch_bounds__(kSolveThreads, 1) solveKernel(SolveArgs A)
 {
     uint32_t epoch = 0;
-    uint32_t* bar = &A.cnt->barrier[A.barrierSlot];
-    const uint32_t tid = blockIdx.x * kThreads + threadIdx.x, stride = gridDim.x * kThreads;
+    uint32_t* bar = A.cnt->barrier[A.barrierSlot];
+    const uint32_t tid = blockIdx.x * kSolveThreads + threadIdx.x, stride = gridDim.x * kSolveThreads;
     const uint32_t numContactColors = A.cnt->numColors[6];
+    uint4 pfInfo = make_uint4(0, 0, 0, 0); RowRegs pf; bool pfValid = false;
+    if (numContactColors)
+    {
+        const uint32_t p = A.colorStart[0] + tid;
+        if (p < A.colorStart[1]) { pfInfo = A.unitInfo[p]; loadRow(pf, A.rows, A.rowImp, pfInfo.z, A.maxContacts); pfValid = true; }
+    }
     for (uint32_t it = 0; it < A.iterations; ++it)
     {
-        for (int kind = 0; kind < 6; ++kind)
+        if (JOINTS) for (int kind = 0; kind < 6; ++kind)
         {
             const uint32_t nc = A.cnt->numColors[kind];
             for (uint32_t c = 0; c < nc; ++c)
@@ -321,7 +434,21 @@ __global__ void __launch_bounds__(kThreads) solveKernel(SolveArgs A)
         for (uint32_t c = 0; c < numContactColors; ++c)
         {
             const uint32_t p0 = A.colorStart[c], p1 = A.colorStart[c + 1];
-            for (uint32_t p = p0 + tid; p < p1; p += stride) solveManifold(p, A.order, A.unitSlotStart, A.manifolds, A.rows, A.rowImp, A.gVel, A.maxContacts);
+            if (pfValid) solveManifold(pfInfo, pf, A.rows, A.rowImp, A.gVel, A.maxContacts);
+            for (uint32_t p = p0 + tid + stride; p < p1; p += stride)
+            {
+                const uint4 man = A.unitInfo[p];
+                RowRegs R; loadRow(R, A.rows, A.rowImp, man.z, A.maxContacts);
+                solveManifold(man, R, A.rows, A.rowImp, A.gVel, A.maxContacts);
+            }
+            // prefetch this thread's first manifold of the next colour (wraps to colour 0 of the next iteration)
+            const uint32_t cn = (c + 1 < numContactColors) ? c + 1 : 0;
+            pfValid = false;
+            if ((c + 1 < numContactColors) || (it + 1 < A.iterations))
+            {
+                const uint32_t p = A.colorStart[cn] + tid;
+                if (p < A.colorStart[cn + 1]) { pfInfo = A.unitInfo[p]; loadRow(pf, A.rows, A.rowImp, pfInfo.z, A.maxContacts); pfValid = true; }
+            }
             gridBarrier(bar, epoch);
         }
     }
@@ -337,7 +464,7 @@ struct JointCounts { uint32_t n[6]; };
 __global__ void solverResetKernel(DeviceCounts* cnt, JointCounts jc)
 {
     if (threadIdx.x < kNumGroups) cnt->numColors[threadIdx.x] = 0;
-    if (threadIdx.x < 8) cnt->barrier[threadIdx.x] = 0;
+    for (int b = 0; b < 8; ++b) cnt->barrier[b][threadIdx.x] = 0;
     if (threadIdx.x < 6) cnt->numJoints[threadIdx.x] = jc.n[threadIdx.x];
 }
 
@@ -363,9 +490,11 @@ static void colorGroup(Context* c, uint32_t group, const uint2* unitBodies, cons
     cudaMemsetAsync(c->levelFill, 0, sizeof(uint32_t) * 3 * (kMaxLevels + 1), c->stream);
     int exactI = exact ? 1 : 0;
     DeviceCounts* cnt = c->counts;
-    void* args[] = { &exactI, &group, (void*)&unitBodies, (void*)&numUnitsDev, &c->gVel, (void*)&N, &c->adjStart, &c->adjList, &color, &order, &roundDone, &colorCount,
-                     &colorStartOut, &colorFill, &cnt, &barrierSlot };
-    cudaLaunchCooperativeKernel((void*)colorKernel, dim3(c->numSMs * 2), dim3(kThreads), args, 0, c->stream);
+    void* args[] = { &exactI, &group, (void*)&unitBodies, (void*)&numUnitsDev, &c->gVel, (void*)&N, &c->adjStart, &c->adjList, &color, &order, &c->unitPending, &c->unitForbid, &c->nbrCount, &c->nbrList,
+                     &roundDone, &colorCount, &colorStartOut, &colorFill, &cnt, &barrierSlot };
+    static int colorBlocksPerSM = 0;
+    if (!colorBlocksPerSM) { cudaOccupancyMaxActiveBlocksPerMultiprocessor(&colorBlocksPerSM, colorKernel, kColorThreads, 0); if (colorBlocksPerSM < 1) colorBlocksPerSM = 1; if (colorBlocksPerSM > 8) colorBlocksPerSM = 8; }
+    cudaLaunchCooperativeKernel((void*)colorKernel, dim3(c->numSMs * colorBlocksPerSM), dim3(kColorThreads), args, 0, c->stream);
     c->launches++;
     (void)maxUnits;
 }
@@ -412,16 +541,21 @@ void launchSolver(Context* c, float dt, uint32_t iterations, uint32_t flags)
     c->launches++;
     scanExclusiveU32(c, slotCount, c->unitSlotStart, &cnt->numManifolds, c->maxManifolds, nullptr);
     initContactRowsKernel<<<G, kThreads, 0, c->stream>>>(c->unitOrder[6], c->unitSlotStart, c->manifolds, c->contacts, c->gVel, c->gPos, c->gInvI,
-                                                         c->rows, c->rowImp, c->slotOfContact, c->maxContacts, dt, cnt);
+                                                         c->rows, c->rowImp, c->slotOfContact, c->unitInfo, c->maxContacts, dt, cnt);
     c->launches++;
 
     // ---- iterations
     SolveArgs A;
-    A.order = c->unitOrder[6]; A.unitSlotStart = c->unitSlotStart; A.manifolds = c->manifolds; A.rows = c->rows; A.rowImp = c->rowImp; A.maxContacts = c->maxContacts;
+    A.unitInfo = c->unitInfo; A.rows = c->rows; A.rowImp = c->rowImp; A.maxContacts = c->maxContacts;
     A.colorStart = contactColorStart; A.joints = ja; A.gVel = c->gVel; A.gInvI = c->gInvI; A.cnt = cnt; A.iterations = iterations; A.barrierSlot = 7;
     void* args[] = { &A };
     if (c->timing) cudaEventRecord(c->ev[4], c->stream);
-    cudaLaunchCooperativeKernel((void*)solveKernel, dim3(c->numSMs * 2), dim3(kThreads), args, 0, c->stream);
+    static int solveBlocksPerSM[2] = { 0, 0 };
+    const int variant = anyJoint ? 1 : 0;
+    void* fn = anyJoint ? (void*)solveKernel<true> : (void*)solveKernel<false>;
+    if (!solveBlocksPerSM[variant]) { cudaOccupancyMaxActiveBlocksPerMultiprocessor(&solveBlocksPerSM[variant], fn, kSolveThreads, 0); if (solveBlocksPerSM[variant] < 1) solveBlocksPerSM[variant] = 1; if (solveBlocksPerSM[variant] > 1) solveBlocksPerSM[variant] = 1; }
+    const int bps = solveBlocksPerSM[variant];
+    cudaLaunchCooperativeKernel(fn, dim3(c->numSMs * bps), dim3(kSolveThreads), args, 0, c->stream);
     c->launches++;
 }
 

@@ -216,6 +216,9 @@ int b200phys_upload_bodies(b200phys_context* ctx, const b200phys_body* bodies, u
 int b200phys_upload_transforms(b200phys_context* ctx, const b200phys_transform* transforms, uint32_t count);
 int b200phys_upload_colliders(b200phys_context* ctx, const b200phys_collider* colliders, uint32_t count);
 int b200phys_upload_joints(b200phys_context* ctx, int kind, const void* joints, const b200phys_body_pair* pairs, uint32_t count);
+/* pose + velocities only (the per-step mutable state, same struct b200phys_download_bodies writes); mass properties, damping and
+ * accumulators keep their uploaded values. count must equal the uploaded body count */
+int b200phys_upload_body_states(b200phys_context* ctx, const b200phys_body_state* states, uint32_t count);
 /* accumulators only (what gameplay code mutates between steps: physics.cpp:626-627); count must equal the uploaded body count */
 int b200phys_upload_forces(b200phys_context* ctx, const float* forceTorque6, uint32_t count);
 
