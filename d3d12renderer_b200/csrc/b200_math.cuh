@@ -7,6 +7,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <float.h>
+#include <math.h>
+#include <string.h>
 
 namespace b200 {
 
@@ -107,6 +109,41 @@ B200_HD m3 quaternionToMat3(q4 q)
     matRef(r, 0, 0) = 1.f - 2.f * (qyy + qzz); matRef(r, 1, 0) = 2.f * (qxy + qwz);       matRef(r, 2, 0) = 2.f * (qxz - qwy);
     matRef(r, 0, 1) = 2.f * (qxy - qwz);       matRef(r, 1, 1) = 1.f - 2.f * (qxx + qzz); matRef(r, 2, 1) = 2.f * (qyz + qwx);
     matRef(r, 0, 2) = 2.f * (qxz + qwy);       matRef(r, 1, 2) = 2.f * (qyz - qwx);       matRef(r, 2, 2) = 1.f - 2.f * (qxx + qyy);
+    return r;
+}
+// math.cpp:443-448
+B200_HD float determinant(const m3& m)
+{
+    return mat(m, 0, 0) * (mat(m, 1, 1) * mat(m, 2, 2) - mat(m, 2, 1) * mat(m, 1, 2))
+         - mat(m, 0, 1) * (mat(m, 1, 0) * mat(m, 2, 2) - mat(m, 2, 0) * mat(m, 1, 2))
+         + mat(m, 0, 2) * (mat(m, 1, 0) * mat(m, 2, 1) - mat(m, 2, 0) * mat(m, 1, 1));
+}
+// math.cpp:276-306
+B200_HD m3 invert(const m3& m)
+{
+    m3 inv;
+    matRef(inv, 0, 0) = mat(m, 1, 1) * mat(m, 2, 2) - mat(m, 2, 1) * mat(m, 1, 2);
+    matRef(inv, 0, 1) = mat(m, 0, 2) * mat(m, 2, 1) - mat(m, 2, 2) * mat(m, 0, 1);
+    matRef(inv, 0, 2) = mat(m, 0, 1) * mat(m, 1, 2) - mat(m, 1, 1) * mat(m, 0, 2);
+    matRef(inv, 1, 0) = mat(m, 1, 2) * mat(m, 2, 0) - mat(m, 2, 2) * mat(m, 1, 0);
+    matRef(inv, 1, 1) = mat(m, 0, 0) * mat(m, 2, 2) - mat(m, 2, 0) * mat(m, 0, 2);
+    matRef(inv, 1, 2) = mat(m, 0, 2) * mat(m, 1, 0) - mat(m, 1, 2) * mat(m, 0, 0);
+    matRef(inv, 2, 0) = mat(m, 1, 0) * mat(m, 2, 1) - mat(m, 2, 0) * mat(m, 1, 1);
+    matRef(inv, 2, 1) = mat(m, 0, 1) * mat(m, 2, 0) - mat(m, 2, 1) * mat(m, 0, 0);
+    matRef(inv, 2, 2) = mat(m, 0, 0) * mat(m, 1, 1) - mat(m, 1, 0) * mat(m, 0, 1);
+    float det = determinant(m);
+    if (det == 0.f) return m3Zero();
+    det = 1.f / det;
+    return inv * det;
+}
+B200_HD float trace(const m3& a) { return mat(a, 0, 0) + mat(a, 1, 1) + mat(a, 2, 2); }
+// math.cpp:778-791
+B200_HD m3 outerProduct(f3 a, f3 b)
+{
+    f3 c0 = a * b.x, c1 = a * b.y, c2 = a * b.z; m3 r;
+    matRef(r, 0, 0) = c0.x; matRef(r, 1, 0) = c0.y; matRef(r, 2, 0) = c0.z;
+    matRef(r, 0, 1) = c1.x; matRef(r, 1, 1) = c1.y; matRef(r, 2, 1) = c1.z;
+    matRef(r, 0, 2) = c2.x; matRef(r, 1, 2) = c2.y; matRef(r, 2, 2) = c2.z;
     return r;
 }
 // math.cpp:793-810

@@ -1,0 +1,122 @@
+"""ctypes binding of libb200host.so: the host-side C++ mirror of the reference's physics API (d3d12renderer_b200/host/).
+
+Used by tests and bench.py to build the BASELINE.json scenes with the reference's own scene-construction semantics (mass
+properties, collider / body index conventions, ragdoll layout, joint builders) and to drive physicsStep()."""
+import ctypes as C
+import os
+import numpy as np
+
+from . import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200host.so")
+_lib = None
+
+CONFIG_SPHERES_ON_GROUND, CONFIG_SPHERE_BOX_DROP, CONFIG_MIXED_PILE, CONFIG_RAGDOLLS = 1, 2, 3, 4
+
+
+def load_library():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("libb200host.so is missing: build it with `make -C d3d12renderer_b200/host`")
+    abi.load_library()   # dependency (resolved through rpath as well)
+    lib = C.CDLL(LIB_PATH)
+    vp, u32 = C.c_void_p, C.c_uint32
+    lib.b200host_scene_create.restype = vp
+    lib.b200host_scene_destroy.argtypes = [vp]
+    lib.b200host_build_config.argtypes = [vp, C.c_int, u32, u32, u32, C.c_uint64, C.c_int, C.c_float]
+    for n in ("b200host_num_bodies", "b200host_num_colliders", "b200host_num_hulls", "b200host_num_hull_vertices"):
+        getattr(lib, n).argtypes = [vp]; getattr(lib, n).restype = u32
+    lib.b200host_num_joints.argtypes = [vp, C.c_int]; lib.b200host_num_joints.restype = u32
+    lib.b200host_num_hull_triangles.argtypes = [vp, u32]; lib.b200host_num_hull_triangles.restype = u32
+    lib.b200host_get_bodies.argtypes = [vp, vp]
+    lib.b200host_get_colliders.argtypes = [vp, vp, vp]; lib.b200host_get_colliders.restype = u32
+    lib.b200host_get_joints.argtypes = [vp, C.c_int, vp, vp]
+    lib.b200host_get_hulls.argtypes = [vp, vp, vp]
+    lib.b200host_get_hull_triangles.argtypes = [vp, u32, vp]
+    lib.b200host_mass_properties.argtypes = [vp, vp, vp, vp, vp]
+    lib.b200host_physics_step.argtypes = [vp, C.POINTER(C.c_float), C.c_float, u32, C.c_int, u32, C.c_int]
+    lib.b200host_get_render_transforms.argtypes = [vp, vp]
+    lib.b200host_get_stats.argtypes = [vp, C.POINTER(abi.Stats)]
+    _lib = lib
+    return lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class HostScene:
+    """One game_scene of the host mirror."""
+
+    def __init__(self):
+        self.lib = load_library()
+        self.ptr = C.c_void_p(self.lib.b200host_scene_create())
+
+    def close(self):
+        if self.ptr:
+            self.lib.b200host_scene_destroy(self.ptr); self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def build_config(self, config, nx, ny=1, nz=1, seed=1, mode=0, spacing=1.25):
+        rc = self.lib.b200host_build_config(self.ptr, config, nx, ny, nz, seed, mode, spacing)
+        if rc:
+            raise ValueError("unknown config %d" % config)
+        return self
+
+    def arrays(self):
+        """Flat boundary arrays (what physicsStepInternal's gather produces)."""
+        lib, s = self.lib, self.ptr
+        nb, nc = lib.b200host_num_bodies(s), lib.b200host_num_colliders(s)
+        bodies = np.zeros(nb, dtype=abi.body_dtype); lib.b200host_get_bodies(s, _p(bodies))
+        colliders = np.zeros(nc, dtype=abi.collider_dtype); transforms = np.zeros(max(1, nc), dtype=abi.transform_dtype)
+        nt = lib.b200host_get_colliders(s, _p(colliders), _p(transforms))
+        out = {"bodies": bodies, "colliders": colliders, "transforms": np.ascontiguousarray(transforms[:max(1, nt)]), "joints": {}}
+        for k in range(6):
+            n = lib.b200host_num_joints(s, k)
+            if n:
+                j = np.zeros(n, dtype=abi.JOINT_DTYPES[k]); p = np.zeros(n, dtype=abi.body_pair_dtype)
+                lib.b200host_get_joints(s, k, _p(j), _p(p)); out["joints"][k] = (j, p)
+        nh = lib.b200host_num_hulls(s)
+        if nh:
+            nv = lib.b200host_num_hull_vertices(s)
+            verts = np.zeros((nv, 3), dtype=np.float32); offs = np.zeros(nh + 1, dtype=np.uint32)
+            lib.b200host_get_hulls(s, _p(verts), _p(offs))
+            out["hull_vertices"] = verts; out["hull_offsets"] = offs; out["hull_triangles"] = []
+            for h in range(nh):
+                t = np.zeros(3 * lib.b200host_num_hull_triangles(s, h), dtype=np.uint32)
+                lib.b200host_get_hull_triangles(s, h, _p(t)); out["hull_triangles"].append(t)
+        return out
+
+    def mass_properties(self, collider):
+        c = np.ascontiguousarray(collider)
+        inertia = np.zeros(9, dtype=np.float32); cog = np.zeros(3, dtype=np.float32); mass = np.zeros(1, dtype=np.float32)
+        self.lib.b200host_mass_properties(self.ptr, _p(c), _p(inertia), _p(cog), _p(mass))
+        return inertia, cog, float(mass[0])
+
+    def physics_step(self, timer, dt, iterations=30, fixed_frame_rate=True, frame_rate=120, exact_order=False):
+        t = C.c_float(timer)
+        rc = self.lib.b200host_physics_step(self.ptr, C.byref(t), dt, iterations, 1 if fixed_frame_rate else 0, frame_rate, 1 if exact_order else 0)
+        if rc:
+            raise abi.B200PhysError("physicsStep failed: %d" % rc)
+        return t.value
+
+    def render_transforms(self):
+        out = np.zeros((self.lib.b200host_num_bodies(self.ptr), 7), dtype=np.float32)
+        self.lib.b200host_get_render_transforms(self.ptr, _p(out)); return out
+
+    def stats(self):
+        st = abi.Stats(); self.lib.b200host_get_stats(self.ptr, C.byref(st)); return st
+
+
+def build_scene(config, nx, ny=1, nz=1, seed=1, mode=0, spacing=1.25):
+    hs = HostScene().build_config(config, nx, ny, nz, seed, mode, spacing)
+    sc = hs.arrays(); sc["host_scene"] = hs
+    return sc

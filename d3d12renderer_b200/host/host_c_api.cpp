@@ -1,0 +1,198 @@
+// host_c_api.cpp -- C entry points over the host mirror for the Python tests / bench: synthetic scene builders for the
+// BASELINE.json configurations, flat-array export, and the physicsStep() driver.
+#include "physics_host.h"
+#include <cstring>
+#include <memory>
+
+using namespace b200;
+using namespace b200host;
+
+namespace {
+
+// random_number_generator (reference src/core/random.h:5-50)
+struct Rng
+{
+    uint64_t state;
+    uint64_t u64() { uint64_t x = state; x ^= x << 13; x ^= x >> 7; x ^= x << 17; state = x; return x; }
+    float f01() { return (uint32_t)u64() / (float)UINT32_MAX; }
+    float between(float lo, float hi) { float t = (f01() - 0.f) / (1.f - 0.f); return lo + t * (hi - lo); }
+};
+
+const physics_material kDynamicMat = { physics_material_type_wood, 0.1f, 0.5f, 1.f };   // application.cpp:215
+const physics_material kStaticMat = { physics_material_type_metal, 0.1f, 1.f, 4.f };    // application.cpp:248-251
+
+void addGround(game_scene& s, float halfX, float halfZ)
+{
+    s.createEntity("Platform").addTransform(mk3(0.f, -4.f, 0.f)).addCollider(collider_component::asAABB(bounding_box::fromCenterRadius(mk3(0.f), mk3(halfX, 4.f, halfZ)), kStaticMat));
+}
+void addWalls(game_scene& s, float ex, float ez, float h)
+{
+    scene_entity w = s.createEntity("Walls"); w.addTransform(mk3(0.f));
+    w.addCollider(collider_component::asAABB(bounding_box::fromCenterRadius(mk3(-(ex + 2.f), h * 0.5f, 0.f), mk3(2.f, h * 0.5f + 2.f, ez + 4.f)), kStaticMat));
+    w.addCollider(collider_component::asAABB(bounding_box::fromCenterRadius(mk3((ex + 2.f), h * 0.5f, 0.f), mk3(2.f, h * 0.5f + 2.f, ez + 4.f)), kStaticMat));
+    w.addCollider(collider_component::asAABB(bounding_box::fromCenterRadius(mk3(0.f, h * 0.5f, -(ez + 2.f)), mk3(ex + 4.f, h * 0.5f + 2.f, 2.f)), kStaticMat));
+    w.addCollider(collider_component::asAABB(bounding_box::fromCenterRadius(mk3(0.f, h * 0.5f, (ez + 2.f)), mk3(ex + 4.f, h * 0.5f + 2.f, 2.f)), kStaticMat));
+}
+
+quat randomRotation(Rng& rng)
+{   // axis = normalize(uniform[-1,1]^3), angle = uniform[0, pi]
+    vec3 axis = mk3(rng.between(-1.f, 1.f), rng.between(-1.f, 1.f), rng.between(-1.f, 1.f));
+    if (sqLen(axis) < 1e-6f) axis = mk3(0.f, 1.f, 0.f);
+    return quatAxisAngle(normalize(axis), rng.between(0.f, B200_PI));
+}
+
+// two shared convex hulls: an 8-vertex frustum and a 12-vertex icosahedron (radius ~0.5)
+void addHullGeometries(game_scene& s)
+{
+    const vec3 fr[8] = { mk3(-0.5f, -0.4f, -0.5f), mk3(0.5f, -0.4f, -0.5f), mk3(0.5f, -0.4f, 0.5f), mk3(-0.5f, -0.4f, 0.5f),
+                         mk3(-0.3f, 0.4f, -0.3f), mk3(0.3f, 0.4f, -0.3f), mk3(0.3f, 0.4f, 0.3f), mk3(-0.3f, 0.4f, 0.3f) };
+    const indexed_triangle32 ft[12] = { {0,1,2},{0,2,3}, {4,6,5},{4,7,6}, {0,4,5},{0,5,1}, {1,5,6},{1,6,2}, {2,6,7},{2,7,3}, {3,7,4},{3,4,0} };
+    s.allocateBoundingHullGeometry(fr, 8, ft, 12);
+    const float t = 1.618034f, k = 0.5f / 1.902113f;
+    const vec3 ic[12] = { k * mk3(-1, t, 0), k * mk3(1, t, 0), k * mk3(-1, -t, 0), k * mk3(1, -t, 0), k * mk3(0, -1, t), k * mk3(0, 1, t),
+                          k * mk3(0, -1, -t), k * mk3(0, 1, -t), k * mk3(t, 0, -1), k * mk3(t, 0, 1), k * mk3(-t, 0, -1), k * mk3(-t, 0, 1) };
+    const indexed_triangle32 it[20] = { {0,11,5},{0,5,1},{0,1,7},{0,7,10},{0,10,11},{1,5,9},{5,11,4},{11,10,2},{10,7,6},{7,1,8},
+                                        {3,9,4},{3,4,2},{3,2,6},{3,6,8},{3,8,9},{4,9,5},{2,4,11},{6,2,10},{8,6,7},{9,8,1} };
+    s.allocateBoundingHullGeometry(ic, 12, it, 20);
+}
+
+} // namespace
+
+extern "C" {
+
+void* b200host_scene_create() { return new game_scene(); }
+void b200host_scene_destroy(void* s) { delete (game_scene*)s; }
+
+// config 1: nx*nz spheres over the ground (mode 0: y = 0.5 + rand*10; mode 1: y = 0.45 "at rest")           [SURVEY 8d config 1]
+// config 2: nx*ny*nz spheres on a jittered lattice inside 5 static boxes (spacing in 1/1000 via `param`)       [config 2]
+// config 3: nx*ny*nz mixed primitives (sphere / capsule / OBB / hull round-robin), random orientations        [config 3]
+// config 4: nx*nz humanoid ragdolls (14 bodies, 17 colliders, 13 joints each) above the ground                [config 4]
+int b200host_build_config(void* sp, int config, uint32_t nx, uint32_t ny, uint32_t nz, uint64_t seed, int mode, float spacing)
+{
+    game_scene& s = *(game_scene*)sp;
+    Rng rng = { seed ? seed : 1 };
+    if (config == 1)
+    {
+        const float half = (nx - 1) * spacing * 0.5f, halfz = (nz - 1) * spacing * 0.5f;
+        for (uint32_t ix = 0; ix < nx; ++ix) for (uint32_t iz = 0; iz < nz; ++iz)
+        {
+            float y = (mode == 0) ? 0.5f + rng.between(0.f, 10.f) : 0.45f;
+            s.createEntity("Sphere").addTransform(mk3(ix * spacing - half, y, iz * spacing - halfz))
+                .addCollider(collider_component::asSphere({ mk3(0.f), 0.5f }, kDynamicMat)).addRigidBody(false, 1.f);
+        }
+        addGround(s, fmaxf(30.f, half + 2.f), fmaxf(30.f, halfz + 2.f));
+        return 0;
+    }
+    if (config == 2 || config == 3)
+    {
+        addHullGeometries(s);
+        const float hx = (nx - 1) * spacing * 0.5f, hz = (nz - 1) * spacing * 0.5f;
+        uint32_t counter = 0;
+        for (uint32_t ix = 0; ix < nx; ++ix) for (uint32_t iy = 0; iy < ny; ++iy) for (uint32_t iz = 0; iz < nz; ++iz, ++counter)
+        {
+            vec3 p = mk3(ix * spacing - hx + rng.between(-0.005f, 0.005f), iy * spacing + 0.6f + rng.between(-0.005f, 0.005f), iz * spacing - hz + rng.between(-0.005f, 0.005f));
+            scene_entity e = s.createEntity("Body");
+            const int kind = (config == 2) ? 0 : (int)(counter & 3u);
+            if (kind == 0) { e.addTransform(p).addCollider(collider_component::asSphere({ mk3(0.f), 0.5f }, kDynamicMat)); }
+            else
+            {
+                e.addTransform(p, randomRotation(rng));
+                if (kind == 1) e.addCollider(collider_component::asCapsule({ mk3(0.f, -0.25f, 0.f), mk3(0.f, 0.25f, 0.f), 0.25f }, kDynamicMat));
+                else if (kind == 2) e.addCollider(collider_component::asOBB({ qIdentity(), mk3(0.f), mk3(0.4f, 0.3f, 0.35f) }, kDynamicMat));
+                else e.addCollider(collider_component::asHull({ qIdentity(), mk3(0.f), (counter >> 2) & 1u }, kDynamicMat));
+            }
+            e.addRigidBody(false, 1.f);
+        }
+        const float ex = hx + 1.1f, ez = hz + 1.1f, h = ny * spacing + 4.f;
+        s.createEntity("Floor").addTransform(mk3(0.f, -4.f, 0.f)).addCollider(collider_component::asAABB(bounding_box::fromCenterRadius(mk3(0.f), mk3(ex + 8.f, 4.f, ez + 8.f)), kStaticMat));
+        addWalls(s, ex, ez, h);
+        return 0;
+    }
+    if (config == 4)
+    {
+        const float half = (nx - 1) * spacing * 0.5f, halfz = (nz - 1) * spacing * 0.5f;
+        for (uint32_t ix = 0; ix < nx; ++ix) for (uint32_t iz = 0; iz < nz; ++iz)
+        {
+            const float y = 1.25f + ((mode == 0) ? rng.between(0.f, 0.5f) : 0.f);
+            const float rot = (mode == 0) ? rng.between(0.f, 6.2831853f) : 0.f;
+            humanoid_ragdoll::create(s, mk3(ix * spacing - half, y, iz * spacing - halfz), rot);
+        }
+        s.createEntity("Test ground").addTransform(mk3(0.f, -4.f, 0.f))
+            .addCollider(collider_component::asAABB(bounding_box::fromCenterRadius(mk3(0.f), mk3(fmaxf(20.f, half + 4.f), 4.f, fmaxf(20.f, halfz + 4.f))), kStaticMat));   // learned_locomotion.cpp:440-444
+        return 0;
+    }
+    return 1;
+}
+
+uint32_t b200host_num_bodies(void* s) { return (uint32_t)((game_scene*)s)->rigidBodies.size(); }
+uint32_t b200host_num_colliders(void* s) { return (uint32_t)((game_scene*)s)->colliders.size(); }
+uint32_t b200host_num_joints(void* s, int kind) { return (uint32_t)((game_scene*)s)->constraintEntities[kind].size(); }
+uint32_t b200host_num_hulls(void* s) { return (uint32_t)((game_scene*)s)->hullGeometries.size(); }
+uint32_t b200host_num_hull_vertices(void* s) { uint32_t n = 0; for (auto& g : ((game_scene*)s)->hullGeometries) n += (uint32_t)g.vertices.size(); return n; }
+uint32_t b200host_num_hull_triangles(void* s, uint32_t h) { return (uint32_t)((game_scene*)s)->hullGeometries[h].faces.size(); }
+
+void b200host_get_bodies(void* s, b200phys_body* out) { std::vector<b200phys_body> b; ((game_scene*)s)->gatherBodies(b); if (!b.empty()) memcpy(out, b.data(), b.size() * sizeof(b200phys_body)); }
+// returns the number of transforms written (capacity must be >= number of entities)
+uint32_t b200host_get_colliders(void* s, b200phys_collider* outC, b200phys_transform* outT)
+{
+    std::vector<b200phys_collider> c; std::vector<b200phys_transform> t; ((game_scene*)s)->gatherColliders(c, t);
+    if (!c.empty()) memcpy(outC, c.data(), c.size() * sizeof(b200phys_collider));
+    if (!t.empty()) memcpy(outT, t.data(), t.size() * sizeof(b200phys_transform));
+    return (uint32_t)t.size();
+}
+void b200host_get_joints(void* s, int kind, void* outStructs, b200phys_body_pair* outPairs)
+{
+    std::vector<uint8_t> st; std::vector<b200phys_body_pair> p; ((game_scene*)s)->gatherJoints(kind, st, p);
+    if (!st.empty()) memcpy(outStructs, st.data(), st.size());
+    if (!p.empty()) memcpy(outPairs, p.data(), p.size() * sizeof(b200phys_body_pair));
+}
+void b200host_get_hulls(void* s, float* verts, uint32_t* offsets)
+{
+    std::vector<float> v; std::vector<uint32_t> o; ((game_scene*)s)->gatherHulls(v, o);
+    if (!v.empty()) memcpy(verts, v.data(), v.size() * 4);
+    memcpy(offsets, o.data(), o.size() * 4);
+}
+void b200host_get_hull_triangles(void* s, uint32_t h, uint32_t* tris)
+{
+    const auto& f = ((game_scene*)s)->hullGeometries[h].faces;
+    for (size_t i = 0; i < f.size(); ++i) { tris[3 * i] = f[i].a; tris[3 * i + 1] = f[i].b; tris[3 * i + 2] = f[i].c; }
+}
+
+// mass properties of one collider in the boundary packing (scene must hold the hull geometries): inertia(9), cog(3), mass
+void b200host_mass_properties(void* s, const b200phys_collider* c, float* inertia9, float* cog3, float* mass)
+{
+    collider_component col; const float* f = c->shape;
+    col.type = (collider_type)c->type; col.material = { physics_material_type_none, c->restitution, c->friction, c->density };
+    switch (c->type)
+    {
+    case collider_type_sphere: col.sphere = { mk3(f[0], f[1], f[2]), f[3] }; break;
+    case collider_type_capsule: col.capsule = { mk3(f[0], f[1], f[2]), mk3(f[3], f[4], f[5]), f[6] }; break;
+    case collider_type_cylinder: col.cylinder = { mk3(f[0], f[1], f[2]), mk3(f[3], f[4], f[5]), f[6] }; break;
+    case collider_type_aabb: col.aabb = bounding_box::fromMinMax(mk3(f[0], f[1], f[2]), mk3(f[3], f[4], f[5])); break;
+    case collider_type_obb: col.obb = { mkq(f[0], f[1], f[2], f[3]), mk3(f[4], f[5], f[6]), mk3(f[7], f[8], f[9]) }; break;
+    default: { uint32_t g; memcpy(&g, &f[7], 4); col.hull = { mkq(f[0], f[1], f[2], f[3]), mk3(f[4], f[5], f[6]), g }; } break;
+    }
+    physics_properties p = col.calculatePhysicsProperties(*(game_scene*)s);
+    memcpy(inertia9, p.inertia.m, 36); cog3[0] = p.cog.x; cog3[1] = p.cog.y; cog3[2] = p.cog.z; *mass = p.mass;
+}
+
+// physicsStep(scene, arena, timer, settings, dt) through the host mirror (needs the CUDA library and a GPU)
+int b200host_physics_step(void* s, float* timer, float dt, uint32_t iterations, int fixedFrameRate, uint32_t frameRate, int exactOrder)
+{
+    physics_settings st; st.fixedFrameRate = fixedFrameRate != 0; st.frameRate = frameRate; st.numRigidSolverIterations = iterations; st.exactConstraintOrder = exactOrder != 0;
+    memory_arena arena;
+    return physicsStep(*(game_scene*)s, arena, *timer, st, dt);
+}
+// entity (render) transforms of the rigid bodies after physicsStep: rotation(4) + position(3) per body
+void b200host_get_render_transforms(void* sp, float* out7)
+{
+    game_scene& s = *(game_scene*)sp;
+    for (size_t i = 0; i < s.rigidBodies.size(); ++i)
+    {
+        const trs& t = s.entities[s.rigidBodyEntity[i]].transform; float* o = out7 + 7 * i;
+        o[0] = t.rotation.x; o[1] = t.rotation.y; o[2] = t.rotation.z; o[3] = t.rotation.w; o[4] = t.position.x; o[5] = t.position.y; o[6] = t.position.z;
+    }
+}
+void b200host_get_stats(void* sp, b200phys_stats* out) { *out = ((game_scene*)sp)->lastStats; }
+
+} // extern "C"

@@ -1,0 +1,541 @@
+// physics_host.cpp -- implementation of the host-side mirror (see physics_host.h). Scene bookkeeping, mass properties
+// (scene-build time), joint builders, the ragdoll generator and the physicsStep() driver. The per-step physics itself runs on
+// the GPU through the C ABI; this file contains no CPU implementation of any step stage.
+#include "physics_host.h"
+#include <cstring>
+#include <cstdio>
+
+using namespace b200;
+
+namespace b200host {
+
+// ------------------------------------------------------------------------------------------------- rigid bodies
+rigid_body_component::rigid_body_component(bool kinematic, float gravityFactor_, float linearDamping_, float angularDamping_)
+{   // rigid_body.cpp:6-27
+    if (kinematic) { invMass = 0.f; invInertia = m3Zero(); } else { invMass = 1.f; invInertia = m3Identity(); }
+    gravityFactor = gravityFactor_; linearDamping = linearDamping_; angularDamping = angularDamping_;
+    localCOGPosition = mk3(0.f); linearVelocity = mk3(0.f); angularVelocity = mk3(0.f); forceAccumulator = mk3(0.f); torqueAccumulator = mk3(0.f);
+}
+
+// ------------------------------------------------------------------------------------------------ mass properties
+// collider_union::calculatePhysicsProperties (physics.cpp:1416-1588): inertia about the shape's own centre of gravity
+physics_properties collider_union::calculatePhysicsProperties(const game_scene& scene) const
+{
+    physics_properties result; result.inertia = m3Zero(); result.cog = mk3(0.f); result.mass = 0.f;
+    switch (type)
+    {
+    case collider_type_sphere:
+    {
+        float sq = sphere.radius * sphere.radius, sqPi = B200_PI * sq;
+        float volume = 4.f / 3.f * sqPi * sphere.radius;   // bounding_volumes.h:35-41
+        result.mass = volume * material.density; result.cog = sphere.center;
+        result.inertia = m3Identity() * (2.f / 5.f * result.mass * sphere.radius * sphere.radius);
+    } break;
+    case collider_type_capsule:
+    {
+        vec3 axis = capsule.positionA - capsule.positionB;
+        if (axis.y < 0.f) axis *= -1.f;
+        float height = len(axis);
+        axis *= (1.f / height);
+        mat3 rot = quaternionToMat3(rotateFromTo(mk3(0.f, 1.f, 0.f), axis));
+        float sq = capsule.radius * capsule.radius, sqPi = B200_PI * sq;
+        float volume = 4.f / 3.f * sqPi * capsule.radius + sqPi * len(capsule.positionA - capsule.positionB);   // bounding_volumes.h:50-58
+        result.mass = volume * material.density; result.cog = (capsule.positionA + capsule.positionB) * 0.5f;
+        float cylMass = material.density * sqPi * height;
+        float hemiMass = material.density * 2.f / 3.f * sqPi * capsule.radius;
+        float sqH = height * height;
+        mat3 I = m3Zero();
+        matRef(I, 1, 1) = sq * cylMass * 0.5f;
+        matRef(I, 0, 0) = matRef(I, 2, 2) = mat(I, 1, 1) * 0.5f + cylMass * sqH / 12.f;
+        float t0 = hemiMass * 2.f * sq / 5.f;
+        matRef(I, 1, 1) += t0 * 2.f;
+        float t1 = height * 0.5f;
+        float t2 = t0 + hemiMass * (t1 * t1 + 3.f / 8.f * sqH);
+        matRef(I, 0, 0) += t2 * 2.f; matRef(I, 2, 2) += t2 * 2.f;
+        result.inertia = transpose(rot) * I * rot;
+    } break;
+    case collider_type_cylinder:
+    {
+        vec3 axis = cylinder.positionA - cylinder.positionB;
+        if (axis.y < 0.f) axis *= -1.f;
+        float height = len(axis);
+        axis *= (1.f / height);
+        mat3 rot = quaternionToMat3(rotateFromTo(mk3(0.f, 1.f, 0.f), axis));
+        float volume = B200_PI * cylinder.radius * cylinder.radius * len(cylinder.positionA - cylinder.positionB);   // bounding_volumes.h:67-73
+        result.mass = volume * material.density; result.cog = (cylinder.positionA + cylinder.positionB) * 0.5f;
+        float sq = cylinder.radius * cylinder.radius, sqH = height * height;
+        mat3 I = m3Zero();
+        matRef(I, 1, 1) = sq * result.mass * 0.5f;
+        matRef(I, 0, 0) = matRef(I, 2, 2) = 1.f / 12.f * result.mass * (3.f * sq + sqH);
+        result.inertia = transpose(rot) * I * rot;
+    } break;
+    case collider_type_aabb:
+    {
+        vec3 dm = aabb.maxCorner - aabb.minCorner;
+        result.mass = dm.x * dm.y * dm.z * material.density; result.cog = (aabb.minCorner + aabb.maxCorner) * 0.5f;
+        vec3 d = ((aabb.maxCorner - aabb.minCorner) * 0.5f) * 2.f;
+        matRef(result.inertia, 0, 0) = 1.f / 12.f * result.mass * (d.y * d.y + d.z * d.z);
+        matRef(result.inertia, 1, 1) = 1.f / 12.f * result.mass * (d.x * d.x + d.z * d.z);
+        matRef(result.inertia, 2, 2) = 1.f / 12.f * result.mass * (d.x * d.x + d.y * d.y);
+    } break;
+    case collider_type_obb:
+    {
+        vec3 d = obb.radius * 2.f;
+        result.mass = d.x * d.y * d.z * material.density; result.cog = obb.center;
+        mat3 I = m3Zero();
+        matRef(I, 0, 0) = 1.f / 12.f * result.mass * (d.y * d.y + d.z * d.z);
+        matRef(I, 1, 1) = 1.f / 12.f * result.mass * (d.x * d.x + d.z * d.z);
+        matRef(I, 2, 2) = 1.f / 12.f * result.mass * (d.x * d.x + d.y * d.y);
+        mat3 rot = quaternionToMat3(obb.rotation);
+        result.inertia = transpose(rot) * I * rot;
+    } break;
+    default:
+    {   // hull: accumulate the covariance of the tetrahedra (origin, face), physics.cpp:1520-1580
+        const bounding_hull_geometry& geom = scene.hullGeometries[hull.geometryIndex];
+        const float s60 = 1.f / 60.f, s120 = 1.f / 120.f;
+        mat3 Cc; for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) matRef(Cc, i, j) = (i == j) ? s60 : s120;
+        float totalMass = 0.f; mat3 totalCov = m3Zero(); vec3 totalCog = mk3(0.f);
+        for (const indexed_triangle32& f : geom.faces)
+        {
+            vec3 w1 = hull.position + hull.rotation * geom.vertices[f.a], w2 = hull.position + hull.rotation * geom.vertices[f.b], w3 = hull.position + hull.rotation * geom.vertices[f.c];
+            mat3 A;
+            matRef(A, 0, 0) = w1.x; matRef(A, 0, 1) = w2.x; matRef(A, 0, 2) = w3.x;
+            matRef(A, 1, 0) = w1.y; matRef(A, 1, 1) = w2.y; matRef(A, 1, 2) = w3.y;
+            matRef(A, 2, 0) = w1.z; matRef(A, 2, 1) = w2.z; matRef(A, 2, 2) = w3.z;
+            float detA = determinant(A);
+            mat3 cov = (A * detA) * Cc * transpose(A);
+            float volume = 1.f / 6.f * detA;
+            totalMass += volume; totalCov = totalCov + cov; totalCog += ((w1 + w2 + w3) * 0.25f) * volume;
+        }
+        totalCog /= totalMass;
+        mat3 Cp = totalCov - outerProduct(totalCog, totalCog) * totalMass;
+        result.cog = totalCog; result.mass = totalMass * material.density;
+        result.inertia = (m3Identity() * trace(Cp) - Cp) * material.density;
+    } break;
+    }
+    return result;
+}
+
+// rigid_body_component::recalculateProperties (rigid_body.cpp:29-81)
+void game_scene::recalculateProperties(entity_handle e)
+{
+    entity_data& ed = entities[e];
+    if (ed.rigidBody < 0) return;
+    rigid_body_component& rb = rigidBodies[ed.rigidBody];
+    if (rb.invMass == 0.f || ed.numColliders == 0) return;
+    std::vector<physics_properties> props;
+    for (entity_handle c = ed.firstColliderEntity; c != null_entity; c = colliders[c].nextEntity) props.push_back(colliders[c].calculatePhysicsProperties(*this));
+    mat3 inertia = m3Zero(); vec3 cog = mk3(0.f); float mass = 0.f;
+    for (const physics_properties& p : props) { mass += p.mass; cog += p.cog * p.mass; }
+    rb.invMass = 1.f / mass;
+    rb.localCOGPosition = cog = cog * rb.invMass;
+    for (const physics_properties& p : props)
+    {
+        vec3 r = p.cog - cog;
+        inertia = inertia + (p.inertia + (m3Identity() * dot(r, r) - outerProduct(r, r)) * p.mass);
+    }
+    rb.invInertia = invert(inertia);
+}
+
+// ----------------------------------------------------------------------------------------------------- entities
+scene_entity game_scene::createEntity(const char* name)
+{
+    entity_data d; d.name = name ? name : "";
+    entities.push_back(d);
+    scene_entity e; e.handle = (entity_handle)(entities.size() - 1); e.scene = this;
+    return e;
+}
+uint32_t game_scene::allocateBoundingHullGeometry(const vec3* vertices, uint32_t numVertices, const indexed_triangle32* triangles, uint32_t numTriangles)
+{
+    bounding_hull_geometry g; g.vertices.assign(vertices, vertices + numVertices); g.faces.assign(triangles, triangles + numTriangles);
+    hullGeometries.push_back(g); hullsDirty = true;
+    return (uint32_t)hullGeometries.size() - 1;
+}
+scene_entity& scene_entity::addTransform(vec3 position, quat rotation, vec3 scale)
+{   // scene.h:96-107 : refreshes physics_transform0/1 when the entity already is a rigid body
+    game_scene::entity_data& d = scene->entities[handle];
+    d.hasTransform = true; d.transform = makeTrs(position, rotation, scale);
+    if (d.rigidBody >= 0) { scene->physicsTransform0[d.rigidBody] = d.transform; scene->physicsTransform1[d.rigidBody] = d.transform; }
+    scene->collidersDirty = true;
+    return *this;
+}
+scene_entity& scene_entity::addCollider(const collider_component& c)
+{   // scene.h:38-63 : child collider entity, prepended to the parent's list, mass properties recomputed
+    game_scene::entity_data& d = scene->entities[handle];
+    collider_component col = c; col.parentEntity = handle; col.nextEntity = d.firstColliderEntity;
+    scene->colliders.push_back(col);
+    d.firstColliderEntity = (entity_handle)(scene->colliders.size() - 1);
+    ++d.numColliders;
+    scene->recalculateProperties(handle);
+    scene->collidersDirty = true;
+    return *this;
+}
+scene_entity& scene_entity::addRigidBody(bool kinematic, float gravityFactor, float linearDamping, float angularDamping)
+{   // scene.h:69-84
+    game_scene::entity_data& d = scene->entities[handle];
+    if (d.rigidBody < 0)
+    {
+        scene->rigidBodies.emplace_back(kinematic, gravityFactor, linearDamping, angularDamping);
+        scene->rigidBodyEntity.push_back(handle);
+        scene->physicsTransform0.push_back(d.transform); scene->physicsTransform1.push_back(d.transform);
+        d.rigidBody = (int32_t)scene->rigidBodies.size() - 1;
+    }
+    else scene->rigidBodies[d.rigidBody] = rigid_body_component(kinematic, gravityFactor, linearDamping, angularDamping);
+    if (!d.hasTransform) { d.transform = makeTrs(mk3(0.f)); }
+    scene->physicsTransform0[d.rigidBody] = d.transform; scene->physicsTransform1[d.rigidBody] = d.transform;
+    scene->recalculateProperties(handle);
+    scene->collidersDirty = true;
+    return *this;
+}
+rigid_body_component& scene_entity::rigidBody() { return scene->rigidBodies[scene->entities[handle].rigidBody]; }
+trs& scene_entity::transform() { return scene->entities[handle].transform; }
+
+game_scene::~game_scene() { if (ctx) { b200phys_destroy(ctx); ctx = nullptr; } }
+
+// ------------------------------------------------------------------------------------------------------- gather
+static void st3(float* o, vec3 v) { o[0] = v.x; o[1] = v.y; o[2] = v.z; }
+static void st4(float* o, quat q) { o[0] = q.x; o[1] = q.y; o[2] = q.z; o[3] = q.w; }
+
+void game_scene::gatherBodies(std::vector<b200phys_body>& out) const
+{   // rbGlobal[] is filled in rigid-body storage order (physics.cpp:1269-1274)
+    out.resize(rigidBodies.size());
+    for (size_t i = 0; i < rigidBodies.size(); ++i)
+    {
+        const rigid_body_component& rb = rigidBodies[i]; const trs& t = physicsTransform1[i]; b200phys_body& b = out[i];
+        st4(b.rotation, t.rotation); st3(b.position, t.position); st3(b.localCOGPosition, rb.localCOGPosition);
+        b.invMass = rb.invMass; memcpy(b.invInertia, rb.invInertia.m, sizeof(b.invInertia));
+        b.gravityFactor = rb.gravityFactor; b.linearDamping = rb.linearDamping; b.angularDamping = rb.angularDamping;
+        st3(b.linearVelocity, rb.linearVelocity); st3(b.angularVelocity, rb.angularVelocity);
+        st3(b.forceAccumulator, rb.forceAccumulator); st3(b.torqueAccumulator, rb.torqueAccumulator);
+    }
+}
+
+void game_scene::gatherColliders(std::vector<b200phys_collider>& outC, std::vector<b200phys_transform>& outT) const
+{   // world collider index = position in EnTT's back-to-front iteration = reverse creation order (physics.cpp:635-641)
+    const size_t C = colliders.size();
+    outC.resize(C); outT.clear();
+    std::vector<int32_t> transformOf(entities.size(), -1);
+    for (size_t i = 0; i < C; ++i)
+    {
+        const collider_component& c = colliders[C - 1 - i];
+        b200phys_collider& o = outC[i]; memset(&o, 0, sizeof(o));
+        switch (c.type)
+        {
+        case collider_type_sphere: st3(o.shape, c.sphere.center); o.shape[3] = c.sphere.radius; break;
+        case collider_type_capsule: st3(o.shape, c.capsule.positionA); st3(o.shape + 3, c.capsule.positionB); o.shape[6] = c.capsule.radius; break;
+        case collider_type_cylinder: st3(o.shape, c.cylinder.positionA); st3(o.shape + 3, c.cylinder.positionB); o.shape[6] = c.cylinder.radius; break;
+        case collider_type_aabb: st3(o.shape, c.aabb.minCorner); st3(o.shape + 3, c.aabb.maxCorner); break;
+        case collider_type_obb: st4(o.shape, c.obb.rotation); st3(o.shape + 4, c.obb.center); st3(o.shape + 7, c.obb.radius); break;
+        default: st4(o.shape, c.hull.rotation); st3(o.shape + 4, c.hull.position); memcpy(&o.shape[7], &c.hull.geometryIndex, 4); break;
+        }
+        o.restitution = c.material.restitution; o.friction = c.material.friction; o.density = c.material.density;
+        o.type = (uint8_t)c.type;
+        const entity_data& parent = entities[c.parentEntity];
+        if (parent.rigidBody >= 0) { o.objectType = B200PHYS_OBJ_RIGID_BODY; o.objectIndex = (uint32_t)parent.rigidBody; o.parentTransform = B200PHYS_NO_TRANSFORM; }
+        else
+        {   // static collider (physics.cpp:667-671); pose = transform_component or identity (:645-647)
+            o.objectType = B200PHYS_OBJ_STATIC; o.objectIndex = 0;
+            if (!parent.hasTransform) o.parentTransform = B200PHYS_NO_TRANSFORM;
+            else
+            {
+                if (transformOf[c.parentEntity] < 0)
+                {
+                    b200phys_transform t; st4(t.rotation, parent.transform.rotation); st3(t.position, parent.transform.position); t.reserved = 0.f;
+                    outT.push_back(t); transformOf[c.parentEntity] = (int32_t)outT.size() - 1;
+                }
+                o.parentTransform = (uint32_t)transformOf[c.parentEntity];
+            }
+        }
+    }
+}
+
+void game_scene::gatherJoints(int kind, std::vector<uint8_t>& outStructs, std::vector<b200phys_body_pair>& outPairs) const
+{   // constraint structs in raw storage order, body indices = rigid body storage indices (physics.cpp:789-805)
+    const void* src = nullptr; size_t n = 0, sz = 0;
+    switch (kind)
+    {
+    case 0: src = distanceConstraints.data(); n = distanceConstraints.size(); sz = sizeof(distance_constraint); break;
+    case 1: src = ballConstraints.data(); n = ballConstraints.size(); sz = sizeof(ball_constraint); break;
+    case 2: src = fixedConstraints.data(); n = fixedConstraints.size(); sz = sizeof(fixed_constraint); break;
+    case 3: src = hingeConstraints.data(); n = hingeConstraints.size(); sz = sizeof(hinge_constraint); break;
+    case 4: src = coneTwistConstraints.data(); n = coneTwistConstraints.size(); sz = sizeof(cone_twist_constraint); break;
+    default: src = sliderConstraints.data(); n = sliderConstraints.size(); sz = sizeof(slider_constraint); break;
+    }
+    outStructs.assign((const uint8_t*)src, (const uint8_t*)src + n * sz);
+    outPairs.resize(n);
+    for (size_t i = 0; i < n; ++i)
+    {
+        outPairs[i].rbA = (uint32_t)entities[constraintEntities[kind][i].rbA].rigidBody;
+        outPairs[i].rbB = (uint32_t)entities[constraintEntities[kind][i].rbB].rigidBody;
+    }
+}
+
+void game_scene::gatherHulls(std::vector<float>& verts, std::vector<uint32_t>& offsets) const
+{
+    verts.clear(); offsets.assign(1, 0u);
+    for (const bounding_hull_geometry& g : hullGeometries)
+    {
+        for (const vec3& v : g.vertices) { verts.push_back(v.x); verts.push_back(v.y); verts.push_back(v.z); }
+        offsets.push_back((uint32_t)(verts.size() / 3));
+    }
+}
+
+void game_scene::scatterBodyStates(const b200phys_body_state* s, uint32_t count)
+{   // integrateVelocity's outputs (rigid_body.cpp:126-142): physics_transform1 + velocities; accumulators cleared
+    for (uint32_t i = 0; i < count && i < rigidBodies.size(); ++i)
+    {
+        rigid_body_component& rb = rigidBodies[i]; trs& t = physicsTransform1[i];
+        t.rotation = mkq(s[i].rotation[0], s[i].rotation[1], s[i].rotation[2], s[i].rotation[3]);
+        t.position = mk3(s[i].position[0], s[i].position[1], s[i].position[2]);
+        rb.linearVelocity = mk3(s[i].linearVelocity[0], s[i].linearVelocity[1], s[i].linearVelocity[2]);
+        rb.angularVelocity = mk3(s[i].angularVelocity[0], s[i].angularVelocity[1], s[i].angularVelocity[2]);
+        rb.forceAccumulator = mk3(0.f); rb.torqueAccumulator = mk3(0.f);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------- joints
+static vec3 inverseTransformPosition(const trs& m, vec3 pos) { vec3 p = conjugate(m.rotation) * (pos - m.position); return mk3(p.x / m.scale.x, p.y / m.scale.y, p.z / m.scale.z); } // math.cpp:528-531
+static vec3 inverseTransformDirection(const trs& m, vec3 dir) { return conjugate(m.rotation) * dir; }
+
+static uint32_t pushPair(game_scene& s, int kind, scene_entity& a, scene_entity& b)
+{
+    s.constraintEntities[kind].push_back({ a.handle, b.handle }); s.jointsDirty = true;
+    return (uint32_t)s.constraintEntities[kind].size() - 1;
+}
+
+distance_constraint_handle addDistanceConstraintFromLocalPoints(scene_entity& a, scene_entity& b, vec3 localAnchorA, vec3 localAnchorB, float distance)
+{   // physics.cpp:128-146
+    distance_constraint c; st3(c.localAnchorA, localAnchorA); st3(c.localAnchorB, localAnchorB); c.globalLength = distance;
+    a.scene->distanceConstraints.push_back(c);
+    return { pushPair(*a.scene, 0, a, b) };
+}
+distance_constraint_handle addDistanceConstraintFromGlobalPoints(scene_entity& a, scene_entity& b, vec3 globalAnchorA, vec3 globalAnchorB)
+{   // physics.cpp:148-157
+    return addDistanceConstraintFromLocalPoints(a, b, inverseTransformPosition(a.transform(), globalAnchorA), inverseTransformPosition(b.transform(), globalAnchorB), len(globalAnchorA - globalAnchorB));
+}
+ball_constraint_handle addBallConstraintFromLocalPoints(scene_entity& a, scene_entity& b, vec3 localAnchorA, vec3 localAnchorB)
+{   // physics.cpp:159-176
+    ball_constraint c; st3(c.localAnchorA, localAnchorA); st3(c.localAnchorB, localAnchorB);
+    a.scene->ballConstraints.push_back(c);
+    return { pushPair(*a.scene, 1, a, b) };
+}
+ball_constraint_handle addBallConstraintFromGlobalPoints(scene_entity& a, scene_entity& b, vec3 globalAnchor)
+{   // physics.cpp:178-186
+    return addBallConstraintFromLocalPoints(a, b, inverseTransformPosition(a.transform(), globalAnchor), inverseTransformPosition(b.transform(), globalAnchor));
+}
+fixed_constraint_handle addFixedConstraintFromGlobalPoints(scene_entity& a, scene_entity& b, vec3 globalAnchor)
+{   // physics.cpp:207-230
+    fixed_constraint c; memset(&c, 0, sizeof(c));
+    const trs& tA = a.transform(); const trs& tB = b.transform();
+    st3(c.localAnchorA, inverseTransformPosition(tA, globalAnchor)); st3(c.localAnchorB, inverseTransformPosition(tB, globalAnchor));
+    st4(c.initialInvRotationDifference, conjugate(tB.rotation) * tA.rotation);
+    a.scene->fixedConstraints.push_back(c);
+    return { pushPair(*a.scene, 2, a, b) };
+}
+hinge_constraint_handle addHingeConstraintFromGlobalPoints(scene_entity& a, scene_entity& b, vec3 globalAnchor, vec3 globalHingeAxis, float minLimit, float maxLimit)
+{   // physics.cpp:232-268
+    hinge_constraint c; memset(&c, 0, sizeof(c));
+    const trs& tA = a.transform(); const trs& tB = b.transform();
+    st3(c.localAnchorA, inverseTransformPosition(tA, globalAnchor)); st3(c.localAnchorB, inverseTransformPosition(tB, globalAnchor));
+    vec3 axisA = inverseTransformDirection(tA, globalHingeAxis), axisB = inverseTransformDirection(tB, globalHingeAxis);
+    st3(c.localHingeAxisA, axisA); st3(c.localHingeAxisB, axisB);
+    vec3 tanA, bitanA; getTangents(axisA, tanA, bitanA);
+    st3(c.localHingeTangentA, tanA); st3(c.localHingeBitangentA, bitanA);
+    st3(c.localHingeTangentB, conjugate(tB.rotation) * (tA.rotation * tanA));
+    c.minRotationLimit = minLimit; c.maxRotationLimit = maxLimit;
+    c.motorType = constraint_velocity_motor; c.motorVelocityOrTargetAngle = 0.f; c.maxMotorTorque = -1.f;
+    a.scene->hingeConstraints.push_back(c);
+    return { pushPair(*a.scene, 3, a, b) };
+}
+cone_twist_constraint_handle addConeTwistConstraintFromGlobalPoints(scene_entity& a, scene_entity& b, vec3 globalAnchor, vec3 globalAxis, float swingLimit, float twistLimit)
+{   // physics.cpp:270-310
+    cone_twist_constraint c; memset(&c, 0, sizeof(c));
+    const trs& tA = a.transform(); const trs& tB = b.transform();
+    st3(c.localAnchorA, inverseTransformPosition(tA, globalAnchor)); st3(c.localAnchorB, inverseTransformPosition(tB, globalAnchor));
+    c.swingLimit = swingLimit; c.twistLimit = twistLimit;
+    vec3 axisA = inverseTransformDirection(tA, globalAxis), axisB = inverseTransformDirection(tB, globalAxis);
+    st3(c.localLimitAxisA, axisA); st3(c.localLimitAxisB, axisB);
+    vec3 tanA, bitanA; getTangents(axisA, tanA, bitanA);
+    st3(c.localLimitTangentA, tanA); st3(c.localLimitBitangentA, bitanA);
+    st3(c.localLimitTangentB, conjugate(tB.rotation) * (tA.rotation * tanA));
+    c.swingMotorType = constraint_velocity_motor; c.swingMotorVelocityOrTargetAngle = 0.f; c.maxSwingMotorTorque = -1.f; c.swingMotorAxis = 0.f;
+    c.twistMotorType = constraint_velocity_motor; c.twistMotorVelocityOrTargetAngle = 0.f; c.maxTwistMotorTorque = -1.f;
+    a.scene->coneTwistConstraints.push_back(c);
+    return { pushPair(*a.scene, 4, a, b) };
+}
+slider_constraint_handle addSliderConstraintFromGlobalPoints(scene_entity& a, scene_entity& b, vec3 globalAnchor, vec3 globalAxis, float minLimit, float maxLimit)
+{   // physics.cpp:312-342
+    slider_constraint c; memset(&c, 0, sizeof(c));
+    const trs& tA = a.transform(); const trs& tB = b.transform();
+    st3(c.localAnchorA, inverseTransformPosition(tA, globalAnchor)); st3(c.localAnchorB, inverseTransformPosition(tB, globalAnchor));
+    st3(c.localAxisA, inverseTransformDirection(tA, globalAxis));
+    st4(c.initialInvRotationDifference, conjugate(tB.rotation) * tA.rotation);
+    c.negDistanceLimit = minLimit; c.posDistanceLimit = maxLimit;
+    c.motorType = constraint_velocity_motor; c.motorVelocityOrTargetDistance = 0.f; c.maxMotorForce = -1.f;
+    a.scene->sliderConstraints.push_back(c);
+    return { pushPair(*a.scene, 5, a, b) };
+}
+
+// ------------------------------------------------------------------------------------------------------ ragdoll
+static inline float deg2rad(float d) { return d * (B200_PI / 180.f); }   // math.h:15,24
+static vec3 transformPosition(const trs& m, vec3 pos) { return m.rotation * (m.scale * pos) + m.position; }   // math.cpp:518-521
+static vec3 transformDirection(const trs& m, vec3 dir) { return m.rotation * dir; }
+
+void humanoid_ragdoll::initialize(game_scene& scene, vec3 initialHipPosition, float initialRotation)
+{   // ragdoll.cpp:10-135 : same body parts, shapes, joints and order
+    const float scale = 0.42f;
+    const bool kin = false; const float gf = 1.f;
+    physics_material material = { physics_material_type_flesh, 0.2f, 1.f, 985.f };
+    const vec3 Z = mk3(0.f, 0.f, 1.f);
+    struct Part { const char* name; trs t; };
+    Part parts[14] = {
+        { "Torso", makeTrs(scale * mk3(0.f, 0.f, 0.f)) },
+        { "Head", makeTrs(scale * mk3(0.f, 1.45f, 0.f)) },
+        { "Left upper arm", makeTrs(scale * mk3(-0.6f, 0.75f, 0.f), quatAxisAngle(Z, deg2rad(-30.f))) },
+        { "Left lower arm", makeTrs(scale * mk3(-0.884f, 0.044f, -0.043f), quatAxisAngle(Z, deg2rad(-20.f))) },
+        { "Right upper arm", makeTrs(scale * mk3(0.6f, 0.75f, 0.f), quatAxisAngle(Z, deg2rad(30.f))) },
+        { "Right lower arm", makeTrs(scale * mk3(0.884f, 0.044f, -0.043f), quatAxisAngle(Z, deg2rad(20.f))) },
+        { "Left upper leg", makeTrs(scale * mk3(-0.371f, -0.812f, 0.f), quatAxisAngle(Z, deg2rad(-10.f))) },
+        { "Left lower leg", makeTrs(scale * mk3(-0.452f, -1.955f, 0.f), quatAxisAngle(Z, deg2rad(-3.5f))) },
+        { "Left foot", makeTrs(scale * mk3(-0.498f, -2.585f, -0.18f)) },
+        { "Left toes", makeTrs(scale * mk3(-0.498f, -2.585f, -0.637f)) },
+        { "Right upper leg", makeTrs(scale * mk3(0.371f, -0.812f, 0.f), quatAxisAngle(Z, deg2rad(10.f))) },
+        { "Right lower leg", makeTrs(scale * mk3(0.452f, -1.955f, 0.f), quatAxisAngle(Z, deg2rad(3.5f))) },
+        { "Right foot", makeTrs(scale * mk3(0.498f, -2.585f, -0.18f)) },
+        { "Right toes", makeTrs(scale * mk3(0.498f, -2.585f, -0.637f)) },
+    };
+    enum { torso, head, lUpperArm, lLowerArm, rUpperArm, rLowerArm, lUpperLeg, lLowerLeg, lFoot, lToes, rUpperLeg, rLowerLeg, rFoot, rToes };
+    auto cap = [&](vec3 a, vec3 b, float r) { bounding_capsule c = { scale * a, scale * b, scale * r }; return collider_component::asCapsule(c, material); };
+    for (int i = 0; i < 14; ++i) { bodyParts[i] = scene.createEntity(parts[i].name); bodyParts[i].addTransform(parts[i].t.position, parts[i].t.rotation); }
+    bodyParts[torso].addCollider(cap(mk3(-0.2f, 0.f, 0.f), mk3(0.2f, 0.f, 0.f), 0.25f)).addCollider(cap(mk3(-0.16f, 0.32f, 0.f), mk3(0.16f, 0.32f, 0.f), 0.2f))
+                    .addCollider(cap(mk3(-0.14f, 0.62f, 0.f), mk3(0.14f, 0.62f, 0.f), 0.22f)).addCollider(cap(mk3(-0.14f, 0.92f, 0.f), mk3(0.14f, 0.92f, 0.f), 0.2f)).addRigidBody(kin, gf);
+    bodyParts[head].addCollider(cap(mk3(0.f, -0.075f, 0.f), mk3(0.f, 0.075f, 0.f), 0.25f)).addRigidBody(kin, gf);
+    bodyParts[lUpperArm].addCollider(cap(mk3(0.f, -0.2f, 0.f), mk3(0.f, 0.2f, 0.f), 0.15f)).addRigidBody(kin, gf);
+    bodyParts[lLowerArm].addCollider(cap(mk3(0.f, -0.2f, 0.f), mk3(0.f, 0.2f, 0.f), 0.15f)).addRigidBody(kin, gf);
+    bodyParts[rUpperArm].addCollider(cap(mk3(0.f, -0.2f, 0.f), mk3(0.f, 0.2f, 0.f), 0.15f)).addRigidBody(kin, gf);
+    bodyParts[rLowerArm].addCollider(cap(mk3(0.f, -0.2f, 0.f), mk3(0.f, 0.2f, 0.f), 0.15f)).addRigidBody(kin, gf);
+    bodyParts[lUpperLeg].addCollider(cap(mk3(0.f, -0.3f, 0.f), mk3(0.f, 0.3f, 0.f), 0.25f)).addRigidBody(kin, gf);
+    bodyParts[lLowerLeg].addCollider(cap(mk3(0.f, -0.3f, 0.f), mk3(0.f, 0.3f, 0.f), 0.18f)).addRigidBody(kin, gf);
+    bodyParts[lFoot].addCollider(collider_component::asAABB(bounding_box::fromCenterRadius(scale * mk3(0.f), scale * mk3(0.1587f, 0.1f, 0.3424f)), material)).addRigidBody(kin, gf);
+    bodyParts[lToes].addCollider(cap(mk3(-0.0587f, 0.f, 0.f), mk3(0.0587f, 0.f, 0.f), 0.1f)).addRigidBody(kin, gf);
+    bodyParts[rUpperLeg].addCollider(cap(mk3(0.f, -0.3f, 0.f), mk3(0.f, 0.3f, 0.f), 0.25f)).addRigidBody(kin, gf);
+    bodyParts[rLowerLeg].addCollider(cap(mk3(0.f, -0.3f, 0.f), mk3(0.f, 0.3f, 0.f), 0.18f)).addRigidBody(kin, gf);
+    bodyParts[rFoot].addCollider(collider_component::asAABB(bounding_box::fromCenterRadius(scale * mk3(0.f), scale * mk3(0.1587f, 0.1f, 0.3424f)), material)).addRigidBody(kin, gf);
+    bodyParts[rToes].addCollider(cap(mk3(-0.0587f, 0.f, 0.f), mk3(0.0587f, 0.f, 0.f), 0.1f)).addRigidBody(kin, gf);
+
+    const trs* T[14]; for (int i = 0; i < 14; ++i) T[i] = &parts[i].t;
+    addConeTwistConstraintFromGlobalPoints(bodyParts[torso], bodyParts[head], transformPosition(*T[torso], scale * mk3(0.f, 1.2f, 0.f)), mk3(0.f, 1.f, 0.f), deg2rad(50.f), deg2rad(90.f));
+    addConeTwistConstraintFromGlobalPoints(bodyParts[torso], bodyParts[lUpperArm], transformPosition(*T[torso], scale * mk3(-0.4f, 1.f, 0.f)), mk3(-1.f, 0.f, 0.f), deg2rad(130.f), deg2rad(90.f));
+    addHingeConstraintFromGlobalPoints(bodyParts[lUpperArm], bodyParts[lLowerArm], transformPosition(*T[lUpperArm], scale * mk3(0.f, -0.42f, 0.f)), normalize(mk3(1.f, 0.f, 1.f)), deg2rad(-5.f), deg2rad(85.f));
+    addConeTwistConstraintFromGlobalPoints(bodyParts[torso], bodyParts[rUpperArm], transformPosition(*T[torso], scale * mk3(0.4f, 1.f, 0.f)), mk3(1.f, 0.f, 0.f), deg2rad(130.f), deg2rad(90.f));
+    addHingeConstraintFromGlobalPoints(bodyParts[rUpperArm], bodyParts[rLowerArm], transformPosition(*T[rUpperArm], scale * mk3(0.f, -0.42f, 0.f)), normalize(mk3(1.f, 0.f, -1.f)), deg2rad(-5.f), deg2rad(85.f));
+    addConeTwistConstraintFromGlobalPoints(bodyParts[torso], bodyParts[lUpperLeg], transformPosition(*T[torso], scale * mk3(-0.3f, -0.25f, 0.f)), transformDirection(*T[lUpperLeg], mk3(0.f, -1.f, 0.f)), -1.f, deg2rad(30.f));
+    addHingeConstraintFromGlobalPoints(bodyParts[lUpperLeg], bodyParts[lLowerLeg], transformPosition(*T[lUpperLeg], scale * mk3(0.f, -0.6f, 0.f)), mk3(1.f, 0.f, 0.f), deg2rad(-90.f), deg2rad(5.f));
+    addConeTwistConstraintFromGlobalPoints(bodyParts[lLowerLeg], bodyParts[lFoot], transformPosition(*T[lLowerLeg], scale * mk3(0.f, -0.52f, 0.f)), transformDirection(*T[lLowerLeg], mk3(0.f, -1.f, 0.f)), deg2rad(75.f), deg2rad(20.f));
+    addHingeConstraintFromGlobalPoints(bodyParts[lFoot], bodyParts[lToes], transformPosition(*T[lFoot], scale * mk3(0.f, 0.f, -0.36f)), mk3(1.f, 0.f, 0.f), deg2rad(-45.f), deg2rad(45.f));
+    addConeTwistConstraintFromGlobalPoints(bodyParts[torso], bodyParts[rUpperLeg], transformPosition(*T[torso], scale * mk3(0.3f, -0.25f, 0.f)), transformDirection(*T[rUpperLeg], mk3(0.f, -1.f, 0.f)), -1.f, deg2rad(30.f));
+    addHingeConstraintFromGlobalPoints(bodyParts[rUpperLeg], bodyParts[rLowerLeg], transformPosition(*T[rUpperLeg], scale * mk3(0.f, -0.6f, 0.f)), mk3(1.f, 0.f, 0.f), deg2rad(-90.f), deg2rad(5.f));
+    addConeTwistConstraintFromGlobalPoints(bodyParts[rLowerLeg], bodyParts[rFoot], transformPosition(*T[rLowerLeg], scale * mk3(0.f, -0.52f, 0.f)), transformDirection(*T[rLowerLeg], mk3(0.f, -1.f, 0.f)), deg2rad(75.f), deg2rad(20.f));
+    addHingeConstraintFromGlobalPoints(bodyParts[rFoot], bodyParts[rToes], transformPosition(*T[rFoot], scale * mk3(0.f, 0.f, -0.36f)), mk3(1.f, 0.f, 0.f), deg2rad(-45.f), deg2rad(45.f));
+
+    // place the whole figure (ragdoll.cpp:105-113)
+    quat rotation = quatAxisAngle(mk3(0.f, 1.f, 0.f), initialRotation);
+    for (int i = 0; i < 14; ++i)
+    {
+        trs& t = bodyParts[i].transform();
+        t.rotation = rotation * t.rotation;
+        t.position = rotation * t.position + initialHipPosition;
+        int rb = scene.entities[bodyParts[i].handle].rigidBody;
+        scene.physicsTransform0[rb] = scene.physicsTransform1[rb] = t;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------ the step
+static inline quat nlerpQuat(quat l, quat u, float t)
+{   // math.h:670-673 : lerp of the 4-vectors, then normalise
+    return normalize(mkq(l.x + t * (u.x - l.x), l.y + t * (u.y - l.y), l.z + t * (u.z - l.z), l.w + t * (u.w - l.w)));
+}
+
+static int ensureContext(game_scene& scene)
+{
+    const uint32_t nb = (uint32_t)scene.rigidBodies.size(), nc = (uint32_t)scene.colliders.size();
+    size_t nj = 1; for (int k = 0; k < 6; ++k) if (scene.constraintEntities[k].size() > nj) nj = scene.constraintEntities[k].size();
+    if (scene.ctx) return 0;
+    b200phys_config cfg; memset(&cfg, 0, sizeof(cfg));
+    cfg.device = 0; cfg.maxBodies = nb + (nb >> 2) + 16; cfg.maxColliders = nc + (nc >> 2) + 16; cfg.maxTransforms = (uint32_t)scene.entities.size() + 1; cfg.maxJointsPerKind = (uint32_t)nj + 16;
+    scene.collidersDirty = scene.jointsDirty = scene.hullsDirty = true;
+    return b200phys_create(&cfg, &scene.ctx);
+}
+
+// physicsStepInternal (physics.cpp:1180-1362): gather pools -> C ABI -> scatter results
+static int physicsStepInternal(game_scene& scene, const physics_settings& settings, float dt)
+{
+    if (scene.rigidBodies.empty()) return 0;   // physics.cpp:1186-1189
+    int r = ensureContext(scene); if (r) return r;
+    if (scene.hullsDirty)
+    {
+        std::vector<float> v; std::vector<uint32_t> o; scene.gatherHulls(v, o);
+        r = b200phys_set_hulls(scene.ctx, v.data(), o.data(), (uint32_t)o.size() - 1); if (r) return r;
+        scene.hullsDirty = false;
+    }
+    std::vector<b200phys_body> bodies; scene.gatherBodies(bodies);
+    r = b200phys_upload_bodies(scene.ctx, bodies.data(), (uint32_t)bodies.size()); if (r) return r;
+    if (scene.collidersDirty)
+    {
+        std::vector<b200phys_collider> cols; std::vector<b200phys_transform> xf; scene.gatherColliders(cols, xf);
+        r = b200phys_upload_transforms(scene.ctx, xf.data(), (uint32_t)xf.size()); if (r) return r;
+        r = b200phys_upload_colliders(scene.ctx, cols.data(), (uint32_t)cols.size()); if (r) return r;
+        scene.collidersDirty = false;
+    }
+    {   // joint parameters (motor targets etc.) are host-mutable between steps (learned_locomotion.cpp:73-91): re-upload every step
+        for (int k = 0; k < 6; ++k)
+        {
+            std::vector<uint8_t> s; std::vector<b200phys_body_pair> p; scene.gatherJoints(k, s, p);
+            r = b200phys_upload_joints(scene.ctx, k, s.data(), p.data(), (uint32_t)p.size()); if (r) return r;
+        }
+        scene.jointsDirty = false;
+    }
+    r = b200phys_step(scene.ctx, dt, settings.numRigidSolverIterations, settings.exactConstraintOrder ? B200PHYS_STEP_EXACT_ORDER : B200PHYS_STEP_FAST); if (r) return r;
+    std::vector<b200phys_body_state> states(bodies.size());
+    r = b200phys_download_bodies(scene.ctx, states.data(), (uint32_t)states.size()); if (r) return r;
+    scene.scatterBodyStates(states.data(), (uint32_t)states.size());
+    r = b200phys_get_stats(scene.ctx, &scene.lastStats);
+    return r;
+}
+
+int physicsStep(game_scene& scene, memory_arena&, float& timer, const physics_settings& settings, float dt)
+{   // physics.cpp:1364-1413
+    int rc = 0;
+    if (settings.fixedFrameRate)
+    {
+        const float h = 1.f / (float)settings.frameRate;
+        timer += dt;
+        uint32_t its = 0;
+        if (timer >= h)
+        {
+            for (size_t i = 0; i < scene.rigidBodies.size(); ++i) scene.physicsTransform0[i] = scene.physicsTransform1[i];
+            while (timer >= h && its++ < settings.maxPhysicsIterationsPerFrame)
+            {
+                int r = physicsStepInternal(scene, settings, h); if (r && !rc) rc = r;
+                timer -= h;
+            }
+        }
+        if (timer >= h) timer = fmodf(timer, h);   // dropping physics frames
+        const float t = timer / h;
+        for (size_t i = 0; i < scene.rigidBodies.size(); ++i)
+        {
+            trs& out = scene.entities[scene.rigidBodyEntity[i]].transform; const trs& a = scene.physicsTransform0[i]; const trs& b = scene.physicsTransform1[i];
+            out.position = lerp(a.position, b.position, t);
+            out.rotation = nlerpQuat(a.rotation, b.rotation, t);
+            out.scale = lerp(a.scale, b.scale, t);
+        }
+    }
+    else
+    {
+        rc = physicsStepInternal(scene, settings, dt);
+        for (size_t i = 0; i < scene.rigidBodies.size(); ++i) scene.entities[scene.rigidBodyEntity[i]].transform = scene.physicsTransform1[i];
+    }
+    return rc;
+}
+
+} // namespace b200host

@@ -1,0 +1,187 @@
+// physics_host.h -- host-side C++ mirror of the reference's physics API surface for the rigid-body step
+// (pkurth/D3D12Renderer src/physics/physics.h, rigid_body.h, constraints.h, bounding_volumes.h, ragdoll.h).
+//
+// Same names, argument meaning and index conventions as the reference so that scene-building code and the call
+// `physicsStep(scene, arena, timer, settings, dt)` read like the original; the step itself is NOT computed here: it is
+// gathered into the flat arrays of include/b200phys.h and executed by the CUDA library through the C ABI.
+// The reference stores components in EnTT pools; this mirror uses flat vectors with the same iteration-order semantics
+// (SURVEY.md 3.5): collider index = reverse creation order, rigid-body index = creation (storage) order, joint arrays in
+// storage order. INTEGRATION.md shows the gather/scatter a maintainer would write against real EnTT pools instead.
+#pragma once
+#include <cstdint>
+#include <functional>
+#include <string>
+#include <vector>
+#include "../csrc/b200_math.cuh"       // the same fp32 helpers the kernels use (host + device)
+#include "../../include/b200phys.h"
+
+namespace b200host {
+
+using vec3 = b200::f3;
+using quat = b200::q4;
+using mat3 = b200::m3;
+
+struct trs { quat rotation; vec3 position; vec3 scale; };   // math.h:494-504
+inline trs makeTrs(vec3 position, quat rotation = b200::qIdentity(), vec3 scale = b200::mk3(1.f)) { trs t; t.rotation = rotation; t.position = position; t.scale = scale; return t; }
+
+#define GRAVITY -9.81f   /* physics.h:11 */
+
+// physics.h:20-47
+enum physics_material_type { physics_material_type_none = -1, physics_material_type_metal, physics_material_type_wood, physics_material_type_flesh, physics_material_type_count };
+struct physics_material { physics_material_type type; float restitution; float friction; float density; };
+
+// physics.h:49-70
+enum physics_object_type : uint8_t { physics_object_type_rigid_body, physics_object_type_static_collider, physics_object_type_force_field, physics_object_type_trigger, physics_object_type_count };
+enum collider_type : uint8_t { collider_type_sphere, collider_type_capsule, collider_type_cylinder, collider_type_aabb, collider_type_obb, collider_type_hull, collider_type_count };
+
+// bounding_volumes.h:30-231
+struct bounding_sphere { vec3 center; float radius; };
+struct bounding_capsule { vec3 positionA; vec3 positionB; float radius; };
+struct bounding_cylinder { vec3 positionA; vec3 positionB; float radius; };
+struct bounding_box
+{
+    vec3 minCorner, maxCorner;
+    static bounding_box fromCenterRadius(vec3 center, vec3 radius) { bounding_box b; b.minCorner = center - radius; b.maxCorner = center + radius; return b; }
+    static bounding_box fromMinMax(vec3 mn, vec3 mx) { bounding_box b; b.minCorner = mn; b.maxCorner = mx; return b; }
+};
+struct bounding_oriented_box { quat rotation; vec3 center; vec3 radius; };
+struct bounding_hull { quat rotation; vec3 position; uint32_t geometryIndex; };
+struct indexed_triangle32 { uint32_t a, b, c; };
+
+// physics.h:13-18
+struct physics_properties { mat3 inertia; vec3 cog; float mass; };
+
+typedef uint32_t entity_handle;
+static const entity_handle null_entity = 0xFFFFFFFFu;
+
+// physics.h:84-171
+struct collider_union
+{
+    union { bounding_sphere sphere; bounding_capsule capsule; bounding_cylinder cylinder; bounding_box aabb; bounding_oriented_box obb; bounding_hull hull; };
+    physics_material material;
+    collider_type type;
+    collider_union() {}
+    physics_properties calculatePhysicsProperties(const struct game_scene& scene) const;   // physics.cpp:1416-1588
+};
+struct collider_component : collider_union
+{
+    static collider_component asSphere(bounding_sphere s, physics_material m) { collider_component r; r.sphere = s; r.type = collider_type_sphere; r.material = m; return r; }
+    static collider_component asCapsule(bounding_capsule c, physics_material m) { collider_component r; r.capsule = c; r.type = collider_type_capsule; r.material = m; return r; }
+    static collider_component asCylinder(bounding_cylinder c, physics_material m) { collider_component r; r.cylinder = c; r.type = collider_type_cylinder; r.material = m; return r; }
+    static collider_component asAABB(bounding_box b, physics_material m) { collider_component r; r.aabb = b; r.type = collider_type_aabb; r.material = m; return r; }
+    static collider_component asOBB(bounding_oriented_box b, physics_material m) { collider_component r; r.obb = b; r.type = collider_type_obb; r.material = m; return r; }
+    static collider_component asHull(bounding_hull h, physics_material m) { collider_component r; r.hull = h; r.type = collider_type_hull; r.material = m; return r; }
+    entity_handle parentEntity = null_entity;
+    entity_handle nextEntity = null_entity;     // next collider of the same parent (most recently added first, scene.h:53-56)
+};
+
+// rigid_body.h:18-46
+struct rigid_body_component
+{
+    rigid_body_component() : rigid_body_component(true, 1.f) {}
+    rigid_body_component(bool kinematic, float gravityFactor = 1.f, float linearDamping = 0.4f, float angularDamping = 0.4f);
+    vec3 localCOGPosition; float invMass; mat3 invInertia;
+    float gravityFactor, linearDamping, angularDamping;
+    vec3 linearVelocity, angularVelocity, forceAccumulator, torqueAccumulator;
+};
+
+// constraints.h:41-45
+enum constraint_motor_type { constraint_velocity_motor, constraint_position_motor };
+// constraints.h:73-80,129-135,175-183,229-257,346-380,497-520 : the boundary structs ARE these structs (same field order)
+typedef b200phys_distance_joint distance_constraint;
+typedef b200phys_ball_joint ball_constraint;
+typedef b200phys_fixed_joint fixed_constraint;
+typedef b200phys_hinge_joint hinge_constraint;
+typedef b200phys_cone_twist_joint cone_twist_constraint;
+typedef b200phys_slider_joint slider_constraint;
+struct distance_constraint_handle { uint32_t index; };
+struct ball_constraint_handle { uint32_t index; };
+struct fixed_constraint_handle { uint32_t index; };
+struct hinge_constraint_handle { uint32_t index; };
+struct cone_twist_constraint_handle { uint32_t index; };
+struct slider_constraint_handle { uint32_t index; };
+
+// physics.h:382-400 (callbacks belong to the event layer, a "next" row)
+struct physics_settings
+{
+    bool fixedFrameRate = true;
+    uint32_t frameRate = 120;
+    uint32_t maxPhysicsIterationsPerFrame = 4;
+    uint32_t numRigidSolverIterations = 30;
+    uint32_t numClothVelocityIterations = 0, numClothPositionIterations = 1, numClothDriftIterations = 0;
+    bool simdBroadPhase = true, simdNarrowPhase = true, simdConstraintSolver = true;   // accepted, ignored: one CUDA path
+    bool exactConstraintOrder = false;   // extension: B200PHYS_STEP_EXACT_ORDER (canonical Gauss-Seidel order)
+};
+
+struct memory_arena {};   // the reference's per-step scratch source (core/memory.h:52-112); device scratch lives in the context
+
+struct bounding_hull_geometry { std::vector<vec3> vertices; std::vector<indexed_triangle32> faces; };
+
+struct game_scene;
+struct scene_entity
+{
+    entity_handle handle = null_entity; game_scene* scene = nullptr;
+    explicit operator bool() const { return handle != null_entity; }
+    scene_entity& addTransform(vec3 position, quat rotation = b200::qIdentity(), vec3 scale = b200::mk3(1.f));                 // addComponent<transform_component>
+    scene_entity& addCollider(const collider_component& c);                                                                     // addComponent<collider_component>
+    scene_entity& addRigidBody(bool kinematic, float gravityFactor = 1.f, float linearDamping = 0.4f, float angularDamping = 0.4f); // addComponent<rigid_body_component>
+    rigid_body_component& rigidBody();
+    trs& transform();
+};
+
+struct game_scene
+{
+    struct entity_data
+    {
+        std::string name; bool hasTransform = false; trs transform;
+        int32_t rigidBody = -1;                 // index into rigidBodies (storage order)
+        entity_handle firstColliderEntity = null_entity; uint32_t numColliders = 0;
+    };
+    std::vector<entity_data> entities;
+    std::vector<rigid_body_component> rigidBodies; std::vector<entity_handle> rigidBodyEntity;
+    std::vector<trs> physicsTransform0, physicsTransform1;      // per rigid body (rigid_body.h:48-58)
+    std::vector<collider_component> colliders;                  // creation order; world index = reverse (physics.cpp:635-641)
+    std::vector<bounding_hull_geometry> hullGeometries;
+    std::vector<distance_constraint> distanceConstraints; std::vector<ball_constraint> ballConstraints; std::vector<fixed_constraint> fixedConstraints;
+    std::vector<hinge_constraint> hingeConstraints; std::vector<cone_twist_constraint> coneTwistConstraints; std::vector<slider_constraint> sliderConstraints;
+    std::vector<b200phys_body_pair> constraintEntities[6];      // (entityA, entityB) per joint, storage order
+
+    scene_entity createEntity(const char* name);
+    uint32_t allocateBoundingHullGeometry(const vec3* vertices, uint32_t numVertices, const indexed_triangle32* triangles, uint32_t numTriangles); // physics.h:207
+    void recalculateProperties(entity_handle e);               // rigid_body.cpp:29-81
+
+    // ---- boundary (what the EnTT shim of INTEGRATION.md does with real pools)
+    void gatherBodies(std::vector<b200phys_body>& out) const;
+    void gatherColliders(std::vector<b200phys_collider>& outColliders, std::vector<b200phys_transform>& outTransforms) const;
+    void gatherJoints(int kind, std::vector<uint8_t>& outStructs, std::vector<b200phys_body_pair>& outPairs) const;
+    void gatherHulls(std::vector<float>& verts, std::vector<uint32_t>& offsets) const;
+    void scatterBodyStates(const b200phys_body_state* states, uint32_t count);
+
+    b200phys_context* ctx = nullptr;  // lazily created device context (registry context variable in the reference's terms)
+    bool collidersDirty = true, jointsDirty = true, hullsDirty = true;
+    b200phys_stats lastStats;
+    ~game_scene();
+};
+
+// physics.h:217-235 (entities must have transform_component; anchors in world space)
+distance_constraint_handle addDistanceConstraintFromLocalPoints(scene_entity& a, scene_entity& b, vec3 localAnchorA, vec3 localAnchorB, float distance);
+distance_constraint_handle addDistanceConstraintFromGlobalPoints(scene_entity& a, scene_entity& b, vec3 globalAnchorA, vec3 globalAnchorB);
+ball_constraint_handle addBallConstraintFromLocalPoints(scene_entity& a, scene_entity& b, vec3 localAnchorA, vec3 localAnchorB);
+ball_constraint_handle addBallConstraintFromGlobalPoints(scene_entity& a, scene_entity& b, vec3 globalAnchor);
+fixed_constraint_handle addFixedConstraintFromGlobalPoints(scene_entity& a, scene_entity& b, vec3 globalAnchor);
+hinge_constraint_handle addHingeConstraintFromGlobalPoints(scene_entity& a, scene_entity& b, vec3 globalAnchor, vec3 globalHingeAxis, float minLimit = 1.f, float maxLimit = -1.f);
+cone_twist_constraint_handle addConeTwistConstraintFromGlobalPoints(scene_entity& a, scene_entity& b, vec3 globalAnchor, vec3 globalAxis, float swingLimit, float twistLimit);
+slider_constraint_handle addSliderConstraintFromGlobalPoints(scene_entity& a, scene_entity& b, vec3 globalAnchor, vec3 globalAxis, float minLimit = 1.f, float maxLimit = -1.f);
+
+// ragdoll.h:7-60 (14 bodies, 17 colliders, 7 cone-twist + 6 hinge joints)
+struct humanoid_ragdoll
+{
+    scene_entity bodyParts[14];
+    void initialize(game_scene& scene, vec3 initialHipPosition, float initialRotation = 0.f);   // ragdoll.cpp:10-135
+    static humanoid_ragdoll create(game_scene& scene, vec3 initialHipPosition, float initialRotation = 0.f) { humanoid_ragdoll r; r.initialize(scene, initialHipPosition, initialRotation); return r; }
+};
+
+// physics.h:405 : returns 0 or the C ABI error code of the failing call (the reference returns void)
+int physicsStep(game_scene& scene, memory_arena& arena, float& timer, const physics_settings& settings, float dt);
+
+} // namespace b200host

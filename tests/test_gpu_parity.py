@@ -129,3 +129,56 @@ def test_pairs_match_brute_force():
     r = run_both(sc, iterations=1)
     brute = r["oracle"].brute_pairs()
     assert np.array_equal(np.sort(brute, order=["a", "b"]), r["gpu_pairs"])
+
+
+# ------------------------------------------------------------------------------------------------ convex shapes, joints
+from d3d12renderer_b200 import host
+
+
+@pytest.mark.parametrize("flags", [abi.STEP_FAST, abi.STEP_EXACT_ORDER])
+def test_mixed_primitives_pile(flags):
+    """BASELINE config 3 in miniature: spheres, capsules, OBBs and convex hulls interpenetrating on a tight lattice. Exercises
+    the analytic, SAT + clipping and GJK + EPA routines; narrow phase uses only + - * / sqrt, so contacts must agree exactly."""
+    sc = host.build_scene(host.CONFIG_MIXED_PILE, 6, 5, 6, seed=1578123, spacing=0.72)
+    r = run_both(sc, iterations=10, flags=flags)
+    check_detection(r, contact_tol=1e-6)
+    ns = r["oracle"].narrow_stats()
+    assert r["stats"].epaOverflows == 0 and ns["epaOutOfMemory"] == 0 and r["stats"].gjkIterationCaps == ns["gjkIterCap"]
+    assert r["stats"].numContacts > 300
+    assert_states_close(r["gpu_states"], r["ref_states"], 1e-4)
+
+
+def test_mixed_primitives_trajectory():
+    sc = host.build_scene(host.CONFIG_MIXED_PILE, 5, 4, 5, seed=99, spacing=0.8)
+    r = run_both(sc, iterations=10, steps=8)
+    check_detection(r, contact_tol=1e-5)
+    assert_states_close(r["gpu_states"], r["ref_states"], 1e-4)
+
+
+@pytest.mark.parametrize("flags", [abi.STEP_FAST, abi.STEP_EXACT_ORDER])
+def test_ragdolls_joints_and_contacts(flags):
+    """BASELINE config 4 in miniature: humanoid ragdolls (hinge + cone-twist chains, capsule / box colliders) falling on the
+    ground; 25 steps so that limits, jointed-neighbour contacts and ground contacts are all active."""
+    sc = host.build_scene(host.CONFIG_RAGDOLLS, 3, 1, 3, seed=20260924, mode=0, spacing=2.5)
+    assert len(sc["joints"][3][0]) == 9 * 6 and len(sc["joints"][4][0]) == 9 * 7
+    r = run_both(sc, iterations=10, flags=flags, steps=25)
+    check_detection(r, contact_tol=1e-5)
+    assert r["stats"].numContacts > 20
+    # joints use atan2 / acos / sin / cos whose device and glibc versions differ in the last ulp: the gate, not bit-equality
+    assert_states_close(r["gpu_states"], r["ref_states"], 1e-4)
+
+
+def test_host_mirror_physics_step_matches_abi():
+    """physicsStep() of the host mirror (fixed 120 Hz sub-stepping + interpolation, reference physics.cpp:1364-1413) drives the
+    same CUDA path: after one frame of exactly one sub-step the physics_transform1 poses equal a direct C-ABI step."""
+    sc = host.build_scene(host.CONFIG_SPHERES_ON_GROUND, 8, 1, 8, seed=15681923, mode=1, spacing=1.25)
+    hs = sc["host_scene"]
+    st = make_stepper(sc)
+    st.step(DT, 30, abi.STEP_FAST)
+    direct = st.download_bodies()
+    timer = hs.physics_step(0.0, float(DT), iterations=30)
+    via_host = hs.arrays()["bodies"]
+    assert abs(timer) < 1e-6
+    assert np.array_equal(via_host["position"], direct["position"]) and np.array_equal(via_host["linearVelocity"], direct["linearVelocity"])
+    # interpolation factor 0 after exactly one sub-step: the render transform still shows the OLD pose (SURVEY fact 9)
+    assert np.allclose(hs.render_transforms()[:, 4:7], sc["bodies"]["position"])
