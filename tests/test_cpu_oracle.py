@@ -1,0 +1,231 @@
+"""CPU-only tests (no GPU): the parity oracle against hand-derived known answers and independent cross-checks, the host
+mirror's scene construction against the oracle, and the C ABI surface of the CUDA library.
+
+The reference ships no tests, golden vectors or fixtures, so parity is pinned by
+ (1) closed-form known answers derived from the cited formulas,
+ (2) brute-force pair enumeration as an independent check of the sweep-and-prune restatement,
+ (3) invariants the reference asserts (depth >= 0, accumulated normal impulse >= 0, |tangent impulse| <= mu * normal impulse),
+ (4) frozen oracle outputs under tests/golden/ (made by tests/golden/make_golden.py)."""
+import ctypes
+import json
+import os
+
+import numpy as np
+import pytest
+
+from d3d12renderer_b200 import abi, scenes, host
+import oracle_lib
+
+DT = np.float32(1.0 / 120.0)
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def world_collider(ctype, shape, restitution=0.1, friction=0.5):
+    c = np.zeros(1, dtype=abi.collider_dtype)
+    c["shape"][0, :len(shape)] = shape
+    c["type"] = ctype; c["restitution"] = restitution; c["friction"] = friction; c["density"] = 1.0
+    c["objectType"] = abi.OBJ_STATIC; c["parentTransform"] = abi.NO_TRANSFORM
+    return c
+
+
+# ---------------------------------------------------------------------------------------------------- known answers
+def test_appendix_c_single_sphere_known_answer():
+    sc = scenes.spheres_on_ground(1, mode="rest")
+    sc["bodies"]["position"][0] = (0, 0.45, 0)
+    assert abs(float(sc["bodies"]["invMass"][0]) - 1.9098593) < 1e-6 and abs(float(sc["bodies"]["invInertia"][0, 0]) - 19.098593) < 1e-5
+    o = oracle_lib.Oracle(sc)
+    o.step(DT, 10)
+    c, b = o.contacts()
+    assert len(c) == 1 and tuple(b[0]) == (0, 1)
+    assert c["friction_restitution"][0] == 0xB5041999
+    assert tuple(c["normal"][0]) == (0.0, -1.0, 0.0)
+    assert abs(float(c["penetrationDepth"][0]) - 0.050000012) < 1e-9
+    assert abs(float(c["point"][0][1]) + 0.025000006) < 1e-9
+    s = o.body_states()[0]
+    assert abs(float(s["linearVelocity"][1]) - 0.59614736) < 1e-7
+    assert abs(float(s["position"][1]) - 0.4549679) < 1e-7
+    assert tuple(s["rotation"]) == (0.0, 0.0, 0.0, 1.0) and not np.any(s["angularVelocity"])
+
+
+def test_free_fall_velocity_known_answer():
+    """v.y after force integration + damping (rigid_body.cpp:105-118): -9.81/120 / (1 + 0.4/120)."""
+    sc = scenes.spheres_on_ground(1, mode="drop")
+    sc["bodies"]["position"][0] = (0, 50.0, 0)
+    o = oracle_lib.Oracle(sc); o.step(DT, 10)
+    assert abs(float(o.body_states()[0]["linearVelocity"][1]) + 0.08147841) < 1e-8
+
+
+def test_sphere_sphere_contact_known_answer():
+    """Two unit spheres 1.5 apart: normal (1,0,0), depth 0.5, point midway (collision_narrow.cpp:376-396)."""
+    o = oracle_lib.Oracle()
+    n, normal, pd = o.collide_pair(world_collider(abi.SPHERE, [0, 0, 0, 1.0]), world_collider(abi.SPHERE, [1.5, 0, 0, 1.0]))
+    assert n == 1
+    # equal types swap (collision_narrow.cpp:2374): A is the second collider, so the normal points from (1.5,0,0) to the origin
+    assert tuple(normal) == (-1.0, 0.0, 0.0) and abs(pd[0][3] - 0.5) < 1e-7 and np.allclose(pd[0][:3], (0.75, 0, 0))
+
+
+def test_sphere_inside_box_and_coincident_spheres_degenerate_cases():
+    o = oracle_lib.Oracle()
+    n, normal, pd = o.collide_pair(world_collider(abi.SPHERE, [0, 0, 0, 0.5]), world_collider(abi.AABB, [-1, -1, -1, 1, 1, 1]))
+    assert n == 1 and tuple(normal) == (0.0, 1.0, 0.0) and abs(pd[0][3] - 0.5) < 1e-7          # centre inside: up normal, depth = r (:464-467)
+    n, normal, pd = o.collide_pair(world_collider(abi.SPHERE, [1, 2, 3, 0.5]), world_collider(abi.SPHERE, [1, 2, 3, 0.25]))
+    assert n == 1 and tuple(normal) == (0.0, 1.0, 0.0) and abs(pd[0][3] - 0.75) < 1e-7        # coincident centres (:382-386)
+
+
+def test_box_box_four_contacts_and_signed_depth_quirk():
+    """AABB-AABB always returns 4 contacts with depth = p[minAxis] * sign(d) (collision_narrow.cpp:1092-1110)."""
+    o = oracle_lib.Oracle()
+    a = world_collider(abi.AABB, [-1, -1, -1, 1, 1, 1]); b = world_collider(abi.AABB, [-0.5, 0.8, -0.5, 0.5, 1.8, 0.5])
+    n, normal, pd = o.collide_pair(a, b)
+    assert n == 4 and abs(abs(normal[1]) - 1.0) < 1e-7 and np.allclose(np.abs(pd[:, 3]), 0.2, atol=1e-6)
+    assert len({float(x) for x in pd[:, 3]}) == 1      # all four share one (signed) depth
+
+
+def test_capsule_capsule_parallel_two_contacts():
+    o = oracle_lib.Oracle()
+    n, normal, pd = o.collide_pair(world_collider(abi.CAPSULE, [-1, 0, 0, 1, 0, 0, 0.3]), world_collider(abi.CAPSULE, [-0.5, 0.5, 0, 1.5, 0.5, 0, 0.3]))
+    assert n == 2 and np.allclose(np.abs(normal), (0, 1, 0), atol=1e-6) and np.allclose(pd[:, 3], 0.1, atol=1e-6)
+
+
+def test_gjk_epa_pairs_give_plausible_contacts():
+    """capsule / obb / hull pairs through GJK + EPA: depth within the EPA tolerance (0.01, collision_epa.h:139) of the analytic value."""
+    sc = host.build_scene(host.CONFIG_MIXED_PILE, 1, 1, 1, seed=3, spacing=1.0)
+    o = oracle_lib.Oracle(sc)
+    box = world_collider(abi.AABB, [-2, -1, -2, 2, 0, 2])
+    n, normal, pd = o.collide_pair(world_collider(abi.CAPSULE, [0, 0.2, 0, 0, 1.0, 0, 0.3]), box)     # vertical capsule 0.1 into the top face
+    assert n == 1 and abs(normal[1] + 1.0) < 1e-3 and abs(pd[0][3] - 0.1) < 0.011
+    hull = np.zeros(1, dtype=abi.collider_dtype); hull["shape"][0, :7] = (0, 0, 0, 1, 0, 0.35, 0); hull["type"] = abi.HULL
+    hull["objectType"] = abi.OBJ_STATIC; hull["parentTransform"] = abi.NO_TRANSFORM    # geometry 0: frustum with bottom face at y = -0.4
+    n, normal, pd = o.collide_pair(box, hull)
+    assert n == 1 and abs(abs(normal[1]) - 1.0) < 1e-3 and abs(pd[0][3] - 0.05) < 0.011
+    assert o.narrow_stats()["asserts"] == 0
+
+
+# ------------------------------------------------------------------------------------- broad phase cross-checks
+@pytest.mark.parametrize("dims", [(6, 5, 7), (10, 3, 4)])
+def test_sap_equals_brute_force(dims):
+    sc = scenes.sphere_pile_settled(*dims)
+    for canonical in (True, False):
+        o = oracle_lib.Oracle(sc, canonical=canonical)
+        for _ in range(3):          # later steps exercise temporal coherence and the variance-axis switch
+            o.step(DT, 4)
+            got = o.pairs().copy()
+            lo = np.minimum(got["a"], got["b"]); hi = np.maximum(got["a"], got["b"])
+            got["a"], got["b"] = lo, hi
+            assert np.array_equal(np.sort(got, order=["a", "b"]), np.sort(o.brute_pairs(), order=["a", "b"]))
+
+
+def test_mixed_scene_sap_equals_brute_force_and_invariants():
+    sc = host.build_scene(host.CONFIG_MIXED_PILE, 5, 4, 5, seed=1578123, spacing=0.75)
+    o = oracle_lib.Oracle(sc)
+    o.step(DT, 10)
+    assert np.array_equal(o.pairs(), np.sort(o.brute_pairs(), order=["a", "b"]))
+    c, _ = o.contacts()
+    assert len(c) > 100
+    ns = o.narrow_stats()
+    assert ns["asserts"] == 0 and ns["epaOutOfMemory"] == 0 and ns["gjkIterCap"] == 0
+    # the device polytope capacities (k_narrow_shapes.cuh) must cover what the oracle needed
+    assert ns["epaMaxTriangles"] <= 160 and ns["epaMaxEdges"] <= 240 and ns["epaMaxPoints"] <= 24
+    imp = np.zeros((len(c), 2), dtype=np.float32)
+    o.lib.oracle_get_contact_impulses(o.ctx, imp.ctypes.data_as(ctypes.c_void_p))
+    friction = (c["friction_restitution"] >> 16).astype(np.float32) / np.float32(65535.0)
+    assert np.all(imp[:, 0] >= 0.0)                                   # constraints.cpp:3433
+    assert np.all(np.abs(imp[:, 1]) <= friction * imp[:, 0] + 1e-4)   # constraints.cpp:3413-3415 (bound uses the previous iteration's normal impulse)
+
+
+def test_solver_order_replay_is_a_permutation_invariant_for_static_contacts():
+    """Config 1 at rest: every contact is sphere-vs-static, so ANY visiting order gives identical bits."""
+    sc = scenes.spheres_on_ground(8, mode="rest")
+    a = oracle_lib.Oracle(sc); b = oracle_lib.Oracle(sc)
+    a.step(DT, 10)
+    rng = np.random.default_rng(0)
+    b.step(DT, 10, contact_order=rng.permutation(64).astype(np.uint32))
+    for f in ("position", "linearVelocity"):
+        assert np.array_equal(a.body_states()[f], b.body_states()[f])
+
+
+# ------------------------------------------------------------------------------------------------ host mirror
+def test_host_mass_properties_match_oracle_bitwise():
+    sc = host.build_scene(host.CONFIG_MIXED_PILE, 3, 2, 3, seed=5, spacing=1.0)
+    o = oracle_lib.Oracle(sc); hs = sc["host_scene"]
+    extra = [world_collider(abi.CYLINDER, [0, -0.4, 0.1, 0.2, 0.5, 0, 0.3]), world_collider(abi.CAPSULE, [0.1, 0.2, -0.4, 0, -0.5, 0.3, 0.2])]
+    cols = [sc["colliders"][i:i + 1] for i in range(len(sc["colliders"]))] + extra
+    seen = set()
+    for c in cols:
+        hi, hc, hm = hs.mass_properties(c); oi, oc, om = o.mass_properties(c)
+        assert np.array_equal(hi, oi) and np.array_equal(hc, oc) and hm == om
+        seen.add(int(c["type"][0]))
+    assert seen == {0, 1, 2, 3, 4, 5}
+
+
+def test_host_ragdoll_layout_and_index_conventions():
+    sc = host.build_scene(host.CONFIG_RAGDOLLS, 2, 1, 1, seed=1, mode=1, spacing=3.0)
+    assert len(sc["bodies"]) == 28 and len(sc["colliders"]) == 2 * 17 + 1           # ragdoll.cpp:36-103 + ground
+    assert len(sc["joints"][3][0]) == 12 and len(sc["joints"][4][0]) == 14          # 6 hinges + 7 cone-twists each
+    col = sc["colliders"]
+    # collider index = reverse creation order (physics.cpp:635-641): the ground (created last) is collider 0
+    assert col["objectType"][0] == abi.OBJ_STATIC and col["type"][0] == abi.AABB
+    # ... and the very first collider created (torso capsule of ragdoll 0, body 0) is the last one
+    assert col["objectIndex"][-1] == 0 and col["type"][-1] == abi.CAPSULE
+    # body indices are storage order: joint 0 of kind cone-twist connects torso (0) and head (1)
+    assert tuple(sc["joints"][4][1][0]) == (0, 1)
+    total_mass = float(np.sum(1.0 / sc["bodies"]["invMass"][:14]))
+    assert 60.0 < total_mass < 95.0                                                 # a ~75 kg human (ragdoll.cpp:16)
+    # compound torso: 4 capsules -> COG above the hip, inertia matrix symmetric positive
+    assert sc["bodies"]["localCOGPosition"][0][1] > 0.05
+
+
+def test_host_scene_matches_python_generator_for_config1():
+    a = scenes.spheres_on_ground(8, mode="rest")
+    b = host.build_scene(host.CONFIG_SPHERES_ON_GROUND, 8, 1, 8, mode=1, spacing=1.25)
+    assert np.array_equal(a["bodies"]["invMass"], b["bodies"]["invMass"]) and np.array_equal(a["bodies"]["invInertia"], b["bodies"]["invInertia"])
+    assert np.allclose(np.sort(a["bodies"]["position"], axis=0), np.sort(b["bodies"]["position"], axis=0))
+
+
+def test_xorshift_generator_matches_reference_definition():
+    """core/random.h:5-50: x ^= x << 13; x ^= x >> 7; x ^= x << 17 on 64 bits; float01 = (uint32)x / UINT_MAX."""
+    r = scenes.Xorshift64(15681923)
+    x = 15681923
+    for _ in range(5):
+        x ^= (x << 13) & 0xFFFFFFFFFFFFFFFF; x ^= x >> 7; x ^= (x << 17) & 0xFFFFFFFFFFFFFFFF
+        assert r.u64() == x
+    v = scenes.xorshift_floats01(15681923, 4)
+    assert np.all((v >= 0) & (v <= 1)) and len(set(v.tolist())) == 4
+
+
+# ---------------------------------------------------------------------------------------------------- C ABI surface
+def test_cuda_library_loads_and_exports_every_declared_symbol():
+    lib = abi.load_library()
+    assert lib.b200phys_version() == 1
+    header = open(os.path.join(ROOT, "include", "b200phys.h")).read()
+    import re
+    declared = sorted(set(re.findall(r"\b(b200phys_[a-z_]+)\s*\(", header)))
+    assert declared, "no declarations found"
+    for name in declared:
+        assert hasattr(lib, name), "libb200phys.so does not export %s" % name
+    assert set(declared) == set(abi.EXPORTS)
+
+
+def test_struct_sizes_match_header():
+    assert abi.body_dtype.itemsize == 140 and abi.body_state_dtype.itemsize == 52 and abi.collider_dtype.itemsize == 64
+    assert abi.transform_dtype.itemsize == 32 and abi.contact_dtype.itemsize == 32 and abi.pair_dtype.itemsize == 8
+    assert [d.itemsize for d in abi.JOINT_DTYPES] == [28, 24, 48, 104, 120, 80]
+    assert ctypes.sizeof(abi.Config) == 16 * 4 and ctypes.sizeof(abi.Stats) == 36 * 4   # 16 / 36 four-byte fields in b200phys.h
+
+
+def test_no_cpu_fallback_without_device():
+    """Without a CUDA device the product must fail loudly, never compute on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(abi.B200PhysError):
+        abi.Stepper(max_bodies=4, max_colliders=4)
+
+
+def test_product_path_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "d3d12renderer_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                for needle in ("import oracle", "oracle_lib", "liboracle", "oracle/", "om_step.h", "om_math.h", "om_shapes.h"):
+                    assert needle not in text, "%s references the oracle (%s)" % (os.path.join(dirpath, f), needle)
