@@ -229,3 +229,22 @@ def test_product_path_never_imports_the_oracle():
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 for needle in ("import oracle", "oracle_lib", "liboracle", "oracle/", "om_step.h", "om_math.h", "om_shapes.h"):
                     assert needle not in text, "%s references the oracle (%s)" % (os.path.join(dirpath, f), needle)
+
+
+# ------------------------------------------------------------------------------------------------ frozen fixtures
+import golden_util
+
+
+@pytest.mark.parametrize("name", golden_util.NAMES)
+def test_oracle_reproduces_golden_fixtures(name):
+    sc, steps, iters, expect = golden_util.load(name)
+    o = oracle_lib.Oracle(sc, canonical=True)
+    for _ in range(steps):
+        o.step(DT, iters)
+    assert np.array_equal(o.pairs(), expect["pairs"])
+    c, b = o.contacts()
+    assert np.array_equal(b, expect["contact_bodies"]) and np.array_equal(c["friction_restitution"], expect["contacts"]["friction_restitution"])
+    s = o.body_states()
+    for f in ("position", "rotation", "linearVelocity", "angularVelocity"):
+        # same compiler flags -> normally bit-identical; 1e-6 leaves room for a different libm (atan2/acos) on another host
+        assert np.max(np.abs(s[f].astype(np.float64) - expect["states"][f]) / np.maximum(1.0, np.abs(expect["states"][f]))) <= 1e-6

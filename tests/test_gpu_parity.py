@@ -182,3 +182,20 @@ def test_host_mirror_physics_step_matches_abi():
     assert np.array_equal(via_host["position"], direct["position"]) and np.array_equal(via_host["linearVelocity"], direct["linearVelocity"])
     # interpolation factor 0 after exactly one sub-step: the render transform still shows the OLD pose
     assert np.allclose(hs.render_transforms()[:, 4:7], sc["bodies"]["position"])
+
+
+import golden_util
+
+
+@pytest.mark.parametrize("name", golden_util.NAMES)
+def test_gpu_reproduces_golden_fixtures(name):
+    """Exact-order mode against the frozen oracle outputs of tests/golden/ (canonical pair order, array-order Gauss-Seidel)."""
+    sc, steps, iters, expect = golden_util.load(name)
+    st = make_stepper(sc)
+    for _ in range(steps):
+        st.step(DT, iters, abi.STEP_EXACT_ORDER)
+    assert np.array_equal(st.download_pairs(), expect["pairs"])
+    assert np.array_equal(st.download_aabbs().view(np.uint32), expect["aabbs"].view(np.uint32))
+    c, b = st.download_contacts()
+    assert np.array_equal(b, expect["contact_bodies"]) and np.array_equal(c["friction_restitution"], expect["contacts"]["friction_restitution"])
+    assert_states_close(st.download_bodies(), expect["states"], 1e-4)
