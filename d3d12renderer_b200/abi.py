@@ -120,10 +120,10 @@ def load_library():
     lib.b200phys_download_contacts.argtypes = [vp, vp, vp, C.POINTER(u32)]
     lib.b200phys_download_collisions.argtypes = [vp, vp, vp, C.POINTER(u32)]
     lib.b200phys_download_solve_order.argtypes = [vp, i32, vp, C.POINTER(u32)]
-    lib.b200phys_halo_pack.argtypes = [vp, i32, f32, f32, C.POINTER(vp), C.POINTER(u32), C.POINTER(u32)]
-    lib.b200phys_halo_unpack.argtypes = [vp, vp, u32]
+    lib.b200phys_halo_pack.argtypes = [vp, i32, f32, f32, vp, vp, u32, u32, C.POINTER(u32)]
+    lib.b200phys_halo_unpack.argtypes = [vp, vp, u32, vp, u32]
     lib.b200phys_halo_clear.argtypes = [vp]
-    lib.b200phys_halo_record_bytes.restype = u32
+    lib.b200phys_halo_record_bytes.restype = u32; lib.b200phys_halo_record_bytes.argtypes = [i32]
     _lib = lib
     return lib
 
@@ -264,6 +264,18 @@ class Stepper:
 
     def download_collisions(self):
         return self._count_then_fetch(self.lib.b200phys_download_collisions, [pair_dtype, np.dtype("u1")], "download_collisions")
+
+    # ---- multi-GPU halo (device pointers: e.g. torch tensors' data_ptr())
+    def halo_pack(self, axis, lo, hi, dst_bodies_ptr, dst_colliders_ptr, cap_bodies, cap_colliders):
+        counts = (C.c_uint32 * 2)()
+        _check(self.lib, self.lib.b200phys_halo_pack(self.ctx, axis, lo, hi, C.c_void_p(dst_bodies_ptr), C.c_void_p(dst_colliders_ptr), cap_bodies, cap_colliders, counts), "halo_pack")
+        return counts[0], counts[1]
+
+    def halo_unpack(self, src_bodies_ptr, num_bodies, src_colliders_ptr, num_colliders):
+        _check(self.lib, self.lib.b200phys_halo_unpack(self.ctx, C.c_void_p(src_bodies_ptr), num_bodies, C.c_void_p(src_colliders_ptr), num_colliders), "halo_unpack")
+
+    def halo_clear(self):
+        _check(self.lib, self.lib.b200phys_halo_clear(self.ctx), "halo_clear")
 
     def download_solve_order(self, kind):
         n = C.c_uint32(0)

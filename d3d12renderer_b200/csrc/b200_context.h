@@ -64,7 +64,8 @@ struct Context
     bool timing = false;
     cudaEvent_t ev[8] = {};
 
-    uint32_t numBodies = 0, numColliders = 0, numTransforms = 0, numHulls = 0;
+    uint32_t numBodies = 0, numColliders = 0, numTransforms = 0, numHulls = 0;   // incl. ghosts
+    uint32_t numOwnedBodies = 0, numOwnedColliders = 0;                            // what the host uploaded
     uint32_t numJoints[6] = {};
     bool stepped = false;
     uint32_t launches = 0;

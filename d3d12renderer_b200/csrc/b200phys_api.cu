@@ -201,14 +201,14 @@ int b200phys_upload_bodies(b200phys_context* ctx, const b200phys_body* bodies, u
         CK(cudaMemcpyAsync(c.staging, bodies, sizeof(b200phys_body) * (size_t)count, cudaMemcpyHostToDevice, c.stream));
         launchUnpackBodies(&c, c.staging, count);
     }
-    c.numBodies = count;
+    c.numBodies = c.numOwnedBodies = count;
     CK(cudaGetLastError());
     return 0;
 }
 
 int b200phys_upload_body_states(b200phys_context* ctx, const b200phys_body_state* states, uint32_t count)
 {
-    if (!ctx || (count && !states) || count != ctx->c.numBodies) return B200PHYS_E_INVALID;
+    if (!ctx || (count && !states) || count != ctx->c.numOwnedBodies) return B200PHYS_E_INVALID;
     Context& c = ctx->c; CK(cudaSetDevice(c.device));
     if (count)
     {
@@ -221,7 +221,7 @@ int b200phys_upload_body_states(b200phys_context* ctx, const b200phys_body_state
 
 int b200phys_upload_forces(b200phys_context* ctx, const float* forceTorque6, uint32_t count)
 {
-    if (!ctx || (count && !forceTorque6) || count != ctx->c.numBodies) return B200PHYS_E_INVALID;
+    if (!ctx || (count && !forceTorque6) || count != ctx->c.numOwnedBodies) return B200PHYS_E_INVALID;
     Context& c = ctx->c; CK(cudaSetDevice(c.device));
     if (count)
     {
@@ -246,7 +246,7 @@ int b200phys_upload_colliders(b200phys_context* ctx, const b200phys_collider* co
     if (!ctx || (count && !colliders) || count > ctx->c.cfg.maxColliders) return B200PHYS_E_INVALID;
     Context& c = ctx->c; CK(cudaSetDevice(c.device));
     if (count) CK(cudaMemcpyAsync(c.cLocal, colliders, sizeof(b200phys_collider) * (size_t)count, cudaMemcpyHostToDevice, c.stream));
-    c.numColliders = count;
+    c.numColliders = c.numOwnedColliders = count;
     return 0;
 }
 
@@ -313,7 +313,7 @@ int b200phys_get_stats(b200phys_context* ctx, b200phys_stats* out)
     int r = fetchCounts(c); if (r) return r;
     const DeviceCounts& d = *c.hostCounts;
     memset(out, 0, sizeof(*out));
-    out->numBodies = c.numBodies; out->numColliders = c.numColliders;
+    out->numBodies = c.numBodies; out->numColliders = c.numColliders; out->reserved[1] = c.numOwnedBodies; out->reserved[2] = c.numOwnedColliders;
     out->numBroadphaseOverlaps = d.numPairs; out->numCollisions = d.numManifolds; out->numContacts = d.numContacts;
     out->numBigColliders = d.numBig; out->numGridCells = d.grid.numCells;
     for (int g = 0; g < 7; ++g) out->numColors[g] = d.numColors[g];

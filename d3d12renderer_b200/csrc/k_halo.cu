@@ -1,9 +1,177 @@
-// k_halo.cu -- multi-GPU ghost-body halo (pack / unpack) entry points of the C ABI. See DESIGN.md "Multi-GPU".
+// k_halo.cu -- multi-GPU ghost-body halo: pack / unpack kernels and their C-ABI entry points (DESIGN.md "Multi-GPU").
+//
+// Bodies are sharded by spatial slab, one context per GPU / rank. Before a step each rank packs the owned bodies (with all
+// their colliders) whose world AABB reaches into a neighbour's slab (+ ghost width) into two dense device arrays; the
+// transport is the caller's (NCCL send/recv over NVLink on exactly these device buffers, see d3d12renderer_b200/parallel.py);
+// the receiver appends them behind its owned bodies / colliders as GHOSTS. Ghosts take part in the broad phase, narrow phase
+// and solver like any body, but their post-step state is discarded: the owner's result wins and is re-sent next step.
+// There is no collective in the data path beyond this neighbour exchange.
 #include "b200_context.h"
-struct b200phys_context { b200::Context c; };
-extern "C" {
-int b200phys_halo_pack(b200phys_context*, int, float, float, void**, uint32_t*, uint32_t*) { return B200PHYS_E_INVALID; }
-int b200phys_halo_unpack(b200phys_context*, const void*, uint32_t) { return B200PHYS_E_INVALID; }
-int b200phys_halo_clear(b200phys_context*) { return B200PHYS_E_INVALID; }
-uint32_t b200phys_halo_record_bytes(void) { return 0; }
+#include "b200_util.cuh"
+
+using namespace b200;
+
+struct b200phys_context { Context c; };
+
+namespace b200 {
+
+static const int kThreads = 256;
+static const uint32_t kHaloBodyFloats = 36;      // b200phys_body (35 floats) + owner-local body index
+static const uint32_t kHaloColliderFloats = 16;  // b200phys_collider (64 bytes), objectIndex = index inside the packed body list
+
+__global__ void __launch_bounds__(kThreads) haloFlagKernel(uint32_t numColliders, uint32_t numBodies, int axis, float lo, float hi,
+    const float4* __restrict__ cLocal, const float4* __restrict__ aabbMin, const float4* __restrict__ aabbMax, uint32_t* __restrict__ bodyFlag)
+{
+    for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < numColliders; i += gridDim.x * kThreads)
+    {
+        const float4 L3 = cLocal[4 * i + 3];
+        const uint32_t tw = __float_as_uint(L3.y), objType = (tw >> 8) & 0xFFu, body = __float_as_uint(L3.z);
+        if (objType != B200PHYS_OBJ_RIGID_BODY || body >= numBodies) continue;
+        const float4 mn = aabbMin[i], mx = aabbMax[i];
+        const float a = axis == 0 ? mn.x : (axis == 1 ? mn.y : mn.z), b = axis == 0 ? mx.x : (axis == 1 ? mx.y : mx.z);
+        if (b >= lo && a < hi) bodyFlag[body] = 1u;      // benign race: every writer stores 1
+    }
 }
+
+__global__ void __launch_bounds__(kThreads) haloColliderFlagKernel(uint32_t numColliders, uint32_t numBodies, const float4* __restrict__ cLocal,
+    const uint32_t* __restrict__ bodyFlag, uint32_t* __restrict__ colFlag)
+{
+    for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < numColliders; i += gridDim.x * kThreads)
+    {
+        const float4 L3 = cLocal[4 * i + 3];
+        const uint32_t tw = __float_as_uint(L3.y), objType = (tw >> 8) & 0xFFu, body = __float_as_uint(L3.z);
+        colFlag[i] = (objType == B200PHYS_OBJ_RIGID_BODY && body < numBodies && bodyFlag[body]) ? 1u : 0u;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) haloPackBodiesKernel(uint32_t numBodies, uint32_t planeStride, const uint32_t* __restrict__ flag, const uint32_t* __restrict__ slot, uint32_t cap,
+    const float4* __restrict__ bRot, const float4* __restrict__ bPos, const float4* __restrict__ bCog, const float4* __restrict__ bInvI,
+    const float4* __restrict__ bVel, const float4* __restrict__ bAng, const float4* __restrict__ bForce, const float4* __restrict__ bTorque, float* __restrict__ out)
+{
+    for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < numBodies; i += gridDim.x * kThreads)
+    {
+        if (!flag[i]) continue;
+        const uint32_t s = slot[i];
+        if (s >= cap) continue;
+        float* o = out + (size_t)s * kHaloBodyFloats;
+        const float4 r = bRot[i], p = bPos[i], cg = bCog[i], c0 = bInvI[i], c1 = bInvI[planeStride + i], c2 = bInvI[2 * planeStride + i];
+        const float4 v = bVel[i], w = bAng[i], F = bForce[i], T = bTorque[i];
+        o[0] = r.x; o[1] = r.y; o[2] = r.z; o[3] = r.w; o[4] = p.x; o[5] = p.y; o[6] = p.z; o[7] = cg.x; o[8] = cg.y; o[9] = cg.z; o[10] = p.w;
+        o[11] = c0.x; o[12] = c0.y; o[13] = c0.z; o[14] = c1.x; o[15] = c1.y; o[16] = c1.z; o[17] = c2.x; o[18] = c2.y; o[19] = c2.z;
+        o[20] = cg.w; o[21] = c0.w; o[22] = c1.w; o[23] = v.x; o[24] = v.y; o[25] = v.z; o[26] = w.x; o[27] = w.y; o[28] = w.z;
+        o[29] = F.x; o[30] = F.y; o[31] = F.z; o[32] = T.x; o[33] = T.y; o[34] = T.z; o[35] = __uint_as_float(i);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) haloPackCollidersKernel(uint32_t numColliders, const uint32_t* __restrict__ colFlag, const uint32_t* __restrict__ colSlot, uint32_t cap,
+    const uint32_t* __restrict__ bodySlot, const float4* __restrict__ cLocal, float4* __restrict__ out)
+{
+    for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < numColliders; i += gridDim.x * kThreads)
+    {
+        if (!colFlag[i]) continue;
+        const uint32_t s = colSlot[i];
+        if (s >= cap) continue;
+        float4 L3 = cLocal[4 * i + 3];
+        L3.z = __uint_as_float(bodySlot[__float_as_uint(L3.z)]);   // body index inside the packed list
+        out[4 * s] = cLocal[4 * i]; out[4 * s + 1] = cLocal[4 * i + 1]; out[4 * s + 2] = cLocal[4 * i + 2]; out[4 * s + 3] = L3;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) haloUnpackBodiesKernel(uint32_t count, uint32_t base, uint32_t planeStride, const float* __restrict__ in,
+    float4* __restrict__ bRot, float4* __restrict__ bPos, float4* __restrict__ bCog, float4* __restrict__ bInvI,
+    float4* __restrict__ bVel, float4* __restrict__ bAng, float4* __restrict__ bForce, float4* __restrict__ bTorque)
+{
+    for (uint32_t k = blockIdx.x * kThreads + threadIdx.x; k < count; k += gridDim.x * kThreads)
+    {
+        const float* b = in + (size_t)k * kHaloBodyFloats; const uint32_t i = base + k;
+        bRot[i] = make_float4(b[0], b[1], b[2], b[3]);
+        bPos[i] = make_float4(b[4], b[5], b[6], b[10]);
+        bCog[i] = make_float4(b[7], b[8], b[9], b[20]);
+        bInvI[i] = make_float4(b[11], b[12], b[13], b[21]);
+        bInvI[planeStride + i] = make_float4(b[14], b[15], b[16], b[22]);
+        bInvI[2 * planeStride + i] = make_float4(b[17], b[18], b[19], 0.f);
+        bVel[i] = make_float4(b[23], b[24], b[25], 0.f); bAng[i] = make_float4(b[26], b[27], b[28], 0.f);
+        bForce[i] = make_float4(b[29], b[30], b[31], 0.f); bTorque[i] = make_float4(b[32], b[33], b[34], 0.f);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) haloUnpackCollidersKernel(uint32_t count, uint32_t base, uint32_t bodyBase, const float4* __restrict__ in, float4* __restrict__ cLocal)
+{
+    for (uint32_t k = blockIdx.x * kThreads + threadIdx.x; k < count; k += gridDim.x * kThreads)
+    {
+        float4 L3 = in[4 * k + 3];
+        L3.z = __uint_as_float(__float_as_uint(L3.z) + bodyBase);
+        const uint32_t i = base + k;
+        cLocal[4 * i] = in[4 * k]; cLocal[4 * i + 1] = in[4 * k + 1]; cLocal[4 * i + 2] = in[4 * k + 2]; cLocal[4 * i + 3] = L3;
+    }
+}
+
+} // namespace b200
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return -(int)e_; } while (0)
+
+extern "C" {
+
+uint32_t b200phys_halo_record_bytes(int which) { return which == 0 ? kHaloBodyFloats * 4u : kHaloColliderFloats * 4u; }
+
+// Packs every OWNED body (and all of its colliders) with a collider AABB overlapping [lo, hi) on `axis` into the caller's
+// device buffers (e.g. torch tensors); returns the counts through outCounts[2] = {bodies, colliders} (host, synchronous).
+int b200phys_halo_pack(b200phys_context* ctx, int axis, float lo, float hi, void* dstBodies, void* dstColliders, uint32_t capBodies, uint32_t capColliders, uint32_t* outCounts)
+{
+    if (!ctx || axis < 0 || axis > 2 || !outCounts) return B200PHYS_E_INVALID;
+    Context& c = ctx->c; CK(cudaSetDevice(c.device));
+    const uint32_t N = c.numOwnedBodies, C = c.numOwnedColliders;
+    outCounts[0] = outCounts[1] = 0;
+    if (!N || !C) return 0;
+    // current world AABBs of the owned colliders (the step recomputes them, ghosts included)
+    const uint32_t savedB = c.numBodies, savedC = c.numColliders;
+    c.numBodies = N; c.numColliders = C;
+    launchWorldColliders(&c);
+    c.numBodies = savedB; c.numColliders = savedC;
+    uint32_t* bodyFlag = c.adjFill;      // scratch (N + 2)
+    uint32_t* bodySlot = c.adjStart;     // scratch (N + 2)
+    uint32_t* colFlag = c.cellOf;        // scratch (C)
+    uint32_t* colSlot = c.pairStart;     // scratch (C + 2)
+    const int G = gridFor(&c, 4);
+    CK(cudaMemsetAsync(bodyFlag, 0, sizeof(uint32_t) * (N + 1), c.stream));
+    haloFlagKernel<<<G, kThreads, 0, c.stream>>>(C, N, axis, lo, hi, c.cLocal, c.aabbMin, c.aabbMax, bodyFlag);
+    scanExclusiveU32(&c, bodyFlag, bodySlot, nullptr, N, nullptr);
+    haloColliderFlagKernel<<<G, kThreads, 0, c.stream>>>(C, N, c.cLocal, bodyFlag, colFlag);
+    scanExclusiveU32(&c, colFlag, colSlot, nullptr, C, nullptr);
+    uint32_t counts[2] = { 0, 0 };
+    CK(cudaMemcpyAsync(&counts[0], bodySlot + N, 4, cudaMemcpyDeviceToHost, c.stream));
+    CK(cudaMemcpyAsync(&counts[1], colSlot + C, 4, cudaMemcpyDeviceToHost, c.stream));
+    if (dstBodies && capBodies)
+        haloPackBodiesKernel<<<G, kThreads, 0, c.stream>>>(N, c.cfg.maxBodies + 1, bodyFlag, bodySlot, capBodies, c.bRot, c.bPos, c.bCog, c.bInvI, c.bVel, c.bAng, c.bForce, c.bTorque, (float*)dstBodies);
+    if (dstColliders && capColliders)
+        haloPackCollidersKernel<<<G, kThreads, 0, c.stream>>>(C, colFlag, colSlot, capColliders, bodySlot, c.cLocal, (float4*)dstColliders);
+    CK(cudaStreamSynchronize(c.stream));
+    CK(cudaGetLastError());
+    outCounts[0] = counts[0]; outCounts[1] = counts[1];
+    if (counts[0] > capBodies || counts[1] > capColliders) return B200PHYS_E_CAPACITY;
+    return 0;
+}
+
+// Appends ghost bodies / colliders (device buffers in the halo record formats) behind the owned ones for the next step.
+int b200phys_halo_unpack(b200phys_context* ctx, const void* srcBodies, uint32_t numBodies, const void* srcColliders, uint32_t numColliders)
+{
+    if (!ctx) return B200PHYS_E_INVALID;
+    Context& c = ctx->c; CK(cudaSetDevice(c.device));
+    if (c.numBodies + numBodies > c.cfg.maxBodies || c.numColliders + numColliders > c.cfg.maxColliders) return B200PHYS_E_CAPACITY;
+    const int G = gridFor(&c, 4);
+    if (numBodies) haloUnpackBodiesKernel<<<G, kThreads, 0, c.stream>>>(numBodies, c.numBodies, c.cfg.maxBodies + 1, (const float*)srcBodies, c.bRot, c.bPos, c.bCog, c.bInvI, c.bVel, c.bAng, c.bForce, c.bTorque);
+    if (numColliders) haloUnpackCollidersKernel<<<G, kThreads, 0, c.stream>>>(numColliders, c.numColliders, c.numBodies, (const float4*)srcColliders, c.cLocal);
+    c.numBodies += numBodies; c.numColliders += numColliders;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// Drops all ghosts: the context is back to its owned bodies / colliders.
+int b200phys_halo_clear(b200phys_context* ctx)
+{
+    if (!ctx) return B200PHYS_E_INVALID;
+    ctx->c.numBodies = ctx->c.numOwnedBodies; ctx->c.numColliders = ctx->c.numOwnedColliders;
+    return 0;
+}
+
+} // extern "C"

@@ -1,0 +1,127 @@
+"""Multi-GPU plumbing: bodies sharded by spatial slab, one process (and one b200phys context) per GPU, ghost-body halo exchange
+between slab neighbours with torch.distributed point-to-point operations (NCCL over NVLink / NVSwitch on the GPU box, gloo
+in the CPU tests). The data path has exactly one exchange per step (two neighbours per rank); there is no global collective.
+
+Ownership: rank r owns the bodies whose centre lies in [bounds[r], bounds[r+1]) along `axis` at scene-build time. Before every
+step a rank packs the owned bodies whose collider AABBs reach within `ghost_width` of a neighbour's slab (device kernels,
+k_halo.cu), sends them, and appends what it receives as ghosts. Ghost results are discarded after the step (owner wins).
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+BODY_RECORD_FLOATS = 36       # b200phys_halo_record_bytes(0) / 4
+COLLIDER_RECORD_FLOATS = 16   # b200phys_halo_record_bytes(1) / 4
+BIG = 3.0e38
+
+
+def slab_bounds(world, lo, hi):
+    """world+1 plane positions splitting [lo, hi] into equal slabs; the outermost planes are open (-inf / +inf)."""
+    b = np.linspace(lo, hi, world + 1).astype(np.float64)
+    b[0] = -BIG; b[-1] = BIG
+    return b
+
+
+def owner_of(x, bounds):
+    """Rank owning coordinate(s) x: the slab [bounds[r], bounds[r+1]) that contains it."""
+    return np.clip(np.searchsorted(bounds, x, side="right") - 1, 0, len(bounds) - 2)
+
+
+def ghost_regions(rank, world, bounds, ghost_width):
+    """[(peer, lo, hi)]: owned bodies whose AABB overlaps [lo, hi) along the axis are ghosts for `peer`."""
+    out = []
+    if rank > 0:
+        out.append((rank - 1, -BIG, float(bounds[rank]) + ghost_width))
+    if rank < world - 1:
+        out.append((rank + 1, float(bounds[rank + 1]) - ghost_width, BIG))
+    return out
+
+
+def exchange_with_neighbours(send, rank, world, device, group=None):
+    """send: {peer: (bodies_tensor [nb, 36] float32, colliders_tensor [nc, 16] float32)} -> received {peer: (bodies, colliders)}.
+    Two rounds of point-to-point operations: counts, then payloads sized by the counts (NCCL on CUDA tensors, gloo on CPU)."""
+    peers = sorted(send.keys())
+    if not peers:
+        return {}
+    cnt_out = {p: torch.tensor([send[p][0].shape[0], send[p][1].shape[0]], dtype=torch.int64, device=device) for p in peers}
+    cnt_in = {p: torch.zeros(2, dtype=torch.int64, device=device) for p in peers}
+    ops = []
+    for p in peers:
+        ops.append(dist.P2POp(dist.isend, cnt_out[p], p, group)); ops.append(dist.P2POp(dist.irecv, cnt_in[p], p, group))
+    for r in dist.batch_isend_irecv(ops):
+        r.wait()
+    recv = {}
+    ops = []
+    for p in peers:
+        nb, nc = int(cnt_in[p][0].item()), int(cnt_in[p][1].item())
+        recv[p] = (torch.empty((nb, BODY_RECORD_FLOATS), dtype=torch.float32, device=device), torch.empty((nc, COLLIDER_RECORD_FLOATS), dtype=torch.float32, device=device))
+        for t_out, t_in in ((send[p][0], recv[p][0]), (send[p][1], recv[p][1])):
+            if t_out.numel():
+                ops.append(dist.P2POp(dist.isend, t_out.contiguous(), p, group))
+            if t_in.numel():
+                ops.append(dist.P2POp(dist.irecv, t_in, p, group))
+    if ops:
+        for r in dist.batch_isend_irecv(ops):
+            r.wait()
+    return recv
+
+
+class SlabShard:
+    """One rank's shard: wraps a Stepper whose uploaded bodies are the OWNED ones and keeps its ghost layer fresh."""
+
+    def __init__(self, stepper, rank, world, bounds, axis=0, ghost_width=1.05, max_ghost_bodies=1 << 18, max_ghost_colliders=1 << 18, device=None):
+        self.st = stepper; self.rank = rank; self.world = world; self.bounds = bounds; self.axis = axis; self.ghost_width = ghost_width
+        self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.regions = ghost_regions(rank, world, bounds, ghost_width)
+        self.send_bodies = {p: torch.empty((max_ghost_bodies, BODY_RECORD_FLOATS), dtype=torch.float32, device=self.device) for p, _, _ in self.regions}
+        self.send_colliders = {p: torch.empty((max_ghost_colliders, COLLIDER_RECORD_FLOATS), dtype=torch.float32, device=self.device) for p, _, _ in self.regions}
+        self.last_ghosts = (0, 0)
+        self._recv_keepalive = None
+
+    def refresh_ghosts(self):
+        """halo_clear -> pack per neighbour (device kernels) -> neighbour exchange -> unpack. Call before every step."""
+        st = self.st
+        st.halo_clear()
+        if self.world == 1:
+            return
+        send = {}
+        for peer, lo, hi in self.regions:
+            sb, sc = self.send_bodies[peer], self.send_colliders[peer]
+            nb, nc = st.halo_pack(self.axis, lo, hi, sb.data_ptr(), sc.data_ptr(), sb.shape[0], sc.shape[0])
+            send[peer] = (sb[:nb], sc[:nc])
+        recv = exchange_with_neighbours(send, self.rank, self.world, self.device)
+        tb = tc = 0
+        for peer in sorted(recv.keys()):
+            b, c = recv[peer]
+            if self.device.type == "cuda":
+                torch.cuda.current_stream().synchronize()   # the receive completed on torch's stream; unpack runs on the stepper's
+            st.halo_unpack(b.data_ptr(), b.shape[0], c.data_ptr(), c.shape[0])
+            tb += b.shape[0]; tc += c.shape[0]
+        st.synchronize()
+        self._recv_keepalive = recv
+        self.last_ghosts = (tb, tc)
+
+    def step(self, dt, iterations, flags=0):
+        self.refresh_ghosts()
+        self.st.step(dt, iterations, flags)
+
+
+def shard_scene(scene, rank, world, bounds, axis=0):
+    """Splits a single-GPU scene dict into this rank's shard: owned bodies (centre inside the slab) with their colliders,
+    static colliders replicated on every rank. Returns (shard_scene, global_body_ids, global_collider_ids)."""
+    bodies, colliders = scene["bodies"], scene["colliders"]
+    if any(len(j[0]) for j in scene.get("joints", {}).values()):
+        raise ValueError("joint chains are not sharded across GPUs yet (shard whole ragdolls instead)")
+    owner = owner_of(bodies["position"][:, axis].astype(np.float64), bounds)
+    mine = np.nonzero(owner == rank)[0]
+    remap = np.full(len(bodies), -1, dtype=np.int64); remap[mine] = np.arange(len(mine))
+    is_body = colliders["objectType"] == 0
+    keep = np.nonzero(~is_body | (remap[np.minimum(colliders["objectIndex"], len(bodies) - 1)] >= 0))[0]
+    sub_c = colliders[keep].copy()
+    bsel = sub_c["objectType"] == 0
+    sub_c["objectIndex"][bsel] = remap[sub_c["objectIndex"][bsel]].astype(np.uint32)
+    out = {"bodies": np.ascontiguousarray(bodies[mine]), "colliders": np.ascontiguousarray(sub_c), "transforms": scene["transforms"], "joints": {}}
+    for k in ("hull_vertices", "hull_offsets", "hull_triangles"):
+        if k in scene:
+            out[k] = scene[k]
+    return out, mine, keep

@@ -237,13 +237,18 @@ int b200phys_download_collisions(b200phys_context* ctx, b200phys_collider_pair* 
 /* order in which the solver visited contacts / joints of one kind inside an iteration (kind 6 = contacts) */
 int b200phys_download_solve_order(b200phys_context* ctx, int kind, uint32_t* outOrder, uint32_t* count);
 
-/* multi-GPU (one context per rank; transport is the caller's: NCCL send/recv on these device buffers) ----------- */
-/* packs bodies+colliders whose AABB reaches into [lo, hi) along `axis` into a device buffer; returns device ptr + count */
-int b200phys_halo_pack(b200phys_context* ctx, int axis, float lo, float hi, void** outDevicePtr, uint32_t* outCount, uint32_t* outBytes);
-/* appends `count` ghost records (received from a neighbour, device memory) as kinematic read-only bodies for the next step */
-int b200phys_halo_unpack(b200phys_context* ctx, const void* devicePtr, uint32_t count);
+/* multi-GPU (one context per GPU / rank, bodies sharded by spatial slab; transport is the caller's: NCCL send/recv on these
+ * DEVICE buffers, see d3d12renderer_b200/parallel.py) ------------------------------------------------------------------------
+ * halo record formats: body = b200phys_body (35 floats) + owner-local index (36 x 4 bytes); collider = b200phys_collider whose
+ * objectIndex is the position of its body inside the packed body list (64 bytes). */
+uint32_t b200phys_halo_record_bytes(int which /* 0 body, 1 collider */);
+/* packs every OWNED body (with all its colliders) that has a collider AABB overlapping [lo, hi) along `axis` into the caller's
+ * device buffers; outCounts[2] = {bodies, colliders} (synchronous). Returns B200PHYS_E_CAPACITY if a buffer is too small. */
+int b200phys_halo_pack(b200phys_context* ctx, int axis, float lo, float hi, void* dstBodiesDevice, void* dstCollidersDevice,
+                       uint32_t capBodies, uint32_t capColliders, uint32_t* outCounts);
+/* appends received ghost bodies / colliders behind the owned ones; they take part in the next step, their results are discarded */
+int b200phys_halo_unpack(b200phys_context* ctx, const void* srcBodiesDevice, uint32_t numBodies, const void* srcCollidersDevice, uint32_t numColliders);
 int b200phys_halo_clear(b200phys_context* ctx);
-uint32_t b200phys_halo_record_bytes(void);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,100 @@
+"""Multi-GPU check (run with torchrun on >= 2 GPUs of one box; not collected by pytest):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/mgpu_check.py
+
+Slab-shards a sphere pile across the ranks with the ghost halo and compares with a single-GPU run of the whole scene:
+ (1) the union over ranks of broad-phase pairs (mapped to global body ids) equals the single-GPU pair set,
+ (2) after one step, bodies far from any slab plane agree to 1e-4; bodies next to a plane differ only through the one-layer
+     ghost approximation (reported)."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from d3d12renderer_b200 import abi, parallel, scenes  # noqa: E402
+
+
+def main():
+    rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    stream = torch.cuda.Stream(); torch.cuda.set_stream(stream)
+    DT = np.float32(1 / 120.0)
+    sc = scenes.sphere_pile_settled(8 * world, 8, 8, seed=11)
+    n = len(sc["bodies"])
+    xs = sc["bodies"]["position"][:, 0]
+    bounds = parallel.slab_bounds(world, float(xs.min()) - 0.5, float(xs.max()) + 0.5)
+    sub, body_ids, col_ids = parallel.shard_scene(sc, rank, world, bounds)
+    cap_b = len(sub["bodies"]) + 4096; cap_c = len(sub["colliders"]) + 4096
+    st = abi.Stepper(max_bodies=cap_b, max_colliders=cap_c, max_transforms=4, device=local)
+    st.set_stream(stream.cuda_stream)
+    st.upload_bodies(sub["bodies"]); st.upload_transforms(sub["transforms"]); st.upload_colliders(sub["colliders"])
+    shard = parallel.SlabShard(st, rank, world, bounds, axis=0, ghost_width=1.05, max_ghost_bodies=4096, max_ghost_colliders=4096)
+    shard.step(DT, 10, abi.STEP_FAST)
+    stats = st.stats()
+    states = st.download_bodies(np.empty(len(sub["bodies"]), dtype=abi.body_state_dtype))
+    pairs = st.download_pairs()
+
+    # local collider index -> global "collider key": dynamic colliders map to their global body id, statics to n + static index
+    n_own_c = len(sub["colliders"])
+    key = np.full(stats.numColliders, -1, dtype=np.int64)
+    own = sub["colliders"]
+    dyn = own["objectType"] == 0
+    key[:n_own_c][dyn] = body_ids[own["objectIndex"][dyn]]
+    key[:n_own_c][~dyn] = n + np.arange((~dyn).sum())
+    # ghosts: fetch their owner-local indices from the packed records we received, map through the peers' global ids
+    all_ids = [None] * world
+    dist.all_gather_object(all_ids, body_ids)
+    gkeys = []
+    for peer in sorted(shard._recv_keepalive.keys()):
+        b, _ = shard._recv_keepalive[peer]
+        owner_local = b[:, 35].contiguous().view(torch.int32).cpu().numpy()
+        gkeys.append(all_ids[peer][owner_local])
+    if gkeys:
+        key[n_own_c:] = np.concatenate(gkeys)   # one collider per ghost body in this scene, same order
+    assert np.all(key >= 0)
+    ga = key[pairs["a"]]; gb = key[pairs["b"]]
+    lo = np.minimum(ga, gb); hi = np.maximum(ga, gb)
+    local_pairs = np.unique(np.stack([lo, hi], 1), axis=0)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, local_pairs)
+    gathered_states = [None] * world
+    dist.all_gather_object(gathered_states, (body_ids, states))
+
+    if rank == 0:
+        full = abi.Stepper(max_bodies=n, max_colliders=len(sc["colliders"]), max_transforms=4, device=local)
+        full.upload_bodies(sc["bodies"]); full.upload_transforms(sc["transforms"]); full.upload_colliders(sc["colliders"])
+        full.step(DT, 10, abi.STEP_FAST)
+        ref_pairs = full.download_pairs(); ref_states = full.download_bodies()
+        c = sc["colliders"]
+        ckey = np.where(c["objectType"] == 0, c["objectIndex"].astype(np.int64), n + np.cumsum(c["objectType"] != 0) - 1)
+        ra = ckey[ref_pairs["a"]]; rb = ckey[ref_pairs["b"]]
+        ref = np.unique(np.stack([np.minimum(ra, rb), np.maximum(ra, rb)], 1), axis=0)
+        # static-static pairs exist on every rank; ghost-ghost pairs are duplicates of the owner's: the union must equal the reference set
+        union = np.unique(np.concatenate(gathered, 0), axis=0)
+        same = union.shape == ref.shape and np.array_equal(union, ref)
+        print("pairs: single-GPU %d, union over %d ranks %d -> %s" % (len(ref), world, len(union), "IDENTICAL" if same else "DIFFERENT"))
+        merged = np.empty(n, dtype=abi.body_state_dtype)
+        for ids, s in gathered_states:
+            merged[ids] = s
+        planes = bounds[1:-1]
+        dist_to_plane = np.min(np.abs(xs[:, None] - planes[None, :]), axis=1) if len(planes) else np.full(n, 1e9)
+        def rel(f, mask):
+            a = merged[f][mask].astype(np.float64); b = ref_states[f][mask].astype(np.float64)
+            return float(np.max(np.abs(a - b) / np.maximum(1.0, np.abs(b)))) if a.size else 0.0
+        far = dist_to_plane > 3.0; near = ~far
+        print("bodies far from a slab plane: %d  max rel err pos %.3g vel %.3g" % (far.sum(), rel("position", far), rel("linearVelocity", far)))
+        print("bodies within 3 m of a plane: %d  max rel err pos %.3g vel %.3g" % (near.sum(), rel("position", near), rel("linearVelocity", near)))
+        print("ghosts per rank (bodies, colliders):", shard.last_ghosts, "owned:", len(sub["bodies"]))
+        ok = same and rel("position", far) <= 1e-4 and rel("linearVelocity", far) <= 1e-3
+        print("MGPU_CHECK", "PASS" if ok else "FAIL")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
