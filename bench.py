@@ -20,6 +20,8 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", ""):
+    os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the single JSON line (NCCL prints its version banner to stdout)
 
 import numpy as np
 
@@ -79,11 +81,12 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
 
 
-def build_scene(rank):
-    """configs[1]: 262 144 spheres (64^3 jittered lattice, spacing 0.96 r=0.5: a settled pile, ~3 contacts per body) in an
-    open box of 5 static AABBs. Every rank owns one such pile (weak scaling, piles are independent)."""
+def build_scene(rank, world):
+    """configs[1]: 262 144 spheres per GPU (64 x 64 x 64 jittered lattice, spacing 0.96, r = 0.5: a settled pile with ~3 contacts
+    per body) in an open box of 5 static AABBs. With N GPUs the pile is (64 N) x 64 x 64 and rank r owns x-layers [64 r, 64 (r+1)):
+    ONE scene, slab-decomposed, coupled through the ghost-body halo (BASELINE configs[4] layout, weak scaling)."""
     from d3d12renderer_b200 import scenes
-    return scenes.sphere_pile_settled(64, 64, 64, seed=519431 + rank)
+    return scenes.sphere_pile_slab(64 * world, 64, 64, 64 * rank, 64 * (rank + 1), seed=519431)
 
 
 def cpu_reference_sample(steps, warmup):
@@ -154,15 +157,33 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     W = max(3, args.warmup); K = args.steps
 
-    sc = build_scene(rank)
+    from d3d12renderer_b200 import parallel
+    sc = build_scene(rank, world)
     n_bodies = len(sc["bodies"]); n_col = len(sc["colliders"])
-    st = abi.Stepper(max_bodies=n_bodies, max_colliders=n_col, max_transforms=4, device=local_rank)
+    ghost_cap = 0 if world == 1 else 3 * 64 * 64 * 2
+    st = abi.Stepper(max_bodies=n_bodies + 2 * ghost_cap, max_colliders=n_col + 2 * ghost_cap, max_transforms=4, device=local_rank)
     stream = torch.cuda.Stream()          # a real (non-default) stream: every kernel of the context and the timing events share it
     torch.cuda.set_stream(stream)
     st.set_stream(stream.cuda_stream)
     host_bodies = abi.PinnedArray(abi.body_dtype, n_bodies); host_bodies.array[:] = sc["bodies"]
     host_states = abi.PinnedArray(abi.body_state_dtype, n_bodies)
     st.upload_transforms(sc["transforms"]); st.upload_colliders(sc["colliders"]); st.upload_bodies(host_bodies.array)
+    # slab planes between ranks; the ghost layer is one collider diameter (+5 %) wide
+    x_lo, x_hi = sc["slab"]
+    planes = [None] * world
+    if world > 1:
+        dist.all_gather_object(planes, (x_lo, x_hi))
+    else:
+        planes = [(x_lo, x_hi)]
+    import numpy as _np
+    bounds = _np.array([-parallel.BIG] + [0.5 * (planes[r][1] + planes[r + 1][0]) for r in range(world - 1)] + [parallel.BIG])
+    shard = parallel.SlabShard(st, rank, world, bounds, axis=0, ghost_width=1.05, max_ghost_bodies=max(1, ghost_cap), max_ghost_colliders=max(1, ghost_cap),
+                               device=torch.device("cuda", local_rank))
+
+    def do_step():
+        if world > 1:
+            shard.refresh_ghosts()      # pack (device) -> NCCL send/recv with the two slab neighbours -> unpack (device)
+        st.step(DT, ITERATIONS, abi.STEP_FAST)
 
     def barrier():
         if world > 1:
@@ -176,7 +197,7 @@ def main():
 
     # ---- device-resident throughput -----------------------------------------------------------------------------
     for _ in range(W):
-        st.step(DT, ITERATIONS, abi.STEP_FAST)
+        do_step()
     barrier()
     clocks = ClockSampler(local_rank)
     if rank == 0:
@@ -185,7 +206,7 @@ def main():
     barrier()
     ev0.record(stream)
     for _ in range(K):
-        st.step(DT, ITERATIONS, abi.STEP_FAST)
+        do_step()
     ev1.record(stream)
     barrier()
     ms_dev = max_over_ranks(ev0.elapsed_time(ev1))
@@ -198,7 +219,7 @@ def main():
     acc = np.zeros(7); contacts = 0; pairs = 0; cells = 0
     R = 10
     for _ in range(R):
-        st.step(DT, ITERATIONS, abi.STEP_FAST)
+        do_step()
         s = st.stats()
         acc += np.array([s.msWorld, s.msBroad, s.msNarrow, s.msInit, s.msSolve, s.msIntegrate, s.msTotal]); contacts += s.numContacts; pairs += s.numBroadphaseOverlaps
     st.enable_timing(False)
@@ -213,15 +234,17 @@ def main():
     hs = host_states.array
     host_forces = abi.PinnedArray(np.float32, n_bodies * 6); hf = host_forces.array.reshape(n_bodies, 6); hf[:] = 0
     st.download_bodies(hs)
+    st.halo_clear()
     for _ in range(2):
-        st.upload_body_states(hs); st.upload_forces(hf); st.step(DT, ITERATIONS, abi.STEP_FAST); st.download_bodies(hs)
+        st.upload_body_states(hs); st.upload_forces(hf); do_step(); st.halo_clear(); st.download_bodies(hs)
     barrier()
     t0 = time.perf_counter()
     for _ in range(K):
         st.upload_body_states(hs)                  # pinned host -> HBM: pose + velocities of every body, 52 B each
         st.upload_forces(hf)                       # pinned host -> HBM: force/torque accumulators, 24 B each
-        st.step(DT, ITERATIONS, abi.STEP_FAST)
-        st.download_bodies(hs)                     # HBM -> pinned host: pose + velocities of every body, 52 B each (synchronises)
+        do_step()                                  # (+ ghost halo exchange with the slab neighbours when N > 1)
+        st.halo_clear()
+        st.download_bodies(hs)                     # HBM -> pinned host: pose + velocities of every OWNED body, 52 B each (synchronises)
     barrier()
     ms_e2e = max_over_ranks((time.perf_counter() - t0) * 1e3)
     checksum = float(np.sum(hs["position"][:, 1].astype(np.float64)))
@@ -242,7 +265,7 @@ def main():
             "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "262144-sphere settled pile per GPU (BASELINE configs[1]), 10 PGS iterations, dt 1/120, fast (coloured) solver order",
                        "bodies": total_bodies, "bodies_per_gpu": n_bodies, "iterations": ITERATIONS, "contacts_per_gpu": contacts, "pairs_per_gpu": pairs,
-                       "steps_per_s": K / (ms_dev * 1e-3), "parallelism": "1 pile per GPU (independent shards, no halo)" if world > 1 else "single GPU",
+                       "steps_per_s": K / (ms_dev * 1e-3), "parallelism": ("slab decomposition along x, %d x 262144 bodies, ghost-body halo over NCCL (%d ghost bodies on rank 0)" % (world, shard.last_ghosts[0])) if world > 1 else "single GPU",
                        "l2_policy": "per-step working set (rows, pair and manifold scratch, body planes) > 126 MB L2; no explicit flush",
                        "state_checksum_y": checksum},
             "e2e": {"value": e2e_value, "unit": "body-steps/s", "ms_per_step": ms_e2e / K, "h2d_bytes_per_step": int(n_bodies * (abi.body_state_dtype.itemsize + 24)),

@@ -142,3 +142,35 @@ def sphere_box_drop(nx=64, ny=64, nz=64, spacing=1.02, jitter=0.005, seed=519431
 def sphere_pile_settled(nx=16, ny=16, nz=16, spacing=0.96, jitter=0.01, seed=7, radius=0.5):
     """Dense overlapping lattice (every sphere touches its neighbours): exercises sphere-sphere contacts + colouring."""
     return sphere_box_drop(nx, ny, nz, spacing=spacing, jitter=jitter, seed=seed, radius=radius, base_y=0.48, walls=True)
+
+
+def sphere_pile_slab(nx_total, ny, nz, ix0, ix1, spacing=0.96, jitter=0.01, seed=7, radius=0.5, base_y=0.48):
+    """x-layers [ix0, ix1) of the (nx_total x ny x nz) settled sphere pile + the 5 static boxes of the WHOLE pile (replicated on
+    every rank). Jitter is drawn per x-layer (seed, layer) so the scene is identical for every world size."""
+    nx = ix1 - ix0
+    n = nx * ny * nz
+    bodies = new_bodies(n)
+    hx = F((nx_total - 1) * spacing * 0.5); hz = F((nz - 1) * spacing * 0.5)
+    iy, iz = np.meshgrid(np.arange(ny), np.arange(nz), indexing="ij")
+    per = ny * nz
+    for k, ix in enumerate(range(ix0, ix1)):
+        j = np.random.default_rng(seed * 1000003 + ix).uniform(-jitter, jitter, size=(per, 3)).astype(np.float32)
+        sl = slice(k * per, (k + 1) * per)
+        bodies["position"][sl, 0] = F(ix) * F(spacing) - hx + j[:, 0]
+        bodies["position"][sl, 1] = iy.ravel().astype(np.float32) * F(spacing) + F(base_y) + j[:, 1]
+        bodies["position"][sl, 2] = iz.ravel().astype(np.float32) * F(spacing) - hz + j[:, 2]
+    set_sphere_bodies(bodies, slice(None), radius, 1.0)
+    colliders = np.zeros(n + 5, dtype=abi.collider_dtype)
+    colliders["shape"][:n, 3] = radius
+    colliders["restitution"][:n] = 0.1; colliders["friction"][:n] = 0.5; colliders["density"][:n] = 1.0
+    colliders["type"][:n] = abi.SPHERE; colliders["objectType"][:n] = abi.OBJ_RIGID_BODY
+    colliders["objectIndex"][:n] = np.arange(n, dtype=np.uint32); colliders["parentTransform"][:n] = abi.NO_TRANSFORM
+    transforms = np.zeros(1, dtype=abi.transform_dtype); transforms["rotation"][0, 3] = 1.0
+    ex = float(hx) + radius + 0.6; ez = float(hz) + radius + 0.6; h = float(ny * spacing) + 4.0
+    static_box(colliders, n, (0, -4.0, 0), (ex + 8.0, 4.0, ez + 8.0), 0)
+    static_box(colliders, n + 1, (-(ex + 2.0), h * 0.5, 0), (2.0, h * 0.5 + 2.0, ez + 4.0), 0)
+    static_box(colliders, n + 2, ((ex + 2.0), h * 0.5, 0), (2.0, h * 0.5 + 2.0, ez + 4.0), 0)
+    static_box(colliders, n + 3, (0, h * 0.5, -(ez + 2.0)), (ex + 4.0, h * 0.5 + 2.0, 2.0), 0)
+    static_box(colliders, n + 4, (0, h * 0.5, (ez + 2.0)), (ex + 4.0, h * 0.5 + 2.0, 2.0), 0)
+    x_lo = float(F(ix0) * F(spacing) - hx) - 0.5 * spacing; x_hi = float(F(ix1 - 1) * F(spacing) - hx) + 0.5 * spacing
+    return {"bodies": bodies, "colliders": colliders, "transforms": transforms, "slab": (x_lo, x_hi), "name": "sphere_pile_slab_%d_%d_of_%d" % (ix0, ix1, nx_total)}
