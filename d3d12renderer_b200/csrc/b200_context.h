@@ -41,6 +41,7 @@ struct DeviceCounts
     uint32_t numJoints[6];
     uint32_t colorStart[kNumGroups][kMaxColors + 1]; // fast mode unit ranges per colour
     uint32_t numBig;
+    uint32_t bigMatrixCount;            // min(numBig, 16) * C: size of the big-collider flag matrix
     uint32_t remaining;                 // colouring work counter
     uint32_t overflowPairs, overflowManifolds, overflowGrid, overflowColors, overflowBig;
     uint32_t epaOverflows, gjkIterationCaps, assertCount;

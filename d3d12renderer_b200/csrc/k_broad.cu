@@ -50,7 +50,16 @@ __global__ void __launch_bounds__(kThreads) bpExtentKernel(uint32_t C, const flo
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { sum += __shfl_down_sync(0xffffffffu, sum, o); n += __shfl_down_sync(0xffffffffu, n, o); }
-    if (laneId() == 0 && n) { atomicAdd(&cnt->extentSumFixed, sum); atomicAdd(&cnt->extentCount, n); }
+    // one pair of atomics per CTA (same-address atomics serialise at one L2 slice)
+    __shared__ unsigned long long sSum[kThreads / 32]; __shared__ uint32_t sN[kThreads / 32];
+    if (laneId() == 0) { sSum[threadIdx.x >> 5] = sum; sN[threadIdx.x >> 5] = n; }
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        unsigned long long ts = 0; uint32_t tn = 0;
+        for (int w = 0; w < kThreads / 32; ++w) { ts += sSum[w]; tn += sN[w]; }
+        if (tn) { atomicAdd(&cnt->extentSumFixed, ts); atomicAdd(&cnt->extentCount, tn); }
+    }
 }
 
 __global__ void __launch_bounds__(kThreads) bpClassifyKernel(uint32_t C, float bigFactor, float cfgCell, const float4* __restrict__ mn, const float4* __restrict__ mx,
@@ -84,10 +93,17 @@ __global__ void __launch_bounds__(kThreads) bpClassifyKernel(uint32_t C, float b
     extBits = __reduce_max_sync(0xffffffffu, extBits);
 #pragma unroll
     for (int a = 0; a < 3; ++a) { lo[a] = __reduce_min_sync(0xffffffffu, lo[a]); hi[a] = __reduce_max_sync(0xffffffffu, hi[a]); }
-    if (laneId() == 0)
-    {
+    __shared__ uint32_t sRed[kThreads / 32][7];
+    if (laneId() == 0) { sRed[threadIdx.x >> 5][0] = extBits; for (int a = 0; a < 3; ++a) { sRed[threadIdx.x >> 5][1 + a] = lo[a]; sRed[threadIdx.x >> 5][4 + a] = hi[a]; } }
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {   // one set of atomics per CTA
+        for (int w = 1; w < kThreads / 32; ++w)
+        {
+            extBits = max(extBits, sRed[w][0]);
+            for (int a = 0; a < 3; ++a) { lo[a] = min(lo[a], sRed[w][1 + a]); hi[a] = max(hi[a], sRed[w][4 + a]); }
+        }
         if (extBits) atomicMax(&cnt->maxSmallExtentBits, extBits);
-#pragma unroll
         for (int a = 0; a < 3; ++a) { if (lo[a] != 0xFFFFFFFFu) atomicMin(&cnt->centreMinBits[a], lo[a]); if (hi[a]) atomicMax(&cnt->centreMaxBits[a], hi[a]); }
     }
 }
@@ -265,13 +281,13 @@ __global__ void __launch_bounds__(kThreads) bpQueryKernel(const float4* __restri
 
 // one CTA per big collider: sweep every collider with a larger index, ordered compaction
 template <bool FILL>
-__global__ void __launch_bounds__(kThreads) bpBigKernel(uint32_t C, const float4* __restrict__ aabbMin, const float4* __restrict__ aabbMax, const uint32_t* __restrict__ bigList,
+__global__ void __launch_bounds__(kThreads) bpBigKernel(uint32_t C, uint32_t firstSlot, const float4* __restrict__ aabbMin, const float4* __restrict__ aabbMax, const uint32_t* __restrict__ bigList,
     uint32_t* __restrict__ pairCount, const uint32_t* __restrict__ pairStart, uint2* __restrict__ pairs, uint32_t maxPairs, DeviceCounts* cnt)
 {
     __shared__ uint32_t warpCnt[kThreads / 32];
     __shared__ uint32_t running;
     const uint32_t numBig = min(cnt->numBig, kMaxBig);
-    for (uint32_t k = blockIdx.x; k < numBig; k += gridDim.x)
+    for (uint32_t k = firstSlot + blockIdx.x; k < numBig; k += gridDim.x)
     {
         const uint32_t id = bigList[k];
         const float4 amn = aabbMin[id], amx = aabbMax[id];
@@ -297,6 +313,41 @@ __global__ void __launch_bounds__(kThreads) bpBigKernel(uint32_t C, const float4
         __syncthreads();
     }
 }
+
+// Big colliders, parallel path (numBig * C <= scratch): flag matrix [slot][j] = (j > id_slot && overlap), ONE exclusive scan over
+// the flattened matrix gives every pair its ordered position inside the big collider's segment.
+__global__ void __launch_bounds__(kThreads) bpBigFlagKernel(uint32_t C, const float4* __restrict__ aabbMin, const float4* __restrict__ aabbMax, const uint32_t* __restrict__ bigList,
+                                                            uint32_t* __restrict__ flags, const DeviceCounts* __restrict__ cnt)
+{
+    __shared__ float4 sMin[16], sMax[16]; __shared__ uint32_t sId[16];
+    const uint32_t nb = min(cnt->numBig, 16u);
+    if (threadIdx.x < nb) { const uint32_t b = bigList[threadIdx.x]; sId[threadIdx.x] = b; sMin[threadIdx.x] = aabbMin[b]; sMax[threadIdx.x] = aabbMax[b]; }
+    __syncthreads();
+    for (uint32_t j = blockIdx.x * kThreads + threadIdx.x; j < C; j += gridDim.x * kThreads)
+    {
+        const float4 mn = ldStream(aabbMin + j), mx = ldStream(aabbMax + j);
+        for (uint32_t k = 0; k < nb; ++k) flags[(size_t)k * C + j] = (j > sId[k] && overlapInclusive(sMin[k], sMax[k], mn, mx)) ? 1u : 0u;
+    }
+}
+__global__ void bpBigCountKernel(uint32_t C, const uint32_t* __restrict__ bigList, const uint32_t* __restrict__ offs, uint32_t* __restrict__ pairCount, DeviceCounts* cnt)
+{
+    const uint32_t nb = min(cnt->numBig, 16u);
+    if (threadIdx.x < nb) pairCount[bigList[threadIdx.x]] = offs[(size_t)(threadIdx.x + 1) * C] - offs[(size_t)threadIdx.x * C];
+}
+__global__ void __launch_bounds__(kThreads) bpBigFillKernel(uint32_t C, const uint32_t* __restrict__ bigList, const uint32_t* __restrict__ flags, const uint32_t* __restrict__ offs,
+                                                            const uint32_t* __restrict__ pairStart, uint2* __restrict__ pairs, uint32_t maxPairs, DeviceCounts* cnt)
+{
+    const uint32_t nb = min(cnt->numBig, 16u);
+    const size_t total = (size_t)nb * C;
+    for (size_t idx = (size_t)blockIdx.x * kThreads + threadIdx.x; idx < total; idx += (size_t)gridDim.x * kThreads)
+    {
+        if (!flags[idx]) continue;
+        const uint32_t k = (uint32_t)(idx / C), j = (uint32_t)(idx - (size_t)k * C), id = bigList[k];
+        const uint32_t pos = pairStart[id] + (offs[idx] - offs[(size_t)k * C]);
+        if (pos < maxPairs) pairs[pos] = make_uint2(id, j); else cnt->overflowPairs = 1;
+    }
+}
+__global__ void bpBigCountDeviceKernel(uint32_t C, DeviceCounts* cnt) { if (threadIdx.x == 0) cnt->bigMatrixCount = min(cnt->numBig, 16u) * C; }
 
 __global__ void bpFinishKernel(uint32_t C, const uint32_t* __restrict__ pairStart, uint32_t maxPairs, DeviceCounts* cnt)
 {
@@ -327,11 +378,25 @@ void launchBroadphase(Context* c)
     bpScatterKernel<<<G, kThreads, 0, c->stream>>>(C, c->aabbMin, c->aabbMax, c->cellOf, c->rankInCell, c->cellStart, c->sortedMin, c->sortedMax);
     cudaMemsetAsync(c->pairCount, 0, sizeof(uint32_t) * (C + 1), c->stream);
     bpQueryKernel<false><<<G, kThreads, 0, c->stream>>>(c->sortedMin, c->sortedMax, c->cellStart, c->aabbMin, c->aabbMax, c->bigList, c->pairCount, c->pairStart, c->pairs, c->maxPairs, cnt);
-    bpBigKernel<false><<<c->numSMs, kThreads, 0, c->stream>>>(C, c->aabbMin, c->aabbMax, c->bigList, c->pairCount, c->pairStart, c->pairs, c->maxPairs, cnt);
+    // big colliders: parallel flag-matrix path for up to 16 of them (scratch: pair-sized buffers that are free until the narrow
+    // phase); beyond that one CTA per big collider sweeps all colliders (bpBigKernel, skips the first 16)
+    uint32_t* bigFlags = c->pairDst; uint32_t* bigOffs = (uint32_t*)c->manScan;
+    const bool matrixFits = (size_t)16 * C + 2 <= (size_t)c->maxPairs;
+    if (matrixFits)
+    {
+        bpBigCountDeviceKernel<<<1, 32, 0, c->stream>>>(C, cnt);
+        bpBigFlagKernel<<<G, kThreads, 0, c->stream>>>(C, c->aabbMin, c->aabbMax, c->bigList, bigFlags, cnt);
+        c->launches += 2;
+        scanExclusiveU32(c, bigFlags, bigOffs, &cnt->bigMatrixCount, 16u * C, nullptr);
+        bpBigCountKernel<<<1, 32, 0, c->stream>>>(C, c->bigList, bigOffs, c->pairCount, cnt);
+        c->launches += 1;
+    }
+    bpBigKernel<false><<<c->numSMs, kThreads, 0, c->stream>>>(C, matrixFits ? 16u : 0u, c->aabbMin, c->aabbMax, c->bigList, c->pairCount, c->pairStart, c->pairs, c->maxPairs, cnt);
     c->launches += 3;
     scanExclusiveU32(c, c->pairCount, c->pairStart, nullptr, C, nullptr);
     bpQueryKernel<true><<<G, kThreads, 0, c->stream>>>(c->sortedMin, c->sortedMax, c->cellStart, c->aabbMin, c->aabbMax, c->bigList, c->pairCount, c->pairStart, c->pairs, c->maxPairs, cnt);
-    bpBigKernel<true><<<c->numSMs, kThreads, 0, c->stream>>>(C, c->aabbMin, c->aabbMax, c->bigList, c->pairCount, c->pairStart, c->pairs, c->maxPairs, cnt);
+    if (matrixFits) { bpBigFillKernel<<<G, kThreads, 0, c->stream>>>(C, c->bigList, bigFlags, bigOffs, c->pairStart, c->pairs, c->maxPairs, cnt); c->launches += 1; }
+    bpBigKernel<true><<<c->numSMs, kThreads, 0, c->stream>>>(C, matrixFits ? 16u : 0u, c->aabbMin, c->aabbMax, c->bigList, c->pairCount, c->pairStart, c->pairs, c->maxPairs, cnt);
     bpFinishKernel<<<1, 32, 0, c->stream>>>(C, c->pairStart, c->maxPairs, cnt);
     c->launches += 3;
 }

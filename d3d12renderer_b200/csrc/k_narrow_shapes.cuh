@@ -524,7 +524,8 @@ struct EpaPoly
     uint16_t newEdgePerPoint[B200_EPA_MAX_POINTS];
     uint32_t nT, nP, nE;
 
-    B200_D bool isActive(uint32_t i) const { return (active[i >> 5] >> (i & 31)) & 1u; }
+    // an invalid index (0xFFFF left behind by a degenerate horizon; the reference reads out of bounds there) counts as inactive
+    B200_D bool isActive(uint32_t i) const { return i < nT && ((active[i >> 5] >> (i & 31)) & 1u); }
     B200_D void setActive(uint32_t i, bool on) { if (on) active[i >> 5] |= (1u << (i & 31)); else active[i >> 5] &= ~(1u << (i & 31)); }
     B200_D static void triInfo(const SupPt& a, const SupPt& b, const SupPt& c, f3& n, float& d)
     {   // collision_epa.cpp:5-11
@@ -558,11 +559,12 @@ struct EpaPoly
             if (!isActive(i)) continue;
             const EpaTri& t = tris[i];
             float d = dot(mk3(t.nx, t.ny, t.nz), np.m - pts[t.a].m);
-            if (d > 0.f) { ++refs[t.eA]; ++refs[t.eB]; ++refs[t.eC]; setActive(i, false); }
+            if (d > 0.f) { if (t.eA < nE) ++refs[t.eA]; if (t.eB < nE) ++refs[t.eB]; if (t.eC < nE) ++refs[t.eC]; setActive(i, false); }
         }
         uint16_t border[B200_EPA_MAX_BORDER]; uint32_t nBorder = 0;
         for (uint32_t i = 0; i < nE; ++i)
             if (refs[i] == 1) { if (nBorder >= B200_EPA_MAX_BORDER) return false; border[nBorder++] = (uint16_t)i; }
+        for (uint32_t i = 0; i <= nP && i < B200_EPA_MAX_POINTS; ++i) newEdgePerPoint[i] = 0xFFFF;
         int npi = pushPoint(np);
         if (npi < 0) return false;
         const uint16_t triOffset = (uint16_t)nT;
@@ -589,6 +591,7 @@ struct EpaPoly
             const uint16_t connect = bNew ? e.a : e.b;
             const uint16_t other = newEdgePerPoint[connect];
             const uint16_t triIndex = (uint16_t)(i + triOffset);
+            if (other == 0xFFFF) continue;
             tris[triIndex].eB = other;
             edges[other].t0 = triIndex;
         }

@@ -206,14 +206,18 @@ struct Polytope   // epa_simplex (collision_epa.h:45-67), same capacities
     // collision_epa.cpp:114-239
     bool addPoint(const SupPoint& np)
     {
+        // Degenerate horizons (two border edges ending in the same point) leave 0xFFFF indices behind; the reference then
+        // reads out of bounds (undefined behaviour). Defined here and on the device: an invalid index is "inactive" / skipped.
         static thread_local uint8_t refs[CAP];
+        auto isActive = [&](uint32_t i) { return i < nT && active[i]; };
+        auto refEdge = [&](uint32_t e) { if (e < nE) ++refs[e]; };
         for (uint32_t i = 0; i < nE; ++i) refs[i] = 0;
         for (uint32_t i = 0; i < nT; ++i)
         {
             if (!active[i]) continue;
             Tri& t = tris[i];
             float d = dot(t.n, np.m - pts[t.a].m);
-            if (d > 0.f) { ++refs[t.eA]; ++refs[t.eB]; ++refs[t.eC]; active[i] = false; }
+            if (d > 0.f) { refEdge(t.eA); refEdge(t.eB); refEdge(t.eC); active[i] = false; }
         }
         uint16_t border[BORDER_CAP]; uint32_t nBorder = 0;
         for (uint32_t i = 0; i < nE; ++i)
@@ -221,6 +225,7 @@ struct Polytope   // epa_simplex (collision_epa.h:45-67), same capacities
             if (refs[i] == 1) { if (nBorder >= BORDER_CAP) return false; border[nBorder++] = (uint16_t)i; }
         }
         static thread_local uint16_t newEdgePerPoint[CAP];
+        for (uint32_t i = 0; i <= nP && i < CAP; ++i) newEdgePerPoint[i] = 0xFFFF;
         int npi = pushPoint(np);
         if (npi < 0) return false;
         uint16_t triOffset = (uint16_t)nT;
@@ -228,7 +233,7 @@ struct Polytope   // epa_simplex (collision_epa.h:45-67), same capacities
         {
             uint16_t ei = border[i];
             Edge& e = edges[ei];
-            bool aAct = active[e.tri[0]], bAct = active[e.tri[1]];
+            bool aAct = isActive(e.tri[0]), bAct = isActive(e.tri[1]);
             uint16_t connect = bAct ? e.a : e.b;
             uint16_t triIndex = (uint16_t)nT;
             int ne = pushEdge(connect, (uint16_t)npi, 0xFFFF, (uint16_t)nT);
@@ -248,6 +253,7 @@ struct Polytope   // epa_simplex (collision_epa.h:45-67), same capacities
             uint16_t connect = bNew ? e.a : e.b;
             uint16_t other = newEdgePerPoint[connect];
             uint16_t triIndex = (uint16_t)(i + triOffset);
+            if (other == 0xFFFF) continue;
             tris[triIndex].eB = other;
             edges[other].tri[0] = triIndex;
         }
