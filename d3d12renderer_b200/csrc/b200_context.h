@@ -32,6 +32,7 @@ struct GridParams
 // device-resident scalars produced and consumed by kernels
 struct DeviceCounts
 {
+    uint32_t numEpaWork;                // GJK hits waiting for EPA this step
     uint32_t numPairs;                  // broad-phase overlaps (clamped to capacity)
     uint32_t numPairsWanted;            // what the scan produced (overflow detection)
     uint32_t keyStart[kNumPairKeys + 1];// bucket ranges of the classified pair list
@@ -112,6 +113,9 @@ struct Context
     uint2* pairsTyped = nullptr;      // type-ordered (collision_narrow.cpp:2374), not yet bucketed
     uint32_t* pairDst = nullptr;      // destination slot of the stable bucket sort
     uint2* pairsSorted = nullptr;     // bucketed, stable
+    float4* epaSimplex = nullptr;     // 9 planes x maxEpaWork: GJK terminal simplices parked for the EPA kernel
+    uint2* epaWork = nullptr;         // (sorted pair slot, bucket)
+    uint32_t maxEpaWork = 0;
     float4* manTmp = nullptr;         // 5 planes x maxPairs: (normal, count), 4 x (point, depth)
     unsigned long long* manScan = nullptr; // per pair (contacts << 32 | collided) and its exclusive scan
     unsigned long long* manScanOut = nullptr;

@@ -39,6 +39,7 @@ int allocateAll(Context& c)
     CK(devAlloc(c.pairCount, C + 2)); CK(devAlloc(c.pairStart, C + 2)); CK(devAlloc(c.pairs, P));
     CK(devAlloc(c.pairKey, P)); CK(devAlloc(c.pairsTyped, P)); CK(devAlloc(c.pairDst, P + 2)); CK(devAlloc(c.pairsSorted, P));
     CK(devAlloc(c.manTmp, 5 * P)); CK(devAlloc(c.manScan, P + 2)); CK(devAlloc(c.manScanOut, P + 2));
+    c.maxEpaWork = (uint32_t)M; CK(devAlloc(c.epaSimplex, 9 * M)); CK(devAlloc(c.epaWork, M));
     CK(devAlloc(c.collisions, M)); CK(devAlloc(c.manifolds, M)); CK(devAlloc(c.contacts, 2 * K)); CK(devAlloc(c.contactBodies, K));
     for (uint32_t gI = 0; gI < kNumGroups; ++gI)
     {
@@ -80,7 +81,7 @@ void freeAll(Context& c)
 {
     void* ptrs[] = { c.bRot, c.bPos, c.bCog, c.bInvI, c.bVel, c.bAng, c.bForce, c.bTorque, c.gVel, c.gPos, c.gInvI, c.cLocal, c.xforms, c.wCol, c.aabbMin, c.aabbMax,
         c.hullVerts, c.hullOffsets, c.hullAabb, c.cellOf, c.rankInCell, c.cellCount, c.cellStart, c.sortedMin, c.sortedMax, c.bigList, c.pairCount, c.pairStart, c.pairs,
-        c.pairKey, c.pairsTyped, c.pairDst, c.pairsSorted, c.manTmp, c.manScan, c.manScanOut, c.collisions, c.manifolds, c.contacts, c.contactBodies,
+        c.pairKey, c.pairsTyped, c.pairDst, c.pairsSorted, c.manTmp, c.manScan, c.manScanOut, c.epaSimplex, c.epaWork, c.collisions, c.manifolds, c.contacts, c.contactBodies,
         c.unitPending, c.unitForbid, c.nbrCount, c.nbrList, c.adjStart, c.adjFill, c.adjList, c.levelStart, c.levelFill, c.slotOfContact, c.unitSlotStart, c.unitInfo, c.rows, c.rowImp, c.scanTmp, c.scanTmp64, c.sortHist, c.staging, c.counts, c.haloBuf };
     for (void* p : ptrs) if (p) cudaFree(p);
     for (uint32_t g = 0; g < kNumGroups; ++g) { if (c.unitColor[g]) cudaFree(c.unitColor[g]); if (c.unitOrder[g]) cudaFree(c.unitOrder[g]); }

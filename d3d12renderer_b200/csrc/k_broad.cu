@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(kThreads) bpResetKernel(DeviceCounts* cnt)
     {
         cnt->extentSumFixed = 0ull; cnt->extentCount = 0; cnt->maxSmallExtentBits = 0; cnt->numBig = 0;
         for (int a = 0; a < 3; ++a) { cnt->centreMinBits[a] = 0xFFFFFFFFu; cnt->centreMaxBits[a] = 0u; }
-        cnt->numPairs = 0; cnt->numPairsWanted = 0;
+        cnt->numPairs = 0; cnt->numPairsWanted = 0; cnt->numEpaWork = 0;
     }
 }
 
@@ -381,7 +381,7 @@ void launchBroadphase(Context* c)
     // big colliders: parallel flag-matrix path for up to 16 of them (scratch: pair-sized buffers that are free until the narrow
     // phase); beyond that one CTA per big collider sweeps all colliders (bpBigKernel, skips the first 16)
     uint32_t* bigFlags = c->pairDst; uint32_t* bigOffs = (uint32_t*)c->manScan;
-    const bool matrixFits = (size_t)16 * C + 2 <= (size_t)c->maxPairs;
+    const bool matrixFits = (size_t)16 * C <= (size_t)c->maxPairs;   // both scratch buffers hold maxPairs + 2 words
     if (matrixFits)
     {
         bpBigCountDeviceKernel<<<1, 32, 0, c->stream>>>(C, cnt);

@@ -90,19 +90,18 @@ B200_D void flushCounters(const NarrowCounters& nc, DeviceCounts* cnt)
     if (nc.asserts) atomicAdd(&cnt->assertCount, nc.asserts);
 }
 
-// cost class 0: closed-form pairs (buckets 0,1,2,3,4,6,7,15); class 1: SAT + clipping (16,18); class 2: GJK + EPA (the rest)
+// cost class 0: closed-form pairs (buckets 0,1,2,3,4,6,7,15); class 1: SAT + clipping (16,18); the rest is GJK (+ EPA) based
 template <int CLASS>
-__global__ void __launch_bounds__(CLASS == 0 ? 256 : 128) npCollideKernel(const uint2* __restrict__ sorted, const float4* __restrict__ wCol, const float4* __restrict__ hullVerts,
-    const uint32_t* __restrict__ hullOffsets, float4* __restrict__ manTmp, unsigned long long* __restrict__ manScan, uint32_t maxPairs, DeviceCounts* cnt)
+__global__ void __launch_bounds__(CLASS == 0 ? 256 : 128) npCollideKernel(const uint2* __restrict__ sorted, const float4* __restrict__ wCol, float4* __restrict__ manTmp,
+    unsigned long long* __restrict__ manScan, uint32_t maxPairs, DeviceCounts* cnt)
 {
     constexpr uint32_t list0[8] = { 0, 1, 2, 3, 4, 6, 7, 15 };
     constexpr uint32_t list1[2] = { 16, 18 };
-    constexpr uint32_t list2[11] = { 5, 8, 9, 10, 11, 12, 13, 14, 17, 19, 20 };
-    constexpr int nList = CLASS == 0 ? 8 : (CLASS == 1 ? 2 : 11);
+    constexpr int nList = CLASS == 0 ? 8 : 2;
     NarrowCounters nc; nc.epaOverflow = nc.gjkCap = nc.asserts = 0;
     for (int li = 0; li < nList; ++li)
     {
-        const uint32_t bucket = CLASS == 0 ? list0[li] : (CLASS == 1 ? list1[li] : list2[li]);
+        const uint32_t bucket = CLASS == 0 ? list0[li] : list1[li];
         const uint32_t q0 = cnt->keyStart[bucket], q1 = cnt->keyStart[bucket + 1];
         for (uint32_t q = q0 + blockIdx.x * blockDim.x + threadIdx.x; q < q1; q += gridDim.x * blockDim.x)
         {
@@ -124,29 +123,78 @@ __global__ void __launch_bounds__(CLASS == 0 ? 256 : 128) npCollideKernel(const 
                 default: hit = boxBox(asBox(A), asBox(B), m); break;
                 }
             }
-            else if (CLASS == 1)
+            else
             {
                 if (bucket == 16) { const BoxS bx = asBox(A); ObbS o; o.q = qIdentity(); o.c = boxCenter(bx); o.r = boxRadius(bx); hit = obbObb(o, asObb(B), m); } // :1142-1148
                 else hit = obbObb(asObb(A), asObb(B), m);
             }
-            else
-            {
-                switch (bucket)
-                {
-                case 8:  hit = segmentShapeBox(asCap(A), false, asBox(B), m, nc); break;
-                case 9:  hit = segmentShapeObb(asCap(A), false, asObb(B), m, nc); break;
-                case 11: hit = cylinderCylinder(asCap(A), asCap(B), m, nc); break;
-                case 12: hit = segmentShapeBox(asCap(A), true, asBox(B), m, nc); break;
-                case 13: hit = segmentShapeObb(asCap(A), true, asObb(B), m, nc); break;
-                default:
-                {   // anything vs hull: 5 sphere, 10 capsule, 14 cylinder, 17 aabb, 19 obb, 20 hull (:496-520,792-818,1045-1071,1150-1176,1529-1584)
-                    const uint32_t ta = __float_as_uint(A.r3.x) & 0xFFu;
-                    hit = gjkEpa(supportFor(ta, A, hullVerts, hullOffsets), supHull(asHull(B, hullVerts, hullOffsets)), m, nc);
-                } break;
-                }
-            }
             storeManifold(manTmp, manScan, q, maxPairs, hit, m);
         }
+    }
+    flushCounters(nc, cnt);
+}
+
+// GJK/EPA-based buckets (5,8,9,10,11,12,13,14,17,19,20), shared by both phases
+template <class NC>
+B200_D bool collideGjkBucket(uint32_t bucket, const ColRec& A, const ColRec& B, const float4* __restrict__ hullVerts, const uint32_t* __restrict__ hullOffsets, Man& m, NC& nc)
+{
+    switch (bucket)
+    {
+    case 8:  return segmentShapeBox(asCap(A), false, asBox(B), m, nc);
+    case 9:  return segmentShapeObb(asCap(A), false, asObb(B), m, nc);
+    case 11: return cylinderCylinder(asCap(A), asCap(B), m, nc);
+    case 12: return segmentShapeBox(asCap(A), true, asBox(B), m, nc);
+    case 13: return segmentShapeObb(asCap(A), true, asObb(B), m, nc);
+    default:
+    {   // anything vs hull: 5 sphere, 10 capsule, 14 cylinder, 17 aabb, 19 obb, 20 hull (:496-520,792-818,1045-1071,1150-1176,1529-1584)
+        const uint32_t ta = __float_as_uint(A.r3.x) & 0xFFu;
+        return gjkEpa(supportFor(ta, A, hullVerts, hullOffsets), supHull(asHull(B, hullVerts, hullOffsets)), m, nc);
+    }
+    }
+}
+
+// phase 1: GJK for every pair of the GJK buckets; misses (and the closed-form exits of cylinder-cylinder) are final, hits are
+// parked with their simplex in the EPA work list
+__global__ void __launch_bounds__(128) npGjkKernel(const uint2* __restrict__ sorted, const float4* __restrict__ wCol, const float4* __restrict__ hullVerts,
+    const uint32_t* __restrict__ hullOffsets, float4* __restrict__ manTmp, unsigned long long* __restrict__ manScan, uint32_t maxPairs,
+    float4* __restrict__ sxPlanes, uint2* __restrict__ epaWork, uint32_t sxCap, DeviceCounts* cnt)
+{
+    constexpr uint32_t list2[11] = { 5, 8, 9, 10, 11, 12, 13, 14, 17, 19, 20 };
+    NarrowCtx<1> nc; nc.epaOverflow = nc.gjkCap = nc.asserts = 0; nc.sxPlanes = sxPlanes; nc.sxCap = sxCap; nc.sxCounter = &cnt->numEpaWork;
+    for (int li = 0; li < 11; ++li)
+    {
+        const uint32_t bucket = list2[li];
+        const uint32_t q0 = cnt->keyStart[bucket], q1 = cnt->keyStart[bucket + 1];
+        for (uint32_t q = q0 + blockIdx.x * blockDim.x + threadIdx.x; q < q1; q += gridDim.x * blockDim.x)
+        {
+            const uint2 pr = sorted[q];
+            const ColRec A = loadCol(wCol, pr.x), B = loadCol(wCol, pr.y);
+            Man m; m.cnt = 0;
+            nc.deferred = false;
+            const bool hit = collideGjkBucket(bucket, A, B, hullVerts, hullOffsets, m, nc);
+            storeManifold(manTmp, manScan, q, maxPairs, hit, m);
+            if (nc.deferred) { if (nc.sxEntry < sxCap) epaWork[nc.sxEntry] = make_uint2(q, bucket); else cnt->overflowManifolds = 1; }
+        }
+    }
+    flushCounters(nc, cnt);
+}
+
+// phase 2: EPA (and the routine's tail: clipping, transform back) for the parked pairs -- every lane has work
+__global__ void __launch_bounds__(128) npEpaKernel(const uint2* __restrict__ sorted, const float4* __restrict__ wCol, const float4* __restrict__ hullVerts,
+    const uint32_t* __restrict__ hullOffsets, float4* __restrict__ manTmp, unsigned long long* __restrict__ manScan, uint32_t maxPairs,
+    float4* __restrict__ sxPlanes, const uint2* __restrict__ epaWork, uint32_t sxCap, DeviceCounts* cnt)
+{
+    NarrowCtx<2> nc; nc.epaOverflow = nc.gjkCap = nc.asserts = 0; nc.sxPlanes = sxPlanes; nc.sxCap = sxCap; nc.sxCounter = nullptr; nc.deferred = false;
+    const uint32_t n = min(cnt->numEpaWork, sxCap);
+    for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x)
+    {
+        const uint2 w = epaWork[e];
+        const uint2 pr = sorted[w.x];
+        const ColRec A = loadCol(wCol, pr.x), B = loadCol(wCol, pr.y);
+        Man m; m.cnt = 0;
+        nc.sxEntry = e;
+        const bool hit = collideGjkBucket(w.y, A, B, hullVerts, hullOffsets, m, nc);
+        storeManifold(manTmp, manScan, w.x, maxPairs, hit, m);
     }
     flushCounters(nc, cnt);
 }
@@ -211,9 +259,11 @@ void launchNarrowphase(Context* c)
     c->launches += 1;
     stableSmallKeySort(c, c->pairKey, &cnt->numPairs, c->maxPairs, kNumPairKeys, c->pairDst, cnt->keyStart);
     npPermuteKernel<<<G, kThreads, 0, c->stream>>>(c->pairsTyped, c->pairDst, c->pairsSorted, cnt);
-    npCollideKernel<0><<<G, 256, 0, c->stream>>>(c->pairsSorted, c->wCol, c->hullVerts, c->hullOffsets, c->manTmp, c->manScan, c->maxPairs, cnt);
-    npCollideKernel<1><<<gridFor(c, 4), 128, 0, c->stream>>>(c->pairsSorted, c->wCol, c->hullVerts, c->hullOffsets, c->manTmp, c->manScan, c->maxPairs, cnt);
-    npCollideKernel<2><<<gridFor(c, 4), 128, 0, c->stream>>>(c->pairsSorted, c->wCol, c->hullVerts, c->hullOffsets, c->manTmp, c->manScan, c->maxPairs, cnt);
+    npCollideKernel<0><<<G, 256, 0, c->stream>>>(c->pairsSorted, c->wCol, c->manTmp, c->manScan, c->maxPairs, cnt);
+    npCollideKernel<1><<<gridFor(c, 4), 128, 0, c->stream>>>(c->pairsSorted, c->wCol, c->manTmp, c->manScan, c->maxPairs, cnt);
+    npGjkKernel<<<gridFor(c, 8), 128, 0, c->stream>>>(c->pairsSorted, c->wCol, c->hullVerts, c->hullOffsets, c->manTmp, c->manScan, c->maxPairs, c->epaSimplex, c->epaWork, c->maxEpaWork, cnt);
+    npEpaKernel<<<gridFor(c, 4), 128, 0, c->stream>>>(c->pairsSorted, c->wCol, c->hullVerts, c->hullOffsets, c->manTmp, c->manScan, c->maxPairs, c->epaSimplex, c->epaWork, c->maxEpaWork, cnt);
+    c->launches += 1;
     npClearTailKernel<<<G, kThreads, 0, c->stream>>>(c->manScan, cnt);
     c->launches += 5;
     scanExclusiveU64(c, c->manScan, c->manScanOut, &cnt->numPairs, c->maxPairs, nullptr);

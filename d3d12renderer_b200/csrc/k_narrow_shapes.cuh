@@ -18,6 +18,19 @@ struct ObbS { q4 q; f3 c, r; };
 struct HullS { q4 q; f3 p; const float4* verts; uint32_t n; };
 
 struct NarrowCounters { uint32_t epaOverflow, gjkCap, asserts; };
+struct SimplexD;
+// GJK and EPA run in separate kernels (k_narrow.cu): PHASE 1 = GJK only, a hit parks its simplex in a work list and the routine
+// reports "no manifold yet"; PHASE 2 = reload the simplex and continue from EPA. The arithmetic per pair is that of the fused
+// routine, only the lanes of the EPA warps are all busy and the GJK kernel carries no polytope.
+template <int PHASE> struct NarrowCtx : NarrowCounters
+{
+    static constexpr int phase = PHASE;
+    float4* sxPlanes;      // 9 planes of float4, plane stride sxCap
+    uint32_t sxCap;
+    uint32_t* sxCounter;   // PHASE 1: work-list size
+    uint32_t sxEntry;      // PHASE 1: entry written (valid when deferred); PHASE 2: entry to read
+    bool deferred;
+};
 
 // ------------------------------------------------------------------------------------------------------- helpers
 B200_D f3 closestPointSegment(f3 q, f3 a, f3 b)
@@ -637,10 +650,45 @@ B200_D void epa(const SimplexD& g, const SupportD& A, const SupportD& B, f3& out
     outDepth = t.dist;
 }
 
-B200_D bool gjkEpa(const SupportD& A, const SupportD& B, Man& m, NarrowCounters& nc)
+B200_D void storeSimplex(float4* __restrict__ pl, uint32_t cap, uint32_t e, const SimplexD& s)
+{
+    const SupPt* pt[4] = { &s.a, &s.b, &s.c, &s.d };
+    float v[36];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { v[9*i] = pt[i]->a.x; v[9*i+1] = pt[i]->a.y; v[9*i+2] = pt[i]->a.z; v[9*i+3] = pt[i]->b.x; v[9*i+4] = pt[i]->b.y; v[9*i+5] = pt[i]->b.z; v[9*i+6] = pt[i]->m.x; v[9*i+7] = pt[i]->m.y; v[9*i+8] = pt[i]->m.z; }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) pl[(size_t)k * cap + e] = make_float4(v[4*k], v[4*k+1], v[4*k+2], v[4*k+3]);
+}
+B200_D void loadSimplex(const float4* __restrict__ pl, uint32_t cap, uint32_t e, SimplexD& s)
+{
+    float v[36];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) { const float4 t = pl[(size_t)k * cap + e]; v[4*k] = t.x; v[4*k+1] = t.y; v[4*k+2] = t.z; v[4*k+3] = t.w; }
+    SupPt* pt[4] = { &s.a, &s.b, &s.c, &s.d };
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { pt[i]->a = mk3(v[9*i], v[9*i+1], v[9*i+2]); pt[i]->b = mk3(v[9*i+3], v[9*i+4], v[9*i+5]); pt[i]->m = mk3(v[9*i+6], v[9*i+7], v[9*i+8]); }
+    s.n = 4;
+}
+
+template <class NC>
+B200_D bool gjkEpa(const SupportD& A, const SupportD& B, Man& m, NC& nc)
 {
     SimplexD s;
-    if (!gjk(A, B, s, nc)) return false;
+    if (NC::phase == 1)
+    {
+        if (!gjk(A, B, s, nc)) return false;
+        // warp-aggregated append to the EPA work list
+        const uint32_t mask = __activemask();
+        const uint32_t lane = threadIdx.x & 31u, leader = (uint32_t)__ffs((int)mask) - 1u;
+        uint32_t base = 0;
+        if (lane == leader) base = atomicAdd(nc.sxCounter, (uint32_t)__popc(mask));
+        base = __shfl_sync(mask, base, (int)leader);
+        const uint32_t e = base + (uint32_t)__popc(mask & ((1u << lane) - 1u));
+        nc.sxEntry = e; nc.deferred = true;
+        if (e < nc.sxCap) storeSimplex(nc.sxPlanes, nc.sxCap, e, s);
+        return false;
+    }
+    loadSimplex(nc.sxPlanes, nc.sxCap, nc.sxEntry, s);
     f3 p, n; float d;
     epa(s, A, B, p, n, d, nc);
     m.n = n; m.cnt = 1; m.d[0] = d; m.p[0] = p;
@@ -649,7 +697,8 @@ B200_D bool gjkEpa(const SupportD& A, const SupportD& B, Man& m, NarrowCounters&
 
 // ------------------------------------------------------------------------------------- GJK/EPA-based shape pairs
 // capsule-aabb (:705-769) / cylinder-aabb (:953-1022)
-B200_D bool segmentShapeBox(const CapS& c, bool isCylinder, const BoxS& a, Man& m, NarrowCounters& nc)
+template <class NC>
+B200_D bool segmentShapeBox(const CapS& c, bool isCylinder, const BoxS& a, Man& m, NC& nc)
 {
     SupportD A = isCylinder ? supCylinder(c) : supCapsule(c);
     SupportD B = supBox(a);
@@ -676,7 +725,8 @@ B200_D bool segmentShapeBox(const CapS& c, bool isCylinder, const BoxS& a, Man& 
     return true;
 }
 // capsule-obb (:771-790) / cylinder-obb (:1024-1043)
-B200_D bool segmentShapeObb(const CapS& c, bool isCylinder, const ObbS& o, Man& m, NarrowCounters& nc)
+template <class NC>
+B200_D bool segmentShapeObb(const CapS& c, bool isCylinder, const ObbS& o, Man& m, NC& nc)
 {
     BoxS bb; bb.mn = o.c - o.r; bb.mx = o.c + o.r;
     CapS c_; c_.a = conjugate(o.q) * (c.a - o.c) + o.c; c_.b = conjugate(o.q) * (c.b - o.c) + o.c; c_.r = c.r;
@@ -689,7 +739,8 @@ B200_D bool segmentShapeObb(const CapS& c, bool isCylinder, const ObbS& o, Man& 
     return false;
 }
 // collision_narrow.cpp:821-951
-B200_D bool cylinderCylinder(const CapS& a, const CapS& b, Man& m, NarrowCounters& nc)
+template <class NC>
+B200_D bool cylinderCylinder(const CapS& a, const CapS& b, Man& m, NC& nc)
 {
     f3 aDir = a.b - a.a;
     f3 bDir = normalize(b.b - b.a);
