@@ -160,7 +160,7 @@ def main():
     from d3d12renderer_b200 import parallel
     sc = build_scene(rank, world)
     n_bodies = len(sc["bodies"]); n_col = len(sc["colliders"])
-    ghost_cap = 0 if world == 1 else 3 * 64 * 64 * 2
+    ghost_cap = 0 if world == 1 else 3 * 64 * 64      # ~2 layers of a 64 x 64 face are ghosts (8.1 k), 1.5x head room
     st = abi.Stepper(max_bodies=n_bodies + 2 * ghost_cap, max_colliders=n_col + 2 * ghost_cap, max_transforms=4, device=local_rank)
     stream = torch.cuda.Stream()          # a real (non-default) stream: every kernel of the context and the timing events share it
     torch.cuda.set_stream(stream)
@@ -182,7 +182,7 @@ def main():
 
     def do_step():
         if world > 1:
-            shard.refresh_ghosts()      # pack (device) -> NCCL send/recv with the two slab neighbours -> unpack (device)
+            shard.refresh_ghosts()      # pack (device) -> one batched NCCL send/recv of fixed-size messages with the slab neighbours -> unpack (device); no host sync
         st.step(DT, ITERATIONS, abi.STEP_FAST)
 
     def barrier():
@@ -265,7 +265,7 @@ def main():
             "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "262144-sphere settled pile per GPU (BASELINE configs[1]), 10 PGS iterations, dt 1/120, fast (coloured) solver order",
                        "bodies": total_bodies, "bodies_per_gpu": n_bodies, "iterations": ITERATIONS, "contacts_per_gpu": contacts, "pairs_per_gpu": pairs,
-                       "steps_per_s": K / (ms_dev * 1e-3), "parallelism": ("slab decomposition along x, %d x 262144 bodies, ghost-body halo over NCCL (%d ghost bodies on rank 0)" % (world, shard.last_ghosts[0])) if world > 1 else "single GPU",
+                       "steps_per_s": K / (ms_dev * 1e-3), "parallelism": ("slab decomposition along x, %d x 262144 bodies, ghost-body halo over NCCL (%d ghost bodies on rank 0)" % (world, shard.ghost_counts()[0])) if world > 1 else "single GPU",
                        "l2_policy": "per-step working set (rows, pair and manifold scratch, body planes) > 126 MB L2; no explicit flush",
                        "state_checksum_y": checksum},
             "e2e": {"value": e2e_value, "unit": "body-steps/s", "ms_per_step": ms_e2e / K, "h2d_bytes_per_step": int(n_bodies * (abi.body_state_dtype.itemsize + 24)),

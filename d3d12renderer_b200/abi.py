@@ -82,6 +82,7 @@ EXPORTS = [
     "b200phys_upload_forces", "b200phys_upload_body_states", "b200phys_step", "b200phys_synchronize", "b200phys_download_bodies", "b200phys_get_stats",
     "b200phys_download_aabbs", "b200phys_download_pairs", "b200phys_download_contacts", "b200phys_download_collisions",
     "b200phys_download_solve_order", "b200phys_halo_pack", "b200phys_halo_unpack", "b200phys_halo_clear", "b200phys_halo_record_bytes",
+    "b200phys_halo_message_bytes", "b200phys_halo_pack_message", "b200phys_halo_unpack_message",
 ]
 
 _lib = None
@@ -123,6 +124,9 @@ def load_library():
     lib.b200phys_halo_pack.argtypes = [vp, i32, f32, f32, vp, vp, u32, u32, C.POINTER(u32)]
     lib.b200phys_halo_unpack.argtypes = [vp, vp, u32, vp, u32]
     lib.b200phys_halo_clear.argtypes = [vp]
+    lib.b200phys_halo_message_bytes.restype = C.c_uint64; lib.b200phys_halo_message_bytes.argtypes = [u32, u32]
+    lib.b200phys_halo_pack_message.argtypes = [vp, i32, f32, f32, vp, u32, u32]
+    lib.b200phys_halo_unpack_message.argtypes = [vp, vp, u32, u32]
     lib.b200phys_halo_record_bytes.restype = u32; lib.b200phys_halo_record_bytes.argtypes = [i32]
     _lib = lib
     return lib
@@ -273,6 +277,16 @@ class Stepper:
 
     def halo_unpack(self, src_bodies_ptr, num_bodies, src_colliders_ptr, num_colliders):
         _check(self.lib, self.lib.b200phys_halo_unpack(self.ctx, C.c_void_p(src_bodies_ptr), num_bodies, C.c_void_p(src_colliders_ptr), num_colliders), "halo_unpack")
+
+    def halo_message_bytes(self, cap_bodies, cap_colliders):
+        return int(self.lib.b200phys_halo_message_bytes(cap_bodies, cap_colliders))
+
+    def halo_pack_message(self, axis, lo, hi, dst_ptr, cap_bodies, cap_colliders):
+        """Asynchronous: fills the fixed-size message at device pointer dst_ptr on the context's stream."""
+        _check(self.lib, self.lib.b200phys_halo_pack_message(self.ctx, axis, lo, hi, C.c_void_p(dst_ptr), cap_bodies, cap_colliders), "halo_pack_message")
+
+    def halo_unpack_message(self, src_ptr, cap_bodies, cap_colliders):
+        _check(self.lib, self.lib.b200phys_halo_unpack_message(self.ctx, C.c_void_p(src_ptr), cap_bodies, cap_colliders), "halo_unpack_message")
 
     def halo_clear(self):
         _check(self.lib, self.lib.b200phys_halo_clear(self.ctx), "halo_clear")

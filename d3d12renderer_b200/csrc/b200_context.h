@@ -44,7 +44,7 @@ struct DeviceCounts
     uint32_t numBig;
     uint32_t bigMatrixCount;            // min(numBig, 16) * C: size of the big-collider flag matrix
     uint32_t remaining;                 // colouring work counter
-    uint32_t overflowPairs, overflowManifolds, overflowGrid, overflowColors, overflowBig;
+    uint32_t overflowPairs, overflowManifolds, overflowGrid, overflowColors, overflowBig, overflowHalo;
     uint32_t epaOverflows, gjkIterationCaps, assertCount;
     unsigned long long extentSumFixed;  // sum of AABB extents, 2^-16 fixed point (deterministic mean)
     uint32_t extentCount;

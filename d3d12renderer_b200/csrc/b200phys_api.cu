@@ -318,7 +318,7 @@ int b200phys_get_stats(b200phys_context* ctx, b200phys_stats* out)
     out->numBroadphaseOverlaps = d.numPairs; out->numCollisions = d.numManifolds; out->numContacts = d.numContacts;
     out->numBigColliders = d.numBig; out->numGridCells = d.grid.numCells;
     for (int g = 0; g < 7; ++g) out->numColors[g] = d.numColors[g];
-    out->overflowPairs = d.overflowPairs; out->overflowManifolds = d.overflowManifolds; out->overflowGrid = d.overflowGrid | d.overflowBig | (d.overflowColors << 8);
+    out->overflowPairs = d.overflowPairs; out->overflowManifolds = d.overflowManifolds; out->overflowGrid = d.overflowGrid | d.overflowBig | (d.overflowColors << 8) | (d.overflowHalo << 16);
     out->epaOverflows = d.epaOverflows; out->gjkIterationCaps = d.gjkIterationCaps; out->assertCount = d.assertCount;
     out->cellSize = d.grid.cellSize;
     out->kernelLaunches = c.launches;
@@ -330,7 +330,7 @@ int b200phys_get_stats(b200phys_context* ctx, b200phys_stats* out)
         out->msWorld = ms[0]; out->msBroad = ms[1]; out->msNarrow = ms[2]; out->msInit = ms[3]; out->msSolve = ms[4]; out->msIntegrate = ms[5];
         cudaEventElapsedTime(&out->msTotal, c.ev[0], c.ev[6]);
     }
-    if (d.overflowPairs || d.overflowManifolds || d.overflowGrid || d.overflowBig || d.overflowColors) return B200PHYS_E_CAPACITY;
+    if (d.overflowPairs || d.overflowManifolds || d.overflowGrid || d.overflowBig || d.overflowColors || d.overflowHalo) return B200PHYS_E_CAPACITY;
     return 0;
 }
 

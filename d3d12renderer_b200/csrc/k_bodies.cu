@@ -174,6 +174,12 @@ __global__ void __launch_bounds__(kThreads) worldCollidersKernel(uint32_t C, uin
         const uint32_t tw = __float_as_uint(L3.y);
         uint32_t type = tw & 0xFFu; const uint32_t objType = (tw >> 8) & 0xFFu;
         const uint32_t objIndex = __float_as_uint(L3.z), parent = __float_as_uint(L3.w);
+        if (objType == B200PHYS_OBJ_NONE)
+        {   // padding slot of a fixed-size halo message: an inverted box overlaps nothing and is never binned
+            wCol[4 * i] = wCol[4 * i + 1] = wCol[4 * i + 2] = make_float4(0.f, 0.f, 0.f, 0.f); wCol[4 * i + 3] = make_float4(__uint_as_float(tw & 0xFFFFu), __uint_as_float(0xFFFFFFFFu), 0.f, 0.f);
+            aabbMin[i] = make_float4(FLT_MAX, FLT_MAX, FLT_MAX, 0.f); aabbMax[i] = make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, 0.f);
+            continue;
+        }
 
         // pose source (physics.cpp:645-647)
         q4 rot = qIdentity(); f3 pos = mk3(0.f);

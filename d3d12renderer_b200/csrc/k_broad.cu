@@ -74,6 +74,7 @@ __global__ void __launch_bounds__(kThreads) bpClassifyKernel(uint32_t C, float b
     {
         const float4 a = ldStream(mn + i), b = ldStream(mx + i);
         const float e = maxExtent(a, b);
+        if (a.x > b.x) { cellOf[i] = 0xFFFFFFFFu; continue; }   // inverted box = halo padding slot: neither binned nor big
         if (!(e <= threshold))
         {   // big (or non-finite): brute force
             const uint32_t k = atomicAdd(&cnt->numBig, 1u);

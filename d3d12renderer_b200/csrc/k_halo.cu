@@ -106,6 +106,58 @@ __global__ void __launch_bounds__(kThreads) haloUnpackCollidersKernel(uint32_t c
     }
 }
 
+__global__ void haloHeaderKernel(const uint32_t* __restrict__ nBodies, const uint32_t* __restrict__ nColliders, uint32_t* __restrict__ header)
+{
+    if (threadIdx.x == 0) { header[0] = *nBodies; header[1] = *nColliders; header[2] = 0; header[3] = 0; }
+}
+
+// fixed-size message: slots below the header counts are ghosts, the rest inert padding (zero-mass body, OBJ_NONE collider)
+__global__ void __launch_bounds__(kThreads) haloUnpackMessageKernel(const uint32_t* __restrict__ header, uint32_t capB, uint32_t capC, uint32_t bodyBase, uint32_t colBase, uint32_t planeStride,
+    const float* __restrict__ inBodies, const float4* __restrict__ inCols,
+    float4* __restrict__ bRot, float4* __restrict__ bPos, float4* __restrict__ bCog, float4* __restrict__ bInvI,
+    float4* __restrict__ bVel, float4* __restrict__ bAng, float4* __restrict__ bForce, float4* __restrict__ bTorque, float4* __restrict__ cLocal, DeviceCounts* cnt)
+{
+    const uint32_t nB = min(header[0], capB), nC = min(header[1], capC);
+    if (blockIdx.x == 0 && threadIdx.x == 0 && (header[0] > capB || header[1] > capC)) cnt->overflowHalo = 1;
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (uint32_t k = blockIdx.x * kThreads + threadIdx.x; k < capB; k += gridDim.x * kThreads)
+    {
+        const uint32_t i = bodyBase + k;
+        if (k < nB)
+        {
+            const float* b = inBodies + (size_t)k * kHaloBodyFloats;
+            bRot[i] = make_float4(b[0], b[1], b[2], b[3]);
+            bPos[i] = make_float4(b[4], b[5], b[6], b[10]);
+            bCog[i] = make_float4(b[7], b[8], b[9], b[20]);
+            bInvI[i] = make_float4(b[11], b[12], b[13], b[21]);
+            bInvI[planeStride + i] = make_float4(b[14], b[15], b[16], b[22]);
+            bInvI[2 * planeStride + i] = make_float4(b[17], b[18], b[19], 0.f);
+            bVel[i] = make_float4(b[23], b[24], b[25], 0.f); bAng[i] = make_float4(b[26], b[27], b[28], 0.f);
+            bForce[i] = make_float4(b[29], b[30], b[31], 0.f); bTorque[i] = make_float4(b[32], b[33], b[34], 0.f);
+        }
+        else
+        {
+            bRot[i] = make_float4(0.f, 0.f, 0.f, 1.f); bPos[i] = z; bCog[i] = z; bInvI[i] = z; bInvI[planeStride + i] = z; bInvI[2 * planeStride + i] = z;
+            bVel[i] = z; bAng[i] = z; bForce[i] = z; bTorque[i] = z;
+        }
+    }
+    for (uint32_t k = blockIdx.x * kThreads + threadIdx.x; k < capC; k += gridDim.x * kThreads)
+    {
+        const uint32_t i = colBase + k;
+        if (k < nC)
+        {
+            float4 L3 = inCols[4 * k + 3];
+            L3.z = __uint_as_float(__float_as_uint(L3.z) + bodyBase);
+            cLocal[4 * i] = inCols[4 * k]; cLocal[4 * i + 1] = inCols[4 * k + 1]; cLocal[4 * i + 2] = inCols[4 * k + 2]; cLocal[4 * i + 3] = L3;
+        }
+        else
+        {
+            cLocal[4 * i] = z; cLocal[4 * i + 1] = z; cLocal[4 * i + 2] = z;
+            cLocal[4 * i + 3] = make_float4(0.f, __uint_as_float((uint32_t)B200PHYS_SPHERE | ((uint32_t)B200PHYS_OBJ_NONE << 8)), __uint_as_float(0xFFFFFFFFu), __uint_as_float(B200PHYS_NO_TRANSFORM));
+        }
+    }
+}
+
 } // namespace b200
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return -(int)e_; } while (0)
@@ -116,13 +168,9 @@ uint32_t b200phys_halo_record_bytes(int which) { return which == 0 ? kHaloBodyFl
 
 // Packs every OWNED body (and all of its colliders) with a collider AABB overlapping [lo, hi) on `axis` into the caller's
 // device buffers (e.g. torch tensors); returns the counts through outCounts[2] = {bodies, colliders} (host, synchronous).
-int b200phys_halo_pack(b200phys_context* ctx, int axis, float lo, float hi, void* dstBodies, void* dstColliders, uint32_t capBodies, uint32_t capColliders, uint32_t* outCounts)
+static int haloPackDevice(Context& c, int axis, float lo, float hi, void* dstBodies, void* dstColliders, uint32_t capBodies, uint32_t capColliders, uint32_t* header, uint32_t* hostCounts)
 {
-    if (!ctx || axis < 0 || axis > 2 || !outCounts) return B200PHYS_E_INVALID;
-    Context& c = ctx->c; CK(cudaSetDevice(c.device));
     const uint32_t N = c.numOwnedBodies, C = c.numOwnedColliders;
-    outCounts[0] = outCounts[1] = 0;
-    if (!N || !C) return 0;
     // current world AABBs of the owned colliders (the step recomputes them, ghosts included)
     const uint32_t savedB = c.numBodies, savedC = c.numColliders;
     c.numBodies = N; c.numColliders = C;
@@ -138,17 +186,57 @@ int b200phys_halo_pack(b200phys_context* ctx, int axis, float lo, float hi, void
     scanExclusiveU32(&c, bodyFlag, bodySlot, nullptr, N, nullptr);
     haloColliderFlagKernel<<<G, kThreads, 0, c.stream>>>(C, N, c.cLocal, bodyFlag, colFlag);
     scanExclusiveU32(&c, colFlag, colSlot, nullptr, C, nullptr);
-    uint32_t counts[2] = { 0, 0 };
-    CK(cudaMemcpyAsync(&counts[0], bodySlot + N, 4, cudaMemcpyDeviceToHost, c.stream));
-    CK(cudaMemcpyAsync(&counts[1], colSlot + C, 4, cudaMemcpyDeviceToHost, c.stream));
+    if (hostCounts)
+    {
+        CK(cudaMemcpyAsync(&hostCounts[0], bodySlot + N, 4, cudaMemcpyDeviceToHost, c.stream));
+        CK(cudaMemcpyAsync(&hostCounts[1], colSlot + C, 4, cudaMemcpyDeviceToHost, c.stream));
+    }
+    if (header) haloHeaderKernel<<<1, 32, 0, c.stream>>>(bodySlot + N, colSlot + C, header);
     if (dstBodies && capBodies)
         haloPackBodiesKernel<<<G, kThreads, 0, c.stream>>>(N, c.cfg.maxBodies + 1, bodyFlag, bodySlot, capBodies, c.bRot, c.bPos, c.bCog, c.bInvI, c.bVel, c.bAng, c.bForce, c.bTorque, (float*)dstBodies);
     if (dstColliders && capColliders)
         haloPackCollidersKernel<<<G, kThreads, 0, c.stream>>>(C, colFlag, colSlot, capColliders, bodySlot, c.cLocal, (float4*)dstColliders);
-    CK(cudaStreamSynchronize(c.stream));
     CK(cudaGetLastError());
+    return 0;
+}
+
+int b200phys_halo_pack(b200phys_context* ctx, int axis, float lo, float hi, void* dstBodies, void* dstColliders, uint32_t capBodies, uint32_t capColliders, uint32_t* outCounts)
+{
+    if (!ctx || axis < 0 || axis > 2 || !outCounts) return B200PHYS_E_INVALID;
+    Context& c = ctx->c; CK(cudaSetDevice(c.device));
+    outCounts[0] = outCounts[1] = 0;
+    if (!c.numOwnedBodies || !c.numOwnedColliders) return 0;
+    uint32_t counts[2] = { 0, 0 };
+    int rc = haloPackDevice(c, axis, lo, hi, dstBodies, dstColliders, capBodies, capColliders, nullptr, counts);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(c.stream));
     outCounts[0] = counts[0]; outCounts[1] = counts[1];
     if (counts[0] > capBodies || counts[1] > capColliders) return B200PHYS_E_CAPACITY;
+    return 0;
+}
+
+uint64_t b200phys_halo_message_bytes(uint32_t capBodies, uint32_t capColliders) { return 16ull + (uint64_t)capBodies * kHaloBodyFloats * 4ull + (uint64_t)capColliders * kHaloColliderFloats * 4ull; }
+
+// Asynchronous on the context's stream; nothing returns to the host.
+int b200phys_halo_pack_message(b200phys_context* ctx, int axis, float lo, float hi, void* dstMessageDev, uint32_t capBodies, uint32_t capColliders)
+{
+    if (!ctx || axis < 0 || axis > 2 || !dstMessageDev) return B200PHYS_E_INVALID;
+    Context& c = ctx->c; CK(cudaSetDevice(c.device));
+    char* base = (char*)dstMessageDev;
+    if (!c.numOwnedBodies || !c.numOwnedColliders) { CK(cudaMemsetAsync(base, 0, 16, c.stream)); return 0; }
+    return haloPackDevice(c, axis, lo, hi, base + 16, base + 16 + (size_t)capBodies * kHaloBodyFloats * 4, capBodies, capColliders, (uint32_t*)base, nullptr);
+}
+
+int b200phys_halo_unpack_message(b200phys_context* ctx, const void* srcMessageDev, uint32_t capBodies, uint32_t capColliders)
+{
+    if (!ctx || !srcMessageDev) return B200PHYS_E_INVALID;
+    Context& c = ctx->c; CK(cudaSetDevice(c.device));
+    if (c.numBodies + capBodies > c.cfg.maxBodies || c.numColliders + capColliders > c.cfg.maxColliders) return B200PHYS_E_CAPACITY;
+    const char* base = (const char*)srcMessageDev;
+    haloUnpackMessageKernel<<<gridFor(&c, 4), kThreads, 0, c.stream>>>((const uint32_t*)base, capBodies, capColliders, c.numBodies, c.numColliders, c.cfg.maxBodies + 1,
+        (const float*)(base + 16), (const float4*)(base + 16 + (size_t)capBodies * kHaloBodyFloats * 4), c.bRot, c.bPos, c.bCog, c.bInvI, c.bVel, c.bAng, c.bForce, c.bTorque, c.cLocal, c.counts);
+    c.numBodies += capBodies; c.numColliders += capColliders;
+    CK(cudaGetLastError());
     return 0;
 }
 

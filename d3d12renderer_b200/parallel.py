@@ -66,40 +66,62 @@ def exchange_with_neighbours(send, rank, world, device, group=None):
     return recv
 
 
-class SlabShard:
-    """One rank's shard: wraps a Stepper whose uploaded bodies are the OWNED ones and keeps its ghost layer fresh."""
+def exchange_fixed(send, recv, group=None):
+    """One round of point-to-point operations on FIXED-size messages: send[peer] -> peer, recv[peer] <- peer (tensors of the same
+    size on both sides). On CUDA tensors (NCCL) wait() only orders torch's current stream behind the transfer: no host sync."""
+    ops = []
+    for p in sorted(send.keys()):
+        ops.append(dist.P2POp(dist.isend, send[p], p, group)); ops.append(dist.P2POp(dist.irecv, recv[p], p, group))
+    if ops:
+        for r in dist.batch_isend_irecv(ops):
+            r.wait()
 
-    def __init__(self, stepper, rank, world, bounds, axis=0, ghost_width=1.05, max_ghost_bodies=1 << 18, max_ghost_colliders=1 << 18, device=None):
+
+class SlabShard:
+    """One rank's shard: wraps a Stepper whose uploaded bodies are the OWNED ones and keeps its ghost layer fresh.
+
+    Per step and neighbour one fixed-size message ([counts][cap body records][cap collider records], b200phys_halo_pack_message)
+    goes each way; the receiver appends all slots, the unused ones as inert padding, so no count ever travels through the host:
+    pack kernels -> one batched NCCL send/recv -> unpack kernel, all stream-ordered. The Stepper's stream must be torch's
+    current stream (`torch.cuda.set_stream`) so that NCCL orders itself against the pack and unpack kernels."""
+
+    def __init__(self, stepper, rank, world, bounds, axis=0, ghost_width=1.05, max_ghost_bodies=1 << 14, max_ghost_colliders=1 << 14, device=None):
         self.st = stepper; self.rank = rank; self.world = world; self.bounds = bounds; self.axis = axis; self.ghost_width = ghost_width
         self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.regions = ghost_regions(rank, world, bounds, ghost_width)
-        self.send_bodies = {p: torch.empty((max_ghost_bodies, BODY_RECORD_FLOATS), dtype=torch.float32, device=self.device) for p, _, _ in self.regions}
-        self.send_colliders = {p: torch.empty((max_ghost_colliders, COLLIDER_RECORD_FLOATS), dtype=torch.float32, device=self.device) for p, _, _ in self.regions}
-        self.last_ghosts = (0, 0)
-        self._recv_keepalive = None
+        self.cap_b = int(max_ghost_bodies); self.cap_c = int(max_ghost_colliders)
+        words = stepper.halo_message_bytes(self.cap_b, self.cap_c) // 4
+        self.send_msg = {p: torch.zeros(words, dtype=torch.float32, device=self.device) for p, _, _ in self.regions}
+        self.recv_msg = {p: torch.zeros(words, dtype=torch.float32, device=self.device) for p, _, _ in self.regions}
+
+    @staticmethod
+    def measure(stepper, rank, world, bounds, axis=0, ghost_width=1.05):
+        """(bodies, colliders) the largest ghost region of this rank would send right now (synchronous; for sizing the messages)."""
+        nb = nc = 0
+        for _, lo, hi in ghost_regions(rank, world, bounds, ghost_width):
+            b, c = stepper.halo_pack(axis, lo, hi, 0, 0, 0x7FFFFFFF, 0x7FFFFFFF)
+            nb = max(nb, b); nc = max(nc, c)
+        return nb, nc
 
     def refresh_ghosts(self):
-        """halo_clear -> pack per neighbour (device kernels) -> neighbour exchange -> unpack. Call before every step."""
+        """halo_clear -> pack per neighbour -> neighbour exchange -> unpack; asynchronous, call before every step."""
         st = self.st
         st.halo_clear()
         if self.world == 1:
             return
-        send = {}
         for peer, lo, hi in self.regions:
-            sb, sc = self.send_bodies[peer], self.send_colliders[peer]
-            nb, nc = st.halo_pack(self.axis, lo, hi, sb.data_ptr(), sc.data_ptr(), sb.shape[0], sc.shape[0])
-            send[peer] = (sb[:nb], sc[:nc])
-        recv = exchange_with_neighbours(send, self.rank, self.world, self.device)
+            st.halo_pack_message(self.axis, lo, hi, self.send_msg[peer].data_ptr(), self.cap_b, self.cap_c)
+        exchange_fixed(self.send_msg, self.recv_msg)
+        for peer in sorted(self.recv_msg.keys()):
+            st.halo_unpack_message(self.recv_msg[peer].data_ptr(), self.cap_b, self.cap_c)
+
+    def ghost_counts(self):
+        """(bodies, colliders) received in the last exchange, summed over neighbours (reads the message headers: synchronous)."""
         tb = tc = 0
-        for peer in sorted(recv.keys()):
-            b, c = recv[peer]
-            if self.device.type == "cuda":
-                torch.cuda.current_stream().synchronize()   # the receive completed on torch's stream; unpack runs on the stepper's
-            st.halo_unpack(b.data_ptr(), b.shape[0], c.data_ptr(), c.shape[0])
-            tb += b.shape[0]; tc += c.shape[0]
-        st.synchronize()
-        self._recv_keepalive = recv
-        self.last_ghosts = (tb, tc)
+        for p in self.recv_msg:
+            h = self.recv_msg[p][:2].view(torch.int32).cpu()
+            tb += int(h[0]); tc += int(h[1])
+        return tb, tc
 
     def step(self, dt, iterations, flags=0):
         self.refresh_ghosts()

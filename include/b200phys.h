@@ -38,7 +38,8 @@ enum { B200PHYS_SPHERE = 0, B200PHYS_CAPSULE = 1, B200PHYS_CYLINDER = 2, B200PHY
        B200PHYS_COLLIDER_TYPE_COUNT = 6 };
 
 /* physics_object_type (reference src/physics/physics.h:49-57) */
-enum { B200PHYS_OBJ_RIGID_BODY = 0, B200PHYS_OBJ_STATIC = 1, B200PHYS_OBJ_FORCE_FIELD = 2, B200PHYS_OBJ_TRIGGER = 3 };
+enum { B200PHYS_OBJ_RIGID_BODY = 0, B200PHYS_OBJ_STATIC = 1, B200PHYS_OBJ_FORCE_FIELD = 2, B200PHYS_OBJ_TRIGGER = 3,
+       B200PHYS_OBJ_NONE = 255 /* inert padding slot (fixed-size halo messages); overlaps nothing */ };
 
 /* constraint_type (reference src/physics/constraints.h:14-28); also the per-iteration kind order (constraints.cpp:3748-3772) */
 enum { B200PHYS_JOINT_DISTANCE = 0, B200PHYS_JOINT_BALL = 1, B200PHYS_JOINT_FIXED = 2, B200PHYS_JOINT_HINGE = 3,
@@ -248,6 +249,14 @@ int b200phys_halo_pack(b200phys_context* ctx, int axis, float lo, float hi, void
                        uint32_t capBodies, uint32_t capColliders, uint32_t* outCounts);
 /* appends received ghost bodies / colliders behind the owned ones; they take part in the next step, their results are discarded */
 int b200phys_halo_unpack(b200phys_context* ctx, const void* srcBodiesDevice, uint32_t numBodies, const void* srcCollidersDevice, uint32_t numColliders);
+/* Fixed-size halo messages (no host round trip): [uint32 numBodies, numColliders, 0, 0][capBodies body records][capColliders
+ * collider records]. pack_message fills a device buffer asynchronously on the context's stream; unpack_message appends ALL
+ * capBodies + capColliders slots behind the current bodies / colliders, the ones beyond the counts in the header as inert
+ * padding (B200PHYS_OBJ_NONE), so the host never needs the counts. A header count above the capacity raises the sticky
+ * overflow flag (b200phys_get_stats -> B200PHYS_E_CAPACITY, overflowGrid bit 16). */
+uint64_t b200phys_halo_message_bytes(uint32_t capBodies, uint32_t capColliders);
+int b200phys_halo_pack_message(b200phys_context* ctx, int axis, float lo, float hi, void* dstMessageDev, uint32_t capBodies, uint32_t capColliders);
+int b200phys_halo_unpack_message(b200phys_context* ctx, const void* srcMessageDev, uint32_t capBodies, uint32_t capColliders);
 int b200phys_halo_clear(b200phys_context* ctx);
 
 #ifdef __cplusplus

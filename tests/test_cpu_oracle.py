@@ -199,7 +199,7 @@ def test_cuda_library_loads_and_exports_every_declared_symbol():
     assert lib.b200phys_version() == 1
     header = open(os.path.join(ROOT, "include", "b200phys.h")).read()
     import re
-    declared = sorted(set(re.findall(r"^(?:int|uint32_t|void\*?|const char\*)\s+(b200phys_[a-z_]+)\s*\(", header, flags=re.M)))
+    declared = sorted(set(re.findall(r"^(?:int|uint32_t|uint64_t|void\*?|const char\*)\s+(b200phys_[a-z_]+)\s*\(", header, flags=re.M)))
     assert declared, "no declarations found"
     for name in declared:
         assert hasattr(lib, name), "libb200phys.so does not export %s" % name

@@ -34,6 +34,12 @@ def _worker(rank, world, port, results):
         send2 = {p: (torch.empty((0, parallel.BODY_RECORD_FLOATS)), torch.empty((0, parallel.COLLIDER_RECORD_FLOATS))) for p in send}
         recv2 = parallel.exchange_with_neighbours(send2, rank, world, dev)
         ok &= all(b.shape[0] == 0 and c.shape[0] == 0 for b, c in recv2.values())
+        # the per-step protocol: one fixed-size message per neighbour and direction, header = counts, tail = padding
+        words = 4 + 8 * parallel.BODY_RECORD_FLOATS + 8 * parallel.COLLIDER_RECORD_FLOATS
+        out = {p: torch.full((words,), float(1000 * rank + p)) for p in send}
+        inn = {p: torch.zeros(words) for p in send}
+        parallel.exchange_fixed(out, inn)
+        ok &= all(bool(torch.all(inn[p] == float(1000 * p + rank))) for p in inn)
         results[rank] = bool(ok) and set(recv.keys()) == set(send.keys())
     finally:
         dist.destroy_process_group()
