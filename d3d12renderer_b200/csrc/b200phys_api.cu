@@ -32,6 +32,7 @@ int allocateAll(Context& c)
     CK(devAlloc(c.bRot, N1)); CK(devAlloc(c.bPos, N1)); CK(devAlloc(c.bCog, N1)); CK(devAlloc(c.bInvI, 3 * N1));
     CK(devAlloc(c.bVel, N1)); CK(devAlloc(c.bAng, N1)); CK(devAlloc(c.bForce, N1)); CK(devAlloc(c.bTorque, N1));
     CK(devAlloc(c.gVel, 2 * N1)); CK(devAlloc(c.gPos, N1)); CK(devAlloc(c.gInvI, 3 * N1));
+    CK(devAlloc(c.bodyMask, N1 + 1)); CK(devAlloc(c.bodyBase, N1 + 1));
     CK(devAlloc(c.cLocal, 4 * C)); CK(devAlloc(c.xforms, 2 * T)); CK(devAlloc(c.wCol, 4 * C)); CK(devAlloc(c.aabbMin, C)); CK(devAlloc(c.aabbMax, C));
     CK(devAlloc(c.hullVerts, 1)); CK(devAlloc(c.hullOffsets, 2)); CK(devAlloc(c.hullAabb, 2));
     CK(devAlloc(c.cellOf, C)); CK(devAlloc(c.rankInCell, C)); CK(devAlloc(c.cellCount, (size_t)c.maxCells + 2)); CK(devAlloc(c.cellStart, (size_t)c.maxCells + 2));
@@ -44,7 +45,7 @@ int allocateAll(Context& c)
     for (uint32_t gI = 0; gI < kNumGroups; ++gI)
     {
         const size_t units = (gI == 6) ? M : J;
-        CK(devAlloc(c.unitColor[gI], units)); CK(devAlloc(c.unitOrder[gI], units));
+        CK(devAlloc(c.unitColor[gI], units)); CK(devAlloc(c.unitOrder[gI], units)); CK(devAlloc(c.unitDep[gI], units));
     }
     CK(devAlloc(c.unitPending, (M > J ? M : J))); CK(devAlloc(c.nbrCount, (M > J ? M : J))); CK(devAlloc(c.nbrList, 16 * (M > J ? M : J))); CK(devAlloc(c.unitForbid, (M > J ? M : J)));
     CK(devAlloc(c.adjStart, N1 + 2)); CK(devAlloc(c.adjFill, N1 + 2)); CK(devAlloc(c.adjList, 2 * (M > J ? M : J)));
@@ -79,12 +80,12 @@ int allocateAll(Context& c)
 
 void freeAll(Context& c)
 {
-    void* ptrs[] = { c.bRot, c.bPos, c.bCog, c.bInvI, c.bVel, c.bAng, c.bForce, c.bTorque, c.gVel, c.gPos, c.gInvI, c.cLocal, c.xforms, c.wCol, c.aabbMin, c.aabbMax,
+    void* ptrs[] = { c.bRot, c.bPos, c.bCog, c.bInvI, c.bVel, c.bAng, c.bForce, c.bTorque, c.gVel, c.gPos, c.gInvI, c.bodyMask, c.bodyBase, c.cLocal, c.xforms, c.wCol, c.aabbMin, c.aabbMax,
         c.hullVerts, c.hullOffsets, c.hullAabb, c.cellOf, c.rankInCell, c.cellCount, c.cellStart, c.sortedMin, c.sortedMax, c.bigList, c.pairCount, c.pairStart, c.pairs,
         c.pairKey, c.pairsTyped, c.pairDst, c.pairsSorted, c.manTmp, c.manScan, c.manScanOut, c.epaSimplex, c.epaWork, c.collisions, c.manifolds, c.contacts, c.contactBodies,
         c.unitPending, c.unitForbid, c.nbrCount, c.nbrList, c.adjStart, c.adjFill, c.adjList, c.levelStart, c.levelFill, c.slotOfContact, c.unitSlotStart, c.unitInfo, c.rows, c.rowImp, c.scanTmp, c.scanTmp64, c.sortHist, c.staging, c.counts, c.haloBuf };
     for (void* p : ptrs) if (p) cudaFree(p);
-    for (uint32_t g = 0; g < kNumGroups; ++g) { if (c.unitColor[g]) cudaFree(c.unitColor[g]); if (c.unitOrder[g]) cudaFree(c.unitOrder[g]); }
+    for (uint32_t g = 0; g < kNumGroups; ++g) { if (c.unitColor[g]) cudaFree(c.unitColor[g]); if (c.unitOrder[g]) cudaFree(c.unitOrder[g]); if (c.unitDep[g]) cudaFree(c.unitDep[g]); }
     for (int k = 0; k < 6; ++k) { if (c.jointIn[k]) cudaFree(c.jointIn[k]); if (c.jointBodies[k]) cudaFree(c.jointBodies[k]); if (c.jointRows[k]) cudaFree(c.jointRows[k]); }
     if (c.hostCounts) cudaFreeHost(c.hostCounts);
     for (int i = 0; i < 8; ++i) if (c.ev[i]) cudaEventDestroy(c.ev[i]);

@@ -134,9 +134,9 @@ __global__ void __launch_bounds__(kThreads) integrateForcesKernel(uint32_t N, fl
         v *= 1.f / (1.f + dt * linDamp);
         w *= 1.f / (1.f + dt * angDamp);
 
-        gVel[2 * i] = mk4(v, invMass);
+        gVel[2 * i] = mk4(v, 0.f);          // .w of both halves: update counter of the dataflow solver (k_solver.cu), 0 = start of step
         gVel[2 * i + 1] = mk4(w, 0.f);
-        gPos[i] = mk4(cogPos, 0.f);
+        gPos[i] = mk4(cogPos, invMass);
         gInvI[3 * i] = mk4(m3Row(Iw, 0), 0.f);
         gInvI[3 * i + 1] = mk4(m3Row(Iw, 1), 0.f);
         gInvI[3 * i + 2] = mk4(m3Row(Iw, 2), 0.f);
@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(kThreads) integrateVelocitiesKernel(uint32_t N
         const f3 pos = xyz(p4) + v * dt;
         const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
         bRot[i] = mk4(rot);
-        bPos[i] = mk4(pos - rot * xyz(cog4), v4.w);   // .w keeps invMass
+        bPos[i] = mk4(pos - rot * xyz(cog4), p4.w);   // .w keeps invMass
         bVel[i] = mk4(v, 0.f); bAng[i] = mk4(w, 0.f);
         bForce[i] = z; bTorque[i] = z;
     }

@@ -53,6 +53,8 @@ struct JointSolveArgs
     const uint32_t* order[6];       // joints sorted by colour
     const uint32_t* colorStart[6];  // colour ranges
     void* rows[6];                  // row of joint j = rows[kind][j]
+    const uint2* bodies[6];         // body pair of joint j
+    const uint2* dep[6];            // dataflow record of solve position p (see k_solver.cu)
 };
 
 // body global state as the joint code sees it (rigid_body_global_state, rigid_body.h:6-16)
@@ -71,7 +73,7 @@ B200_D BodyGD loadBodyG(uint32_t b, uint32_t N, const float4* __restrict__ bRot,
     BodyGD g;
     if (b >= N) { g.rot = mkq(0.f, 0.f, 0.f, 0.f); g.cog = mk3(0.f); }   // memset dummy (physics.cpp:1279)
     else { g.rot = toq(bRot[b]); g.cog = xyz(bCog[b]); }
-    g.pos = xyz(gPos[b]); g.I = loadInvInertiaJ(gInvI, b); g.invMass = gVel[2 * b].w;
+    g.pos = xyz(gPos[b]); g.I = loadInvInertiaJ(gInvI, b); g.invMass = gPos[b].w;
     return g;
 }
 B200_D f3 ld3p(const float* p) { return mk3(p[0], p[1], p[2]); }
@@ -369,41 +371,35 @@ __global__ void __launch_bounds__(128) initJointsKernel(JointInitArgs P)
 
 // ------------------------------------------------------------------------------------------------------ solving
 struct BodyVel { f3 v, w; float invMass; };
-B200_D BodyVel loadVel(const float4* gVel, uint32_t b) { const float4 a = ldCg(gVel + 2 * b), c = ldCg(gVel + 2 * b + 1); BodyVel r; r.v = xyz(a); r.w = xyz(c); r.invMass = a.w; return r; }
-B200_D void storeVel(float4* gVel, uint32_t b, const BodyVel& s) { if (s.invMass != 0.f) { stCg(gVel + 2 * b, mk4(s.v, s.invMass)); stCg(gVel + 2 * b + 1, mk4(s.w, 0.f)); } }
 
-B200_D void solveJoint(int kind, const JointSolveArgs& J, uint32_t p, float4* __restrict__ gVel, const float4* __restrict__ gInvI)
+// one joint (index i of its kind) applied to the velocities of its two bodies; the caller (k_solver.cu) loads A and B when the
+// dataflow counters say they are current, and stores them afterwards
+B200_D void solveJoint(int kind, const JointSolveArgs& J, uint32_t i, BodyVel& A, BodyVel& B, const float4* __restrict__ gInvI)
 {
-    const uint32_t i = J.order[kind][p];
     switch (kind)
     {
     case 0: // constraints.cpp:242-264
     {
         const DistanceRowD c = ((const DistanceRowD*)J.rows[0])[i];
-        BodyVel A = loadVel(gVel, c.a), B = loadVel(gVel, c.b);
         const f3 avA = A.v + cross(A.w, c.rA), avB = B.v + cross(B.w, c.rB);
         const float Cdot = dot(c.u, avB - avA) + c.bias;
         const float lambda = -c.mass * Cdot;
         const f3 P = lambda * c.u;
         A.v -= A.invMass * P; A.w -= c.angA * lambda; B.v += B.invMass * P; B.w += c.angB * lambda;
-        storeVel(gVel, c.a, A); storeVel(gVel, c.b, B);
     } break;
     case 1: // constraints.cpp:505-528
     {
         const BallRowD c = ((const BallRowD*)J.rows[1])[i];
-        BodyVel A = loadVel(gVel, c.a), B = loadVel(gVel, c.b);
         const m3 IA = loadInvInertiaJ(gInvI, c.a), IB = loadInvInertiaJ(gInvI, c.b);
         const f3 avA = A.v + cross(A.w, c.rA), avB = B.v + cross(B.w, c.rB);
         const f3 Cdot = avB - avA + c.bias;
         const f3 P = solve3(c.invMass, -Cdot);
         A.v -= A.invMass * P; A.w -= IA * cross(c.rA, P);
         B.v += B.invMass * P; B.w += IB * cross(c.rB, P);
-        storeVel(gVel, c.a, A); storeVel(gVel, c.b, B);
     } break;
     case 2: // constraints.cpp:788-823
     {
         const FixedRowD c = ((const FixedRowD*)J.rows[2])[i];
-        BodyVel A = loadVel(gVel, c.a), B = loadVel(gVel, c.b);
         const m3 IA = loadInvInertiaJ(gInvI, c.a), IB = loadInvInertiaJ(gInvI, c.b);
         {
             const f3 Cdot = B.w - A.w;
@@ -417,13 +413,11 @@ B200_D void solveJoint(int kind, const JointSolveArgs& J, uint32_t p, float4* __
             A.v -= A.invMass * P; A.w -= IA * cross(c.rA, P);
             B.v += B.invMass * P; B.w += IB * cross(c.rB, P);
         }
-        storeVel(gVel, c.a, A); storeVel(gVel, c.b, B);
     } break;
     case 3: // constraints.cpp:1215-1307 : motor -> limit -> rotation -> position
     {
         HingeRowD* row = ((HingeRowD*)J.rows[3]) + i;
         const HingeRowD c = *row;
-        BodyVel A = loadVel(gVel, c.a), B = loadVel(gVel, c.b);
         const m3 IA = loadInvInertiaJ(gInvI, c.a), IB = loadInvInertiaJ(gInvI, c.b);
         f3 vA = A.v, wA = A.w, vB = B.v, wB = B.w;
         const f3 axis = c.axis;
@@ -464,13 +458,11 @@ B200_D void solveJoint(int kind, const JointSolveArgs& J, uint32_t p, float4* __
             vB += B.invMass * P; wB += IB * cross(c.rB, P);
         }
         A.v = vA; A.w = wA; B.v = vB; B.w = wB;
-        storeVel(gVel, c.a, A); storeVel(gVel, c.b, B);
     } break;
     case 4: // constraints.cpp:1955-2070 : twist motor -> swing motor -> twist limit -> swing limit -> position
     {
         ConeTwistRowD* row = ((ConeTwistRowD*)J.rows[4]) + i;
         const ConeTwistRowD c = *row;
-        BodyVel A = loadVel(gVel, c.a), B = loadVel(gVel, c.b);
         const m3 IA = loadInvInertiaJ(gInvI, c.a), IB = loadInvInertiaJ(gInvI, c.b);
         f3 vA = A.v, wA = A.w, vB = B.v, wB = B.w;
         const f3 tw = c.twistAxis;
@@ -524,13 +516,11 @@ B200_D void solveJoint(int kind, const JointSolveArgs& J, uint32_t p, float4* __
             vB += B.invMass * P; wB += IB * cross(c.rB, P);
         }
         A.v = vA; A.w = wA; B.v = vB; B.w = wB;
-        storeVel(gVel, c.a, A); storeVel(gVel, c.b, B);
     } break;
     default: // slider, constraints.cpp:2763-2846 : motor -> limit -> rotation -> position
     {
         SliderRowD* row = ((SliderRowD*)J.rows[5]) + i;
         const SliderRowD c = *row;
-        BodyVel A = loadVel(gVel, c.a), B = loadVel(gVel, c.b);
         const m3 IA = loadInvInertiaJ(gInvI, c.a), IB = loadInvInertiaJ(gInvI, c.b);
         f3 vA = A.v, wA = A.w, vB = B.v, wB = B.w;
         if (c.solveMotor)
@@ -568,7 +558,6 @@ B200_D void solveJoint(int kind, const JointSolveArgs& J, uint32_t p, float4* __
             vB += B.invMass * tb; wB += IB * (c.rBxt * lx + c.rBxb * ly);
         }
         A.v = vA; A.w = wA; B.v = vB; B.w = wB;
-        storeVel(gVel, c.a, A); storeVel(gVel, c.b, B);
     } break;
     }
 }

@@ -28,29 +28,29 @@ static const int kColorThreads = 1024;   // fat CTAs: fewer arrivals per grid ba
 static const int kSolveThreads = 512;
 static const uint32_t kUncolored = 0xFFFFFFFFu;
 
-B200_D bool bodyIsDynamic(const float4* __restrict__ gVel, uint32_t b, uint32_t N) { return b < N && gVel[2 * b].w > 0.f; }
+B200_D bool bodyIsDynamic(const float4* __restrict__ gMass, uint32_t b, uint32_t N) { return b < N && gMass[b].w > 0.f; }
 B200_D uint32_t hashPriority(uint32_t x) { x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16; return x; }
 
 // ------------------------------------------------------------------------------------------------------ adjacency
-__global__ void __launch_bounds__(kThreads) adjCountKernel(const uint2* __restrict__ unitBodies, const uint32_t* __restrict__ numUnits, const float4* __restrict__ gVel, uint32_t N, uint32_t* __restrict__ adjCount)
+__global__ void __launch_bounds__(kThreads) adjCountKernel(const uint2* __restrict__ unitBodies, const uint32_t* __restrict__ numUnits, const float4* __restrict__ gMass, uint32_t N, uint32_t* __restrict__ adjCount)
 {
     const uint32_t n = *numUnits;
     for (uint32_t u = blockIdx.x * kThreads + threadIdx.x; u < n; u += gridDim.x * kThreads)
     {
         const uint2 b = unitBodies[u];
-        if (bodyIsDynamic(gVel, b.x, N)) atomicAdd(&adjCount[b.x], 1u);
-        if (b.y != b.x && bodyIsDynamic(gVel, b.y, N)) atomicAdd(&adjCount[b.y], 1u);
+        if (bodyIsDynamic(gMass, b.x, N)) atomicAdd(&adjCount[b.x], 1u);
+        if (b.y != b.x && bodyIsDynamic(gMass, b.y, N)) atomicAdd(&adjCount[b.y], 1u);
     }
 }
-__global__ void __launch_bounds__(kThreads) adjFillKernel(const uint2* __restrict__ unitBodies, const uint32_t* __restrict__ numUnits, const float4* __restrict__ gVel, uint32_t N,
+__global__ void __launch_bounds__(kThreads) adjFillKernel(const uint2* __restrict__ unitBodies, const uint32_t* __restrict__ numUnits, const float4* __restrict__ gMass, uint32_t N,
                                                           const uint32_t* __restrict__ adjStart, uint32_t* __restrict__ adjFill, uint32_t* __restrict__ adjList)
 {
     const uint32_t n = *numUnits;
     for (uint32_t u = blockIdx.x * kThreads + threadIdx.x; u < n; u += gridDim.x * kThreads)
     {
         const uint2 b = unitBodies[u];
-        if (bodyIsDynamic(gVel, b.x, N)) adjList[adjStart[b.x] + atomicAdd(&adjFill[b.x], 1u)] = u;
-        if (b.y != b.x && bodyIsDynamic(gVel, b.y, N)) adjList[adjStart[b.y] + atomicAdd(&adjFill[b.y], 1u)] = u;
+        if (bodyIsDynamic(gMass, b.x, N)) adjList[adjStart[b.x] + atomicAdd(&adjFill[b.x], 1u)] = u;
+        if (b.y != b.x && bodyIsDynamic(gMass, b.y, N)) adjList[adjStart[b.y] + atomicAdd(&adjFill[b.y], 1u)] = u;
     }
 }
 
@@ -73,14 +73,14 @@ static const uint32_t kNbrStride = 16;   // explicit "who waits for me" list per
 // visits every neighbour v != u of unit u (units sharing a dynamic body); 4 adjacency entries are loaded per trip so the
 // loads overlap (the lists are short: latency, not bandwidth, is what costs here)
 template <typename F>
-B200_D void forEachNeighbour(uint32_t u, uint2 b, const float4* __restrict__ gVel, uint32_t N, const uint32_t* __restrict__ adjStart, const uint32_t* __restrict__ adjList, F&& f)
+B200_D void forEachNeighbour(uint32_t u, uint2 b, const float4* __restrict__ gMass, uint32_t N, const uint32_t* __restrict__ adjStart, const uint32_t* __restrict__ adjList, F&& f)
 {
 #pragma unroll
     for (int side = 0; side < 2; ++side)
     {
         const uint32_t body = side ? b.y : b.x;
         if (side && b.y == b.x) break;
-        if (!bodyIsDynamic(gVel, body, N)) continue;
+        if (!bodyIsDynamic(gMass, body, N)) continue;
         const uint32_t a0 = adjStart[body], a1 = adjStart[body + 1];
         for (uint32_t a = a0; a < a1; a += 4)
         {
@@ -94,7 +94,7 @@ B200_D void forEachNeighbour(uint32_t u, uint2 b, const float4* __restrict__ gVe
 }
 
 __global__ void __launch_bounds__(kColorThreads) colorKernel(int exact, uint32_t group, const uint2* __restrict__ unitBodies, const uint32_t* __restrict__ numUnitsPtr,
-    const float4* __restrict__ gVel, uint32_t N, const uint32_t* __restrict__ adjStart, const uint32_t* __restrict__ adjList,
+    const float4* __restrict__ gMass, uint32_t N, const uint32_t* __restrict__ adjStart, const uint32_t* __restrict__ adjList,
     uint32_t* __restrict__ color, uint32_t* __restrict__ order, uint32_t* __restrict__ pending, unsigned long long* __restrict__ forbid,
     uint32_t* __restrict__ nbrCount, uint32_t* __restrict__ nbrList,
     uint32_t* __restrict__ roundDone, uint32_t* __restrict__ colorCount /* kMaxLevels+1 */,
@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(kColorThreads) colorKernel(int exact, uint32_t
         const uint2 b = unitBodies[u];
         const uint32_t pu = hashPriority(u);
         uint32_t pend = 0, nw = 0;
-        forEachNeighbour(u, b, gVel, N, adjStart, adjList, [&](uint32_t v)
+        forEachNeighbour(u, b, gMass, N, adjStart, adjList, [&](uint32_t v)
         {
             const uint32_t pv = hashPriority(v);
             if (ranksBefore(exact, v, pv, u, pu)) ++pend;
@@ -182,12 +182,12 @@ __global__ void __launch_bounds__(kColorThreads) colorKernel(int exact, uint32_t
             {
                 const uint2 b = unitBodies[u];
                 const uint32_t pu = hashPriority(u);
-                forEachNeighbour(u, b, gVel, N, adjStart, adjList, [&](uint32_t v)
+                forEachNeighbour(u, b, gMass, N, adjStart, adjList, [&](uint32_t v)
                 { if (ranksBefore(exact, u, pu, v, hashPriority(v))) { if (exact) atomicMax(&forbid[v], (unsigned long long)(c + 1u)); else { atomicOr(&forbid[v], 1ull << c); atomicAdd(&forbid[v], 0xFFFF000000000000ull); } } });
                 if (exact)
                 {
                     __threadfence();
-                    forEachNeighbour(u, b, gVel, N, adjStart, adjList, [&](uint32_t v)
+                    forEachNeighbour(u, b, gMass, N, adjStart, adjList, [&](uint32_t v)
                     { if (ranksBefore(exact, u, pu, v, hashPriority(v))) atomicSub(&pending[v], 1u); });
                 }
             }
@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(kColorThreads) colorKernel(int exact, uint32_t
 // ------------------------------------------------------------------------------------------------ contact rows
 // row planes (float4 each, plane stride = maxContacts; a warp reads 512 contiguous bytes per plane), indexed by solve slot:
 //  0: rA.xyz, massN   1: rB.xyz, massT   2: normal.xyz, bias   3: tangent.xyz, friction
-//  4: nAngA.xyz       5: nAngB.xyz       6: tAngA.xyz          7: tAngB.xyz
+//  4: nAngA.xyz, invMassA   5: nAngB.xyz, invMassB   6: tAngA.xyz   7: tAngB.xyz
 __global__ void __launch_bounds__(kThreads) slotCountKernel(const uint32_t* __restrict__ order, const uint4* __restrict__ manifolds, uint32_t* __restrict__ slotCount, const DeviceCounts* __restrict__ cnt)
 {
     const uint32_t n = cnt->numManifolds;
@@ -294,9 +294,10 @@ __global__ void __launch_bounds__(kThreads) initContactRowsKernel(const uint32_t
         const uint32_t slot0 = unitSlotStart[p];
         unitInfo[p] = make_uint4(man.x, man.y, slot0, man.w);   // solve-order record: one 128-bit load per manifold and iteration
         const float4 vA4 = gVel[2 * man.x], wA4 = gVel[2 * man.x + 1], vB4 = gVel[2 * man.y], wB4 = gVel[2 * man.y + 1];
-        const f3 posA = xyz(gPos[man.x]), posB = xyz(gPos[man.y]);
+        const float4 pA4 = gPos[man.x], pB4 = gPos[man.y];
+        const f3 posA = xyz(pA4), posB = xyz(pB4);
         const m3 IA = loadInvInertia(gInvI, man.x), IB = loadInvInertia(gInvI, man.y);
-        const float imA = vA4.w, imB = vB4.w;
+        const float imA = pA4.w, imB = pB4.w;
         for (uint32_t k = 0; k < man.w; ++k)
         {
             const uint32_t ci = man.z + k, slot = slot0 + k;
@@ -330,8 +331,8 @@ __global__ void __launch_bounds__(kThreads) initContactRowsKernel(const uint32_t
             rows[(size_t)maxContacts + slot] = mk4(rB, massT);
             rows[(size_t)2 * maxContacts + slot] = mk4(normal, bias);
             rows[(size_t)3 * maxContacts + slot] = mk4(tangent, friction);
-            rows[(size_t)4 * maxContacts + slot] = mk4(nAngA, 0.f);
-            rows[(size_t)5 * maxContacts + slot] = mk4(nAngB, 0.f);
+            rows[(size_t)4 * maxContacts + slot] = mk4(nAngA, imA);
+            rows[(size_t)5 * maxContacts + slot] = mk4(nAngB, imB);
             rows[(size_t)6 * maxContacts + slot] = mk4(tAngA, 0.f);
             rows[(size_t)7 * maxContacts + slot] = mk4(tAngB, 0.f);
             rowImp[slot] = make_float2(0.f, 0.f);
@@ -374,82 +375,214 @@ B200_D void applyRow(RowRegs& R, float imA, float imB, f3& vA, f3& wA, f3& vB, f
     }
 }
 
-// one manifold: `first` already holds the rows of its first contact (prefetched before the grid barrier)
-B200_D void solveManifold(const uint4 man, RowRegs& first, const float4* __restrict__ rows, float2* __restrict__ rowImp, float4* __restrict__ gVel, uint32_t maxContacts)
+// ------------------------------------------------------------------------------------------- dataflow bookkeeping
+// The PGS sweep is executed as a DATAFLOW, not as colour phases separated by grid barriers: every dynamic body carries an
+// update counter (the .w lanes of its two 16-byte velocity halves, both written together with the data, so each half is
+// self-validating and no fence is needed on either side). A unit (manifold or joint) knows, for each of its dynamic bodies,
+// its rank among the units touching that body within one sweep and the body's degree; in sweep `it` it may run exactly
+// when both counters read it * degree + rank, and it publishes rank + 1. The solve order (colour-sorted in fast mode,
+// level-sorted canonical order in exact mode) only decides who comes first at each body; a unit never waits for anything
+// but its true predecessors, so the sweep overlaps across colours and iterations and the memory system stays busy.
+// dep record per solve position: .x / .y = rank | degree << 16 for body a / b, 0xFFFFFFFF = not dynamic (never waited for).
+__global__ void __launch_bounds__(kThreads) depMaskKernel(const uint2* __restrict__ unitBodies, const uint32_t* __restrict__ numUnits, const uint32_t* __restrict__ color,
+                                                          const float4* __restrict__ gMass, uint32_t N, unsigned long long* __restrict__ bodyMask)
 {
-    const float4 a0 = ldCg(gVel + 2 * man.x), a1 = ldCg(gVel + 2 * man.x + 1), b0 = ldCg(gVel + 2 * man.y), b1 = ldCg(gVel + 2 * man.y + 1);
-    const float imA = a0.w, imB = b0.w;
-    if (imA == 0.f && imB == 0.f) return;                        // :3394
-    f3 vA = xyz(a0), wA = xyz(a1), vB = xyz(b0), wB = xyz(b1);
-    applyRow(first, imA, imB, vA, wA, vB, wB);
-    rowImp[man.z] = first.imp;
-    for (uint32_t k = 1; k < man.w; ++k)
+    const uint32_t n = *numUnits;
+    for (uint32_t u = blockIdx.x * kThreads + threadIdx.x; u < n; u += gridDim.x * kThreads)
     {
-        RowRegs R; loadRow(R, rows, rowImp, man.z + k, maxContacts);
-        applyRow(R, imA, imB, vA, wA, vB, wB);
-        rowImp[man.z + k] = R.imp;
+        const uint2 b = unitBodies[u];
+        const unsigned long long bit = 1ull << min(color[u], 63u);
+        if (bodyIsDynamic(gMass, b.x, N)) atomicOr(&bodyMask[b.x], bit);
+        if (b.y != b.x && bodyIsDynamic(gMass, b.y, N)) atomicOr(&bodyMask[b.y], bit);
     }
-    if (imA != 0.f) { stCg(gVel + 2 * man.x, mk4(vA, imA)); stCg(gVel + 2 * man.x + 1, mk4(wA, 0.f)); }
-    if (imB != 0.f) { stCg(gVel + 2 * man.y, mk4(vB, imB)); stCg(gVel + 2 * man.y + 1, mk4(wB, 0.f)); }
 }
+
+__global__ void __launch_bounds__(kThreads) depRankKernel(int exact, const uint2* __restrict__ unitBodies, const uint32_t* __restrict__ numUnits, const uint32_t* __restrict__ color,
+    const uint32_t* __restrict__ order, const float4* __restrict__ gMass, uint32_t N, const unsigned long long* __restrict__ bodyMask, const uint32_t* __restrict__ bodyBase,
+    const uint32_t* __restrict__ adjStart, const uint32_t* __restrict__ adjList, uint2* __restrict__ dep)
+{
+    const uint32_t n = *numUnits;
+    for (uint32_t p = blockIdx.x * kThreads + threadIdx.x; p < n; p += gridDim.x * kThreads)
+    {
+        const uint32_t u = order[p];
+        const uint2 b = unitBodies[u];
+        uint32_t enc[2] = { 0xFFFFFFFFu, 0xFFFFFFFFu };
+#pragma unroll
+        for (int side = 0; side < 2; ++side)
+        {
+            const uint32_t body = side ? b.y : b.x;
+            if (side && b.y == b.x) break;
+            if (!bodyIsDynamic(gMass, body, N)) continue;
+            uint32_t rank = bodyBase[body], deg = rank;
+            if (exact)
+            {   // canonical order: by unit index
+                const uint32_t a0 = adjStart[body], a1 = adjStart[body + 1];
+                for (uint32_t a = a0; a < a1; ++a) rank += (adjList[a] < u) ? 1u : 0u;
+                deg += a1 - a0;
+            }
+            else
+            {   // units sharing a body have distinct colours and the sweep runs colour by colour
+                const unsigned long long m = bodyMask[body];
+                rank += (uint32_t)__popcll(m & ((1ull << min(color[u], 63u)) - 1ull));
+                deg += (uint32_t)__popcll(m);
+            }
+            enc[side] = (rank & 0xFFFFu) | (deg << 16);
+        }
+        dep[p] = make_uint2(enc[0], enc[1]);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) bodyBaseAddKernel(int exact, uint32_t N, unsigned long long* __restrict__ bodyMask, const uint32_t* __restrict__ adjStart, uint32_t* __restrict__ bodyBase, DeviceCounts* cnt)
+{
+    for (uint32_t b = blockIdx.x * kThreads + threadIdx.x; b < N; b += gridDim.x * kThreads)
+    {
+        const uint32_t add = exact ? (adjStart[b + 1] - adjStart[b]) : (uint32_t)__popcll(bodyMask[b]);
+        if (!exact) bodyMask[b] = 0ull;
+        if (add) { const uint32_t t = bodyBase[b] + add; bodyBase[b] = t; if (t > 0xFFFFu) cnt->overflowColors = 8; }
+    }
+}
+
+// with several groups (joint kinds, then contacts) a body's total degree is only known after the last group
+struct DepFinalizeArgs { const uint2* unitBodies[kNumGroups]; const uint32_t* order[kNumGroups]; uint2* dep[kNumGroups]; const uint32_t* numUnits[kNumGroups]; };
+__global__ void __launch_bounds__(kThreads) depFinalizeKernel(DepFinalizeArgs F, const uint32_t* __restrict__ bodyBase)
+{
+    for (uint32_t g = 0; g < kNumGroups; ++g)
+    {
+        if (!F.numUnits[g]) continue;
+        const uint32_t n = *F.numUnits[g];
+        for (uint32_t p = blockIdx.x * kThreads + threadIdx.x; p < n; p += gridDim.x * kThreads)
+        {
+            const uint2 b = F.unitBodies[g][F.order[g][p]];
+            uint2 d = F.dep[g][p];
+            if (d.x != 0xFFFFFFFFu) d.x = (d.x & 0xFFFFu) | (bodyBase[b.x] << 16);
+            if (d.y != 0xFFFFFFFFu) d.y = (d.y & 0xFFFFu) | (bodyBase[b.y] << 16);
+            F.dep[g][p] = d;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ the PGS sweep
+B200_D float4 ldRelaxed4(const float4* p)
+{
+    float4 v;
+    asm volatile("ld.relaxed.gpu.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+B200_D void stRelaxed4(float4* p, float4 v)
+{
+    asm volatile("st.relaxed.gpu.global.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+B200_D uint32_t ldRelaxedU32(const uint32_t* p) { uint32_t v; asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
 
 struct SolveArgs
 {
-    const uint4* unitInfo; const float4* rows; float2* rowImp; uint32_t maxContacts;
-    const uint32_t* colorStart;      // contacts: per-colour unit ranges (kMaxLevels + 1)
+    const uint4* unitInfo; const uint2* unitDep; const float4* rows; float2* rowImp; uint32_t maxContacts;
     JointSolveArgs joints;
-    float4* gVel; const float4* gInvI;
-    DeviceCounts* cnt; uint32_t iterations; uint32_t barrierSlot;
+    float4* gVel; const float4* gPos; const float4* gInvI;
+    DeviceCounts* cnt; uint32_t iterations;
 };
 
-// The persistent PGS kernel: iterations x (joint kinds in reference order, then contacts) x colours, grid barrier between
-// colours; one fat CTA per SM (148 arrivals per barrier). Software pipelining across the barrier: the manifold record and
-// the 128-byte row a thread needs FIRST in the next colour do not depend on other CTAs, so they are loaded into registers
-// BEFORE the barrier; after it only the two 32-byte body records are on the critical path.
+static const uint32_t kSpinLimit = 1u << 22;    // polls before a unit gives up and aborts the sweep (seconds; never reached by a consistent graph)
+
+// Persistent kernel, one CTA per SM (all co-resident: a unit may poll for a predecessor owned by any other warp). Global
+// solve position q = joints of kind 0..5 in their solve order, then the manifolds; thread t owns positions t, t + T, ...
+// in every sweep. A warp retries its 32 current units together until all have run, so a unit that depends on another lane's
+// unit of the same warp (only at colour / level boundaries) cannot block it.
 template <bool JOINTS>
 __global__ void __launch_bounds__(kSolveThreads, 1) solveKernel(SolveArgs A)
 {
-    uint32_t epoch = 0;
-    uint32_t* bar = A.cnt->barrier[A.barrierSlot];
-    const uint32_t tid = blockIdx.x * kSolveThreads + threadIdx.x, stride = gridDim.x * kSolveThreads;
-    const uint32_t numContactColors = A.cnt->numColors[6];
-    uint4 pfInfo = make_uint4(0, 0, 0, 0); RowRegs pf; bool pfValid = false;
-    if (numContactColors)
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t T = gridDim.x * kSolveThreads;
+    const uint32_t warpBase = blockIdx.x * kSolveThreads + (threadIdx.x & ~31u);
+    uint32_t segEnd[7];
     {
-        const uint32_t p = A.colorStart[0] + tid;
-        if (p < A.colorStart[1]) { pfInfo = A.unitInfo[p]; loadRow(pf, A.rows, A.rowImp, pfInfo.z, A.maxContacts); pfValid = true; }
+        uint32_t run = 0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) { if (JOINTS) run += A.cnt->numJoints[k]; segEnd[k] = run; }
+        run += A.cnt->numManifolds; segEnd[6] = run;
     }
-    for (uint32_t it = 0; it < A.iterations; ++it)
+    const uint32_t total = segEnd[6];
+    const uint32_t* abortFlag = &A.cnt->solverAbort;
+    bool aborted = false;
+    for (uint32_t it = 0; it < A.iterations && !aborted; ++it)
     {
-        if (JOINTS) for (int kind = 0; kind < 6; ++kind)
+        for (uint32_t qb = warpBase; qb < total && !aborted; qb += T)
         {
-            const uint32_t nc = A.cnt->numColors[kind];
-            for (uint32_t c = 0; c < nc; ++c)
+            const uint32_t q = qb + lane;
+            bool done = !(q < total);
+            int kind = 6; uint32_t p = q;
+            if (JOINTS && !done)
             {
-                const uint32_t p0 = A.joints.colorStart[kind][c], p1 = A.joints.colorStart[kind][c + 1];
-                for (uint32_t p = p0 + tid; p < p1; p += stride) solveJoint(kind, A.joints, p, A.gVel, A.gInvI);
-                gridBarrier(bar, epoch);
+                kind = 0;
+#pragma unroll
+                for (int k = 0; k < 6; ++k) if (q >= segEnd[k]) kind = k + 1;
+                if (kind) p = q - segEnd[kind - 1];
             }
-        }
-        for (uint32_t c = 0; c < numContactColors; ++c)
-        {
-            const uint32_t p0 = A.colorStart[c], p1 = A.colorStart[c + 1];
-            if (pfValid) solveManifold(pfInfo, pf, A.rows, A.rowImp, A.gVel, A.maxContacts);
-            for (uint32_t p = p0 + tid + stride; p < p1; p += stride)
+            uint32_t bodyA = 0, bodyB = 0, jointIndex = 0; uint2 dep = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
+            uint4 info = make_uint4(0, 0, 0, 0); RowRegs R; float imA = 0.f, imB = 0.f;
+            if (!done)
             {
-                const uint4 man = A.unitInfo[p];
-                RowRegs R; loadRow(R, A.rows, A.rowImp, man.z, A.maxContacts);
-                solveManifold(man, R, A.rows, A.rowImp, A.gVel, A.maxContacts);
+                if (kind == 6)
+                {
+                    info = A.unitInfo[p]; dep = A.unitDep[p];
+                    loadRow(R, A.rows, A.rowImp, info.z, A.maxContacts);
+                    bodyA = info.x; bodyB = info.y; imA = R.r[4].w; imB = R.r[5].w;
+                }
+                else
+                {
+                    jointIndex = A.joints.order[kind][p]; dep = A.joints.dep[kind][p];
+                    const uint2 jb = A.joints.bodies[kind][jointIndex];
+                    bodyA = jb.x; bodyB = jb.y; imA = A.gPos[bodyA].w; imB = A.gPos[bodyB].w;
+                }
+                if (imA == 0.f && imB == 0.f) done = true;                 // constraints.cpp:3394 (and a joint between two fixed bodies moves nothing)
             }
-            // prefetch this thread's first manifold of the next colour (wraps to colour 0 of the next iteration)
-            const uint32_t cn = (c + 1 < numContactColors) ? c + 1 : 0;
-            pfValid = false;
-            if ((c + 1 < numContactColors) || (it + 1 < A.iterations))
+            const bool dynA = dep.x != 0xFFFFFFFFu, dynB = dep.y != 0xFFFFFFFFu;
+            const uint32_t expA = it * (dep.x >> 16) + (dep.x & 0xFFFFu), expB = it * (dep.y >> 16) + (dep.y & 0xFFFFu);
+            float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, b0 = a0, b1 = a0;
+            if (!done)
+            {   // bodies nobody writes (static, kinematic stand-in): read once
+                if (!dynA) { a0 = A.gVel[2 * bodyA]; a1 = A.gVel[2 * bodyA + 1]; }
+                if (!dynB) { b0 = A.gVel[2 * bodyB]; b1 = A.gVel[2 * bodyB + 1]; }
+            }
+            uint32_t spins = 0;
+            while (__any_sync(0xffffffffu, !done))
             {
-                const uint32_t p = A.colorStart[cn] + tid;
-                if (p < A.colorStart[cn + 1]) { pfInfo = A.unitInfo[p]; loadRow(pf, A.rows, A.rowImp, pfInfo.z, A.maxContacts); pfValid = true; }
+                if (done) continue;
+                if (dynA) { a0 = ldRelaxed4(A.gVel + 2 * bodyA); a1 = ldRelaxed4(A.gVel + 2 * bodyA + 1); }
+                if (dynB) { b0 = ldRelaxed4(A.gVel + 2 * bodyB); b1 = ldRelaxed4(A.gVel + 2 * bodyB + 1); }
+                const bool ready = (!dynA || (__float_as_uint(a0.w) == expA && __float_as_uint(a1.w) == expA)) &&
+                                   (!dynB || (__float_as_uint(b0.w) == expB && __float_as_uint(b1.w) == expB));
+                if (!ready)
+                {
+                    if ((++spins & 255u) == 0u && (spins >= kSpinLimit || ldRelaxedU32(abortFlag)))
+                    {   // inconsistent dependency records (colour overflow): stop the whole sweep instead of hanging the device
+                        atomicExch(&A.cnt->solverAbort, 1u); A.cnt->overflowColors = 4; done = true; aborted = true;
+                    }
+                    continue;
+                }
+                f3 vA = xyz(a0), wA = xyz(a1), vB = xyz(b0), wB = xyz(b1);
+                if (kind == 6)
+                {
+                    applyRow(R, imA, imB, vA, wA, vB, wB);
+                    A.rowImp[info.z] = R.imp;
+                    for (uint32_t k = 1; k < info.w; ++k)
+                    {
+                        RowRegs Rk; loadRow(Rk, A.rows, A.rowImp, info.z + k, A.maxContacts);
+                        applyRow(Rk, imA, imB, vA, wA, vB, wB);
+                        A.rowImp[info.z + k] = Rk.imp;
+                    }
+                }
+                else
+                {
+                    BodyVel JA, JB; JA.v = vA; JA.w = wA; JA.invMass = imA; JB.v = vB; JB.w = wB; JB.invMass = imB;
+                    solveJoint(kind, A.joints, jointIndex, JA, JB, A.gInvI);
+                    vA = JA.v; wA = JA.w; vB = JB.v; wB = JB.w;
+                }
+                if (dynA) { const float ver = __uint_as_float(expA + 1u); stRelaxed4(A.gVel + 2 * bodyA, mk4(vA, ver)); stRelaxed4(A.gVel + 2 * bodyA + 1, mk4(wA, ver)); }
+                if (dynB) { const float ver = __uint_as_float(expB + 1u); stRelaxed4(A.gVel + 2 * bodyB, mk4(vB, ver)); stRelaxed4(A.gVel + 2 * bodyB + 1, mk4(wB, ver)); }
+                done = true;
             }
-            gridBarrier(bar, epoch);
+            aborted = __any_sync(0xffffffffu, aborted);
         }
     }
 }
@@ -466,6 +599,7 @@ __global__ void solverResetKernel(DeviceCounts* cnt, JointCounts jc)
     if (threadIdx.x < kNumGroups) cnt->numColors[threadIdx.x] = 0;
     for (int b = 0; b < 8; ++b) cnt->barrier[b][threadIdx.x] = 0;
     if (threadIdx.x < 6) cnt->numJoints[threadIdx.x] = jc.n[threadIdx.x];
+    if (threadIdx.x == 0) cnt->solverAbort = 0;
 }
 
 // colour one group of units (joint kind or contacts); leaves order[] and colour ranges behind
@@ -477,11 +611,11 @@ static void colorGroup(Context* c, uint32_t group, const uint2* unitBodies, cons
     cudaMemsetAsync(c->adjFill, 0, sizeof(uint32_t) * (N + 2), c->stream);
     cudaMemsetAsync(c->adjStart, 0, sizeof(uint32_t) * (N + 2), c->stream);
     uint32_t* adjCount = c->adjFill;   // counts are built in adjFill, scanned into adjStart, then adjFill is re-zeroed as the fill cursor
-    adjCountKernel<<<G, kThreads, 0, c->stream>>>(unitBodies, numUnitsDev, c->gVel, N, adjCount);
+    adjCountKernel<<<G, kThreads, 0, c->stream>>>(unitBodies, numUnitsDev, c->gPos, N, adjCount);
     c->launches++;
     scanExclusiveU32(c, adjCount, c->adjStart, nullptr, N + 1, nullptr);
     cudaMemsetAsync(c->adjFill, 0, sizeof(uint32_t) * (N + 2), c->stream);
-    adjFillKernel<<<G, kThreads, 0, c->stream>>>(unitBodies, numUnitsDev, c->gVel, N, c->adjStart, c->adjFill, c->adjList);
+    adjFillKernel<<<G, kThreads, 0, c->stream>>>(unitBodies, numUnitsDev, c->gPos, N, c->adjStart, c->adjFill, c->adjList);
     c->launches++;
 
     uint32_t* roundDone = c->levelFill;                       // kMaxLevels + 1
@@ -490,12 +624,17 @@ static void colorGroup(Context* c, uint32_t group, const uint2* unitBodies, cons
     cudaMemsetAsync(c->levelFill, 0, sizeof(uint32_t) * 3 * (kMaxLevels + 1), c->stream);
     int exactI = exact ? 1 : 0;
     DeviceCounts* cnt = c->counts;
-    void* args[] = { &exactI, &group, (void*)&unitBodies, (void*)&numUnitsDev, &c->gVel, (void*)&N, &c->adjStart, &c->adjList, &color, &order, &c->unitPending, &c->unitForbid, &c->nbrCount, &c->nbrList,
+    void* args[] = { &exactI, &group, (void*)&unitBodies, (void*)&numUnitsDev, &c->gPos /* .w = invMass */, (void*)&N, &c->adjStart, &c->adjList, &color, &order, &c->unitPending, &c->unitForbid, &c->nbrCount, &c->nbrList,
                      &roundDone, &colorCount, &colorStartOut, &colorFill, &cnt, &barrierSlot };
     static int colorBlocksPerSM = 0;
     if (!colorBlocksPerSM) { cudaOccupancyMaxActiveBlocksPerMultiprocessor(&colorBlocksPerSM, colorKernel, kColorThreads, 0); if (colorBlocksPerSM < 1) colorBlocksPerSM = 1; if (colorBlocksPerSM > 8) colorBlocksPerSM = 8; }
     cudaLaunchCooperativeKernel((void*)colorKernel, dim3(c->numSMs * colorBlocksPerSM), dim3(kColorThreads), args, 0, c->stream);
     c->launches++;
+    // dataflow records of this group (rank / degree of every unit at its bodies), then fold the group into the per-body totals
+    if (!exact) { depMaskKernel<<<G, kThreads, 0, c->stream>>>(unitBodies, numUnitsDev, color, c->gPos, N, c->bodyMask); c->launches++; }
+    depRankKernel<<<G, kThreads, 0, c->stream>>>(exactI, unitBodies, numUnitsDev, color, order, c->gPos, N, c->bodyMask, c->bodyBase, c->adjStart, c->adjList, c->unitDep[group]);
+    bodyBaseAddKernel<<<G, kThreads, 0, c->stream>>>(exactI, N, c->bodyMask, c->adjStart, c->bodyBase, cnt);
+    c->launches += 2;
     (void)maxUnits;
 }
 
@@ -507,6 +646,8 @@ void launchSolver(Context* c, float dt, uint32_t iterations, uint32_t flags)
     JointCounts jc; for (int k = 0; k < 6; ++k) jc.n[k] = c->numJoints[k];
     solverResetKernel<<<1, 32, 0, c->stream>>>(cnt, jc);
     c->launches++;
+    cudaMemsetAsync(c->bodyMask, 0, sizeof(unsigned long long) * (c->numBodies + 2), c->stream);
+    cudaMemsetAsync(c->bodyBase, 0, sizeof(uint32_t) * (c->numBodies + 2), c->stream);
 
     // ---- joints: colour each kind, initialise rows
     JointSolveArgs ja;
@@ -514,7 +655,7 @@ void launchSolver(Context* c, float dt, uint32_t iterations, uint32_t flags)
     bool anyJoint = false;
     for (int k = 0; k < 6; ++k)
     {
-        ja.order[k] = c->unitOrder[k]; ja.colorStart[k] = c->levelStart + (size_t)k * (kMaxLevels + 1); ja.rows[k] = c->jointRows[k];
+        ja.order[k] = c->unitOrder[k]; ja.colorStart[k] = c->levelStart + (size_t)k * (kMaxLevels + 1); ja.rows[k] = c->jointRows[k]; ja.bodies[k] = c->jointBodies[k]; ja.dep[k] = c->unitDep[k];
         ji.in[k] = c->jointIn[k]; ji.bodies[k] = c->jointBodies[k]; ji.rows[k] = c->jointRows[k]; ji.count[k] = c->numJoints[k];
         if (c->numJoints[k])
         {
@@ -545,9 +686,21 @@ void launchSolver(Context* c, float dt, uint32_t iterations, uint32_t flags)
     c->launches++;
 
     // ---- iterations
+    if (anyJoint)
+    {   // several groups: the degrees in the records of the earlier groups are partial until now
+        DepFinalizeArgs F;
+        for (uint32_t g = 0; g < kNumGroups; ++g)
+        {
+            const bool used = g == 6 || c->numJoints[g] != 0;
+            F.unitBodies[g] = g == 6 ? unitBodies : c->jointBodies[g]; F.order[g] = c->unitOrder[g]; F.dep[g] = c->unitDep[g];
+            F.numUnits[g] = !used ? nullptr : (g == 6 ? &cnt->numManifolds : &cnt->numJoints[g]);
+        }
+        depFinalizeKernel<<<G, kThreads, 0, c->stream>>>(F, c->bodyBase);
+        c->launches++;
+    }
     SolveArgs A;
-    A.unitInfo = c->unitInfo; A.rows = c->rows; A.rowImp = c->rowImp; A.maxContacts = c->maxContacts;
-    A.colorStart = contactColorStart; A.joints = ja; A.gVel = c->gVel; A.gInvI = c->gInvI; A.cnt = cnt; A.iterations = iterations; A.barrierSlot = 7;
+    A.unitInfo = c->unitInfo; A.unitDep = c->unitDep[6]; A.rows = c->rows; A.rowImp = c->rowImp; A.maxContacts = c->maxContacts;
+    A.joints = ja; A.gVel = c->gVel; A.gPos = c->gPos; A.gInvI = c->gInvI; A.cnt = cnt; A.iterations = iterations;
     void* args[] = { &A };
     if (c->timing) cudaEventRecord(c->ev[4], c->stream);
     static int solveBlocksPerSM[2] = { 0, 0 };
