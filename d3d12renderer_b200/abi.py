@@ -82,7 +82,7 @@ EXPORTS = [
     "b200phys_upload_forces", "b200phys_upload_body_states", "b200phys_step", "b200phys_synchronize", "b200phys_download_bodies", "b200phys_get_stats",
     "b200phys_download_aabbs", "b200phys_download_pairs", "b200phys_download_contacts", "b200phys_download_collisions",
     "b200phys_download_solve_order", "b200phys_halo_pack", "b200phys_halo_unpack", "b200phys_halo_clear", "b200phys_halo_record_bytes",
-    "b200phys_halo_message_bytes", "b200phys_halo_pack_message", "b200phys_halo_unpack_message",
+    "b200phys_halo_message_bytes", "b200phys_halo_pack_message", "b200phys_halo_unpack_message", "b200phys_migrate_pack", "b200phys_migrate_unpack",
 ]
 
 _lib = None
@@ -127,6 +127,8 @@ def load_library():
     lib.b200phys_halo_message_bytes.restype = C.c_uint64; lib.b200phys_halo_message_bytes.argtypes = [u32, u32]
     lib.b200phys_halo_pack_message.argtypes = [vp, i32, f32, f32, vp, u32, u32]
     lib.b200phys_halo_unpack_message.argtypes = [vp, vp, u32, u32]
+    lib.b200phys_migrate_pack.argtypes = [vp, i32, f32, f32, vp, vp, u32, u32, C.POINTER(u32), C.POINTER(u32)]
+    lib.b200phys_migrate_unpack.argtypes = [vp, vp, u32, u32, C.POINTER(u32)]
     lib.b200phys_halo_record_bytes.restype = u32; lib.b200phys_halo_record_bytes.argtypes = [i32]
     _lib = lib
     return lib
@@ -287,6 +289,21 @@ class Stepper:
 
     def halo_unpack_message(self, src_ptr, cap_bodies, cap_colliders):
         _check(self.lib, self.lib.b200phys_halo_unpack_message(self.ctx, C.c_void_p(src_ptr), cap_bodies, cap_colliders), "halo_unpack_message")
+
+    def migrate_pack(self, axis, lo, hi, dst_down_ptr, dst_up_ptr, cap_bodies, cap_colliders, num_owned=None):
+        """-> (dest[num_owned] uint32: 0 stays / 1 down / 2 up, counts (bodies down, colliders down, bodies up, colliders up))."""
+        num_owned = self.num_bodies if num_owned is None else num_owned
+        dest = np.zeros(max(1, num_owned), dtype=np.uint32); counts = (C.c_uint32 * 4)()
+        _check(self.lib, self.lib.b200phys_migrate_pack(self.ctx, axis, lo, hi, C.c_void_p(dst_down_ptr), C.c_void_p(dst_up_ptr), cap_bodies, cap_colliders,
+                                                        dest.ctypes.data_as(C.POINTER(C.c_uint32)), counts), "migrate_pack")
+        self.num_bodies = num_owned - int(counts[0]) - int(counts[2])
+        return dest[:num_owned], tuple(int(x) for x in counts)
+
+    def migrate_unpack(self, src_ptr, cap_bodies, cap_colliders):
+        counts = (C.c_uint32 * 2)()
+        _check(self.lib, self.lib.b200phys_migrate_unpack(self.ctx, C.c_void_p(src_ptr), cap_bodies, cap_colliders, counts), "migrate_unpack")
+        self.num_bodies += int(counts[0])
+        return int(counts[0]), int(counts[1])
 
     def halo_clear(self):
         _check(self.lib, self.lib.b200phys_halo_clear(self.ctx), "halo_clear")

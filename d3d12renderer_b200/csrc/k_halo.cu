@@ -158,6 +158,60 @@ __global__ void __launch_bounds__(kThreads) haloUnpackMessageKernel(const uint32
     }
 }
 
+// ------------------------------------------------------------------------------------------------------- migration
+// dest[b]: 0 = stays, 1 = goes to the lower neighbour (position below lo), 2 = to the upper neighbour (position >= hi)
+__global__ void __launch_bounds__(kThreads) migrateDestKernel(uint32_t numBodies, int axis, float lo, float hi, const float4* __restrict__ bPos, uint32_t* __restrict__ dest,
+                                                              uint32_t* __restrict__ flagL, uint32_t* __restrict__ flagR, uint32_t* __restrict__ flagKeep)
+{
+    for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < numBodies; i += gridDim.x * kThreads)
+    {
+        const float4 p = bPos[i];
+        const float x = axis == 0 ? p.x : (axis == 1 ? p.y : p.z);
+        const uint32_t d = x < lo ? 1u : (x >= hi ? 2u : 0u);
+        dest[i] = d; flagL[i] = d == 1u; flagR[i] = d == 2u; flagKeep[i] = d == 0u;
+    }
+}
+// colliders follow their body; everything that is not attached to an owned rigid body (static geometry) stays
+__global__ void __launch_bounds__(kThreads) migrateColliderFlagKernel(uint32_t numColliders, uint32_t numBodies, const float4* __restrict__ cLocal, const uint32_t* __restrict__ dest,
+                                                                      uint32_t* __restrict__ flagL, uint32_t* __restrict__ flagR, uint32_t* __restrict__ flagKeep)
+{
+    for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < numColliders; i += gridDim.x * kThreads)
+    {
+        const float4 L3 = cLocal[4 * i + 3];
+        const uint32_t tw = __float_as_uint(L3.y), objType = (tw >> 8) & 0xFFu, body = __float_as_uint(L3.z);
+        const uint32_t d = (objType == B200PHYS_OBJ_RIGID_BODY && body < numBodies) ? dest[body] : 0u;
+        flagL[i] = d == 1u; flagR[i] = d == 2u; flagKeep[i] = d == 0u;
+    }
+}
+// out-of-place compaction of the ten body planes (plane p of the scratch starts at p * scratchStride)
+__global__ void __launch_bounds__(kThreads) migrateGatherBodiesKernel(uint32_t numBodies, uint32_t planeStride, const uint32_t* __restrict__ keep, const uint32_t* __restrict__ slot,
+    const float4* __restrict__ bRot, const float4* __restrict__ bPos, const float4* __restrict__ bCog, const float4* __restrict__ bInvI,
+    const float4* __restrict__ bVel, const float4* __restrict__ bAng, const float4* __restrict__ bForce, const float4* __restrict__ bTorque, float4* __restrict__ scratch, uint32_t scratchStride)
+{
+    for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < numBodies; i += gridDim.x * kThreads)
+    {
+        if (!keep[i]) continue;
+        const uint32_t s = slot[i];
+        scratch[s] = bRot[i]; scratch[(size_t)scratchStride + s] = bPos[i]; scratch[(size_t)2 * scratchStride + s] = bCog[i];
+        scratch[(size_t)3 * scratchStride + s] = bInvI[i]; scratch[(size_t)4 * scratchStride + s] = bInvI[planeStride + i]; scratch[(size_t)5 * scratchStride + s] = bInvI[2 * planeStride + i];
+        scratch[(size_t)6 * scratchStride + s] = bVel[i]; scratch[(size_t)7 * scratchStride + s] = bAng[i];
+        scratch[(size_t)8 * scratchStride + s] = bForce[i]; scratch[(size_t)9 * scratchStride + s] = bTorque[i];
+    }
+}
+__global__ void __launch_bounds__(kThreads) migrateGatherCollidersKernel(uint32_t numColliders, uint32_t numBodies, const uint32_t* __restrict__ keep, const uint32_t* __restrict__ slot,
+    const uint32_t* __restrict__ bodySlot, const float4* __restrict__ cLocal, float4* __restrict__ scratch)
+{
+    for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < numColliders; i += gridDim.x * kThreads)
+    {
+        if (!keep[i]) continue;
+        const uint32_t s = slot[i];
+        float4 L3 = cLocal[4 * i + 3];
+        const uint32_t tw = __float_as_uint(L3.y), objType = (tw >> 8) & 0xFFu, body = __float_as_uint(L3.z);
+        if (objType == B200PHYS_OBJ_RIGID_BODY && body < numBodies) L3.z = __uint_as_float(bodySlot[body]);   // index after compaction
+        scratch[4 * s] = cLocal[4 * i]; scratch[4 * s + 1] = cLocal[4 * i + 1]; scratch[4 * s + 2] = cLocal[4 * i + 2]; scratch[4 * s + 3] = L3;
+    }
+}
+
 } // namespace b200
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return -(int)e_; } while (0)
@@ -259,6 +313,93 @@ int b200phys_halo_clear(b200phys_context* ctx)
 {
     if (!ctx) return B200PHYS_E_INVALID;
     ctx->c.numBodies = ctx->c.numOwnedBodies; ctx->c.numColliders = ctx->c.numOwnedColliders;
+    return 0;
+}
+
+// ---- migration: bodies whose position left [lo, hi) on `axis` move to the neighbouring rank with all their colliders.
+// Synchronous (the owned counts change, the host must know them); call it every few steps, with no ghosts present.
+// Messages have the halo message layout. outDest (host, numOwnedBodies entries, may be null) receives 0 / 1 / 2 per body so
+// that the caller can carry its own per-body data (global ids) along; outCounts = {bodies down, colliders down, bodies up,
+// colliders up}. Joints are not migrated: a context with joints returns B200PHYS_E_INVALID.
+int b200phys_migrate_pack(b200phys_context* ctx, int axis, float lo, float hi, void* dstMessageDown, void* dstMessageUp, uint32_t capBodies, uint32_t capColliders,
+                          uint32_t* outDest, uint32_t* outCounts)
+{
+    if (!ctx || axis < 0 || axis > 2 || !dstMessageDown || !dstMessageUp || !outCounts) return B200PHYS_E_INVALID;
+    Context& c = ctx->c; CK(cudaSetDevice(c.device));
+    for (int k = 0; k < 6; ++k) if (c.numJoints[k]) return B200PHYS_E_INVALID;
+    if (c.numBodies != c.numOwnedBodies || c.numColliders != c.numOwnedColliders) return B200PHYS_E_INVALID;   // drop the ghosts first (b200phys_halo_clear)
+    const uint32_t N = c.numOwnedBodies, C = c.numOwnedColliders;
+    outCounts[0] = outCounts[1] = outCounts[2] = outCounts[3] = 0;
+    char* msg[2] = { (char*)dstMessageDown, (char*)dstMessageUp };
+    if (!N) { CK(cudaMemsetAsync(msg[0], 0, 16, c.stream)); CK(cudaMemsetAsync(msg[1], 0, 16, c.stream)); CK(cudaStreamSynchronize(c.stream)); return 0; }
+    // scratch (all dead between steps): per-body words in the pair-sized buffers, plane scratch in the contact rows
+    const size_t P = c.maxPairs;
+    if ((size_t)4 * (N + 2) > P || (size_t)4 * (C + 2) > P || (size_t)10 * N > (size_t)8 * c.maxContacts || (size_t)4 * C > (size_t)8 * c.maxContacts) return B200PHYS_E_CAPACITY;
+    uint32_t* dest = c.pairDst;                       // N
+    uint32_t* flag[3] = { c.pairDst + (N + 2), c.pairDst + 2 * (size_t)(N + 2), c.pairDst + 3 * (size_t)(N + 2) };   // down, up, keep
+    uint32_t* slot[3] = { (uint32_t*)c.manScan, (uint32_t*)c.manScan + (N + 2), (uint32_t*)c.manScan + 2 * (size_t)(N + 2) };
+    uint32_t* cflag[3] = { (uint32_t*)c.manScanOut, (uint32_t*)c.manScanOut + (C + 2), (uint32_t*)c.manScanOut + 2 * (size_t)(C + 2) };
+    uint32_t* cslot[3] = { (uint32_t*)c.pairsTyped, (uint32_t*)c.pairsTyped + (C + 2), (uint32_t*)c.pairsTyped + 2 * (size_t)(C + 2) };
+    const int G = gridFor(&c, 4);
+    const uint32_t planeStride = c.cfg.maxBodies + 1;
+    migrateDestKernel<<<G, kThreads, 0, c.stream>>>(N, axis, lo, hi, c.bPos, dest, flag[0], flag[1], flag[2]);
+    migrateColliderFlagKernel<<<G, kThreads, 0, c.stream>>>(C, N, c.cLocal, dest, cflag[0], cflag[1], cflag[2]);
+    for (int d = 0; d < 3; ++d)
+    {
+        scanExclusiveU32(&c, flag[d], slot[d], nullptr, N, nullptr);
+        if (C) scanExclusiveU32(&c, cflag[d], cslot[d], nullptr, C, nullptr); else CK(cudaMemsetAsync(cslot[d], 0, 4, c.stream));
+    }
+    uint32_t counts[6] = { 0, 0, 0, 0, 0, 0 };
+    for (int d = 0; d < 3; ++d)
+    {
+        CK(cudaMemcpyAsync(&counts[2 * d], slot[d] + N, 4, cudaMemcpyDeviceToHost, c.stream));
+        if (C) CK(cudaMemcpyAsync(&counts[2 * d + 1], cslot[d] + C, 4, cudaMemcpyDeviceToHost, c.stream));
+    }
+    for (int d = 0; d < 2; ++d)
+    {
+        float* outB = (float*)(msg[d] + 16); float4* outC = (float4*)(msg[d] + 16 + (size_t)capBodies * kHaloBodyFloats * 4);
+        haloPackBodiesKernel<<<G, kThreads, 0, c.stream>>>(N, planeStride, flag[d], slot[d], capBodies, c.bRot, c.bPos, c.bCog, c.bInvI, c.bVel, c.bAng, c.bForce, c.bTorque, outB);
+        if (C) haloPackCollidersKernel<<<G, kThreads, 0, c.stream>>>(C, cflag[d], cslot[d], capColliders, slot[d], c.cLocal, outC);
+        haloHeaderKernel<<<1, 32, 0, c.stream>>>(slot[d] + N, cslot[d] + C, (uint32_t*)msg[d]);
+    }
+    // compaction of what stays
+    float4* scratch = c.rows;
+    migrateGatherBodiesKernel<<<G, kThreads, 0, c.stream>>>(N, planeStride, flag[2], slot[2], c.bRot, c.bPos, c.bCog, c.bInvI, c.bVel, c.bAng, c.bForce, c.bTorque, scratch, N);
+    CK(cudaStreamSynchronize(c.stream));
+    CK(cudaGetLastError());
+    const uint32_t keptB = counts[4], keptC = counts[5];
+    if (counts[0] > capBodies || counts[2] > capBodies || counts[1] > capColliders || counts[3] > capColliders) return B200PHYS_E_CAPACITY;   // nothing was modified yet
+    if (outDest) CK(cudaMemcpyAsync(outDest, dest, sizeof(uint32_t) * N, cudaMemcpyDeviceToHost, c.stream));
+    float4* planes[10] = { c.bRot, c.bPos, c.bCog, c.bInvI, c.bInvI + planeStride, c.bInvI + 2 * (size_t)planeStride, c.bVel, c.bAng, c.bForce, c.bTorque };
+    for (int p = 0; p < 10; ++p) if (keptB) CK(cudaMemcpyAsync(planes[p], scratch + (size_t)p * N, sizeof(float4) * keptB, cudaMemcpyDeviceToDevice, c.stream));
+    if (C)
+    {
+        CK(cudaStreamSynchronize(c.stream));          // the plane scratch is reused for the colliders
+        migrateGatherCollidersKernel<<<G, kThreads, 0, c.stream>>>(C, N, cflag[2], cslot[2], slot[2], c.cLocal, scratch);
+        if (keptC) CK(cudaMemcpyAsync(c.cLocal, scratch, sizeof(float4) * 4 * (size_t)keptC, cudaMemcpyDeviceToDevice, c.stream));
+    }
+    CK(cudaStreamSynchronize(c.stream));
+    CK(cudaGetLastError());
+    c.numBodies = c.numOwnedBodies = keptB; c.numColliders = c.numOwnedColliders = keptC;
+    outCounts[0] = counts[0]; outCounts[1] = counts[1]; outCounts[2] = counts[2]; outCounts[3] = counts[3];
+    return 0;
+}
+
+// Appends the bodies / colliders of a migration message as OWNED; returns the counts through outCounts[2] (synchronous).
+int b200phys_migrate_unpack(b200phys_context* ctx, const void* srcMessageDev, uint32_t capBodies, uint32_t capColliders, uint32_t* outCounts)
+{
+    if (!ctx || !srcMessageDev || !outCounts) return B200PHYS_E_INVALID;
+    Context& c = ctx->c; CK(cudaSetDevice(c.device));
+    if (c.numBodies != c.numOwnedBodies || c.numColliders != c.numOwnedColliders) return B200PHYS_E_INVALID;
+    uint32_t hdr[4] = { 0, 0, 0, 0 };
+    CK(cudaMemcpyAsync(hdr, srcMessageDev, 16, cudaMemcpyDeviceToHost, c.stream));
+    CK(cudaStreamSynchronize(c.stream));
+    outCounts[0] = hdr[0]; outCounts[1] = hdr[1];
+    if (hdr[0] > capBodies || hdr[1] > capColliders) return B200PHYS_E_CAPACITY;
+    const char* base = (const char*)srcMessageDev;
+    int rc = b200phys_halo_unpack(ctx, base + 16, hdr[0], base + 16 + (size_t)capBodies * kHaloBodyFloats * 4, hdr[1]);
+    if (rc) return rc;
+    c.numOwnedBodies = c.numBodies; c.numOwnedColliders = c.numColliders;
     return 0;
 }
 

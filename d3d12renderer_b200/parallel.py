@@ -115,6 +115,51 @@ class SlabShard:
         for peer in sorted(self.recv_msg.keys()):
             st.halo_unpack_message(self.recv_msg[peer].data_ptr(), self.cap_b, self.cap_c)
 
+    def migrate(self, ids=None):
+        """Hands bodies that left this rank's slab (position beyond a slab plane) over to the neighbouring rank, colliders included;
+        every rank must call it at the same step (every few steps is enough: until then the old owner keeps simulating the
+        body, so keep ghost_width >= collider size + the distance a body travels between two migrations). Synchronous.
+        ids: optional per-owned-body int64 array (e.g. global ids) that is carried along; returns the new array."""
+        st = self.st
+        st.halo_clear()
+        if self.world == 1:
+            return ids
+        if not hasattr(self, "mig_send"):
+            words = st.halo_message_bytes(self.cap_b, self.cap_c) // 4
+            self.mig_send = [torch.zeros(words, dtype=torch.float32, device=self.device) for _ in range(2)]       # down, up
+            self.mig_recv = {p: torch.zeros(words, dtype=torch.float32, device=self.device) for p, _, _ in self.regions}
+        lo, hi = float(self.bounds[self.rank]), float(self.bounds[self.rank + 1])
+        dest, counts = st.migrate_pack(self.axis, lo, hi, self.mig_send[0].data_ptr(), self.mig_send[1].data_ptr(), self.cap_b, self.cap_c)
+        send = {}
+        if self.rank > 0:
+            send[self.rank - 1] = self.mig_send[0]
+        if self.rank < self.world - 1:
+            send[self.rank + 1] = self.mig_send[1]
+        exchange_fixed(send, self.mig_recv)
+        received = {}
+        for peer in sorted(self.mig_recv.keys()):
+            received[peer] = st.migrate_unpack(self.mig_recv[peer].data_ptr(), self.cap_b, self.cap_c)
+        self.last_migration = (counts, received)
+        if ids is None:
+            return None
+        ids = np.asarray(ids)
+        out_ids = {}
+        if self.rank > 0:
+            out_ids[self.rank - 1] = torch.from_numpy(np.ascontiguousarray(ids[dest == 1]).astype(np.int64)).to(self.device)
+        if self.rank < self.world - 1:
+            out_ids[self.rank + 1] = torch.from_numpy(np.ascontiguousarray(ids[dest == 2]).astype(np.int64)).to(self.device)
+        in_ids = {p: torch.empty(received[p][0], dtype=torch.int64, device=self.device) for p in received}   # sizes known from the messages
+        ops = []
+        for p in sorted(out_ids.keys()):
+            if out_ids[p].numel():
+                ops.append(dist.P2POp(dist.isend, out_ids[p], p))
+            if in_ids[p].numel():
+                ops.append(dist.P2POp(dist.irecv, in_ids[p], p))
+        if ops:
+            for r in dist.batch_isend_irecv(ops):
+                r.wait()
+        return np.concatenate([ids[dest == 0]] + [in_ids[p].cpu().numpy() for p in sorted(in_ids.keys())])
+
     def ghost_counts(self):
         """(bodies, colliders) received in the last exchange, summed over neighbours (reads the message headers: synchronous)."""
         tb = tc = 0

@@ -257,6 +257,15 @@ int b200phys_halo_unpack(b200phys_context* ctx, const void* srcBodiesDevice, uin
 uint64_t b200phys_halo_message_bytes(uint32_t capBodies, uint32_t capColliders);
 int b200phys_halo_pack_message(b200phys_context* ctx, int axis, float lo, float hi, void* dstMessageDev, uint32_t capBodies, uint32_t capColliders);
 int b200phys_halo_unpack_message(b200phys_context* ctx, const void* srcMessageDev, uint32_t capBodies, uint32_t capColliders);
+/* Migration (multi-GPU): bodies whose position left [lo, hi) on `axis` move, with all their colliders, into two messages of the
+ * halo message layout (down = below lo, up = at or above hi) and are removed from this context (the body and collider arrays
+ * are compacted, order preserved). Synchronous; requires no ghosts (b200phys_halo_clear first) and no joints.
+ * outDest (host, one entry per previously owned body, may be NULL): 0 stays / 1 down / 2 up, so that callers can carry per-body
+ * data of their own along. outCounts[4] = {bodies down, colliders down, bodies up, colliders up}.
+ * migrate_unpack appends a received message as OWNED bodies / colliders; outCounts[2] = {bodies, colliders}. */
+int b200phys_migrate_pack(b200phys_context* ctx, int axis, float lo, float hi, void* dstMessageDownDev, void* dstMessageUpDev,
+                          uint32_t capBodies, uint32_t capColliders, uint32_t* outDest, uint32_t* outCounts);
+int b200phys_migrate_unpack(b200phys_context* ctx, const void* srcMessageDev, uint32_t capBodies, uint32_t capColliders, uint32_t* outCounts);
 int b200phys_halo_clear(b200phys_context* ctx);
 
 #ifdef __cplusplus
