@@ -49,7 +49,7 @@ assert hinge_joint_dtype.itemsize == 104 and cone_twist_joint_dtype.itemsize == 
 SPHERE, CAPSULE, CYLINDER, AABB, OBB, HULL = range(6)
 OBJ_RIGID_BODY, OBJ_STATIC, OBJ_FORCE_FIELD, OBJ_TRIGGER = range(4)
 NO_TRANSFORM = 0xFFFFFFFF
-STEP_FAST, STEP_EXACT_ORDER = 0, 1
+STEP_FAST, STEP_EXACT_ORDER, STEP_PERMUTED = 0, 1, 2
 
 
 class Config(C.Structure):

@@ -43,6 +43,7 @@ struct DeviceCounts
     uint32_t colorStart[kNumGroups][kMaxColors + 1]; // fast mode unit ranges per colour
     uint32_t numBig;
     uint32_t bigMatrixCount;            // min(numBig, 16) * C: size of the big-collider flag matrix
+    uint32_t colorQueueHead, colorQueueTail;   // ready queue of the colouring
     uint32_t solverAbort;               // set when the dataflow sweep gave up (inconsistent dependency records)
     uint32_t remaining;                 // colouring work counter
     uint32_t overflowPairs, overflowManifolds, overflowGrid, overflowColors, overflowBig, overflowHalo;
@@ -129,6 +130,7 @@ struct Context
     uint32_t* unitColor[kNumGroups] = {};   // colour / level per unit
     uint32_t* unitOrder[kNumGroups] = {};   // units sorted by colour (solve order)
     uint2* unitDep[kNumGroups] = {};        // dataflow record per solve position: rank | degree << 16 for each body
+    uint32_t* colorQueue = nullptr;         // ready queue of the colouring (max units of any group)
     unsigned long long* bodyMask = nullptr; // colours taken at each body (current group)
     uint32_t* bodyBase = nullptr;           // units per body in the groups coloured so far
     uint32_t* unitPending = nullptr;        // colouring: unresolved higher-ranked neighbours per unit

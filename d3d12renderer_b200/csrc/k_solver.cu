@@ -3,14 +3,15 @@
 // Reference: constraint_solver (src/physics/constraints.cpp:3711-3772), collision constraints :3307-3449.
 // The reference visits constraints Gauss-Seidel in array order on one thread; its AVX2 path re-orders them into
 // conflict-free 8-wide batches (constraints.cpp:51-184). Here the unit of scheduling is a MANIFOLD (all contacts of one
-// collider pair, solved in order by one thread) or a joint; units are scheduled in "colours":
-//   * exact mode : colour = wavefront level = 1 + max(level of earlier units sharing a dynamic body). Executing levels in
-//                  order reproduces sequential Gauss-Seidel in canonical array order bit for bit.
-//   * fast mode  : Jones-Plassmann colouring with a fixed hash priority (deterministic), <= 64 colours.
-// Inside one colour no two units touch the same dynamic body, so a colour is one embarrassingly parallel sweep; colours are
-// separated by a hand-written grid barrier inside ONE persistent cooperative kernel (grid = SM count), i.e. the
-// iterations x colours loop costs no kernel launches. The static dummy body and kinematic bodies never conflict
-// (constraints.cpp:82-83).
+// collider pair, solved in order by one thread) or a joint. A step fixes a SOLVE ORDER of the units and derives from it,
+// for every unit and each of its dynamic bodies, the unit's rank among that body's units; the sweep itself is a dataflow
+// over per-body update counters (see solveKernel): no colour phases, no grid barriers.
+//   * exact mode    : canonical array order => bit for bit the sequential Gauss-Seidel sweep.
+//   * fast mode     : units sorted by a deterministic Jones-Plassmann colouring (fixed hash priority, <= 48 colours), computed
+//                     by a queue-driven kernel without rounds or barriers: short dependency chains through the bodies.
+//   * permuted mode : a fixed pseudo-random permutation instead of the colouring (nothing to compute, longer chains).
+// The order is exported (b200phys_download_solve_order) so that the oracle can replay it. The static dummy body and kinematic
+// bodies never order anything (constraints.cpp:82-83).
 //
 // HBM traffic per contact and iteration: one 128-byte row (8 coalesced 128-bit planes) + 8 B impulses read/written +
 // two 32-byte body records gathered and scattered (the only per-body data the iterations touch).
@@ -24,7 +25,6 @@ namespace b200 {
 static_assert(sizeof(ConeTwistRowD) <= 512 && sizeof(SliderRowD) <= 512 && sizeof(HingeRowD) <= 512 && sizeof(FixedRowD) <= 512, "joint rows are allocated 512 bytes each");
 
 static const int kThreads = 256;
-static const int kColorThreads = 1024;   // fat CTAs: fewer arrivals per grid barrier
 static const int kSolveThreads = 512;
 static const uint32_t kUncolored = 0xFFFFFFFFu;
 
@@ -93,171 +93,172 @@ B200_D void forEachNeighbour(uint32_t u, uint2 b, const float4* __restrict__ gMa
     }
 }
 
-__global__ void __launch_bounds__(kColorThreads) colorKernel(int exact, uint32_t group, const uint2* __restrict__ unitBodies, const uint32_t* __restrict__ numUnitsPtr,
+// ---- queue-driven Jones-Plassmann colouring (fast order). The classic formulation re-scans all units once per round with a
+// grid barrier in between (25 rounds x 11 us on the 778 k-manifold pile). Here the thread whose decrement brings a unit's
+// pending count to zero hands the unit to a global ready queue, and every warp keeps taking 32 tickets from that queue: a
+// unit is coloured as soon as its last higher-priority neighbour is, there is no barrier and no re-scan, and the result is the
+// same deterministic colouring (every unit still decides from exactly the colours of its higher-priority neighbours).
+// All same-address traffic is warp-aggregated: one atomic per 32 tickets, one per warp pass for the enqueues.
+static const uint32_t kQueueEmpty = 0xFFFFFFFFu;
+static const int kColorRunThreads = 256;
+
+__global__ void __launch_bounds__(kThreads) colorInitKernel(const uint2* __restrict__ unitBodies, const uint32_t* __restrict__ numUnitsPtr,
     const float4* __restrict__ gMass, uint32_t N, const uint32_t* __restrict__ adjStart, const uint32_t* __restrict__ adjList,
-    uint32_t* __restrict__ color, uint32_t* __restrict__ order, uint32_t* __restrict__ pending, unsigned long long* __restrict__ forbid,
-    uint32_t* __restrict__ nbrCount, uint32_t* __restrict__ nbrList,
-    uint32_t* __restrict__ roundDone, uint32_t* __restrict__ colorCount /* kMaxLevels+1 */,
-    uint32_t* __restrict__ colorStartOut /* kMaxLevels+1 */, uint32_t* __restrict__ colorFill, DeviceCounts* cnt, uint32_t barrierSlot)
+    uint32_t* __restrict__ color, unsigned long long* __restrict__ forbid, uint32_t* __restrict__ nbrCount, uint32_t* __restrict__ nbrList,
+    uint32_t* __restrict__ queue, DeviceCounts* cnt)
 {
-    __shared__ uint32_t sRed[kColorThreads / 32];
-    __shared__ uint32_t sHist[kMaxColors], sBase[kMaxColors];   // fast mode: per-CTA colour histogram / scatter bases (no same-address global atomics)
-    uint32_t epoch = 0;
-    uint32_t* bar = cnt->barrier[barrierSlot];
     const uint32_t n = *numUnitsPtr;
-    const uint32_t maxColors = exact ? kMaxLevels : kMaxColors;
-    const uint32_t tid = blockIdx.x * kColorThreads + threadIdx.x, stride = gridDim.x * kColorThreads;
+    const uint32_t rounds = (n + gridDim.x * kThreads - 1) / (gridDim.x * kThreads);
+    for (uint32_t r = 0; r < rounds; ++r)
+    {
+        const uint32_t u = (r * gridDim.x + blockIdx.x) * kThreads + threadIdx.x;
+        bool seed = false;
+        if (u < n)
+        {
+            const uint2 b = unitBodies[u];
+            const uint32_t pu = hashPriority(u);
+            uint32_t pend = 0, nw = 0;
+            forEachNeighbour(u, b, gMass, N, adjStart, adjList, [&](uint32_t v)
+            {
+                if (ranksBefore(0, v, hashPriority(v), u, pu)) ++pend;
+                else { if (nw < kNbrStride) nbrList[(size_t)u * kNbrStride + nw] = v; ++nw; }
+            });
+            // pending << 48 | colour mask in ONE 64-bit word: a notifier's OR and its decrement go to the same address, which the
+            // memory model keeps in program order, so the thread that sees the count reach zero also sees every colour bit
+            forbid[u] = (unsigned long long)pend << 48;
+            color[u] = kUncolored; nbrCount[u] = nw;
+            seed = pend == 0;
+        }
+        const uint32_t ballot = __ballot_sync(0xffffffffu, seed);
+        if (ballot)
+        {
+            uint32_t base = 0;
+            if (laneId() == 0) base = atomicAdd(&cnt->colorQueueTail, (uint32_t)__popc(ballot));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (seed) queue[base + __popc(ballot & laneMaskLt())] = u;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kColorRunThreads) colorRunKernel(uint32_t group, const uint2* __restrict__ unitBodies, const uint32_t* __restrict__ numUnitsPtr,
+    const float4* __restrict__ gMass, uint32_t N, const uint32_t* __restrict__ adjStart, const uint32_t* __restrict__ adjList,
+    uint32_t* __restrict__ color, unsigned long long* __restrict__ forbid, const uint32_t* __restrict__ nbrCount, const uint32_t* __restrict__ nbrList,
+    uint32_t* __restrict__ queue, uint32_t* __restrict__ colorCount, DeviceCounts* cnt)
+{
+    __shared__ uint32_t sHist[kMaxColors];
+    const uint32_t n = *numUnitsPtr;
     if (threadIdx.x < kMaxColors) sHist[threadIdx.x] = 0;
     __syncthreads();
-
-    // ---- phase 0: dependency counts + the list of units that wait for u
-    for (uint32_t u = tid; u < n; u += stride)
+    uint32_t localMax = 0;
+    for (;;)
     {
-        const uint2 b = unitBodies[u];
-        const uint32_t pu = hashPriority(u);
-        uint32_t pend = 0, nw = 0;
-        forEachNeighbour(u, b, gMass, N, adjStart, adjList, [&](uint32_t v)
+        uint32_t base = 0;
+        if (laneId() == 0) base = atomicAdd(&cnt->colorQueueHead, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        const uint32_t idx = base + laneId();
+        bool done = idx >= n;
+        uint32_t spins = 0;
+        while (__any_sync(0xffffffffu, !done))
         {
-            const uint32_t pv = hashPriority(v);
-            if (ranksBefore(exact, v, pv, u, pu)) ++pend;
-            else { if (nw < kNbrStride) nbrList[(size_t)u * kNbrStride + nw] = v; ++nw; }
-        });
-        // fast mode packs both into ONE 64-bit word (pending << 48 | colour mask): the notifier's OR and its decrement go to the
-        // same address, which the memory model keeps in program order, so no fence is needed on either side
-        if (exact) { pending[u] = pend; forbid[u] = 0ull; } else forbid[u] = (unsigned long long)pend << 48;
-        color[u] = kUncolored; nbrCount[u] = nw;
-    }
-    gridBarrier(bar, epoch);
-
-    uint32_t total = 0, localMax = 0, doneMask = 0;
-    for (uint32_t round = 0; round < kMaxLevels && total < n; ++round)
-    {
-        uint32_t colouredHere = 0;
-        for (uint32_t u = tid; u < n; u += stride)
-        {
-            const uint32_t k = (u - tid) / stride;                 // this thread's k-th unit: done bits live in a register
-            if (k < 32 ? ((doneMask >> k) & 1u) : (color[u] != kUncolored)) continue;
-            unsigned long long f;
-            if (exact)
+            uint32_t ready[kNbrStride]; uint32_t nReady = 0;
+            if (!done)
             {
-                if (ldCgU32(pending + u) != 0) continue;
-                __threadfence();                                   // acquire: the notifiers' level updates precede their pending decrements
-                asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(f) : "l"(forbid + u) : "memory");
+                uint32_t u;
+                asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(u) : "l"(queue + idx) : "memory");
+                if (u != kQueueEmpty)
+                {
+                    done = true;
+                    unsigned long long f;
+                    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(f) : "l"(forbid + u) : "memory");
+                    f |= 0xFFFF000000000000ull;                    // only 48 colours are representable
+                    uint32_t c = (uint32_t)(__ffsll((long long)~f) - 1);
+                    if (c >= 48u) { c = 47u; cnt->overflowColors = 1; }
+                    color[u] = c;
+                    atomicAdd(&sHist[c], 1u);
+                    localMax = max(localMax, c + 1u);
+                    const uint32_t nw = nbrCount[u];
+                    const unsigned long long bit = 1ull << c;
+                    if (nw <= kNbrStride)
+                    {   // the waiting units are listed explicitly: 4 independent 128-bit loads, then the atomics back to back
+                        uint32_t w[kNbrStride];
+                        const uint4* L = reinterpret_cast<const uint4*>(nbrList + (size_t)u * kNbrStride);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) { const uint4 q = (4u * j < nw) ? L[j] : make_uint4(0, 0, 0, 0); w[4 * j] = q.x; w[4 * j + 1] = q.y; w[4 * j + 2] = q.z; w[4 * j + 3] = q.w; }
+                        unsigned long long old[kNbrStride];
+#pragma unroll
+                        for (int j = 0; j < (int)kNbrStride; ++j) if ((uint32_t)j < nw) { atomicOr(&forbid[w[j]], bit); old[j] = atomicAdd(&forbid[w[j]], 0xFFFF000000000000ull); }   // += -(1 << 48)
+#pragma unroll
+                        for (int j = 0; j < (int)kNbrStride; ++j) if ((uint32_t)j < nw && (old[j] >> 48) == 1ull) ready[nReady++] = w[j];
+                    }
+                    else
+                    {   // rare: more waiting units than the list holds -> walk the adjacency, enqueue one by one
+                        const uint2 b = unitBodies[u];
+                        const uint32_t pu = hashPriority(u);
+                        forEachNeighbour(u, b, gMass, N, adjStart, adjList, [&](uint32_t v)
+                        {
+                            if (!ranksBefore(0, u, pu, v, hashPriority(v))) return;
+                            atomicOr(&forbid[v], bit);
+                            const unsigned long long o = atomicAdd(&forbid[v], 0xFFFF000000000000ull);
+                            if ((o >> 48) == 1ull) { const uint32_t t = atomicAdd(&cnt->colorQueueTail, 1u); if (t < n) queue[t] = v; }
+                        });
+                    }
+                }
+                else if (++spins > (1u << 22)) { cnt->overflowColors = 2; done = true; }   // refuse to hang (cyclic graph cannot happen)
             }
-            else
+            // hand the newly ready units to the queue: one reservation per warp and pass
+            uint32_t incl = nReady;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (laneId() >= (uint32_t)o) incl += t; }
+            const uint32_t totalReady = __shfl_sync(0xffffffffu, incl, 31);
+            if (totalReady)
             {
-                asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(f) : "l"(forbid + u) : "memory");
-                if ((f >> 48) != 0ull) continue;
-                f |= 0xFFFF000000000000ull;                        // only 48 colours are representable in fast mode
-            }
-            if (k < 32) doneMask |= (1u << k);
-            uint32_t c = exact ? (uint32_t)f : (uint32_t)(__ffsll((long long)~f) - 1);
-            if (c >= (exact ? maxColors : 48u)) { c = (exact ? maxColors : 48u) - 1; cnt->overflowColors = 1; }
-            color[u] = c;
-            if (exact) atomicAdd(&colorCount[c], 1u); else atomicAdd(&sHist[c], 1u);
-            localMax = max(localMax, c + 1u);
-            ++colouredHere;
-            const uint32_t nw = nbrCount[u];
-            if (nw <= kNbrStride)
-            {   // the waiting units are listed explicitly: 4 independent 128-bit loads, then fire-and-forget atomics
-                uint32_t w[kNbrStride];
-                const uint4* L = reinterpret_cast<const uint4*>(nbrList + (size_t)u * kNbrStride);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) { const uint4 q = (4u * j < nw) ? L[j] : make_uint4(0, 0, 0, 0); w[4 * j] = q.x; w[4 * j + 1] = q.y; w[4 * j + 2] = q.z; w[4 * j + 3] = q.w; }
-                if (exact)
-                {
-#pragma unroll
-                    for (int j = 0; j < (int)kNbrStride; ++j) if ((uint32_t)j < nw) atomicMax(&forbid[w[j]], (unsigned long long)(c + 1u));
-                    __threadfence();
-#pragma unroll
-                    for (int j = 0; j < (int)kNbrStride; ++j) if ((uint32_t)j < nw) atomicSub(&pending[w[j]], 1u);
-                }
-                else
-                {
-#pragma unroll
-                    for (int j = 0; j < (int)kNbrStride; ++j) if ((uint32_t)j < nw) { atomicOr(&forbid[w[j]], 1ull << c); atomicAdd(&forbid[w[j]], 0xFFFF000000000000ull); }   // += -(1 << 48)
-                }
-            }
-            else
-            {
-                const uint2 b = unitBodies[u];
-                const uint32_t pu = hashPriority(u);
-                forEachNeighbour(u, b, gMass, N, adjStart, adjList, [&](uint32_t v)
-                { if (ranksBefore(exact, u, pu, v, hashPriority(v))) { if (exact) atomicMax(&forbid[v], (unsigned long long)(c + 1u)); else { atomicOr(&forbid[v], 1ull << c); atomicAdd(&forbid[v], 0xFFFF000000000000ull); } } });
-                if (exact)
-                {
-                    __threadfence();
-                    forEachNeighbour(u, b, gMass, N, adjStart, adjList, [&](uint32_t v)
-                    { if (ranksBefore(exact, u, pu, v, hashPriority(v))) atomicSub(&pending[v], 1u); });
-                }
+                uint32_t qb = 0;
+                if (laneId() == 0) qb = atomicAdd(&cnt->colorQueueTail, totalReady);
+                qb = __shfl_sync(0xffffffffu, qb, 0) + incl - nReady;
+                for (uint32_t j = 0; j < nReady; ++j) if (qb + j < n) asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" :: "l"(queue + qb + j), "r"(ready[j]) : "memory");
             }
         }
-        uint32_t v = colouredHere;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-        if (laneId() == 0) sRed[threadIdx.x >> 5] = v;
-        __syncthreads();
-        if (threadIdx.x == 0) { uint32_t t = 0; for (int w = 0; w < kColorThreads / 32; ++w) t += sRed[w]; if (t) atomicAdd(&roundDone[round], t); }
-        gridBarrier(bar, epoch);
-        const uint32_t done = ldCgU32(roundDone + round);
-        if (done == 0 && total < n) { if (tid == 0) cnt->overflowColors = 2; break; }   // no progress: refuse to spin
-        total += done;
-        if (tid == 0) cnt->remaining = round + 1;   // diagnostic: colouring rounds of the last group
     }
     localMax = __reduce_max_sync(0xffffffffu, localMax);
     if (laneId() == 0 && localMax) atomicMax(&cnt->numColors[group], localMax);
     __syncthreads();
-    if (!exact && threadIdx.x < kMaxColors && sHist[threadIdx.x]) atomicAdd(&colorCount[threadIdx.x], sHist[threadIdx.x]);
-    gridBarrier(bar, epoch);
+    if (threadIdx.x < kMaxColors && sHist[threadIdx.x]) atomicAdd(&colorCount[threadIdx.x], sHist[threadIdx.x]);
+}
 
-    // counting sort by colour: exclusive scan of the histogram (one CTA; <= 65536 entries), then scatter
-    const uint32_t numColors = min(ldCgU32(&cnt->numColors[group]), maxColors);
-    if (blockIdx.x == 0)
+// colour ranges (<= 48 colours: one warp) ...
+__global__ void colorScanKernel(uint32_t group, const uint32_t* __restrict__ colorCount, uint32_t* __restrict__ colorStartOut, DeviceCounts* cnt)
+{
+    if (threadIdx.x == 0)
     {
-        __shared__ uint32_t carry;
-        if (threadIdx.x == 0) carry = 0;
-        __syncthreads();
-        for (uint32_t base = 0; base < numColors; base += kColorThreads)
-        {
-            const uint32_t i = base + threadIdx.x;
-            const uint32_t x = (i < numColors) ? ldCgU32(colorCount + i) : 0u;
-            uint32_t incl = x;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (laneId() >= (uint32_t)o) incl += t; }
-            if (laneId() == 31) sRed[threadIdx.x >> 5] = incl;
-            __syncthreads();
-            uint32_t woff = 0; for (uint32_t w = 0; w < (threadIdx.x >> 5); ++w) woff += sRed[w];
-            const uint32_t c0 = carry;
-            if (i < numColors) { colorStartOut[i] = c0 + woff + incl - x; if (!exact && i <= kMaxColors) cnt->colorStart[group][i] = c0 + woff + incl - x; }
-            __syncthreads();
-            if (threadIdx.x == kColorThreads - 1) carry = c0 + woff + incl;
-            __syncthreads();
-        }
-        if (threadIdx.x == 0) { colorStartOut[numColors] = carry; if (!exact && numColors <= kMaxColors) cnt->colorStart[group][numColors] = carry; }
+        const uint32_t numColors = min(cnt->numColors[group], kMaxColors);
+        uint32_t run = 0;
+        for (uint32_t c = 0; c < numColors; ++c) { colorStartOut[c] = run; cnt->colorStart[group][c] = run; run += colorCount[c]; }
+        colorStartOut[numColors] = run; cnt->colorStart[group][numColors] = run;
     }
-    gridBarrier(bar, epoch);
-    if (exact)
+}
+// ... and the counting sort by colour: each CTA reserves one range per colour for its chunk of units, then ranks inside it in
+// shared memory (no same-address global atomics per unit). Also collects the colours present at every dynamic body.
+__global__ void __launch_bounds__(kThreads) colorScatterKernel(const uint2* __restrict__ unitBodies, const uint32_t* __restrict__ numUnitsPtr, const uint32_t* __restrict__ color,
+    const float4* __restrict__ gMass, uint32_t N, const uint32_t* __restrict__ colorStart, uint32_t* __restrict__ colorFill, uint32_t* __restrict__ order, unsigned long long* __restrict__ bodyMask)
+{
+    __shared__ uint32_t sHist[kMaxColors], sBase[kMaxColors];
+    const uint32_t n = *numUnitsPtr;
+    const uint32_t per = (n + gridDim.x - 1) / gridDim.x, u0 = blockIdx.x * per, u1 = min(n, u0 + per);
+    if (threadIdx.x < kMaxColors) sHist[threadIdx.x] = 0;
+    __syncthreads();
+    for (uint32_t u = u0 + threadIdx.x; u < u1; u += kThreads) atomicAdd(&sHist[min(color[u], kMaxColors - 1)], 1u);
+    __syncthreads();
+    if (threadIdx.x < kMaxColors) { const uint32_t h = sHist[threadIdx.x]; sBase[threadIdx.x] = h ? (colorStart[threadIdx.x] + atomicAdd(&colorFill[threadIdx.x], h)) : 0u; }
+    __syncthreads();
+    for (uint32_t u = u0 + threadIdx.x; u < u1; u += kThreads)
     {
-        for (uint32_t u = tid; u < n; u += stride)
-        {
-            const uint32_t c = min(color[u], maxColors - 1);
-            const uint32_t pos = ldCgU32(colorStartOut + c) + atomicAdd(&colorFill[c], 1u);
-            order[pos] = u;
-        }
-    }
-    else
-    {   // each CTA reserves one range per colour (its histogram from the rounds above), then ranks inside it in shared memory
-        if (threadIdx.x < kMaxColors)
-        {
-            const uint32_t h = sHist[threadIdx.x];
-            sBase[threadIdx.x] = h ? (ldCgU32(colorStartOut + threadIdx.x) + atomicAdd(&colorFill[threadIdx.x], h)) : 0u;
-        }
-        __syncthreads();
-        for (uint32_t u = tid; u < n; u += stride)
-        {
-            const uint32_t c = min(color[u], maxColors - 1);
-            order[atomicAdd(&sBase[c], 1u)] = u;
-        }
+        const uint32_t c = min(color[u], kMaxColors - 1);
+        order[atomicAdd(&sBase[c], 1u)] = u;
+        const uint2 b = unitBodies[u];
+        const unsigned long long bit = 1ull << min(c, 63u);
+        if (bodyIsDynamic(gMass, b.x, N)) atomicOr(&bodyMask[b.x], bit);
+        if (b.y != b.x && bodyIsDynamic(gMass, b.y, N)) atomicOr(&bodyMask[b.y], bit);
     }
 }
 
@@ -384,20 +385,40 @@ B200_D void applyRow(RowRegs& R, float imA, float imB, f3& vA, f3& wA, f3& vB, f
 // level-sorted canonical order in exact mode) only decides who comes first at each body; a unit never waits for anything
 // but its true predecessors, so the sweep overlaps across colours and iterations and the memory system stays busy.
 // dep record per solve position: .x / .y = rank | degree << 16 for body a / b, 0xFFFFFFFF = not dynamic (never waited for).
-__global__ void __launch_bounds__(kThreads) depMaskKernel(const uint2* __restrict__ unitBodies, const uint32_t* __restrict__ numUnits, const uint32_t* __restrict__ color,
-                                                          const float4* __restrict__ gMass, uint32_t N, unsigned long long* __restrict__ bodyMask)
+// A cheap bijection of [0, n): invertible mixing on ceil(log2 n) bits (odd multiplications, xor-shifts), cycle-walked back
+// into range. The fast solve order is this pseudo-random permutation of the units: in a random order the dependency chains
+// through the bodies are short (the same depth a Jones-Plassmann colouring needs rounds), and since the dataflow sweep only
+// needs SOME total order per body, no colouring has to be computed at all.
+B200_D uint32_t permuteBits(uint32_t x, uint32_t mask, uint32_t half)
+{
+    x = (x * 0x9E3779B1u) & mask; x ^= x >> half;
+    x = (x * 0x85EBCA6Bu) & mask; x ^= x >> half;
+    x = (x * 0xC2B2AE35u) & mask; x ^= x >> half;
+    return x;
+}
+B200_D uint32_t permutePos(uint32_t u, uint32_t n)
+{
+    const uint32_t bits = n > 1u ? 32u - (uint32_t)__clz(n - 1u) : 1u;
+    const uint32_t mask = bits >= 32u ? 0xFFFFFFFFu : ((1u << bits) - 1u), half = (bits + 1u) / 2u;
+    uint32_t x = permuteBits(u, mask, half);
+    while (x >= n) x = permuteBits(x, mask, half);
+    return x;
+}
+// mode 1: canonical order (position = unit index); mode 2: the pseudo-random permutation
+__global__ void __launch_bounds__(kThreads) orderKernel(int mode, const uint32_t* __restrict__ numUnits, uint32_t* __restrict__ order)
 {
     const uint32_t n = *numUnits;
-    for (uint32_t u = blockIdx.x * kThreads + threadIdx.x; u < n; u += gridDim.x * kThreads)
-    {
-        const uint2 b = unitBodies[u];
-        const unsigned long long bit = 1ull << min(color[u], 63u);
-        if (bodyIsDynamic(gMass, b.x, N)) atomicOr(&bodyMask[b.x], bit);
-        if (b.y != b.x && bodyIsDynamic(gMass, b.y, N)) atomicOr(&bodyMask[b.y], bit);
-    }
+    for (uint32_t u = blockIdx.x * kThreads + threadIdx.x; u < n; u += gridDim.x * kThreads) order[mode == 2 ? permutePos(u, n) : u] = u;
 }
 
-__global__ void __launch_bounds__(kThreads) depRankKernel(int exact, const uint2* __restrict__ unitBodies, const uint32_t* __restrict__ numUnits, const uint32_t* __restrict__ color,
+__global__ void __launch_bounds__(kThreads) colorQueueResetKernel(const uint32_t* __restrict__ numUnits, uint32_t* __restrict__ queue, DeviceCounts* cnt)
+{
+    const uint32_t n = *numUnits;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { cnt->colorQueueHead = 0; cnt->colorQueueTail = 0; }
+    for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n + 32u; i += gridDim.x * kThreads) queue[i] = 0xFFFFFFFFu;
+}
+
+__global__ void __launch_bounds__(kThreads) depRankKernel(int mode /* 0 colours, 1 canonical index order, 2 permuted order */, const uint2* __restrict__ unitBodies, const uint32_t* __restrict__ numUnits, const uint32_t* __restrict__ color,
     const uint32_t* __restrict__ order, const float4* __restrict__ gMass, uint32_t N, const unsigned long long* __restrict__ bodyMask, const uint32_t* __restrict__ bodyBase,
     const uint32_t* __restrict__ adjStart, const uint32_t* __restrict__ adjList, uint2* __restrict__ dep)
 {
@@ -414,10 +435,11 @@ __global__ void __launch_bounds__(kThreads) depRankKernel(int exact, const uint2
             if (side && b.y == b.x) break;
             if (!bodyIsDynamic(gMass, body, N)) continue;
             uint32_t rank = bodyBase[body], deg = rank;
-            if (exact)
-            {   // canonical order: by unit index
+            if (mode)
+            {   // the body's units in solve-position order
                 const uint32_t a0 = adjStart[body], a1 = adjStart[body + 1];
-                for (uint32_t a = a0; a < a1; ++a) rank += (adjList[a] < u) ? 1u : 0u;
+                if (mode == 1) { for (uint32_t a = a0; a < a1; ++a) rank += (adjList[a] < u) ? 1u : 0u; }
+                else { for (uint32_t a = a0; a < a1; ++a) rank += (permutePos(adjList[a], n) < p) ? 1u : 0u; }
                 deg += a1 - a0;
             }
             else
@@ -603,7 +625,7 @@ __global__ void solverResetKernel(DeviceCounts* cnt, JointCounts jc)
 }
 
 // colour one group of units (joint kind or contacts); leaves order[] and colour ranges behind
-static void colorGroup(Context* c, uint32_t group, const uint2* unitBodies, const uint32_t* numUnitsDev, uint32_t maxUnits, bool exact,
+static void colorGroup(Context* c, uint32_t group, const uint2* unitBodies, const uint32_t* numUnitsDev, uint32_t maxUnits, bool exact, bool permuted,
                        uint32_t* color, uint32_t* order, uint32_t* colorStartOut, uint32_t barrierSlot)
 {
     const uint32_t N = c->numBodies;
@@ -618,22 +640,30 @@ static void colorGroup(Context* c, uint32_t group, const uint2* unitBodies, cons
     adjFillKernel<<<G, kThreads, 0, c->stream>>>(unitBodies, numUnitsDev, c->gPos, N, c->adjStart, c->adjFill, c->adjList);
     c->launches++;
 
-    uint32_t* roundDone = c->levelFill;                       // kMaxLevels + 1
-    uint32_t* colorCount = c->levelFill + (kMaxLevels + 1);   // kMaxLevels + 1
-    uint32_t* colorFill = c->levelFill + 2 * (kMaxLevels + 1);
-    cudaMemsetAsync(c->levelFill, 0, sizeof(uint32_t) * 3 * (kMaxLevels + 1), c->stream);
-    int exactI = exact ? 1 : 0;
     DeviceCounts* cnt = c->counts;
-    void* args[] = { &exactI, &group, (void*)&unitBodies, (void*)&numUnitsDev, &c->gPos /* .w = invMass */, (void*)&N, &c->adjStart, &c->adjList, &color, &order, &c->unitPending, &c->unitForbid, &c->nbrCount, &c->nbrList,
-                     &roundDone, &colorCount, &colorStartOut, &colorFill, &cnt, &barrierSlot };
-    static int colorBlocksPerSM = 0;
-    if (!colorBlocksPerSM) { cudaOccupancyMaxActiveBlocksPerMultiprocessor(&colorBlocksPerSM, colorKernel, kColorThreads, 0); if (colorBlocksPerSM < 1) colorBlocksPerSM = 1; if (colorBlocksPerSM > 8) colorBlocksPerSM = 8; }
-    cudaLaunchCooperativeKernel((void*)colorKernel, dim3(c->numSMs * colorBlocksPerSM), dim3(kColorThreads), args, 0, c->stream);
-    c->launches++;
+    const int mode = exact ? 1 : (permuted ? 2 : 0);
+    if (mode == 0)
+    {   // deterministic Jones-Plassmann colouring, queue driven
+        uint32_t* colorCount = c->levelFill + (kMaxLevels + 1);   // kMaxColors entries used
+        uint32_t* colorFill = c->levelFill + 2 * (kMaxLevels + 1);
+        uint32_t* queue = c->colorQueue;
+        cudaMemsetAsync(colorCount, 0, sizeof(uint32_t) * kMaxColors, c->stream);
+        cudaMemsetAsync(colorFill, 0, sizeof(uint32_t) * kMaxColors, c->stream);
+        colorQueueResetKernel<<<G, kThreads, 0, c->stream>>>(numUnitsDev, queue, cnt);
+        colorInitKernel<<<G, kThreads, 0, c->stream>>>(unitBodies, numUnitsDev, c->gPos, N, c->adjStart, c->adjList, color, c->unitForbid, c->nbrCount, c->nbrList, queue, cnt);
+        colorRunKernel<<<c->numSMs * 4, kColorRunThreads, 0, c->stream>>>(group, unitBodies, numUnitsDev, c->gPos, N, c->adjStart, c->adjList, color, c->unitForbid, c->nbrCount, c->nbrList, queue, colorCount, cnt);
+        colorScanKernel<<<1, 32, 0, c->stream>>>(group, colorCount, colorStartOut, cnt);
+        colorScatterKernel<<<G, kThreads, 0, c->stream>>>(unitBodies, numUnitsDev, color, c->gPos, N, colorStartOut, colorFill, order, c->bodyMask);
+        c->launches += 5;
+    }
+    else
+    {
+        orderKernel<<<G, kThreads, 0, c->stream>>>(mode, numUnitsDev, order);
+        c->launches++;
+    }
     // dataflow records of this group (rank / degree of every unit at its bodies), then fold the group into the per-body totals
-    if (!exact) { depMaskKernel<<<G, kThreads, 0, c->stream>>>(unitBodies, numUnitsDev, color, c->gPos, N, c->bodyMask); c->launches++; }
-    depRankKernel<<<G, kThreads, 0, c->stream>>>(exactI, unitBodies, numUnitsDev, color, order, c->gPos, N, c->bodyMask, c->bodyBase, c->adjStart, c->adjList, c->unitDep[group]);
-    bodyBaseAddKernel<<<G, kThreads, 0, c->stream>>>(exactI, N, c->bodyMask, c->adjStart, c->bodyBase, cnt);
+    depRankKernel<<<G, kThreads, 0, c->stream>>>(mode, unitBodies, numUnitsDev, color, order, c->gPos, N, c->bodyMask, c->bodyBase, c->adjStart, c->adjList, c->unitDep[group]);
+    bodyBaseAddKernel<<<G, kThreads, 0, c->stream>>>(mode != 0, N, c->bodyMask, c->adjStart, c->bodyBase, cnt);
     c->launches += 2;
     (void)maxUnits;
 }
@@ -643,6 +673,7 @@ void launchSolver(Context* c, float dt, uint32_t iterations, uint32_t flags)
     DeviceCounts* cnt = c->counts;
     const int G = gridFor(c, 8);
     const bool exact = (flags & B200PHYS_STEP_EXACT_ORDER) != 0;
+    const bool permuted = !exact && (flags & B200PHYS_STEP_PERMUTED) != 0;
     JointCounts jc; for (int k = 0; k < 6; ++k) jc.n[k] = c->numJoints[k];
     solverResetKernel<<<1, 32, 0, c->stream>>>(cnt, jc);
     c->launches++;
@@ -660,7 +691,7 @@ void launchSolver(Context* c, float dt, uint32_t iterations, uint32_t flags)
         if (c->numJoints[k])
         {
             anyJoint = true;
-            colorGroup(c, (uint32_t)k, c->jointBodies[k], &cnt->numJoints[k], c->numJoints[k], exact, c->unitColor[k], c->unitOrder[k],
+            colorGroup(c, (uint32_t)k, c->jointBodies[k], &cnt->numJoints[k], c->numJoints[k], exact, permuted, c->unitColor[k], c->unitOrder[k],
                        c->levelStart + (size_t)k * (kMaxLevels + 1), (uint32_t)k);
         }
     }
@@ -676,7 +707,7 @@ void launchSolver(Context* c, float dt, uint32_t iterations, uint32_t flags)
     manifoldBodiesKernel<<<G, kThreads, 0, c->stream>>>(c->manifolds, unitBodies, cnt);
     c->launches++;
     uint32_t* contactColorStart = c->levelStart + (size_t)6 * (kMaxLevels + 1);
-    colorGroup(c, 6, unitBodies, &cnt->numManifolds, c->maxManifolds, exact, c->unitColor[6], c->unitOrder[6], contactColorStart, 6);
+    colorGroup(c, 6, unitBodies, &cnt->numManifolds, c->maxManifolds, exact, permuted, c->unitColor[6], c->unitOrder[6], contactColorStart, 6);
     uint32_t* slotCount = c->pairDst;              // scratch reuse
     slotCountKernel<<<G, kThreads, 0, c->stream>>>(c->unitOrder[6], c->manifolds, slotCount, cnt);
     c->launches++;

@@ -51,8 +51,11 @@ enum { B200PHYS_MOTOR_VELOCITY = 0, B200PHYS_MOTOR_POSITION = 1 };
 #define B200PHYS_NO_TRANSFORM 0xFFFFFFFFu
 
 /* step flags */
-#define B200PHYS_STEP_EXACT_ORDER 1u /* wavefront levels: reproduces Gauss-Seidel in canonical array order exactly (parity mode) */
-#define B200PHYS_STEP_FAST        0u /* conflict-free colouring (the reference's AVX2 path also re-orders: constraints.cpp:51-184) */
+#define B200PHYS_STEP_EXACT_ORDER 1u /* Gauss-Seidel in canonical array order, exactly (parity mode) */
+#define B200PHYS_STEP_FAST        0u /* colour-sorted order: short dependency chains (the reference's AVX2 path also re-orders:
+                                        constraints.cpp:51-184); the order is exported by b200phys_download_solve_order */
+#define B200PHYS_STEP_PERMUTED    2u /* like FAST, but a fixed pseudo-random permutation instead of a colouring: cheaper to set up,
+                                        longer dependency chains in the sweep */
 
 /* rigid_body_component + physics_transform1_component (reference src/physics/rigid_body.h:18-58). 35 floats. */
 typedef struct b200phys_body {

@@ -11,7 +11,7 @@ def probe(sc, iters=10, steps=30, label="", flags=0):
     st.enable_timing(True)
     acc = None; n = 0
     for s in range(steps):
-        st.step(np.float32(1/120.), iters, flags)
+        st.step(np.float32(1/120.), iters, flags or int(os.environ.get('PROBE_FLAGS', '0')))
         s_ = st.stats()
         if s >= 5:
             v = np.array([s_.msWorld, s_.msBroad, s_.msNarrow, s_.msInit, s_.msSolve, s_.msIntegrate, s_.msTotal])
@@ -49,7 +49,7 @@ def probe_host(config, nx, ny, nz, label, spacing, iters=10, steps=12, mode=0, s
     st.enable_timing(True)
     acc = None; n = 0
     for s in range(steps):
-        st.step(np.float32(1/120.), iters, 0)
+        st.step(np.float32(1/120.), iters, int(os.environ.get('PROBE_FLAGS', '0')))
         s_ = st.stats(check=False)
         if s >= 3:
             v = np.array([s_.msWorld, s_.msBroad, s_.msNarrow, s_.msInit, s_.msSolve, s_.msIntegrate, s_.msTotal]); acc = v if acc is None else acc + v; n += 1
