@@ -85,12 +85,12 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
 
 
-def build_scene(rank, world):
+def build_scene(rank, world, nx=64):
     """configs[1]: 262 144 spheres per GPU (64 x 64 x 64 jittered lattice, spacing 0.96, r = 0.5: a settled pile with ~3 contacts
     per body) in an open box of 5 static AABBs. With N GPUs the pile is (64 N) x 64 x 64 and rank r owns x-layers [64 r, 64 (r+1)):
     ONE scene, slab-decomposed, coupled through the ghost-body halo (BASELINE configs[4] layout, weak scaling)."""
     from d3d12renderer_b200 import scenes
-    return scenes.sphere_pile_slab(64 * world, 64, 64, 64 * rank, 64 * (rank + 1), seed=519431)
+    return scenes.sphere_pile_slab(nx * world, 64, 64 if nx == 64 else 128, nx * rank, nx * (rank + 1), seed=519431)
 
 
 def cpu_reference_sample(steps, warmup):
@@ -142,6 +142,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config5", action="store_true", help="1 048 576 spheres per GPU (128 x 64 x 128 slab per rank: BASELINE configs[4], 8.4 M bodies on 8 GPUs) instead of the default 262 144")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); local_rank = int(os.environ.get("LOCAL_RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
 
@@ -162,9 +163,9 @@ def main():
     W = max(3, args.warmup); K = args.steps
 
     from d3d12renderer_b200 import parallel
-    sc = build_scene(rank, world)
+    sc = build_scene(rank, world, 128 if args.config5 else 64)
     n_bodies = len(sc["bodies"]); n_col = len(sc["colliders"])
-    ghost_cap = 0 if world == 1 else 3 * 64 * 64      # ~2 layers of a 64 x 64 face are ghosts (8.1 k), 1.5x head room
+    ghost_cap = 0 if world == 1 else 3 * 64 * (128 if args.config5 else 64)      # ~2 layers of the slab face are ghosts, 1.5x head room
     st = abi.Stepper(max_bodies=n_bodies + 2 * ghost_cap, max_colliders=n_col + 2 * ghost_cap, max_transforms=4, device=local_rank)
     stream = torch.cuda.Stream()          # a real (non-default) stream: every kernel of the context and the timing events share it
     torch.cuda.set_stream(stream)
@@ -267,9 +268,9 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": "body-steps/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "262144-sphere settled pile per GPU (BASELINE configs[1]), 10 PGS iterations, dt 1/120, fast (colour-sorted) solver order, dataflow sweep",
+            "config": {"workload": ("1048576-sphere settled pile per GPU (BASELINE configs[4])" if args.config5 else "262144-sphere settled pile per GPU (BASELINE configs[1])") + ", 10 PGS iterations, dt 1/120, fast (colour-sorted) solver order, dataflow sweep",
                        "bodies": total_bodies, "bodies_per_gpu": n_bodies, "iterations": ITERATIONS, "contacts_per_gpu": contacts, "pairs_per_gpu": pairs,
-                       "steps_per_s": K / (ms_dev * 1e-3), "parallelism": ("slab decomposition along x, %d x 262144 bodies, ghost-body halo over NCCL (%d ghost bodies on rank 0)" % (world, shard.ghost_counts()[0])) if world > 1 else "single GPU",
+                       "steps_per_s": K / (ms_dev * 1e-3), "parallelism": ("slab decomposition along x, %d slabs, ghost-body halo over NCCL (%d ghost bodies on rank 0)" % (world, shard.ghost_counts()[0])) if world > 1 else "single GPU",
                        "l2_policy": "per-step working set (rows, pair and manifold scratch, body planes) > 126 MB L2; no explicit flush",
                        "state_checksum_y": checksum},
             "e2e": {"value": e2e_value, "unit": "body-steps/s", "ms_per_step": ms_e2e / K, "h2d_bytes_per_step": int(n_bodies * (abi.body_state_dtype.itemsize + 24)),
