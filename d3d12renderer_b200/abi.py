@@ -23,6 +23,7 @@ collider_dtype = np.dtype([
 pair_dtype = np.dtype([("a", "u4"), ("b", "u4")])
 body_pair_dtype = np.dtype([("rbA", "u4"), ("rbB", "u4")])
 contact_dtype = np.dtype([("point", "f4", 3), ("penetrationDepth", "f4"), ("normal", "f4", 3), ("friction_restitution", "u4")])
+begin_event_dtype = np.dtype([("colliderA", "u4"), ("colliderB", "u4"), ("point", "f4", 3), ("normal", "f4", 3), ("relativeVelocity", "f4", 3)])
 
 distance_joint_dtype = np.dtype([("localAnchorA", "f4", 3), ("localAnchorB", "f4", 3), ("globalLength", "f4")])
 ball_joint_dtype = np.dtype([("localAnchorA", "f4", 3), ("localAnchorB", "f4", 3)])
@@ -82,7 +83,7 @@ EXPORTS = [
     "b200phys_upload_forces", "b200phys_upload_body_states", "b200phys_step", "b200phys_synchronize", "b200phys_download_bodies", "b200phys_get_stats",
     "b200phys_download_aabbs", "b200phys_download_pairs", "b200phys_download_contacts", "b200phys_download_collisions",
     "b200phys_download_solve_order", "b200phys_halo_pack", "b200phys_halo_unpack", "b200phys_halo_clear", "b200phys_halo_record_bytes",
-    "b200phys_halo_message_bytes", "b200phys_halo_pack_message", "b200phys_halo_unpack_message", "b200phys_migrate_pack", "b200phys_migrate_unpack",
+    "b200phys_halo_message_bytes", "b200phys_halo_pack_message", "b200phys_halo_unpack_message", "b200phys_migrate_pack", "b200phys_migrate_unpack", "b200phys_enable_events", "b200phys_download_events",
 ]
 
 _lib = None
@@ -129,6 +130,8 @@ def load_library():
     lib.b200phys_halo_unpack_message.argtypes = [vp, vp, u32, u32]
     lib.b200phys_migrate_pack.argtypes = [vp, i32, f32, f32, vp, vp, u32, u32, C.POINTER(u32), C.POINTER(u32)]
     lib.b200phys_migrate_unpack.argtypes = [vp, vp, u32, u32, C.POINTER(u32)]
+    lib.b200phys_enable_events.argtypes = [vp, i32]
+    lib.b200phys_download_events.argtypes = [vp, vp, u32, C.POINTER(u32), vp, u32, C.POINTER(u32)]
     lib.b200phys_halo_record_bytes.restype = u32; lib.b200phys_halo_record_bytes.argtypes = [i32]
     _lib = lib
     return lib
@@ -279,6 +282,18 @@ class Stepper:
 
     def halo_unpack(self, src_bodies_ptr, num_bodies, src_colliders_ptr, num_colliders):
         _check(self.lib, self.lib.b200phys_halo_unpack(self.ctx, C.c_void_p(src_bodies_ptr), num_bodies, C.c_void_p(src_colliders_ptr), num_colliders), "halo_unpack")
+
+    # ---- collision begin / end events
+    def enable_events(self, on=True):
+        _check(self.lib, self.lib.b200phys_enable_events(self.ctx, 1 if on else 0), "enable_events")
+
+    def download_events(self):
+        """-> (begin events [begin_event_dtype], end events [pair_dtype]) of the last step."""
+        nb, ne = C.c_uint32(0), C.c_uint32(0)
+        self.lib.b200phys_download_events(self.ctx, None, 0, C.byref(nb), None, 0, C.byref(ne))
+        b = np.zeros(nb.value, dtype=begin_event_dtype); e = np.zeros(ne.value, dtype=pair_dtype)
+        _check(self.lib, self.lib.b200phys_download_events(self.ctx, _ptr(b) if nb.value else None, nb.value, C.byref(nb), _ptr(e) if ne.value else None, ne.value, C.byref(ne)), "download_events")
+        return b, e
 
     def halo_message_bytes(self, cap_bodies, cap_colliders):
         return int(self.lib.b200phys_halo_message_bytes(cap_bodies, cap_colliders))

@@ -44,6 +44,7 @@ struct DeviceCounts
     uint32_t numBig;
     uint32_t bigMatrixCount;            // min(numBig, 16) * C: size of the big-collider flag matrix
     uint32_t colorQueueHead, colorQueueTail;   // ready queue of the colouring
+    uint32_t numPrevCollisions, numBeginEvents, numEndEvents;   // collision event layer (k_events.cu)
     uint32_t solverAbort;               // set when the dataflow sweep gave up (inconsistent dependency records)
     uint32_t remaining;                 // colouring work counter
     uint32_t overflowPairs, overflowManifolds, overflowGrid, overflowColors, overflowBig, overflowHalo;
@@ -130,6 +131,10 @@ struct Context
     uint32_t* unitColor[kNumGroups] = {};   // colour / level per unit
     uint32_t* unitOrder[kNumGroups] = {};   // units sorted by colour (solve order)
     uint2* unitDep[kNumGroups] = {};        // dataflow record per solve position: rank | degree << 16 for each body
+    // collision begin / end events (allocated by b200phys_enable_events)
+    bool eventsEnabled = false; int evParity = 0;
+    unsigned long long* evKeys[2] = {}; uint2* evPairs[2] = {}; uint32_t* evFlag[2] = {}; uint32_t* evSlot[2] = {};
+    b200phys_collision_begin_event* evBegin = nullptr; b200phys_collider_pair* evEnd = nullptr;
     uint32_t* colorQueue = nullptr;         // ready queue of the colouring (max units of any group)
     unsigned long long* bodyMask = nullptr; // colours taken at each body (current group)
     uint32_t* bodyBase = nullptr;           // units per body in the groups coloured so far
@@ -188,6 +193,7 @@ void launchSolver(Context* c, float dt, uint32_t iterations, uint32_t flags);
 void launchPackAabbs(Context* c, float* devOut);
 
 // utilities (b200_util.cu)
+void launchCollisionEvents(Context* c);
 void scanExclusiveU32(Context* c, const uint32_t* in, uint32_t* out, const uint32_t* devCount, uint32_t maxCount, uint32_t* totalOut /*device, may be null*/);
 void scanExclusiveU64(Context* c, const unsigned long long* in, unsigned long long* out, const uint32_t* devCount, uint32_t maxCount, unsigned long long* totalOut);
 // stable counting sort of n (device count) elements by small keys (< numKeys <= 64): dst[i] = destination slot, keyStart[k] = ranges

@@ -86,6 +86,8 @@ void freeAll(Context& c)
         c.pairKey, c.pairsTyped, c.pairDst, c.pairsSorted, c.manTmp, c.manScan, c.manScanOut, c.epaSimplex, c.epaWork, c.collisions, c.manifolds, c.contacts, c.contactBodies,
         c.unitPending, c.unitForbid, c.nbrCount, c.nbrList, c.adjStart, c.adjFill, c.adjList, c.levelStart, c.levelFill, c.slotOfContact, c.unitSlotStart, c.unitInfo, c.rows, c.rowImp, c.scanTmp, c.scanTmp64, c.sortHist, c.staging, c.counts, c.haloBuf };
     for (void* p : ptrs) if (p) cudaFree(p);
+    for (int k = 0; k < 2; ++k) { if (c.evKeys[k]) cudaFree(c.evKeys[k]); if (c.evPairs[k]) cudaFree(c.evPairs[k]); if (c.evFlag[k]) cudaFree(c.evFlag[k]); if (c.evSlot[k]) cudaFree(c.evSlot[k]); }
+    if (c.evBegin) cudaFree(c.evBegin); if (c.evEnd) cudaFree(c.evEnd);
     for (uint32_t g = 0; g < kNumGroups; ++g) { if (c.unitColor[g]) cudaFree(c.unitColor[g]); if (c.unitOrder[g]) cudaFree(c.unitOrder[g]); if (c.unitDep[g]) cudaFree(c.unitDep[g]); }
     for (int k = 0; k < 6; ++k) { if (c.jointIn[k]) cudaFree(c.jointIn[k]); if (c.jointBodies[k]) cudaFree(c.jointBodies[k]); if (c.jointRows[k]) cudaFree(c.jointRows[k]); }
     if (c.hostCounts) cudaFreeHost(c.hostCounts);
@@ -281,6 +283,7 @@ int b200phys_step(b200phys_context* ctx, float dt, uint32_t numSolverIterations,
     launchNarrowphase(&c);                                  // physics.cpp:1233
     if (c.timing) cudaEventRecord(c.ev[3], c.stream);
     launchIntegrateForces(&c, dt);                          // physics.cpp:1266-1279
+    launchCollisionEvents(&c);                              // physics.cpp:1284
     launchSolver(&c, dt, numSolverIterations, flags);       // physics.cpp:1316-1334 (records ev[4] before the iterations)
     if (c.timing) cudaEventRecord(c.ev[5], c.stream);
     launchIntegrateVelocities(&c, dt);                      // physics.cpp:1338-1348
@@ -288,6 +291,45 @@ int b200phys_step(b200phys_context* ctx, float dt, uint32_t numSolverIterations,
     c.stepped = true;
     CK(cudaGetLastError());
     return 0;
+}
+
+int b200phys_enable_events(b200phys_context* ctx, int enable)
+{
+    if (!ctx) return B200PHYS_E_INVALID;
+    Context& c = ctx->c; CK(cudaSetDevice(c.device));
+    if (enable && !c.evBegin)
+    {
+        if (c.cfg.maxColliders >= (1u << 28)) return B200PHYS_E_INVALID;      // 28 bits per collider in the event key
+        const size_t M = c.maxManifolds;
+        for (int k = 0; k < 2; ++k) { CK(devAlloc(c.evKeys[k], M + 2)); CK(devAlloc(c.evPairs[k], M + 2)); CK(devAlloc(c.evFlag[k], M + 2)); CK(devAlloc(c.evSlot[k], M + 2)); }
+        CK(devAlloc(c.evBegin, M + 1)); CK(devAlloc(c.evEnd, M + 1));
+    }
+    if (enable && !c.eventsEnabled)
+    {   // start from an empty "previous frame" (event_context is created empty, physics.cpp:946-950)
+        CK(cudaStreamSynchronize(c.stream));
+        const uint32_t zero[3] = { 0, 0, 0 };
+        CK(cudaMemcpy(&c.counts->numPrevCollisions, zero, sizeof(zero), cudaMemcpyHostToDevice));
+    }
+    c.eventsEnabled = enable != 0;
+    return 0;
+}
+
+int b200phys_download_events(b200phys_context* ctx, b200phys_collision_begin_event* beginOut, uint32_t beginCapacity, uint32_t* numBegin,
+                             b200phys_collider_pair* endOut, uint32_t endCapacity, uint32_t* numEnd)
+{
+    if (!ctx || !numBegin || !numEnd) return B200PHYS_E_INVALID;
+    Context& c = ctx->c; CK(cudaSetDevice(c.device));
+    *numBegin = *numEnd = 0;
+    if (!c.eventsEnabled || !c.stepped) return 0;
+    uint32_t n[2] = { 0, 0 };
+    CK(cudaMemcpyAsync(n, &c.counts->numBeginEvents, sizeof(n), cudaMemcpyDeviceToHost, c.stream));
+    CK(cudaStreamSynchronize(c.stream));
+    *numBegin = n[0]; *numEnd = n[1];
+    const uint32_t nb = n[0] < beginCapacity ? n[0] : beginCapacity, ne = n[1] < endCapacity ? n[1] : endCapacity;
+    if (beginOut && nb) CK(cudaMemcpyAsync(beginOut, c.evBegin, sizeof(b200phys_collision_begin_event) * (size_t)nb, cudaMemcpyDeviceToHost, c.stream));
+    if (endOut && ne) CK(cudaMemcpyAsync(endOut, c.evEnd, sizeof(b200phys_collider_pair) * (size_t)ne, cudaMemcpyDeviceToHost, c.stream));
+    CK(cudaStreamSynchronize(c.stream));
+    return (n[0] > beginCapacity || n[1] > endCapacity) ? B200PHYS_E_CAPACITY : 0;
 }
 
 int b200phys_synchronize(b200phys_context* ctx)

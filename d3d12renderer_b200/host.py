@@ -38,6 +38,9 @@ def load_library():
     lib.b200host_get_hull_triangles.argtypes = [vp, u32, vp]
     lib.b200host_mass_properties.argtypes = [vp, vp, vp, vp, vp]
     lib.b200host_physics_step.argtypes = [vp, C.POINTER(C.c_float), C.c_float, u32, C.c_int, u32, C.c_int]
+    lib.b200host_physics_step_with_events.argtypes = [vp, C.POINTER(C.c_float), C.c_float, u32, C.c_int, u32, C.c_int]
+    lib.b200host_event_log_counts.argtypes = [C.POINTER(u32)]; lib.b200host_event_log_counts.restype = u32
+    lib.b200host_event_log_get.argtypes = [vp, vp, vp]
     lib.b200host_get_render_transforms.argtypes = [vp, vp]
     lib.b200host_get_stats.argtypes = [vp, C.POINTER(abi.Stats)]
     _lib = lib
@@ -107,6 +110,18 @@ class HostScene:
         if rc:
             raise abi.B200PhysError("physicsStep failed: %d" % rc)
         return t.value
+
+    def physics_step_with_events(self, timer, dt, iterations=30, fixed_frame_rate=True, frame_rate=120, exact_order=False):
+        """physicsStep with collision callbacks installed -> (timer, begin entity pairs [n,2], begin payload [n,9], end entity pairs [m,2])
+        in the order the callbacks fired."""
+        t = C.c_float(timer)
+        rc = self.lib.b200host_physics_step_with_events(self.ptr, C.byref(t), dt, iterations, 1 if fixed_frame_rate else 0, frame_rate, 1 if exact_order else 0)
+        if rc:
+            raise abi.B200PhysError("physicsStep failed: %d" % rc)
+        ne = C.c_uint32(0); nb = self.lib.b200host_event_log_counts(C.byref(ne))
+        be = np.zeros((nb, 2), dtype=np.uint32); pl = np.zeros((nb, 9), dtype=np.float32); ee = np.zeros((ne.value, 2), dtype=np.uint32)
+        self.lib.b200host_event_log_get(_p(be), _p(pl), _p(ee))
+        return t.value, be, pl, ee
 
     def render_transforms(self):
         out = np.zeros((self.lib.b200host_num_bodies(self.ptr), 7), dtype=np.float32)

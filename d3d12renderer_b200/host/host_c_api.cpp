@@ -183,6 +183,29 @@ int b200host_physics_step(void* s, float* timer, float dt, uint32_t iterations, 
     memory_arena arena;
     return physicsStep(*(game_scene*)s, arena, *timer, st, dt);
 }
+// same, with collision callbacks installed that log what they receive (tests): begin = entityA, entityB, position, normal,
+// relative velocity (2 + 9 values); end = entityA, entityB. The logs are overwritten by every call.
+static std::vector<uint32_t> gBeginEntities, gEndEntities; static std::vector<float> gBeginPayload;
+int b200host_physics_step_with_events(void* s, float* timer, float dt, uint32_t iterations, int fixedFrameRate, uint32_t frameRate, int exactOrder)
+{
+    physics_settings st; st.fixedFrameRate = fixedFrameRate != 0; st.frameRate = frameRate; st.numRigidSolverIterations = iterations; st.exactConstraintOrder = exactOrder != 0;
+    gBeginEntities.clear(); gEndEntities.clear(); gBeginPayload.clear();
+    st.collisionBeginCallback = [](const collision_begin_event& e)
+    {
+        gBeginEntities.push_back(e.entityA); gBeginEntities.push_back(e.entityB);
+        const float v[9] = { e.position.x, e.position.y, e.position.z, e.normal.x, e.normal.y, e.normal.z, e.relativeVelocity.x, e.relativeVelocity.y, e.relativeVelocity.z };
+        gBeginPayload.insert(gBeginPayload.end(), v, v + 9);
+    };
+    st.collisionEndCallback = [](const collision_end_event& e) { gEndEntities.push_back(e.entityA); gEndEntities.push_back(e.entityB); };
+    memory_arena arena;
+    return physicsStep(*(game_scene*)s, arena, *timer, st, dt);
+}
+uint32_t b200host_event_log_counts(uint32_t* numEnd) { *numEnd = (uint32_t)gEndEntities.size() / 2; return (uint32_t)gBeginEntities.size() / 2; }
+void b200host_event_log_get(uint32_t* beginEntities, float* beginPayload9, uint32_t* endEntities)
+{
+    if (!gBeginEntities.empty()) { memcpy(beginEntities, gBeginEntities.data(), 4 * gBeginEntities.size()); memcpy(beginPayload9, gBeginPayload.data(), 4 * gBeginPayload.size()); }
+    if (!gEndEntities.empty()) memcpy(endEntities, gEndEntities.data(), 4 * gEndEntities.size());
+}
 // entity (render) transforms of the rigid bodies after physicsStep: rotation(4) + position(3) per body
 void b200host_get_render_transforms(void* sp, float* out7)
 {

@@ -2,6 +2,7 @@
 // (scene-build time), joint builders, the ragdoll generator and the physicsStep() driver. The per-step physics itself runs on
 // the GPU through the C ABI; this file contains no CPU implementation of any step stage.
 #include "physics_host.h"
+#include <algorithm>
 #include <cstring>
 #include <cstdio>
 
@@ -495,7 +496,41 @@ static int physicsStepInternal(game_scene& scene, const physics_settings& settin
         }
         scene.jointsDirty = false;
     }
+    const bool wantEvents = (bool)settings.collisionBeginCallback || (bool)settings.collisionEndCallback;
+    if (wantEvents != scene.eventsEnabled) { r = b200phys_enable_events(scene.ctx, wantEvents ? 1 : 0); if (r) return r; scene.eventsEnabled = wantEvents; }
     r = b200phys_step(scene.ctx, dt, settings.numRigidSolverIterations, settings.exactConstraintOrder ? B200PHYS_STEP_EXACT_ORDER : B200PHYS_STEP_FAST); if (r) return r;
+    if (wantEvents)
+    {   // handleCollisionCallbacks (physics.cpp:1037-1178): the device did the frame-to-frame diff, the host only dispatches, in the
+        // reference's order: both lists sorted by (colliderA, colliderB) and merged, end before begin on ties of position
+        uint32_t nb = 0, ne = 0;
+        r = b200phys_download_events(scene.ctx, nullptr, 0, &nb, nullptr, 0, &ne); if (r && r != B200PHYS_E_CAPACITY) return r;
+        std::vector<b200phys_collision_begin_event> be(nb); std::vector<b200phys_collider_pair> ee(ne);
+        r = b200phys_download_events(scene.ctx, be.data(), nb, &nb, ee.data(), ne, &ne); if (r) return r;
+        std::sort(be.begin(), be.end(), [](const b200phys_collision_begin_event& x, const b200phys_collision_begin_event& y) { return x.colliderA != y.colliderA ? x.colliderA < y.colliderA : x.colliderB < y.colliderB; });
+        std::sort(ee.begin(), ee.end(), [](const b200phys_collider_pair& x, const b200phys_collider_pair& y) { return x.a != y.a ? x.a < y.a : x.b < y.b; });
+        const size_t C = scene.colliders.size();
+        auto col = [&](uint32_t worldIndex) -> const collider_component& { return scene.colliders[C - 1 - worldIndex]; };   // physics.cpp:1058-1059
+        size_t ib = 0, ie = 0;
+        while (ib < be.size() || ie < ee.size())
+        {
+            const bool takeEnd = ie < ee.size() && (ib >= be.size() || ee[ie].a < be[ib].colliderA || (ee[ie].a == be[ib].colliderA && ee[ie].b < be[ib].colliderB));
+            if (takeEnd)
+            {
+                const collider_component& a = col(ee[ie].a); const collider_component& b = col(ee[ie].b);
+                if (settings.collisionEndCallback) settings.collisionEndCallback(collision_end_event{ a.parentEntity, b.parentEntity, a, b });
+                ++ie;
+            }
+            else
+            {
+                const b200phys_collision_begin_event& e = be[ib];
+                const collider_component& a = col(e.colliderA); const collider_component& b = col(e.colliderB);
+                if (settings.collisionBeginCallback)
+                    settings.collisionBeginCallback(collision_begin_event{ a.parentEntity, b.parentEntity, a, b, b200::mk3(e.point[0], e.point[1], e.point[2]),
+                                                                           b200::mk3(e.normal[0], e.normal[1], e.normal[2]), b200::mk3(e.relativeVelocity[0], e.relativeVelocity[1], e.relativeVelocity[2]) });
+                ++ib;
+            }
+        }
+    }
     std::vector<b200phys_body_state> states(bodies.size());
     r = b200phys_download_bodies(scene.ctx, states.data(), (uint32_t)states.size()); if (r) return r;
     scene.scatterBodyStates(states.data(), (uint32_t)states.size());

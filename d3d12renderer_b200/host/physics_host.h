@@ -101,7 +101,23 @@ struct hinge_constraint_handle { uint32_t index; };
 struct cone_twist_constraint_handle { uint32_t index; };
 struct slider_constraint_handle { uint32_t index; };
 
-// physics.h:382-400 (callbacks belong to the event layer, a "next" row)
+// physics.h:356-380: collision events handed to the callbacks of physics_settings
+struct game_scene;
+struct collision_begin_event
+{
+    entity_handle entityA, entityB;                  // parents of the two colliders (scene_entity in the reference)
+    const collider_component& colliderA; const collider_component& colliderB;
+    vec3 position, normal, relativeVelocity;
+};
+struct collision_end_event
+{
+    entity_handle entityA, entityB;
+    const collider_component& colliderA; const collider_component& colliderB;
+};
+typedef std::function<void(const collision_begin_event&)> collision_begin_event_func;
+typedef std::function<void(const collision_end_event&)> collision_end_event_func;
+
+// physics.h:382-400
 struct physics_settings
 {
     bool fixedFrameRate = true;
@@ -111,6 +127,8 @@ struct physics_settings
     uint32_t numClothVelocityIterations = 0, numClothPositionIterations = 1, numClothDriftIterations = 0;
     bool simdBroadPhase = true, simdNarrowPhase = true, simdConstraintSolver = true;   // accepted, ignored: one CUDA path
     bool exactConstraintOrder = false;   // extension: B200PHYS_STEP_EXACT_ORDER (canonical Gauss-Seidel order)
+    collision_begin_event_func collisionBeginCallback;   // physics.h:398-399; called in the reference's order (sorted by collider pair)
+    collision_end_event_func collisionEndCallback;
 };
 
 struct memory_arena {};   // the reference's per-step scratch source (core/memory.h:52-112); device scratch lives in the context
@@ -141,6 +159,7 @@ struct game_scene
     std::vector<rigid_body_component> rigidBodies; std::vector<entity_handle> rigidBodyEntity;
     std::vector<trs> physicsTransform0, physicsTransform1;      // per rigid body (rigid_body.h:48-58)
     std::vector<collider_component> colliders;                  // creation order; world index = reverse (physics.cpp:635-641)
+    bool eventsEnabled = false;                                 // collision events switched on in the device context
     std::vector<bounding_hull_geometry> hullGeometries;
     std::vector<distance_constraint> distanceConstraints; std::vector<ball_constraint> ballConstraints; std::vector<fixed_constraint> fixedConstraints;
     std::vector<hinge_constraint> hingeConstraints; std::vector<cone_twist_constraint> coneTwistConstraints; std::vector<slider_constraint> sliderConstraints;

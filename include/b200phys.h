@@ -174,6 +174,14 @@ typedef struct b200phys_contact {
     uint32_t friction_restitution;  /* (uint16 friction << 16) | uint16 restitution, truncating (collision_narrow.cpp:2237) */
 } b200phys_contact;
 
+/* Collision begin event (collision_begin_event, physics.h:363-375): contact point and normal averaged over the manifold, relative
+ * velocity (B - A) of the two bodies at that point before the solver ran. */
+typedef struct b200phys_collision_begin_event
+{
+    uint32_t colliderA, colliderB;      /* in the narrow phase's type order */
+    float    point[3], normal[3], relativeVelocity[3];
+} b200phys_collision_begin_event;
+
 typedef struct b200phys_config {
     int32_t  device;                /* CUDA device ordinal */
     uint32_t maxBodies;
@@ -232,6 +240,13 @@ int b200phys_synchronize(b200phys_context* ctx);
 
 /* results (device -> host) --------------------------------------------------------------------------------------- */
 int b200phys_download_bodies(b200phys_context* ctx, b200phys_body_state* out, uint32_t count);
+/* Collision begin / end events (reference: handleCollisionCallbacks, physics.cpp:1037-1178). Off by default; enabling allocates the
+ * per-manifold key lists. After every step: the collider pairs that collide now but did not in the previous step (begin, with the
+ * averaged contact) and those that stopped colliding (end), each list ordered by (type bucket, lower collider, higher collider).
+ * The first enabled step reports every collision as a begin. Trigger / force-field overlap events are not produced yet. */
+int b200phys_enable_events(b200phys_context* ctx, int enable);
+int b200phys_download_events(b200phys_context* ctx, b200phys_collision_begin_event* beginOut, uint32_t beginCapacity, uint32_t* numBegin,
+                             b200phys_collider_pair* endOut, uint32_t endCapacity, uint32_t* numEnd);
 int b200phys_get_stats(b200phys_context* ctx, b200phys_stats* out);
 /* parity / event-layer taps (each returns the element count through *count; out may be NULL to query the count) */
 int b200phys_download_aabbs(b200phys_context* ctx, float* outMinMax6, uint32_t* count);

@@ -366,6 +366,48 @@ void Oracle::solveContacts(const uint32_t* order, uint32_t n)
 }
 
 // ------------------------------------------------------------------------------------------------------- the step
+// handleCollisionCallbacks (physics.cpp:1037-1178): this frame's colliding pairs, sorted, are merged against last frame's;
+// pairs only in the new list raise a begin event (contact point / normal averaged over the manifold, relative velocity of the
+// two bodies at that point from the post-force, pre-solve global state), pairs only in the old list an end event.
+// The reference keys by EnTT entity handles; collider indices (its own dense stand-in for them, physics.cpp:1058-1059) are used here.
+void Oracle::collisionEvents()
+{
+    std::vector<CollisionKey> cur;
+    uint32_t contactOffset = 0;
+    for (size_t i = 0; i < collisions.size(); ++i)
+    {
+        cur.push_back(CollisionKey{ collisions[i].a, collisions[i].b, contactOffset, contactCount[i] });
+        contactOffset += contactCount[i];
+    }
+    auto less = [](const CollisionKey& x, const CollisionKey& y) { return x.a != y.a ? x.a < y.a : x.b < y.b; };
+    auto same = [](const CollisionKey& x, const CollisionKey& y) { return x.a == y.a && x.b == y.b; };
+    std::sort(cur.begin(), cur.end(), less);
+    beginEvents.clear(); endEvents.clear();
+    const uint32_t dummy = (uint32_t)bodies.size();
+    auto begin = [&](const CollisionKey& k)
+    {
+        const float norm = 1.f / (float)k.numContacts;
+        V3 point = v3(0.f), normal = v3(0.f);
+        for (uint32_t i = 0; i < k.numContacts; ++i) { point += contacts[k.contactOffset + i].point; normal += contacts[k.contactOffset + i].normal; }
+        point *= norm; normal *= norm;
+        const WCol& ca = wcol[k.a]; const WCol& cb = wcol[k.b];
+        const BodyG& A = g[ca.objType == B200PHYS_OBJ_RIGID_BODY ? ca.objIndex : dummy];
+        const BodyG& B = g[cb.objType == B200PHYS_OBJ_RIGID_BODY ? cb.objIndex : dummy];
+        const V3 velA = A.v + cross(A.w, point - A.position), velB = B.v + cross(B.w, point - B.position);
+        beginEvents.push_back(BeginEvent{ k.a, k.b, point, normal, velB - velA });
+    };
+    size_t p = 0, t = 0;
+    while (p < prevFrameCollisions.size() && t < cur.size())
+    {
+        if (same(prevFrameCollisions[p], cur[t])) { ++p; ++t; continue; }
+        if (less(prevFrameCollisions[p], cur[t])) { endEvents.push_back(Pair{ prevFrameCollisions[p].a, prevFrameCollisions[p].b }); ++p; }
+        else { begin(cur[t]); ++t; }
+    }
+    while (p < prevFrameCollisions.size()) { endEvents.push_back(Pair{ prevFrameCollisions[p].a, prevFrameCollisions[p].b }); ++p; }
+    while (t < cur.size()) { begin(cur[t]); ++t; }
+    prevFrameCollisions = std::move(cur);
+}
+
 void Oracle::step(float dt, uint32_t iterations, const uint32_t* contactOrder, const uint32_t* const jointOrder[6])
 {
     nstats = NarrowStats();
@@ -374,6 +416,7 @@ void Oracle::step(float dt, uint32_t iterations, const uint32_t* contactOrder, c
     broadphaseSAP();                        double t2 = nowMs();
     narrowphase();                          double t3 = nowMs();
     integrateForces(dt);                    double t4 = nowMs();
+    collisionEvents();                      // physics.cpp:1284 (after the force integration, before the solver)
     initJoints(dt);
     initContacts(dt);                       double t5 = nowMs();
     for (uint32_t it = 0; it < iterations; ++it)

@@ -53,6 +53,14 @@ struct Oracle
     NarrowStats nstats;
     uint32_t numNonCollisionInteractions = 0;
 
+    // collision begin / end events (handleCollisionCallbacks, physics.cpp:1037-1178), keyed by collider pair instead of entity pair
+    struct CollisionKey { uint32_t a, b, contactOffset, numContacts; };
+    struct BeginEvent { uint32_t a, b; V3 point, normal, relativeVelocity; };
+    std::vector<CollisionKey> prevFrameCollisions;      // event_context::prevFrameCollisions (physics.cpp:946-950)
+    std::vector<BeginEvent> beginEvents;
+    std::vector<Pair> endEvents;
+    void collisionEvents();
+
     int pairOrder = ORDER_CANONICAL;
     // timing of the last step by reference stage name (ms)
     double msWorld = 0, msBroad = 0, msNarrow = 0, msForces = 0, msInit = 0, msSolve = 0, msIntegrate = 0;

@@ -135,6 +135,20 @@ void oracle_get_contacts(oracle_ctx* c, b200phys_contact* out, b200phys_body_pai
         if (bodies) bodies[i] = c->o.contactBodies[i];
     }
 }
+// collision begin / end events of the last step: begin = 11 floats (a, b as uint32 bits, point, normal, relative velocity)
+uint32_t oracle_num_begin_events(oracle_ctx* c) { return (uint32_t)c->o.beginEvents.size(); }
+uint32_t oracle_num_end_events(oracle_ctx* c) { return (uint32_t)c->o.endEvents.size(); }
+void oracle_get_events(oracle_ctx* c, uint32_t* beginPairs, float* beginPayload9, uint32_t* endPairs)
+{
+    for (size_t i = 0; i < c->o.beginEvents.size(); ++i)
+    {
+        const auto& e = c->o.beginEvents[i];
+        beginPairs[2 * i] = e.a; beginPairs[2 * i + 1] = e.b;
+        const float v[9] = { e.point.x, e.point.y, e.point.z, e.normal.x, e.normal.y, e.normal.z, e.relativeVelocity.x, e.relativeVelocity.y, e.relativeVelocity.z };
+        for (int k = 0; k < 9; ++k) beginPayload9[9 * i + k] = v[k];
+    }
+    for (size_t i = 0; i < c->o.endEvents.size(); ++i) { endPairs[2 * i] = c->o.endEvents[i].a; endPairs[2 * i + 1] = c->o.endEvents[i].b; }
+}
 uint32_t oracle_num_collisions(oracle_ctx* c) { return (uint32_t)c->o.collisions.size(); }
 void oracle_get_collisions(oracle_ctx* c, b200phys_collider_pair* out, uint8_t* counts)
 {

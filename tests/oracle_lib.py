@@ -155,6 +155,13 @@ class Oracle:
         p = np.empty(n, dtype=abi.pair_dtype); k = np.empty(n, dtype=np.uint8)
         self.lib.oracle_get_collisions(self.ctx, _p(p), _p(k)); return p, k
 
+    def events(self):
+        """Collision begin / end events of the last step: (begin pairs [n,2], begin payload [n,9] = point, normal, relative velocity, end pairs [m,2])."""
+        self.lib.oracle_num_begin_events.restype = C.c_uint32; self.lib.oracle_num_end_events.restype = C.c_uint32
+        nb, ne = self.lib.oracle_num_begin_events(self.ctx), self.lib.oracle_num_end_events(self.ctx)
+        bp = np.zeros((nb, 2), dtype=np.uint32); pl = np.zeros((nb, 9), dtype=np.float32); ep = np.zeros((ne, 2), dtype=np.uint32)
+        self.lib.oracle_get_events(self.ctx, _p(bp), _p(pl), _p(ep)); return bp, pl, ep
+
     def narrow_stats(self):
         out = np.zeros(8, dtype=np.uint32); self.lib.oracle_get_narrow_stats(self.ctx, _p(out))
         return dict(zip(["gjkIterCap", "gjkErrors", "epaNotConverged", "epaOutOfMemory", "asserts", "epaMaxTriangles", "epaMaxEdges", "epaMaxPoints"], out.tolist()))

@@ -248,3 +248,21 @@ def test_oracle_reproduces_golden_fixtures(name):
     for f in ("position", "rotation", "linearVelocity", "angularVelocity"):
         # same compiler flags -> normally bit-identical; 1e-6 leaves room for a different libm (atan2/acos) on another host
         assert np.max(np.abs(s[f].astype(np.float64) - expect["states"][f]) / np.maximum(1.0, np.abs(expect["states"][f]))) <= 1e-6
+
+
+def test_oracle_collision_events_first_step_all_begin_then_none():
+    """event_context starts empty (physics.cpp:946-950): the first step reports every collision as a begin event; an unchanged
+    contact set reports nothing; the payload is the manifold average and the pre-solve relative velocity."""
+    import oracle_lib
+    sc = scenes.spheres_on_ground(4, mode="rest")
+    orc = oracle_lib.Oracle(sc, canonical=True)
+    orc.step(np.float32(1 / 120.0), 10)
+    bp, pl, ep = orc.events()
+    col, cnt = orc.collisions()
+    assert len(bp) == len(col) == 16 and len(ep) == 0
+    assert np.allclose(pl[:, 3:6], pl[0, 3:6]) and abs(abs(pl[0, 4]) - 1.0) < 1e-6        # sphere on floor: vertical normal
+    g = np.float32(9.81) / 120
+    assert np.allclose(np.abs(pl[:, 7]), g / (1 + 0.4 / 120), rtol=1e-4)                  # one step of gravity (damped), before the solver
+    orc.step(np.float32(1 / 120.0), 10)
+    bp2, _, ep2 = orc.events()
+    assert len(bp2) == 0 and len(ep2) == 0

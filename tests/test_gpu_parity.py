@@ -199,3 +199,49 @@ def test_gpu_reproduces_golden_fixtures(name):
     c, b = st.download_contacts()
     assert np.array_equal(b, expect["contact_bodies"]) and np.array_equal(c["friction_restitution"], expect["contacts"]["friction_restitution"])
     assert_states_close(st.download_bodies(), expect["states"], 1e-4)
+
+
+def _sorted_events(pairs, payload=None):
+    order = np.lexsort((pairs[:, 1], pairs[:, 0])) if len(pairs) else np.zeros(0, dtype=np.int64)
+    return (pairs[order], payload[order]) if payload is not None else pairs[order]
+
+
+def test_collision_begin_end_events_match_the_oracle():
+    """handleCollisionCallbacks (physics.cpp:1037-1178): per step the collider pairs that start / stop colliding, with the manifold-
+    averaged contact and the pre-solve relative velocity; device diff of consecutive manifold lists against the oracle's merge."""
+    sc = scenes.sphere_box_drop(6, 5, 6, spacing=1.04, base_y=0.55)
+    sc["bodies"]["linearVelocity"][:, 1] = -3.0          # hit the floor and each other within a few steps, then bounce
+    st = make_stepper(sc); st.enable_events(True)
+    orc = oracle_lib.Oracle(sc, canonical=True)
+    total_b = total_e = 0
+    for step in range(40):
+        st.step(DT, 10, abi.STEP_EXACT_ORDER); orc.step(DT, 10)
+        b, e = st.download_events()
+        ob, opl, oe = orc.events()
+        gb, gpl = _sorted_events(np.stack([b["colliderA"], b["colliderB"]], 1).astype(np.uint32), np.concatenate([b["point"], b["normal"], b["relativeVelocity"]], 1))
+        rb, rpl = _sorted_events(ob, opl)
+        assert np.array_equal(gb, rb), "begin events differ at step %d" % step
+        assert np.array_equal(_sorted_events(np.stack([e["a"], e["b"]], 1).astype(np.uint32)), _sorted_events(oe)), "end events differ at step %d" % step
+        if len(gb):
+            assert np.max(np.abs(gpl - rpl) / np.maximum(1.0, np.abs(rpl))) <= 1e-4
+        total_b += len(gb); total_e += len(oe)
+    assert total_b > 100 and total_e > 10, (total_b, total_e)     # the scene really produces both kinds
+
+
+def test_host_mirror_collision_callbacks_fire_in_reference_order():
+    """physics_settings::collisionBeginCallback / collisionEndCallback through the host mirror: entity pairs sorted like the reference's
+    merge loop, payload equal to the C-ABI events of the same step."""
+    sc = host.build_scene(host.CONFIG_SPHERES_ON_GROUND, 6, 1, 6, seed=15681923, mode=1, spacing=1.25)
+    hs = sc["host_scene"]
+    st = make_stepper(sc); st.enable_events(True)
+    timer = 0.0
+    seen_begin = 0
+    for step in range(3):
+        st.step(DT, 30, abi.STEP_FAST)
+        b, e = st.download_events()
+        timer, be, pl, ee = hs.physics_step_with_events(timer, float(DT), iterations=30)
+        assert len(be) == len(b) and len(ee) == len(e)
+        order = np.lexsort((b["colliderB"], b["colliderA"]))
+        assert np.allclose(pl[:, 0:3], b["point"][order]) and np.allclose(pl[:, 6:9], b["relativeVelocity"][order])
+        seen_begin += len(be)
+    assert seen_begin >= 36          # every resting sphere starts touching the ground in the first step
