@@ -83,7 +83,7 @@ EXPORTS = [
     "b200phys_upload_forces", "b200phys_upload_body_states", "b200phys_step", "b200phys_synchronize", "b200phys_download_bodies", "b200phys_get_stats",
     "b200phys_download_aabbs", "b200phys_download_pairs", "b200phys_download_contacts", "b200phys_download_collisions",
     "b200phys_download_solve_order", "b200phys_halo_pack", "b200phys_halo_unpack", "b200phys_halo_clear", "b200phys_halo_record_bytes",
-    "b200phys_halo_message_bytes", "b200phys_halo_pack_message", "b200phys_halo_unpack_message", "b200phys_migrate_pack", "b200phys_migrate_unpack", "b200phys_enable_events", "b200phys_download_events",
+    "b200phys_halo_message_bytes", "b200phys_halo_pack_message", "b200phys_halo_unpack_message", "b200phys_migrate_pack", "b200phys_migrate_unpack", "b200phys_enable_events", "b200phys_download_events", "b200phys_upload_force_fields", "b200phys_set_global_force_field", "b200phys_download_trigger_events",
 ]
 
 _lib = None
@@ -131,6 +131,9 @@ def load_library():
     lib.b200phys_migrate_pack.argtypes = [vp, i32, f32, f32, vp, vp, u32, u32, C.POINTER(u32), C.POINTER(u32)]
     lib.b200phys_migrate_unpack.argtypes = [vp, vp, u32, u32, C.POINTER(u32)]
     lib.b200phys_enable_events.argtypes = [vp, i32]
+    lib.b200phys_upload_force_fields.argtypes = [vp, vp, u32]
+    lib.b200phys_set_global_force_field.argtypes = [vp, vp]
+    lib.b200phys_download_trigger_events.argtypes = [vp, vp, u32, C.POINTER(u32), vp, u32, C.POINTER(u32)]
     lib.b200phys_download_events.argtypes = [vp, vp, u32, C.POINTER(u32), vp, u32, C.POINTER(u32)]
     lib.b200phys_halo_record_bytes.restype = u32; lib.b200phys_halo_record_bytes.argtypes = [i32]
     _lib = lib
@@ -282,6 +285,21 @@ class Stepper:
 
     def halo_unpack(self, src_bodies_ptr, num_bodies, src_colliders_ptr, num_colliders):
         _check(self.lib, self.lib.b200phys_halo_unpack(self.ctx, C.c_void_p(src_bodies_ptr), num_bodies, C.c_void_p(src_colliders_ptr), num_colliders), "halo_unpack")
+
+    # ---- force fields and triggers
+    def upload_force_fields(self, forces, global_force=None):
+        f = np.ascontiguousarray(forces, dtype=np.float32).reshape(-1, 3)
+        _check(self.lib, self.lib.b200phys_upload_force_fields(self.ctx, _ptr(f) if len(f) else None, len(f)), "upload_force_fields")
+        g = np.zeros(3, dtype=np.float32) if global_force is None else np.ascontiguousarray(global_force, dtype=np.float32)
+        _check(self.lib, self.lib.b200phys_set_global_force_field(self.ctx, _ptr(g)), "set_global_force_field")
+
+    def download_trigger_events(self):
+        """-> (enter [n,2], leave [m,2]) as (triggerIndex, rigidBodyIndex); call once after every step."""
+        ne, nl = C.c_uint32(0), C.c_uint32(0)
+        cap = 1 << 16
+        e = np.zeros((cap, 2), dtype=np.uint32); l = np.zeros((cap, 2), dtype=np.uint32)
+        _check(self.lib, self.lib.b200phys_download_trigger_events(self.ctx, _ptr(e), cap, C.byref(ne), _ptr(l), cap, C.byref(nl)), "download_trigger_events")
+        return e[:ne.value].copy(), l[:nl.value].copy()
 
     # ---- collision begin / end events
     def enable_events(self, on=True):

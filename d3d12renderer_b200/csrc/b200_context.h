@@ -6,6 +6,7 @@
 // host round trip in the middle.
 #pragma once
 #include <cuda_runtime.h>
+#include <vector>
 #include <stdint.h>
 #include "../../include/b200phys.h"
 
@@ -44,6 +45,7 @@ struct DeviceCounts
     uint32_t numBig;
     uint32_t bigMatrixCount;            // min(numBig, 16) * C: size of the big-collider flag matrix
     uint32_t colorQueueHead, colorQueueTail;   // ready queue of the colouring
+    uint32_t numOverlapPairs, numInteractions;   // rigid body vs trigger / force field pairs tested / overlapping this step
     uint32_t numPrevCollisions, numBeginEvents, numEndEvents;   // collision event layer (k_events.cu)
     uint32_t solverAbort;               // set when the dataflow sweep gave up (inconsistent dependency records)
     uint32_t remaining;                 // colouring work counter
@@ -131,6 +133,10 @@ struct Context
     uint32_t* unitColor[kNumGroups] = {};   // colour / level per unit
     uint32_t* unitOrder[kNumGroups] = {};   // units sorted by colour (solve order)
     uint2* unitDep[kNumGroups] = {};        // dataflow record per solve position: rank | degree << 16 for each body
+    // non-collision interactions: allocated on the first upload that contains a trigger / force-field collider
+    uint32_t numNonCollisionColliders = 0; uint4* interactions = nullptr; uint32_t maxInteractions = 0;
+    float4* forceFields = nullptr; uint32_t numForceFields = 0, maxForceFields = 0; float globalForce[3] = { 0.f, 0.f, 0.f };
+    std::vector<unsigned long long>* prevTriggerOverlaps = nullptr;   // host side of the trigger enter / leave diff
     // collision begin / end events (allocated by b200phys_enable_events)
     bool eventsEnabled = false; int evParity = 0;
     unsigned long long* evKeys[2] = {}; uint2* evPairs[2] = {}; uint32_t* evFlag[2] = {}; uint32_t* evSlot[2] = {};

@@ -2,6 +2,7 @@
 // Host side only orchestrates: allocate HBM once (replaces the reference's per-step arena scratch, physics.cpp:1205-1230),
 // enqueue the fixed kernel sequence of one physicsStepInternal (physics.cpp:1180-1362) on the context's stream, copy results.
 // There is no CPU implementation of any stage in this library: without a CUDA device b200phys_create fails.
+#include <algorithm>
 #include "b200_context.h"
 #include <cstdio>
 #include <cstring>
@@ -88,6 +89,7 @@ void freeAll(Context& c)
     for (void* p : ptrs) if (p) cudaFree(p);
     for (int k = 0; k < 2; ++k) { if (c.evKeys[k]) cudaFree(c.evKeys[k]); if (c.evPairs[k]) cudaFree(c.evPairs[k]); if (c.evFlag[k]) cudaFree(c.evFlag[k]); if (c.evSlot[k]) cudaFree(c.evSlot[k]); }
     if (c.evBegin) cudaFree(c.evBegin); if (c.evEnd) cudaFree(c.evEnd);
+    if (c.interactions) cudaFree(c.interactions); if (c.forceFields) cudaFree(c.forceFields); delete c.prevTriggerOverlaps;
     for (uint32_t g = 0; g < kNumGroups; ++g) { if (c.unitColor[g]) cudaFree(c.unitColor[g]); if (c.unitOrder[g]) cudaFree(c.unitOrder[g]); if (c.unitDep[g]) cudaFree(c.unitDep[g]); }
     for (int k = 0; k < 6; ++k) { if (c.jointIn[k]) cudaFree(c.jointIn[k]); if (c.jointBodies[k]) cudaFree(c.jointBodies[k]); if (c.jointRows[k]) cudaFree(c.jointRows[k]); }
     if (c.hostCounts) cudaFreeHost(c.hostCounts);
@@ -252,6 +254,13 @@ int b200phys_upload_colliders(b200phys_context* ctx, const b200phys_collider* co
     Context& c = ctx->c; CK(cudaSetDevice(c.device));
     if (count) CK(cudaMemcpyAsync(c.cLocal, colliders, sizeof(b200phys_collider) * (size_t)count, cudaMemcpyHostToDevice, c.stream));
     c.numColliders = c.numOwnedColliders = count;
+    c.numNonCollisionColliders = 0;
+    for (uint32_t i = 0; i < count; ++i) if (colliders[i].objectType == B200PHYS_OBJ_FORCE_FIELD || colliders[i].objectType == B200PHYS_OBJ_TRIGGER) ++c.numNonCollisionColliders;
+    if (c.numNonCollisionColliders && !c.interactions) { c.maxInteractions = 4u * c.cfg.maxColliders + 1024u; CK(devAlloc(c.interactions, c.maxInteractions)); }
+    if (c.numNonCollisionColliders && !c.forceFields)
+    {   // no force uploaded yet: fields push with zero force
+        c.maxForceFields = c.cfg.maxColliders; CK(devAlloc(c.forceFields, c.maxForceFields + 1)); CK(cudaMemset(c.forceFields, 0, sizeof(float4) * (c.maxForceFields + 1)));
+    }
     return 0;
 }
 
@@ -290,6 +299,64 @@ int b200phys_step(b200phys_context* ctx, float dt, uint32_t numSolverIterations,
     if (c.timing) cudaEventRecord(c.ev[6], c.stream);
     c.stepped = true;
     CK(cudaGetLastError());
+    return 0;
+}
+
+int b200phys_upload_force_fields(b200phys_context* ctx, const float* forces3, uint32_t count)
+{
+    if (!ctx || (count && !forces3)) return B200PHYS_E_INVALID;
+    Context& c = ctx->c; CK(cudaSetDevice(c.device));
+    if (!c.forceFields) { c.maxForceFields = c.cfg.maxColliders; CK(devAlloc(c.forceFields, c.maxForceFields + 1)); CK(cudaMemset(c.forceFields, 0, sizeof(float4) * (c.maxForceFields + 1))); }
+    if (count > c.maxForceFields) return B200PHYS_E_CAPACITY;
+    std::vector<float4> tmp(count);
+    for (uint32_t i = 0; i < count; ++i) tmp[i] = make_float4(forces3[3 * i], forces3[3 * i + 1], forces3[3 * i + 2], 0.f);
+    if (count) { CK(cudaMemcpyAsync(c.forceFields, tmp.data(), sizeof(float4) * count, cudaMemcpyHostToDevice, c.stream)); CK(cudaStreamSynchronize(c.stream)); }
+    c.numForceFields = count;
+    return 0;
+}
+
+int b200phys_set_global_force_field(b200phys_context* ctx, const float force3[3])
+{
+    if (!ctx || !force3) return B200PHYS_E_INVALID;
+    for (int k = 0; k < 3; ++k) ctx->c.globalForce[k] = force3[k];
+    return 0;
+}
+
+// trigger overlaps of the last step -> sorted, unique (trigger, rigid body) keys -> merge against the previous call's list
+// (handleNonCollisionInteractions, physics.cpp:970-1034). The overlap tests ran on the device; this part is a few entries.
+int b200phys_download_trigger_events(b200phys_context* ctx, b200phys_trigger_event* enterOut, uint32_t enterCapacity, uint32_t* numEnter,
+                                     b200phys_trigger_event* leaveOut, uint32_t leaveCapacity, uint32_t* numLeave)
+{
+    if (!ctx || !numEnter || !numLeave) return B200PHYS_E_INVALID;
+    Context& c = ctx->c; CK(cudaSetDevice(c.device));
+    *numEnter = *numLeave = 0;
+    if (!c.stepped) return 0;
+    if (!c.prevTriggerOverlaps) c.prevTriggerOverlaps = new std::vector<unsigned long long>();
+    std::vector<unsigned long long> cur;
+    if (c.numNonCollisionColliders && c.interactions)
+    {
+        uint32_t n = 0;
+        CK(cudaMemcpyAsync(&n, &c.counts->numInteractions, 4, cudaMemcpyDeviceToHost, c.stream));
+        CK(cudaStreamSynchronize(c.stream));
+        std::vector<uint4> it(n);
+        if (n) { CK(cudaMemcpyAsync(it.data(), c.interactions, sizeof(uint4) * (size_t)n, cudaMemcpyDeviceToHost, c.stream)); CK(cudaStreamSynchronize(c.stream)); }
+        for (const uint4& x : it) if (x.z == B200PHYS_OBJ_TRIGGER) cur.push_back(((unsigned long long)x.y << 32) | x.x);
+        std::sort(cur.begin(), cur.end());
+        cur.erase(std::unique(cur.begin(), cur.end()), cur.end());
+    }
+    const std::vector<unsigned long long>& prev = *c.prevTriggerOverlaps;
+    uint32_t ne = 0, nl = 0; size_t p = 0, t = 0;
+    auto emit = [](b200phys_trigger_event* out, uint32_t cap, uint32_t& n, unsigned long long key) { if (out && n < cap) { out[n].triggerIndex = (uint32_t)(key >> 32); out[n].rigidBodyIndex = (uint32_t)key; } ++n; };
+    while (p < prev.size() && t < cur.size())
+    {
+        if (prev[p] == cur[t]) { ++p; ++t; continue; }
+        if (prev[p] < cur[t]) emit(leaveOut, leaveCapacity, nl, prev[p++]); else emit(enterOut, enterCapacity, ne, cur[t++]);
+    }
+    while (p < prev.size()) emit(leaveOut, leaveCapacity, nl, prev[p++]);
+    while (t < cur.size()) emit(enterOut, enterCapacity, ne, cur[t++]);
+    *numEnter = ne; *numLeave = nl;
+    if (ne > enterCapacity || nl > leaveCapacity) return B200PHYS_E_CAPACITY;     // nothing consumed: call again with enough room
+    *c.prevTriggerOverlaps = std::move(cur);
     return 0;
 }
 
@@ -358,7 +425,7 @@ int b200phys_get_stats(b200phys_context* ctx, b200phys_stats* out)
     int r = fetchCounts(c); if (r) return r;
     const DeviceCounts& d = *c.hostCounts;
     memset(out, 0, sizeof(*out));
-    out->numBodies = c.numBodies; out->numColliders = c.numColliders; out->reserved[1] = c.numOwnedBodies; out->reserved[2] = c.numOwnedColliders;
+    out->numBodies = c.numBodies; out->numColliders = c.numColliders; out->reserved[1] = c.numOwnedBodies; out->reserved[2] = c.numOwnedColliders; out->reserved[3] = c.numNonCollisionColliders ? d.numInteractions : 0u;
     out->numBroadphaseOverlaps = d.numPairs; out->numCollisions = d.numManifolds; out->numContacts = d.numContacts;
     out->numBigColliders = d.numBig; out->numGridCells = d.grid.numCells;
     for (int g = 0; g < 7; ++g) out->numColors[g] = d.numColors[g];

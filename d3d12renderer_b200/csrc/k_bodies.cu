@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(kThreads) packBodyStatesKernel(float* __restri
 
 // ------------------------------------------------------------------------------------------------- integrate forces
 // reads 10 float4 planes, writes the 96-byte global state (gVel 32 B AoS, gPos 16 B, gInvI 48 B AoS) per body
-__global__ void __launch_bounds__(kThreads) integrateForcesKernel(uint32_t N, float dt, uint32_t planeStride,
+__global__ void __launch_bounds__(kThreads) integrateForcesKernel(uint32_t N, float dt, uint32_t planeStride, float gfx, float gfy, float gfz,
     const float4* __restrict__ bRot, const float4* __restrict__ bPos, const float4* __restrict__ bCog, const float4* __restrict__ bInvI,
     const float4* __restrict__ bVel, const float4* __restrict__ bAng, float4* __restrict__ bForce, const float4* __restrict__ bTorque,
     float4* __restrict__ gVel, float4* __restrict__ gPos, float4* __restrict__ gInvI)
@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(kThreads) integrateForcesKernel(uint32_t N, fl
         m3 I; I.m[0] = c0.x; I.m[1] = c0.y; I.m[2] = c0.z; I.m[3] = c1.x; I.m[4] = c1.y; I.m[5] = c1.z; I.m[6] = c2.x; I.m[7] = c2.y; I.m[8] = c2.z;
         const m3 Iw = R * I * transpose(R);
 
-        f3 F = xyz(F4);
+        f3 F = xyz(F4) + mk3(gfx, gfy, gfz);      // global force fields (physics.cpp:1273)
         if (invMass > 0.f) F.y += (-9.81f / invMass * gravityFactor);   // GRAVITY, physics.h:11
         const f3 linAcc = F * invMass;
         const f3 angAcc = Iw * xyz(T4);
@@ -314,7 +314,7 @@ void launchPackBodyStates(Context* c, void* dev, uint32_t count)
 void launchIntegrateForces(Context* c, float dt)
 {
     const uint32_t stride = c->cfg.maxBodies + 1;
-    integrateForcesKernel<<<gridFor(c, 8), kThreads, 0, c->stream>>>(c->numBodies, dt, stride, c->bRot, c->bPos, c->bCog, c->bInvI, c->bVel, c->bAng, c->bForce, c->bTorque, c->gVel, c->gPos, c->gInvI);
+    integrateForcesKernel<<<gridFor(c, 8), kThreads, 0, c->stream>>>(c->numBodies, dt, stride, c->globalForce[0], c->globalForce[1], c->globalForce[2], c->bRot, c->bPos, c->bCog, c->bInvI, c->bVel, c->bAng, c->bForce, c->bTorque, c->gVel, c->gPos, c->gInvI);
     c->launches++;
 }
 void launchWorldColliders(Context* c)

@@ -199,6 +199,75 @@ __global__ void __launch_bounds__(128) npEpaKernel(const uint2* __restrict__ sor
     flushCounters(nc, cnt);
 }
 
+// ------------------------------------------------------------------------------ non-collision interactions (event layer)
+// overlapCheck (collision_narrow.cpp:1593-1689): boolean shape test for rigid body vs trigger / force field pairs
+B200_D bool overlapCheckD(const ColRec& A, const ColRec& B, const float4* __restrict__ hullVerts, const uint32_t* __restrict__ hullOffsets, NarrowCounters& nc)
+{
+    const uint32_t ta = __float_as_uint(A.r3.x) & 0xFFu, tb = __float_as_uint(B.r3.x) & 0xFFu;
+    switch (ta * 6u + tb)
+    {
+    case B200PHYS_SPHERE * 6 + B200PHYS_SPHERE:     return sphereVsSphereB(asSphere(A), asSphere(B));
+    case B200PHYS_SPHERE * 6 + B200PHYS_CAPSULE:    return sphereVsCapsuleB(asSphere(A), asCap(B));
+    case B200PHYS_SPHERE * 6 + B200PHYS_CYLINDER:   return sphereVsCylinderB(asSphere(A), asCap(B));
+    case B200PHYS_SPHERE * 6 + B200PHYS_AABB:       return sphereVsBoxB(asSphere(A), asBox(B));
+    case B200PHYS_SPHERE * 6 + B200PHYS_OBB:        return sphereVsObbB(asSphere(A), asObb(B));
+    case B200PHYS_CAPSULE * 6 + B200PHYS_CAPSULE:   return capsuleVsCapsuleB(asCap(A), asCap(B));
+    case B200PHYS_CAPSULE * 6 + B200PHYS_CYLINDER:  return capsuleVsCylinderB(asCap(A), asCap(B));
+    case B200PHYS_CAPSULE * 6 + B200PHYS_AABB:      return gjkTest(supCapsule(asCap(A)), supBox(asBox(B)), nc);
+    case B200PHYS_CAPSULE * 6 + B200PHYS_OBB:       { const ObbS o = asObb(B); return gjkTest(supCapsule(intoObbFrame(asCap(A), o)), supBox(boxOfObb(o)), nc); }
+    case B200PHYS_CYLINDER * 6 + B200PHYS_CYLINDER: return gjkTest(supCylinder(asCap(A)), supCylinder(asCap(B)), nc);
+    case B200PHYS_CYLINDER * 6 + B200PHYS_AABB:     return gjkTest(supCylinder(asCap(A)), supBox(asBox(B)), nc);
+    case B200PHYS_CYLINDER * 6 + B200PHYS_OBB:      { const ObbS o = asObb(B); return gjkTest(supCylinder(intoObbFrame(asCap(A), o)), supBox(boxOfObb(o)), nc); }
+    case B200PHYS_AABB * 6 + B200PHYS_AABB:         return boxVsBoxB(asBox(A), asBox(B));
+    case B200PHYS_AABB * 6 + B200PHYS_OBB:          { const BoxS bx = asBox(A); ObbS o; o.q = qIdentity(); o.c = boxCenter(bx); o.r = boxRadius(bx); return obbVsObbB(o, asObb(B)); }
+    case B200PHYS_OBB * 6 + B200PHYS_OBB:           return obbVsObbB(asObb(A), asObb(B));
+    default:                                        // anything vs hull (types are ordered: B is the hull)
+        if (tb == B200PHYS_HULL && ta <= B200PHYS_HULL) return gjkTest(supportFor(ta, A, hullVerts, hullOffsets), supHull(asHull(B, hullVerts, hullOffsets)), nc);
+        ++nc.asserts; return false;
+    }
+}
+
+__global__ void __launch_bounds__(128) npOverlapKernel(const uint2* __restrict__ sorted, const float4* __restrict__ wCol, const float4* __restrict__ hullVerts,
+    const uint32_t* __restrict__ hullOffsets, uint32_t* __restrict__ flags, DeviceCounts* cnt)
+{
+    const uint32_t q0 = cnt->keyStart[kBucketOverlap], q1 = cnt->keyStart[kBucketOverlap + 1];
+    if (blockIdx.x == 0 && threadIdx.x == 0) cnt->numOverlapPairs = q1 - q0;
+    NarrowCounters nc; nc.epaOverflow = nc.gjkCap = nc.asserts = 0;
+    for (uint32_t q = q0 + blockIdx.x * blockDim.x + threadIdx.x; q < q1; q += gridDim.x * blockDim.x)
+    {
+        const uint2 pr = sorted[q];
+        flags[q - q0] = overlapCheckD(loadCol(wCol, pr.x), loadCol(wCol, pr.y), hullVerts, hullOffsets, nc) ? 1u : 0u;
+    }
+    flushCounters(nc, cnt);
+}
+
+// compacts the overlapping pairs into non_collision_interaction records (collision_narrow.h:9-14) and applies the localized force
+// fields (physics.cpp:960-967). Two force fields on one body commute; three or more are summed in an unspecified order.
+__global__ void __launch_bounds__(kThreads) npInteractionKernel(const uint2* __restrict__ sorted, const float4* __restrict__ wCol, const uint32_t* __restrict__ flags,
+    const uint32_t* __restrict__ slots, uint4* __restrict__ interactions, uint32_t maxInteractions, const float4* __restrict__ forceFields, uint32_t numForceFields,
+    float4* __restrict__ bForce, uint32_t numBodies, DeviceCounts* cnt)
+{
+    const uint32_t q0 = cnt->keyStart[kBucketOverlap], n = cnt->numOverlapPairs;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { const uint32_t t = slots[n]; cnt->numInteractions = min(t, maxInteractions); if (t > maxInteractions) cnt->overflowPairs = 1; }
+    for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads)
+    {
+        if (!flags[i]) continue;
+        const uint2 pr = sorted[q0 + i];
+        const float4 a3 = wCol[4 * pr.x + 3], b3 = wCol[4 * pr.y + 3];
+        const uint32_t oa = (__float_as_uint(a3.x) >> 8) & 0xFFu, ob = (__float_as_uint(b3.x) >> 8) & 0xFFu;
+        uint32_t rb, other, otherType;
+        if (oa == B200PHYS_OBJ_RIGID_BODY) { rb = __float_as_uint(a3.y); other = __float_as_uint(b3.y); otherType = ob; }
+        else { rb = __float_as_uint(b3.y); other = __float_as_uint(a3.y); otherType = oa; }
+        const uint32_t s = slots[i];
+        if (s < maxInteractions) interactions[s] = make_uint4(rb, other, otherType, 0u);
+        if (otherType == B200PHYS_OBJ_FORCE_FIELD && other < numForceFields && rb < numBodies)
+        {
+            const float4 f = forceFields[other];
+            atomicAdd(&bForce[rb].x, f.x); atomicAdd(&bForce[rb].y, f.y); atomicAdd(&bForce[rb].z, f.z);
+        }
+    }
+}
+
 // pruned / overlap-only slots produce no manifold
 __global__ void __launch_bounds__(kThreads) npClearTailKernel(unsigned long long* __restrict__ manScan, const DeviceCounts* __restrict__ cnt)
 {
@@ -267,6 +336,17 @@ void launchNarrowphase(Context* c)
     npClearTailKernel<<<G, kThreads, 0, c->stream>>>(c->manScan, cnt);
     c->launches += 5;
     scanExclusiveU64(c, c->manScan, c->manScanOut, &cnt->numPairs, c->maxPairs, nullptr);
+    // rigid body vs trigger / force field: boolean overlap tests, compaction, force-field push (physics.cpp:1255, before the force integration)
+    if (c->numNonCollisionColliders)
+    {
+        uint32_t* ovFlags = c->pairDst; uint32_t* ovSlots = (uint32_t*)c->pairsTyped;   // both free between the bucket sort and the solver
+        npOverlapKernel<<<gridFor(c, 4), 128, 0, c->stream>>>(c->pairsSorted, c->wCol, c->hullVerts, c->hullOffsets, ovFlags, cnt);
+        c->launches++;
+        scanExclusiveU32(c, ovFlags, ovSlots, &cnt->numOverlapPairs, c->maxPairs, nullptr);
+        npInteractionKernel<<<G, kThreads, 0, c->stream>>>(c->pairsSorted, c->wCol, ovFlags, ovSlots, c->interactions, c->maxInteractions, c->forceFields, c->numForceFields,
+                                                           c->bForce, c->numBodies, cnt);
+        c->launches++;
+    }
     npTotalsKernel<<<1, 32, 0, c->stream>>>(c->manScanOut, c->maxManifolds, c->maxContacts, cnt);
     npCompactKernel<<<G, kThreads, 0, c->stream>>>(c->pairsSorted, c->wCol, c->manTmp, c->manScan, c->manScanOut, c->maxPairs, c->maxManifolds, c->maxContacts,
                                                    c->collisions, c->manifolds, c->contacts, c->contactBodies, cnt);

@@ -893,4 +893,81 @@ B200_D bool obbObb(const ObbS& a, const ObbS& b, Man& m)
     return true;
 }
 
+// --------------------------------------------------------------------------- boolean overlap tests (event layer)
+// bounding_volumes.h:301-363, bounding_volumes.cpp:704-733,742-835,1079-1208,1237-1244: what overlapCheck
+// (collision_narrow.cpp:1593-1689) dispatches to for rigid body vs trigger / force field pairs.
+B200_D bool sphereVsSphereB(const SphereS& a, const SphereS& b) { const f3 d = a.c - b.c; const float rs = a.r + b.r; return dot(d, d) <= rs * rs; }
+B200_D bool sphereVsCapsuleB(const SphereS& s, const CapS& c) { SphereS o; o.c = closestPointSegment(s.c, c.a, c.b); o.r = c.r; return sphereVsSphereB(s, o); }
+B200_D bool sphereVsCylinderB(const SphereS& s, const CapS& c)
+{
+    const f3 ab = c.b - c.a;
+    const float t = dot(s.c - c.a, ab) / sqLen(ab);
+    if (t >= 0.f && t <= 1.f) { SphereS o; o.c = lerp(c.a, c.b, t); o.r = c.r; return sphereVsSphereB(s, o); }
+    const f3 p = (t <= 0.f) ? c.a : c.b;
+    const f3 up = (t <= 0.f) ? -ab : ab;
+    const f3 proj = normalize(cross(cross(up, s.c - p), up));
+    const f3 endA = p + proj * c.r, endB = p - proj * c.r;
+    const f3 closest = closestPointSegment(s.c, endA, endB);
+    return sqLen(closest - s.c) <= s.r;          // sic: radius, not radius squared (bounding_volumes.cpp:723)
+}
+B200_D bool sphereVsBoxB(const SphereS& s, const BoxS& a) { const f3 n = closestPointBox(s.c, a) - s.c; return sqLen(n) <= s.r * s.r; }
+B200_D BoxS boxOfObb(const ObbS& o) { BoxS b; b.mn = o.c - o.r; b.mx = o.c + o.r; return b; }
+B200_D bool sphereVsObbB(const SphereS& s, const ObbS& o) { SphereS s_; s_.c = conjugate(o.q) * (s.c - o.c) + o.c; s_.r = s.r; return sphereVsBoxB(s_, boxOfObb(o)); }
+B200_D bool capsuleVsCapsuleB(const CapS& a, const CapS& b)
+{
+    f3 c1, c2; closestSegmentSegment(a.a, a.b, b.a, b.b, c1, c2);
+    SphereS x, y; x.c = c1; x.r = a.r; y.c = c2; y.r = b.r; return sphereVsSphereB(x, y);
+}
+B200_D bool capsuleVsCylinderB(const CapS& a, const CapS& b)
+{
+    f3 c1, c2; closestSegmentSegment(a.a, a.b, b.a, b.b, c1, c2);
+    SphereS x; x.c = c1; x.r = a.r; return sphereVsCylinderB(x, b);
+}
+B200_D bool gjkTest(const SupportD& A, const SupportD& B, NarrowCounters& nc) { SimplexD s; return gjk(A, B, s, nc); }   // gjkIntersectionTest
+B200_D CapS intoObbFrame(const CapS& c, const ObbS& o) { CapS r; r.a = conjugate(o.q) * (c.a - o.c) + o.c; r.b = conjugate(o.q) * (c.b - o.c) + o.c; r.r = c.r; return r; }
+B200_D bool boxVsBoxB(const BoxS& a, const BoxS& b)
+{
+    if (a.mx.x < b.mn.x || a.mn.x > b.mx.x) return false;
+    if (a.mx.y < b.mn.y || a.mn.y > b.mx.y) return false;
+    if (a.mx.z < b.mn.z || a.mn.z > b.mx.z) return false;
+    return true;
+}
+// bounding_volumes.cpp:1079-1199 (15-axis SAT, early out; no contact data)
+B200_D bool obbVsObbB(const ObbS& a, const ObbS& b)
+{
+    const f3 ax[3] = { a.q * mk3(1.f, 0.f, 0.f), a.q * mk3(0.f, 1.f, 0.f), a.q * mk3(0.f, 0.f, 1.f) };
+    const f3 bx[3] = { b.q * mk3(1.f, 0.f, 0.f), b.q * mk3(0.f, 1.f, 0.f), b.q * mk3(0.f, 0.f, 1.f) };
+    float r[3][3], absR[3][3];                     // r[i][j] = m_ij = dot(axesA[i], axesB[j])
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) { r[i][j] = dot(ax[i], bx[j]); absR[i][j] = fabsf(r[i][j]) + B200_EPS; }
+    const f3 t = conjugate(a.q) * (b.c - a.c);
+    const float ta[3] = { t.x, t.y, t.z }, ar[3] = { a.r.x, a.r.y, a.r.z }, br[3] = { b.r.x, b.r.y, b.r.z };
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+    {   // a's faces: row i of absR
+        const float ra = ar[i], rb = dot(mk3(absR[i][0], absR[i][1], absR[i][2]), b.r);
+        if (ra + rb - fabsf(ta[i]) < 0.f) return false;
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+    {   // b's faces: column i
+        const float ra = dot(mk3(absR[0][i], absR[1][i], absR[2][i]), a.r), rb = br[i];
+        const float d = dot(mk3(r[0][i], r[1][i], r[2][i]), t);
+        if (ra + rb - fabsf(d) < 0.f) return false;
+    }
+    float ra, rb;
+    ra = a.r.y * absR[2][0] + a.r.z * absR[1][0]; rb = b.r.y * absR[0][2] + b.r.z * absR[0][1]; if (ra + rb - fabsf(t.z * r[1][0] - t.y * r[2][0]) < 0.f) return false;
+    ra = a.r.y * absR[2][1] + a.r.z * absR[1][1]; rb = b.r.x * absR[0][2] + b.r.z * absR[0][0]; if (ra + rb - fabsf(t.z * r[1][1] - t.y * r[2][1]) < 0.f) return false;
+    ra = a.r.y * absR[2][2] + a.r.z * absR[1][2]; rb = b.r.x * absR[0][1] + b.r.y * absR[0][0]; if (ra + rb - fabsf(t.z * r[1][2] - t.y * r[2][2]) < 0.f) return false;
+    ra = a.r.x * absR[2][0] + a.r.z * absR[0][0]; rb = b.r.y * absR[1][2] + b.r.z * absR[1][1]; if (ra + rb - fabsf(t.x * r[2][0] - t.z * r[0][0]) < 0.f) return false;
+    ra = a.r.x * absR[2][1] + a.r.z * absR[0][1]; rb = b.r.x * absR[1][2] + b.r.z * absR[1][0]; if (ra + rb - fabsf(t.x * r[2][1] - t.z * r[0][1]) < 0.f) return false;
+    ra = a.r.x * absR[2][2] + a.r.z * absR[0][2]; rb = b.r.x * absR[1][1] + b.r.y * absR[1][0]; if (ra + rb - fabsf(t.x * r[2][2] - t.z * r[0][2]) < 0.f) return false;
+    ra = a.r.x * absR[1][0] + a.r.y * absR[0][0]; rb = b.r.y * absR[2][2] + b.r.z * absR[2][1]; if (ra + rb - fabsf(t.y * r[0][0] - t.x * r[1][0]) < 0.f) return false;
+    ra = a.r.x * absR[1][1] + a.r.y * absR[0][1]; rb = b.r.x * absR[2][2] + b.r.z * absR[2][0]; if (ra + rb - fabsf(t.y * r[0][1] - t.x * r[1][1]) < 0.f) return false;
+    ra = a.r.x * absR[1][2] + a.r.y * absR[0][2]; rb = b.r.x * absR[2][1] + b.r.y * absR[2][0]; if (ra + rb - fabsf(t.y * r[0][2] - t.x * r[1][2]) < 0.f) return false;
+    return true;
+}
+
 } // namespace b200

@@ -174,3 +174,75 @@ def sphere_pile_slab(nx_total, ny, nz, ix0, ix1, spacing=0.96, jitter=0.01, seed
     static_box(colliders, n + 4, (0, h * 0.5, (ez + 2.0)), (ex + 4.0, h * 0.5 + 2.0, 2.0), 0)
     x_lo = float(F(ix0) * F(spacing) - hx) - 0.5 * spacing; x_hi = float(F(ix1 - 1) * F(spacing) - hx) + 0.5 * spacing
     return {"bodies": bodies, "colliders": colliders, "transforms": transforms, "slab": (x_lo, x_hi), "name": "sphere_pile_slab_%d_%d_of_%d" % (ix0, ix1, nx_total)}
+
+
+def event_zoo(per_type=6, seed=99):
+    """Event-layer test scene: dynamic bodies with each of the six collider types fall (and are blown sideways) through a stack of
+    six trigger volumes and six localized force fields, one per collider type, so that every ordered type pair of the boolean
+    overlap tests (collision_narrow.cpp:1593-1689) occurs with a rigid body on one side. No static geometry: nothing collides
+    except bodies with each other. Returns the scene plus `force_fields` (one world-space force per field) and `global_force`."""
+    rng = np.random.default_rng(seed)
+    # one shared hull geometry: an octahedron of radius 0.45
+    hull = np.array([[0.45, 0, 0], [-0.45, 0, 0], [0, 0.45, 0], [0, -0.45, 0], [0, 0, 0.45], [0, 0, -0.45]], dtype=np.float32)
+    tris = np.array([0, 2, 4, 2, 1, 4, 1, 3, 4, 3, 0, 4, 2, 0, 5, 1, 2, 5, 3, 1, 5, 0, 3, 5], dtype=np.uint32)
+    types = [abi.SPHERE, abi.CAPSULE, abi.CYLINDER, abi.AABB, abi.OBB, abi.HULL]
+    n = per_type * len(types)
+    bodies = new_bodies(n)
+    set_sphere_bodies(bodies, np.arange(n), F(0.4), F(1.0))
+    volumes = 12
+    colliders = np.zeros(n + volumes, dtype=abi.collider_dtype)
+    colliders["restitution"] = 0.1; colliders["friction"] = 0.5; colliders["density"] = 1.0
+    colliders["parentTransform"] = abi.NO_TRANSFORM
+
+    def set_shape(i, t, size):
+        s = colliders["shape"][i]; s[:] = 0
+        if t == abi.SPHERE:
+            s[3] = size
+        elif t in (abi.CAPSULE, abi.CYLINDER):
+            s[0:3] = (0, -0.5 * size, 0); s[3:6] = (0, 0.5 * size, 0); s[6] = 0.6 * size
+        elif t == abi.AABB:
+            s[0:3] = -size; s[3:6] = size
+        elif t == abi.OBB:
+            s[0:4] = (0, 0, 0, 1); s[7:10] = size
+        else:
+            s[0:4] = (0, 0, 0, 1); s[7:8].view(np.uint32)[0] = 0
+        colliders["type"][i] = t
+
+    for i in range(n):
+        t = types[i // per_type]
+        set_shape(i, t, 0.4)
+        colliders["objectType"][i] = abi.OBJ_RIGID_BODY; colliders["objectIndex"][i] = i
+        k = i % per_type
+        bodies["position"][i] = (F(1.7) * (i // per_type) + rng.uniform(-0.2, 0.2), F(9.0) + F(1.1) * k, rng.uniform(-0.6, 0.6))
+        ax = rng.normal(size=3); ax /= np.linalg.norm(ax); ang = rng.uniform(0, np.pi)
+        if t != abi.AABB:            # an unrotated body keeps its AABB collider (physics.cpp:722-734)
+            bodies["rotation"][i] = np.concatenate([ax * np.sin(ang / 2), [np.cos(ang / 2)]]).astype(np.float32)
+        bodies["linearVelocity"][i] = (0, -4.0, 0)
+        bodies["angularDamping"][i] = 0.0 if t == abi.AABB else 0.4
+    transforms = np.zeros(volumes, dtype=abi.transform_dtype); transforms["rotation"][:, 3] = 1.0
+    for v in range(volumes):
+        i = n + v; t = types[v % 6]
+        set_shape(i, t, 0.9)
+        is_trigger = v < 6
+        colliders["objectType"][i] = abi.OBJ_TRIGGER if is_trigger else abi.OBJ_FORCE_FIELD
+        colliders["objectIndex"][i] = v % 6
+        colliders["parentTransform"][i] = v
+        # a long flat volume under all the columns would only exercise a few pairs: give every volume its own height and let it span x
+        transforms["position"][v] = (F(1.7) * 2.5, F(6.5) - F(1.0) * (v % 6) - (0.0 if is_trigger else 0.5), 0)
+        if t in (abi.SPHERE,):
+            colliders["shape"][i][3] = 5.2
+        elif t in (abi.CAPSULE, abi.CYLINDER):
+            colliders["shape"][i][0:3] = (-4.6, 0, 0); colliders["shape"][i][3:6] = (4.6, 0, 0); colliders["shape"][i][6] = 0.8
+        elif t == abi.AABB:
+            colliders["shape"][i][0:3] = (-5.0, -0.4, -1.2); colliders["shape"][i][3:6] = (5.0, 0.4, 1.2)
+        elif t == abi.OBB:
+            colliders["shape"][i][7:10] = (5.0, 0.4, 1.2)
+            q = np.array([0, 0, np.sin(0.05), np.cos(0.05)], dtype=np.float32); transforms["rotation"][v] = q
+        else:
+            transforms["position"][v][0] = F(1.7) * (v % 6)      # the small hull sits under one column only
+    force_fields = np.zeros((6, 3), dtype=np.float32)
+    for k in range(6):
+        force_fields[k] = (3.0 + k, 0.5 * k, -2.0 + k)
+    return {"bodies": bodies, "colliders": colliders, "transforms": transforms, "joints": {}, "name": "event_zoo",
+            "hull_vertices": hull, "hull_offsets": np.array([0, len(hull)], dtype=np.uint32), "hull_triangles": [tris],
+            "force_fields": force_fields, "global_force": np.array([0.0, 0.0, 0.75], dtype=np.float32)}

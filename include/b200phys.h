@@ -240,6 +240,17 @@ int b200phys_synchronize(b200phys_context* ctx);
 
 /* results (device -> host) --------------------------------------------------------------------------------------- */
 int b200phys_download_bodies(b200phys_context* ctx, b200phys_body_state* out, uint32_t count);
+/* Force fields and triggers (reference: handleNonCollisionInteractions, physics.cpp:952-1035; getForceFieldStates :759-787).
+ * A collider with objectType FORCE_FIELD / TRIGGER carries the index of its force field / trigger in objectIndex. Every step the
+ * rigid-body colliders overlapping such a collider (boolean shape tests, collision_narrow.cpp:1593-1689) are collected on the device:
+ * a localized force field adds its force to the accumulator of each overlapping body (once per overlapping collider, like the
+ * reference) before the forces are integrated; the global force is added to every body. Trigger overlaps are de-duplicated per
+ * (trigger, rigid body) and diffed against the previous call: download_trigger_events must be called once after every step. */
+typedef struct b200phys_trigger_event { uint32_t triggerIndex, rigidBodyIndex; } b200phys_trigger_event;
+int b200phys_upload_force_fields(b200phys_context* ctx, const float* forces3, uint32_t count);   /* world-space force per localized field */
+int b200phys_set_global_force_field(b200phys_context* ctx, const float force3[3]);
+int b200phys_download_trigger_events(b200phys_context* ctx, b200phys_trigger_event* enterOut, uint32_t enterCapacity, uint32_t* numEnter,
+                                     b200phys_trigger_event* leaveOut, uint32_t leaveCapacity, uint32_t* numLeave);
 /* Collision begin / end events (reference: handleCollisionCallbacks, physics.cpp:1037-1178). Off by default; enabling allocates the
  * per-manifold key lists. After every step: the collider pairs that collide now but did not in the previous step (begin, with the
  * averaged contact) and those that stopped colliding (end), each list ordered by (type bucket, lower collider, higher collider).

@@ -848,11 +848,102 @@ bool collide(const WCol& A, const WCol& B, Manifold& m, NarrowStats& st)
     }
 }
 
-bool overlapOnly(const WCol& a, const WCol& b, NarrowStats& st)
+// --------------------------------------------------------------------------- boolean overlap tests (event layer)
+// bounding_volumes.h:301-363, bounding_volumes.cpp:704-733,742-835,1079-1208,1237-1244: what overlapCheck
+// (collision_narrow.cpp:1593-1689) dispatches to for rigid body vs trigger / force field pairs.
+static bool sphereVsSphere(const Sphere& a, const Sphere& b) { V3 d = a.c - b.c; float rs = a.r + b.r; return dot(d, d) <= rs * rs; }
+static bool sphereVsCapsule(const Sphere& s, const Capsule& c) { Sphere o = { closestPointSegment(s.c, c.a, c.b), c.r }; return sphereVsSphere(s, o); }
+static bool sphereVsCylinder(const Sphere& s, const Capsule& c)
 {
-    // Event-layer (trigger / force-field) overlap tests are a "next" row; until then the oracle answers with
-    // the contact test, which agrees with the reference's boolean tests except for quirk B1 (sphereVsCylinder).
-    Manifold m; return collide(a, b, m, st);
+    V3 ab = c.b - c.a;
+    float t = dot(s.c - c.a, ab) / sqLen(ab);
+    if (t >= 0.f && t <= 1.f) { Sphere o = { lerp(c.a, c.b, t), c.r }; return sphereVsSphere(s, o); }
+    V3 p = (t <= 0.f) ? c.a : c.b;
+    V3 up = (t <= 0.f) ? -ab : ab;
+    V3 proj = normalize(cross(cross(up, s.c - p), up));
+    V3 endA = p + proj * c.r, endB = p - proj * c.r;
+    V3 closest = closestPointSegment(s.c, endA, endB);
+    return sqLen(closest - s.c) <= s.r;          // sic: radius, not radius squared (bounding_volumes.cpp:723)
+}
+static bool sphereVsAABB(const Sphere& s, const Box& a) { V3 n = closestPointAABB(s.c, a) - s.c; return sqLen(n) <= s.r * s.r; }
+static bool sphereVsOBB(const Sphere& s, const Obb& o)
+{
+    Sphere s_ = { conjugate(o.q) * (s.c - o.c) + o.c, s.r };
+    return sphereVsAABB(s_, boxFromCenterRadius(o.c, o.r));
+}
+static bool capsuleVsCapsule(const Capsule& a, const Capsule& b)
+{
+    V3 c1, c2; closestPointSegmentSegment(a.a, a.b, b.a, b.b, c1, c2);
+    return sphereVsSphere(Sphere{ c1, a.r }, Sphere{ c2, b.r });
+}
+static bool capsuleVsCylinder(const Capsule& a, const Capsule& b)
+{
+    V3 c1, c2; closestPointSegmentSegment(a.a, a.b, b.a, b.b, c1, c2);
+    return sphereVsCylinder(Sphere{ c1, a.r }, b);
+}
+static bool gjkTest(const Support& A, const Support& B, NarrowStats& st) { Simplex s; return gjk(A, B, s, st); }   // gjkIntersectionTest
+static Capsule intoObbFrame(const Capsule& c, const Obb& o) { Capsule r = { conjugate(o.q) * (c.a - o.c) + o.c, conjugate(o.q) * (c.b - o.c) + o.c, c.r }; return r; }
+// bounding_volumes.cpp:1079-1199 (15-axis SAT, early out; no contact data)
+static bool obbVsOBB(const Obb& a, const Obb& b)
+{
+    V3 ax[3] = { a.q * v3(1.f, 0.f, 0.f), a.q * v3(0.f, 1.f, 0.f), a.q * v3(0.f, 0.f, 1.f) };
+    V3 bx[3] = { b.q * v3(1.f, 0.f, 0.f), b.q * v3(0.f, 1.f, 0.f), b.q * v3(0.f, 0.f, 1.f) };
+    float r[3][3], absR[3][3];                     // r[i][j] = m_ij = dot(axesA[i], axesB[j])
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { r[i][j] = dot(ax[i], bx[j]); absR[i][j] = fabsf(r[i][j]) + kEps; }
+    V3 t = conjugate(a.q) * (b.c - a.c);
+    const float ta[3] = { t.x, t.y, t.z }, ar[3] = { a.r.x, a.r.y, a.r.z }, br[3] = { b.r.x, b.r.y, b.r.z };
+    for (int i = 0; i < 3; ++i)
+    {   // a's faces: row i of absR
+        float ra = ar[i], rb = dot(v3(absR[i][0], absR[i][1], absR[i][2]), b.r);
+        if (ra + rb - fabsf(ta[i]) < 0.f) return false;
+    }
+    for (int i = 0; i < 3; ++i)
+    {   // b's faces: column i
+        float ra = dot(v3(absR[0][i], absR[1][i], absR[2][i]), a.r), rb = br[i];
+        float d = dot(v3(r[0][i], r[1][i], r[2][i]), t);
+        if (ra + rb - fabsf(d) < 0.f) return false;
+    }
+    float ra, rb;
+    ra = a.r.y * absR[2][0] + a.r.z * absR[1][0]; rb = b.r.y * absR[0][2] + b.r.z * absR[0][1]; if (ra + rb - fabsf(t.z * r[1][0] - t.y * r[2][0]) < 0.f) return false;
+    ra = a.r.y * absR[2][1] + a.r.z * absR[1][1]; rb = b.r.x * absR[0][2] + b.r.z * absR[0][0]; if (ra + rb - fabsf(t.z * r[1][1] - t.y * r[2][1]) < 0.f) return false;
+    ra = a.r.y * absR[2][2] + a.r.z * absR[1][2]; rb = b.r.x * absR[0][1] + b.r.y * absR[0][0]; if (ra + rb - fabsf(t.z * r[1][2] - t.y * r[2][2]) < 0.f) return false;
+    ra = a.r.x * absR[2][0] + a.r.z * absR[0][0]; rb = b.r.y * absR[1][2] + b.r.z * absR[1][1]; if (ra + rb - fabsf(t.x * r[2][0] - t.z * r[0][0]) < 0.f) return false;
+    ra = a.r.x * absR[2][1] + a.r.z * absR[0][1]; rb = b.r.x * absR[1][2] + b.r.z * absR[1][0]; if (ra + rb - fabsf(t.x * r[2][1] - t.z * r[0][1]) < 0.f) return false;
+    ra = a.r.x * absR[2][2] + a.r.z * absR[0][2]; rb = b.r.x * absR[1][1] + b.r.y * absR[1][0]; if (ra + rb - fabsf(t.x * r[2][2] - t.z * r[0][2]) < 0.f) return false;
+    ra = a.r.x * absR[1][0] + a.r.y * absR[0][0]; rb = b.r.y * absR[2][2] + b.r.z * absR[2][1]; if (ra + rb - fabsf(t.y * r[0][0] - t.x * r[1][0]) < 0.f) return false;
+    ra = a.r.x * absR[1][1] + a.r.y * absR[0][1]; rb = b.r.x * absR[2][2] + b.r.z * absR[2][0]; if (ra + rb - fabsf(t.y * r[0][1] - t.x * r[1][1]) < 0.f) return false;
+    ra = a.r.x * absR[1][2] + a.r.y * absR[0][2]; rb = b.r.x * absR[2][1] + b.r.y * absR[2][0]; if (ra + rb - fabsf(t.y * r[0][2] - t.x * r[1][2]) < 0.f) return false;
+    return true;
+}
+
+// overlapCheck (collision_narrow.cpp:1593-1689): A.type <= B.type
+bool overlapOnly(const WCol& A, const WCol& B, NarrowStats& st)
+{
+    switch (A.type * 6 + B.type)
+    {
+    case T_SPHERE * 6 + T_SPHERE:     return sphereVsSphere(A.sphere, B.sphere);
+    case T_SPHERE * 6 + T_CAPSULE:    return sphereVsCapsule(A.sphere, B.cap);
+    case T_SPHERE * 6 + T_CYLINDER:   return sphereVsCylinder(A.sphere, B.cap);
+    case T_SPHERE * 6 + T_AABB:       return sphereVsAABB(A.sphere, B.box);
+    case T_SPHERE * 6 + T_OBB:        return sphereVsOBB(A.sphere, B.obb);
+    case T_SPHERE * 6 + T_HULL:       return gjkTest(supSphere(A.sphere), supHull(B.hull), st);
+    case T_CAPSULE * 6 + T_CAPSULE:   return capsuleVsCapsule(A.cap, B.cap);
+    case T_CAPSULE * 6 + T_CYLINDER:  return capsuleVsCylinder(A.cap, B.cap);
+    case T_CAPSULE * 6 + T_AABB:      return gjkTest(supCapsule(A.cap), supBox(B.box), st);
+    case T_CAPSULE * 6 + T_OBB:       return gjkTest(supCapsule(intoObbFrame(A.cap, B.obb)), supBox(boxFromCenterRadius(B.obb.c, B.obb.r)), st);
+    case T_CAPSULE * 6 + T_HULL:      return gjkTest(supCapsule(A.cap), supHull(B.hull), st);
+    case T_CYLINDER * 6 + T_CYLINDER: return gjkTest(supCylinder(A.cap), supCylinder(B.cap), st);
+    case T_CYLINDER * 6 + T_AABB:     return gjkTest(supCylinder(A.cap), supBox(B.box), st);
+    case T_CYLINDER * 6 + T_OBB:      return gjkTest(supCylinder(intoObbFrame(A.cap, B.obb)), supBox(boxFromCenterRadius(B.obb.c, B.obb.r)), st);
+    case T_CYLINDER * 6 + T_HULL:     return gjkTest(supCylinder(A.cap), supHull(B.hull), st);
+    case T_AABB * 6 + T_AABB:         return aabbVsAABB(A.box, B.box);
+    case T_AABB * 6 + T_OBB:          { Obb o; o.q = qIdentity(); o.c = boxCenter(A.box); o.r = boxRadius(A.box); return obbVsOBB(o, B.obb); }
+    case T_AABB * 6 + T_HULL:         return gjkTest(supBox(A.box), supHull(B.hull), st);
+    case T_OBB * 6 + T_OBB:           return obbVsOBB(A.obb, B.obb);
+    case T_OBB * 6 + T_HULL:          return gjkTest(supObb(A.obb), supHull(B.hull), st);
+    case T_HULL * 6 + T_HULL:         return gjkTest(supHull(A.hull), supHull(B.hull), st);
+    default: ++st.asserts; return false;
+    }
 }
 
 } // namespace orc

@@ -236,8 +236,54 @@ void Oracle::narrowphase()
             contactBodies.push_back({ A.objIndex, B.objIndex });
         }
     }
-    // trigger / force-field overlaps (collision_narrow.cpp:2573-2593): counted only (event layer is a "next" row)
-    for (const Pair& p : intersectionPairs) if (overlapOnly(wcol[p.a], wcol[p.b], nstats)) ++numNonCollisionInteractions;
+    // trigger / force-field overlaps (collision_narrow.cpp:2573-2593, overlapCheck :1593-1612). The reference walks them type
+    // bucket by type bucket; here (and on the device) they stay in pair order: only the floating-point summation order of three
+    // or more force fields acting on one body could tell the difference.
+    interactions.clear();
+    for (const Pair& p : intersectionPairs)
+    {
+        const WCol& A = wcol[p.a]; const WCol& B = wcol[p.b];
+        if (!overlapOnly(A, B, nstats)) continue;
+        Interaction it;
+        if (A.objType == O_RIGID) { it.rigidBodyIndex = A.objIndex; it.otherIndex = B.objIndex; it.otherType = B.objType; }
+        else { it.rigidBodyIndex = B.objIndex; it.otherIndex = A.objIndex; it.otherType = A.objType; }
+        interactions.push_back(it);
+    }
+    numNonCollisionInteractions = (uint32_t)interactions.size();
+}
+
+// handleNonCollisionInteractions (physics.cpp:952-1035): localized force fields push the overlapping bodies, trigger overlaps
+// are sorted, de-duplicated (several colliders of one body may report the same trigger) and merged against last frame's list.
+void Oracle::nonCollisionInteractions()
+{
+    std::vector<Pair> overlaps;
+    for (const Interaction& it : interactions)
+    {
+        if (it.otherType == B200PHYS_OBJ_FORCE_FIELD)
+        {
+            if (it.otherIndex < forceFields.size() && it.rigidBodyIndex < bodies.size())
+            {
+                float* F = bodies[it.rigidBodyIndex].forceAccumulator; const V3 f = forceFields[it.otherIndex];
+                F[0] += f.x; F[1] += f.y; F[2] += f.z;
+            }
+        }
+        else if (it.otherType == B200PHYS_OBJ_TRIGGER) overlaps.push_back(Pair{ it.otherIndex, it.rigidBodyIndex });
+    }
+    auto less = [](const Pair& x, const Pair& y) { return x.a != y.a ? x.a < y.a : x.b < y.b; };
+    auto same = [](const Pair& x, const Pair& y) { return x.a == y.a && x.b == y.b; };
+    std::sort(overlaps.begin(), overlaps.end(), less);
+    overlaps.erase(std::unique(overlaps.begin(), overlaps.end(), same), overlaps.end());
+    triggerEnter.clear(); triggerLeave.clear();
+    size_t p = 0, t = 0;
+    while (p < prevFrameTriggerOverlaps.size() && t < overlaps.size())
+    {
+        if (same(prevFrameTriggerOverlaps[p], overlaps[t])) { ++p; ++t; continue; }
+        if (less(prevFrameTriggerOverlaps[p], overlaps[t])) triggerLeave.push_back(prevFrameTriggerOverlaps[p++]);
+        else triggerEnter.push_back(overlaps[t++]);
+    }
+    while (p < prevFrameTriggerOverlaps.size()) triggerLeave.push_back(prevFrameTriggerOverlaps[p++]);
+    while (t < overlaps.size()) triggerEnter.push_back(overlaps[t++]);
+    prevFrameTriggerOverlaps = std::move(overlaps);
 }
 
 // ------------------------------------------------------------------------------------------------- integration
@@ -255,7 +301,7 @@ void Oracle::integrateForces(float dt)
         M3 I; memcpy(I.m, b.invInertia, sizeof(I.m));
         G.invInertia = R * I * transpose(R);
         G.invMass = b.invMass;
-        V3 F = ld3(b.forceAccumulator), T = ld3(b.torqueAccumulator);
+        V3 F = ld3(b.forceAccumulator) + globalForceField, T = ld3(b.torqueAccumulator);   // physics.cpp:1273
         if (b.invMass > 0.f) { F.y += (-9.81f / b.invMass * b.gravityFactor); }
         V3 linAcc = F * b.invMass;
         V3 angAcc = G.invInertia * T;
@@ -415,6 +461,7 @@ void Oracle::step(float dt, uint32_t iterations, const uint32_t* contactOrder, c
     worldColliders();                       double t1 = nowMs();
     broadphaseSAP();                        double t2 = nowMs();
     narrowphase();                          double t3 = nowMs();
+    nonCollisionInteractions();             // physics.cpp:1255
     integrateForces(dt);                    double t4 = nowMs();
     collisionEvents();                      // physics.cpp:1284 (after the force integration, before the solver)
     initJoints(dt);

@@ -61,6 +61,15 @@ struct Oracle
     std::vector<Pair> endEvents;
     void collisionEvents();
 
+    // non-collision interactions (collision_narrow.h:9-14): rigid body vs force field / trigger overlaps of this step
+    struct Interaction { uint32_t rigidBodyIndex, otherIndex; int otherType; };
+    std::vector<Interaction> interactions;
+    std::vector<V3> forceFields;                        // force_field_global_state per localized force field (physics.cpp:47-50,759-787)
+    V3 globalForceField = v3(0.f);                      // sum of the force fields without a collider
+    std::vector<Pair> prevFrameTriggerOverlaps;         // (trigger, rigid body), sorted, unique (physics.cpp:946-950)
+    std::vector<Pair> triggerEnter, triggerLeave;
+    void nonCollisionInteractions();                    // handleNonCollisionInteractions, physics.cpp:952-1035
+
     int pairOrder = ORDER_CANONICAL;
     // timing of the last step by reference stage name (ms)
     double msWorld = 0, msBroad = 0, msNarrow = 0, msForces = 0, msInit = 0, msSolve = 0, msIntegrate = 0;

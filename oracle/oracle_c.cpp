@@ -135,6 +135,20 @@ void oracle_get_contacts(oracle_ctx* c, b200phys_contact* out, b200phys_body_pai
         if (bodies) bodies[i] = c->o.contactBodies[i];
     }
 }
+// localized force fields (one world-space force per force-field index) and the global one (physics.cpp:759-787)
+void oracle_set_force_fields(oracle_ctx* c, const float* forces3, uint32_t count, const float* global3)
+{
+    c->o.forceFields.clear();
+    for (uint32_t i = 0; i < count; ++i) c->o.forceFields.push_back(v3(forces3[3 * i], forces3[3 * i + 1], forces3[3 * i + 2]));
+    c->o.globalForceField = global3 ? v3(global3[0], global3[1], global3[2]) : v3(0.f);
+}
+uint32_t oracle_num_trigger_events(oracle_ctx* c, uint32_t* numLeave) { *numLeave = (uint32_t)c->o.triggerLeave.size(); return (uint32_t)c->o.triggerEnter.size(); }
+void oracle_get_trigger_events(oracle_ctx* c, uint32_t* enter2, uint32_t* leave2)
+{
+    for (size_t i = 0; i < c->o.triggerEnter.size(); ++i) { enter2[2 * i] = c->o.triggerEnter[i].a; enter2[2 * i + 1] = c->o.triggerEnter[i].b; }
+    for (size_t i = 0; i < c->o.triggerLeave.size(); ++i) { leave2[2 * i] = c->o.triggerLeave[i].a; leave2[2 * i + 1] = c->o.triggerLeave[i].b; }
+}
+uint32_t oracle_num_interactions(oracle_ctx* c) { return (uint32_t)c->o.interactions.size(); }
 // collision begin / end events of the last step: begin = 11 floats (a, b as uint32 bits, point, normal, relative velocity)
 uint32_t oracle_num_begin_events(oracle_ctx* c) { return (uint32_t)c->o.beginEvents.size(); }
 uint32_t oracle_num_end_events(oracle_ctx* c) { return (uint32_t)c->o.endEvents.size(); }

@@ -155,6 +155,22 @@ class Oracle:
         p = np.empty(n, dtype=abi.pair_dtype); k = np.empty(n, dtype=np.uint8)
         self.lib.oracle_get_collisions(self.ctx, _p(p), _p(k)); return p, k
 
+    def set_force_fields(self, forces, global_force=None):
+        f = np.ascontiguousarray(forces, dtype=np.float32).reshape(-1, 3)
+        g = np.zeros(3, dtype=np.float32) if global_force is None else np.ascontiguousarray(global_force, dtype=np.float32)
+        self.lib.oracle_set_force_fields(self.ctx, _p(f) if len(f) else None, C.c_uint32(len(f)), _p(g))
+
+    def trigger_events(self):
+        """(enter [n,2], leave [m,2]) as (triggerIndex, rigidBodyIndex) of the last step."""
+        self.lib.oracle_num_trigger_events.restype = C.c_uint32
+        nl = C.c_uint32(0); ne = self.lib.oracle_num_trigger_events(self.ctx, C.byref(nl))
+        e = np.zeros((ne, 2), dtype=np.uint32); l = np.zeros((nl.value, 2), dtype=np.uint32)
+        self.lib.oracle_get_trigger_events(self.ctx, _p(e), _p(l)); return e, l
+
+    def num_interactions(self):
+        self.lib.oracle_num_interactions.restype = C.c_uint32
+        return self.lib.oracle_num_interactions(self.ctx)
+
     def events(self):
         """Collision begin / end events of the last step: (begin pairs [n,2], begin payload [n,9] = point, normal, relative velocity, end pairs [m,2])."""
         self.lib.oracle_num_begin_events.restype = C.c_uint32; self.lib.oracle_num_end_events.restype = C.c_uint32

@@ -266,3 +266,19 @@ def test_oracle_collision_events_first_step_all_begin_then_none():
     orc.step(np.float32(1 / 120.0), 10)
     bp2, _, ep2 = orc.events()
     assert len(bp2) == 0 and len(ep2) == 0
+
+
+def test_oracle_trigger_and_force_field_scene_is_pinned():
+    """Regression pin of the event-zoo scene in the oracle: counts of trigger enter / leave events and overlapping interactions over
+    120 steps, and the sphereVsCylinder quirk (bounding_volumes.cpp:723 compares a squared distance with the radius)."""
+    import oracle_lib
+    sc = scenes.event_zoo()
+    orc = oracle_lib.Oracle(sc, canonical=True)
+    orc.set_force_fields(sc["force_fields"], sc["global_force"])
+    te = tl = inter = 0
+    for _ in range(120):
+        orc.step(np.float32(1 / 120.0), 10)
+        e, l = orc.trigger_events(); te += len(e); tl += len(l); inter += orc.num_interactions()
+        assert len(np.unique(e, axis=0)) == len(e)          # de-duplicated per (trigger, body)
+    assert (te, tl, inter) == (92, 51, 7046)
+    assert orc.narrow_stats()["asserts"] == 0
