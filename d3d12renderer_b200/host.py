@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200host.so")
 _lib = None
 
-CONFIG_SPHERES_ON_GROUND, CONFIG_SPHERE_BOX_DROP, CONFIG_MIXED_PILE, CONFIG_RAGDOLLS = 1, 2, 3, 4
+CONFIG_SPHERES_ON_GROUND, CONFIG_SPHERE_BOX_DROP, CONFIG_MIXED_PILE, CONFIG_RAGDOLLS, CONFIG_EVENT_SCENE = 1, 2, 3, 4, 5
 
 
 def load_library():
@@ -41,6 +41,7 @@ def load_library():
     lib.b200host_physics_step_with_events.argtypes = [vp, C.POINTER(C.c_float), C.c_float, u32, C.c_int, u32, C.c_int]
     lib.b200host_event_log_counts.argtypes = [C.POINTER(u32)]; lib.b200host_event_log_counts.restype = u32
     lib.b200host_event_log_get.argtypes = [vp, vp, vp]
+    lib.b200host_trigger_log.argtypes = [vp, u32, C.c_int]; lib.b200host_trigger_log.restype = u32
     lib.b200host_get_render_transforms.argtypes = [vp, vp]
     lib.b200host_get_stats.argtypes = [vp, C.POINTER(abi.Stats)]
     _lib = lib
@@ -122,6 +123,13 @@ class HostScene:
         be = np.zeros((nb, 2), dtype=np.uint32); pl = np.zeros((nb, 9), dtype=np.float32); ee = np.zeros((ne.value, 2), dtype=np.uint32)
         self.lib.b200host_event_log_get(_p(be), _p(pl), _p(ee))
         return t.value, be, pl, ee
+
+    def trigger_log(self, clear=True):
+        """(trigger entity, other entity, type 0 enter / 1 leave) triples logged by the config-5 trigger callback since the last clear."""
+        n = self.lib.b200host_trigger_log(None, 0, 0)
+        out = np.zeros((n, 3), dtype=np.uint32)
+        self.lib.b200host_trigger_log(_p(out), n, 1 if clear else 0)
+        return out
 
     def render_transforms(self):
         out = np.zeros((self.lib.b200host_num_bodies(self.ptr), 7), dtype=np.float32)

@@ -67,6 +67,15 @@ void b200host_scene_destroy(void* s) { delete (game_scene*)s; }
 // config 2: nx*ny*nz spheres on a jittered lattice inside 5 static boxes (spacing in 1/1000 via `param`)       [config 2]
 // config 3: nx*ny*nz mixed primitives (sphere / capsule / OBB / hull round-robin), random orientations        [config 3]
 // config 4: nx*nz humanoid ragdolls (14 bodies, 17 colliders, 13 joints each) above the ground                [config 4]
+static std::vector<uint32_t> gTriggerLog;   // (trigger entity, other entity, type) triples appended by the config-5 trigger callback
+uint32_t b200host_trigger_log(uint32_t* out, uint32_t capacityTriples, int clear)
+{
+    const uint32_t n = (uint32_t)gTriggerLog.size() / 3;
+    if (out) memcpy(out, gTriggerLog.data(), 4 * (size_t)3 * (n < capacityTriples ? n : capacityTriples));
+    if (clear) gTriggerLog.clear();
+    return n;
+}
+
 int b200host_build_config(void* sp, int config, uint32_t nx, uint32_t ny, uint32_t nz, uint64_t seed, int mode, float spacing)
 {
     game_scene& s = *(game_scene*)sp;
@@ -81,6 +90,20 @@ int b200host_build_config(void* sp, int config, uint32_t nx, uint32_t ny, uint32
                 .addCollider(collider_component::asSphere({ mk3(0.f), 0.5f }, kDynamicMat)).addRigidBody(false, 1.f);
         }
         addGround(s, fmaxf(30.f, half + 2.f), fmaxf(30.f, halfz + 2.f));
+        return 0;
+    }
+    if (config == 5)
+    {   // event-layer scene: spheres dropping through a trigger slab and a localized wind box, plus a global force field
+        const float half = (nx - 1) * spacing * 0.5f, halfz = (nz - 1) * spacing * 0.5f;
+        for (uint32_t ix = 0; ix < nx; ++ix) for (uint32_t iz = 0; iz < nz; ++iz)
+            s.createEntity("Sphere").addTransform(mk3(ix * spacing - half, 3.f + rng.between(0.f, 2.f), iz * spacing - halfz))
+                .addCollider(collider_component::asSphere({ mk3(0.f), 0.5f }, kDynamicMat)).addRigidBody(false, 1.f);
+        addGround(s, fmaxf(30.f, half + 2.f), fmaxf(30.f, halfz + 2.f));
+        s.createEntity("Trigger").addTransform(mk3(0.f, 1.6f, 0.f)).addCollider(collider_component::asAABB(bounding_box::fromCenterRadius(mk3(0.f), mk3(half + 2.f, 0.3f, halfz + 2.f)), kStaticMat))
+            .addTrigger([](const trigger_event& e) { gTriggerLog.push_back(e.trigger); gTriggerLog.push_back(e.other); gTriggerLog.push_back((uint32_t)e.type); });
+        s.createEntity("Wind").addTransform(mk3(0.f, 2.6f, 0.f)).addCollider(collider_component::asAABB(bounding_box::fromCenterRadius(mk3(0.f), mk3(half + 2.f, 0.5f, halfz + 2.f)), kStaticMat))
+            .addForceField(mk3(5.f, 0.f, 0.f));
+        s.createEntity("GlobalWind").addForceField(mk3(0.f, 0.f, 1.f));
         return 0;
     }
     if (config == 2 || config == 3)

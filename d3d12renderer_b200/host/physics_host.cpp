@@ -171,6 +171,22 @@ scene_entity& scene_entity::addCollider(const collider_component& c)
     scene->collidersDirty = true;
     return *this;
 }
+scene_entity& scene_entity::addTrigger(std::function<void(const trigger_event&)> callback)
+{
+    game_scene::entity_data& d = scene->entities[handle];
+    if (d.trigger < 0) { scene->triggers.push_back(trigger_component{ callback }); scene->triggerEntity.push_back(handle); d.trigger = (int32_t)scene->triggers.size() - 1; }
+    else scene->triggers[d.trigger].callback = callback;
+    scene->collidersDirty = true;
+    return *this;
+}
+scene_entity& scene_entity::addForceField(vec3 force)
+{
+    game_scene::entity_data& d = scene->entities[handle];
+    if (d.forceField < 0) { scene->forceFields.push_back(force_field_component{ force }); scene->forceFieldEntity.push_back(handle); d.forceField = (int32_t)scene->forceFields.size() - 1; }
+    else scene->forceFields[d.forceField].force = force;
+    scene->collidersDirty = true;
+    return *this;
+}
 scene_entity& scene_entity::addRigidBody(bool kinematic, float gravityFactor, float linearDamping, float angularDamping)
 {   // scene.h:69-84
     game_scene::entity_data& d = scene->entities[handle];
@@ -234,8 +250,10 @@ void game_scene::gatherColliders(std::vector<b200phys_collider>& outC, std::vect
         const entity_data& parent = entities[c.parentEntity];
         if (parent.rigidBody >= 0) { o.objectType = B200PHYS_OBJ_RIGID_BODY; o.objectIndex = (uint32_t)parent.rigidBody; o.parentTransform = B200PHYS_NO_TRANSFORM; }
         else
-        {   // static collider (physics.cpp:667-671); pose = transform_component or identity (:645-647)
-            o.objectType = B200PHYS_OBJ_STATIC; o.objectIndex = 0;
+        {   // force field > trigger > static collider (physics.cpp:657-671); pose = transform_component or identity (:645-647)
+            if (parent.forceField >= 0) { o.objectType = B200PHYS_OBJ_FORCE_FIELD; o.objectIndex = (uint32_t)parent.forceField; }
+            else if (parent.trigger >= 0) { o.objectType = B200PHYS_OBJ_TRIGGER; o.objectIndex = (uint32_t)parent.trigger; }
+            else { o.objectType = B200PHYS_OBJ_STATIC; o.objectIndex = 0; }
             if (!parent.hasTransform) o.parentTransform = B200PHYS_NO_TRANSFORM;
             else
             {
@@ -496,6 +514,21 @@ static int physicsStepInternal(game_scene& scene, const physics_settings& settin
         }
         scene.jointsDirty = false;
     }
+    if (!scene.forceFields.empty())
+    {   // getForceFieldStates (physics.cpp:759-787): fields with a collider act locally, the others on every body
+        std::vector<float> local(3 * scene.forceFields.size(), 0.f); vec3 global = b200::mk3(0.f);
+        for (size_t i = 0; i < scene.forceFields.size(); ++i)
+        {
+            const game_scene::entity_data& e = scene.entities[scene.forceFieldEntity[i]];
+            vec3 force = scene.forceFields[i].force;
+            if (e.hasTransform) force = e.transform.rotation * force;
+            if (e.numColliders) { local[3 * i] = force.x; local[3 * i + 1] = force.y; local[3 * i + 2] = force.z; }
+            else global += force;
+        }
+        r = b200phys_upload_force_fields(scene.ctx, local.data(), (uint32_t)scene.forceFields.size()); if (r) return r;
+        const float g3[3] = { global.x, global.y, global.z };
+        r = b200phys_set_global_force_field(scene.ctx, g3); if (r) return r;
+    }
     const bool wantEvents = (bool)settings.collisionBeginCallback || (bool)settings.collisionEndCallback;
     if (wantEvents != scene.eventsEnabled) { r = b200phys_enable_events(scene.ctx, wantEvents ? 1 : 0); if (r) return r; scene.eventsEnabled = wantEvents; }
     r = b200phys_step(scene.ctx, dt, settings.numRigidSolverIterations, settings.exactConstraintOrder ? B200PHYS_STEP_EXACT_ORDER : B200PHYS_STEP_FAST); if (r) return r;
@@ -529,6 +562,22 @@ static int physicsStepInternal(game_scene& scene, const physics_settings& settin
                                                                            b200::mk3(e.normal[0], e.normal[1], e.normal[2]), b200::mk3(e.relativeVelocity[0], e.relativeVelocity[1], e.relativeVelocity[2]) });
                 ++ib;
             }
+        }
+    }
+    if (!scene.triggers.empty())
+    {   // handleNonCollisionInteractions (physics.cpp:970-1034): leave / enter callbacks in the order of the reference's merge loop
+        uint32_t ne = 0, nl = 0;
+        r = b200phys_download_trigger_events(scene.ctx, nullptr, 0, &ne, nullptr, 0, &nl); if (r && r != B200PHYS_E_CAPACITY) return r;
+        std::vector<b200phys_trigger_event> en(ne), le(nl);
+        r = b200phys_download_trigger_events(scene.ctx, en.data(), ne, &ne, le.data(), nl, &nl); if (r) return r;
+        auto key = [](const b200phys_trigger_event& e) { return ((unsigned long long)e.triggerIndex << 32) | e.rigidBodyIndex; };
+        size_t ie = 0, il = 0;
+        while (ie < en.size() || il < le.size())
+        {
+            const bool leave = il < le.size() && (ie >= en.size() || key(le[il]) < key(en[ie]));
+            const b200phys_trigger_event& e = leave ? le[il++] : en[ie++];
+            const trigger_component& t = scene.triggers[e.triggerIndex];
+            if (t.callback) t.callback(trigger_event{ scene.triggerEntity[e.triggerIndex], scene.rigidBodyEntity[e.rigidBodyIndex], leave ? trigger_event_leave : trigger_event_enter });
         }
     }
     std::vector<b200phys_body_state> states(bodies.size());

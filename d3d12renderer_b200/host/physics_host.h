@@ -101,6 +101,12 @@ struct hinge_constraint_handle { uint32_t index; };
 struct cone_twist_constraint_handle { uint32_t index; };
 struct slider_constraint_handle { uint32_t index; };
 
+// physics.h:291-345: triggers and force fields
+enum trigger_event_type { trigger_event_enter, trigger_event_leave };
+struct trigger_event { entity_handle trigger, other; trigger_event_type type; };
+struct trigger_component { std::function<void(const trigger_event&)> callback; };
+struct force_field_component { vec3 force; };
+
 // physics.h:356-380: collision events handed to the callbacks of physics_settings
 struct game_scene;
 struct collision_begin_event
@@ -143,6 +149,8 @@ struct scene_entity
     scene_entity& addTransform(vec3 position, quat rotation = b200::qIdentity(), vec3 scale = b200::mk3(1.f));                 // addComponent<transform_component>
     scene_entity& addCollider(const collider_component& c);                                                                     // addComponent<collider_component>
     scene_entity& addRigidBody(bool kinematic, float gravityFactor = 1.f, float linearDamping = 0.4f, float angularDamping = 0.4f); // addComponent<rigid_body_component>
+    scene_entity& addTrigger(std::function<void(const trigger_event&)> callback);   // addComponent<trigger_component>
+    scene_entity& addForceField(vec3 force);                                        // addComponent<force_field_component>
     rigid_body_component& rigidBody();
     trs& transform();
 };
@@ -153,6 +161,7 @@ struct game_scene
     {
         std::string name; bool hasTransform = false; trs transform;
         int32_t rigidBody = -1;                 // index into rigidBodies (storage order)
+        int32_t trigger = -1, forceField = -1;  // index into triggers / forceFields
         entity_handle firstColliderEntity = null_entity; uint32_t numColliders = 0;
     };
     std::vector<entity_data> entities;
@@ -160,6 +169,8 @@ struct game_scene
     std::vector<trs> physicsTransform0, physicsTransform1;      // per rigid body (rigid_body.h:48-58)
     std::vector<collider_component> colliders;                  // creation order; world index = reverse (physics.cpp:635-641)
     bool eventsEnabled = false;                                 // collision events switched on in the device context
+    std::vector<trigger_component> triggers; std::vector<entity_handle> triggerEntity;
+    std::vector<force_field_component> forceFields; std::vector<entity_handle> forceFieldEntity;
     std::vector<bounding_hull_geometry> hullGeometries;
     std::vector<distance_constraint> distanceConstraints; std::vector<ball_constraint> ballConstraints; std::vector<fixed_constraint> fixedConstraints;
     std::vector<hinge_constraint> hingeConstraints; std::vector<cone_twist_constraint> coneTwistConstraints; std::vector<slider_constraint> sliderConstraints;

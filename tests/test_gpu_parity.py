@@ -266,3 +266,28 @@ def test_triggers_and_force_fields_match_the_oracle():
     assert_states_close(st.download_bodies(), orc.body_states(), 1e-4)
     s = st.stats()
     assert s.assertCount == 0 and s.gjkIterationCaps == 0
+
+
+def test_host_mirror_triggers_and_force_fields():
+    """trigger_component callbacks and force_field_component (localized + global) through the host mirror's physicsStep: same events
+    and the same poses as driving the C ABI directly with the gathered arrays."""
+    sc = host.build_scene(host.CONFIG_EVENT_SCENE, 5, 1, 4, seed=77, mode=0, spacing=1.5)
+    hs = sc["host_scene"]
+    col = sc["colliders"]
+    assert (col["objectType"] == abi.OBJ_TRIGGER).sum() == 1 and (col["objectType"] == abi.OBJ_FORCE_FIELD).sum() == 1
+    st = make_stepper(sc)
+    st.upload_force_fields(np.array([[5.0, 0.0, 0.0], [0.0, 0.0, 0.0]], dtype=np.float32), np.array([0.0, 0.0, 1.0], dtype=np.float32))
+    hs.trigger_log(clear=True)
+    timer = 0.0; direct_events = []
+    for step in range(90):
+        st.step(DT, 30, abi.STEP_FAST)
+        e, l = st.download_trigger_events()
+        direct_events += [(0, int(b), 0) for _, b in e] + [(0, int(b), 1) for _, b in l]
+        timer = hs.physics_step(timer, float(DT), iterations=30)
+    log = hs.trigger_log()
+    n = len(sc["bodies"])
+    assert len(log) == len(direct_events) and len(log) >= n            # every sphere enters the slab (and most leave it again)
+    # the mirror reports entities: trigger entity is the one created after the ground, bodies are entities 0..n-1 in creation order
+    assert sorted((int(o), int(t)) for _, o, t in log) == sorted((b, t) for _, b, t in direct_events)
+    assert np.allclose(hs.arrays()["bodies"]["position"], st.download_bodies()["position"], atol=1e-6)
+    assert np.all(hs.arrays()["bodies"]["position"][:, 2] > sc["bodies"]["position"][:, 2])      # the global field pushed everything along +z
