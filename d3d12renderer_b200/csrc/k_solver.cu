@@ -49,8 +49,9 @@ __global__ void __launch_bounds__(kThreads) adjFillKernel(const uint2* __restric
     for (uint32_t u = blockIdx.x * kThreads + threadIdx.x; u < n; u += gridDim.x * kThreads)
     {
         const uint2 b = unitBodies[u];
-        if (bodyIsDynamic(gMass, b.x, N)) adjList[adjStart[b.x] + atomicAdd(&adjFill[b.x], 1u)] = u;
-        if (b.y != b.x && bodyIsDynamic(gMass, b.y, N)) adjList[adjStart[b.y] + atomicAdd(&adjFill[b.y], 1u)] = u;
+        // entry = unit << 1 | which of the unit's two bodies this list belongs to
+        if (bodyIsDynamic(gMass, b.x, N)) adjList[adjStart[b.x] + atomicAdd(&adjFill[b.x], 1u)] = u << 1;
+        if (b.y != b.x && bodyIsDynamic(gMass, b.y, N)) adjList[adjStart[b.y] + atomicAdd(&adjFill[b.y], 1u)] = (u << 1) | 1u;
     }
 }
 
@@ -70,7 +71,7 @@ B200_D bool ranksBefore(int exact, uint32_t v, uint32_t pv, uint32_t u, uint32_t
 
 static const uint32_t kNbrStride = 16;   // explicit "who waits for me" list per unit (falls back to adjacency traversal above this)
 
-// visits every neighbour v != u of unit u (units sharing a dynamic body); 4 adjacency entries are loaded per trip so the
+// visits every neighbour v != u of unit u (units sharing a dynamic body; a unit sharing both bodies is visited twice); 4 adjacency entries are loaded per trip so the
 // loads overlap (the lists are short: latency, not bandwidth, is what costs here)
 template <typename F>
 B200_D void forEachNeighbour(uint32_t u, uint2 b, const float4* __restrict__ gMass, uint32_t N, const uint32_t* __restrict__ adjStart, const uint32_t* __restrict__ adjList, F&& f)
@@ -86,9 +87,9 @@ B200_D void forEachNeighbour(uint32_t u, uint2 b, const float4* __restrict__ gMa
         {
             uint32_t v[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) v[j] = (a + j < a1) ? adjList[a + j] : u;
+            for (int j = 0; j < 4; ++j) v[j] = (a + j < a1) ? adjList[a + j] : (u << 1);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) if (v[j] != u) f(v[j]);
+            for (int j = 0; j < 4; ++j) if ((v[j] >> 1) != u) f(v[j] >> 1, v[j] & 1u);      // neighbour, and which of ITS bodies is the shared one
         }
     }
 }
@@ -100,6 +101,8 @@ B200_D void forEachNeighbour(uint32_t u, uint2 b, const float4* __restrict__ gMa
 // same deterministic colouring (every unit still decides from exactly the colours of its higher-priority neighbours).
 // All same-address traffic is warp-aggregated: one atomic per 32 tickets, one per warp pass for the enqueues.
 static const uint32_t kQueueEmpty = 0xFFFFFFFFu;
+static const uint32_t kColorPollSleepNs = 200;
+static const uint32_t kMaxFastColors = 26;     // colour bits per body-side field of the state word
 static const int kColorRunThreads = 256;
 
 __global__ void __launch_bounds__(kThreads) colorInitKernel(const uint2* __restrict__ unitBodies, const uint32_t* __restrict__ numUnitsPtr,
@@ -118,14 +121,17 @@ __global__ void __launch_bounds__(kThreads) colorInitKernel(const uint2* __restr
             const uint2 b = unitBodies[u];
             const uint32_t pu = hashPriority(u);
             uint32_t pend = 0, nw = 0;
-            forEachNeighbour(u, b, gMass, N, adjStart, adjList, [&](uint32_t v)
+            forEachNeighbour(u, b, gMass, N, adjStart, adjList, [&](uint32_t v, uint32_t vside)
             {
                 if (ranksBefore(0, v, hashPriority(v), u, pu)) ++pend;
-                else { if (nw < kNbrStride) nbrList[(size_t)u * kNbrStride + nw] = v; ++nw; }
+                else { if (nw < kNbrStride) nbrList[(size_t)u * kNbrStride + nw] = (v << 1) | vside; ++nw; }
             });
-            // pending << 48 | colour mask in ONE 64-bit word: a notifier's OR and its decrement go to the same address, which the
-            // memory model keeps in program order, so the thread that sees the count reach zero also sees every colour bit
-            forbid[u] = (unsigned long long)pend << 48;
+            // ONE 64-bit word per unit: pending << 52 | colours seen through body B << 26 | colours seen through body A. The units
+            // around one body are a clique (pairwise distinct colours), so within one field every colour bit is added at most once
+            // and a notifier needs a single atomicAdd (+ colour bit, - 1 pending) per waiting unit; the thread whose add brings the
+            // count to zero has, by the order of the atomics on that word, every colour bit in what it reads back afterwards.
+            if (pend > 0xFFFu) { pend = 0xFFFu; cnt->overflowColors = 1; }
+            forbid[u] = (unsigned long long)pend << 52;
             color[u] = kUncolored; nbrCount[u] = nw;
             seed = pend == 0;
         }
@@ -171,14 +177,14 @@ __global__ void __launch_bounds__(kColorRunThreads) colorRunKernel(uint32_t grou
                     done = true;
                     unsigned long long f;
                     asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(f) : "l"(forbid + u) : "memory");
-                    f |= 0xFFFF000000000000ull;                    // only 48 colours are representable
-                    uint32_t c = (uint32_t)(__ffsll((long long)~f) - 1);
-                    if (c >= 48u) { c = 47u; cnt->overflowColors = 1; }
+                    const uint32_t taken = (uint32_t)(f & 0x3FFFFFFull) | (uint32_t)((f >> 26) & 0x3FFFFFFull);
+                    uint32_t c = (uint32_t)(__ffs((int)~taken) - 1);
+                    if (c >= kMaxFastColors) { c = kMaxFastColors - 1; cnt->overflowColors = 1; }   // 26 colours per field
                     color[u] = c;
                     atomicAdd(&sHist[c], 1u);
                     localMax = max(localMax, c + 1u);
                     const uint32_t nw = nbrCount[u];
-                    const unsigned long long bit = 1ull << c;
+                    const unsigned long long dec = 0xFFF0000000000000ull;     // -1 in the pending field
                     if (nw <= kNbrStride)
                     {   // the waiting units are listed explicitly: 4 independent 128-bit loads, then the atomics back to back
                         uint32_t w[kNbrStride];
@@ -187,37 +193,35 @@ __global__ void __launch_bounds__(kColorRunThreads) colorRunKernel(uint32_t grou
                         for (int j = 0; j < 4; ++j) { const uint4 q = (4u * j < nw) ? L[j] : make_uint4(0, 0, 0, 0); w[4 * j] = q.x; w[4 * j + 1] = q.y; w[4 * j + 2] = q.z; w[4 * j + 3] = q.w; }
                         unsigned long long old[kNbrStride];
 #pragma unroll
-                        for (int j = 0; j < (int)kNbrStride; ++j) if ((uint32_t)j < nw) { atomicOr(&forbid[w[j]], bit); old[j] = atomicAdd(&forbid[w[j]], 0xFFFF000000000000ull); }   // += -(1 << 48)
+                        for (int j = 0; j < (int)kNbrStride; ++j) if ((uint32_t)j < nw) old[j] = atomicAdd(&forbid[w[j] >> 1], (1ull << (c + 26u * (w[j] & 1u))) + dec);
 #pragma unroll
-                        for (int j = 0; j < (int)kNbrStride; ++j) if ((uint32_t)j < nw && (old[j] >> 48) == 1ull) ready[nReady++] = w[j];
+                        for (int j = 0; j < (int)kNbrStride; ++j) if ((uint32_t)j < nw && (old[j] >> 52) == 1ull) ready[nReady++] = w[j] >> 1;
                     }
                     else
                     {   // rare: more waiting units than the list holds -> walk the adjacency, enqueue one by one
                         const uint2 b = unitBodies[u];
                         const uint32_t pu = hashPriority(u);
-                        forEachNeighbour(u, b, gMass, N, adjStart, adjList, [&](uint32_t v)
+                        forEachNeighbour(u, b, gMass, N, adjStart, adjList, [&](uint32_t v, uint32_t vside)
                         {
                             if (!ranksBefore(0, u, pu, v, hashPriority(v))) return;
-                            atomicOr(&forbid[v], bit);
-                            const unsigned long long o = atomicAdd(&forbid[v], 0xFFFF000000000000ull);
-                            if ((o >> 48) == 1ull) { const uint32_t t = atomicAdd(&cnt->colorQueueTail, 1u); if (t < n) queue[t] = v; }
+                            const unsigned long long o = atomicAdd(&forbid[v], (1ull << (c + 26u * vside)) + dec);
+                            if ((o >> 52) == 1ull) { const uint32_t t = atomicAdd(&cnt->colorQueueTail, 1u); if (t < n) queue[t] = v; }
                         });
                     }
                 }
                 else if (++spins > (1u << 22)) { cnt->overflowColors = 2; done = true; }   // refuse to hang (cyclic graph cannot happen)
             }
-            // hand the newly ready units to the queue: one reservation per warp and pass
+            // hand the newly ready units to the queue: one reservation per warp and pass (a pass in which nobody ran a unit
+            // is a pure poll: skip the bookkeeping and back off a little so that the working warps get the issue slots)
+            if (!__any_sync(0xffffffffu, nReady != 0u)) { if (__any_sync(0xffffffffu, !done)) __nanosleep(kColorPollSleepNs); continue; }
             uint32_t incl = nReady;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (laneId() >= (uint32_t)o) incl += t; }
             const uint32_t totalReady = __shfl_sync(0xffffffffu, incl, 31);
-            if (totalReady)
-            {
-                uint32_t qb = 0;
-                if (laneId() == 0) qb = atomicAdd(&cnt->colorQueueTail, totalReady);
-                qb = __shfl_sync(0xffffffffu, qb, 0) + incl - nReady;
-                for (uint32_t j = 0; j < nReady; ++j) if (qb + j < n) asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" :: "l"(queue + qb + j), "r"(ready[j]) : "memory");
-            }
+            uint32_t qb = 0;
+            if (laneId() == 0) qb = atomicAdd(&cnt->colorQueueTail, totalReady);
+            qb = __shfl_sync(0xffffffffu, qb, 0) + incl - nReady;
+            for (uint32_t j = 0; j < nReady; ++j) if (qb + j < n) asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" :: "l"(queue + qb + j), "r"(ready[j]) : "memory");
         }
     }
     localMax = __reduce_max_sync(0xffffffffu, localMax);
@@ -438,8 +442,8 @@ __global__ void __launch_bounds__(kThreads) depRankKernel(int mode /* 0 colours,
             if (mode)
             {   // the body's units in solve-position order
                 const uint32_t a0 = adjStart[body], a1 = adjStart[body + 1];
-                if (mode == 1) { for (uint32_t a = a0; a < a1; ++a) rank += (adjList[a] < u) ? 1u : 0u; }
-                else { for (uint32_t a = a0; a < a1; ++a) rank += (permutePos(adjList[a], n) < p) ? 1u : 0u; }
+                if (mode == 1) { for (uint32_t a = a0; a < a1; ++a) rank += ((adjList[a] >> 1) < u) ? 1u : 0u; }
+                else { for (uint32_t a = a0; a < a1; ++a) rank += (permutePos(adjList[a] >> 1, n) < p) ? 1u : 0u; }
                 deg += a1 - a0;
             }
             else
