@@ -141,6 +141,7 @@ struct Context
     bool eventsEnabled = false; int evParity = 0;
     unsigned long long* evKeys[2] = {}; uint2* evPairs[2] = {}; uint32_t* evFlag[2] = {}; uint32_t* evSlot[2] = {};
     b200phys_collision_begin_event* evBegin = nullptr; b200phys_collider_pair* evEnd = nullptr;
+    unsigned long long* scanStatus = nullptr; uint32_t* scanState = nullptr; uint32_t scanStatusTiles = 0, scanEpoch = 0;   // single-pass scan
     uint32_t* colorQueue = nullptr;         // ready queue of the colouring (max units of any group)
     unsigned long long* bodyMask = nullptr; // colours taken at each body (current group)
     uint32_t* bodyBase = nullptr;           // units per body in the groups coloured so far

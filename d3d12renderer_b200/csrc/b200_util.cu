@@ -126,9 +126,113 @@ static void scanExclusive(Context* c, const T* in, T* out, const uint32_t* devCo
     c->launches += 3;
 }
 
+// ---- single-pass exclusive scan (decoupled look-back): ONE launch instead of reduce / spine / apply. Tiles are handed out by an
+// atomic ticket so that every tile a CTA looks back at is already owned by a running CTA; a tile publishes (epoch, state, value)
+// in one 64-bit word, the epoch (a per-context launch counter) makes clearing the status array unnecessary; the last CTA to leave
+// resets the ticket counter for the next launch.
+static const int kLbThreads = 256, kLbItems = 8, kLbTile = kLbThreads * kLbItems;
+struct ScanLbState { unsigned int ticket, done; };
+
+__global__ void __launch_bounds__(kLbThreads) scanLookbackKernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, const uint32_t* __restrict__ devCount, uint32_t hostCount,
+                                                                 unsigned long long* __restrict__ status, ScanLbState* __restrict__ state, uint32_t epoch, uint32_t* __restrict__ totalOut)
+{
+    __shared__ uint32_t warpSums[kLbThreads / 32];
+    __shared__ uint32_t sTile, sPrefix, sTileTotal;
+    const uint32_t n = devCount ? *devCount : hostCount;
+    const uint32_t numTiles = (n + kLbTile - 1) / kLbTile;
+    const unsigned long long tagAgg = ((unsigned long long)epoch << 34) | (1ull << 32), tagPre = ((unsigned long long)epoch << 34) | (2ull << 32);
+    for (;;)
+    {
+        if (threadIdx.x == 0) sTile = atomicAdd(&state->ticket, 1u);
+        __syncthreads();
+        const uint32_t tile = sTile;
+        if (tile >= numTiles) break;
+        const uint32_t base = tile * kLbTile + threadIdx.x * kLbItems;
+        uint32_t v[kLbItems]; uint32_t local = 0;
+        if (base + kLbItems <= n)
+        {
+            const uint4 a = *reinterpret_cast<const uint4*>(in + base), b = *reinterpret_cast<const uint4*>(in + base + 4);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        }
+        else
+        {
+#pragma unroll
+            for (int k = 0; k < kLbItems; ++k) v[k] = (base + k < n) ? in[base + k] : 0u;
+        }
+#pragma unroll
+        for (int k = 0; k < kLbItems; ++k) local += v[k];
+        uint32_t incl = local;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (laneId() >= (uint32_t)o) incl += t; }
+        if (laneId() == 31) warpSums[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        if (threadIdx.x < 32)
+        {
+            const uint32_t w = (threadIdx.x < kLbThreads / 32) ? warpSums[threadIdx.x] : 0u;
+            uint32_t wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, wi, o); if (laneId() >= (uint32_t)o) wi += t; }
+            if (threadIdx.x < kLbThreads / 32) warpSums[threadIdx.x] = wi - w;
+            if (threadIdx.x == kLbThreads / 32 - 1) sTileTotal = wi;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0)
+        {
+            const uint32_t total = sTileTotal;
+            uint32_t prefix = 0;
+            if (tile == 0) atomicExch(&status[0], tagPre | total);
+            else
+            {
+                atomicExch(&status[tile], tagAgg | total);                 // publish the aggregate, then look back
+                for (uint32_t p = tile; p-- > 0; )
+                {
+                    unsigned long long st;
+                    do { asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(st) : "l"(status + p) : "memory"); } while ((st >> 34) != epoch || ((st >> 32) & 3ull) == 0ull);
+                    prefix += (uint32_t)st;
+                    if (((st >> 32) & 3ull) == 2ull) break;                  // an inclusive prefix ends the walk
+                }
+                atomicExch(&status[tile], tagPre | (prefix + total));
+            }
+            sPrefix = prefix;
+            if (tile == numTiles - 1) { out[n] = prefix + total; if (totalOut) *totalOut = prefix + total; }
+        }
+        __syncthreads();
+        uint32_t excl = sPrefix + warpSums[threadIdx.x >> 5] + (incl - local);
+        if (base + kLbItems <= n)
+        {
+            uint4 a, b;
+            a.x = excl; excl += v[0]; a.y = excl; excl += v[1]; a.z = excl; excl += v[2]; a.w = excl; excl += v[3];
+            b.x = excl; excl += v[4]; b.y = excl; excl += v[5]; b.z = excl; excl += v[6]; b.w = excl;
+            *reinterpret_cast<uint4*>(out + base) = a; *reinterpret_cast<uint4*>(out + base + 4) = b;
+        }
+        else
+        {
+#pragma unroll
+            for (int k = 0; k < kLbItems; ++k) { if (base + k < n) out[base + k] = excl; excl += v[k]; }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0)
+    {
+        if (n == 0 && blockIdx.x == 0) { out[0] = 0; if (totalOut) *totalOut = 0; }
+        if (atomicAdd(&state->done, 1u) == gridDim.x - 1) { state->ticket = 0; state->done = 0; }     // last one out: ready for the next launch
+    }
+}
+
 void scanExclusiveU32(Context* c, const uint32_t* in, uint32_t* out, const uint32_t* devCount, uint32_t maxCount, uint32_t* totalOut)
 {
-    scanExclusive<uint32_t>(c, in, out, devCount, maxCount, c->scanTmp, totalOut);
+    if (maxCount == 0) return;
+    const uint32_t maxTiles = (maxCount + kLbTile - 1) / kLbTile;
+    if (maxTiles > c->scanStatusTiles || (((uintptr_t)in | (uintptr_t)out) & 15u))
+    {   // unaligned buffers or more tiles than the status array holds: the three-kernel version
+        scanExclusive<uint32_t>(c, in, out, devCount, maxCount, c->scanTmp, totalOut);
+        return;
+    }
+    int blocks = gridFor(c, 4);
+    if ((uint32_t)blocks > maxTiles) blocks = (int)maxTiles;
+    c->scanEpoch = (c->scanEpoch + 1u) & 0x3FFFFFFFu; if (c->scanEpoch == 0) c->scanEpoch = 1;
+    scanLookbackKernel<<<blocks, kLbThreads, 0, c->stream>>>(in, out, devCount, maxCount, c->scanStatus, (ScanLbState*)c->scanState, c->scanEpoch, totalOut);
+    c->launches += 1;
 }
 void scanExclusiveU64(Context* c, const unsigned long long* in, unsigned long long* out, const uint32_t* devCount, uint32_t maxCount, unsigned long long* totalOut)
 {
