@@ -44,6 +44,7 @@ struct DeviceCounts
     uint32_t colorStart[kNumGroups][kMaxColors + 1]; // fast mode unit ranges per colour
     uint32_t numBig;
     uint32_t bigMatrixCount;            // min(numBig, 16) * C: size of the big-collider flag matrix
+    uint32_t numRefManifolds, refNumColors;     // colour reuse across steps: size / colour count of the remembered list
     uint32_t colorQueueHead, colorQueueTail;   // ready queue of the colouring
     uint32_t numOverlapPairs, numInteractions;   // rigid body vs trigger / force field pairs tested / overlapping this step
     uint32_t numPrevCollisions, numBeginEvents, numEndEvents;   // collision event layer (k_events.cu)
@@ -142,6 +143,8 @@ struct Context
     unsigned long long* evKeys[2] = {}; uint2* evPairs[2] = {}; uint32_t* evFlag[2] = {}; uint32_t* evSlot[2] = {};
     b200phys_collision_begin_event* evBegin = nullptr; b200phys_collider_pair* evEnd = nullptr;
     unsigned long long* scanStatus = nullptr; uint32_t* scanState = nullptr; uint32_t scanStatusTiles = 0, scanEpoch = 0;   // single-pass scan
+    unsigned long long* refKeys[2] = {}; uint8_t* refColors = nullptr; uint8_t* colorKey = nullptr; int refParity = 0, colorAge = 0;   // colour reuse across steps
+    uint8_t* refColorsJoint[6] = {}; uint32_t jointColorCount[6] = {}; int jointColorAge[6] = {};
     uint32_t* colorQueue = nullptr;         // ready queue of the colouring (max units of any group)
     unsigned long long* bodyMask = nullptr; // colours taken at each body (current group)
     uint32_t* bodyBase = nullptr;           // units per body in the groups coloured so far

@@ -35,6 +35,8 @@ int allocateAll(Context& c)
     CK(devAlloc(c.gVel, 2 * N1)); CK(devAlloc(c.gPos, N1)); CK(devAlloc(c.gInvI, 3 * N1));
     CK(devAlloc(c.bodyMask, N1 + 1)); CK(devAlloc(c.bodyBase, N1 + 1));
     CK(devAlloc(c.colorQueue, (M > J ? M : J) + 32));
+    for (int k = 0; k < 6; ++k) CK(devAlloc(c.refColorsJoint[k], J + 2));
+    CK(devAlloc(c.refKeys[0], M + 2)); CK(devAlloc(c.refKeys[1], M + 2)); CK(devAlloc(c.refColors, M + 2)); CK(devAlloc(c.colorKey, M + 2));
     c.scanStatusTiles = (uint32_t)((16 * P + 2047) / 2048 + 64); CK(devAlloc(c.scanStatus, c.scanStatusTiles)); CK(devAlloc(c.scanState, 4));
     CK(cudaMemset(c.scanStatus, 0, sizeof(unsigned long long) * c.scanStatusTiles)); CK(cudaMemset(c.scanState, 0, 16));
     CK(devAlloc(c.cLocal, 4 * C)); CK(devAlloc(c.xforms, 2 * T)); CK(devAlloc(c.wCol, 4 * C)); CK(devAlloc(c.aabbMin, C)); CK(devAlloc(c.aabbMax, C));
@@ -84,11 +86,12 @@ int allocateAll(Context& c)
 
 void freeAll(Context& c)
 {
-    void* ptrs[] = { c.bRot, c.bPos, c.bCog, c.bInvI, c.bVel, c.bAng, c.bForce, c.bTorque, c.gVel, c.gPos, c.gInvI, c.bodyMask, c.bodyBase, c.colorQueue, c.scanStatus, c.scanState, c.cLocal, c.xforms, c.wCol, c.aabbMin, c.aabbMax,
+    void* ptrs[] = { c.bRot, c.bPos, c.bCog, c.bInvI, c.bVel, c.bAng, c.bForce, c.bTorque, c.gVel, c.gPos, c.gInvI, c.bodyMask, c.bodyBase, c.refKeys[0], c.refKeys[1], c.refColors, c.colorKey, c.colorQueue, c.scanStatus, c.scanState, c.cLocal, c.xforms, c.wCol, c.aabbMin, c.aabbMax,
         c.hullVerts, c.hullOffsets, c.hullAabb, c.cellOf, c.rankInCell, c.cellCount, c.cellStart, c.sortedMin, c.sortedMax, c.bigList, c.pairCount, c.pairStart, c.pairs,
         c.pairKey, c.pairsTyped, c.pairDst, c.pairsSorted, c.manTmp, c.manScan, c.manScanOut, c.epaSimplex, c.epaWork, c.collisions, c.manifolds, c.contacts, c.contactBodies,
         c.unitPending, c.unitForbid, c.nbrCount, c.nbrList, c.adjStart, c.adjFill, c.adjList, c.levelStart, c.levelFill, c.slotOfContact, c.unitSlotStart, c.unitInfo, c.rows, c.rowImp, c.scanTmp, c.scanTmp64, c.sortHist, c.staging, c.counts, c.haloBuf };
     for (void* p : ptrs) if (p) cudaFree(p);
+    for (int k = 0; k < 6; ++k) if (c.refColorsJoint[k]) cudaFree(c.refColorsJoint[k]);
     for (int k = 0; k < 2; ++k) { if (c.evKeys[k]) cudaFree(c.evKeys[k]); if (c.evPairs[k]) cudaFree(c.evPairs[k]); if (c.evFlag[k]) cudaFree(c.evFlag[k]); if (c.evSlot[k]) cudaFree(c.evSlot[k]); }
     if (c.evBegin) cudaFree(c.evBegin); if (c.evEnd) cudaFree(c.evEnd);
     if (c.interactions) cudaFree(c.interactions); if (c.forceFields) cudaFree(c.forceFields); delete c.prevTriggerOverlaps;

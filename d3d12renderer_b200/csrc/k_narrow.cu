@@ -106,9 +106,16 @@ __global__ void __launch_bounds__(CLASS == 0 ? 256 : 128) npCollideKernel(const 
         for (uint32_t q = q0 + blockIdx.x * blockDim.x + threadIdx.x; q < q1; q += gridDim.x * blockDim.x)
         {
             const uint2 pr = sorted[q];
-            const ColRec A = loadCol(wCol, pr.x), B = loadCol(wCol, pr.y);
             Man m; m.cnt = 0;
             bool hit = false;
+            if (CLASS == 0 && bucket == 0)
+            {   // sphere - sphere, the bulk of a pile: only the first 16 bytes of each 64-byte collider record are needed
+                ColRec A, B; A.r0 = wCol[4 * pr.x]; B.r0 = wCol[4 * pr.y];
+                hit = sphereSphere(asSphere(A), asSphere(B), m, nc);
+                storeManifold(manTmp, manScan, q, maxPairs, hit, m);
+                continue;
+            }
+            const ColRec A = loadCol(wCol, pr.x), B = loadCol(wCol, pr.y);
             if (CLASS == 0)
             {
                 switch (bucket)

@@ -422,7 +422,7 @@ __global__ void __launch_bounds__(kThreads) colorQueueResetKernel(const uint32_t
     for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n + 32u; i += gridDim.x * kThreads) queue[i] = 0xFFFFFFFFu;
 }
 
-__global__ void __launch_bounds__(kThreads) depRankKernel(int mode /* 0 colours, 1 canonical index order, 2 permuted order */, const uint2* __restrict__ unitBodies, const uint32_t* __restrict__ numUnits, const uint32_t* __restrict__ color,
+__global__ void __launch_bounds__(kThreads) depRankKernel(int mode /* 0 colours, 1 canonical index order, 2 permuted order, 3 positions from posOf */, const uint32_t* __restrict__ posOf, const uint2* __restrict__ unitBodies, const uint32_t* __restrict__ numUnits, const uint32_t* __restrict__ color,
     const uint32_t* __restrict__ order, const float4* __restrict__ gMass, uint32_t N, const unsigned long long* __restrict__ bodyMask, const uint32_t* __restrict__ bodyBase,
     const uint32_t* __restrict__ adjStart, const uint32_t* __restrict__ adjList, uint2* __restrict__ dep)
 {
@@ -442,7 +442,8 @@ __global__ void __launch_bounds__(kThreads) depRankKernel(int mode /* 0 colours,
             if (mode)
             {   // the body's units in solve-position order
                 const uint32_t a0 = adjStart[body], a1 = adjStart[body + 1];
-                if (mode == 1) { for (uint32_t a = a0; a < a1; ++a) rank += ((adjList[a] >> 1) < u) ? 1u : 0u; }
+                if (mode == 3) { for (uint32_t a = a0; a < a1; ++a) rank += (posOf[adjList[a] >> 1] < p) ? 1u : 0u; }
+                else if (mode == 1) { for (uint32_t a = a0; a < a1; ++a) rank += ((adjList[a] >> 1) < u) ? 1u : 0u; }
                 else { for (uint32_t a = a0; a < a1; ++a) rank += (permutePos(adjList[a] >> 1, n) < p) ? 1u : 0u; }
                 deg += a1 - a0;
             }
@@ -466,6 +467,63 @@ __global__ void __launch_bounds__(kThreads) bodyBaseAddKernel(int exact, uint32_
         if (!exact) bodyMask[b] = 0ull;
         if (add) { const uint32_t t = bodyBase[b] + add; bodyBase[b] = t; if (t > 0xFFFFu) cnt->overflowColors = 8; }
     }
+}
+
+// ---- colour reuse across steps (contacts): the contact graph of a resting or slowly moving scene barely changes from one step to
+// the next, and the dataflow sweep does not need a PROPER colouring, only a total order with short dependency chains. Every
+// manifold has a key (type bucket, lower collider, higher collider); the manifold list is sorted by it in every step. Between two
+// full colourings (every `recolorEvery` steps) a manifold inherits the colour its key had in the previous step (binary search in
+// last step's sorted keys); new pairs get a hashed colour. Units are then stable-sorted by colour and ranked by POSITION, so two
+// neighbours that ended up with the same colour are simply ordered by index: correct for any input, fast when most colours
+// are still conflict-free.
+B200_D uint32_t pairBucketOf(uint32_t ta, uint32_t tb) { if (ta > tb) { const uint32_t t = ta; ta = tb; tb = t; } return ta * 6u - (ta * (ta - 1u)) / 2u + (tb - ta); }
+__global__ void __launch_bounds__(kThreads) manifoldKeysKernel(const uint2* __restrict__ collisions, const float4* __restrict__ wCol, unsigned long long* __restrict__ keys, const DeviceCounts* __restrict__ cnt)
+{
+    const uint32_t n = cnt->numManifolds;
+    for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads)
+    {
+        const uint2 pr = collisions[i];
+        const uint32_t ta = __float_as_uint(wCol[4 * pr.x + 3].x) & 0xFFu, tb = __float_as_uint(wCol[4 * pr.y + 3].x) & 0xFFu;
+        keys[i] = ((unsigned long long)pairBucketOf(ta, tb) << 56) | ((unsigned long long)min(pr.x, pr.y) << 28) | (unsigned long long)max(pr.x, pr.y);
+    }
+}
+__global__ void __launch_bounds__(kThreads) colorInheritKernel(const unsigned long long* __restrict__ keys, const unsigned long long* __restrict__ refKeys, const uint8_t* __restrict__ refColors,
+    uint8_t* __restrict__ colorKey, uint32_t* __restrict__ color, DeviceCounts* cnt)
+{
+    const uint32_t n = cnt->numManifolds, nRef = cnt->numRefManifolds, numColors = max(cnt->refNumColors, 1u);
+    if (blockIdx.x == 0 && threadIdx.x == 0) cnt->numColors[6] = numColors;
+    for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads)
+    {
+        const unsigned long long k = keys[i];
+        uint32_t lo = 0, hi = nRef;
+        while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (refKeys[mid] < k) lo = mid + 1; else hi = mid; }
+        uint32_t c;
+        if (lo < nRef && refKeys[lo] == k) c = refColors[lo];
+        else c = hashPriority((uint32_t)k ^ (uint32_t)(k >> 28)) % numColors;       // a pair that did not touch last step
+        colorKey[i] = (uint8_t)c; color[i] = c;
+    }
+}
+// joints keep their index from step to step: inheriting is a copy
+__global__ void __launch_bounds__(kThreads) jointColorCopyKernel(int toRef, const uint32_t* __restrict__ numUnits, uint32_t* __restrict__ color, uint8_t* __restrict__ colorKey, uint8_t* __restrict__ ref)
+{
+    const uint32_t n = *numUnits;
+    for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads)
+    {
+        if (toRef) ref[i] = (uint8_t)min(color[i], 255u);
+        else { const uint32_t c = ref[i]; colorKey[i] = (uint8_t)c; color[i] = c; }
+    }
+}
+__global__ void __launch_bounds__(kThreads) orderFromPosKernel(const uint32_t* __restrict__ numUnits, const uint32_t* __restrict__ posOf, uint32_t* __restrict__ order)
+{
+    const uint32_t n = *numUnits;
+    for (uint32_t u = blockIdx.x * kThreads + threadIdx.x; u < n; u += gridDim.x * kThreads) order[posOf[u]] = u;
+}
+// remember this step's (key, colour) per manifold for the next step
+__global__ void __launch_bounds__(kThreads) colorRememberKernel(const uint32_t* __restrict__ color, uint8_t* __restrict__ refColors, DeviceCounts* cnt)
+{
+    const uint32_t n = cnt->numManifolds;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { cnt->numRefManifolds = n; cnt->refNumColors = cnt->numColors[6]; }
+    for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) refColors[i] = (uint8_t)min(color[i], 255u);
 }
 
 // with several groups (joint kinds, then contacts) a body's total degree is only known after the last group
@@ -629,9 +687,10 @@ __global__ void solverResetKernel(DeviceCounts* cnt, JointCounts jc)
 }
 
 // colour one group of units (joint kind or contacts); leaves order[] and colour ranges behind
-static void colorGroup(Context* c, uint32_t group, const uint2* unitBodies, const uint32_t* numUnitsDev, uint32_t maxUnits, bool exact, bool permuted,
+static void colorGroup(Context* c, uint32_t group, const uint2* unitBodies, const uint32_t* numUnitsDev, uint32_t maxUnits, bool exact, bool permuted, bool inherit,
                        uint32_t* color, uint32_t* order, uint32_t* colorStartOut, uint32_t barrierSlot)
 {
+    uint32_t* posOf = c->unitPending;      // scratch, one word per unit
     const uint32_t N = c->numBodies;
     const int G = gridFor(c, 8);
     cudaMemsetAsync(c->adjFill, 0, sizeof(uint32_t) * (N + 2), c->stream);
@@ -645,8 +704,14 @@ static void colorGroup(Context* c, uint32_t group, const uint2* unitBodies, cons
     c->launches++;
 
     DeviceCounts* cnt = c->counts;
-    const int mode = exact ? 1 : (permuted ? 2 : 0);
-    if (mode == 0)
+    const int mode = exact ? 1 : (permuted ? 2 : (inherit ? 3 : 0));
+    if (mode == 3)
+    {   // colours inherited from the previous step (colorInheritKernel ran before): stable sort by colour, rank by position
+        stableSmallKeySort(c, c->colorKey, numUnitsDev, maxUnits, kMaxColors, posOf, cnt->colorStart[group]);
+        orderFromPosKernel<<<G, kThreads, 0, c->stream>>>(numUnitsDev, posOf, order);
+        c->launches++;
+    }
+    else if (mode == 0)
     {   // deterministic Jones-Plassmann colouring, queue driven
         uint32_t* colorCount = c->levelFill + (kMaxLevels + 1);   // kMaxColors entries used
         uint32_t* colorFill = c->levelFill + 2 * (kMaxLevels + 1);
@@ -666,7 +731,7 @@ static void colorGroup(Context* c, uint32_t group, const uint2* unitBodies, cons
         c->launches++;
     }
     // dataflow records of this group (rank / degree of every unit at its bodies), then fold the group into the per-body totals
-    depRankKernel<<<G, kThreads, 0, c->stream>>>(mode, unitBodies, numUnitsDev, color, order, c->gPos, N, c->bodyMask, c->bodyBase, c->adjStart, c->adjList, c->unitDep[group]);
+    depRankKernel<<<G, kThreads, 0, c->stream>>>(mode, posOf, unitBodies, numUnitsDev, color, order, c->gPos, N, c->bodyMask, c->bodyBase, c->adjStart, c->adjList, c->unitDep[group]);
     bodyBaseAddKernel<<<G, kThreads, 0, c->stream>>>(mode != 0, N, c->bodyMask, c->adjStart, c->bodyBase, cnt);
     c->launches += 2;
     (void)maxUnits;
@@ -695,8 +760,14 @@ void launchSolver(Context* c, float dt, uint32_t iterations, uint32_t flags)
         if (c->numJoints[k])
         {
             anyJoint = true;
-            colorGroup(c, (uint32_t)k, c->jointBodies[k], &cnt->numJoints[k], c->numJoints[k], exact, permuted, c->unitColor[k], c->unitOrder[k],
+            // the joint graph only changes when joints are uploaded with a different count: colour it once, then inherit
+            const bool fast = !exact && !permuted;
+            const bool inheritJ = fast && c->jointColorCount[k] == c->numJoints[k] && c->jointColorAge[k] > 0 && c->jointColorAge[k] < 64;
+            if (inheritJ) { jointColorCopyKernel<<<G, kThreads, 0, c->stream>>>(0, &cnt->numJoints[k], c->unitColor[k], c->colorKey, c->refColorsJoint[k]); c->launches++; }
+            colorGroup(c, (uint32_t)k, c->jointBodies[k], &cnt->numJoints[k], c->numJoints[k], exact, permuted, inheritJ, c->unitColor[k], c->unitOrder[k],
                        c->levelStart + (size_t)k * (kMaxLevels + 1), (uint32_t)k);
+            if (fast && !inheritJ) { jointColorCopyKernel<<<G, kThreads, 0, c->stream>>>(1, &cnt->numJoints[k], c->unitColor[k], c->colorKey, c->refColorsJoint[k]); c->launches++; c->jointColorCount[k] = c->numJoints[k]; c->jointColorAge[k] = 0; }
+            if (fast) ++c->jointColorAge[k]; else c->jointColorAge[k] = 0;
         }
     }
     if (anyJoint)
@@ -711,7 +782,29 @@ void launchSolver(Context* c, float dt, uint32_t iterations, uint32_t flags)
     manifoldBodiesKernel<<<G, kThreads, 0, c->stream>>>(c->manifolds, unitBodies, cnt);
     c->launches++;
     uint32_t* contactColorStart = c->levelStart + (size_t)6 * (kMaxLevels + 1);
-    colorGroup(c, 6, unitBodies, &cnt->numManifolds, c->maxManifolds, exact, permuted, c->unitColor[6], c->unitOrder[6], contactColorStart, 6);
+    // colour reuse: a full colouring every `recolorEvery` steps, inherited colours in between (fast mode only)
+    static int recolorEvery = -1;
+    if (recolorEvery < 0) { const char* e = getenv("B200PHYS_RECOLOR_EVERY"); recolorEvery = e ? atoi(e) : 0; }     // tuning override
+    const int every = recolorEvery > 0 ? recolorEvery : (c->cfg.reserved[0] ? (int)c->cfg.reserved[0] : 8);
+    const bool fastColored = !exact && !permuted;
+    unsigned long long* keysCur = c->refKeys[c->refParity]; unsigned long long* keysRef = c->refKeys[c->refParity ^ 1];
+    bool inherit = false;
+    if (fastColored)
+    {
+        manifoldKeysKernel<<<G, kThreads, 0, c->stream>>>(c->collisions, c->wCol, keysCur, cnt);
+        c->launches++;
+        inherit = c->colorAge > 0 && c->colorAge < every;
+        if (inherit) { colorInheritKernel<<<G, kThreads, 0, c->stream>>>(keysCur, keysRef, c->refColors, c->colorKey, c->unitColor[6], cnt); c->launches++; }
+    }
+    colorGroup(c, 6, unitBodies, &cnt->numManifolds, c->maxManifolds, exact, permuted, inherit, c->unitColor[6], c->unitOrder[6], contactColorStart, 6);
+    if (fastColored)
+    {
+        colorRememberKernel<<<G, kThreads, 0, c->stream>>>(c->unitColor[6], c->refColors, cnt);
+        c->launches++;
+        c->refParity ^= 1;
+        c->colorAge = (c->colorAge + 1 >= every) ? 0 : c->colorAge + 1;
+    }
+    else c->colorAge = 0;       // another mode ran: the remembered colours are stale
     uint32_t* slotCount = c->pairDst;              // scratch reuse
     slotCountKernel<<<G, kThreads, 0, c->stream>>>(c->unitOrder[6], c->manifolds, slotCount, cnt);
     c->launches++;

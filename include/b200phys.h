@@ -194,7 +194,8 @@ typedef struct b200phys_config {
     float    cellSize;              /* 0: automatic (largest small-collider AABB extent) */
     float    bigFactor;             /* colliders whose AABB extent exceeds bigFactor * mean extent skip the grid (0: 3) */
     uint32_t maxContacts;           /* contact capacity            (0: 2 * maxManifolds + 1024) */
-    uint32_t reserved[5];
+    uint32_t reserved[5];           /* reserved[0]: fast mode colours the contact graph afresh every this many steps and lets the
+                                       manifolds inherit their colour in between (0: 8; 1: colour every step) */
 } b200phys_config;
 
 /* the five counters the reference publishes (physics.cpp:1258-1262) + capacities + per-stage device times */
