@@ -176,25 +176,37 @@ __global__ void __launch_bounds__(kLbThreads) scanLookbackKernel(const uint32_t*
             if (threadIdx.x == kLbThreads / 32 - 1) sTileTotal = wi;
         }
         __syncthreads();
-        if (threadIdx.x == 0)
-        {
+        if (threadIdx.x < 32)
+        {   // warp 0: publish the tile aggregate, then look back 32 predecessors at a time until an inclusive prefix is found
             const uint32_t total = sTileTotal;
             uint32_t prefix = 0;
-            if (tile == 0) atomicExch(&status[0], tagPre | total);
+            if (tile == 0) { if (threadIdx.x == 0) atomicExch(&status[0], tagPre | total); }
             else
             {
-                atomicExch(&status[tile], tagAgg | total);                 // publish the aggregate, then look back
-                for (uint32_t p = tile; p-- > 0; )
+                if (threadIdx.x == 0) atomicExch(&status[tile], tagAgg | total);
+                int32_t window = (int32_t)tile - 1;                            // nearest predecessor of this window
+                for (;;)
                 {
-                    unsigned long long st;
-                    do { asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(st) : "l"(status + p) : "memory"); } while ((st >> 34) != epoch || ((st >> 32) & 3ull) == 0ull);
-                    prefix += (uint32_t)st;
-                    if (((st >> 32) & 3ull) == 2ull) break;                  // an inclusive prefix ends the walk
+                    const int32_t p = window - (int32_t)threadIdx.x;
+                    unsigned long long st = tagPre;                            // lanes before tile 0 act as an empty prefix
+                    if (p >= 0)
+                        do { asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(st) : "l"(status + p) : "memory"); } while ((st >> 34) != epoch || ((st >> 32) & 3ull) == 0ull);
+                    const bool isPrefix = ((st >> 32) & 3ull) == 2ull;
+                    const uint32_t prefMask = __ballot_sync(0xffffffffu, isPrefix);
+                    const uint32_t first = prefMask ? (uint32_t)__ffs((int)prefMask) - 1u : 32u;     // nearest lane holding a prefix
+                    uint32_t v = (threadIdx.x <= first) ? (uint32_t)st : 0u;
+                    v = __reduce_add_sync(0xffffffffu, v);
+                    prefix += v;
+                    if (prefMask) break;
+                    window -= 32;
                 }
-                atomicExch(&status[tile], tagPre | (prefix + total));
+                if (threadIdx.x == 0) atomicExch(&status[tile], tagPre | (prefix + total));
             }
-            sPrefix = prefix;
-            if (tile == numTiles - 1) { out[n] = prefix + total; if (totalOut) *totalOut = prefix + total; }
+            if (threadIdx.x == 0)
+            {
+                sPrefix = prefix;
+                if (tile == numTiles - 1) { out[n] = prefix + total; if (totalOut) *totalOut = prefix + total; }
+            }
         }
         __syncthreads();
         uint32_t excl = sPrefix + warpSums[threadIdx.x >> 5] + (incl - local);
