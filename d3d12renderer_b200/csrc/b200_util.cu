@@ -246,9 +246,105 @@ void scanExclusiveU32(Context* c, const uint32_t* in, uint32_t* out, const uint3
     scanLookbackKernel<<<blocks, kLbThreads, 0, c->stream>>>(in, out, devCount, maxCount, c->scanStatus, (ScanLbState*)c->scanState, c->scanEpoch, totalOut);
     c->launches += 1;
 }
+// 64-bit variant (two packed 32-bit sums per element): the tile status is two self-validating words, (tag | low half) and
+// (tag | high half); a reader accepts a tile only when both words carry the same tag
+static const int kLb64Items = 4, kLb64Tile = kLbThreads * kLb64Items;
+__global__ void __launch_bounds__(kLbThreads) scanLookbackKernel64(const unsigned long long* __restrict__ in, unsigned long long* __restrict__ out, const uint32_t* __restrict__ devCount, uint32_t hostCount,
+                                                                   unsigned long long* __restrict__ status /* 2 words per tile */, ScanLbState* __restrict__ state, uint32_t epoch)
+{
+    __shared__ unsigned long long warpSums[kLbThreads / 32];
+    __shared__ unsigned long long sPrefix, sTileTotal; __shared__ uint32_t sTile;
+    const uint32_t n = devCount ? *devCount : hostCount;
+    const uint32_t numTiles = (n + kLb64Tile - 1) / kLb64Tile;
+    const unsigned long long tagAgg = ((unsigned long long)epoch << 34) | (1ull << 32), tagPre = ((unsigned long long)epoch << 34) | (2ull << 32);
+    for (;;)
+    {
+        if (threadIdx.x == 0) sTile = atomicAdd(&state->ticket, 1u);
+        __syncthreads();
+        const uint32_t tile = sTile;
+        if (tile >= numTiles) break;
+        const uint32_t base = tile * kLb64Tile + threadIdx.x * kLb64Items;
+        unsigned long long v[kLb64Items]; unsigned long long local = 0;
+#pragma unroll
+        for (int k = 0; k < kLb64Items; ++k) { v[k] = (base + k < n) ? in[base + k] : 0ull; local += v[k]; }
+        unsigned long long incl = local;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o); if (laneId() >= (uint32_t)o) incl += t; }
+        if (laneId() == 31) warpSums[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        if (threadIdx.x < 32)
+        {
+            const unsigned long long w = (threadIdx.x < kLbThreads / 32) ? warpSums[threadIdx.x] : 0ull;
+            unsigned long long wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const unsigned long long t = __shfl_up_sync(0xffffffffu, wi, o); if (laneId() >= (uint32_t)o) wi += t; }
+            if (threadIdx.x < kLbThreads / 32) warpSums[threadIdx.x] = wi - w;
+            if (threadIdx.x == kLbThreads / 32 - 1) sTileTotal = wi;
+        }
+        __syncthreads();
+        if (threadIdx.x < 32)
+        {
+            const unsigned long long total = sTileTotal;
+            unsigned long long prefix = 0;
+            auto publish = [&](unsigned long long tag, unsigned long long val)
+            { atomicExch(&status[2 * tile], tag | (val & 0xFFFFFFFFull)); atomicExch(&status[2 * tile + 1], tag | (val >> 32)); };
+            if (tile == 0) { if (threadIdx.x == 0) publish(tagPre, total); }
+            else
+            {
+                if (threadIdx.x == 0) publish(tagAgg, total);
+                int32_t window = (int32_t)tile - 1;
+                for (;;)
+                {
+                    const int32_t p = window - (int32_t)threadIdx.x;
+                    unsigned long long lo = tagPre, hi = tagPre;
+                    if (p >= 0)
+                        do
+                        {
+                            asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(lo) : "l"(status + 2 * p) : "memory");
+                            asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(hi) : "l"(status + 2 * p + 1) : "memory");
+                        } while ((lo >> 34) != epoch || ((lo >> 32) & 3ull) == 0ull || (lo >> 32) != (hi >> 32));
+                    const bool isPrefix = ((lo >> 32) & 3ull) == 2ull;
+                    const uint32_t prefMask = __ballot_sync(0xffffffffu, isPrefix);
+                    const uint32_t first = prefMask ? (uint32_t)__ffs((int)prefMask) - 1u : 32u;
+                    unsigned long long val = (threadIdx.x <= first) ? ((lo & 0xFFFFFFFFull) | (hi << 32)) : 0ull;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) val += __shfl_down_sync(0xffffffffu, val, o);
+                    val = __shfl_sync(0xffffffffu, val, 0);
+                    prefix += val;
+                    if (prefMask) break;
+                    window -= 32;
+                }
+                if (threadIdx.x == 0) publish(tagPre, prefix + total);
+            }
+            if (threadIdx.x == 0) { sPrefix = prefix; if (tile == numTiles - 1) out[n] = prefix + total; }
+        }
+        __syncthreads();
+        unsigned long long excl = sPrefix + warpSums[threadIdx.x >> 5] + (incl - local);
+#pragma unroll
+        for (int k = 0; k < kLb64Items; ++k) { if (base + k < n) out[base + k] = excl; excl += v[k]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0)
+    {
+        if (n == 0 && blockIdx.x == 0) out[0] = 0ull;
+        if (atomicAdd(&state->done, 1u) == gridDim.x - 1) { state->ticket = 0; state->done = 0; }
+    }
+}
+
 void scanExclusiveU64(Context* c, const unsigned long long* in, unsigned long long* out, const uint32_t* devCount, uint32_t maxCount, unsigned long long* totalOut)
 {
-    scanExclusive<unsigned long long>(c, in, out, devCount, maxCount, c->scanTmp64, totalOut);
+    if (maxCount == 0) return;
+    const uint32_t maxTiles = (maxCount + kLb64Tile - 1) / kLb64Tile;
+    if (2 * (size_t)maxTiles > c->scanStatusTiles || totalOut)
+    {
+        scanExclusive<unsigned long long>(c, in, out, devCount, maxCount, c->scanTmp64, totalOut);
+        return;
+    }
+    int blocks = gridFor(c, 4);
+    if ((uint32_t)blocks > maxTiles) blocks = (int)maxTiles;
+    c->scanEpoch = (c->scanEpoch + 1u) & 0x3FFFFFFFu; if (c->scanEpoch == 0) c->scanEpoch = 1;
+    scanLookbackKernel64<<<blocks, kLbThreads, 0, c->stream>>>(in, out, devCount, maxCount, c->scanStatus, (ScanLbState*)c->scanState, c->scanEpoch);
+    c->launches += 1;
 }
 
 // ------------------------------------------------------------------------------------------ stable small-key sort
