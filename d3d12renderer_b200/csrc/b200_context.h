@@ -145,6 +145,8 @@ struct Context
     unsigned long long* scanStatus = nullptr; uint32_t* scanState = nullptr; uint32_t scanStatusTiles = 0, scanEpoch = 0;   // single-pass scan
     unsigned long long* refKeys[2] = {}; uint8_t* refColors = nullptr; uint8_t* colorKey = nullptr; int refParity = 0, colorAge = 0;   // colour reuse across steps
     uint8_t* refColorsJoint[6] = {}; uint32_t jointColorCount[6] = {}; int jointColorAge[6] = {};
+    // the per-step accumulator upload runs on its own stream so that it overlaps the collision detection (b200phys_upload_forces)
+    cudaStream_t copyStream = nullptr; cudaEvent_t evCopyGate = nullptr, evForcesDone = nullptr; bool forcesPending = false; void* forceStaging = nullptr;
     uint32_t* colorQueue = nullptr;         // ready queue of the colouring (max units of any group)
     unsigned long long* bodyMask = nullptr; // colours taken at each body (current group)
     uint32_t* bodyBase = nullptr;           // units per body in the groups coloured so far
@@ -191,7 +193,8 @@ static inline int gridFor(const Context* c, int blocksPerSM = 8) { return c->num
 
 // ---- stage launchers (one per .cu file) ------------------------------------------------------------------------
 void launchUnpackBodies(Context* c, const void* devStaging, uint32_t count);
-void launchUnpackForces(Context* c, const void* devStaging, uint32_t count);
+void launchUnpackForces(Context* c, const void* devStaging, uint32_t count, cudaStream_t stream);
+void waitPendingForceUpload(Context* c);    // orders the context's stream behind an accumulator upload still running on the copy stream
 void launchUnpackBodyStates(Context* c, const void* devStaging, uint32_t count);
 void launchPackBodyStates(Context* c, void* devStaging, uint32_t count);
 void launchIntegrateForces(Context* c, float dt);

@@ -72,6 +72,7 @@ int allocateAll(Context& c)
     if (c.stagingBytes < C * 24) c.stagingBytes = C * 24;
     if (c.stagingBytes < 1024) c.stagingBytes = 1024;
     CK(devAlloc(c.staging, c.stagingBytes));
+    { float* fs = nullptr; CK(devAlloc(fs, (size_t)g.maxBodies * 6 + 8)); c.forceStaging = fs; }
     CK(devAlloc(c.counts, 1));
     CK(cudaMemset(c.counts, 0, sizeof(DeviceCounts)));
     CK(cudaHostAlloc((void**)&c.hostCounts, sizeof(DeviceCounts), cudaHostAllocDefault));
@@ -99,6 +100,9 @@ void freeAll(Context& c)
     for (int k = 0; k < 6; ++k) { if (c.jointIn[k]) cudaFree(c.jointIn[k]); if (c.jointBodies[k]) cudaFree(c.jointBodies[k]); if (c.jointRows[k]) cudaFree(c.jointRows[k]); }
     if (c.hostCounts) cudaFreeHost(c.hostCounts);
     for (int i = 0; i < 8; ++i) if (c.ev[i]) cudaEventDestroy(c.ev[i]);
+    if (c.copyStream) cudaStreamDestroy(c.copyStream);
+    if (c.evCopyGate) cudaEventDestroy(c.evCopyGate); if (c.evForcesDone) cudaEventDestroy(c.evForcesDone);
+    if (c.forceStaging) cudaFree(c.forceStaging);
     if (c.ownStream) cudaStreamDestroy(c.ownStream);
 }
 
@@ -149,6 +153,8 @@ int b200phys_create(const b200phys_config* config, b200phys_context** out)
     c.numSMs = prop.multiProcessorCount;
     if (!prop.cooperativeLaunch) { delete ctx; return -(int)cudaErrorNotSupported; }
     CK(cudaStreamCreateWithFlags(&c.ownStream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c.copyStream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&c.evCopyGate, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&c.evForcesDone, cudaEventDisableTiming));
     c.stream = c.ownStream;
     int r = allocateAll(c);
     if (r != 0) { freeAll(c); delete ctx; return r; }
@@ -210,6 +216,7 @@ int b200phys_upload_bodies(b200phys_context* ctx, const b200phys_body* bodies, u
     Context& c = ctx->c; CK(cudaSetDevice(c.device));
     if (count)
     {
+        waitPendingForceUpload(&c);                     // a full upload overwrites the accumulators too
         CK(cudaMemcpyAsync(c.staging, bodies, sizeof(b200phys_body) * (size_t)count, cudaMemcpyHostToDevice, c.stream));
         launchUnpackBodies(&c, c.staging, count);
     }
@@ -237,8 +244,15 @@ int b200phys_upload_forces(b200phys_context* ctx, const float* forceTorque6, uin
     Context& c = ctx->c; CK(cudaSetDevice(c.device));
     if (count)
     {
-        CK(cudaMemcpyAsync(c.staging, forceTorque6, 24 * (size_t)count, cudaMemcpyHostToDevice, c.stream));
-        launchUnpackForces(&c, c.staging, count);
+        // On the copy stream, gated behind everything already queued on the context's stream (the previous step, a state
+        // upload): the transfer and the unpack then overlap the next step's collision detection, which does not read the
+        // accumulators; the step waits for them right before the force integration (waitPendingForceUpload).
+        CK(cudaEventRecord(c.evCopyGate, c.stream));
+        CK(cudaStreamWaitEvent(c.copyStream, c.evCopyGate, 0));
+        CK(cudaMemcpyAsync(c.forceStaging, forceTorque6, 24 * (size_t)count, cudaMemcpyHostToDevice, c.copyStream));
+        launchUnpackForces(&c, c.forceStaging, count, c.copyStream);
+        CK(cudaEventRecord(c.evForcesDone, c.copyStream));
+        c.forcesPending = true;
     }
     CK(cudaGetLastError());
     return 0;
@@ -290,12 +304,14 @@ int b200phys_step(b200phys_context* ctx, float dt, uint32_t numSolverIterations,
     Context& c = ctx->c; CK(cudaSetDevice(c.device));
     c.launches = 0;
     if (c.timing) cudaEventRecord(c.ev[0], c.stream);
+    if (c.numNonCollisionColliders) waitPendingForceUpload(&c);   // force fields add to the accumulators during the narrow phase
     launchWorldColliders(&c);                               // physics.cpp:1217
     if (c.timing) cudaEventRecord(c.ev[1], c.stream);
     launchBroadphase(&c);                                   // physics.cpp:1222
     if (c.timing) cudaEventRecord(c.ev[2], c.stream);
     launchNarrowphase(&c);                                  // physics.cpp:1233
     if (c.timing) cudaEventRecord(c.ev[3], c.stream);
+    waitPendingForceUpload(&c);
     launchIntegrateForces(&c, dt);                          // physics.cpp:1266-1279
     launchCollisionEvents(&c);                              // physics.cpp:1284
     launchSolver(&c, dt, numSolverIterations, flags);       // physics.cpp:1316-1334 (records ev[4] before the iterations)
@@ -408,6 +424,7 @@ int b200phys_synchronize(b200phys_context* ctx)
 {
     if (!ctx) return B200PHYS_E_INVALID;
     CK(cudaSetDevice(ctx->c.device));
+    if (ctx->c.forcesPending) CK(cudaStreamSynchronize(ctx->c.copyStream));     // an accumulator upload no step has consumed yet
     CK(cudaStreamSynchronize(ctx->c.stream));
     return 0;
 }

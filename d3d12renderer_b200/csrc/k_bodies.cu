@@ -293,10 +293,14 @@ void launchUnpackBodies(Context* c, const void* dev, uint32_t count)
     unpackBodiesKernel<<<gridFor(c, 4), kThreads, 0, c->stream>>>((const float*)dev, count, c->bRot, c->bPos, c->bCog, c->bInvI, c->bVel, c->bAng, c->bForce, c->bTorque, stride);
     c->launches++;
 }
-void launchUnpackForces(Context* c, const void* dev, uint32_t count)
+void waitPendingForceUpload(Context* c)
+{
+    if (c->forcesPending) { cudaStreamWaitEvent(c->stream, c->evForcesDone, 0); c->forcesPending = false; }
+}
+void launchUnpackForces(Context* c, const void* dev, uint32_t count, cudaStream_t stream)
 {
     if (!count) return;
-    unpackForcesKernel<<<gridFor(c, 4), kThreads, 0, c->stream>>>((const float*)dev, count, c->bForce, c->bTorque);
+    unpackForcesKernel<<<gridFor(c, 4), kThreads, 0, stream>>>((const float*)dev, count, c->bForce, c->bTorque);
     c->launches++;
 }
 void launchUnpackBodyStates(Context* c, const void* dev, uint32_t count)

@@ -224,6 +224,7 @@ uint32_t b200phys_halo_record_bytes(int which) { return which == 0 ? kHaloBodyFl
 // device buffers (e.g. torch tensors); returns the counts through outCounts[2] = {bodies, colliders} (host, synchronous).
 static int haloPackDevice(Context& c, int axis, float lo, float hi, void* dstBodies, void* dstColliders, uint32_t capBodies, uint32_t capColliders, uint32_t* header, uint32_t* hostCounts)
 {
+    waitPendingForceUpload(&c);     // the body records carry the accumulators
     const uint32_t N = c.numOwnedBodies, C = c.numOwnedColliders;
     // current world AABBs of the owned colliders (the step recomputes them, ghosts included)
     const uint32_t savedB = c.numBodies, savedC = c.numColliders;
@@ -328,6 +329,7 @@ int b200phys_migrate_pack(b200phys_context* ctx, int axis, float lo, float hi, v
     Context& c = ctx->c; CK(cudaSetDevice(c.device));
     for (int k = 0; k < 6; ++k) if (c.numJoints[k]) return B200PHYS_E_INVALID;
     if (c.numBodies != c.numOwnedBodies || c.numColliders != c.numOwnedColliders) return B200PHYS_E_INVALID;   // drop the ghosts first (b200phys_halo_clear)
+    waitPendingForceUpload(&c);
     const uint32_t N = c.numOwnedBodies, C = c.numOwnedColliders;
     outCounts[0] = outCounts[1] = outCounts[2] = outCounts[3] = 0;
     char* msg[2] = { (char*)dstMessageDown, (char*)dstMessageUp };

@@ -232,7 +232,10 @@ int b200phys_upload_joints(b200phys_context* ctx, int kind, const void* joints, 
 /* pose + velocities only (the per-step mutable state, same struct b200phys_download_bodies writes); mass properties, damping and
  * accumulators keep their uploaded values. count must equal the uploaded body count */
 int b200phys_upload_body_states(b200phys_context* ctx, const b200phys_body_state* states, uint32_t count);
-/* accumulators only (what gameplay code mutates between steps: physics.cpp:626-627); count must equal the uploaded body count */
+/* accumulators only (what gameplay code mutates between steps: physics.cpp:626-627); count must equal the uploaded body count.
+ * The transfer runs on the context's copy stream and overlaps the collision detection of the next b200phys_step, which waits for
+ * it right before the force integration: with page-locked host memory (b200phys_host_alloc) the buffer must stay untouched until
+ * that step (or b200phys_synchronize) has returned; pageable memory is staged by the driver before this call returns. */
 int b200phys_upload_forces(b200phys_context* ctx, const float* forceTorque6, uint32_t count);
 
 /* the step: physicsStepInternal (physics.cpp:1180-1362) ------------------------------------------------------------- */
