@@ -310,3 +310,17 @@ def test_accumulator_upload_overlapping_the_step_matches_the_oracle():
         st.step(DT, 10, abi.STEP_EXACT_ORDER); orc.step(DT, 10)
         states = st.download_bodies()
         assert_states_close(states, orc.body_states(), 1e-4)
+
+
+def test_permuted_order_and_inherited_colours_replayed_by_the_oracle():
+    """The two set-up shortcuts of the fast path leave the parity contract untouched: B200PHYS_STEP_PERMUTED (pseudo-random order, no
+    colouring) and inherited colours (steps 2..8 after a full colouring) both export the order they used, and the oracle replaying
+    that order lands on the same state."""
+    sc = scenes.sphere_pile_settled(8, 6, 8)
+    r = run_both(sc, iterations=10, flags=abi.STEP_PERMUTED, steps=3)
+    check_detection(r)
+    assert sorted(r["order"].tolist()) == list(range(len(r["order"])))          # a permutation of the manifolds
+    assert_states_close(r["gpu_states"], r["ref_states"], 1e-4)
+    r = run_both(sc, iterations=10, flags=abi.STEP_FAST, steps=11)                  # crosses a re-colouring (every 8 steps)
+    check_detection(r)
+    assert_states_close(r["gpu_states"], r["ref_states"], 1e-4)
