@@ -31,9 +31,9 @@ DT = np.float32(1.0 / 120.0)
 # algorithmic bytes: per contact and solver iteration: row 120 + 2 x 28 read, 8 + 2 x 24 written
 B_KITER = 232.0
 # DRAM traffic of one solveKernel launch on the N=1 workload (778 k contacts, 10 iterations), from one `ncu --set full` capture:
-# dram__bytes_read.sum 1.010558 GB + dram__bytes_write.sum 12.06 MB (profiles/r01_final_cfg2_ncu_full_summary.txt). Below the
+# dram__bytes_read.sum 985.9 MB + dram__bytes_write.sum 11.6 MB (profiles/r01_final_solve_ncu_full_summary.txt). Below the
 # algorithmic 1.80 GB because the 32-byte body records mostly hit in L2.
-NCU_SOLVE_DRAM_BYTES = 1.010558e9 + 12.058624e6
+NCU_SOLVE_DRAM_BYTES = 985.903616e6 + 11.636224e6
 B_GRID, B_PAIR_OUT = 136.0, 8.0
 CPU_SAMPLE_DIMS = (32, 16, 32)   # 16 384 spheres: the largest pile the reference's uint16 collider indices allow (<= 32 767)
 
@@ -277,7 +277,7 @@ def main():
                     "d2h_bytes_per_step": int(n_bodies * abi.body_state_dtype.itemsize)},
             "gpu_launches": int(launches_per_step * K),
             "roofline": {"bound": "hbm", "kernel": "solveKernel (PGS iterations)", "achieved": solve_gbs, "peak": peak, "unit": "GB/s", "frac": solve_gbs / peak,
-                         "traffic": NCU_SOLVE_DRAM_BYTES if world == 1 else None, "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of solveKernel, ncu --set full on this workload (profiles/r01_final_cfg2_ncu_full_summary.txt)", "peak_source": peak_src, "algorithmic_bytes_per_launch": solve_bytes, "launch_ms": acc[4],
+                         "traffic": NCU_SOLVE_DRAM_BYTES if world == 1 else None, "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of solveKernel, ncu --set full on this workload (profiles/r01_final_solve_ncu_full_summary.txt)", "peak_source": peak_src, "algorithmic_bytes_per_launch": solve_bytes, "launch_ms": acc[4],
                          "broad_phase": {"achieved": broad_gbs, "frac": broad_gbs / peak, "algorithmic_bytes": broad_bytes, "ms": acc[1]}},
             "stage_ms": {"world": acc[0], "broad": acc[1], "narrow": acc[2], "init": acc[3], "solve": acc[4], "integrate": acc[5], "total": acc[6]},
             "clocks": clock_info,
