@@ -97,6 +97,7 @@ def cpu_reference_sample(steps, warmup):
     """The reference's scalar CPU algorithm (oracle restatement) on a pile it can address (uint16 collider indices),
     same lattice and density as the GPU workload; 1 thread like the reference's step."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.setdefault("B200_ORACLE_VARIANT", "fast")   # timing build: -O2 -mavx2 -mfma -ffast-math like the reference's /arch:AVX2 /fp:fast
     import oracle_lib
     from d3d12renderer_b200 import scenes
     sc = scenes.sphere_pile_settled(*CPU_SAMPLE_DIMS, seed=519431)
@@ -127,7 +128,7 @@ def run_reference(args, rank, world):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": "262144-sphere settled pile (BASELINE configs[1]), 10 PGS iterations, dt 1/120", "bodies": total_bodies, "iterations": ITERATIONS},
         "cpu_baseline": {"value": s["body_steps_per_s"], "unit": "body-steps/s", "cores": 1, "kind": "port",
-                         "sample": "%d-sphere pile of the same lattice (the reference's uint16 indices cap colliders at 32767), %d steps, scalar oracle restatement, 1 thread; %d contacts; stage ms %s"
+                         "sample": "%d-sphere pile of the same lattice (the reference's uint16 indices cap colliders at 32767), %d steps, oracle restatement built -mavx2 -mfma -ffast-math (the reference's /arch:AVX2 /fp:fast), 1 thread like the reference's step; %d contacts; stage ms %s"
                                    % (s["bodies"], steps, s["contacts"], json.dumps(s["stage_ms"]))},
         "e2e": {"value": s["body_steps_per_s"], "unit": "body-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -262,7 +263,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         s = cpu_reference_sample(20, 2)
         cpu = {"value": s["body_steps_per_s"], "unit": "body-steps/s", "cores": 1, "kind": "port",
-               "sample": "%d-sphere pile of the same lattice (reference uint16 collider limit), %d steps in %.1f s, scalar oracle restatement, 1 thread" % (s["bodies"], s["steps"], s["seconds"])}
+               "sample": "%d-sphere pile of the same lattice (reference uint16 collider limit), %d steps in %.1f s, oracle restatement built -mavx2 -mfma -ffast-math (the reference's /arch:AVX2 /fp:fast), 1 thread like the reference's step" % (s["bodies"], s["steps"], s["seconds"])}
 
     if rank == 0:
         line = {

@@ -23,7 +23,15 @@ def load():
         return _lib
     if not os.path.exists(LIB):
         build()
-    lib = C.CDLL(LIB)
+    path = LIB
+    if os.environ.get("B200_ORACLE_VARIANT") == "fast":      # bench.py only: the AVX2 / fast-math build as the CPU timing baseline
+        fast = os.path.join(ORACLE_DIR, "liboracle_fast.so")
+        if os.path.exists(fast):
+            path = fast
+    try:
+        lib = C.CDLL(path)
+    except OSError:
+        lib = C.CDLL(LIB)
     vp, u32, f32 = C.c_void_p, C.c_uint32, C.c_float
     lib.oracle_create.restype = vp
     for name in ["oracle_destroy", "oracle_stage_detect", "oracle_stage_world_and_aabbs"]:
