@@ -26,7 +26,11 @@ def load():
     path = LIB
     if os.environ.get("B200_ORACLE_VARIANT") == "fast":      # bench.py only: the AVX2 / fast-math build as the CPU timing baseline
         fast = os.path.join(ORACLE_DIR, "liboracle_fast.so")
-        if os.path.exists(fast):
+        try:
+            flags = open("/proc/cpuinfo").read()
+        except OSError:
+            flags = ""
+        if os.path.exists(fast) and " avx2" in flags and " fma" in flags:      # never risk an illegal instruction inside the bench process
             path = fast
     try:
         lib = C.CDLL(path)
