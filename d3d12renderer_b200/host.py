@@ -42,6 +42,7 @@ def load_library():
     lib.b200host_event_log_counts.argtypes = [C.POINTER(u32)]; lib.b200host_event_log_counts.restype = u32
     lib.b200host_event_log_get.argtypes = [vp, vp, vp]
     lib.b200host_trigger_log.argtypes = [vp, u32, C.c_int]; lib.b200host_trigger_log.restype = u32
+    lib.b200host_save_yaml.argtypes = [vp, C.c_char_p]; lib.b200host_load_yaml.argtypes = [vp, C.c_char_p]
     lib.b200host_get_render_transforms.argtypes = [vp, vp]
     lib.b200host_get_stats.argtypes = [vp, C.POINTER(abi.Stats)]
     _lib = lib
@@ -130,6 +131,18 @@ class HostScene:
         out = np.zeros((n, 3), dtype=np.uint32)
         self.lib.b200host_trigger_log(_p(out), n, 1 if clear else 0)
         return out
+
+    def save_yaml(self, path):
+        """Writes the physics components in the reference's scene-file layout (serialization_yaml.cpp)."""
+        if self.lib.b200host_save_yaml(self.ptr, str(path).encode()):
+            raise IOError("cannot write %s" % path)
+
+    def load_yaml(self, path):
+        """Adds the entities of a reference scene file (physics components only); returns how many were created."""
+        n = self.lib.b200host_load_yaml(self.ptr, str(path).encode())
+        if n < 0:
+            raise IOError("%s is not a scene file" % path)
+        return n
 
     def render_transforms(self):
         out = np.zeros((self.lib.b200host_num_bodies(self.ptr), 7), dtype=np.float32)

@@ -1,6 +1,7 @@
 // host_c_api.cpp -- C entry points over the host mirror for the Python tests / bench: synthetic scene builders for the
 // BASELINE.json configurations, flat-array export, and the physicsStep() driver.
 #include "physics_host.h"
+#include <fstream>
 #include <cstring>
 #include <memory>
 
@@ -197,6 +198,18 @@ void b200host_mass_properties(void* s, const b200phys_collider* c, float* inerti
     }
     physics_properties p = col.calculatePhysicsProperties(*(game_scene*)s);
     memcpy(inertia9, p.inertia.m, 36); cog3[0] = p.cog.x; cog3[1] = p.cog.y; cog3[2] = p.cog.z; *mass = p.mass;
+}
+
+// scene files: the physics components of the reference's YAML scenes (scene_yaml.cpp); 0 on success
+int b200host_save_yaml(void* s, const char* path)
+{
+    std::ofstream f(path);
+    return f && saveSceneYaml(*(game_scene*)s, f, "b200host") ? 0 : 1;
+}
+int b200host_load_yaml(void* s, const char* path)       // entities created, -1 on failure
+{
+    std::ifstream f(path);
+    return f ? loadSceneYaml(*(game_scene*)s, f) : -1;
 }
 
 // physicsStep(scene, arena, timer, settings, dt) through the host mirror (needs the CUDA library and a GPU)

@@ -12,6 +12,7 @@
 #include <functional>
 #include <string>
 #include <vector>
+#include <iosfwd>
 #include "../csrc/b200_math.cuh"       // the same fp32 helpers the kernels use (host + device)
 #include "../../include/b200phys.h"
 
@@ -212,6 +213,10 @@ struct humanoid_ragdoll
 };
 
 // physics.h:405 : returns 0 or the C ABI error code of the failing call (the reference returns void)
+// scene files (physics components of the reference's YAML scenes, src/scene/serialization_yaml.cpp): scene_yaml.cpp
+bool saveSceneYaml(const game_scene& scene, std::ostream& out, const char* sceneName = nullptr);
+int loadSceneYaml(game_scene& scene, std::istream& in);      // entities created, -1 if the input has no "Entities" list
+
 int physicsStep(game_scene& scene, memory_arena& arena, float& timer, const physics_settings& settings, float dt);
 
 } // namespace b200host

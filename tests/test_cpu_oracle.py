@@ -282,3 +282,52 @@ def test_oracle_trigger_and_force_field_scene_is_pinned():
         assert len(np.unique(e, axis=0)) == len(e)          # de-duplicated per (trigger, body)
     assert (te, tl, inter) == (92, 51, 7046)
     assert orc.narrow_stats()["asserts"] == 0
+
+
+def test_scene_yaml_round_trip_and_reference_style_file(tmp_path):
+    """Host mirror scene files (physics components of the reference's YAML scenes, serialization_yaml.cpp:74-240,395-520): a saved
+    scene loads back to the same bodies / colliders; a hand-written file in the reference's layout (with the renderer keys a real
+    scene carries) loads its physics components and ignores the rest."""
+    from d3d12renderer_b200 import host
+    sc = host.build_scene(host.CONFIG_EVENT_SCENE, 3, 1, 2, seed=5, mode=0, spacing=1.5)
+    path = tmp_path / "scene.yaml"
+    sc["host_scene"].save_yaml(path)
+    back = host.HostScene(); n = back.load_yaml(path)
+    a, b = sc["host_scene"].arrays(), back.arrays()
+    assert n == 6 + 1 + 3 and len(b["bodies"]) == len(a["bodies"]) == 6          # spheres, ground, trigger / wind / global wind
+    for f in ("rotation", "position", "invMass", "invInertia", "localCOGPosition", "gravityFactor", "linearDamping", "angularDamping"):
+        assert np.allclose(a["bodies"][f], b["bodies"][f], rtol=1e-6, atol=1e-7), f
+    # the trigger callback is code, not data: its collider comes back as a static one; everything else is identical
+    ca, cb = a["colliders"], b["colliders"]
+    assert len(ca) == len(cb) and np.array_equal(ca["type"], cb["type"]) and np.allclose(ca["shape"], cb["shape"], atol=1e-6)
+    assert np.allclose(ca["friction"], cb["friction"]) and np.array_equal(ca["objectType"] == abi.OBJ_RIGID_BODY, cb["objectType"] == abi.OBJ_RIGID_BODY)
+    assert (cb["objectType"] == abi.OBJ_FORCE_FIELD).sum() == 1
+
+    ref = tmp_path / "reference_style.yaml"
+    ref.write_text(
+        "Scene: test\n"
+        "Camera:\n  Position: [0, 3, 8]\n  Near plane: 0.1\n"
+        "Sun:\n  Color: [1, 0.93, 0.76]\n  Cascades: 3\n"
+        "Entities:\n"
+        "  - Tag: Ball\n"
+        "    Transform:\n      Position: [1, 2.5, -3]\n      Rotation: [0, 0, 0, 1]\n      Scale: [1, 1, 1]\n"
+        "    Dynamic: true\n"
+        "    Mesh:\n      Handle: 1234\n      Flags: 1\n"
+        "    Rigid body:\n      Local COG: [0, 0, 0]\n      Inv mass: 1.9098593\n      Inv inertia: [19.098593, 0, 0, 0, 19.098593, 0, 0, 0, 19.098593]\n"
+        "      Gravity factor: 1\n      Linear damping: 0.4\n      Angular damping: 0.4\n"
+        "    Colliders:\n"
+        "      - Type: Sphere\n        Center: [0, 0, 0]\n        Radius: 0.5\n        Restitution: 0.1\n        Friction: 0.5\n        Density: 1\n"
+        "  - Tag: Platform\n"
+        "    Transform:\n      Position: [0, -4, 0]\n      Rotation: [0, 0, 0, 1]\n      Scale: [1, 1, 1]\n"
+        "    Colliders:\n"
+        "      - Type: AABB\n        Min corner: [-30, -4, -30]\n        Max corner: [30, 4, 30]\n        Restitution: 0.1\n        Friction: 1\n        Density: 4\n"
+        "      - Type: OBB\n        Center: [0, 5, 0]\n        Radius: [1, 0.5, 2]\n        Rotation: [0, 0.38268343, 0, 0.92387953]\n        Restitution: 0.1\n        Friction: 1\n        Density: 4\n"
+        "  - Tag: Lamp\n    Point light:\n      Color: [1, 1, 1]\n      Intensity: 20\n")
+    hs = host.HostScene(); assert hs.load_yaml(ref) == 3
+    arr = hs.arrays()
+    assert len(arr["bodies"]) == 1 and np.allclose(arr["bodies"]["position"][0], (1, 2.5, -3))
+    assert abs(float(arr["bodies"]["invMass"][0]) - 1.9098593) < 1e-5             # recomputed from the unit-density sphere: the same value
+    col = arr["colliders"]
+    assert len(col) == 3 and sorted(col["type"].tolist()) == [abi.SPHERE, abi.AABB, abi.OBB]
+    obb = col[col["type"] == abi.OBB][0]
+    assert np.allclose(obb["shape"][0:4], (0, 0.38268343, 0, 0.92387953)) and np.allclose(obb["shape"][7:10], (1, 0.5, 2))
