@@ -324,3 +324,22 @@ def test_permuted_order_and_inherited_colours_replayed_by_the_oracle():
     r = run_both(sc, iterations=10, flags=abi.STEP_FAST, steps=11)                  # crosses a re-colouring (every 8 steps)
     check_detection(r)
     assert_states_close(r["gpu_states"], r["ref_states"], 1e-4)
+
+
+def test_capacity_overflow_is_reported_not_fatal():
+    """Errors are returned, never trapped: a context created too small for the scene's pair / manifold
+    count keeps stepping, reports B200PHYS_E_CAPACITY through get_stats with the overflow counters set, and the bodies stay finite;
+    a context that is large enough reports nothing."""
+    sc = scenes.sphere_pile_settled(8, 6, 8)
+    small = make_stepper(sc, max_pairs=512, max_manifolds=256)
+    for _ in range(3):
+        small.step(DT, 10, abi.STEP_FAST)
+    with pytest.raises(abi.B200PhysError):
+        small.stats()
+    s = small.stats(check=False)
+    assert s.overflowPairs == 1 and s.numBroadphaseOverlaps <= 512
+    assert np.all(np.isfinite(small.download_bodies()["position"]))
+    ok = make_stepper(sc)
+    ok.step(DT, 10, abi.STEP_FAST)
+    s = ok.stats()
+    assert s.overflowPairs == 0 and s.overflowManifolds == 0 and s.overflowGrid == 0
