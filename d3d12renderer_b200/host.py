@@ -152,6 +152,49 @@ class HostScene:
         st = abi.Stats(); self.lib.b200host_get_stats(self.ptr, C.byref(st)); return st
 
 
+class LocomotionEnv:
+    """Batched version of the reference's RL environment (learned_locomotion.cpp:393-488): E ragdolls, one GPU physics step for all.
+    reset() / step(actions [E, 27]) -> states [E, 66], rewards [E], failed [E] (a failed environment must be reset by the caller)."""
+
+    def __init__(self, num_envs, spacing=4.0):
+        self.lib = load_library()
+        lib = self.lib
+        lib.b200env_create.restype = C.c_void_p; lib.b200env_create.argtypes = [C.c_uint32, C.c_float]
+        lib.b200env_destroy.argtypes = [C.c_void_p]
+        lib.b200env_state_size.restype = C.c_uint32; lib.b200env_action_size.restype = C.c_uint32
+        lib.b200env_reset.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        lib.b200env_reward.argtypes = [C.c_void_p, C.c_uint32]; lib.b200env_reward.restype = C.c_float
+        lib.b200env_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.b200env_ranges.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        self.num_envs = int(num_envs)
+        self.state_size = int(lib.b200env_state_size()); self.action_size = int(lib.b200env_action_size())
+        self.ptr = C.c_void_p(lib.b200env_create(self.num_envs, spacing))
+
+    def close(self):
+        if self.ptr:
+            self.lib.b200env_destroy(self.ptr); self.ptr = None
+
+    def reset(self, index=-1):
+        n = self.num_envs if index < 0 else 1
+        out = np.zeros((n, self.state_size), dtype=np.float32)
+        self.lib.b200env_reset(self.ptr, int(index), _p(out)); return out
+
+    def reward(self, index):
+        return float(self.lib.b200env_reward(self.ptr, int(index)))
+
+    def action_ranges(self):
+        lo = np.zeros(self.action_size, dtype=np.float32); hi = np.zeros(self.action_size, dtype=np.float32)
+        self.lib.b200env_ranges(self.ptr, _p(lo), _p(hi)); return lo, hi
+
+    def step(self, actions):
+        a = np.ascontiguousarray(actions, dtype=np.float32).reshape(self.num_envs, self.action_size)
+        states = np.zeros((self.num_envs, self.state_size), dtype=np.float32); rewards = np.zeros(self.num_envs, dtype=np.float32); failed = np.zeros(self.num_envs, dtype=np.int32)
+        rc = self.lib.b200env_step(self.ptr, _p(a), _p(states), _p(rewards), _p(failed))
+        if rc:
+            raise abi.B200PhysError("physicsStep failed inside the environment: %d" % rc)
+        return states, rewards, failed.astype(bool)
+
+
 def build_scene(config, nx, ny=1, nz=1, seed=1, mode=0, spacing=1.25):
     hs = HostScene().build_config(config, nx, ny, nz, seed, mode, spacing)
     sc = hs.arrays(); sc["host_scene"] = hs

@@ -1,0 +1,261 @@
+// locomotion_env.cpp -- the reference's RL environment (src/learning/learned_locomotion.{h,cpp}) over the host mirror, batched:
+// E humanoid ragdolls stand on one ground box, far enough apart never to touch, and ONE physicsStep (one b200phys_step on the GPU)
+// advances all of them; state, reward and failure test are the reference's formulas evaluated per environment on the host from the
+// downloaded poses. The single-environment C interface the reference exports to Python (learned_locomotion.cpp:393-488:
+// getPhysicsStateSize / getPhysicsActionSize / getPhysicsRanges / resetPhysics / updatePhysics) is the E = 1 case.
+// Not reproduced: the random pushes (testPhysicsInteraction ray casts with probability 0.02 per step, :448-458).
+#include "physics_host.h"
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+namespace b200host {
+
+namespace {
+
+const uint32_t kParts = 14, kConeTwists = 7, kHinges = 6;
+const uint32_t kActionFloats = kConeTwists * 3 + kHinges;            // learning_action (learned_locomotion.h:19-35)
+const uint32_t kStateFloats = 13 * 3 + kActionFloats;                // learning_state (:44-67)
+enum { torso, head, lUpperArm, lLowerArm, rUpperArm, rLowerArm, lUpperLeg, lLowerLeg, lFoot, lToes, rUpperLeg, rLowerLeg, rFoot, rToes };
+const int kParent[kParts] = { -1, torso, torso, lUpperArm, torso, rUpperArm, torso, lUpperLeg, lLowerLeg, lFoot, torso, rUpperLeg, rLowerLeg, rFoot };   // ragdoll.cpp:156-169
+const float kPi = 3.14159265358979323846f;
+
+vec3 transformPositionT(const trs& m, vec3 p) { return m.rotation * (m.scale * p) + m.position; }                       // math.cpp:518-521
+vec3 inverseTransformPositionT(const trs& m, vec3 p) { vec3 q = conjugate(m.rotation) * (p - m.position); return b200::mk3(q.x / m.scale.x, q.y / m.scale.y, q.z / m.scale.z); }
+vec3 inverseTransformDirectionT(const trs& m, vec3 d) { return conjugate(m.rotation) * d; }
+
+struct Env
+{
+    humanoid_ragdoll ragdoll;
+    float lastSmoothedAction[kActionFloats];
+    float headTargetHeight; vec3 torsoVelocityTarget;
+    vec3 localPositions[kParts][6];
+    vec3 targetPositions[kParts][6], targetVelocities[kParts][6]; quat localTargetRotation[kParts];
+    trs initialTransform[kParts];
+    uint32_t firstBody, firstConeTwist, firstHinge;
+};
+
+} // namespace
+
+struct locomotion_env_batch
+{
+    game_scene scene; std::vector<Env> envs; float physicsTimer = 0.f;
+
+    const trs& partTransform(const Env& e, int part) const { return scene.physicsTransform1[e.firstBody + part]; }
+    const rigid_body_component& partBody(const Env& e, int part) const { return scene.rigidBodies[e.firstBody + part]; }
+    vec3 globalCOG(const Env& e, int part) const { const trs& t = partTransform(e, part); return t.position + t.rotation * partBody(e, part).localCOGPosition; }   // rigid_body.cpp:83-86
+
+    // learned_locomotion::getCoordinateSystem (:113-120): torso COG projected to the ground, identity rotation
+    trs coordinateSystem(const Env& e) const { vec3 cog = globalCOG(e, torso); cog.y = 0.f; return makeTrs(cog); }
+
+    // training_locomotion::getLocalPositions (:191-250): the six face centres of the part's local collider bounds
+    void localPositions(Env& e, int part)
+    {
+        vec3 mn = b200::mk3(3.4e38f), mx = b200::mk3(-3.4e38f);
+        auto grow = [&](vec3 p) { mn = b200::mk3(fminf(mn.x, p.x), fminf(mn.y, p.y), fminf(mn.z, p.z)); mx = b200::mk3(fmaxf(mx.x, p.x), fmaxf(mx.y, p.y), fmaxf(mx.z, p.z)); };
+        const game_scene::entity_data& d = scene.entities[e.ragdoll.bodyParts[part].handle];
+        for (entity_handle c = d.firstColliderEntity; c != null_entity; c = scene.colliders[c].nextEntity)
+        {
+            const collider_component& col = scene.colliders[c];
+            if (col.type == collider_type_sphere) { grow(col.sphere.center - b200::mk3(col.sphere.radius)); grow(col.sphere.center + b200::mk3(col.sphere.radius)); }
+            else if (col.type == collider_type_capsule)
+            {
+                const vec3 r3 = b200::mk3(col.capsule.radius);
+                grow(col.capsule.positionA + r3); grow(col.capsule.positionA - r3); grow(col.capsule.positionB + r3); grow(col.capsule.positionB - r3);
+            }
+            else if (col.type == collider_type_aabb) { grow(col.aabb.minCorner); grow(col.aabb.maxCorner); }
+        }
+        const vec3 c = (mn + mx) * 0.5f, r = (mx - mn) * 0.5f;
+        e.localPositions[part][0] = c - b200::mk3(r.x, 0.f, 0.f); e.localPositions[part][1] = c - b200::mk3(0.f, r.y, 0.f); e.localPositions[part][2] = c - b200::mk3(0.f, 0.f, r.z);
+        e.localPositions[part][3] = c + b200::mk3(r.x, 0.f, 0.f); e.localPositions[part][4] = c + b200::mk3(0.f, r.y, 0.f); e.localPositions[part][5] = c + b200::mk3(0.f, 0.f, r.z);
+    }
+    vec3 pointVelocity(const Env& e, int part, vec3 localP) const
+    {   // rigid_body_component::getGlobalPointVelocity (rigid_body.cpp:88-93)
+        const trs& t = partTransform(e, part); const rigid_body_component& rb = partBody(e, part);
+        return rb.linearVelocity + cross(rb.angularVelocity, transformPositionT(t, localP) - globalCOG(e, part));
+    }
+    quat localRotation(const Env& e, int part) const
+    {
+        const quat parentRotation = kParent[part] >= 0 ? partTransform(e, kParent[part]).rotation : b200::qIdentity();
+        return partTransform(e, part).rotation * conjugate(parentRotation);
+    }
+
+    // learned_locomotion::updateConstraint (:71-90) for every joint of the environment
+    void applyAction(Env& e, const float* action)
+    {   // :92-111 : exponential smoothing with beta = 0.1, then position motors with 200 Nm
+        for (uint32_t i = 0; i < kActionFloats; ++i) e.lastSmoothedAction[i] += (action[i] - e.lastSmoothedAction[i]) * 0.1f;     // lerp(out, in, beta)
+        for (uint32_t i = 0; i < kConeTwists; ++i)
+        {
+            cone_twist_constraint& c = scene.coneTwistConstraints[e.firstConeTwist + i]; const float* a = e.lastSmoothedAction + 3 * i;
+            c.maxSwingMotorTorque = 200.f; c.maxTwistMotorTorque = 200.f;
+            c.swingMotorType = constraint_position_motor; c.twistMotorType = constraint_position_motor;
+            c.twistMotorVelocityOrTargetAngle = a[0]; c.swingMotorVelocityOrTargetAngle = a[1]; c.swingMotorAxis = a[2];
+        }
+        for (uint32_t i = 0; i < kHinges; ++i)
+        {
+            hinge_constraint& c = scene.hingeConstraints[e.firstHinge + i];
+            c.maxMotorTorque = 200.f; c.motorType = constraint_position_motor; c.motorVelocityOrTargetAngle = e.lastSmoothedAction[3 * kConeTwists + i];
+        }
+        scene.jointsDirty = true;
+    }
+
+    // learned_locomotion::getState (:131-146) + hasFallen (:148-151)
+    bool getState(const Env& e, float* out) const
+    {
+        const trs cs = coordinateSystem(e);
+        vec3* v = reinterpret_cast<vec3*>(out);
+        auto read = [&](int part, vec3& pos, vec3& vel) { pos = inverseTransformPositionT(cs, globalCOG(e, part)); vel = inverseTransformDirectionT(cs, partBody(e, part).linearVelocity); };
+        v[0] = inverseTransformDirectionT(cs, partBody(e, torso).linearVelocity);       // cogVelocity
+        read(lToes, v[1], v[2]); read(rToes, v[3], v[4]); read(torso, v[5], v[6]); read(head, v[7], v[8]); read(lLowerArm, v[9], v[10]); read(rLowerArm, v[11], v[12]);
+        memcpy(out + 39, e.lastSmoothedAction, sizeof(float) * kActionFloats);
+        return v[7].y < 1.f;
+    }
+
+    // training_locomotion::getReward (:329-355) with readPartDifference (:284-311)
+    float getReward(const Env& e) const
+    {
+        float positionError = 0.f, velocityError = 0.f, rotationError = 0.f;
+        for (uint32_t p = 0; p < kParts; ++p)
+        {
+            const trs& t = partTransform(e, p);
+            for (int i = 0; i < 6; ++i)
+            {
+                positionError += b200::len(transformPositionT(t, e.localPositions[p][i]) - e.targetPositions[p][i]);
+                velocityError += b200::len(pointVelocity(e, p, e.localPositions[p][i]) - e.targetVelocities[p][i]);
+            }
+            const quat diff = e.localTargetRotation[p] * conjugate(localRotation(e, p));
+            rotationError += 2.f * acosf(fminf(fmaxf(diff.w, -1.f), 1.f));
+        }
+        const float vcmError = b200::len(partBody(e, torso).linearVelocity - e.torsoVelocityTarget);
+        const float rp = expf(-10.f / kParts * positionError), rv = expf(-1.f / kParts * velocityError), rlocal = expf(-10.f / kParts * rotationError), rvcm = expf(-vcmError);
+        const float headHeight = partTransform(e, head).position.y;
+        const float fall = fminf(fmaxf(1.3f - 1.4f * (e.headTargetHeight - headHeight), 0.f), 1.f);
+        return fall * (rp + rv + rlocal + rvcm);
+    }
+
+    // resetPhysics (:436-460) for one environment: initial pose, zero velocities, training targets from that pose, zero action
+    void reset(uint32_t index)
+    {
+        Env& e = envs[index];
+        for (uint32_t p = 0; p < kParts; ++p)
+        {
+            const uint32_t b = e.firstBody + p;
+            scene.physicsTransform0[b] = scene.physicsTransform1[b] = e.initialTransform[p];
+            scene.entities[scene.rigidBodyEntity[b]].transform = e.initialTransform[p];
+            rigid_body_component& rb = scene.rigidBodies[b];
+            rb.linearVelocity = rb.angularVelocity = rb.forceAccumulator = rb.torqueAccumulator = b200::mk3(0.f);
+        }
+        for (uint32_t p = 0; p < kParts; ++p)
+        {   // training_locomotion::reset (:313-324): targets = the pose right now
+            localPositions(e, p);
+            for (int i = 0; i < 6; ++i) { e.targetPositions[p][i] = transformPositionT(partTransform(e, p), e.localPositions[p][i]); e.targetVelocities[p][i] = pointVelocity(e, p, e.localPositions[p][i]); }
+            e.localTargetRotation[p] = localRotation(e, p);
+        }
+        memset(e.lastSmoothedAction, 0, sizeof(e.lastSmoothedAction));          // learned_locomotion::reset (:36-43)
+        const float zero[kActionFloats] = {};
+        applyAction(e, zero);
+        e.headTargetHeight = partTransform(e, head).position.y;
+        e.torsoVelocityTarget = b200::mk3(0.f);
+    }
+
+    void create(uint32_t numEnvs, float spacing)
+    {
+        const uint32_t side = (uint32_t)ceilf(sqrtf((float)numEnvs));
+        const float half = (side - 1) * spacing * 0.5f;
+        physics_material groundMaterial = { physics_material_type_metal, 0.1f, 1.f, 4.f };
+        envs.resize(numEnvs);
+        for (uint32_t i = 0; i < numEnvs; ++i)
+        {
+            Env& e = envs[i];
+            e.firstBody = (uint32_t)scene.rigidBodies.size(); e.firstConeTwist = (uint32_t)scene.coneTwistConstraints.size(); e.firstHinge = (uint32_t)scene.hingeConstraints.size();
+            e.ragdoll = humanoid_ragdoll::create(scene, b200::mk3((i % side) * spacing - half, 1.25f, (i / side) * spacing - half));
+            for (uint32_t p = 0; p < kParts; ++p) e.initialTransform[p] = scene.physicsTransform1[e.firstBody + p];
+        }
+        const float ext = fmaxf(20.f, half + 10.f);
+        scene.createEntity("Test ground").addTransform(b200::mk3(0.f, -4.f, 0.f)).addCollider(collider_component::asAABB(bounding_box::fromCenterRadius(b200::mk3(0.f), b200::mk3(ext, 4.f, ext)), groundMaterial));
+        for (uint32_t i = 0; i < numEnvs; ++i) reset(i);
+    }
+
+    // updatePhysics (:462-488) for all environments: apply the actions, ONE 60 Hz physics step, read state / reward / failure
+    int step(const float* actions, float* outStates, float* outRewards, int* outFailed)
+    {
+        for (uint32_t i = 0; i < envs.size(); ++i) applyAction(envs[i], actions + (size_t)i * kActionFloats);
+        physics_settings settings; settings.frameRate = 60;
+        memory_arena arena; physicsTimer = 0.f;
+        const int rc = physicsStep(scene, arena, physicsTimer, settings, 1.f / (float)settings.frameRate);
+        if (rc) return rc;
+        for (uint32_t i = 0; i < envs.size(); ++i)
+        {
+            const bool failed = getState(envs[i], outStates + (size_t)i * kStateFloats);
+            outFailed[i] = failed ? 1 : 0;
+            outRewards[i] = failed ? 0.f : getReward(envs[i]);
+        }
+        return 0;
+    }
+};
+
+} // namespace b200host
+
+using namespace b200host;
+
+extern "C" {
+
+// ---- batched interface
+void* b200env_create(uint32_t numEnvs, float spacing) { locomotion_env_batch* b = new locomotion_env_batch(); b->create(numEnvs ? numEnvs : 1, spacing > 0.f ? spacing : 4.f); return b; }
+void b200env_destroy(void* env) { delete (locomotion_env_batch*)env; }
+uint32_t b200env_state_size(void) { return kStateFloats; }
+uint32_t b200env_action_size(void) { return kActionFloats; }
+uint32_t b200env_num_envs(void* env) { return (uint32_t)((locomotion_env_batch*)env)->envs.size(); }
+// index < 0: every environment; writes the state(s) after the reset
+void b200env_reset(void* env, int index, float* outStates)
+{
+    locomotion_env_batch& b = *(locomotion_env_batch*)env;
+    for (uint32_t i = 0; i < b.envs.size(); ++i)
+        if (index < 0 || (uint32_t)index == i) { b.reset(i); if (outStates) b.getState(b.envs[i], outStates + (size_t)(index < 0 ? i : 0) * kStateFloats); }
+}
+float b200env_reward(void* env, uint32_t index) { locomotion_env_batch& b = *(locomotion_env_batch*)env; return b.getReward(b.envs[index]); }
+int b200env_step(void* env, const float* actions, float* outStates, float* outRewards, int* outFailed) { return ((locomotion_env_batch*)env)->step(actions, outStates, outRewards, outFailed); }
+// action limits from the joints' own limits (getLimits, learned_locomotion.cpp:357-383); the state is unbounded
+void b200env_ranges(void* env, float* actionMin, float* actionMax)
+{
+    locomotion_env_batch& b = *(locomotion_env_batch*)env; const Env& e = b.envs[0];
+    uint32_t k = 0;
+    for (uint32_t i = 0; i < kConeTwists; ++i)
+    {
+        const cone_twist_constraint& c = b.scene.coneTwistConstraints[e.firstConeTwist + i];
+        actionMin[k] = c.twistLimit >= 0.f ? -c.twistLimit : -kPi; actionMax[k++] = c.twistLimit >= 0.f ? c.twistLimit : kPi;
+        actionMin[k] = c.swingLimit >= 0.f ? -c.swingLimit : -kPi; actionMax[k++] = c.swingLimit >= 0.f ? c.swingLimit : kPi;
+        actionMin[k] = -kPi; actionMax[k++] = kPi;
+    }
+    for (uint32_t i = 0; i < kHinges; ++i)
+    {
+        const hinge_constraint& c = b.scene.hingeConstraints[e.firstHinge + i];
+        actionMin[k] = c.minRotationLimit <= 0.f ? c.minRotationLimit : -kPi; actionMax[k++] = c.maxRotationLimit >= 0.f ? c.maxRotationLimit : kPi;
+    }
+}
+
+// ---- the reference's five functions (learned_locomotion.cpp:393-488), one environment
+static locomotion_env_batch* gSingle = nullptr;
+int getPhysicsStateSize(void) { return (int)kStateFloats; }
+int getPhysicsActionSize(void) { return (int)kActionFloats; }
+void getPhysicsRanges(float* stateMin, float* stateMax, float* actionMin, float* actionMax)
+{
+    for (uint32_t i = 0; i < kStateFloats; ++i) { stateMin[i] = -3.402823466e38f; stateMax[i] = 3.402823466e38f; }
+    locomotion_env_batch tmp; tmp.create(1, 4.f);
+    b200env_ranges(&tmp, actionMin, actionMax);
+}
+void resetPhysics(float* outState)
+{
+    if (!gSingle) { gSingle = new locomotion_env_batch(); gSingle->create(1, 4.f); }
+    gSingle->reset(0);
+    if (outState) gSingle->getState(gSingle->envs[0], outState);
+}
+int updatePhysics(float* action, float* outState, float* outReward)
+{
+    if (!gSingle) resetPhysics(nullptr);
+    int failed = 0;
+    const int rc = gSingle->step(action, outState, outReward, &failed);
+    return rc ? 1 : failed;
+}
+
+} // extern "C"

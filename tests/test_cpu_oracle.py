@@ -331,3 +331,31 @@ def test_scene_yaml_round_trip_and_reference_style_file(tmp_path):
     assert len(col) == 3 and sorted(col["type"].tolist()) == [abi.SPHERE, abi.AABB, abi.OBB]
     obb = col[col["type"] == abi.OBB][0]
     assert np.allclose(obb["shape"][0:4], (0, 0.38268343, 0, 0.92387953)) and np.allclose(obb["shape"][7:10], (1, 0.5, 2))
+
+
+def test_locomotion_env_sizes_ranges_reset_state_and_reward():
+    """The RL environment of learned_locomotion.{h,cpp} over the host mirror (host/locomotion_env.cpp), the parts that need no GPU:
+    state / action sizes (learning_state 13 vec3 + the smoothed action, learning_action 7 cone-twist x 3 + 6 hinge), action limits
+    from the ragdoll's joint limits (getLimits :357-383), the state right after a reset (positions relative to the torso COG
+    projected to the ground, :113-146) and the reward of the reset pose (all error terms zero: fall * 4, :329-355)."""
+    from d3d12renderer_b200 import host
+    env = host.LocomotionEnv(4, spacing=5.0)
+    assert (env.state_size, env.action_size) == (66, 27)
+    lo, hi = env.action_ranges()
+    d = np.deg2rad
+    # neck: twist 90, swing 50; shoulders: twist 90, swing 130; hips: no swing limit given twist 30 -> (-1 => pi); ankles: twist 20, swing 75
+    assert np.allclose(hi[0:3], (d(90), d(50), np.pi), atol=1e-6) and np.allclose(lo[0:3], (-d(90), -d(50), -np.pi), atol=1e-6)
+    assert np.allclose(hi[9:12], (d(30), np.pi, np.pi), atol=1e-6)                 # left hip: swingLimit -1 means unlimited
+    assert np.allclose(lo[21:27], d([-5, -5, -90, -45, -90, -45]), atol=1e-6) and np.allclose(hi[21:27], d([85, 85, 5, 45, 5, 45]), atol=1e-6)
+    s = env.reset()
+    assert s.shape == (4, 66) and np.allclose(s, s[0], atol=1e-5)                  # every environment starts in the same pose, in its own frame
+    st = s[0]
+    assert np.allclose(st[0:3], 0) and np.allclose(st[39:66], 0)                   # at rest, zero smoothed action
+    torso_pos, head_pos = st[15:18], st[21:24]
+    assert abs(torso_pos[0]) < 1e-6 and abs(torso_pos[2]) < 1e-6 and torso_pos[1] > 1.25      # the frame origin is the torso COG on the ground
+    assert abs(head_pos[1] - (1.25 + 0.42 * 1.45)) < 1e-5 and head_pos[1] > 1.0               # head at hip height + 0.42 * 1.45
+    left_toes, right_toes = st[3:6], st[9:12]
+    assert abs(left_toes[0] + right_toes[0]) < 1e-5 and left_toes[0] < 0 < right_toes[0] and left_toes[2] < 0   # mirrored, toes in front (-z)
+    for i in range(4):
+        assert abs(env.reward(i) - 4.0) < 5e-3            # acos near 1 turns rounding in the rotation term into ~1e-3
+    env.close()

@@ -343,3 +343,29 @@ def test_capacity_overflow_is_reported_not_fatal():
     ok.step(DT, 10, abi.STEP_FAST)
     s = ok.stats()
     assert s.overflowPairs == 0 and s.overflowManifolds == 0 and s.overflowGrid == 0
+
+
+def test_batched_locomotion_env_steps_on_the_gpu():
+    """host/locomotion_env.cpp: 16 ragdoll environments advanced by one physicsStep per call (60 Hz, 30 solver iterations like
+    updatePhysics, learned_locomotion.cpp:462-488). Zero actions hold the reset pose with 200 Nm position motors; random actions make
+    the figures fall, which shows as failed = head below 1 m; resetting one environment restores its reset state and reward."""
+    env = host.LocomotionEnv(16, spacing=5.0)
+    s0 = env.reset()
+    lo, hi = env.action_ranges()
+    states, rewards, failed = env.step(np.zeros((16, 27), dtype=np.float32))
+    assert states.shape == (16, 66) and np.all(np.isfinite(states)) and not failed.any()
+    assert np.all(rewards > 2.0) and np.all(rewards <= 4.0 + 1e-4)
+    assert np.allclose(states[:, 21:24], s0[:, 21:24], atol=0.05)                  # heads have barely moved after 1/60 s
+    assert np.abs(states - states[0]).max() < 0.02                                  # same figure in every environment (solver order noise only)
+    rng = np.random.default_rng(3)
+    ever_failed = np.zeros(16, dtype=bool)
+    for _ in range(120):
+        a = rng.uniform(lo, hi, size=(16, 27)).astype(np.float32)
+        states, rewards, failed = env.step(a)
+        assert np.all(np.isfinite(states)) and np.all(rewards >= 0.0)
+        assert np.array_equal(failed, states[:, 22] < 1.0) and np.all(rewards[failed] == 0.0)
+        ever_failed |= failed
+    assert ever_failed.sum() >= 8                                                    # flailing figures fall within two seconds
+    again = env.reset(3)
+    assert np.allclose(again[0], s0[3], atol=1e-5) and abs(env.reward(3) - 4.0) < 5e-3
+    env.close()
