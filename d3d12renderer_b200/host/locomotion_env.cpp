@@ -21,23 +21,6 @@ enum { torso, head, lUpperArm, lLowerArm, rUpperArm, rLowerArm, lUpperLeg, lLowe
 const int kParent[kParts] = { -1, torso, torso, lUpperArm, torso, rUpperArm, torso, lUpperLeg, lLowerLeg, lFoot, torso, rUpperLeg, rLowerLeg, rFoot };   // ragdoll.cpp:156-169
 const float kPi = 3.14159265358979323846f;
 
-// the per-environment loops (action smoothing, state, reward) are independent: spread them over the host cores
-template <typename F> void parallelFor(uint32_t n, F&& f)
-{
-    const uint32_t hw = std::thread::hardware_concurrency();
-    const uint32_t workers = n < 256 ? 1u : (hw ? (hw > 32u ? 32u : hw) : 1u);
-    if (workers <= 1) { for (uint32_t i = 0; i < n; ++i) f(i); return; }
-    std::vector<std::thread> pool;
-    const uint32_t chunk = (n + workers - 1) / workers;
-    for (uint32_t w = 0; w < workers; ++w)
-    {
-        const uint32_t b = w * chunk, e = b + chunk < n ? b + chunk : n;
-        if (b >= e) break;
-        pool.emplace_back([b, e, &f]() { for (uint32_t i = b; i < e; ++i) f(i); });
-    }
-    for (std::thread& t : pool) t.join();
-}
-
 vec3 transformPositionT(const trs& m, vec3 p) { return m.rotation * (m.scale * p) + m.position; }                       // math.cpp:518-521
 vec3 inverseTransformPositionT(const trs& m, vec3 p) { vec3 q = conjugate(m.rotation) * (p - m.position); return b200::mk3(q.x / m.scale.x, q.y / m.scale.y, q.z / m.scale.z); }
 vec3 inverseTransformDirectionT(const trs& m, vec3 d) { return conjugate(m.rotation) * d; }
@@ -196,7 +179,7 @@ struct locomotion_env_batch
     // updatePhysics (:462-488) for all environments: apply the actions, ONE 60 Hz physics step, read state / reward / failure
     int step(const float* actions, float* outStates, float* outRewards, int* outFailed)
     {
-        parallelFor((uint32_t)envs.size(), [&](uint32_t i) { applyAction(envs[i], actions + (size_t)i * kActionFloats); });
+        parallelFor((uint32_t)envs.size(), [&](uint32_t i) { applyAction(envs[i], actions + (size_t)i * kActionFloats); }, 256u);
         scene.jointsDirty = true;
         physics_settings settings; settings.frameRate = 60;
         memory_arena arena; physicsTimer = 0.f;
@@ -207,7 +190,7 @@ struct locomotion_env_batch
             const bool failed = getState(envs[i], outStates + (size_t)i * kStateFloats);
             outFailed[i] = failed ? 1 : 0;
             outRewards[i] = failed ? 0.f : getReward(envs[i]);
-        });
+        }, 256u);
         return 0;
     }
 };

@@ -201,22 +201,28 @@ scene_entity& scene_entity::addRigidBody(bool kinematic, float gravityFactor, fl
     if (!d.hasTransform) { d.transform = makeTrs(mk3(0.f)); }
     scene->physicsTransform0[d.rigidBody] = d.transform; scene->physicsTransform1[d.rigidBody] = d.transform;
     scene->recalculateProperties(handle);
+    scene->jointPairsDirty = true;      // joints of this entity now resolve to a body index
     scene->collidersDirty = true;
     return *this;
 }
 rigid_body_component& scene_entity::rigidBody() { return scene->rigidBodies[scene->entities[handle].rigidBody]; }
 trs& scene_entity::transform() { return scene->entities[handle].transform; }
 
-game_scene::~game_scene() { if (ctx) { b200phys_destroy(ctx); ctx = nullptr; } }
+game_scene::~game_scene()
+{
+    if (stageBodies) b200phys_host_free(stageBodies);
+    if (stageStates) b200phys_host_free(stageStates);
+    if (ctx) { b200phys_destroy(ctx); ctx = nullptr; }
+}
 
 // ------------------------------------------------------------------------------------------------------- gather
 static void st3(float* o, vec3 v) { o[0] = v.x; o[1] = v.y; o[2] = v.z; }
 static void st4(float* o, quat q) { o[0] = q.x; o[1] = q.y; o[2] = q.z; o[3] = q.w; }
 
-void game_scene::gatherBodies(std::vector<b200phys_body>& out) const
+void game_scene::gatherBodies(std::vector<b200phys_body>& out) const { out.resize(rigidBodies.size()); gatherBodies(out.data()); }
+void game_scene::gatherBodies(b200phys_body* out) const
 {   // rbGlobal[] is filled in rigid-body storage order (physics.cpp:1269-1274)
-    out.resize(rigidBodies.size());
-    for (size_t i = 0; i < rigidBodies.size(); ++i)
+    parallelFor((uint32_t)rigidBodies.size(), [&](uint32_t i)
     {
         const rigid_body_component& rb = rigidBodies[i]; const trs& t = physicsTransform1[i]; b200phys_body& b = out[i];
         st4(b.rotation, t.rotation); st3(b.position, t.position); st3(b.localCOGPosition, rb.localCOGPosition);
@@ -224,7 +230,7 @@ void game_scene::gatherBodies(std::vector<b200phys_body>& out) const
         b.gravityFactor = rb.gravityFactor; b.linearDamping = rb.linearDamping; b.angularDamping = rb.angularDamping;
         st3(b.linearVelocity, rb.linearVelocity); st3(b.angularVelocity, rb.angularVelocity);
         st3(b.forceAccumulator, rb.forceAccumulator); st3(b.torqueAccumulator, rb.torqueAccumulator);
-    }
+    });
 }
 
 void game_scene::gatherColliders(std::vector<b200phys_collider>& outC, std::vector<b200phys_transform>& outT) const
@@ -289,6 +295,33 @@ void game_scene::gatherJoints(int kind, std::vector<uint8_t>& outStructs, std::v
     }
 }
 
+const void* game_scene::jointStructs(int kind, size_t& n) const
+{
+    switch (kind)
+    {
+    case 0: n = distanceConstraints.size(); return distanceConstraints.data();
+    case 1: n = ballConstraints.size(); return ballConstraints.data();
+    case 2: n = fixedConstraints.size(); return fixedConstraints.data();
+    case 3: n = hingeConstraints.size(); return hingeConstraints.data();
+    case 4: n = coneTwistConstraints.size(); return coneTwistConstraints.data();
+    default: n = sliderConstraints.size(); return sliderConstraints.data();
+    }
+}
+void game_scene::refreshJointPairs()
+{   // body indices = rigid body storage indices (physics.cpp:789-805); they only change when joints or bodies are added
+    for (int kind = 0; kind < 6; ++kind)
+    {
+        const size_t n = constraintEntities[kind].size();
+        jointPairs[kind].resize(n);
+        for (size_t i = 0; i < n; ++i)
+        {
+            jointPairs[kind][i].rbA = (uint32_t)entities[constraintEntities[kind][i].rbA].rigidBody;
+            jointPairs[kind][i].rbB = (uint32_t)entities[constraintEntities[kind][i].rbB].rigidBody;
+        }
+    }
+    jointPairsDirty = false;
+}
+
 void game_scene::gatherHulls(std::vector<float>& verts, std::vector<uint32_t>& offsets) const
 {
     verts.clear(); offsets.assign(1, 0u);
@@ -301,7 +334,8 @@ void game_scene::gatherHulls(std::vector<float>& verts, std::vector<uint32_t>& o
 
 void game_scene::scatterBodyStates(const b200phys_body_state* s, uint32_t count)
 {   // integrateVelocity's outputs (rigid_body.cpp:126-142): physics_transform1 + velocities; accumulators cleared
-    for (uint32_t i = 0; i < count && i < rigidBodies.size(); ++i)
+    const uint32_t n = count < (uint32_t)rigidBodies.size() ? count : (uint32_t)rigidBodies.size();
+    parallelFor(n, [&](uint32_t i)
     {
         rigid_body_component& rb = rigidBodies[i]; trs& t = physicsTransform1[i];
         t.rotation = mkq(s[i].rotation[0], s[i].rotation[1], s[i].rotation[2], s[i].rotation[3]);
@@ -309,7 +343,7 @@ void game_scene::scatterBodyStates(const b200phys_body_state* s, uint32_t count)
         rb.linearVelocity = mk3(s[i].linearVelocity[0], s[i].linearVelocity[1], s[i].linearVelocity[2]);
         rb.angularVelocity = mk3(s[i].angularVelocity[0], s[i].angularVelocity[1], s[i].angularVelocity[2]);
         rb.forceAccumulator = mk3(0.f); rb.torqueAccumulator = mk3(0.f);
-    }
+    });
 }
 
 // ------------------------------------------------------------------------------------------------------- joints
@@ -318,7 +352,7 @@ static vec3 inverseTransformDirection(const trs& m, vec3 dir) { return conjugate
 
 static uint32_t pushPair(game_scene& s, int kind, scene_entity& a, scene_entity& b)
 {
-    s.constraintEntities[kind].push_back({ a.handle, b.handle }); s.jointsDirty = true;
+    s.constraintEntities[kind].push_back({ a.handle, b.handle }); s.jointsDirty = true; s.jointPairsDirty = true;
     return (uint32_t)s.constraintEntities[kind].size() - 1;
 }
 
@@ -497,8 +531,18 @@ static int physicsStepInternal(game_scene& scene, const physics_settings& settin
         r = b200phys_set_hulls(scene.ctx, v.data(), o.data(), (uint32_t)o.size() - 1); if (r) return r;
         scene.hullsDirty = false;
     }
-    std::vector<b200phys_body> bodies; scene.gatherBodies(bodies);
-    r = b200phys_upload_bodies(scene.ctx, bodies.data(), (uint32_t)bodies.size()); if (r) return r;
+    const uint32_t numBodies = (uint32_t)scene.rigidBodies.size();
+    if (numBodies > scene.stageCapacity)
+    {   // page-locked staging, kept across steps
+        if (scene.stageBodies) b200phys_host_free(scene.stageBodies);
+        if (scene.stageStates) b200phys_host_free(scene.stageStates);
+        scene.stageCapacity = numBodies + (numBodies >> 2) + 16;
+        scene.stageBodies = (b200phys_body*)b200phys_host_alloc(sizeof(b200phys_body) * (size_t)scene.stageCapacity);
+        scene.stageStates = (b200phys_body_state*)b200phys_host_alloc(sizeof(b200phys_body_state) * (size_t)scene.stageCapacity);
+        if (!scene.stageBodies || !scene.stageStates) return B200PHYS_E_INVALID;
+    }
+    scene.gatherBodies(scene.stageBodies);
+    r = b200phys_upload_bodies(scene.ctx, scene.stageBodies, numBodies); if (r) return r;
     if (scene.collidersDirty)
     {
         std::vector<b200phys_collider> cols; std::vector<b200phys_transform> xf; scene.gatherColliders(cols, xf);
@@ -509,8 +553,9 @@ static int physicsStepInternal(game_scene& scene, const physics_settings& settin
     {   // joint parameters (motor targets etc.) are host-mutable between steps (learned_locomotion.cpp:73-91): re-upload every step
         for (int k = 0; k < 6; ++k)
         {
-            std::vector<uint8_t> s; std::vector<b200phys_body_pair> p; scene.gatherJoints(k, s, p);
-            r = b200phys_upload_joints(scene.ctx, k, s.data(), p.data(), (uint32_t)p.size()); if (r) return r;
+            if (scene.jointPairsDirty) scene.refreshJointPairs();
+            size_t n = 0; const void* structs = scene.jointStructs(k, n);        // straight from the scene's arrays
+            r = b200phys_upload_joints(scene.ctx, k, structs, scene.jointPairs[k].data(), (uint32_t)n); if (r) return r;
         }
         scene.jointsDirty = false;
     }
@@ -580,9 +625,8 @@ static int physicsStepInternal(game_scene& scene, const physics_settings& settin
             if (t.callback) t.callback(trigger_event{ scene.triggerEntity[e.triggerIndex], scene.rigidBodyEntity[e.rigidBodyIndex], leave ? trigger_event_leave : trigger_event_enter });
         }
     }
-    std::vector<b200phys_body_state> states(bodies.size());
-    r = b200phys_download_bodies(scene.ctx, states.data(), (uint32_t)states.size()); if (r) return r;
-    scene.scatterBodyStates(states.data(), (uint32_t)states.size());
+    r = b200phys_download_bodies(scene.ctx, scene.stageStates, numBodies); if (r) return r;
+    scene.scatterBodyStates(scene.stageStates, numBodies);
     r = b200phys_get_stats(scene.ctx, &scene.lastStats);
     return r;
 }

@@ -12,6 +12,7 @@
 #include <functional>
 #include <string>
 #include <vector>
+#include <thread>
 #include <iosfwd>
 #include "../csrc/b200_math.cuh"       // the same fp32 helpers the kernels use (host + device)
 #include "../../include/b200phys.h"
@@ -138,6 +139,23 @@ struct physics_settings
     collision_end_event_func collisionEndCallback;
 };
 
+// independent per-element loops (gather / scatter / per-environment work) spread over the host cores
+template <typename F> inline void parallelFor(uint32_t n, F&& f, uint32_t minParallel = 4096u)
+{
+    const uint32_t hw = std::thread::hardware_concurrency();
+    const uint32_t workers = n < minParallel ? 1u : (hw ? (hw > 32u ? 32u : hw) : 1u);
+    if (workers <= 1) { for (uint32_t i = 0; i < n; ++i) f(i); return; }
+    std::vector<std::thread> pool;
+    const uint32_t chunk = (n + workers - 1) / workers;
+    for (uint32_t w = 0; w < workers; ++w)
+    {
+        const uint32_t b = w * chunk, e = b + chunk < n ? b + chunk : n;
+        if (b >= e) break;
+        pool.emplace_back([b, e, &f]() { for (uint32_t i = b; i < e; ++i) f(i); });
+    }
+    for (std::thread& t : pool) t.join();
+}
+
 struct memory_arena {};   // the reference's per-step scratch source (core/memory.h:52-112); device scratch lives in the context
 
 struct bounding_hull_geometry { std::vector<vec3> vertices; std::vector<indexed_triangle32> faces; };
@@ -183,6 +201,9 @@ struct game_scene
 
     // ---- boundary (what the EnTT shim of INTEGRATION.md does with real pools)
     void gatherBodies(std::vector<b200phys_body>& out) const;
+    void gatherBodies(b200phys_body* out) const;                 // out holds rigidBodies.size() entries
+    const void* jointStructs(int kind, size_t& count) const;    // the constraint structs ARE the boundary structs: no copy
+    void refreshJointPairs();
     void gatherColliders(std::vector<b200phys_collider>& outColliders, std::vector<b200phys_transform>& outTransforms) const;
     void gatherJoints(int kind, std::vector<uint8_t>& outStructs, std::vector<b200phys_body_pair>& outPairs) const;
     void gatherHulls(std::vector<float>& verts, std::vector<uint32_t>& offsets) const;
@@ -191,6 +212,9 @@ struct game_scene
     b200phys_context* ctx = nullptr;  // lazily created device context (registry context variable in the reference's terms)
     bool collidersDirty = true, jointsDirty = true, hullsDirty = true;
     b200phys_stats lastStats;
+    // page-locked staging reused from step to step (gather -> upload, download -> scatter) and the cached joint body pairs
+    b200phys_body* stageBodies = nullptr; b200phys_body_state* stageStates = nullptr; uint32_t stageCapacity = 0;
+    std::vector<b200phys_body_pair> jointPairs[6]; bool jointPairsDirty = true;
     ~game_scene();
 };
 
