@@ -49,7 +49,6 @@ struct DeviceCounts
     uint32_t numOverlapPairs, numInteractions;   // rigid body vs trigger / force field pairs tested / overlapping this step
     uint32_t numPrevCollisions, numBeginEvents, numEndEvents;   // collision event layer (k_events.cu)
     uint32_t solverAbort;               // set when the dataflow sweep gave up (inconsistent dependency records)
-    uint32_t remaining;                 // colouring work counter
     uint32_t overflowPairs, overflowManifolds, overflowGrid, overflowColors, overflowBig, overflowHalo;
     uint32_t epaOverflows, gjkIterationCaps, assertCount;
     unsigned long long extentSumFixed;  // sum of AABB extents, 2^-16 fixed point (deterministic mean)
@@ -57,7 +56,6 @@ struct DeviceCounts
     uint32_t maxSmallExtentBits;        // float bits (non-negative floats order like uints)
     uint32_t centreMinBits[3], centreMaxBits[3]; // sortable-uint encoded floats
     GridParams grid;
-    uint32_t barrier[8][32];            // grid barrier words of the cooperative kernels ([0] arrivals, [16] release flag)
 };
 
 template <typename T> struct DevBuf { T* p = nullptr; size_t n = 0; };

@@ -38,22 +38,4 @@ B200_D uint32_t laneMaskLt() { uint32_t m; asm("mov.u32 %0, %%lanemask_lt;" : "=
 B200_D uint32_t floatToSortable(float f) { uint32_t u = __float_as_uint(f); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); }
 B200_D float sortableToFloat(uint32_t u) { u = (u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u; return __uint_as_float(u); }
 
-// Grid-wide barrier for cooperative (co-resident) launches: one monotone arrival counter in HBM/L2 (bar[0], zero at kernel
-// start). Every CTA arrives with one fire-and-forget atomic (RED) and polls the counter until all CTAs of this epoch have
-// arrived. Release: __threadfence before the arrive; acquire: ld.acquire on the poll. Grids are kept at 1-2 fat CTAs per
-// SM (148..296 arrivals) so the single address is not a bottleneck (measured ~2 us per barrier on B200).
-B200_D void gridBarrier(uint32_t* bar, uint32_t& epoch)
-{
-    __syncthreads();
-    if (threadIdx.x == 0)
-    {
-        __threadfence();
-        atomicAdd(bar, 1u);
-        const uint32_t target = (epoch + 1u) * gridDim.x;
-        while (ldAcquireU32(bar) < target) { __nanosleep(20); }
-    }
-    ++epoch;
-    __syncthreads();
-}
-
 } // namespace b200

@@ -455,7 +455,6 @@ int b200phys_get_stats(b200phys_context* ctx, b200phys_stats* out)
     out->epaOverflows = d.epaOverflows; out->gjkIterationCaps = d.gjkIterationCaps; out->assertCount = d.assertCount;
     out->cellSize = d.grid.cellSize;
     out->kernelLaunches = c.launches;
-    out->reserved[0] = d.remaining;   // colouring rounds of the last group (diagnostic)
     if (c.timing && c.stepped)
     {
         float ms[6] = {};

@@ -681,7 +681,6 @@ struct JointCounts { uint32_t n[6]; };
 __global__ void solverResetKernel(DeviceCounts* cnt, JointCounts jc)
 {
     if (threadIdx.x < kNumGroups) cnt->numColors[threadIdx.x] = 0;
-    for (int b = 0; b < 8; ++b) cnt->barrier[b][threadIdx.x] = 0;
     if (threadIdx.x < 6) cnt->numJoints[threadIdx.x] = jc.n[threadIdx.x];
     if (threadIdx.x == 0) cnt->solverAbort = 0;
 }

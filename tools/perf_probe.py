@@ -17,7 +17,7 @@ def probe(sc, iters=10, steps=30, label="", flags=0):
             v = np.array([s_.msWorld, s_.msBroad, s_.msNarrow, s_.msInit, s_.msSolve, s_.msIntegrate, s_.msTotal])
             acc = v if acc is None else acc + v; n += 1
     acc /= n
-    print("%s N=%d pairs=%d manifolds=%d contacts=%d colors=%d cells=%d cellSize=%.3f big=%d launches=%d rounds=%d" % (label, nb, s_.numBroadphaseOverlaps, s_.numCollisions, s_.numContacts, s_.numColors[6], s_.numGridCells, s_.cellSize, s_.numBigColliders, s_.kernelLaunches, s_.reserved[0]))
+    print("%s N=%d pairs=%d manifolds=%d contacts=%d colors=%d cells=%d cellSize=%.3f big=%d launches=%d" % (label, nb, s_.numBroadphaseOverlaps, s_.numCollisions, s_.numContacts, s_.numColors[6], s_.numGridCells, s_.cellSize, s_.numBigColliders, s_.kernelLaunches))
     print("   ms: world %.3f broad %.3f narrow %.3f init %.3f solve %.3f integrate %.3f total %.3f  -> %.1f steps/s" % (*acc, 1000.0/acc[6]))
     st.close()
 
