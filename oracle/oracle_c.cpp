@@ -205,6 +205,20 @@ int oracle_collide_pair(oracle_ctx* c, const b200phys_collider* a, const b200phy
     return (int)m.n;
 }
 
+// boolean overlap test of two colliders (overlapCheck, collision_narrow.cpp:1593-1689): 1 / 0
+int oracle_overlap_pair(oracle_ctx* c, const b200phys_collider* a, const b200phys_collider* b)
+{
+    Oracle tmp; tmp.hulls = c->o.hulls;
+    tmp.colliders.push_back(*a); tmp.colliders.push_back(*b);
+    tmp.colliders[0].objectType = O_STATIC; tmp.colliders[1].objectType = O_STATIC;
+    tmp.colliders[0].parentTransform = B200PHYS_NO_TRANSFORM; tmp.colliders[1].parentTransform = B200PHYS_NO_TRANSFORM;
+    tmp.worldColliders();
+    WCol A = tmp.wcol[0], B = tmp.wcol[1];
+    if (!(A.type < B.type)) std::swap(A, B);
+    NarrowStats st;
+    return overlapOnly(A, B, st) ? 1 : 0;
+}
+
 void oracle_mass_properties(oracle_ctx* c, const b200phys_collider* col, float* inertia9, float* cog3, float* mass)
 {
     massProperties(*col, c->o.hulls, inertia9, cog3, mass);

@@ -203,6 +203,11 @@ class Oracle:
         n = self.lib.oracle_collide_pair(self.ctx, _p(a), _p(b), _p(normal), _p(pd))
         return n, normal, pd[:n]
 
+    def overlap_pair(self, col_a, col_b):
+        a = np.ascontiguousarray(col_a); b = np.ascontiguousarray(col_b)
+        self.lib.oracle_overlap_pair.restype = C.c_int
+        return bool(self.lib.oracle_overlap_pair(self.ctx, _p(a), _p(b)))
+
     def mass_properties(self, collider):
         c = np.ascontiguousarray(collider)
         inertia = np.zeros(9, dtype=np.float32); cog = np.zeros(3, dtype=np.float32); mass = np.zeros(1, dtype=np.float32)

@@ -359,3 +359,75 @@ def test_locomotion_env_sizes_ranges_reset_state_and_reward():
     for i in range(4):
         assert abs(env.reward(i) - 4.0) < 5e-3            # acos near 1 turns rounding in the rotation term into ~1e-3
     env.close()
+
+
+# ------------------------------------------------------------------- more hand-derived known answers (the reference ships none)
+def _quat(axis, angle):
+    a = np.asarray(axis, dtype=np.float64); a /= np.linalg.norm(a)
+    return list(a * np.sin(angle / 2)) + [np.cos(angle / 2)]
+
+
+def test_sphere_capsule_and_sphere_cylinder_known_answers():
+    """sphere-capsule = sphere vs the sphere at the closest point of the capsule axis (collision_narrow.cpp:398-406); sphere-cylinder
+    inside the slab 0 <= t <= 1 likewise, beyond the caps against the cap disc (:408-449)."""
+    o = oracle_lib.Oracle()
+    cap = world_collider(abi.CAPSULE, [0, -1, 0, 0, 1, 0, 0.5])
+    n, normal, pd = o.collide_pair(world_collider(abi.SPHERE, [0.8, 0.25, 0, 0.5]), cap)
+    assert n == 1 and np.allclose(normal, (-1, 0, 0), atol=1e-6) and abs(pd[0][3] - 0.2) < 1e-6        # centres 0.8 apart, radii 0.5 + 0.5
+    assert np.allclose(pd[0][:3], (0.4, 0.25, 0), atol=1e-6)                                           # midway between the surfaces
+    n, normal, pd = o.collide_pair(world_collider(abi.SPHERE, [0, 1.9, 0, 0.5]), cap)                  # beyond the end: the hemisphere
+    assert n == 1 and np.allclose(normal, (0, -1, 0), atol=1e-6) and abs(pd[0][3] - 0.1) < 1e-6
+    cyl = world_collider(abi.CYLINDER, [0, -1, 0, 0, 1, 0, 0.5])
+    n, normal, pd = o.collide_pair(world_collider(abi.SPHERE, [0.8, 0.25, 0, 0.5]), cyl)               # side: same as the capsule
+    assert n == 1 and np.allclose(normal, (-1, 0, 0), atol=1e-6) and abs(pd[0][3] - 0.2) < 1e-6
+    n, normal, pd = o.collide_pair(world_collider(abi.SPHERE, [0.2, 1.4, 0, 0.5]), cyl)                # above the flat cap (a capsule would be round here)
+    assert n == 1 and np.allclose(normal, (0, -1, 0), atol=1e-5) and abs(pd[0][3] - 0.1) < 1e-5
+    assert o.collide_pair(world_collider(abi.SPHERE, [0, 1.9, 0, 0.5]), cyl)[0] == 0                   # 0.9 above the cap: the cylinder has no hemisphere
+
+
+def test_sphere_obb_is_sphere_aabb_in_the_box_frame():
+    """collision_narrow.cpp:480-494: the sphere is rotated into the OBB frame, tested against the AABB, the result rotated back."""
+    o = oracle_lib.Oracle()
+    q = _quat([0, 0, 1], np.pi / 2)          # box x axis -> world y
+    obb = world_collider(abi.OBB, q + [0, 0, 0] + [2.0, 0.5, 1.0])       # world extents: 0.5 along x, 2 along y
+    n, normal, pd = o.collide_pair(world_collider(abi.SPHERE, [0.9, 0.3, 0.2, 0.5]), obb)
+    assert n == 1 and np.allclose(normal, (-1, 0, 0), atol=1e-6) and abs(pd[0][3] - 0.1) < 1e-6        # face at x = 0.5, sphere reaches 0.4
+    assert o.collide_pair(world_collider(abi.SPHERE, [1.01, 0, 0, 0.5]), obb)[0] == 0
+    assert o.collide_pair(world_collider(abi.SPHERE, [0, 2.4, 0, 0.5]), obb)[0] == 1                   # the long axis is y in the world
+
+
+def test_obb_obb_face_contact_is_clipped_to_four_points():
+    """obb-obb SAT + clipping (collision_narrow.cpp:1179-1527): a small box resting 0.1 deep on a big one gives the four corners of
+    its bottom face, each 0.1 deep, normal along y."""
+    o = oracle_lib.Oracle()
+    big = world_collider(abi.OBB, [0, 0, 0, 1] + [0, 0, 0] + [2, 1, 2])
+    small = world_collider(abi.OBB, _quat([0, 1, 0], 0.3) + [0.2, 1.4, -0.1] + [0.5, 0.5, 0.5])
+    n, normal, pd = o.collide_pair(big, small)
+    assert n == 4 and abs(abs(normal[1]) - 1.0) < 1e-6 and np.allclose(pd[:, 3], 0.1, atol=1e-5)
+    corners = np.array([[sx * 0.5, 0, sz * 0.5] for sx in (-1, 1) for sz in (-1, 1)])
+    c, s = np.cos(0.3), np.sin(0.3)
+    world = np.stack([c * corners[:, 0] + s * corners[:, 2] + 0.2, np.full(4, 0.95), -s * corners[:, 0] + c * corners[:, 2] - 0.1], 1)
+    got = pd[:, :3][np.lexsort((pd[:, 2], pd[:, 0]))]; want = world[np.lexsort((world[:, 2], world[:, 0]))]
+    assert np.allclose(got[:, [0, 2]], want[:, [0, 2]], atol=1e-4)                                      # x / z of the contact points = the small box's bottom corners
+
+
+def test_boolean_overlap_tests_known_answers_and_the_cylinder_quirk():
+    """overlapCheck's tests (bounding_volumes.h:301-363, bounding_volumes.cpp:704-733,1079-1199): touching counts as overlapping; the
+    sphere-vs-cylinder-cap branch compares a SQUARED distance with the radius (bounding_volumes.cpp:723): a sphere of radius 0.25 whose
+    centre is 0.45 above the cap rim region reports an overlap although 0.45 > 0.25, because 0.45^2 = 0.2025 <= 0.25."""
+    o = oracle_lib.Oracle()
+    S = lambda x, y, z, r: world_collider(abi.SPHERE, [x, y, z, r])
+    assert o.overlap_pair(S(0, 0, 0, 1), S(2, 0, 0, 1)) and not o.overlap_pair(S(0, 0, 0, 1), S(2.001, 0, 0, 1))
+    box = world_collider(abi.AABB, [-1, -1, -1, 1, 1, 1])
+    assert o.overlap_pair(S(1.4, 0, 0, 0.5), box) and not o.overlap_pair(S(1.6, 0, 0, 0.5), box)
+    assert o.overlap_pair(S(1.3, 1.3, 0, 0.5), box) and not o.overlap_pair(S(1.4, 1.4, 0, 0.5), box)     # corner region: distance, not a box test
+    cyl = world_collider(abi.CYLINDER, [0, -1, 0, 0, 1, 0, 0.5])
+    assert o.overlap_pair(S(0.2, 1.45, 0, 0.25), cyl)            # the quirk: 0.45 above the cap, radius 0.25, but 0.2025 <= 0.25
+    assert not o.overlap_pair(S(0.2, 1.6, 0, 0.25), cyl)         # 0.36 > 0.25
+    assert o.overlap_pair(S(0.7, 0, 0, 0.25), cyl) and not o.overlap_pair(S(0.8, 0, 0, 0.25), cyl)       # the side is an ordinary sphere test
+    a = world_collider(abi.OBB, [0, 0, 0, 1] + [0, 0, 0] + [1, 1, 1])
+    b = world_collider(abi.OBB, _quat([0, 0, 1], np.pi / 4) + [2.3, 0, 0] + [1, 1, 1])                    # rotated 45 deg: reaches 1.414 towards a
+    assert o.overlap_pair(a, b) and not o.overlap_pair(a, world_collider(abi.OBB, _quat([0, 0, 1], np.pi / 4) + [2.5, 0, 0] + [1, 1, 1]))
+    cap = world_collider(abi.CAPSULE, [0, -1, 0, 0, 1, 0, 0.25])
+    assert o.overlap_pair(cap, world_collider(abi.CAPSULE, [0.4, 0, -1, 0.4, 0, 1, 0.25])) and not o.overlap_pair(cap, world_collider(abi.CAPSULE, [0.6, 0, -1, 0.6, 0, 1, 0.25]))
+    assert o.overlap_pair(cap, box) and not o.overlap_pair(world_collider(abi.CAPSULE, [1.3, -1, 0, 1.3, 1, 0, 0.25]), box)   # GJK test
