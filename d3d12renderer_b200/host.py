@@ -42,6 +42,7 @@ def load_library():
     lib.b200host_event_log_counts.argtypes = [C.POINTER(u32)]; lib.b200host_event_log_counts.restype = u32
     lib.b200host_event_log_get.argtypes = [vp, vp, vp]
     lib.b200host_trigger_log.argtypes = [vp, u32, C.c_int]; lib.b200host_trigger_log.restype = u32
+    lib.b200host_test_physics_interaction.argtypes = [vp, vp, vp, C.c_float]
     lib.b200host_save_yaml.argtypes = [vp, C.c_char_p]; lib.b200host_load_yaml.argtypes = [vp, C.c_char_p]
     lib.b200host_get_render_transforms.argtypes = [vp, vp]
     lib.b200host_get_stats.argtypes = [vp, C.POINTER(abi.Stats)]
@@ -132,6 +133,11 @@ class HostScene:
         self.lib.b200host_trigger_log(_p(out), n, 1 if clear else 0)
         return out
 
+    def test_physics_interaction(self, origin, direction, strength=1000.0):
+        """testPhysicsInteraction (physics.cpp:555-629): the first rigid body the ray hits gets direction * strength at the hit point."""
+        o = np.ascontiguousarray(origin, dtype=np.float32); d = np.ascontiguousarray(direction, dtype=np.float32)
+        self.lib.b200host_test_physics_interaction(self.ptr, _p(o), _p(d), float(strength))
+
     def save_yaml(self, path):
         """Writes the physics components in the reference's scene-file layout (serialization_yaml.cpp)."""
         if self.lib.b200host_save_yaml(self.ptr, str(path).encode()):
@@ -166,6 +172,7 @@ class LocomotionEnv:
         lib.b200env_reward.argtypes = [C.c_void_p, C.c_uint32]; lib.b200env_reward.restype = C.c_float
         lib.b200env_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.b200env_ranges.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.b200env_set_push_probability.argtypes = [C.c_void_p, C.c_float]
         self.num_envs = int(num_envs)
         self.state_size = int(lib.b200env_state_size()); self.action_size = int(lib.b200env_action_size())
         self.ptr = C.c_void_p(lib.b200env_create(self.num_envs, spacing))
@@ -178,6 +185,10 @@ class LocomotionEnv:
         n = self.num_envs if index < 0 else 1
         out = np.zeros((n, self.state_size), dtype=np.float32)
         self.lib.b200env_reset(self.ptr, int(index), _p(out)); return out
+
+    def set_push_probability(self, p):
+        """Chance per environment and step of a random sideways push (0.02 in the reference, learned_locomotion.cpp:448)."""
+        self.lib.b200env_set_push_probability(self.ptr, float(p))
 
     def reward(self, index):
         return float(self.lib.b200env_reward(self.ptr, int(index)))

@@ -200,6 +200,12 @@ void b200host_mass_properties(void* s, const b200phys_collider* c, float* inerti
     memcpy(inertia9, p.inertia.m, 36); cog3[0] = p.cog.x; cog3[1] = p.cog.y; cog3[2] = p.cog.z; *mass = p.mass;
 }
 
+// testPhysicsInteraction (physics.cpp:555-629): the pushed body's accumulators show up in b200host_get_bodies
+void b200host_test_physics_interaction(void* s, const float* origin3, const float* direction3, float strength)
+{
+    testPhysicsInteraction(*(game_scene*)s, mk3(origin3[0], origin3[1], origin3[2]), mk3(direction3[0], direction3[1], direction3[2]), strength);
+}
+
 // scene files: the physics components of the reference's YAML scenes (scene_yaml.cpp); 0 on success
 int b200host_save_yaml(void* s, const char* path)
 {

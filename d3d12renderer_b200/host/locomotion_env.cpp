@@ -3,7 +3,8 @@
 // advances all of them; state, reward and failure test are the reference's formulas evaluated per environment on the host from the
 // downloaded poses. The single-environment C interface the reference exports to Python (learned_locomotion.cpp:393-488:
 // getPhysicsStateSize / getPhysicsActionSize / getPhysicsRanges / resetPhysics / updatePhysics) is the E = 1 case.
-// Not reproduced: the random pushes (testPhysicsInteraction ray casts with probability 0.02 per step, :448-458).
+// The random pushes (a ray cast at a random body part with probability 0.02 per step, :448-458) use one xorshift64 stream per
+// environment (the reference seeds its single stream with the wall clock) and only test the environment's own bodies.
 #include "physics_host.h"
 #include <cmath>
 #include <cstring>
@@ -34,6 +35,7 @@ struct Env
     vec3 targetPositions[kParts][6], targetVelocities[kParts][6]; quat localTargetRotation[kParts];
     trs initialTransform[kParts];
     uint32_t firstBody, firstConeTwist, firstHinge;
+    uint64_t rngState;
 };
 
 } // namespace
@@ -41,6 +43,20 @@ struct Env
 struct locomotion_env_batch
 {
     game_scene scene; std::vector<Env> envs; float physicsTimer = 0.f;
+    float pushProbability = 0.02f;      // learned_locomotion.cpp:448
+
+    static uint64_t nextRandom(uint64_t& state) { uint64_t x = state; x ^= x << 13; x ^= x >> 7; x ^= x << 17; state = x; return x; }          // core/random.h:14-24
+    static float random01(uint64_t& state) { return (uint32_t)nextRandom(state) / (float)0xFFFFFFFFu; }
+    // updatePhysics :448-458: push a random body part sideways from 5 m away
+    void maybePush(Env& e)
+    {
+        if (!(random01(e.rngState) < pushProbability)) return;
+        const uint32_t part = (uint32_t)nextRandom(e.rngState) % (kParts - 1);                 // randomUint32Between(0, NUM_BODY_PARTS - 1)
+        const vec3 target = partTransform(e, (int)part).position + b200::mk3(0.f, 0.2f, 0.f);
+        const float dx = -1.f + 2.f * random01(e.rngState), dz = -1.f + 2.f * random01(e.rngState);
+        const vec3 direction = b200::normalize(b200::mk3(dx, 0.f, dz));
+        testPhysicsInteraction(scene, target - direction * 5.f, direction, 1000.f, e.firstBody, kParts);
+    }
 
     const trs& partTransform(const Env& e, int part) const { return scene.physicsTransform1[e.firstBody + part]; }
     const rigid_body_component& partBody(const Env& e, int part) const { return scene.rigidBodies[e.firstBody + part]; }
@@ -167,6 +183,7 @@ struct locomotion_env_batch
         for (uint32_t i = 0; i < numEnvs; ++i)
         {
             Env& e = envs[i];
+            e.rngState = 0x9E3779B97F4A7C15ull ^ ((uint64_t)(i + 1) * 0xD1B54A32D192ED03ull);
             e.firstBody = (uint32_t)scene.rigidBodies.size(); e.firstConeTwist = (uint32_t)scene.coneTwistConstraints.size(); e.firstHinge = (uint32_t)scene.hingeConstraints.size();
             e.ragdoll = humanoid_ragdoll::create(scene, b200::mk3((i % side) * spacing - half, 1.25f, (i / side) * spacing - half));
             for (uint32_t p = 0; p < kParts; ++p) e.initialTransform[p] = scene.physicsTransform1[e.firstBody + p];
@@ -181,6 +198,7 @@ struct locomotion_env_batch
     {
         parallelFor((uint32_t)envs.size(), [&](uint32_t i) { applyAction(envs[i], actions + (size_t)i * kActionFloats); }, 256u);
         scene.jointsDirty = true;
+        if (pushProbability > 0.f) for (Env& e : envs) maybePush(e);
         physics_settings settings; settings.frameRate = 60;
         memory_arena arena; physicsTimer = 0.f;
         const int rc = physicsStep(scene, arena, physicsTimer, settings, 1.f / (float)settings.frameRate);
@@ -206,6 +224,7 @@ void* b200env_create(uint32_t numEnvs, float spacing) { locomotion_env_batch* b 
 void b200env_destroy(void* env) { delete (locomotion_env_batch*)env; }
 uint32_t b200env_state_size(void) { return kStateFloats; }
 uint32_t b200env_action_size(void) { return kActionFloats; }
+void b200env_set_push_probability(void* env, float p) { ((locomotion_env_batch*)env)->pushProbability = p; }
 uint32_t b200env_num_envs(void* env) { return (uint32_t)((locomotion_env_batch*)env)->envs.size(); }
 // index < 0: every environment; writes the state(s) after the reset
 void b200env_reset(void* env, int index, float* outStates)

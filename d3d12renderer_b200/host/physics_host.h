@@ -241,6 +241,9 @@ struct humanoid_ragdoll
 bool saveSceneYaml(const game_scene& scene, std::ostream& out, const char* sceneName = nullptr);
 int loadSceneYaml(game_scene& scene, std::istream& in);      // entities created, -1 if the input has no "Entities" list
 
+// physics.h:404: a ray pushes the first rigid body it hits (force + torque accumulators for the next step); ray_interaction.cpp
+void testPhysicsInteraction(game_scene& scene, vec3 rayOrigin, vec3 rayDirection, float strength = 1000.f, uint32_t firstBody = 0, uint32_t numBodies = 0xFFFFFFFFu);   // the body range restricts the test (batched environments)
+
 int physicsStep(game_scene& scene, memory_arena& arena, float& timer, const physics_settings& settings, float dt);
 
 } // namespace b200host

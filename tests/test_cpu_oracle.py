@@ -431,3 +431,31 @@ def test_boolean_overlap_tests_known_answers_and_the_cylinder_quirk():
     cap = world_collider(abi.CAPSULE, [0, -1, 0, 0, 1, 0, 0.25])
     assert o.overlap_pair(cap, world_collider(abi.CAPSULE, [0.4, 0, -1, 0.4, 0, 1, 0.25])) and not o.overlap_pair(cap, world_collider(abi.CAPSULE, [0.6, 0, -1, 0.6, 0, 1, 0.25]))
     assert o.overlap_pair(cap, box) and not o.overlap_pair(world_collider(abi.CAPSULE, [1.3, -1, 0, 1.3, 1, 0, 0.25]), box)   # GJK test
+
+
+def test_ray_interaction_pushes_the_first_body_hit():
+    """testPhysicsInteraction (physics.cpp:555-629) in the host mirror: a vertical ray 0.25 off a resting sphere's centre hits it at
+    height sqrt(r^2 - 0.25^2) above the centre; that body gets force = direction * strength and torque = (hit - COG) x force, nobody
+    else gets anything; static geometry and misses leave every accumulator untouched."""
+    sc = host.build_scene(host.CONFIG_SPHERES_ON_GROUND, 3, 1, 3, seed=1, mode=1, spacing=1.25)
+    hs = sc["host_scene"]
+    b = sc["bodies"]
+    target = 4
+    x0, y0, z0 = (float(v) for v in b["position"][target])
+    hs.test_physics_interaction([x0 + 0.25, 5.0, z0], [0.0, -1.0, 0.0], 1000.0)
+    after = hs.arrays()["bodies"]
+    assert np.allclose(after["forceAccumulator"][target], (0, -1000, 0))
+    assert np.allclose(after["torqueAccumulator"][target], (0, 0, -250.0), atol=1e-3)        # (0.25, 0.433, 0) x (0, -1000, 0)
+    others = np.arange(len(b)) != target
+    assert not np.any(after["forceAccumulator"][others]) and not np.any(after["torqueAccumulator"][others])
+    hs.test_physics_interaction([50.0, 5.0, 50.0], [0.0, -1.0, 0.0], 1000.0)                  # only the static ground is there
+    hs.test_physics_interaction([x0, 5.0, z0], [0.0, 1.0, 0.0], 1000.0)                       # pointing away
+    again = hs.arrays()["bodies"]
+    assert np.array_equal(again["forceAccumulator"], after["forceAccumulator"])
+    # of two spheres in a row the nearer one is pushed
+    row = [i for i in range(len(b)) if abs(float(b["position"][i][2]) - z0) < 1e-6]
+    first = min(row, key=lambda i: float(b["position"][i][0]))
+    hs.test_physics_interaction([-20.0, float(b["position"][first][1]), z0], [1.0, 0.0, 0.0], 10.0)
+    final = hs.arrays()["bodies"]
+    pushed = np.nonzero(np.any(final["forceAccumulator"] != again["forceAccumulator"], axis=1))[0].tolist()
+    assert pushed == [first] and np.allclose(final["forceAccumulator"][first] - again["forceAccumulator"][first], (10, 0, 0))

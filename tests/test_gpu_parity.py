@@ -350,6 +350,7 @@ def test_batched_locomotion_env_steps_on_the_gpu():
     updatePhysics, learned_locomotion.cpp:462-488). Zero actions hold the reset pose with 200 Nm position motors; random actions make
     the figures fall, which shows as failed = head below 1 m; resetting one environment restores its reset state and reward."""
     env = host.LocomotionEnv(16, spacing=5.0)
+    env.set_push_probability(0.0)                  # the pose-holding check below wants no random pushes
     s0 = env.reset()
     lo, hi = env.action_ranges()
     states, rewards, failed = env.step(np.zeros((16, 27), dtype=np.float32))
@@ -357,6 +358,7 @@ def test_batched_locomotion_env_steps_on_the_gpu():
     assert np.all(rewards > 2.0) and np.all(rewards <= 4.0 + 1e-4)
     assert np.allclose(states[:, 21:24], s0[:, 21:24], atol=0.05)                  # heads have barely moved after 1/60 s
     assert np.abs(states - states[0]).max() < 0.02                                  # same figure in every environment (solver order noise only)
+    env.set_push_probability(0.02)                 # the reference's value
     rng = np.random.default_rng(3)
     ever_failed = np.zeros(16, dtype=bool)
     for _ in range(120):
