@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(kThreads) haloPackBodiesKernel(uint32_t numBod
 }
 
 __global__ void __launch_bounds__(kThreads) haloPackCollidersKernel(uint32_t numColliders, const uint32_t* __restrict__ colFlag, const uint32_t* __restrict__ colSlot, uint32_t cap,
-    const uint32_t* __restrict__ bodySlot, const float4* __restrict__ cLocal, float4* __restrict__ out)
+    const uint32_t* __restrict__ bodySlot, uint32_t capBodies, const float4* __restrict__ cLocal, float4* __restrict__ out)
 {
     for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < numColliders; i += gridDim.x * kThreads)
     {
@@ -72,7 +72,16 @@ __global__ void __launch_bounds__(kThreads) haloPackCollidersKernel(uint32_t num
         const uint32_t s = colSlot[i];
         if (s >= cap) continue;
         float4 L3 = cLocal[4 * i + 3];
-        L3.z = __uint_as_float(bodySlot[__float_as_uint(L3.z)]);   // body index inside the packed list
+        const uint32_t bs = bodySlot[__float_as_uint(L3.z)];        // body index inside the packed list
+        if (bs >= capBodies)
+        {   // its body did not fit into the message (overflow, flagged by the receiver through the header): send an inert slot instead of a
+            // collider that would point past the packed body list
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            out[4 * s] = z; out[4 * s + 1] = z; out[4 * s + 2] = z;
+            out[4 * s + 3] = make_float4(0.f, __uint_as_float((uint32_t)B200PHYS_SPHERE | ((uint32_t)B200PHYS_OBJ_NONE << 8)), __uint_as_float(0xFFFFFFFFu), __uint_as_float(B200PHYS_NO_TRANSFORM));
+            continue;
+        }
+        L3.z = __uint_as_float(bs);
         out[4 * s] = cLocal[4 * i]; out[4 * s + 1] = cLocal[4 * i + 1]; out[4 * s + 2] = cLocal[4 * i + 2]; out[4 * s + 3] = L3;
     }
 }
@@ -147,10 +156,15 @@ __global__ void __launch_bounds__(kThreads) haloUnpackMessageKernel(const uint32
         if (k < nC)
         {
             float4 L3 = inCols[4 * k + 3];
-            L3.z = __uint_as_float(__float_as_uint(L3.z) + bodyBase);
-            cLocal[4 * i] = inCols[4 * k]; cLocal[4 * i + 1] = inCols[4 * k + 1]; cLocal[4 * i + 2] = inCols[4 * k + 2]; cLocal[4 * i + 3] = L3;
+            const uint32_t packedBody = __float_as_uint(L3.z);
+            if (packedBody < nB)
+            {
+                L3.z = __uint_as_float(packedBody + bodyBase);
+                cLocal[4 * i] = inCols[4 * k]; cLocal[4 * i + 1] = inCols[4 * k + 1]; cLocal[4 * i + 2] = inCols[4 * k + 2]; cLocal[4 * i + 3] = L3;
+                continue;
+            }
         }
-        else
+        // padding slot, or a collider whose body is not in the message (sender-side overflow / inert slot)
         {
             cLocal[4 * i] = z; cLocal[4 * i + 1] = z; cLocal[4 * i + 2] = z;
             cLocal[4 * i + 3] = make_float4(0.f, __uint_as_float((uint32_t)B200PHYS_SPHERE | ((uint32_t)B200PHYS_OBJ_NONE << 8)), __uint_as_float(0xFFFFFFFFu), __uint_as_float(B200PHYS_NO_TRANSFORM));
@@ -250,7 +264,7 @@ static int haloPackDevice(Context& c, int axis, float lo, float hi, void* dstBod
     if (dstBodies && capBodies)
         haloPackBodiesKernel<<<G, kThreads, 0, c.stream>>>(N, c.cfg.maxBodies + 1, bodyFlag, bodySlot, capBodies, c.bRot, c.bPos, c.bCog, c.bInvI, c.bVel, c.bAng, c.bForce, c.bTorque, (float*)dstBodies);
     if (dstColliders && capColliders)
-        haloPackCollidersKernel<<<G, kThreads, 0, c.stream>>>(C, colFlag, colSlot, capColliders, bodySlot, c.cLocal, (float4*)dstColliders);
+        haloPackCollidersKernel<<<G, kThreads, 0, c.stream>>>(C, colFlag, colSlot, capColliders, bodySlot, capBodies, c.cLocal, (float4*)dstColliders);
     CK(cudaGetLastError());
     return 0;
 }
@@ -361,7 +375,7 @@ int b200phys_migrate_pack(b200phys_context* ctx, int axis, float lo, float hi, v
     {
         float* outB = (float*)(msg[d] + 16); float4* outC = (float4*)(msg[d] + 16 + (size_t)capBodies * kHaloBodyFloats * 4);
         haloPackBodiesKernel<<<G, kThreads, 0, c.stream>>>(N, planeStride, flag[d], slot[d], capBodies, c.bRot, c.bPos, c.bCog, c.bInvI, c.bVel, c.bAng, c.bForce, c.bTorque, outB);
-        if (C) haloPackCollidersKernel<<<G, kThreads, 0, c.stream>>>(C, cflag[d], cslot[d], capColliders, slot[d], c.cLocal, outC);
+        if (C) haloPackCollidersKernel<<<G, kThreads, 0, c.stream>>>(C, cflag[d], cslot[d], capColliders, slot[d], capBodies, c.cLocal, outC);
         haloHeaderKernel<<<1, 32, 0, c.stream>>>(slot[d] + N, cslot[d] + C, (uint32_t*)msg[d]);
     }
     // compaction of what stays

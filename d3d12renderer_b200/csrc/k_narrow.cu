@@ -297,7 +297,7 @@ __global__ void npTotalsKernel(const unsigned long long* __restrict__ scanOut, u
 
 __global__ void __launch_bounds__(kThreads) npCompactKernel(const uint2* __restrict__ sorted, const float4* __restrict__ wCol, const float4* __restrict__ manTmp,
     const unsigned long long* __restrict__ manScan, const unsigned long long* __restrict__ scanOut, uint32_t maxPairs, uint32_t maxManifolds, uint32_t maxContacts,
-    uint2* __restrict__ collisions, uint4* __restrict__ manifolds, float4* __restrict__ contacts, uint2* __restrict__ contactBodies, const DeviceCounts* __restrict__ cnt)
+    uint2* __restrict__ collisions, uint4* __restrict__ manifolds, float4* __restrict__ contacts, uint2* __restrict__ contactBodies, DeviceCounts* __restrict__ cnt)
 {
     const uint32_t n = cnt->keyStart[kBucketDropped];   // collision buckets come first
     for (uint32_t q = blockIdx.x * kThreads + threadIdx.x; q < n; q += gridDim.x * kThreads)
@@ -307,7 +307,12 @@ __global__ void __launch_bounds__(kThreads) npCompactKernel(const uint2* __restr
         if (!count) continue;
         const unsigned long long ex = scanOut[q];
         const uint32_t mi = (uint32_t)(ex & 0xFFFFFFFFull), cs = (uint32_t)(ex >> 32);
-        if (mi >= maxManifolds || cs + count > maxContacts) continue;
+        if (mi >= maxManifolds || cs + count > maxContacts)
+        {   // out of capacity: manifold and contact prefix sums are monotone, so what fits is a PREFIX of the canonical list; the first
+            // manifold that does not fit cuts both counts (npTotalsKernel clamped them to the capacities before this kernel)
+            atomicMin(&cnt->numManifolds, mi); atomicMin(&cnt->numContacts, cs);
+            continue;
+        }
         const uint2 pr = sorted[q];
         const float4 a2 = wCol[4 * pr.x + 2], a3 = wCol[4 * pr.x + 3], b2 = wCol[4 * pr.y + 2], b3 = wCol[4 * pr.y + 3];
         // writeScalarContact (collision_narrow.cpp:2228-2237): truncating 16+16 bit packing

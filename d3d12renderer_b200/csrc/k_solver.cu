@@ -297,6 +297,7 @@ __global__ void __launch_bounds__(kThreads) initContactRowsKernel(const uint32_t
     {
         const uint4 man = manifolds[order[p]];
         const uint32_t slot0 = unitSlotStart[p];
+        if (slot0 + man.w > maxContacts) { unitInfo[p] = make_uint4(man.x, man.y, 0u, 0u); continue; }   // cannot happen with consistent counts (npCompactKernel cuts both lists together)
         unitInfo[p] = make_uint4(man.x, man.y, slot0, man.w);   // solve-order record: one 128-bit load per manifold and iteration
         const float4 vA4 = gVel[2 * man.x], wA4 = gVel[2 * man.x + 1], vB4 = gVel[2 * man.y], wB4 = gVel[2 * man.y + 1];
         const float4 pA4 = gPos[man.x], pB4 = gPos[man.y];
@@ -500,6 +501,7 @@ __global__ void __launch_bounds__(kThreads) colorInheritKernel(const unsigned lo
         uint32_t c;
         if (lo < nRef && refKeys[lo] == k) c = refColors[lo];
         else c = hashPriority((uint32_t)k ^ (uint32_t)(k >> 28)) % numColors;       // a pair that did not touch last step
+        c = min(c, kMaxColors - 1u);                                                // (a failed colouring can leave 255 behind: the stable sort takes keys < kMaxColors)
         colorKey[i] = (uint8_t)c; color[i] = c;
     }
 }
@@ -510,7 +512,7 @@ __global__ void __launch_bounds__(kThreads) jointColorCopyKernel(int toRef, cons
     for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads)
     {
         if (toRef) ref[i] = (uint8_t)min(color[i], 255u);
-        else { const uint32_t c = ref[i]; colorKey[i] = (uint8_t)c; color[i] = c; }
+        else { const uint32_t c = min((uint32_t)ref[i], kMaxColors - 1u); colorKey[i] = (uint8_t)c; color[i] = c; }
     }
 }
 __global__ void __launch_bounds__(kThreads) orderFromPosKernel(const uint32_t* __restrict__ numUnits, const uint32_t* __restrict__ posOf, uint32_t* __restrict__ order)

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200host.so")
 _lib = None
 
-CONFIG_SPHERES_ON_GROUND, CONFIG_SPHERE_BOX_DROP, CONFIG_MIXED_PILE, CONFIG_RAGDOLLS, CONFIG_EVENT_SCENE = 1, 2, 3, 4, 5
+CONFIG_SPHERES_ON_GROUND, CONFIG_SPHERE_BOX_DROP, CONFIG_MIXED_PILE, CONFIG_RAGDOLLS, CONFIG_EVENT_SCENE, CONFIG_JOINT_ZOO, CONFIG_VEHICLES = 1, 2, 3, 4, 5, 6, 7
 
 
 def load_library():

@@ -35,6 +35,8 @@ void addWalls(game_scene& s, float ex, float ez, float h)
     w.addCollider(collider_component::asAABB(bounding_box::fromCenterRadius(mk3(0.f, h * 0.5f, (ez + 2.f)), mk3(ex + 4.f, h * 0.5f + 2.f, 2.f)), kStaticMat));
 }
 
+inline float deg2radf(float d) { return d * (B200_PI / 180.f); }
+
 quat randomRotation(Rng& rng)
 {   // axis = normalize(uniform[-1,1]^3), angle = uniform[0, pi]
     vec3 axis = mk3(rng.between(-1.f, 1.f), rng.between(-1.f, 1.f), rng.between(-1.f, 1.f));
@@ -130,6 +132,111 @@ int b200host_build_config(void* sp, int config, uint32_t nx, uint32_t ny, uint32
         const float ex = hx + 1.1f, ez = hz + 1.1f, h = ny * spacing + 4.f;
         s.createEntity("Floor").addTransform(mk3(0.f, -4.f, 0.f)).addCollider(collider_component::asAABB(bounding_box::fromCenterRadius(mk3(0.f), mk3(ex + 8.f, 4.f, ez + 8.f)), kStaticMat));
         addWalls(s, ex, ez, h);
+        return 0;
+    }
+    if (config == 6)
+    {   // joint zoo: nx x nz copies of eleven small mechanisms covering distance / ball / fixed / slider joints and every motor and
+        // limit of the hinge, cone-twist and slider joints (constraints.cpp:189-264,460-528,736-823,1079-1307,1782-2070,2638-2846).
+        // Mechanisms hang from kinematic anchors (invMass 0), are spaced so that different mechanisms never touch, and start out of
+        // equilibrium so that limits and motors are active within the first steps. `mode` seeds small per-copy variations.
+        const float DX = spacing > 0.f ? spacing : 30.f;
+        const physics_material mat = kDynamicMat;
+        for (uint32_t cx = 0; cx < nx; ++cx) for (uint32_t cz = 0; cz < nz; ++cz)
+        {
+            const vec3 O = mk3(cx * DX, 0.f, cz * 40.f);
+            const float jig = rng.between(-0.05f, 0.05f);
+            auto anchorAt = [&](vec3 p) { scene_entity a = s.createEntity("Anchor"); a.addTransform(O + p).addRigidBody(true); return a; };
+            auto sphereAt = [&](vec3 p, float r) { scene_entity e = s.createEntity("Ball"); e.addTransform(O + p).addCollider(collider_component::asSphere({ mk3(0.f), r }, mat)).addRigidBody(false); return e; };
+            auto capsuleAt = [&](vec3 p, quat q, float h, float r) { scene_entity e = s.createEntity("Link"); e.addTransform(O + p, q).addCollider(collider_component::asCapsule({ mk3(0.f, -h, 0.f), mk3(0.f, h, 0.f), r }, mat)).addRigidBody(false); return e; };
+            auto boxAt = [&](vec3 p, quat q, vec3 r) { scene_entity e = s.createEntity("Box"); e.addTransform(O + p, q).addCollider(collider_component::asOBB({ qIdentity(), mk3(0.f), r }, mat)).addRigidBody(false); return e; };
+            const quat horiz = quatAxisAngle(mk3(0.f, 0.f, 1.f), deg2radf(90.f));      // capsule axis along x
+            {   // A: distance chain (pendulum of three spheres), starts sideways
+                scene_entity prev = anchorAt(mk3(0.f, 8.f, 0.f)); vec3 pp = O + mk3(0.f, 8.f, 0.f);
+                for (int i = 0; i < 3; ++i)
+                {
+                    const vec3 p = mk3(0.8f * (i + 1) + jig, 8.f - 0.3f * (i + 1), 0.f);
+                    scene_entity b = sphereAt(p, 0.25f);
+                    addDistanceConstraintFromGlobalPoints(prev, b, pp, O + p);
+                    prev = b; pp = O + p;
+                }
+            }
+            {   // B: ball-joint chain of three capsules laid out horizontally
+                scene_entity prev = anchorAt(mk3(0.f, 8.f, 3.f));
+                for (int i = 0; i < 3; ++i)
+                {
+                    scene_entity b = capsuleAt(mk3(0.5f + 1.0f * i, 8.f, 3.f), horiz, 0.35f, 0.12f);
+                    addBallConstraintFromGlobalPoints(prev, b, O + mk3(1.0f * i, 8.f, 3.f));
+                    prev = b;
+                }
+            }
+            {   // C: two boxes welded by a fixed joint, tumbling onto the ground
+                scene_entity a = boxAt(mk3(0.f, 1.6f + jig, 6.f), quatAxisAngle(normalize(mk3(1.f, 0.3f, 0.2f)), 0.4f), mk3(0.4f, 0.2f, 0.3f));
+                scene_entity b = boxAt(mk3(0.9f, 1.9f + jig, 6.f), quatAxisAngle(normalize(mk3(0.f, 1.f, 0.5f)), 0.9f), mk3(0.3f, 0.3f, 0.2f));
+                addFixedConstraintFromGlobalPoints(a, b, O + mk3(0.45f, 1.75f, 6.f));
+                a.rigidBody().angularVelocity = mk3(1.f, 2.f, -1.5f); b.rigidBody().linearVelocity = mk3(0.f, -1.f, 0.5f);
+            }
+            {   // D: slider along x with limits and a velocity motor
+                scene_entity base = anchorAt(mk3(0.f, 5.f, 9.f)); scene_entity b = boxAt(mk3(0.f, 5.f, 9.f), qIdentity(), mk3(0.3f, 0.2f, 0.2f));
+                slider_constraint& c = getConstraint(s, addSliderConstraintFromGlobalPoints(base, b, O + mk3(0.f, 5.f, 9.f), mk3(1.f, 0.f, 0.f), -0.05f, 0.06f));
+                c.motorType = constraint_velocity_motor; c.maxMotorForce = 200.f; c.motorVelocityOrTargetDistance = 1.5f;
+            }
+            {   // E: vertical slider with a position motor holding the box against gravity, no limits
+                scene_entity base = anchorAt(mk3(0.f, 5.f, 12.f)); scene_entity b = boxAt(mk3(0.f, 5.f, 12.f), qIdentity(), mk3(0.2f, 0.2f, 0.2f));
+                slider_constraint& c = getConstraint(s, addSliderConstraintFromGlobalPoints(base, b, O + mk3(0.f, 5.f, 12.f), normalize(mk3(0.1f, 1.f, 0.f))));
+                c.motorType = constraint_position_motor; c.maxMotorForce = 80.f; c.motorVelocityOrTargetDistance = 0.3f;
+            }
+            {   // F: hinge with a velocity motor (no limits)
+                scene_entity base = anchorAt(mk3(0.f, 5.f, 15.f)); scene_entity b = capsuleAt(mk3(0.5f, 5.f, 15.f), horiz, 0.4f, 0.1f);
+                hinge_constraint& c = getConstraint(s, addHingeConstraintFromGlobalPoints(base, b, O + mk3(0.f, 5.f, 15.f), mk3(0.f, 0.f, 1.f)));
+                c.motorType = constraint_velocity_motor; c.maxMotorTorque = 50.f; c.motorVelocityOrTargetAngle = 2.f;
+            }
+            {   // G: hinge with limits and a position motor
+                scene_entity base = anchorAt(mk3(0.f, 5.f, 18.f)); scene_entity b = capsuleAt(mk3(0.5f, 5.f, 18.f), horiz, 0.4f, 0.1f);
+                hinge_constraint& c = getConstraint(s, addHingeConstraintFromGlobalPoints(base, b, O + mk3(0.f, 5.f, 18.f), mk3(0.f, 0.f, 1.f), deg2radf(-45.f), deg2radf(60.f)));
+                c.motorType = constraint_position_motor; c.maxMotorTorque = 40.f; c.motorVelocityOrTargetAngle = 0.5f;
+            }
+            {   // H: free hinge with a narrow limit: falls under gravity into the limit within a few steps
+                scene_entity base = anchorAt(mk3(0.f, 5.f, 21.f)); scene_entity b = capsuleAt(mk3(0.5f, 5.f, 21.f), horiz, 0.4f, 0.1f);
+                addHingeConstraintFromGlobalPoints(base, b, O + mk3(0.f, 5.f, 21.f), mk3(0.f, 0.f, 1.f), deg2radf(-2.f), deg2radf(2.f));
+                b.rigidBody().angularVelocity = mk3(0.f, 0.f, -3.f);
+            }
+            {   // I: cone-twist, swing velocity motor + twist limit
+                scene_entity base = anchorAt(mk3(0.f, 5.f, 24.f)); scene_entity b = capsuleAt(mk3(0.f, 4.5f, 24.f), qIdentity(), 0.4f, 0.1f);
+                cone_twist_constraint& c = getConstraint(s, addConeTwistConstraintFromGlobalPoints(base, b, O + mk3(0.f, 5.f, 24.f), mk3(0.f, -1.f, 0.f), deg2radf(40.f), deg2radf(20.f)));
+                c.swingMotorType = constraint_velocity_motor; c.maxSwingMotorTorque = 30.f; c.swingMotorVelocityOrTargetAngle = 1.5f; c.swingMotorAxis = 0.7f;
+                b.rigidBody().angularVelocity = mk3(0.f, 4.f, 0.f);          // twists into the twist limit
+            }
+            {   // J: cone-twist, swing position motor + twist position motor
+                scene_entity base = anchorAt(mk3(0.f, 5.f, 27.f)); scene_entity b = capsuleAt(mk3(0.f, 4.5f, 27.f), qIdentity(), 0.4f, 0.1f);
+                cone_twist_constraint& c = getConstraint(s, addConeTwistConstraintFromGlobalPoints(base, b, O + mk3(0.f, 5.f, 27.f), mk3(0.f, -1.f, 0.f), deg2radf(60.f), deg2radf(45.f)));
+                c.swingMotorType = constraint_position_motor; c.maxSwingMotorTorque = 25.f; c.swingMotorVelocityOrTargetAngle = 0.4f; c.swingMotorAxis = 1.9f;
+                c.twistMotorType = constraint_position_motor; c.maxTwistMotorTorque = 10.f; c.twistMotorVelocityOrTargetAngle = 0.3f;
+            }
+            {   // K: cone-twist, twist velocity motor, narrow swing limit hit by a sideways kick
+                scene_entity base = anchorAt(mk3(0.f, 5.f, 30.f)); scene_entity b = capsuleAt(mk3(0.f, 4.5f, 30.f), qIdentity(), 0.4f, 0.1f);
+                cone_twist_constraint& c = getConstraint(s, addConeTwistConstraintFromGlobalPoints(base, b, O + mk3(0.f, 5.f, 30.f), mk3(0.f, -1.f, 0.f), deg2radf(3.f), deg2radf(-1.f)));
+                c.twistMotorType = constraint_velocity_motor; c.maxTwistMotorTorque = 5.f; c.twistMotorVelocityOrTargetAngle = 3.f;
+                b.rigidBody().linearVelocity = mk3(2.f, 0.f, 1.f);
+            }
+        }
+        s.createEntity("Ground").addTransform(mk3(0.f, -4.f, 0.f))
+            .addCollider(collider_component::asAABB(bounding_box::fromCenterRadius(mk3(0.f), mk3(nx * DX + 20.f, 4.f, nz * 40.f + 20.f)), kStaticMat));
+        return 0;
+    }
+    if (config == 7)
+    {   // nx x nz vehicles (vehicle.cpp:303-497) dropped on the ground; mode 1: engine and steering motors driven
+        const float DX = spacing > 0.f ? spacing : 8.f;
+        for (uint32_t ix = 0; ix < nx; ++ix) for (uint32_t iz = 0; iz < nz; ++iz)
+        {
+            vehicle v = vehicle::create(s, mk3(ix * DX, 1.1f + rng.between(0.f, 0.2f), iz * DX), (mode == 0) ? 0.f : rng.between(0.f, 6.2831853f));
+            if (mode)
+            {
+                getConstraint(s, v.motorConstraint).motorVelocityOrTargetAngle = 6.f;
+                getConstraint(s, v.steeringWheelConstraint).motorVelocityOrTargetAngle = 0.35f;
+            }
+        }
+        s.createEntity("Ground").addTransform(mk3(0.f, -4.f, 0.f))
+            .addCollider(collider_component::asAABB(bounding_box::fromCenterRadius(mk3(0.f), mk3(nx * DX + 20.f, 4.f, nz * DX + 20.f)), kStaticMat));
         return 0;
     }
     if (config == 4)

@@ -351,9 +351,83 @@ static vec3 inverseTransformPosition(const trs& m, vec3 pos) { vec3 p = conjugat
 static vec3 inverseTransformDirection(const trs& m, vec3 dir) { return conjugate(m.rotation) * dir; }
 
 static uint32_t pushPair(game_scene& s, int kind, scene_entity& a, scene_entity& b)
-{
+{   // returns the stable id of the new joint (the constraint entity of the reference, physics.cpp:87-126)
     s.constraintEntities[kind].push_back({ a.handle, b.handle }); s.jointsDirty = true; s.jointPairsDirty = true;
-    return (uint32_t)s.constraintEntities[kind].size() - 1;
+    const uint32_t id = (uint32_t)s.constraintIndexOfId[kind].size();
+    s.constraintIds[kind].push_back(id); s.constraintIndexOfId[kind].push_back((int32_t)s.constraintEntities[kind].size() - 1);
+    return id;
+}
+
+// addConstraint (physics.cpp:344-378): the struct is stored as given
+distance_constraint_handle addConstraint(scene_entity& a, scene_entity& b, const distance_constraint& c) { a.scene->distanceConstraints.push_back(c); return { pushPair(*a.scene, 0, a, b) }; }
+ball_constraint_handle addConstraint(scene_entity& a, scene_entity& b, const ball_constraint& c) { a.scene->ballConstraints.push_back(c); return { pushPair(*a.scene, 1, a, b) }; }
+fixed_constraint_handle addConstraint(scene_entity& a, scene_entity& b, const fixed_constraint& c) { a.scene->fixedConstraints.push_back(c); return { pushPair(*a.scene, 2, a, b) }; }
+hinge_constraint_handle addConstraint(scene_entity& a, scene_entity& b, const hinge_constraint& c) { a.scene->hingeConstraints.push_back(c); return { pushPair(*a.scene, 3, a, b) }; }
+cone_twist_constraint_handle addConstraint(scene_entity& a, scene_entity& b, const cone_twist_constraint& c) { a.scene->coneTwistConstraints.push_back(c); return { pushPair(*a.scene, 4, a, b) }; }
+slider_constraint_handle addConstraint(scene_entity& a, scene_entity& b, const slider_constraint& c) { a.scene->sliderConstraints.push_back(c); return { pushPair(*a.scene, 5, a, b) }; }
+
+// getConstraint (physics.cpp:380-408). Joint parameters are host-mutable between steps (motor targets): the step re-uploads them.
+static size_t indexOf(game_scene& s, int kind, uint32_t id) { return (size_t)s.constraintIndexOfId[kind].at(id); }
+distance_constraint& getConstraint(game_scene& s, distance_constraint_handle h) { s.jointsDirty = true; return s.distanceConstraints.at(indexOf(s, 0, h.entity)); }
+ball_constraint& getConstraint(game_scene& s, ball_constraint_handle h) { s.jointsDirty = true; return s.ballConstraints.at(indexOf(s, 1, h.entity)); }
+fixed_constraint& getConstraint(game_scene& s, fixed_constraint_handle h) { s.jointsDirty = true; return s.fixedConstraints.at(indexOf(s, 2, h.entity)); }
+hinge_constraint& getConstraint(game_scene& s, hinge_constraint_handle h) { s.jointsDirty = true; return s.hingeConstraints.at(indexOf(s, 3, h.entity)); }
+cone_twist_constraint& getConstraint(game_scene& s, cone_twist_constraint_handle h) { s.jointsDirty = true; return s.coneTwistConstraints.at(indexOf(s, 4, h.entity)); }
+slider_constraint& getConstraint(game_scene& s, slider_constraint_handle h) { s.jointsDirty = true; return s.sliderConstraints.at(indexOf(s, 5, h.entity)); }
+
+// deleteConstraint (physics.cpp:410-520): the pools are EnTT storages, destroying the constraint entity swaps the last element into the
+// hole; the same happens here so that joint array order (= Gauss-Seidel order of the scalar solver) stays what the reference would have
+template <typename T> static void swapAndPop(std::vector<T>& v, size_t i) { v[i] = v.back(); v.pop_back(); }
+static void eraseJoint(game_scene& s, int kind, uint32_t id)
+{
+    if (id >= s.constraintIndexOfId[kind].size() || s.constraintIndexOfId[kind][id] < 0) return;
+    const size_t i = (size_t)s.constraintIndexOfId[kind][id], last = s.constraintEntities[kind].size() - 1;
+    switch (kind)
+    {
+    case 0: swapAndPop(s.distanceConstraints, i); break;
+    case 1: swapAndPop(s.ballConstraints, i); break;
+    case 2: swapAndPop(s.fixedConstraints, i); break;
+    case 3: swapAndPop(s.hingeConstraints, i); break;
+    case 4: swapAndPop(s.coneTwistConstraints, i); break;
+    default: swapAndPop(s.sliderConstraints, i); break;
+    }
+    const uint32_t movedId = s.constraintIds[kind][last];
+    swapAndPop(s.constraintEntities[kind], i); swapAndPop(s.constraintIds[kind], i);
+    s.constraintIndexOfId[kind][id] = -1;
+    if (i != last) s.constraintIndexOfId[kind][movedId] = (int32_t)i;
+    s.jointsDirty = true; s.jointPairsDirty = true;
+}
+void deleteConstraint(game_scene& s, distance_constraint_handle h) { eraseJoint(s, 0, h.entity); }
+void deleteConstraint(game_scene& s, ball_constraint_handle h) { eraseJoint(s, 1, h.entity); }
+void deleteConstraint(game_scene& s, fixed_constraint_handle h) { eraseJoint(s, 2, h.entity); }
+void deleteConstraint(game_scene& s, hinge_constraint_handle h) { eraseJoint(s, 3, h.entity); }
+void deleteConstraint(game_scene& s, cone_twist_constraint_handle h) { eraseJoint(s, 4, h.entity); }
+void deleteConstraint(game_scene& s, slider_constraint_handle h) { eraseJoint(s, 5, h.entity); }
+void deleteAllConstraints(game_scene& s)
+{   // physics.cpp:410-418
+    s.distanceConstraints.clear(); s.ballConstraints.clear(); s.fixedConstraints.clear(); s.hingeConstraints.clear(); s.coneTwistConstraints.clear(); s.sliderConstraints.clear();
+    for (int k = 0; k < 6; ++k) { s.constraintEntities[k].clear(); s.constraintIds[k].clear(); for (int32_t& x : s.constraintIndexOfId[k]) x = -1; }
+    s.jointsDirty = true; s.jointPairsDirty = true;
+}
+void deleteAllConstraintsFromEntity(scene_entity& e)
+{   // physics.cpp:522-552: every joint with the entity at either end
+    game_scene& s = *e.scene;
+    for (int k = 0; k < 6; ++k)
+        for (size_t i = s.constraintEntities[k].size(); i-- > 0;)
+            if (s.constraintEntities[k][i].rbA == e.handle || s.constraintEntities[k][i].rbB == e.handle) eraseJoint(s, k, s.constraintIds[k][i]);
+}
+constraint_entity_iterator::constraint_entity_iterator(scene_entity e)
+{
+    if (!e) return;
+    game_scene& s = *e.scene;
+    for (int k = 0; k < 6; ++k)
+        for (size_t i = 0; i < s.constraintEntities[k].size(); ++i)
+        {
+            const b200phys_body_pair& p = s.constraintEntities[k][i];
+            if (p.rbA != e.handle && p.rbB != e.handle) continue;
+            scene_entity other; other.scene = e.scene; other.handle = (p.rbA == e.handle) ? p.rbB : p.rbA;     // getOtherEntity, physics.h:266-270
+            items.push_back({ other, (constraint_type)k, (uint32_t)i });
+        }
 }
 
 distance_constraint_handle addDistanceConstraintFromLocalPoints(scene_entity& a, scene_entity& b, vec3 localAnchorA, vec3 localAnchorB, float distance)
@@ -499,6 +573,168 @@ void humanoid_ragdoll::initialize(game_scene& scene, vec3 initialHipPosition, fl
         t.rotation = rotation * t.rotation;
         t.position = rotation * t.position + initialHipPosition;
         int rb = scene.entities[bodyParts[i].handle].rigidBody;
+        scene.physicsTransform0[rb] = scene.physicsTransform1[rb] = t;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------ vehicle
+// vehicle::initialize (vehicle.cpp:303-497) without the render meshes: the same 16 parts, colliders (gear teeth = capsules, wheels =
+// cylinders, motor = box; rods, suspensions and hollow gear bodies carry no collider, vehicle.cpp:270), joint anchors, limits and motors.
+namespace {
+struct GearDesc { float height, cylinderRadius, cylinderInnerRadius; uint32_t numTeeth; float toothLength, toothWidth, friction, density; };   // vehicle.cpp:5-16
+struct WheelDesc { float height, radius, innerRadius, friction, density; };                                                                       // vehicle.cpp:18-26
+struct Attachment { int type; float rodLength, rodThickness; GearDesc gear; WheelDesc wheel; };     // 0 none, 1 gear, 2 wheel (vehicle.cpp:28-52)
+Attachment attachNone(float len, float th) { Attachment a = {}; a.type = 0; a.rodLength = len; a.rodThickness = th; return a; }
+Attachment attachGear(float len, float th, GearDesc g) { Attachment a = {}; a.type = 1; a.rodLength = len; a.rodThickness = th; a.gear = g; return a; }
+Attachment attachWheel(float len, float th, WheelDesc w) { Attachment a = {}; a.type = 2; a.rodLength = len; a.rodThickness = th; a.wheel = w; return a; }
+
+void attachColliders(scene_entity axis, const Attachment& at, float sign)
+{   // vehicle.cpp:54-140 (collider part)
+    const float rodOffset = at.rodLength * sign;
+    if (at.type == 1)
+    {
+        const GearDesc& d = at.gear;
+        for (uint32_t i = 0; i < d.numTeeth; ++i)
+        {
+            const float angle = i * 6.28318530718f / d.numTeeth;                      // M_TAU (math.h:19)
+            const quat localRotation = quatAxisAngle(mk3(0.f, 1.f, 0.f), angle);
+            const vec3 center = localRotation * mk3(d.cylinderRadius + d.toothLength * 0.5f, 0.f, 0.f);
+            bounding_capsule c;
+            c.positionA = center + mk3(0.f, rodOffset, 0.f) - localRotation * mk3(d.toothLength * 0.5f, 0.f, 0.f);
+            c.positionB = center + mk3(0.f, rodOffset, 0.f) + localRotation * mk3(d.toothLength * 0.5f, 0.f, 0.f);
+            c.radius = d.toothWidth * 0.5f;
+            axis.addCollider(collider_component::asCapsule(c, { physics_material_type_wood, 0.2f, d.friction, d.density }));
+        }
+    }
+    else if (at.type == 2)
+    {
+        const WheelDesc& d = at.wheel;
+        bounding_cylinder c = { mk3(0.f, rodOffset - d.height * 0.5f, 0.f), mk3(0.f, rodOffset + d.height * 0.5f, 0.f), d.radius };
+        axis.addCollider(collider_component::asCylinder(c, { physics_material_type_wood, 0.2f, d.friction, d.density }));
+    }
+}
+scene_entity makeAxis(game_scene& scene, vec3 position, quat rotation, GearDesc desc, const Attachment* first = nullptr, const Attachment* second = nullptr)
+{   // createAxis, vehicle.cpp:142-171
+    scene_entity axis = scene.createEntity("Axis"); axis.addTransform(position, rotation);
+    attachColliders(axis, attachGear(0.f, 0.f, desc), 1.f);
+    if (first) attachColliders(axis, *first, 1.f);
+    if (second) attachColliders(axis, *second, -1.f);
+    axis.addRigidBody(false);
+    return axis;
+}
+scene_entity makeGearAxis(game_scene& scene, vec3 position, quat rotation, float length, uint32_t numTeeth, float toothLength, float toothWidth, float friction, float density)
+{   // createGearAxis, vehicle.cpp:173-217
+    scene_entity axis = scene.createEntity("Gear Axis"); axis.addTransform(position, rotation);
+    const float distance = length - toothWidth, stride = distance / (numTeeth - 1), leftOffset = -0.5f * length + 0.5f * toothWidth;
+    for (uint32_t i = 0; i < numTeeth; ++i)
+    {
+        const vec3 center = mk3(leftOffset + i * stride, toothWidth * 0.5f, 0.f);
+        bounding_capsule c = { center + mk3(0.f, toothLength * 0.5f, 0.f), center - mk3(0.f, toothLength * 0.5f, 0.f), toothWidth * 0.5f };
+        axis.addCollider(collider_component::asCapsule(c, { physics_material_type_wood, 0.2f, friction, density }));
+    }
+    axis.addRigidBody(false);
+    return axis;
+}
+scene_entity makeWheel(game_scene& scene, vec3 position, quat rotation, WheelDesc d)
+{   // createWheel, vehicle.cpp:219-247
+    scene_entity w = scene.createEntity("Wheel"); w.addTransform(position, rotation);
+    bounding_cylinder c = { mk3(0.f, -d.height * 0.5f, 0.f), mk3(0.f, d.height * 0.5f, 0.f), d.radius };
+    w.addCollider(collider_component::asCylinder(c, { physics_material_type_wood, 0.2f, d.friction, d.density }));
+    w.addRigidBody(false);
+    return w;
+}
+scene_entity makeBare(game_scene& scene, const char* name, vec3 position, quat rotation)
+{   // createWheelSuspension / createRod (vehicle.cpp:249-301): rigid bodies without colliders, default mass properties
+    scene_entity e = scene.createEntity(name); e.addTransform(position, rotation); e.addRigidBody(false);
+    return e;
+}
+scene_entity makeRod(game_scene& scene, vec3 from, vec3 to) { return makeBare(scene, "Rod", (from + to) * 0.5f, rotateFromTo(mk3(0.f, 1.f, 0.f), normalize(to - from))); }
+} // namespace
+
+void vehicle::initialize(game_scene& scene, vec3 initialMotorPosition, float initialRotation)
+{
+    const float density = 2000.f;
+    parts[motor] = scene.createEntity("Motor");
+    parts[motor].addTransform(mk3(0.f), qIdentity())
+        .addCollider(collider_component::asAABB(bounding_box::fromCenterRadius(mk3(0.f), mk3(0.6f, 0.1f, 1.f)), { physics_material_type_wood, 0.2f, 0.f, density })).addRigidBody(false);
+    const GearDesc motorGearDesc = { 0.1f, 0.2f, 0.f, 8, 0.07f, 0.1f, 0.f, density };
+    const float rodThickness = 0.05f;
+    const GearDesc steeringWheelDesc = { 0.1f, 0.4f, 0.2f, 0, 0.07f, 0.1f, 0.f, density };
+    WheelDesc wheelDesc; wheelDesc.height = 0.3f; wheelDesc.radius = 0.7f; wheelDesc.innerRadius = wheelDesc.radius * 0.4f; wheelDesc.friction = 1.f; wheelDesc.density = 50.f;
+    const float motorGearY = 0.25f, gearOffset = 0.26f;
+
+    parts[motorGear] = makeAxis(scene, mk3(0.f, motorGearY, 0.f), qIdentity(), motorGearDesc);
+    motorConstraint = addHingeConstraintFromGlobalPoints(parts[motor], parts[motorGear], mk3(0.f, motorGearY, 0.f), mk3(0.f, 1.f, 0.f));
+    { hinge_constraint& c = getConstraint(scene, motorConstraint); c.maxMotorTorque = 500.f; c.motorVelocityOrTargetAngle = 0.f; }
+
+    const float driveAxisLength = 4.5f;
+    const Attachment driveAxisAttachment = attachGear(driveAxisLength * 0.57f - 1.1f, rodThickness, motorGearDesc);
+    parts[driveAxis] = makeAxis(scene, mk3(0.f, motorGearY + gearOffset, gearOffset), quatAxisAngle(mk3(-1.f, 0.f, 0.f), deg2rad(90.f)), motorGearDesc, nullptr, &driveAxisAttachment);
+    addHingeConstraintFromGlobalPoints(parts[motor], parts[driveAxis], mk3(0.f, motorGearY + gearOffset, gearOffset), mk3(0.f, 0.f, 1.f));
+
+    const float axisLength = 1.5f, suspensionLength = 0.4f;
+    const float frontAxisOffsetZ = -driveAxisLength * 0.5f + gearOffset * 2.f;
+    const vec3 frontAxisPos = mk3(0.f, motorGearY + gearOffset, frontAxisOffsetZ);
+    parts[frontAxis] = makeRod(scene, frontAxisPos + mk3(axisLength, 0.f, 0.f), frontAxisPos - mk3(axisLength, 0.f, 0.f));
+    addFixedConstraintFromGlobalPoints(parts[motor], parts[frontAxis], frontAxisPos);
+
+    const Attachment steeringWheelAttachment = attachGear(2.f, rodThickness, motorGearDesc);
+    const quat steeringWheelRot = quatAxisAngle(mk3(-1.f, 0.f, 0.f), deg2rad(-80.f));
+    const vec3 steeringWheelPos = mk3(0.f, 1.12f, 0.81f);
+    parts[steeringWheel] = makeAxis(scene, steeringWheelPos, steeringWheelRot, steeringWheelDesc, nullptr, &steeringWheelAttachment);
+    steeringWheelConstraint = addHingeConstraintFromGlobalPoints(parts[motor], parts[steeringWheel], steeringWheelPos, steeringWheelRot * mk3(0.f, -1.f, 0.f));
+    { hinge_constraint& c = getConstraint(scene, steeringWheelConstraint); c.motorType = constraint_position_motor; c.maxMotorTorque = 1000.f; c.motorVelocityOrTargetAngle = 0.f; }
+
+    const vec3 steeringAxisPos = mk3(0.f, motorGearY + gearOffset + 0.06f, frontAxisOffsetZ + 0.49f);
+    const float steeringAxisLength = axisLength * 1.05f;
+    parts[steeringAxis] = makeGearAxis(scene, steeringAxisPos, steeringWheelRot, steeringAxisLength, 8, motorGearDesc.toothLength, motorGearDesc.toothWidth, motorGearDesc.friction, motorGearDesc.density);
+    addSliderConstraintFromGlobalPoints(parts[motor], parts[steeringAxis], steeringAxisPos, mk3(1.f, 0.f, 0.f), -4.f, 4.f);
+    const vec3 leftSteeringAttach = steeringAxisPos - mk3(steeringAxisLength * 0.5f, 0.f, 0.f), rightSteeringAttach = steeringAxisPos + mk3(steeringAxisLength * 0.5f, 0.f, 0.f);
+
+    const vec3 leftSuspPos = frontAxisPos - mk3(axisLength, 0.f, 0.f), leftSuspAttach = leftSuspPos + mk3(0.f, 0.f, suspensionLength);
+    parts[leftWheelSuspension] = makeBare(scene, "Wheel suspension", leftSuspPos, qIdentity());
+    addHingeConstraintFromGlobalPoints(parts[motor], parts[leftWheelSuspension], leftSuspPos, mk3(0.f, 1.f, 0.f), deg2rad(-45.f), deg2rad(45.f));
+    const vec3 rightSuspPos = frontAxisPos + mk3(axisLength, 0.f, 0.f), rightSuspAttach = rightSuspPos + mk3(0.f, 0.f, suspensionLength);
+    parts[rightWheelSuspension] = makeBare(scene, "Wheel suspension", rightSuspPos, qIdentity());
+    addHingeConstraintFromGlobalPoints(parts[motor], parts[rightWheelSuspension], rightSuspPos, mk3(0.f, 1.f, 0.f), deg2rad(-45.f), deg2rad(45.f));
+
+    const vec3 leftFrontWheelPos = leftSuspPos - mk3(suspensionLength * 0.5f, 0.f, 0.f), rightFrontWheelPos = rightSuspPos + mk3(suspensionLength * 0.5f, 0.f, 0.f);
+    parts[leftFrontWheel] = makeWheel(scene, leftFrontWheelPos, quatAxisAngle(mk3(0.f, 0.f, 1.f), deg2rad(90.f)), wheelDesc);
+    parts[rightFrontWheel] = makeWheel(scene, rightFrontWheelPos, quatAxisAngle(mk3(0.f, 0.f, 1.f), deg2rad(90.f)), wheelDesc);
+    addHingeConstraintFromGlobalPoints(parts[leftFrontWheel], parts[leftWheelSuspension], leftFrontWheelPos, mk3(1.f, 0.f, 0.f));
+    addHingeConstraintFromGlobalPoints(parts[rightFrontWheel], parts[rightWheelSuspension], rightFrontWheelPos, mk3(1.f, 0.f, 0.f));
+
+    parts[leftWheelArm] = makeRod(scene, leftSteeringAttach, leftSuspAttach);
+    parts[rightWheelArm] = makeRod(scene, rightSteeringAttach, rightSuspAttach);
+    addBallConstraintFromGlobalPoints(parts[leftWheelSuspension], parts[leftWheelArm], leftSuspAttach);
+    addBallConstraintFromGlobalPoints(parts[steeringAxis], parts[leftWheelArm], leftSteeringAttach);
+    addBallConstraintFromGlobalPoints(parts[rightWheelSuspension], parts[rightWheelArm], rightSuspAttach);
+    addBallConstraintFromGlobalPoints(parts[steeringAxis], parts[rightWheelArm], rightSteeringAttach);
+
+    GearDesc rearAxisGearDesc = motorGearDesc; rearAxisGearDesc.cylinderRadius = 0.5f; rearAxisGearDesc.cylinderInnerRadius = 0.4f; rearAxisGearDesc.numTeeth = 17;
+    const float rearAxisOffsetZ = driveAxisLength * 0.505f, rearAxisOffsetX = -gearOffset;
+    parts[differentialSunGear] = makeAxis(scene, mk3(rearAxisOffsetX, motorGearY + gearOffset, rearAxisOffsetZ), quatAxisAngle(mk3(0.f, 0.f, -1.f), deg2rad(90.f)), rearAxisGearDesc);
+    addHingeConstraintFromGlobalPoints(parts[motor], parts[differentialSunGear], mk3(rearAxisOffsetX, motorGearY + gearOffset, rearAxisOffsetZ), mk3(1.f, 0.f, 0.f));
+
+    const vec3 spiderPos = mk3(0.11f, motorGearY + gearOffset * 2.f, rearAxisOffsetZ);
+    const Attachment spiderAttachment = attachNone(0.2f, 0.02f);
+    parts[differentialSpiderGear] = makeAxis(scene, spiderPos, qIdentity(), motorGearDesc, &spiderAttachment);
+    addHingeConstraintFromGlobalPoints(parts[differentialSunGear], parts[differentialSpiderGear], spiderPos, mk3(0.f, 1.f, 0.f));
+
+    const vec3 leftRearWheelPos = spiderPos + mk3(-gearOffset, -gearOffset, 0.f), rightRearWheelPos = spiderPos + mk3(gearOffset, -gearOffset, 0.f);
+    const Attachment leftWheelAttachment = attachWheel(axisLength + spiderPos.x, rodThickness, wheelDesc), rightWheelAttachment = attachWheel(axisLength - spiderPos.x, rodThickness, wheelDesc);
+    parts[leftRearWheel] = makeAxis(scene, leftRearWheelPos, quatAxisAngle(mk3(0.f, 0.f, -1.f), deg2rad(90.f)), motorGearDesc, nullptr, &leftWheelAttachment);
+    parts[rightRearWheel] = makeAxis(scene, rightRearWheelPos, quatAxisAngle(mk3(0.f, 0.f, -1.f), deg2rad(90.f)), motorGearDesc, &rightWheelAttachment, nullptr);
+    addHingeConstraintFromGlobalPoints(parts[motor], parts[leftRearWheel], leftRearWheelPos, mk3(1.f, 0.f, 0.f));
+    addHingeConstraintFromGlobalPoints(parts[motor], parts[rightRearWheel], rightRearWheelPos, mk3(1.f, 0.f, 0.f));
+
+    const quat rotation = quatAxisAngle(mk3(0.f, 1.f, 0.f), initialRotation);
+    for (int i = 0; i < numParts; ++i)
+    {   // vehicle.cpp:486-496
+        trs& t = parts[i].transform();
+        t.position = rotation * t.position + initialMotorPosition;
+        t.rotation = rotation * t.rotation;
+        const int rb = scene.entities[parts[i].handle].rigidBody;
         scene.physicsTransform0[rb] = scene.physicsTransform1[rb] = t;
     }
 }

@@ -96,12 +96,15 @@ typedef b200phys_fixed_joint fixed_constraint;
 typedef b200phys_hinge_joint hinge_constraint;
 typedef b200phys_cone_twist_joint cone_twist_constraint;
 typedef b200phys_slider_joint slider_constraint;
-struct distance_constraint_handle { uint32_t index; };
-struct ball_constraint_handle { uint32_t index; };
-struct fixed_constraint_handle { uint32_t index; };
-struct hinge_constraint_handle { uint32_t index; };
-struct cone_twist_constraint_handle { uint32_t index; };
-struct slider_constraint_handle { uint32_t index; };
+// physics.h:209-214: a handle names the constraint ENTITY; here a stable id (constraints move inside their pool when another one
+// is deleted: EnTT swap-and-pop, mirrored by deleteConstraint)
+struct distance_constraint_handle { uint32_t entity; };
+struct ball_constraint_handle { uint32_t entity; };
+struct fixed_constraint_handle { uint32_t entity; };
+struct hinge_constraint_handle { uint32_t entity; };
+struct cone_twist_constraint_handle { uint32_t entity; };
+struct slider_constraint_handle { uint32_t entity; };
+enum constraint_type { constraint_type_distance, constraint_type_ball, constraint_type_fixed, constraint_type_hinge, constraint_type_cone_twist, constraint_type_slider, constraint_type_collision, constraint_type_count }; // constraints.h:14-28
 
 // physics.h:291-345: triggers and force fields
 enum trigger_event_type { trigger_event_enter, trigger_event_leave };
@@ -194,6 +197,8 @@ struct game_scene
     std::vector<distance_constraint> distanceConstraints; std::vector<ball_constraint> ballConstraints; std::vector<fixed_constraint> fixedConstraints;
     std::vector<hinge_constraint> hingeConstraints; std::vector<cone_twist_constraint> coneTwistConstraints; std::vector<slider_constraint> sliderConstraints;
     std::vector<b200phys_body_pair> constraintEntities[6];      // (entityA, entityB) per joint, storage order
+    std::vector<uint32_t> constraintIds[6];                     // stable id of the joint at each storage position (the constraint entity)
+    std::vector<int32_t> constraintIndexOfId[6];                // id -> storage position, -1 once deleted
 
     scene_entity createEntity(const char* name);
     uint32_t allocateBoundingHullGeometry(const vec3* vertices, uint32_t numVertices, const indexed_triangle32* triangles, uint32_t numTriangles); // physics.h:207
@@ -227,6 +232,65 @@ fixed_constraint_handle addFixedConstraintFromGlobalPoints(scene_entity& a, scen
 hinge_constraint_handle addHingeConstraintFromGlobalPoints(scene_entity& a, scene_entity& b, vec3 globalAnchor, vec3 globalHingeAxis, float minLimit = 1.f, float maxLimit = -1.f);
 cone_twist_constraint_handle addConeTwistConstraintFromGlobalPoints(scene_entity& a, scene_entity& b, vec3 globalAnchor, vec3 globalAxis, float swingLimit, float twistLimit);
 slider_constraint_handle addSliderConstraintFromGlobalPoints(scene_entity& a, scene_entity& b, vec3 globalAnchor, vec3 globalAxis, float minLimit = 1.f, float maxLimit = -1.f);
+
+// physics.h:237-264
+distance_constraint_handle addConstraint(scene_entity& a, scene_entity& b, const distance_constraint& c);
+ball_constraint_handle addConstraint(scene_entity& a, scene_entity& b, const ball_constraint& c);
+fixed_constraint_handle addConstraint(scene_entity& a, scene_entity& b, const fixed_constraint& c);
+hinge_constraint_handle addConstraint(scene_entity& a, scene_entity& b, const hinge_constraint& c);
+cone_twist_constraint_handle addConstraint(scene_entity& a, scene_entity& b, const cone_twist_constraint& c);
+slider_constraint_handle addConstraint(scene_entity& a, scene_entity& b, const slider_constraint& c);
+distance_constraint& getConstraint(game_scene& scene, distance_constraint_handle handle);
+ball_constraint& getConstraint(game_scene& scene, ball_constraint_handle handle);
+fixed_constraint& getConstraint(game_scene& scene, fixed_constraint_handle handle);
+hinge_constraint& getConstraint(game_scene& scene, hinge_constraint_handle handle);
+cone_twist_constraint& getConstraint(game_scene& scene, cone_twist_constraint_handle handle);
+slider_constraint& getConstraint(game_scene& scene, slider_constraint_handle handle);
+void deleteAllConstraints(game_scene& scene);
+void deleteConstraint(game_scene& scene, distance_constraint_handle handle);
+void deleteConstraint(game_scene& scene, ball_constraint_handle handle);
+void deleteConstraint(game_scene& scene, fixed_constraint_handle handle);
+void deleteConstraint(game_scene& scene, hinge_constraint_handle handle);
+void deleteConstraint(game_scene& scene, cone_twist_constraint_handle handle);
+void deleteConstraint(game_scene& scene, slider_constraint_handle handle);
+void deleteAllConstraintsFromEntity(scene_entity& entity);
+
+// physics.h:273-337: range-for over the colliders of an entity (most recently added first) and over its constraints
+struct collider_component_iterator
+{
+    explicit collider_component_iterator(scene_entity e) : scene(e.scene), first(e ? e.scene->entities[e.handle].firstColliderEntity : null_entity) {}
+    struct iterator
+    {
+        game_scene* scene; entity_handle collider;
+        friend bool operator!=(const iterator& a, const iterator& b) { return a.collider != b.collider; }
+        iterator& operator++() { collider = scene->colliders[collider].nextEntity; return *this; }
+        collider_component& operator*() { return scene->colliders[collider]; }
+    };
+    iterator begin() { return iterator{ scene, first }; }
+    iterator end() { return iterator{ scene, null_entity }; }
+    game_scene* scene; entity_handle first;
+};
+struct constraint_entity_iterator
+{   // yields (other entity, constraint_type, storage index) for every joint attached to the entity; order: by kind, then storage order
+    // (the reference walks a per-entity edge list, physics.cpp:87-126: most recently added first -- the SET is the same)
+    struct item { scene_entity other; constraint_type type; uint32_t index; };
+    explicit constraint_entity_iterator(scene_entity e);
+    std::vector<item> items;
+    std::vector<item>::iterator begin() { return items.begin(); }
+    std::vector<item>::iterator end() { return items.end(); }
+};
+
+// vehicle.h:5-40 (16 parts; hinge joints with a velocity motor (engine) and a position motor (steering wheel), hinge limits, one fixed,
+// one slider with limits, four ball joints): the acceptance scene for the joint kinds the ragdoll does not use
+struct vehicle
+{
+    enum { motor, motorGear, driveAxis, frontAxis, steeringWheel, steeringAxis, leftWheelSuspension, rightWheelSuspension, leftFrontWheel, rightFrontWheel,
+           leftWheelArm, rightWheelArm, differentialSunGear, differentialSpiderGear, leftRearWheel, rightRearWheel, numParts };
+    scene_entity parts[numParts];
+    hinge_constraint_handle motorConstraint, steeringWheelConstraint;
+    void initialize(game_scene& scene, vec3 initialMotorPosition, float initialRotation = 0.f);   // vehicle.cpp:303-497
+    static vehicle create(game_scene& scene, vec3 initialMotorPosition, float initialRotation = 0.f) { vehicle v; v.initialize(scene, initialMotorPosition, initialRotation); return v; }
+};
 
 // ragdoll.h:7-60 (14 bodies, 17 colliders, 7 cone-twist + 6 hinge joints)
 struct humanoid_ragdoll

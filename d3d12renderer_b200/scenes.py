@@ -246,3 +246,105 @@ def event_zoo(per_type=6, seed=99):
     return {"bodies": bodies, "colliders": colliders, "transforms": transforms, "joints": {}, "name": "event_zoo",
             "hull_vertices": hull, "hull_offsets": np.array([0, len(hull)], dtype=np.uint32), "hull_triangles": [tris],
             "force_fields": force_fields, "global_force": np.array([0.0, 0.0, 0.75], dtype=np.float32)}
+
+
+def contact_zoo(per_pair=16, seed=4242, spacing=4.0):
+    """Narrow-phase test scene: for each of the 21 ordered collider type pairs (collision_narrow.cpp:374-1584) `per_pair` two-body
+    instances that interpenetrate -- random relative poses plus the special configurations the routines branch on (parallel capsule /
+    cylinder axes, cylinder cap-to-cap, segment shapes lying flat on a box face, axis-aligned boxes on every side, sphere centre inside
+    a box, coincident sphere centres). Instances sit on a lattice `spacing` apart so that only the intended pairs touch. A body keeps
+    an AABB collider only while its rotation is exactly identity (physics.cpp:722-734), so AABB bodies are never rotated here.
+    No static geometry. Returns the usual scene dict; body 2k and 2k+1 form instance k."""
+    rng = np.random.default_rng(seed)
+    types = [abi.SPHERE, abi.CAPSULE, abi.CYLINDER, abi.AABB, abi.OBB, abi.HULL]
+    pairs = [(a, b) for a in types for b in types if a <= b]
+    n_inst = len(pairs) * per_pair
+    n = 2 * n_inst
+    bodies = new_bodies(n)
+    set_sphere_bodies(bodies, np.arange(n), F(0.4), F(1.0))
+    colliders = np.zeros(n, dtype=abi.collider_dtype)
+    colliders["restitution"] = 0.1; colliders["friction"] = 0.5; colliders["density"] = 1.0
+    colliders["parentTransform"] = abi.NO_TRANSFORM
+    colliders["objectType"] = abi.OBJ_RIGID_BODY; colliders["objectIndex"] = np.arange(n, dtype=np.uint32)
+    # two hull geometries: octahedron (6 vertices) and an irregular 8-vertex frustum
+    octa = np.array([[0.45, 0, 0], [-0.45, 0, 0], [0, 0.45, 0], [0, -0.45, 0], [0, 0, 0.45], [0, 0, -0.45]], dtype=np.float32)
+    octa_t = np.array([0, 2, 4, 2, 1, 4, 1, 3, 4, 3, 0, 4, 2, 0, 5, 1, 2, 5, 3, 1, 5, 0, 3, 5], dtype=np.uint32)
+    fr = np.array([[-0.5, -0.4, -0.5], [0.5, -0.4, -0.5], [0.5, -0.4, 0.5], [-0.5, -0.4, 0.5], [-0.3, 0.4, -0.3], [0.3, 0.4, -0.3], [0.3, 0.4, 0.3], [-0.3, 0.4, 0.3]], dtype=np.float32)
+    fr_t = np.array([0, 1, 2, 0, 2, 3, 4, 6, 5, 4, 7, 6, 0, 4, 5, 0, 5, 1, 1, 5, 6, 1, 6, 2, 2, 6, 7, 2, 7, 3, 3, 7, 4, 3, 4, 0], dtype=np.uint32)
+
+    def rand_quat():
+        ax = rng.normal(size=3); ax /= np.linalg.norm(ax); ang = rng.uniform(0, np.pi)
+        return np.concatenate([ax * np.sin(ang / 2), [np.cos(ang / 2)]]).astype(np.float32)
+
+    def set_shape(i, t, k):
+        s = colliders["shape"][i]; s[:] = 0
+        if t == abi.SPHERE:
+            s[0:3] = rng.uniform(-0.05, 0.05, 3); s[3] = rng.uniform(0.3, 0.5)
+        elif t in (abi.CAPSULE, abi.CYLINDER):
+            h = rng.uniform(0.25, 0.5); s[0:3] = (0, -h, 0); s[3:6] = (0, h, 0); s[6] = rng.uniform(0.15, 0.3)
+        elif t == abi.AABB:
+            r = rng.uniform(0.25, 0.5, 3); s[0:3] = -r; s[3:6] = r
+        elif t == abi.OBB:
+            s[0:4] = rand_quat() if (k & 1) else (0, 0, 0, 1); s[4:7] = rng.uniform(-0.05, 0.05, 3); s[7:10] = rng.uniform(0.25, 0.5, 3)
+        else:
+            s[0:4] = rand_quat() if (k & 1) else (0, 0, 0, 1); s[4:7] = rng.uniform(-0.05, 0.05, 3); s[7:8].view(np.uint32)[0] = k & 1
+        colliders["type"][i] = t
+
+    side = int(np.ceil(np.sqrt(n_inst)))
+    inst = 0
+    for (ta, tb) in pairs:
+        for k in range(per_pair):
+            ia, ib = 2 * inst, 2 * inst + 1
+            base = np.array([(inst % side) * spacing, 5.0 + 0.37 * (inst % 3), (inst // side) * spacing], dtype=np.float32)
+            set_shape(ia, ta, k); set_shape(ib, tb, k + 1)
+            qa = np.array([0, 0, 0, 1], dtype=np.float32) if ta == abi.AABB else rand_quat()
+            qb = np.array([0, 0, 0, 1], dtype=np.float32) if tb == abi.AABB else rand_quat()
+            off = rng.normal(size=3); off = off / np.linalg.norm(off) * rng.uniform(0.05, 0.65)
+            special = k % 8
+            seg = (abi.CAPSULE, abi.CYLINDER)
+            if ta in seg and tb in seg and special in (1, 2, 3):
+                qb = qa.copy()                                  # parallel axes (|cos| > 0.99 branch)
+                R = _quat_to_mat(qa)
+                if special == 1: off = R @ np.array([0.3, 0.2, 0.0])            # side by side, overlapping intervals -> 2 contacts
+                elif special == 2: off = R @ np.array([0.05, 0.75, 0.0])        # end to end (disjoint intervals / cap to cap)
+                else: off = R @ np.array([0.25, 0.55, 0.1])                     # partial interval overlap
+            elif ta in seg and tb in (abi.AABB, abi.OBB) and special in (1, 2):
+                # segment shape lying flat on the +y face of the box: EPA normal along a box axis, axis perpendicular to it -> 2-point clip
+                if tb == abi.OBB:
+                    colliders["shape"][ib][0:4] = (0, 0, 0, 1)
+                Rb = _quat_to_mat(qb)
+                qa = _quat_mul(qb, np.array([0, 0, np.sin(np.pi / 4), np.cos(np.pi / 4)], dtype=np.float32))    # capsule axis along the box's x
+                ry = colliders["shape"][ib][4] if tb == abi.AABB else colliders["shape"][ib][8]
+                off = -(Rb @ np.array([0.02 * special, ry + colliders["shape"][ia][6] * 0.8, 0.03]))
+            elif ta == abi.AABB and tb == abi.AABB:
+                axis = special % 3; sign = 1.0 if (special & 1) else -1.0
+                off = rng.uniform(-0.1, 0.1, 3); off[axis] = sign * rng.uniform(0.3, 0.6)                   # min-overlap axis with both signs (quirk B13)
+            elif ta == abi.SPHERE and tb == abi.SPHERE and special == 1:
+                off = np.zeros(3); colliders["shape"][ia][0:3] = 0; colliders["shape"][ib][0:3] = 0       # coincident centres -> normal (0,1,0)
+            elif ta == abi.SPHERE and tb in (abi.AABB, abi.OBB) and special == 1:
+                off = rng.uniform(-0.05, 0.05, 3)                                                          # sphere centre inside the box
+            elif ta == abi.OBB and tb == abi.OBB and special in (1, 2):
+                colliders["shape"][ia][0:4] = (0, 0, 0, 1); colliders["shape"][ib][0:4] = (0, 0, 0, 1)
+                qb = qa.copy() if special == 1 else _quat_mul(qa, np.array([0, np.sin(0.3), 0, np.cos(0.3)], dtype=np.float32))
+                off = _quat_to_mat(qa) @ np.array([0.1, 0.55, 0.05])                                       # face-face stacks (4-point manifolds, reduction)
+            bodies["position"][ia] = base + 0.5 * off.astype(np.float32); bodies["position"][ib] = base - 0.5 * off.astype(np.float32)
+            bodies["rotation"][ia] = qa; bodies["rotation"][ib] = qb
+            bodies["linearVelocity"][ia] = rng.uniform(-1, 1, 3); bodies["linearVelocity"][ib] = rng.uniform(-1, 1, 3)
+            bodies["angularVelocity"][ia] = rng.uniform(-1, 1, 3) if ta != abi.AABB else 0; bodies["angularVelocity"][ib] = rng.uniform(-1, 1, 3) if tb != abi.AABB else 0
+            inst += 1
+    transforms = np.zeros(1, dtype=abi.transform_dtype); transforms["rotation"][0, 3] = 1.0
+    verts = np.concatenate([octa, fr]); offs = np.array([0, len(octa), len(octa) + len(fr)], dtype=np.uint32)
+    return {"bodies": bodies, "colliders": colliders, "transforms": transforms, "joints": {}, "name": "contact_zoo_%d" % per_pair,
+            "hull_vertices": verts, "hull_offsets": offs, "hull_triangles": [octa_t, fr_t], "pair_types": pairs, "per_pair": per_pair}
+
+
+def _quat_to_mat(q):
+    x, y, z, w = [float(v) for v in q]
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                     [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                     [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+
+
+def _quat_mul(a, b):
+    ax, ay, az, aw = [float(v) for v in a]; bx, by, bz, bw = [float(v) for v in b]
+    return np.array([aw * bx + ax * bw + ay * bz - az * by, aw * by - ax * bz + ay * bw + az * bx, aw * bz + ax * by - ay * bx + az * bw, aw * bw - ax * bx - ay * by - az * bz], dtype=np.float32)

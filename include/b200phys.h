@@ -224,7 +224,11 @@ int b200phys_enable_timing(b200phys_context* ctx, int enabled);
 void* b200phys_host_alloc(size_t bytes);
 void b200phys_host_free(void* p);
 
-/* scene upload (host -> device): replaces the EnTT pool walks of physics.cpp:631-756, 789-805, 1266-1276 ------------ */
+/* scene upload (host -> device): replaces the EnTT pool walks of physics.cpp:631-756, 789-805, 1266-1276 ------------
+ * Buffer lifetime: uploads are enqueued (cudaMemcpyAsync) on the context's stream and return immediately. Pageable host
+ * memory is staged by the driver before the call returns and may be reused at once. PAGE-LOCKED memory (b200phys_host_alloc,
+ * cudaHostAlloc) is read by DMA later: it must stay untouched until the next call that synchronises the context has returned
+ * (b200phys_synchronize, any b200phys_download_*, b200phys_get_stats). */
 int b200phys_set_hulls(b200phys_context* ctx, const float* vertices, const uint32_t* vertexOffsets, uint32_t numHulls);
 int b200phys_upload_bodies(b200phys_context* ctx, const b200phys_body* bodies, uint32_t count);
 int b200phys_upload_transforms(b200phys_context* ctx, const b200phys_transform* transforms, uint32_t count);

@@ -1,0 +1,179 @@
+"""GPU parity tests, second set (round 2): what round 1 left untested.
+
+  * 16 K - 32 K-body sub-scenes of BASELINE configs 2, 3 and 4 (the grid with many cells, big-collider path, EPA work list, colour
+    inheritance at a size where warps, CTAs and scans wrap around), pairs bit-exact, contacts <= 1e-5, states <= 1e-4, every overflow /
+    cap counter zero or equal to the oracle's;
+  * a contact-level comparison of all 21 collider type pairs, the six cylinder pairs and AABB-AABB included;
+  * distance / ball / fixed / slider joints and every motor and limit of hinge, cone-twist and slider; the vehicle acceptance scene;
+  * contact / manifold capacity overflow is reported and memory-safe.
+All of them call the CUDA path through the C ABI and compare with the CPU oracle on the same seeded inputs."""
+import numpy as np
+import pytest
+
+from d3d12renderer_b200 import abi, scenes, host
+import oracle_lib
+from test_gpu_parity import make_stepper, rel_err, assert_states_close, run_both, check_detection, DT
+
+pytestmark = pytest.mark.gpu
+
+
+def assert_no_overflow(stats, oracle):
+    ns = oracle.narrow_stats()
+    assert stats.overflowPairs == 0 and stats.overflowManifolds == 0 and stats.overflowGrid == 0
+    assert stats.epaOverflows == 0 and ns["epaOutOfMemory"] == 0
+    assert stats.gjkIterationCaps == ns["gjkIterCap"] and stats.assertCount == ns["asserts"]
+
+
+@pytest.mark.parametrize("flags", [abi.STEP_FAST, abi.STEP_EXACT_ORDER])
+def test_config2_subscene_32k_spheres(flags):
+    """BASELINE config 2 at 32 768 spheres (32^3 settled pile in the open box): ~400 k pairs, ~96 k contacts."""
+    sc = scenes.sphere_pile_settled(32, 32, 32)
+    r = run_both(sc, iterations=10, flags=flags)
+    check_detection(r)
+    assert r["stats"].numBroadphaseOverlaps > 300000 and r["stats"].numContacts > 80000
+    assert_no_overflow(r["stats"], r["oracle"])
+    assert_states_close(r["gpu_states"], r["ref_states"], 1e-4)
+
+
+def test_config2_subscene_trajectory_crosses_recolouring():
+    """12 consecutive fast-mode steps of a 16 K pile: a full colouring, seven inherited orders, another full colouring, each replayed by the
+    oracle; pair list and contacts stay bit-exact every step."""
+    sc = scenes.sphere_pile_settled(32, 16, 32)
+    st = make_stepper(sc); orc = oracle_lib.Oracle(sc, canonical=True)
+    for step in range(12):
+        st.step(DT, 10, abi.STEP_FAST)
+        order = st.download_solve_order(6)
+        orc.step(DT, 10, contact_order=order)
+        assert np.array_equal(st.download_pairs(), orc.pairs()), "pairs differ at step %d" % step
+        c, b = st.download_contacts(); rc, rb = orc.contacts()
+        assert np.array_equal(b, rb) and rel_err(c["penetrationDepth"], rc["penetrationDepth"]) <= 1e-5
+        assert_states_close(st.download_bodies(), orc.body_states(), 1e-4)
+    assert st.stats().overflowPairs == 0
+
+
+@pytest.mark.parametrize("flags", [abi.STEP_FAST, abi.STEP_EXACT_ORDER])
+def test_config3_subscene_32k_mixed_primitives(flags):
+    """BASELINE config 3 at 32 768 bodies (sphere / capsule / OBB / hull round robin, random orientations, tight lattice): closed-form,
+    SAT + clipping and GJK + EPA routines all busy (~130 k manifolds); the EPA work list and its caps at scale."""
+    sc = host.build_scene(host.CONFIG_MIXED_PILE, 32, 32, 32, seed=1578123, spacing=0.72)
+    r = run_both(sc, iterations=10, flags=flags)
+    check_detection(r, contact_tol=1e-5)
+    assert r["stats"].numContacts > 100000
+    assert_no_overflow(r["stats"], r["oracle"])
+    assert_states_close(r["gpu_states"], r["ref_states"], 1e-4)
+
+
+def test_config3_subscene_trajectory():
+    sc = host.build_scene(host.CONFIG_MIXED_PILE, 32, 16, 32, seed=77, spacing=0.8)
+    r = run_both(sc, iterations=10, steps=4)
+    check_detection(r, contact_tol=1e-5)
+    assert_no_overflow(r["stats"], r["oracle"])
+    assert_states_close(r["gpu_states"], r["ref_states"], 1e-4)
+
+
+@pytest.mark.parametrize("flags", [abi.STEP_FAST, abi.STEP_EXACT_ORDER])
+def test_config4_subscene_16k_ragdoll_bodies(flags):
+    """BASELINE config 4 at 1 156 ragdolls = 16 184 bodies, 19 652 colliders, 8 092 cone-twist + 6 936 hinge joints, packed so
+    tightly that neighbouring figures collide; 30 steps so that feet reach the ground and limits engage."""
+    sc = host.build_scene(host.CONFIG_RAGDOLLS, 34, 1, 34, seed=20260924, mode=0, spacing=0.7)
+    assert len(sc["bodies"]) == 16184 and len(sc["joints"][4][0]) == 1156 * 7 and len(sc["joints"][3][0]) == 1156 * 6
+    r = run_both(sc, iterations=10, flags=flags, steps=30)
+    check_detection(r, contact_tol=1e-5)
+    assert r["stats"].numContacts > 2000
+    assert_no_overflow(r["stats"], r["oracle"])
+    assert_states_close(r["gpu_states"], r["ref_states"], 1e-4)
+
+
+# ----------------------------------------------------------------------------------------- all 21 narrow-phase routines
+def test_contact_zoo_every_type_pair_per_contact():
+    """Every one of the 21 `intersection(A, B)` routines (collision_narrow.cpp:374-1584) produces manifolds here -- the six cylinder
+    pairs and AABB-AABB included -- and every contact (point, normal, depth, packed material, body pair) is compared with the oracle.
+    The narrow phase uses + - * / sqrt only and the library is built without FMA contraction: agreement is expected to the last bit
+    (tolerance 1e-6 relative as the written bar)."""
+    sc = scenes.contact_zoo(per_pair=24)
+    r = run_both(sc, iterations=10, flags=abi.STEP_EXACT_ORDER)
+    check_detection(r, contact_tol=1e-6)
+    pairs, counts = r["stepper"].download_collisions()
+    rp, rk = r["oracle"].collisions()
+    assert np.array_equal(pairs, rp) and np.array_equal(counts, rk)
+    col = sc["colliders"]
+    ta = np.minimum(col["type"][pairs["a"]], col["type"][pairs["b"]]).astype(int); tb = np.maximum(col["type"][pairs["a"]], col["type"][pairs["b"]]).astype(int)
+    for a in range(6):
+        for b in range(a, 6):
+            hit = (ta == a) & (tb == b)
+            assert hit.sum() >= 12, "type pair (%d, %d) produced only %d manifolds" % (a, b, hit.sum())
+    # multi-point manifolds exist for the routines that can produce them
+    for a, b in [(1, 1), (1, 2), (2, 2), (1, 3), (2, 3), (3, 3), (3, 4), (4, 4)]:
+        assert (counts[(ta == a) & (tb == b)] > 1).any(), (a, b)
+    assert_no_overflow(r["stats"], r["oracle"])
+    assert_states_close(r["gpu_states"], r["ref_states"], 1e-4)
+
+
+# ---------------------------------------------------------------------------------------------- joints, motors, vehicle
+def _step_compare(sc, steps, flags, tol, iterations=30):
+    st = make_stepper(sc); orc = oracle_lib.Oracle(sc, canonical=True)
+    for step in range(steps):
+        st.step(DT, iterations, flags)
+        if flags == abi.STEP_EXACT_ORDER:
+            orc.step(DT, iterations)
+        else:
+            orc.step(DT, iterations, contact_order=st.download_solve_order(6), joint_orders={k: st.download_solve_order(k) for k in sc["joints"]})
+        gpu, ref = st.download_bodies(), orc.body_states()
+        for f in ("position", "rotation", "linearVelocity", "angularVelocity"):
+            e = rel_err(gpu[f], ref[f])
+            assert e <= tol, "step %d: %s differs by %g" % (step, f, e)
+    assert np.array_equal(st.download_pairs(), orc.pairs())
+    return st, orc
+
+
+@pytest.mark.parametrize("flags", [abi.STEP_FAST, abi.STEP_EXACT_ORDER])
+def test_joint_zoo_all_kinds_motors_and_limits(flags):
+    """Distance, ball, fixed and slider joints (constraints.cpp:189-264,460-528,736-823,2638-2846) plus hinge / cone-twist / slider with
+    velocity motors, position motors and limits, hanging from kinematic anchors; 8 copies, 40 steps, compared after EVERY step."""
+    sc = host.build_scene(host.CONFIG_JOINT_ZOO, 4, 1, 2, seed=11, mode=0, spacing=30.0)
+    counts = {k: len(v[0]) for k, v in sc["joints"].items()}
+    assert counts == {0: 24, 1: 24, 2: 8, 3: 24, 4: 24, 5: 16}
+    st, orc = _step_compare(sc, 40, flags, 1e-4)
+    s = st.stats()
+    assert s.assertCount == orc.narrow_stats()["asserts"]
+    # the mechanisms really moved: the velocity-motor hinge turned, the slider ran into its limit
+    moved = np.abs(st.download_bodies()["position"] - sc["bodies"]["position"]).max(axis=1)
+    assert (moved > 0.05).sum() >= 60
+
+
+def test_vehicle_scene_matches_the_oracle():
+    """The reference's vehicle (vehicle.cpp:303-497): 16 parts, 11 hinges (engine velocity motor, steering position motor, suspension
+    limits), 1 fixed, 1 slider with limits, 4 ball joints, gear-tooth capsules and wheel cylinders; six of them with the motors running
+    drop on the ground and drive for 60 steps."""
+    sc = host.build_scene(host.CONFIG_VEHICLES, 3, 1, 2, seed=5, mode=1, spacing=8.0)
+    assert len(sc["bodies"]) == 6 * 16 and {k: len(v[0]) for k, v in sc["joints"].items()} == {1: 24, 2: 6, 3: 66, 5: 6}
+    st, orc = _step_compare(sc, 60, abi.STEP_FAST, 1e-4)
+    c, _ = st.download_contacts(); rc, _ = orc.contacts()
+    assert len(c) == len(rc) and len(c) > 20
+    assert rel_err(c["point"], rc["point"]) <= 1e-4
+
+
+# --------------------------------------------------------------------------------------------------- capacity handling
+def test_contact_and_manifold_capacity_overflow_is_safe():
+    """running out of CONTACT capacity while manifold capacity is left (and vice versa) must cut both lists consistently:
+    the step keeps running on a prefix of the canonical manifold list, reports B200PHYS_E_CAPACITY, and every downloaded manifold /
+    contact / body pair is a valid prefix of the full result."""
+    sc = host.build_scene(host.CONFIG_MIXED_PILE, 8, 6, 8, seed=3, spacing=0.72)
+    full = make_stepper(sc); full.step(DT, 10, abi.STEP_EXACT_ORDER)
+    fc, fb = full.download_contacts(); fp, fk = full.download_collisions()
+    assert len(fc) > 600 and (fk > 1).any()
+    for kw in (dict(max_contacts=300), dict(max_manifolds=200), dict(max_contacts=257, max_manifolds=300)):
+        small = make_stepper(sc, **kw)
+        for _ in range(2):
+            small.step(DT, 10, abi.STEP_EXACT_ORDER)
+        with pytest.raises(abi.B200PhysError):
+            small.stats()
+        s = small.stats(check=False)
+        assert s.overflowManifolds == 1
+        assert np.all(np.isfinite(small.download_bodies()["position"]))
+        small2 = make_stepper(sc, **kw); small2.step(DT, 10, abi.STEP_EXACT_ORDER)
+        c, b = small2.download_contacts(); p, k = small2.download_collisions()
+        assert len(c) <= kw.get("max_contacts", 1 << 30) and len(p) <= kw.get("max_manifolds", 1 << 30)
+        assert int(k.sum()) == len(c), "manifold and contact lists must be cut together"
+        assert np.array_equal(p, fp[:len(p)]) and np.array_equal(k, fk[:len(k)]) and np.array_equal(b, fb[:len(b)])
+        assert np.array_equal(c["point"], fc["point"][:len(c)])
