@@ -1,0 +1,164 @@
+"""ctypes binding of oracle/_ref/libref.so -- the reference's OWN physics code (pkurth/D3D12Renderer src/physics, src/scene, EnTT)
+compiled with g++ by oracle/ref_build (TEST INFRASTRUCTURE ONLY: the checker of the checker, and bench.py's CPU baseline)."""
+import ctypes as C
+import os
+import numpy as np
+
+from d3d12renderer_b200 import abi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB = os.path.join(ROOT, "oracle", "_ref", "libref.so")
+LIB_FAST = os.path.join(ROOT, "oracle", "_ref", "libref_fast.so")
+_libs = {}
+
+
+def available(fast=False):
+    return os.path.exists(LIB_FAST if fast else LIB)
+
+
+def load(fast=False):
+    key = bool(fast)
+    if key in _libs:
+        return _libs[key]
+    lib = C.CDLL(LIB_FAST if fast else LIB)
+    vp, u32, f32, i32 = C.c_void_p, C.c_uint32, C.c_float, C.c_int
+    lib.ref_scene_create.restype = vp
+    lib.ref_scene_destroy.argtypes = [vp]
+    lib.ref_set_hulls.argtypes = [vp, vp, u32, vp, vp]
+    lib.ref_scene_build.argtypes = [vp, vp, u32, vp, u32, vp, u32]
+    lib.ref_scene_get_bodies.argtypes = [vp, vp]
+    lib.ref_scene_add_joints.argtypes = [vp, i32, vp, vp, u32]
+    lib.ref_scene_set_force_fields.argtypes = [vp, vp, u32, vp]
+    lib.ref_scene_add_ragdoll.argtypes = [vp, vp, f32]; lib.ref_scene_add_ragdoll.restype = u32
+    lib.ref_scene_add_vehicle.argtypes = [vp, vp, f32, f32, f32]; lib.ref_scene_add_vehicle.restype = u32
+    lib.ref_scene_add_ground.argtypes = [vp, vp, vp, vp, f32, f32, f32]
+    for n in ("ref_scene_num_bodies", "ref_scene_num_colliders"):
+        getattr(lib, n).argtypes = [vp]; getattr(lib, n).restype = u32
+    lib.ref_scene_num_joints.argtypes = [vp, i32]; lib.ref_scene_num_joints.restype = u32
+    lib.ref_scene_set_hinge_motor.argtypes = [vp, u32, i32, f32, f32]
+    lib.ref_scene_step.argtypes = [vp, f32, u32, i32, u32, i32, i32, i32]
+    lib.ref_scene_last_step_seconds.argtypes = [vp]; lib.ref_scene_last_step_seconds.restype = C.c_double
+    lib.ref_scene_get_states.argtypes = [vp, vp]
+    lib.ref_scene_body_storage_index.argtypes = [vp, u32]; lib.ref_scene_body_storage_index.restype = u32
+    lib.ref_scene_detect.argtypes = [vp, i32, i32, vp, vp, vp, u32, vp, vp, vp, vp, u32, vp]
+    lib.ref_collide_pair.argtypes = [vp, vp, i32, vp, vp]; lib.ref_collide_pair.restype = i32
+    lib.ref_random_floats01.argtypes = [C.c_uint64, vp, u32]
+    lib.ref_mass_properties.argtypes = [vp, vp, vp, vp]
+    lib.ref_assert_count.argtypes = [i32]; lib.ref_assert_count.restype = u32
+    _libs[key] = lib
+    return lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def set_hulls(scene, fast=False):
+    """Hull geometries are process-global in the reference (physics.cpp:14)."""
+    lib = load(fast)
+    if "hull_vertices" not in scene:
+        lib.ref_set_hulls(None, None, 0, None, None); return
+    v = np.ascontiguousarray(scene["hull_vertices"], dtype=np.float32); o = np.ascontiguousarray(scene["hull_offsets"], dtype=np.uint32)
+    tris = [np.ascontiguousarray(t, dtype=np.uint32) for t in scene["hull_triangles"]]
+    to = np.zeros(len(tris) + 1, dtype=np.uint32); to[1:] = np.cumsum([len(t) // 3 for t in tris])
+    t = np.concatenate(tris) if tris else np.zeros(0, dtype=np.uint32)
+    lib.ref_set_hulls(_p(v), _p(o), len(o) - 1, _p(t), _p(to))
+
+
+class RefScene:
+    """One game_scene of the compiled reference."""
+
+    def __init__(self, scene=None, fast=False):
+        self.lib = load(fast); self.fast = fast
+        self.ptr = C.c_void_p(self.lib.ref_scene_create())
+        if scene is not None:
+            self.build(scene)
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                self.lib.ref_scene_destroy(self.ptr); self.ptr = None
+        except Exception:
+            pass
+
+    def build(self, scene):
+        set_hulls(scene, self.fast)
+        b = np.ascontiguousarray(scene["bodies"]); t = np.ascontiguousarray(scene["transforms"]); c = np.ascontiguousarray(scene["colliders"])
+        self.lib.ref_scene_build(self.ptr, _p(b), len(b), _p(t), len(t), _p(c), len(c))
+        for kind, (joints, pairs) in sorted(scene.get("joints", {}).items()):
+            j = np.ascontiguousarray(joints); p = np.ascontiguousarray(pairs)
+            self.lib.ref_scene_add_joints(self.ptr, kind, _p(j), _p(p), len(j))
+        if "force_fields" in scene:
+            f = np.ascontiguousarray(scene["force_fields"], dtype=np.float32); g = np.ascontiguousarray(scene.get("global_force", np.zeros(3)), dtype=np.float32)
+            self.lib.ref_scene_set_force_fields(self.ptr, _p(f), len(f), _p(g))
+
+    def add_ragdoll(self, hip, rotation=0.0):
+        h = np.ascontiguousarray(hip, dtype=np.float32); return self.lib.ref_scene_add_ragdoll(self.ptr, _p(h), rotation)
+
+    def add_vehicle(self, pos, rotation=0.0):
+        h = np.ascontiguousarray(pos, dtype=np.float32); return self.lib.ref_scene_add_vehicle(self.ptr, _p(h), rotation, 0.0, 0.0)
+
+    def add_ground(self, center, radius, position, restitution=0.1, friction=1.0, density=4.0):
+        c = np.ascontiguousarray(center, dtype=np.float32); r = np.ascontiguousarray(radius, dtype=np.float32); p = np.ascontiguousarray(position, dtype=np.float32)
+        self.lib.ref_scene_add_ground(self.ptr, _p(c), _p(r), _p(p), restitution, friction, density)
+
+    def set_hinge_motor(self, index, motor_type, value, max_torque):
+        self.lib.ref_scene_set_hinge_motor(self.ptr, index, motor_type, value, max_torque)
+
+    def num_bodies(self): return self.lib.ref_scene_num_bodies(self.ptr)
+    def num_colliders(self): return self.lib.ref_scene_num_colliders(self.ptr)
+    def num_joints(self, kind): return self.lib.ref_scene_num_joints(self.ptr, kind)
+
+    def step(self, dt, iterations, simd=False, fixed_frame_rate=False, frame_rate=120):
+        """physicsStep; fixed_frame_rate False = exactly one physicsStepInternal(dt) (physics.cpp:1404-1412)."""
+        s = 1 if simd else 0
+        self.lib.ref_scene_step(self.ptr, dt, iterations, 1 if fixed_frame_rate else 0, frame_rate, s, s, s)
+
+    def last_step_seconds(self): return self.lib.ref_scene_last_step_seconds(self.ptr)
+
+    def body_states(self):
+        out = np.zeros(self.num_bodies(), dtype=abi.body_state_dtype); self.lib.ref_scene_get_states(self.ptr, _p(out)); return out
+
+    def bodies(self):
+        out = np.zeros(self.num_bodies(), dtype=abi.body_dtype); self.lib.ref_scene_get_bodies(self.ptr, _p(out)); return out
+
+    def storage_indices(self):
+        return np.array([self.lib.ref_scene_body_storage_index(self.ptr, i) for i in range(self.num_bodies())], dtype=np.uint32)
+
+    def detect(self, simd=False):
+        """getWorldSpaceColliders -> broadphase -> narrowphase on the current state -> dict (pairs in the reference's SAP order)."""
+        nc = self.num_colliders()
+        cap_p = nc * 64 + 5000
+        aabbs = np.zeros((nc, 6), dtype=np.float32); world = np.zeros((nc, 16), dtype=np.float32)
+        counts = np.zeros(5, dtype=np.uint32)
+        s = 1 if simd else 0
+        while True:
+            pairs = np.zeros((cap_p, 2), dtype=np.uint32); cap_c = 4 * cap_p
+            contacts = np.zeros(cap_c, dtype=abi.contact_dtype); cb = np.zeros(cap_c, dtype=abi.body_pair_dtype)
+            cpairs = np.zeros((cap_c, 2), dtype=np.uint32); ccounts = np.zeros(cap_c, dtype=np.uint8)
+            # detection mutates the SAP context; callers use a fresh scene per call or accept that
+            self.lib.ref_scene_detect(self.ptr, s, s, _p(aabbs), _p(world), _p(pairs), cap_p, _p(contacts), _p(cb), _p(cpairs), _p(ccounts), cap_c, _p(counts))
+            if counts[1] <= cap_p:
+                break
+            cap_p = int(counts[1]) + 16
+        return dict(aabbs=aabbs, world=world, pairs=pairs[:counts[1]], contacts=contacts[:counts[3]], contact_bodies=cb[:counts[3]],
+                    collision_pairs=cpairs[:counts[2]], contact_counts=ccounts[:counts[2]], num_interactions=int(counts[4]))
+
+
+def collide_pair(col_a, col_b, simd=False, fast=False):
+    lib = load(fast)
+    a = np.ascontiguousarray(col_a); b = np.ascontiguousarray(col_b)
+    normal = np.zeros(3, dtype=np.float32); pd = np.zeros((4, 4), dtype=np.float32)
+    n = lib.ref_collide_pair(_p(a), _p(b), 1 if simd else 0, _p(normal), _p(pd))
+    return n, normal, pd[:min(n, 4)]
+
+
+def random_floats01(seed, n):
+    out = np.zeros(n, dtype=np.float32); load().ref_random_floats01(seed, _p(out), n); return out
+
+
+def mass_properties(collider):
+    c = np.ascontiguousarray(collider)
+    inertia = np.zeros(9, dtype=np.float32); cog = np.zeros(3, dtype=np.float32); mass = np.zeros(1, dtype=np.float32)
+    load().ref_mass_properties(_p(c), _p(inertia), _p(cog), _p(mass))
+    return inertia, cog, float(mass[0])
