@@ -1,13 +1,18 @@
 #!/usr/bin/env python
-"""bench.py -- physics steps/sec of the B200-native rigid-body stepper on BASELINE.json's single-GPU headline configuration
-(configs[1]: 262 144 spheres box-drop pile, 10 PGS iterations), one process per GPU.
+"""bench.py -- physics steps/sec of the B200-native rigid-body stepper (BASELINE.json metric), one process per GPU.
 
-  python bench.py --gpus 1 --steps K --warmup W                   # our arm (CUDA path through the C ABI)
-  python bench.py --impl reference --gpus 1 --steps K --warmup W  # the reference's CPU algorithm (oracle restatement; the reference
-                                                                  # itself is MSVC/Windows-only and does not compile here)
-A step = one physicsStepInternal (world colliders -> broad phase -> narrow phase -> PGS iterations -> integration) over all bodies.
-`value` is device-resident throughput (inputs already in HBM); `e2e` includes the per-step host->device upload of every
-body record from pinned memory and the device->host download of every pose/velocity through the public C ABI calls.
+  python bench.py --gpus N --steps K --warmup W                    # our arm: the CUDA path through the C ABI (libb200phys.so)
+  python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's OWN code (oracle/_ref/libref_fast.so: its physics
+                                                                   # sources compiled with g++, AVX2 path on) on the host cores
+
+Headline workload (N = 1): BASELINE configs[2], 1 048 576 mixed primitives (sphere / capsule / OBB / convex hull round robin, random
+orientations, 128 x 64 x 128 lattice settled into a pile inside 5 static boxes), 10 PGS iterations, dt 1/120. With N GPUs the pile is
+(128 N) x 64 x 128, slab-decomposed along x, ghost-body halo between slab neighbours: weak scaling, 1 048 576 bodies per GPU, i.e. the
+8.4 M-body scene of configs[4] at N = 8. A step = one physicsStepInternal (world colliders -> broad phase -> narrow phase -> PGS
+iterations -> integration) over all bodies. `value` = bodies x steps/s with state resident in HBM; `e2e` = the same through the public
+C-ABI calls with per-step pinned-host uploads of every pose / velocity / accumulator and the download of every pose / velocity.
+The other single-GPU configurations (configs[0], [1], [3]) are measured in the same run and reported under "configs"; "like_for_like"
+is configs[0] (1 024 spheres), the one scene the reference's 16-bit indices allow at full size, run by both arms.
 Prints ONE JSON line on rank 0.
 """
 import argparse
@@ -28,14 +33,16 @@ import numpy as np
 METRIC = "physics steps/sec at N rigid bodies (value = bodies x steps/s, whole job)"
 ITERATIONS = 10
 DT = np.float32(1.0 / 120.0)
-# algorithmic bytes: per contact and solver iteration: row 120 + 2 x 28 read, 8 + 2 x 24 written
-B_KITER = 232.0
-# DRAM traffic of one solveKernel launch on the N=1 workload (778 k contacts, 10 iterations), from one `ncu --set full` capture:
-# dram__bytes_read.sum 985.9 MB + dram__bytes_write.sum 11.6 MB (profiles/r01_final_solve_ncu_full_summary.txt). Below the
-# algorithmic 1.80 GB because the 32-byte body records mostly hit in L2.
-NCU_SOLVE_DRAM_BYTES = 985.903616e6 + 11.636224e6
-B_GRID, B_PAIR_OUT = 136.0, 8.0
-CPU_SAMPLE_DIMS = (32, 16, 32)   # 16 384 spheres: the largest pile the reference's uint16 collider indices allow (<= 32 767)
+MIXED_DIMS = (128, 64, 128)      # per GPU: 1 048 576 bodies (BASELINE configs[2])
+MIXED_SPACING = 0.8
+MIXED_SEED = 1578123
+CPU_SAMPLE_DIMS = (32, 16, 32)   # 16 384 bodies of the same lattice: the largest the reference's uint16 collider indices allow (<= 32 767)
+# algorithmic bytes per unit
+B_GRID, B_PAIR_OUT = 136.0, 8.0          # broad phase: per collider (bin, sort, ranges, query re-read) + per emitted pair
+B_PAIR_NARROW, B_CONTACT_OUT = 64.0, 40.0  # narrow phase: 2 x (16 shape + 16 tags) gathered per pair; contact 32 + body pair 8 written
+B_KINIT = 316.0                          # row set-up: contact 40 + 2 x 76 body state read, 124-byte row written
+B_KITER, B_JITER = 232.0, 376.0          # per contact / joint and PGS iteration
+B_BODY = 424.0                           # force + velocity integration, world colliders
 
 
 def measured_hbm_peak():
@@ -46,6 +53,15 @@ def measured_hbm_peak():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    """DRAM bytes per launch of the hot kernels from the committed `ncu --set full` summaries (profiles/r02_ncu_traffic.json)."""
+    p = os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")
+    try:
+        return json.load(open(p))
+    except Exception:
+        return {}
 
 
 class ClockSampler:
@@ -85,65 +101,179 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
 
 
-def build_scene(rank, world, nx=64):
-    """configs[1]: 262 144 spheres per GPU (64 x 64 x 64 jittered lattice, spacing 0.96, r = 0.5: a settled pile with ~3 contacts
-    per body) in an open box of 5 static AABBs. With N GPUs the pile is (64 N) x 64 x 64 and rank r owns x-layers [64 r, 64 (r+1)):
-    ONE scene, slab-decomposed, coupled through the ghost-body halo (BASELINE configs[4] layout, weak scaling)."""
-    from d3d12renderer_b200 import scenes
-    return scenes.sphere_pile_slab(nx * world, 64, 64 if nx == 64 else 128, nx * rank, nx * (rank + 1), seed=519431)
+# ------------------------------------------------------------------------------------------------------------ scenes
+def mixed_slab(rank, world, dims=MIXED_DIMS):
+    """x-layers of rank `rank` of the (dims[0] * world) x dims[1] x dims[2] mixed pile + the static boxes of the whole pile."""
+    from d3d12renderer_b200 import host
+    nx = dims[0]
+    return host.build_mixed_slab(nx * world, dims[1], dims[2], nx * rank, nx * (rank + 1), seed=MIXED_SEED, spacing=MIXED_SPACING)
 
 
-def cpu_reference_sample(steps, warmup):
-    """The reference's scalar CPU algorithm (oracle restatement) on a pile it can address (uint16 collider indices),
-    same lattice and density as the GPU workload; 1 thread like the reference's step."""
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    os.environ.setdefault("B200_ORACLE_VARIANT", "fast")   # timing build: -O2 -mavx2 -mfma -ffast-math like the reference's /arch:AVX2 /fp:fast
-    import oracle_lib
-    from d3d12renderer_b200 import scenes
-    sc = scenes.sphere_pile_settled(*CPU_SAMPLE_DIMS, seed=519431)
-    n = len(sc["bodies"])
-    orc = oracle_lib.Oracle(sc, canonical=False)    # reference SAP order: no canonicalisation work on the clock
+def make_stepper(sc, device=0, ghost_cap=0, **kw):
+    from d3d12renderer_b200 import abi
+    nb, nc = len(sc["bodies"]), len(sc["colliders"])
+    nj = max([len(j[0]) for j in sc.get("joints", {}).values()] + [1])
+    st = abi.Stepper(max_bodies=nb + 2 * ghost_cap, max_colliders=nc + 2 * ghost_cap, max_transforms=max(4, len(sc["transforms"])), max_joints=nj, device=device, **kw)
+    if "hull_vertices" in sc:
+        st.set_hulls(sc["hull_vertices"], sc["hull_offsets"])
+    st.upload_transforms(np.ascontiguousarray(sc["transforms"])); st.upload_colliders(np.ascontiguousarray(sc["colliders"])); st.upload_bodies(np.ascontiguousarray(sc["bodies"]))
+    for k, (j, p) in sc.get("joints", {}).items():
+        st.upload_joints(k, j, p)
+    return st
+
+
+def kernel_table(st, do_step, reps):
+    """Mean device time of every kernel group over `reps` steps (CUDA events on the launching stream, recorded by the library)."""
+    st.enable_timing(True)
+    acc = {}; order = []; counts = dict(contacts=0.0, pairs=0.0, manifolds=0.0); stage = np.zeros(7)
+    for _ in range(reps):
+        do_step()
+        s = st.stats(check=False)
+        stage += np.array([s.msWorld, s.msBroad, s.msNarrow, s.msInit, s.msSolve, s.msIntegrate, s.msTotal])
+        counts["contacts"] += s.numContacts; counts["pairs"] += s.numBroadphaseOverlaps; counts["manifolds"] += s.numCollisions
+        for name, ms in st.timeline():
+            if name not in acc:
+                acc[name] = 0.0; order.append(name)
+            acc[name] += ms
+    st.enable_timing(False)
+    return {k: acc[k] / reps for k in order}, {k: v / reps for k, v in counts.items()}, stage / reps
+
+
+def rooflines(kernels, counts, n_bodies, n_colliders, n_joints, peak):
+    """Algorithmic bytes (SURVEY 8d model) / measured time for the kernel groups that move the data; -> {group: {...}}."""
+    P, K = counts["pairs"], counts["contacts"]
+    model = {
+        "broad_phase": (n_colliders * B_GRID + P * B_PAIR_OUT, ["bp_build", "bp_query"]),
+        "narrow_phase": (P * B_PAIR_NARROW + K * B_CONTACT_OUT, ["np_classify_sort", "np_closed_form_sat", "np_gjk", "np_epa", "np_compact"]),
+        "solver_rows": (K * B_KINIT, ["solver_rows"]),
+        "solve": (K * ITERATIONS * B_KITER + n_joints * ITERATIONS * B_JITER, ["solve"]),
+        "bodies": (n_bodies * B_BODY, ["world_colliders", "integrate_forces", "integrate_velocities"]),
+    }
+    out = {}
+    for name, (nbytes, groups) in model.items():
+        ms = sum(kernels.get(g, 0.0) for g in groups)
+        gbs = nbytes / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+        out[name] = {"algorithmic_bytes": nbytes, "ms": ms, "achieved": gbs, "frac": gbs / peak}
+    return out
+
+
+def time_steps(do_step, barrier, stream, warmup, steps):
+    import torch
     for _ in range(warmup):
-        orc.step(DT, ITERATIONS)
-    stage = np.zeros(7)
-    t0 = time.perf_counter()
+        do_step()
+    barrier()
+    ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
     for _ in range(steps):
-        orc.step(DT, ITERATIONS)
-        stage += orc.stage_ms()
-    t = time.perf_counter() - t0
-    names = ["world_colliders", "broad_phase", "narrow_phase", "integrate_forces", "initialize_constraints", "solve_constraints", "integrate_velocities"]
-    return {"bodies": n, "steps": steps, "seconds": t, "steps_per_s": steps / t, "body_steps_per_s": n * steps / t,
-            "contacts": len(orc.contacts()[0]), "stage_ms": {k: float(v / steps) for k, v in zip(names, stage)}}
+        do_step()
+    ev1.record(stream)
+    barrier()
+    return ev0.elapsed_time(ev1)
+
+
+def side_config(name, sc, peak, steps, warmup=5, iterations=ITERATIONS):
+    """One of the other single-GPU BASELINE configurations, measured like the headline (device-resident)."""
+    import torch
+    from d3d12renderer_b200 import abi
+    st = make_stepper(sc)
+    stream = torch.cuda.current_stream()
+    st.set_stream(stream.cuda_stream)
+    sync = torch.cuda.synchronize
+    ms = time_steps(lambda: st.step(DT, iterations, abi.STEP_FAST), sync, stream, warmup, steps)
+    kernels, counts, stage = kernel_table(st, lambda: st.step(DT, iterations, abi.STEP_FAST), 6)
+    ms_exact = time_steps(lambda: st.step(DT, iterations, abi.STEP_EXACT_ORDER), sync, stream, 3, max(4, steps // 4))
+    s = st.stats(check=False)
+    nj = sum(len(j[0]) for j in sc.get("joints", {}).values())
+    rf = rooflines(kernels, counts, len(sc["bodies"]), len(sc["colliders"]), nj, peak)
+    out = {"workload": name, "bodies": len(sc["bodies"]), "colliders": len(sc["colliders"]), "joints": nj, "contacts": counts["contacts"], "pairs": counts["pairs"],
+           "ms_per_step": ms / steps, "steps_per_s": steps / (ms * 1e-3), "body_steps_per_s": len(sc["bodies"]) * steps / (ms * 1e-3),
+           "ms_per_step_exact_order": ms_exact / max(4, steps // 4), "kernel_ms": kernels, "launches_per_step": int(s.kernelLaunches),
+           "roofline": {k: {"frac": v["frac"], "achieved_gbs": v["achieved"], "ms": v["ms"]} for k, v in rf.items() if k in ("broad_phase", "solve")},
+           "overflow": [int(s.overflowPairs), int(s.overflowManifolds), int(s.overflowGrid), int(s.epaOverflows)]}
+    st.close()
+    return out
+
+
+# --------------------------------------------------------------------------------------------------- the CPU arm
+def reference_library():
+    """(module, kind): the compiled reference (oracle/_ref, `reference`) when it is there, else the oracle restatement (`port`)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import ref_lib
+    if ref_lib.available(fast=True):
+        flags = ""
+        try:
+            flags = open("/proc/cpuinfo").read()
+        except OSError:
+            pass
+        if " avx2" in flags and " fma" in flags:
+            return ref_lib, "reference"
+    return None, "port"
+
+
+def cpu_run(sc, steps, warmup, iterations=ITERATIONS):
+    """The reference's own physicsStep (compiled from its sources, its AVX2 path on: physics.h:394-396 defaults) on `sc`, 1 thread like
+    the reference's step; falls back to the oracle restatement (scalar path, -mavx2 -ffast-math build) when oracle/_ref is absent."""
+    ref_lib, kind = reference_library()
+    n = len(sc["bodies"])
+    if kind == "reference":
+        r = ref_lib.RefScene(sc, fast=True)
+        for _ in range(warmup):
+            r.step(DT, iterations, simd=True)
+        t = 0.0
+        for _ in range(steps):
+            r.step(DT, iterations, simd=True); t += r.last_step_seconds()
+        how = "the reference's own sources (src/physics, src/scene, EnTT) compiled with g++ -O2 -mavx2 -mfma -ffast-math (its /arch:AVX2 /fp:fast), physicsStep with simdBroadPhase = simdNarrowPhase = simdConstraintSolver = true (its defaults), 1 thread (the reference's step is single-threaded)"
+    else:
+        os.environ.setdefault("B200_ORACLE_VARIANT", "fast")
+        import oracle_lib
+        o = oracle_lib.Oracle(sc, canonical=False)
+        for _ in range(warmup):
+            o.step(DT, iterations)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            o.step(DT, iterations)
+        t = time.perf_counter() - t0
+        how = "oracle restatement of the reference's scalar path built -mavx2 -mfma -ffast-math (oracle/_ref not available here), 1 thread"
+    return {"bodies": n, "steps": steps, "seconds": t, "ms_per_step": 1e3 * t / steps, "steps_per_s": steps / t, "body_steps_per_s": n * steps / t, "kind": kind, "how": how}
+
+
+def cpu_sample_scene():
+    from d3d12renderer_b200 import host
+    return host.build_scene(host.CONFIG_MIXED_PILE, *CPU_SAMPLE_DIMS, seed=MIXED_SEED, spacing=MIXED_SPACING)
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 40)); warmup = max(1, min(args.warmup, 3))
-    s = cpu_reference_sample(steps, warmup)
-    total_bodies = 262144 * args.gpus
+    from d3d12renderer_b200 import scenes
+    steps = max(1, min(args.steps, 60)); warmup = max(1, min(args.warmup, 2))
+    sc = cpu_sample_scene()
+    s = cpu_run(sc, steps, warmup)
+    lfl = cpu_run(scenes.spheres_on_ground(32, mode="rest"), 200, 10)
+    sample = ("%d-body mixed pile of the headline workload's lattice (%d x %d x %d of 128 x 64 x 128 per GPU; the reference's uint16 collider indices cap a scene at 32 767 colliders), "
+              "%d steps in %.1f s; %s" % (s["bodies"], *CPU_SAMPLE_DIMS, steps, s["seconds"], s["how"]))
     line = {
         "impl": "reference", "metric": METRIC, "value": s["body_steps_per_s"], "unit": "body-steps/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
-        "ms_per_step": 1000.0 * s["seconds"] / steps * (262144.0 / s["bodies"]), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "262144-sphere settled pile (BASELINE configs[1]), 10 PGS iterations, dt 1/120", "bodies": total_bodies, "iterations": ITERATIONS},
-        "cpu_baseline": {"value": s["body_steps_per_s"], "unit": "body-steps/s", "cores": 1, "kind": "port",
-                         "sample": "%d-sphere pile of the same lattice (the reference's uint16 indices cap colliders at 32767), %d steps, oracle restatement built -mavx2 -mfma -ffast-math (the reference's /arch:AVX2 /fp:fast), 1 thread like the reference's step; %d contacts; stage ms %s"
-                                   % (s["bodies"], steps, s["contacts"], json.dumps(s["stage_ms"]))},
+        "ms_per_step": s["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "%d-body mixed-primitive pile (bounded SAMPLE of BASELINE configs[2]: same lattice, seed and spacing, %d x %d x %d), 10 PGS iterations, dt 1/120, measured as run (nothing extrapolated)" % (s["bodies"], *CPU_SAMPLE_DIMS),
+                   "bodies": s["bodies"], "iterations": ITERATIONS, "steps_per_s": s["steps_per_s"], "sample_of": "1048576-body mixed pile per GPU"},
+        "cpu_baseline": {"value": s["body_steps_per_s"], "unit": "body-steps/s", "cores": 1, "kind": s["kind"], "sample": sample},
+        "like_for_like": {"workload": "BASELINE configs[0]: 1024 spheres resting on the ground box, 10 PGS iterations (full size on both arms)", "steps_per_s": lfl["steps_per_s"], "ms_per_step": lfl["ms_per_step"], "kind": lfl["kind"]},
         "e2e": {"value": s["body_steps_per_s"], "unit": "body-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
 
 
+# ----------------------------------------------------------------------------------------------------------- main
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--config5", action="store_true", help="1 048 576 spheres per GPU (128 x 64 x 128 slab per rank: BASELINE configs[4], 8.4 M bodies on 8 GPUs) instead of the default 262 144")
+    ap.add_argument("--no-side-configs", action="store_true", help="skip configs[0], [1], [3] and the strong-scaling point (profiling runs)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); local_rank = int(os.environ.get("LOCAL_RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
 
@@ -153,7 +283,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from d3d12renderer_b200 import abi
+    from d3d12renderer_b200 import abi, parallel, scenes, host
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
@@ -162,34 +292,9 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     W = max(3, args.warmup); K = args.steps
-
-    from d3d12renderer_b200 import parallel
-    sc = build_scene(rank, world, 128 if args.config5 else 64)
-    n_bodies = len(sc["bodies"]); n_col = len(sc["colliders"])
-    ghost_cap = 0 if world == 1 else 3 * 64 * (128 if args.config5 else 64)      # ~2 layers of the slab face are ghosts, 1.5x head room
-    st = abi.Stepper(max_bodies=n_bodies + 2 * ghost_cap, max_colliders=n_col + 2 * ghost_cap, max_transforms=4, device=local_rank)
+    peak, peak_src = measured_hbm_peak()
     stream = torch.cuda.Stream()          # a real (non-default) stream: every kernel of the context and the timing events share it
     torch.cuda.set_stream(stream)
-    st.set_stream(stream.cuda_stream)
-    host_bodies = abi.PinnedArray(abi.body_dtype, n_bodies); host_bodies.array[:] = sc["bodies"]
-    host_states = abi.PinnedArray(abi.body_state_dtype, n_bodies)
-    st.upload_transforms(sc["transforms"]); st.upload_colliders(sc["colliders"]); st.upload_bodies(host_bodies.array)
-    # slab planes between ranks; the ghost layer is one collider diameter (+5 %) wide
-    x_lo, x_hi = sc["slab"]
-    planes = [None] * world
-    if world > 1:
-        dist.all_gather_object(planes, (x_lo, x_hi))
-    else:
-        planes = [(x_lo, x_hi)]
-    import numpy as _np
-    bounds = _np.array([-parallel.BIG] + [0.5 * (planes[r][1] + planes[r + 1][0]) for r in range(world - 1)] + [parallel.BIG])
-    shard = parallel.SlabShard(st, rank, world, bounds, axis=0, ghost_width=1.05, max_ghost_bodies=max(1, ghost_cap), max_ghost_colliders=max(1, ghost_cap),
-                               device=torch.device("cuda", local_rank))
-
-    def do_step():
-        if world > 1:
-            shard.refresh_ghosts()      # pack (device) -> one batched NCCL send/recv of fixed-size messages with the slab neighbours -> unpack (device); no host sync
-        st.step(DT, ITERATIONS, abi.STEP_FAST)
 
     def barrier():
         if world > 1:
@@ -201,92 +306,155 @@ def main():
             t = torch.tensor([x], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); return float(t.item())
         return x
 
-    # ---- device-resident throughput -----------------------------------------------------------------------------
+    def sum_over_ranks(x):
+        if world > 1:
+            t = torch.tensor([x], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.SUM); return float(t.item())
+        return x
+
+    def sharded(sc, ghost_layers=3.0):
+        """Stepper + slab shard for this rank's part of a slab-decomposed scene."""
+        n_bodies = len(sc["bodies"])
+        per_layer = max(1, n_bodies // max(1, int(round((sc["slab"][1] - sc["slab"][0]) / MIXED_SPACING))))
+        ghost_cap = 0 if world == 1 else int(ghost_layers * per_layer)
+        st = make_stepper(sc, device=local_rank, ghost_cap=ghost_cap)
+        st.set_stream(stream.cuda_stream)
+        planes = [None] * world
+        if world > 1:
+            dist.all_gather_object(planes, sc["slab"])
+        else:
+            planes = [sc["slab"]]
+        bounds = np.array([-parallel.BIG] + [0.5 * (planes[r][1] + planes[r + 1][0]) for r in range(world - 1)] + [parallel.BIG])
+        shard = parallel.SlabShard(st, rank, world, bounds, axis=0, ghost_width=1.05, max_ghost_bodies=max(1, ghost_cap), max_ghost_colliders=max(1, ghost_cap),
+                                   device=torch.device("cuda", local_rank))
+        return st, shard
+
+    # ================================================================ headline: mixed pile, 1 048 576 bodies per GPU (weak scaling)
+    sc = mixed_slab(rank, world)
+    n_bodies = len(sc["bodies"]); n_col = len(sc["colliders"])
+    st, shard = sharded(sc)
+
+    def do_step(flags=abi.STEP_FAST):
+        if world > 1:
+            shard.refresh_ghosts()      # pack (device) -> one batched NCCL send/recv of fixed-size messages with the slab neighbours -> unpack (device); no host sync
+        st.step(DT, ITERATIONS, flags)
+
     for _ in range(W):
         do_step()
     barrier()
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
-    ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record(stream)
-    for _ in range(K):
-        do_step()
-    ev1.record(stream)
-    barrier()
-    ms_dev = max_over_ranks(ev0.elapsed_time(ev1))
+    ms_dev = max_over_ranks(time_steps(do_step, barrier, stream, 0, K))
     clock_info = clocks.stop() if rank == 0 else None
-    stats = st.stats()
+    stats = st.stats(check=False)
     launches_per_step = stats.kernelLaunches
+    overflow = [int(stats.overflowPairs), int(stats.overflowManifolds), int(stats.overflowGrid)]
 
-    # ---- per-kernel device times for the roofline (CUDA events on the launching stream, live) --------------------
-    st.enable_timing(True)
-    acc = np.zeros(7); contacts = 0; pairs = 0; cells = 0
-    R = 10
-    for _ in range(R):
-        do_step()
-        s = st.stats()
-        acc += np.array([s.msWorld, s.msBroad, s.msNarrow, s.msInit, s.msSolve, s.msIntegrate, s.msTotal]); contacts += s.numContacts; pairs += s.numBroadphaseOverlaps
-    st.enable_timing(False)
-    acc /= R; contacts /= R; pairs /= R
-    peak, peak_src = measured_hbm_peak()
-    solve_bytes = contacts * ITERATIONS * B_KITER
-    solve_gbs = solve_bytes / (acc[4] * 1e-3) / 1e9 if acc[4] > 0 else 0.0
-    broad_bytes = n_col * B_GRID + pairs * B_PAIR_OUT
-    broad_gbs = broad_bytes / (acc[1] * 1e-3) / 1e9 if acc[1] > 0 else 0.0
+    kernels, counts, stage = kernel_table(st, do_step, 8)
+    rf = rooflines(kernels, counts, n_bodies, n_col, 0, peak)
+    ms_exact = max_over_ranks(time_steps(lambda: do_step(abi.STEP_EXACT_ORDER), barrier, stream, 2, max(3, K // 5))) / max(3, K // 5)
+    for _ in range(2):
+        do_step()                                   # back on the fast order (colour memory) before the end-to-end loop
 
-    # ---- end to end through the public API: H2D of every body record + step + D2H of every pose/velocity ----------
-    hs = host_states.array
+    # ---- end to end through the public API: H2D of every body state + accumulators, step, D2H of every pose / velocity ----------
+    host_states = abi.PinnedArray(abi.body_state_dtype, n_bodies); hs = host_states.array
     host_forces = abi.PinnedArray(np.float32, n_bodies * 6); hf = host_forces.array.reshape(n_bodies, 6); hf[:] = 0
-    st.download_bodies(hs)
-    st.halo_clear()
+    st.halo_clear(); st.download_bodies(hs)
     for _ in range(2):
         st.upload_body_states(hs); st.upload_forces(hf); do_step(); st.halo_clear(); st.download_bodies(hs)
     barrier()
+    K2 = max(5, K // 2)
     t0 = time.perf_counter()
-    for _ in range(K):
+    for _ in range(K2):
         st.upload_body_states(hs)                  # pinned host -> HBM: pose + velocities of every body, 52 B each
-        st.upload_forces(hf)                       # pinned host -> HBM: force/torque accumulators, 24 B each
+        st.upload_forces(hf)                       # pinned host -> HBM: force / torque accumulators, 24 B each (copy stream, overlaps collision detection)
         do_step()                                  # (+ ghost halo exchange with the slab neighbours when N > 1)
         st.halo_clear()
         st.download_bodies(hs)                     # HBM -> pinned host: pose + velocities of every OWNED body, 52 B each (synchronises)
     barrier()
-    ms_e2e = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    ms_e2e = max_over_ranks((time.perf_counter() - t0) * 1e3) / K2
     checksum = float(np.sum(hs["position"][:, 1].astype(np.float64)))
+    ghosts = shard.ghost_counts()[0] if world > 1 else 0
+    st.close(); host_states.free(); host_forces.free()
 
     total_bodies = n_bodies * world
     value = total_bodies * K / (ms_dev * 1e-3)
-    e2e_value = total_bodies * K / (ms_e2e * 1e-3)
+    e2e_value = total_bodies / (ms_e2e * 1e-3)
 
-    cpu = None
+    # ================================================================ strong scaling point (N > 1): ONE 1 048 576-body pile over N GPUs
+    strong = None
+    if world > 1 and not args.no_side_configs:
+        nx = MIXED_DIMS[0] // world
+        sc2 = host.build_mixed_slab(MIXED_DIMS[0], MIXED_DIMS[1], MIXED_DIMS[2], nx * rank, nx * (rank + 1), seed=MIXED_SEED, spacing=MIXED_SPACING)
+        st2, shard2 = sharded(sc2)
+
+        def step2():
+            shard2.refresh_ghosts(); st2.step(DT, ITERATIONS, abi.STEP_FAST)
+        ms2 = max_over_ranks(time_steps(step2, barrier, stream, W, K))
+        st2.close()
+        strong = {"workload": "ONE 1048576-body mixed pile (128 x 64 x 128) slab-decomposed over %d GPUs (fixed total: strong scaling)" % world, "bodies": MIXED_DIMS[0] * MIXED_DIMS[1] * MIXED_DIMS[2],
+                  "ms_per_step": ms2 / K, "steps_per_s": K / (ms2 * 1e-3), "n_gpus": world, "note": "efficiency = (N=1 headline ms_per_step) / (N x this ms_per_step)"}
+
+    # ================================================================ N = 1: the other single-GPU configurations + the CPU arm
+    side = {}; lfl = None; cpu = None
+    if rank == 0 and world == 1 and not args.no_side_configs:
+        c1 = scenes.spheres_on_ground(32, mode="rest")
+        side["configs[0]"] = side_config("1024 spheres resting on the ground box (BASELINE configs[0])", c1, peak, 200, warmup=20)
+        side["configs[1]"] = side_config("262144-sphere settled pile in the open box (BASELINE configs[1])", scenes.sphere_pile_settled(64, 64, 64, seed=519431), peak, 40)
+        side["configs[3]"] = side_config("16384 ragdolls: 229376 bodies, 278528 colliders, 114688 cone-twist + 98304 hinge joints (BASELINE configs[3])",
+                                         host.build_scene(host.CONFIG_RAGDOLLS, 128, 1, 128, seed=20260924, mode=0, spacing=1.6), peak, 40)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        s = cpu_reference_sample(20, 2)
-        cpu = {"value": s["body_steps_per_s"], "unit": "body-steps/s", "cores": 1, "kind": "port",
-               "sample": "%d-sphere pile of the same lattice (reference uint16 collider limit), %d steps in %.1f s, oracle restatement built -mavx2 -mfma -ffast-math (the reference's /arch:AVX2 /fp:fast), 1 thread like the reference's step" % (s["bodies"], s["steps"], s["seconds"])}
+        s = cpu_run(cpu_sample_scene(), 12, 1)
+        cpu = {"value": s["body_steps_per_s"], "unit": "body-steps/s", "cores": 1, "kind": s["kind"], "ms_per_step": s["ms_per_step"],
+               "sample": "%d-body mixed pile of the same lattice (%d x %d x %d; the reference's uint16 collider indices cap a scene at 32767 colliders), %d steps in %.1f s; %s"
+                         % (s["bodies"], *CPU_SAMPLE_DIMS, s["steps"], s["seconds"], s["how"])}
+        l = cpu_run(scenes.spheres_on_ground(32, mode="rest"), 200, 10)
+        ours = side.get("configs[0]")
+        lfl = {"workload": "BASELINE configs[0]: 1024 spheres resting on the ground box, 10 PGS iterations -- the one scene both arms run at full size",
+               "reference_steps_per_s": l["steps_per_s"], "reference_ms_per_step": l["ms_per_step"], "reference_kind": l["kind"],
+               "ours_steps_per_s": ours["steps_per_s"] if ours else None, "ours_ms_per_step": ours["ms_per_step"] if ours else None}
 
     if rank == 0:
+        dom = max(kernels, key=lambda k: kernels[k])
+        group_of = {"bp_build": "broad_phase", "bp_query": "broad_phase", "np_classify_sort": "narrow_phase", "np_closed_form_sat": "narrow_phase", "np_gjk": "narrow_phase",
+                    "np_epa": "narrow_phase", "np_compact": "narrow_phase", "solver_rows": "solver_rows", "solver_order": "solver_rows", "solve": "solve"}
+        # per-kernel algorithmic bytes for the dominant kernel group (same model, split by what that kernel touches)
+        P, Kc = counts["pairs"], counts["contacts"]
+        dom_bytes = {"solve": Kc * ITERATIONS * B_KITER, "bp_query": n_col * 24.0 + P * B_PAIR_OUT, "bp_build": n_col * (B_GRID - 24.0), "solver_rows": Kc * B_KINIT,
+                     "np_epa": counts["manifolds"] * (152.0 + 128.0 + 80.0), "np_gjk": P * B_PAIR_NARROW, "np_closed_form_sat": P * B_PAIR_NARROW,
+                     "np_compact": counts["manifolds"] * 80.0 + Kc * B_CONTACT_OUT + P * 16.0, "np_classify_sort": P * (8.0 + 32.0 + 1.0 + 4.0 + 16.0)}.get(dom, 0.0)
+        dom_gbs = dom_bytes / (kernels[dom] * 1e-3) / 1e9 if kernels[dom] > 0 else 0.0
+        traffic = ncu_traffic()
         line = {
             "metric": METRIC, "value": value, "unit": "body-steps/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": ("1048576-sphere settled pile per GPU (BASELINE configs[4])" if args.config5 else "262144-sphere settled pile per GPU (BASELINE configs[1])") + ", 10 PGS iterations, dt 1/120, fast (colour-sorted) solver order, dataflow sweep",
-                       "bodies": total_bodies, "bodies_per_gpu": n_bodies, "iterations": ITERATIONS, "contacts_per_gpu": contacts, "pairs_per_gpu": pairs,
-                       "steps_per_s": K / (ms_dev * 1e-3), "parallelism": ("slab decomposition along x, %d slabs, ghost-body halo over NCCL (%d ghost bodies on rank 0)" % (world, shard.ghost_counts()[0])) if world > 1 else "single GPU",
-                       "l2_policy": "per-step working set (rows, pair and manifold scratch, body planes) > 126 MB L2; no explicit flush",
-                       "state_checksum_y": checksum},
-            "e2e": {"value": e2e_value, "unit": "body-steps/s", "ms_per_step": ms_e2e / K, "h2d_bytes_per_step": int(n_bodies * (abi.body_state_dtype.itemsize + 24)),
+            "config": {"workload": "1048576 mixed primitives per GPU (sphere / capsule / OBB / convex hull, BASELINE configs[2]; %d x 64 x 128 pile over %d GPU(s) = configs[4] layout), 10 PGS iterations, dt 1/120, fast (colour-sorted) solver order"
+                                   % (MIXED_DIMS[0] * world, world),
+                       "bodies": total_bodies, "bodies_per_gpu": n_bodies, "iterations": ITERATIONS, "contacts_per_gpu": counts["contacts"], "pairs_per_gpu": counts["pairs"], "manifolds_per_gpu": counts["manifolds"],
+                       "steps_per_s": K / (ms_dev * 1e-3), "ms_per_step_exact_order": ms_exact,
+                       "parallelism": ("slab decomposition along x, %d slabs, ghost-body halo over NCCL (%d ghost bodies on rank 0)" % (world, ghosts)) if world > 1 else "single GPU",
+                       "l2_policy": "per-step working set (rows, pair and manifold scratch, body planes: > 1 GB) >> 126 MB L2; no explicit flush",
+                       "state_checksum_y": checksum, "overflow": overflow},
+            "e2e": {"value": e2e_value, "unit": "body-steps/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(n_bodies * (abi.body_state_dtype.itemsize + 24)),
                     "d2h_bytes_per_step": int(n_bodies * abi.body_state_dtype.itemsize)},
             "gpu_launches": int(launches_per_step * K),
-            "roofline": {"bound": "hbm", "kernel": "solveKernel (PGS iterations)", "achieved": solve_gbs, "peak": peak, "unit": "GB/s", "frac": solve_gbs / peak,
-                         "traffic": NCU_SOLVE_DRAM_BYTES if world == 1 else None, "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of solveKernel, ncu --set full on this workload (profiles/r01_final_solve_ncu_full_summary.txt)", "peak_source": peak_src, "algorithmic_bytes_per_launch": solve_bytes, "launch_ms": acc[4],
-                         "broad_phase": {"achieved": broad_gbs, "frac": broad_gbs / peak, "algorithmic_bytes": broad_bytes, "ms": acc[1]}},
-            "stage_ms": {"world": acc[0], "broad": acc[1], "narrow": acc[2], "init": acc[3], "solve": acc[4], "integrate": acc[5], "total": acc[6]},
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": dom_gbs, "peak": peak, "unit": "GB/s", "frac": dom_gbs / peak, "launch_ms": kernels[dom],
+                         "algorithmic_bytes_per_launch": dom_bytes, "traffic": traffic.get(dom), "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full (profiles/r02_ncu_traffic.json)" if traffic.get(dom) else None,
+                         "peak_source": peak_src, "stage": group_of.get(dom),
+                         "stages": {k: {"frac": v["frac"], "achieved": v["achieved"], "ms": v["ms"], "algorithmic_bytes": v["algorithmic_bytes"]} for k, v in rf.items()}},
+            "kernel_ms": kernels,
+            "stage_ms": {"world": stage[0], "broad": stage[1], "narrow": stage[2], "init": stage[3], "solve": stage[4], "integrate": stage[5], "total": stage[6]},
             "clocks": clock_info,
         }
+        if strong is not None:
+            line["strong_scaling"] = strong
+        if side:
+            line["configs"] = side
+        if lfl is not None:
+            line["like_for_like"] = lfl
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line))
-    st.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -82,7 +82,7 @@ EXPORTS = [
     "b200phys_set_hulls", "b200phys_upload_bodies", "b200phys_upload_transforms", "b200phys_upload_colliders", "b200phys_upload_joints",
     "b200phys_upload_forces", "b200phys_upload_body_states", "b200phys_step", "b200phys_synchronize", "b200phys_download_bodies", "b200phys_get_stats",
     "b200phys_download_aabbs", "b200phys_download_pairs", "b200phys_download_contacts", "b200phys_download_collisions",
-    "b200phys_download_solve_order", "b200phys_halo_pack", "b200phys_halo_unpack", "b200phys_halo_clear", "b200phys_halo_record_bytes",
+    "b200phys_download_solve_order", "b200phys_get_timeline", "b200phys_halo_pack", "b200phys_halo_unpack", "b200phys_halo_clear", "b200phys_halo_record_bytes",
     "b200phys_halo_message_bytes", "b200phys_halo_pack_message", "b200phys_halo_unpack_message", "b200phys_migrate_pack", "b200phys_migrate_unpack", "b200phys_enable_events", "b200phys_download_events", "b200phys_upload_force_fields", "b200phys_set_global_force_field", "b200phys_download_trigger_events",
 ]
 
@@ -117,6 +117,7 @@ def load_library():
     lib.b200phys_synchronize.argtypes = [vp]
     lib.b200phys_download_bodies.argtypes = [vp, vp, u32]
     lib.b200phys_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    lib.b200phys_get_timeline.argtypes = [vp, vp, u32, vp, u32, C.POINTER(u32)]
     lib.b200phys_download_aabbs.argtypes = [vp, vp, C.POINTER(u32)]
     lib.b200phys_download_pairs.argtypes = [vp, vp, C.POINTER(u32)]
     lib.b200phys_download_contacts.argtypes = [vp, vp, vp, C.POINTER(u32)]
@@ -250,6 +251,13 @@ class Stepper:
         if check:
             _check(self.lib, code, "get_stats")
         return st
+
+    def timeline(self):
+        """[(kernel group name, ms)] of the last step (enable_timing(True) first)."""
+        names = C.create_string_buffer(4096); ms = (C.c_float * 64)(); n = C.c_uint32(0)
+        _check(self.lib, self.lib.b200phys_get_timeline(self.ctx, names, 4096, ms, 64, C.byref(n)), "get_timeline")
+        labels = names.value.decode().split("\n")[:n.value]
+        return [(labels[i], float(ms[i])) for i in range(min(n.value, len(labels)))]
 
     def _count_then_fetch(self, fn, dtypes, name):
         n = C.c_uint32(0)

@@ -69,6 +69,9 @@ struct Context
     cudaStream_t ownStream = nullptr;
     bool timing = false;
     cudaEvent_t ev[8] = {};
+    // per-kernel-group timeline (b200phys_get_timeline): mark i closes the interval that started at mark i - 1
+    static const int kMaxMarks = 32;
+    cudaEvent_t markEv[kMaxMarks] = {}; const char* markName[kMaxMarks] = {}; int numMarks = 0;
 
     uint32_t numBodies = 0, numColliders = 0, numTransforms = 0, numHulls = 0;   // incl. ghosts
     uint32_t numOwnedBodies = 0, numOwnedColliders = 0;                            // what the host uploaded
@@ -185,6 +188,14 @@ struct Context
     uint8_t* haloBuf = nullptr; uint32_t haloCap = 0;
     uint32_t numGhostBodies = 0, numGhostColliders = 0;
 };
+
+// records the end of a kernel group on the context's stream when timing is enabled (no-op otherwise)
+static inline void timelineMark(Context* c, const char* name)
+{
+    if (!c->timing || c->numMarks >= Context::kMaxMarks) return;
+    if (!c->markEv[c->numMarks]) cudaEventCreate(&c->markEv[c->numMarks]);
+    cudaEventRecord(c->markEv[c->numMarks], c->stream); c->markName[c->numMarks] = name; ++c->numMarks;
+}
 
 // launch geometry shared by every grid-stride kernel: a multiple of the SM count (148 on B200)
 static inline int gridFor(const Context* c, int blocksPerSM = 8) { return c->numSMs * blocksPerSM; }

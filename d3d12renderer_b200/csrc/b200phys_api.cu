@@ -100,6 +100,7 @@ void freeAll(Context& c)
     for (int k = 0; k < 6; ++k) { if (c.jointIn[k]) cudaFree(c.jointIn[k]); if (c.jointBodies[k]) cudaFree(c.jointBodies[k]); if (c.jointRows[k]) cudaFree(c.jointRows[k]); }
     if (c.hostCounts) cudaFreeHost(c.hostCounts);
     for (int i = 0; i < 8; ++i) if (c.ev[i]) cudaEventDestroy(c.ev[i]);
+    for (int i = 0; i < Context::kMaxMarks; ++i) if (c.markEv[i]) cudaEventDestroy(c.markEv[i]);
     if (c.copyStream) cudaStreamDestroy(c.copyStream);
     if (c.evCopyGate) cudaEventDestroy(c.evCopyGate); if (c.evForcesDone) cudaEventDestroy(c.evForcesDone);
     if (c.forceStaging) cudaFree(c.forceStaging);
@@ -302,10 +303,12 @@ int b200phys_step(b200phys_context* ctx, float dt, uint32_t numSolverIterations,
 {
     if (!ctx || !(dt > 0.f)) return B200PHYS_E_INVALID;
     Context& c = ctx->c; CK(cudaSetDevice(c.device));
-    c.launches = 0;
+    c.launches = 0; c.numMarks = 0;
     if (c.timing) cudaEventRecord(c.ev[0], c.stream);
+    timelineMark(&c, "begin");
     if (c.numNonCollisionColliders) waitPendingForceUpload(&c);   // force fields add to the accumulators during the narrow phase
     launchWorldColliders(&c);                               // physics.cpp:1217
+    timelineMark(&c, "world_colliders");
     if (c.timing) cudaEventRecord(c.ev[1], c.stream);
     launchBroadphase(&c);                                   // physics.cpp:1222
     if (c.timing) cudaEventRecord(c.ev[2], c.stream);
@@ -314,9 +317,11 @@ int b200phys_step(b200phys_context* ctx, float dt, uint32_t numSolverIterations,
     waitPendingForceUpload(&c);
     launchIntegrateForces(&c, dt);                          // physics.cpp:1266-1279
     launchCollisionEvents(&c);                              // physics.cpp:1284
+    timelineMark(&c, "integrate_forces");
     launchSolver(&c, dt, numSolverIterations, flags);       // physics.cpp:1316-1334 (records ev[4] before the iterations)
     if (c.timing) cudaEventRecord(c.ev[5], c.stream);
     launchIntegrateVelocities(&c, dt);                      // physics.cpp:1338-1348
+    timelineMark(&c, "integrate_velocities");
     if (c.timing) cudaEventRecord(c.ev[6], c.stream);
     c.stepped = true;
     CK(cudaGetLastError());
@@ -463,6 +468,29 @@ int b200phys_get_stats(b200phys_context* ctx, b200phys_stats* out)
         cudaEventElapsedTime(&out->msTotal, c.ev[0], c.ev[6]);
     }
     if (d.overflowPairs || d.overflowManifolds || d.overflowGrid || d.overflowBig || d.overflowColors || d.overflowHalo) return B200PHYS_E_CAPACITY;
+    return 0;
+}
+
+int b200phys_get_timeline(b200phys_context* ctx, char* namesOut, uint32_t namesCapacity, float* msOut, uint32_t msCapacity, uint32_t* count)
+{
+    if (!ctx || !count) return B200PHYS_E_INVALID;
+    Context& c = ctx->c; CK(cudaSetDevice(c.device));
+    *count = 0;
+    if (!c.timing || !c.stepped || c.numMarks < 2) return 0;
+    CK(cudaStreamSynchronize(c.stream));
+    size_t used = 0;
+    if (namesOut && namesCapacity) namesOut[0] = 0;
+    for (int i = 1; i < c.numMarks; ++i)
+    {
+        float ms = 0.f; cudaEventElapsedTime(&ms, c.markEv[i - 1], c.markEv[i]);
+        if (msOut && (uint32_t)(i - 1) < msCapacity) msOut[i - 1] = ms;
+        if (namesOut)
+        {
+            const size_t len = strlen(c.markName[i]);
+            if (used + len + 2 <= namesCapacity) { memcpy(namesOut + used, c.markName[i], len); used += len; namesOut[used++] = '\n'; namesOut[used] = 0; }
+        }
+    }
+    *count = (uint32_t)(c.numMarks - 1);
     return 0;
 }
 

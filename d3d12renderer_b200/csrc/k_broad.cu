@@ -377,6 +377,7 @@ void launchBroadphase(Context* c)
     c->launches += 6;
     scanExclusiveU32(c, c->cellCount, c->cellStart, &cnt->grid.numCells, c->maxCells, nullptr);
     bpScatterKernel<<<G, kThreads, 0, c->stream>>>(C, c->aabbMin, c->aabbMax, c->cellOf, c->rankInCell, c->cellStart, c->sortedMin, c->sortedMax);
+    timelineMark(c, "bp_build");
     cudaMemsetAsync(c->pairCount, 0, sizeof(uint32_t) * (C + 1), c->stream);
     bpQueryKernel<false><<<G, kThreads, 0, c->stream>>>(c->sortedMin, c->sortedMax, c->cellStart, c->aabbMin, c->aabbMax, c->bigList, c->pairCount, c->pairStart, c->pairs, c->maxPairs, cnt);
     // big colliders: parallel flag-matrix path for up to 16 of them (scratch: pair-sized buffers that are free until the narrow
@@ -400,6 +401,7 @@ void launchBroadphase(Context* c)
     bpBigKernel<true><<<c->numSMs, kThreads, 0, c->stream>>>(C, matrixFits ? 16u : 0u, c->aabbMin, c->aabbMax, c->bigList, c->pairCount, c->pairStart, c->pairs, c->maxPairs, cnt);
     bpFinishKernel<<<1, 32, 0, c->stream>>>(C, c->pairStart, c->maxPairs, cnt);
     c->launches += 3;
+    timelineMark(c, "bp_query");
 }
 
 } // namespace b200

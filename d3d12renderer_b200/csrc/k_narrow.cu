@@ -340,11 +340,15 @@ void launchNarrowphase(Context* c)
     c->launches += 1;
     stableSmallKeySort(c, c->pairKey, &cnt->numPairs, c->maxPairs, kNumPairKeys, c->pairDst, cnt->keyStart);
     npPermuteKernel<<<G, kThreads, 0, c->stream>>>(c->pairsTyped, c->pairDst, c->pairsSorted, cnt);
+    timelineMark(c, "np_classify_sort");
     npCollideKernel<0><<<G, 256, 0, c->stream>>>(c->pairsSorted, c->wCol, c->manTmp, c->manScan, c->maxPairs, cnt);
     npCollideKernel<1><<<gridFor(c, 4), 128, 0, c->stream>>>(c->pairsSorted, c->wCol, c->manTmp, c->manScan, c->maxPairs, cnt);
+    timelineMark(c, "np_closed_form_sat");
     npGjkKernel<<<gridFor(c, 8), 128, 0, c->stream>>>(c->pairsSorted, c->wCol, c->hullVerts, c->hullOffsets, c->manTmp, c->manScan, c->maxPairs, c->epaSimplex, c->epaWork, c->maxEpaWork, cnt);
+    timelineMark(c, "np_gjk");
     npEpaKernel<<<gridFor(c, 4), 128, 0, c->stream>>>(c->pairsSorted, c->wCol, c->hullVerts, c->hullOffsets, c->manTmp, c->manScan, c->maxPairs, c->epaSimplex, c->epaWork, c->maxEpaWork, cnt);
     c->launches += 1;
+    timelineMark(c, "np_epa");
     npClearTailKernel<<<G, kThreads, 0, c->stream>>>(c->manScan, cnt);
     c->launches += 5;
     scanExclusiveU64(c, c->manScan, c->manScanOut, &cnt->numPairs, c->maxPairs, nullptr);
@@ -363,6 +367,7 @@ void launchNarrowphase(Context* c)
     npCompactKernel<<<G, kThreads, 0, c->stream>>>(c->pairsSorted, c->wCol, c->manTmp, c->manScan, c->manScanOut, c->maxPairs, c->maxManifolds, c->maxContacts,
                                                    c->collisions, c->manifolds, c->contacts, c->contactBodies, cnt);
     c->launches += 2;
+    timelineMark(c, "np_compact");
 }
 
 } // namespace b200

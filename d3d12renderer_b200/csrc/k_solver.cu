@@ -806,6 +806,7 @@ void launchSolver(Context* c, float dt, uint32_t iterations, uint32_t flags)
         c->colorAge = (c->colorAge + 1 >= every) ? 0 : c->colorAge + 1;
     }
     else c->colorAge = 0;       // another mode ran: the remembered colours are stale
+    timelineMark(c, "solver_order");
     uint32_t* slotCount = c->pairDst;              // scratch reuse
     slotCountKernel<<<G, kThreads, 0, c->stream>>>(c->unitOrder[6], c->manifolds, slotCount, cnt);
     c->launches++;
@@ -832,6 +833,7 @@ void launchSolver(Context* c, float dt, uint32_t iterations, uint32_t flags)
     A.joints = ja; A.gVel = c->gVel; A.gPos = c->gPos; A.gInvI = c->gInvI; A.cnt = cnt; A.iterations = iterations;
     void* args[] = { &A };
     if (c->timing) cudaEventRecord(c->ev[4], c->stream);
+    timelineMark(c, "solver_rows");
     static int solveBlocksPerSM[2] = { 0, 0 };
     const int variant = anyJoint ? 1 : 0;
     void* fn = anyJoint ? (void*)solveKernel<true> : (void*)solveKernel<false>;
@@ -839,6 +841,7 @@ void launchSolver(Context* c, float dt, uint32_t iterations, uint32_t flags)
     const int bps = solveBlocksPerSM[variant];
     cudaLaunchCooperativeKernel(fn, dim3(c->numSMs * bps), dim3(kSolveThreads), args, 0, c->stream);
     c->launches++;
+    timelineMark(c, "solve");
 }
 
 } // namespace b200

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200host.so")
 _lib = None
 
-CONFIG_SPHERES_ON_GROUND, CONFIG_SPHERE_BOX_DROP, CONFIG_MIXED_PILE, CONFIG_RAGDOLLS, CONFIG_EVENT_SCENE, CONFIG_JOINT_ZOO, CONFIG_VEHICLES = 1, 2, 3, 4, 5, 6, 7
+CONFIG_SPHERES_ON_GROUND, CONFIG_SPHERE_BOX_DROP, CONFIG_MIXED_PILE, CONFIG_RAGDOLLS, CONFIG_EVENT_SCENE, CONFIG_JOINT_ZOO, CONFIG_VEHICLES, CONFIG_REFERENCE_VEHICLE = 1, 2, 3, 4, 5, 6, 7, 8
 
 
 def load_library():
@@ -27,6 +27,7 @@ def load_library():
     lib.b200host_scene_create.restype = vp
     lib.b200host_scene_destroy.argtypes = [vp]
     lib.b200host_build_config.argtypes = [vp, C.c_int, u32, u32, u32, C.c_uint64, C.c_int, C.c_float]
+    lib.b200host_build_mixed_slab.argtypes = [vp, u32, u32, u32, u32, u32, C.c_uint64, C.c_float]
     for n in ("b200host_num_bodies", "b200host_num_colliders", "b200host_num_hulls", "b200host_num_hull_vertices"):
         getattr(lib, n).argtypes = [vp]; getattr(lib, n).restype = u32
     lib.b200host_num_joints.argtypes = [vp, C.c_int]; lib.b200host_num_joints.restype = u32
@@ -204,6 +205,17 @@ class LocomotionEnv:
         if rc:
             raise abi.B200PhysError("physicsStep failed inside the environment: %d" % rc)
         return states, rewards, failed.astype(bool)
+
+
+def build_mixed_slab(nx_total, ny, nz, ix0, ix1, seed=1578123, spacing=0.8):
+    """x-layers [ix0, ix1) of the BASELINE config-3 mixed pile (nx_total x ny x nz) + the static boxes of the whole pile; 'slab' = the x range
+    this slab owns (planes half-way to the neighbouring layers), for the multi-GPU decomposition."""
+    hs = HostScene()
+    hs.lib.b200host_build_mixed_slab(hs.ptr, nx_total, ny, nz, ix0, ix1, seed, spacing)
+    sc = hs.arrays(); sc["host_scene"] = hs
+    hx = np.float32((nx_total - 1) * spacing * 0.5)
+    sc["slab"] = (float(np.float32(ix0) * np.float32(spacing) - hx) - 0.5 * spacing, float(np.float32(ix1 - 1) * np.float32(spacing) - hx) + 0.5 * spacing)
+    return sc
 
 
 def build_scene(config, nx, ny=1, nz=1, seed=1, mode=0, spacing=1.25):

@@ -170,9 +170,9 @@ int b200host_build_config(void* sp, int config, uint32_t nx, uint32_t ny, uint32
                 }
             }
             {   // C: two boxes welded by a fixed joint, tumbling onto the ground
-                scene_entity a = boxAt(mk3(0.f, 1.6f + jig, 6.f), quatAxisAngle(normalize(mk3(1.f, 0.3f, 0.2f)), 0.4f), mk3(0.4f, 0.2f, 0.3f));
-                scene_entity b = boxAt(mk3(0.9f, 1.9f + jig, 6.f), quatAxisAngle(normalize(mk3(0.f, 1.f, 0.5f)), 0.9f), mk3(0.3f, 0.3f, 0.2f));
-                addFixedConstraintFromGlobalPoints(a, b, O + mk3(0.45f, 1.75f, 6.f));
+                scene_entity a = boxAt(mk3(0.f, 0.75f + jig, 6.f), quatAxisAngle(normalize(mk3(1.f, 0.3f, 0.2f)), 0.4f), mk3(0.4f, 0.2f, 0.3f));
+                scene_entity b = boxAt(mk3(0.9f, 1.05f + jig, 6.f), quatAxisAngle(normalize(mk3(0.f, 1.f, 0.5f)), 0.9f), mk3(0.3f, 0.3f, 0.2f));
+                addFixedConstraintFromGlobalPoints(a, b, O + mk3(0.45f, 0.9f, 6.f));
                 a.rigidBody().angularVelocity = mk3(1.f, 2.f, -1.5f); b.rigidBody().linearVelocity = mk3(0.f, -1.f, 0.5f);
             }
             {   // D: slider along x with limits and a velocity motor
@@ -229,6 +229,11 @@ int b200host_build_config(void* sp, int config, uint32_t nx, uint32_t ny, uint32
         for (uint32_t ix = 0; ix < nx; ++ix) for (uint32_t iz = 0; iz < nz; ++iz)
         {
             vehicle v = vehicle::create(s, mk3(ix * DX, 1.1f + rng.between(0.f, 0.2f), iz * DX), (mode == 0) ? 0.f : rng.between(0.f, 6.2831853f));
+            for (int i = 0; i < vehicle::numParts; ++i)
+            {   // what addComponent<transform_component> does on a rigid body (scene.h:96-107): vehicle::initialize itself leaves the physics transforms unplaced
+                const int rb = s.entities[v.parts[i].handle].rigidBody;
+                s.physicsTransform0[rb] = s.physicsTransform1[rb] = v.parts[i].transform();
+            }
             if (mode)
             {
                 getConstraint(s, v.motorConstraint).motorVelocityOrTargetAngle = 6.f;
@@ -237,6 +242,13 @@ int b200host_build_config(void* sp, int config, uint32_t nx, uint32_t ny, uint32
         }
         s.createEntity("Ground").addTransform(mk3(0.f, -4.f, 0.f))
             .addCollider(collider_component::asAABB(bounding_box::fromCenterRadius(mk3(0.f), mk3(nx * DX + 20.f, 4.f, nz * DX + 20.f)), kStaticMat));
+        return 0;
+    }
+    if (config == 8)
+    {   // ONE vehicle exactly as vehicle::create leaves it (physics transforms unplaced, see vehicle::initialize) over a ground box whose top
+        // is at y = -1: the scene tests/test_ref_pins_oracle.py builds with the reference's own vehicle::create
+        vehicle::create(s, mk3(3.f, 1.f, -2.f), 0.5f);
+        s.createEntity("Ground").addTransform(mk3(0.f, -5.f, 0.f)).addCollider(collider_component::asAABB(bounding_box::fromCenterRadius(mk3(0.f), mk3(28.f, 4.f, 28.f)), kStaticMat));
         return 0;
     }
     if (config == 4)
@@ -253,6 +265,37 @@ int b200host_build_config(void* sp, int config, uint32_t nx, uint32_t ny, uint32
         return 0;
     }
     return 1;
+}
+
+// x-layers [ix0, ix1) of the config-3 mixed pile of nxTotal x ny x nz bodies + the static boxes of the WHOLE pile (replicated on every
+// rank): the multi-GPU slab of the bench. The random stream is advanced for every lattice site, so the union over all slabs is exactly
+// the scene b200host_build_config(3, nxTotal, ny, nz, ...) builds, whatever the number of ranks.
+int b200host_build_mixed_slab(void* sp, uint32_t nxTotal, uint32_t ny, uint32_t nz, uint32_t ix0, uint32_t ix1, uint64_t seed, float spacing)
+{
+    game_scene& s = *(game_scene*)sp;
+    Rng rng = { seed ? seed : 1 };
+    addHullGeometries(s);
+    const float hx = (nxTotal - 1) * spacing * 0.5f, hz = (nz - 1) * spacing * 0.5f;
+    uint32_t counter = 0;
+    for (uint32_t ix = 0; ix < nxTotal; ++ix) for (uint32_t iy = 0; iy < ny; ++iy) for (uint32_t iz = 0; iz < nz; ++iz, ++counter)
+    {
+        const vec3 p = mk3(ix * spacing - hx + rng.between(-0.005f, 0.005f), iy * spacing + 0.6f + rng.between(-0.005f, 0.005f), iz * spacing - hz + rng.between(-0.005f, 0.005f));
+        const int kind = (int)(counter & 3u);
+        quat q = qIdentity();
+        if (kind != 0) q = randomRotation(rng);
+        if (ix < ix0 || ix >= ix1) continue;
+        scene_entity e = s.createEntity("Body");
+        e.addTransform(p, q);
+        if (kind == 0) e.addCollider(collider_component::asSphere({ mk3(0.f), 0.5f }, kDynamicMat));
+        else if (kind == 1) e.addCollider(collider_component::asCapsule({ mk3(0.f, -0.25f, 0.f), mk3(0.f, 0.25f, 0.f), 0.25f }, kDynamicMat));
+        else if (kind == 2) e.addCollider(collider_component::asOBB({ qIdentity(), mk3(0.f), mk3(0.4f, 0.3f, 0.35f) }, kDynamicMat));
+        else e.addCollider(collider_component::asHull({ qIdentity(), mk3(0.f), (counter >> 2) & 1u }, kDynamicMat));
+        e.addRigidBody(false, 1.f);
+    }
+    const float ex = hx + 1.1f, ez = hz + 1.1f, h = ny * spacing + 4.f;
+    s.createEntity("Floor").addTransform(mk3(0.f, -4.f, 0.f)).addCollider(collider_component::asAABB(bounding_box::fromCenterRadius(mk3(0.f), mk3(ex + 8.f, 4.f, ez + 8.f)), kStaticMat));
+    addWalls(s, ex, ez, h);
+    return 0;
 }
 
 uint32_t b200host_num_bodies(void* s) { return (uint32_t)((game_scene*)s)->rigidBodies.size(); }

@@ -730,12 +730,12 @@ void vehicle::initialize(game_scene& scene, vec3 initialMotorPosition, float ini
 
     const quat rotation = quatAxisAngle(mk3(0.f, 1.f, 0.f), initialRotation);
     for (int i = 0; i < numParts; ++i)
-    {   // vehicle.cpp:486-496
+    {   // vehicle.cpp:486-496: ONLY the transform_component moves. Unlike humanoid_ragdoll (ragdoll.cpp:111-112) the reference does not
+        // refresh physics_transform0 / 1 here, so the simulation itself starts from the unplaced pose (and overwrites the render transform
+        // after the first step). Reproduced as is; a caller that wants the placement to stick re-adds the transform (scene.h:96-107).
         trs& t = parts[i].transform();
         t.position = rotation * t.position + initialMotorPosition;
         t.rotation = rotation * t.rotation;
-        const int rb = scene.entities[parts[i].handle].rigidBody;
-        scene.physicsTransform0[rb] = scene.physicsTransform1[rb] = t;
     }
 }
 

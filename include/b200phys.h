@@ -268,6 +268,10 @@ int b200phys_enable_events(b200phys_context* ctx, int enable);
 int b200phys_download_events(b200phys_context* ctx, b200phys_collision_begin_event* beginOut, uint32_t beginCapacity, uint32_t* numBegin,
                              b200phys_collider_pair* endOut, uint32_t endCapacity, uint32_t* numEnd);
 int b200phys_get_stats(b200phys_context* ctx, b200phys_stats* out);
+/* Per-kernel-group device times of the LAST step (timing must be enabled): *count intervals in launch order; names are written as one
+ * '\n'-separated string (kernel group names such as "bp_query", "np_epa", "solve"), msOut[i] is the CUDA-event time of interval i.
+ * The analogue of the reference's CPU_PROFILE_BLOCK tree (physics.cpp:1182, collision_broad.cpp:299, ...), per kernel group. */
+int b200phys_get_timeline(b200phys_context* ctx, char* namesOut, uint32_t namesCapacity, float* msOut, uint32_t msCapacity, uint32_t* count);
 /* parity / event-layer taps (each returns the element count through *count; out may be NULL to query the count) */
 int b200phys_download_aabbs(b200phys_context* ctx, float* outMinMax6, uint32_t* count);
 int b200phys_download_pairs(b200phys_context* ctx, b200phys_collider_pair* out, uint32_t* count);

@@ -32,6 +32,7 @@ struct RefScene
     std::vector<entity_handle> bodyEntities, transformEntities;
     float timer = 0.f;
     double lastStepSeconds = 0.0;
+    std::vector<uint32> triggerLog;          // (trigger index, rigid body index, 0 enter / 1 leave) triples of the last step, callback order
     RefScene() { arena.initialize(0, GB(8)); }
 };
 
@@ -119,7 +120,17 @@ int ref_scene_build(void* p, const b200phys_body* bodies, uint32 numBodies, cons
         const uint32 t = order[k];
         scene_entity e = R.scene.createEntity("parent");
         e.addComponent<transform_component>(v3(transforms[t].position), q4(transforms[t].rotation));
-        if (kind[t] == B200PHYS_OBJ_TRIGGER) e.addComponent<trigger_component>();
+        if (kind[t] == B200PHYS_OBJ_TRIGGER)
+        {
+            RefScene* self = &R; const uint32 triggerIndex = index[t];
+            e.addComponent<trigger_component>();
+            e.getComponent<trigger_component>().callback = [self, triggerIndex](trigger_event ev)
+            {
+                uint32 body = 0xFFFFFFFFu;
+                for (size_t b = 0; b < self->bodyEntities.size(); ++b) if (self->bodyEntities[b] == ev.other.handle) { body = (uint32)b; break; }
+                self->triggerLog.push_back(triggerIndex); self->triggerLog.push_back(body); self->triggerLog.push_back((uint32)ev.type);
+            };
+        }
         if (kind[t] == B200PHYS_OBJ_FORCE_FIELD) e.addComponent<force_field_component>();
         R.transformEntities[t] = e.handle;
     }
@@ -244,10 +255,17 @@ void ref_scene_step(void* p, float dt, uint32 iterations, int fixedFrameRate, ui
     physics_settings s;
     s.fixedFrameRate = fixedFrameRate != 0; s.frameRate = frameRate; s.numRigidSolverIterations = iterations;
     s.simdBroadPhase = simdBroad != 0; s.simdNarrowPhase = simdNarrow != 0; s.simdConstraintSolver = simdSolver != 0;
+    R.triggerLog.clear();
     const auto t0 = std::chrono::steady_clock::now();
     R.arena.reset();                                       // application::update resets the frame arena (application.cpp:521)
     physicsStep(R.scene, R.arena, R.timer, s, dt);
     R.lastStepSeconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+uint32 ref_scene_trigger_log(void* p, uint32* out, uint32 capacityTriples)
+{
+    RefScene& R = *(RefScene*)p; const uint32 n = (uint32)R.triggerLog.size() / 3;
+    if (out) memcpy(out, R.triggerLog.data(), 12 * (size_t)(n < capacityTriples ? n : capacityTriples));
+    return n;
 }
 double ref_scene_last_step_seconds(void* p) { return ((RefScene*)p)->lastStepSeconds; }
 

@@ -42,7 +42,10 @@ template <typename T> using ref = std::shared_ptr<T>;
 template <typename T> using weakref = std::weak_ptr<T>;
 template <typename T, typename... Args> inline ref<T> make_ref(Args&&... args) { return std::make_shared<T>(std::forward<Args>(args)...); }
 
-#define arraysize(arr) (sizeof(arr) / sizeof((arr)[0]))
+// arraysize must also work on the array views that replace the reference's "named members / array" unions (ref_array_view below)
+template <typename T> struct ref_array_count;
+template <typename T, size_t N> struct ref_array_count<T[N]> { static constexpr size_t value = N; };
+#define arraysize(arr) (ref_array_count<std::remove_cv_t<std::remove_reference_t<decltype(arr)>>>::value)
 
 template <typename T> constexpr inline auto min(T a, T b) { return (a < b) ? a : b; }
 template <typename T> constexpr inline auto max(T a, T b) { return (a < b) ? b : a; }
@@ -65,6 +68,7 @@ template <typename T, int N> struct ref_array_view
     T& operator[](size_t i) { return (reinterpret_cast<T*>(this) - N)[i]; }
     const T& operator[](size_t i) const { return (reinterpret_cast<const T*>(this) - N)[i]; }
 };
+template <typename T, int N> struct ref_array_count<ref_array_view<T, N>> { static constexpr size_t value = N; };
 // same idea, placed FIRST in a struct with [[no_unique_address]] so that it adds no size: view over the members that follow it
 template <typename T> struct ref_array_front
 {

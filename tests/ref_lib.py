@@ -39,6 +39,7 @@ def load(fast=False):
     lib.ref_scene_step.argtypes = [vp, f32, u32, i32, u32, i32, i32, i32]
     lib.ref_scene_last_step_seconds.argtypes = [vp]; lib.ref_scene_last_step_seconds.restype = C.c_double
     lib.ref_scene_get_states.argtypes = [vp, vp]
+    lib.ref_scene_trigger_log.argtypes = [vp, vp, u32]; lib.ref_scene_trigger_log.restype = u32
     lib.ref_scene_body_storage_index.argtypes = [vp, u32]; lib.ref_scene_body_storage_index.restype = u32
     lib.ref_scene_detect.argtypes = [vp, i32, i32, vp, vp, vp, u32, vp, vp, vp, vp, u32, vp]
     lib.ref_collide_pair.argtypes = [vp, vp, i32, vp, vp]; lib.ref_collide_pair.restype = i32
@@ -113,6 +114,14 @@ class RefScene:
         """physicsStep; fixed_frame_rate False = exactly one physicsStepInternal(dt) (physics.cpp:1404-1412)."""
         s = 1 if simd else 0
         self.lib.ref_scene_step(self.ptr, dt, iterations, 1 if fixed_frame_rate else 0, frame_rate, s, s, s)
+
+    def trigger_log(self):
+        """(trigger index, rigid body index, 0 enter / 1 leave) of the last step, in the order the reference fired the callbacks."""
+        n = self.lib.ref_scene_trigger_log(self.ptr, None, 0)
+        out = np.zeros((n, 3), dtype=np.uint32)
+        if n:
+            self.lib.ref_scene_trigger_log(self.ptr, _p(out), n)
+        return out
 
     def last_step_seconds(self): return self.lib.ref_scene_last_step_seconds(self.ptr)
 
