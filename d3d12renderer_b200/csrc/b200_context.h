@@ -34,6 +34,7 @@ struct GridParams
 struct DeviceCounts
 {
     uint32_t numEpaWork;                // GJK hits waiting for EPA this step
+    uint32_t epaWorkHead;               // next work-list entry to hand out (warp-cooperative EPA kernel)
     uint32_t numPairs;                  // broad-phase overlaps (clamped to capacity)
     uint32_t numPairsWanted;            // what the scan produced (overflow detection)
     uint32_t keyStart[kNumPairKeys + 1];// bucket ranges of the classified pair list

@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(kThreads) bpResetKernel(DeviceCounts* cnt)
     {
         cnt->extentSumFixed = 0ull; cnt->extentCount = 0; cnt->maxSmallExtentBits = 0; cnt->numBig = 0;
         for (int a = 0; a < 3; ++a) { cnt->centreMinBits[a] = 0xFFFFFFFFu; cnt->centreMaxBits[a] = 0u; }
-        cnt->numPairs = 0; cnt->numPairsWanted = 0; cnt->numEpaWork = 0;
+        cnt->numPairs = 0; cnt->numPairsWanted = 0; cnt->numEpaWork = 0; cnt->epaWorkHead = 0;
     }
 }
 

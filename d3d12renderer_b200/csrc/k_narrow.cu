@@ -6,6 +6,7 @@
 //                (bucket, colliderA, colliderB, slot); material combine and 16+16 bit packing as in :2221-2253
 #include "b200_context.h"
 #include "k_narrow_shapes.cuh"
+#include <cstdlib>
 
 namespace b200 {
 
@@ -206,6 +207,34 @@ __global__ void __launch_bounds__(128) npEpaKernel(const uint2* __restrict__ sor
     flushCounters(nc, cnt);
 }
 
+// phase 2, warp-cooperative: one warp per parked pair, polytope in shared memory (k_narrow_shapes.cuh, EpaWarp). All lanes run the
+// routine's scalar parts uniformly (same loads: broadcast), the EPA loops are split across the lanes; lane 0 writes the manifold.
+static const int kEpaWarpsPerCta = 4;
+__global__ void __launch_bounds__(kEpaWarpsPerCta * 32) npEpaWarpKernel(const uint2* __restrict__ sorted, const float4* __restrict__ wCol, const float4* __restrict__ hullVerts,
+    const uint32_t* __restrict__ hullOffsets, float4* __restrict__ manTmp, unsigned long long* __restrict__ manScan, uint32_t maxPairs,
+    float4* __restrict__ sxPlanes, const uint2* __restrict__ epaWork, uint32_t sxCap, DeviceCounts* cnt)
+{
+    extern __shared__ __align__(16) unsigned char epaSmem[];
+    EpaWarpShared* sh = reinterpret_cast<EpaWarpShared*>(epaSmem) + (threadIdx.x >> 5);
+    NarrowCtx<3> nc; nc.epaOverflow = nc.gjkCap = nc.asserts = 0; nc.sxPlanes = sxPlanes; nc.sxCap = sxCap; nc.sxCounter = nullptr; nc.deferred = false; nc.epaShared = sh;
+    const uint32_t n = min(cnt->numEpaWork, sxCap);
+    for (;;)
+    {   // pairs take 1..20 expansions: hand the work list out dynamically, one entry per warp at a time
+        uint32_t e = 0;
+        if ((threadIdx.x & 31u) == 0u) e = atomicAdd(&cnt->epaWorkHead, 1u);
+        e = __shfl_sync(0xffffffffu, e, 0);
+        if (e >= n) break;
+        const uint2 w = epaWork[e];
+        const uint2 pr = sorted[w.x];
+        const ColRec A = loadCol(wCol, pr.x), B = loadCol(wCol, pr.y);
+        Man m; m.cnt = 0;
+        nc.sxEntry = e;
+        const bool hit = collideGjkBucket(w.y, A, B, hullVerts, hullOffsets, m, nc);
+        if ((threadIdx.x & 31u) == 0u) storeManifold(manTmp, manScan, w.x, maxPairs, hit, m);
+    }
+    if ((threadIdx.x & 31u) == 0u) flushCounters(nc, cnt);
+}
+
 // ------------------------------------------------------------------------------ non-collision interactions (event layer)
 // overlapCheck (collision_narrow.cpp:1593-1689): boolean shape test for rigid body vs trigger / force field pairs
 B200_D bool overlapCheckD(const ColRec& A, const ColRec& B, const float4* __restrict__ hullVerts, const uint32_t* __restrict__ hullOffsets, NarrowCounters& nc)
@@ -346,7 +375,19 @@ void launchNarrowphase(Context* c)
     timelineMark(c, "np_closed_form_sat");
     npGjkKernel<<<gridFor(c, 8), 128, 0, c->stream>>>(c->pairsSorted, c->wCol, c->hullVerts, c->hullOffsets, c->manTmp, c->manScan, c->maxPairs, c->epaSimplex, c->epaWork, c->maxEpaWork, cnt);
     timelineMark(c, "np_gjk");
-    npEpaKernel<<<gridFor(c, 4), 128, 0, c->stream>>>(c->pairsSorted, c->wCol, c->hullVerts, c->hullOffsets, c->manTmp, c->manScan, c->maxPairs, c->epaSimplex, c->epaWork, c->maxEpaWork, cnt);
+    {
+        static int epaMode = -1, epaBps = 0;       // B200PHYS_EPA=warp selects the warp-cooperative kernel (measured slower); B200PHYS_EPA_BPS = resident CTAs per SM (tuning)
+        if (epaMode < 0) { const char* e = getenv("B200PHYS_EPA"); epaMode = (e && e[0] == 'w') ? 1 : 0; const char* b = getenv("B200PHYS_EPA_BPS"); epaBps = b ? atoi(b) : 0; }
+        if (epaMode == 0)
+            npEpaKernel<<<gridFor(c, epaBps > 0 ? epaBps : 8), 128, 0, c->stream>>>(c->pairsSorted, c->wCol, c->hullVerts, c->hullOffsets, c->manTmp, c->manScan, c->maxPairs, c->epaSimplex, c->epaWork, c->maxEpaWork, cnt);
+        else
+        {
+            const size_t smem = sizeof(EpaWarpShared) * kEpaWarpsPerCta;
+            static bool attr = false;
+            if (!attr) { cudaFuncSetAttribute(npEpaWarpKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+            npEpaWarpKernel<<<gridFor(c, epaBps > 0 ? epaBps : 6), kEpaWarpsPerCta * 32, smem, c->stream>>>(c->pairsSorted, c->wCol, c->hullVerts, c->hullOffsets, c->manTmp, c->manScan, c->maxPairs, c->epaSimplex, c->epaWork, c->maxEpaWork, cnt);
+        }
+    }
     c->launches += 1;
     timelineMark(c, "np_epa");
     npClearTailKernel<<<G, kThreads, 0, c->stream>>>(c->manScan, cnt);

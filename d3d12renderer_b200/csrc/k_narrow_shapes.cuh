@@ -28,8 +28,9 @@ template <int PHASE> struct NarrowCtx : NarrowCounters
     float4* sxPlanes;      // 9 planes of float4, plane stride sxCap
     uint32_t sxCap;
     uint32_t* sxCounter;   // PHASE 1: work-list size
-    uint32_t sxEntry;      // PHASE 1: entry written (valid when deferred); PHASE 2: entry to read
+    uint32_t sxEntry;      // PHASE 1: entry written (valid when deferred); PHASE 2 / 3: entry to read
     bool deferred;
+    struct EpaWarpShared* epaShared;   // PHASE 3: this warp's polytope in shared memory (warp-cooperative EPA, every lane runs the routine uniformly)
 };
 
 // ------------------------------------------------------------------------------------------------------- helpers
@@ -418,6 +419,30 @@ struct SupportD
         }
         }
     }
+    // the same mapping evaluated by a whole warp on uniform arguments: hull vertices are split over the lanes (first maximum wins, like the
+    // sequential scan), the closed-form shapes are evaluated redundantly. Every lane returns the same point.
+    B200_D f3 evalWarp(f3 dir) const
+    {
+        if (type != B200PHYS_HULL) return eval(dir);
+        const uint32_t lane = threadIdx.x & 31u;
+        f3 d = conjugate(q) * dir;
+        float maxDist = -FLT_MAX; uint32_t bestI = 0xFFFFFFFFu;
+        for (uint32_t i = lane; i < nv; i += 32u)
+        {
+            const float4 v4 = verts[i];
+            const float t = dot(d, mk3(v4.x, v4.y, v4.z));
+            if (t > maxDist) { maxDist = t; bestI = i; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+        {
+            const float ot = __shfl_xor_sync(0xffffffffu, maxDist, o); const uint32_t oi = __shfl_xor_sync(0xffffffffu, bestI, o);
+            if (oi != 0xFFFFFFFFu && (bestI == 0xFFFFFFFFu || ot > maxDist || (ot == maxDist && oi < bestI))) { maxDist = ot; bestI = oi; }
+        }
+        f3 best = mk3(0.f);
+        if (bestI != 0xFFFFFFFFu) { const float4 v4 = verts[bestI]; best = mk3(v4.x, v4.y, v4.z); }
+        return c + q * best;
+    }
 };
 B200_D SupportD supSphere(const SphereS& s) { SupportD r; r.type = B200PHYS_SPHERE; r.a = s.c; r.r = s.r; return r; }
 B200_D SupportD supCapsule(const CapS& s) { SupportD r; r.type = B200PHYS_CAPSULE; r.a = s.a; r.b = s.b; r.r = s.r; return r; }
@@ -430,6 +455,7 @@ B200_D SupportD supHull(const HullS& s) { SupportD r; r.type = B200PHYS_HULL; r.
 struct SupPt { f3 a, b, m; };
 struct SimplexD { SupPt a, b, c, d; uint32_t n; };
 B200_D SupPt minkowski(const SupportD& A, const SupportD& B, f3 dir) { SupPt p; p.a = A.eval(dir); p.b = B.eval(-dir); p.m = p.a - p.b; return p; }
+B200_D SupPt minkowskiWarp(const SupportD& A, const SupportD& B, f3 dir) { SupPt p; p.a = A.evalWarp(dir); p.b = B.evalWarp(-dir); p.m = p.a - p.b; return p; }
 B200_D f3 crossABA(f3 a, f3 b) { return cross(cross(a, b), a); }
 
 #define B200_GJK_STOP 0
@@ -650,6 +676,198 @@ B200_D void epa(const SimplexD& g, const SupportD& A, const SupportD& B, f3& out
     outDepth = t.dist;
 }
 
+// ---- warp-cooperative EPA (PHASE 3). One warp expands ONE polytope that lives in shared memory; all 32 lanes execute the calling
+// routine uniformly (same pair, same data) and split the per-triangle / per-edge loops of collision_epa.cpp:94-239 among themselves.
+// Every step reproduces the sequential result exactly: the closest triangle is the first minimum (ties -> lowest index), horizon edges
+// are compacted in ascending edge order (ballot prefix), the i-th horizon edge creates edge nE + i and triangle nT + i like the
+// sequential pushes do, and the two places where a later loop iteration overwrites an earlier one (newEdgePerPoint, edges[other].t0)
+// become max-reductions over the iteration index. Capacity failures are detected before anything is appended: the sequential code
+// would bail out half way, but its result only depends on the closest triangle found BEFORE the failed expansion.
+// Capacities follow the reference where it has a real bound (<= 128 border edges, collision_epa.cpp:141; 4 + 20 points) and are sized
+// for the observed maxima elsewhere (the reference's arrays hold 1024).
+#define B200_EPAW_MAX_POINTS 24
+#define B200_EPAW_MAX_TRIS 160
+#define B200_EPAW_MAX_EDGES 240
+#define B200_EPAW_MAX_BORDER 128
+struct EpaWarpShared
+{
+    float4 triN[B200_EPAW_MAX_TRIS];                    // normal.xyz, distance
+    float pts[(B200_EPAW_MAX_POINTS + 1) * 9];          // a.xyz, b.xyz, m.xyz per support point
+    int32_t refs[B200_EPAW_MAX_EDGES];                  // per-round reference counts, then the link targets of the second pass
+    uint16_t triA[B200_EPAW_MAX_TRIS], triB[B200_EPAW_MAX_TRIS], triC[B200_EPAW_MAX_TRIS], triEA[B200_EPAW_MAX_TRIS], triEB[B200_EPAW_MAX_TRIS], triEC[B200_EPAW_MAX_TRIS];
+    uint16_t edgeA[B200_EPAW_MAX_EDGES], edgeB[B200_EPAW_MAX_EDGES], edgeT0[B200_EPAW_MAX_EDGES], edgeT1[B200_EPAW_MAX_EDGES];
+    uint16_t border[B200_EPAW_MAX_BORDER];
+    int32_t newEdgePerPoint[B200_EPAW_MAX_POINTS + 1];
+    uint32_t active[B200_EPAW_MAX_TRIS / 32];
+};
+
+struct EpaWarp
+{
+    EpaWarpShared& S; uint32_t lane; uint32_t nT, nP, nE;
+    B200_D EpaWarp(EpaWarpShared& s) : S(s), lane(threadIdx.x & 31u), nT(0), nP(0), nE(0) {}
+    B200_D bool isActive(uint32_t i) const { return i < nT && ((S.active[i >> 5] >> (i & 31)) & 1u); }
+    B200_D f3 ptM(uint32_t i) const { return mk3(S.pts[9 * i + 6], S.pts[9 * i + 7], S.pts[9 * i + 8]); }
+    B200_D SupPt pt(uint32_t i) const { SupPt p; const float* f = S.pts + 9 * i; p.a = mk3(f[0], f[1], f[2]); p.b = mk3(f[3], f[4], f[5]); p.m = mk3(f[6], f[7], f[8]); return p; }
+    B200_D void setPoint(uint32_t i, const SupPt& p)
+    {   // lanes 0..8 store one float each (all lanes hold the same p)
+        const float v[9] = { p.a.x, p.a.y, p.a.z, p.b.x, p.b.y, p.b.z, p.m.x, p.m.y, p.m.z };
+        if (lane < 9) S.pts[9 * i + lane] = v[lane];
+    }
+    B200_D void setTri(uint32_t i, uint16_t a, uint16_t b, uint16_t c, uint16_t eA, uint16_t eB, uint16_t eC, f3 n, float d)
+    { S.triA[i] = a; S.triB[i] = b; S.triC[i] = c; S.triEA[i] = eA; S.triEB[i] = eB; S.triEC[i] = eC; S.triN[i] = make_float4(n.x, n.y, n.z, d); }
+    B200_D void setEdge(uint32_t i, uint16_t a, uint16_t b, uint16_t t0, uint16_t t1) { S.edgeA[i] = a; S.edgeB[i] = b; S.edgeT0[i] = t0; S.edgeT1[i] = t1; }
+
+    B200_D void init(const SimplexD& g)
+    {
+        if (lane < B200_EPAW_MAX_TRIS / 32) S.active[lane] = 0;
+        setPoint(0, g.a); setPoint(1, g.b); setPoint(2, g.c); setPoint(3, g.d);
+        if (lane == 0)
+        {
+            f3 n; float d;
+            EpaPoly::triInfo(g.a, g.b, g.d, n, d); setTri(0, 0, 1, 3, 4, 3, 0, n, d);
+            EpaPoly::triInfo(g.b, g.c, g.d, n, d); setTri(1, 1, 2, 3, 5, 4, 1, n, d);
+            EpaPoly::triInfo(g.c, g.a, g.d, n, d); setTri(2, 2, 0, 3, 3, 5, 2, n, d);
+            EpaPoly::triInfo(g.a, g.c, g.b, n, d); setTri(3, 0, 2, 1, 1, 0, 2, n, d);
+            setEdge(0, 0, 1, 0, 3); setEdge(1, 1, 2, 1, 3); setEdge(2, 2, 0, 2, 3);
+            setEdge(3, 0, 3, 2, 0); setEdge(4, 1, 3, 0, 1); setEdge(5, 2, 3, 1, 2);
+            S.active[0] = 0xFu;
+        }
+        nP = 4; nT = 4; nE = 6;
+        __syncwarp();
+    }
+    // collision_epa.cpp:94-112: first minimum of dist over the active triangles
+    B200_D uint32_t closest() const
+    {
+        uint32_t best = 0xFFFFFFFFu; float mind = FLT_MAX;
+        for (uint32_t i = lane; i < nT; i += 32u) { const float d = S.triN[i].w; if (isActive(i) && d < mind) { mind = d; best = i; } }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+        {
+            const float od = __shfl_xor_sync(0xffffffffu, mind, o); const uint32_t ob = __shfl_xor_sync(0xffffffffu, best, o);
+            if (ob != 0xFFFFFFFFu && (best == 0xFFFFFFFFu || od < mind || (od == mind && ob < best))) { mind = od; best = ob; }
+        }
+        return best;
+    }
+    // collision_epa.cpp:114-239
+    B200_D bool addPoint(const SupPt& np)
+    {
+        const uint32_t FULL = 0xffffffffu;
+        for (uint32_t i = lane; i < nE; i += 32u) S.refs[i] = 0;
+        for (uint32_t i = lane; i <= nP && i < B200_EPAW_MAX_POINTS + 1; i += 32u) S.newEdgePerPoint[i] = -1;
+        __syncwarp();
+        // triangles that see the new point are removed; their edges are counted
+        for (uint32_t base = 0; base < nT; base += 32u)
+        {
+            const uint32_t i = base + lane;
+            bool removed = false;
+            if (i < nT && isActive(i))
+            {
+                const float4 t = S.triN[i];
+                const float d = dot(mk3(t.x, t.y, t.z), np.m - ptM(S.triA[i]));
+                if (d > 0.f)
+                {
+                    removed = true;
+                    const uint32_t eA = S.triEA[i], eB = S.triEB[i], eC = S.triEC[i];
+                    if (eA < nE) atomicAdd(&S.refs[eA], 1); if (eB < nE) atomicAdd(&S.refs[eB], 1); if (eC < nE) atomicAdd(&S.refs[eC], 1);
+                }
+            }
+            const uint32_t rem = __ballot_sync(FULL, removed);
+            if (lane == 0 && rem) S.active[base >> 5] &= ~rem;
+        }
+        __syncwarp();
+        // horizon = edges referenced exactly once, in ascending edge order
+        uint32_t nBorder = 0;
+        for (uint32_t base = 0; base < nE; base += 32u)
+        {
+            const uint32_t e = base + lane;
+            const bool flag = e < nE && S.refs[e] == 1;
+            const uint32_t b = __ballot_sync(FULL, flag);
+            const uint32_t pos = nBorder + (uint32_t)__popc(b & ((1u << lane) - 1u));
+            if (flag && pos < B200_EPAW_MAX_BORDER) S.border[pos] = (uint16_t)e;
+            nBorder += (uint32_t)__popc(b);
+        }
+        if (nBorder > B200_EPAW_MAX_BORDER) return false;
+        if (nP >= B200_EPAW_MAX_POINTS) return false;
+        if (nE + nBorder > B200_EPAW_MAX_EDGES || nT + nBorder > B200_EPAW_MAX_TRIS) return false;
+        __syncwarp();
+        const uint32_t npi = nP, triOffset = nT, edgeOffset = nE;
+        setPoint(npi, np);
+        // one new edge and one new triangle per horizon edge
+        for (uint32_t base = 0; base < nBorder; base += 32u)
+        {
+            const uint32_t i = base + lane;
+            if (i < nBorder)
+            {
+                const uint32_t ei = S.border[i];
+                const uint16_t ea = S.edgeA[ei], eb = S.edgeB[ei];
+                const bool aAct = isActive(S.edgeT0[ei]), bAct = isActive(S.edgeT1[ei]);
+                const uint16_t connect = bAct ? ea : eb;
+                const uint32_t triIndex = triOffset + i, ne = edgeOffset + i;
+                setEdge(ne, connect, (uint16_t)npi, 0xFFFF, (uint16_t)triIndex);
+                atomicMax(&S.newEdgePerPoint[connect], (int32_t)ne);            // the sequential loop keeps the LAST edge written per point
+                const uint16_t bI = connect, cI = bAct ? eb : ea;
+                f3 n; float d; EpaPoly::triInfo(np, pt(bI), pt(cI), n, d);
+                setTri(triIndex, (uint16_t)npi, bI, cI, (uint16_t)ei, 0xFFFF, (uint16_t)ne, n, d);
+                if (aAct) S.edgeT1[ei] = (uint16_t)triIndex; else S.edgeT0[ei] = (uint16_t)triIndex;
+            }
+        }
+        nP = npi + 1; nT = triOffset + nBorder; nE = edgeOffset + nBorder;
+        __syncwarp();
+        // activity bits of the new triangles; link targets start empty
+        for (uint32_t i = triOffset + lane; i < nT; i += 32u) atomicOr(&S.active[i >> 5], 1u << (i & 31u));
+        for (uint32_t i = edgeOffset + lane; i < nE; i += 32u) S.refs[i] = -1;
+        __syncwarp();
+        // second pass: connect neighbouring new triangles through the new edges
+        for (uint32_t base = 0; base < nBorder; base += 32u)
+        {
+            const uint32_t i = base + lane;
+            if (i < nBorder)
+            {
+                const uint32_t ei = S.border[i];
+                const bool bNew = S.edgeT1[ei] >= triOffset;
+                const uint16_t connect = bNew ? S.edgeA[ei] : S.edgeB[ei];
+                const int32_t other = S.newEdgePerPoint[connect];
+                const uint32_t triIndex = triOffset + i;
+                if (other >= 0) { S.triEB[triIndex] = (uint16_t)other; atomicMax(&S.refs[other], (int32_t)triIndex); }   // later iterations overwrite earlier ones
+            }
+        }
+        __syncwarp();
+        for (uint32_t i = edgeOffset + lane; i < nE; i += 32u) if (S.refs[i] >= 0) S.edgeT0[i] = (uint16_t)S.refs[i];
+        __syncwarp();
+        return true;
+    }
+};
+
+// collision_epa.h:96-168 with the polytope shared by the warp; every lane returns the same result
+B200_D void epaWarp(EpaWarpShared& sh, const SimplexD& g, const SupportD& A, const SupportD& B, f3& outPoint, f3& outNormal, float& outDepth, NarrowCounters& nc)
+{
+    EpaWarp P(sh);
+    __syncwarp();
+    P.init(g);
+    uint32_t ci = 0;
+    for (uint32_t it = 0; it < 20; ++it)
+    {
+        ci = P.closest();
+        if (ci == 0xFFFFFFFFu) { if (P.lane == 0) ++nc.asserts; ci = 0; break; }
+        const float4 t = sh.triN[ci];
+        const f3 tn = mk3(t.x, t.y, t.z);
+        SupPt a = minkowskiWarp(A, B, tn);
+        float dd = dot(a.m, tn);
+        if (dd - t.w < 0.01f) break;
+        if (!P.addPoint(a)) { if (P.lane == 0) ++nc.epaOverflow; break; }
+    }
+    const float4 t = sh.triN[ci];
+    const f3 tn = mk3(t.x, t.y, t.z);
+    const SupPt a = P.pt(sh.triA[ci]), b = P.pt(sh.triB[ci]), c = P.pt(sh.triC[ci]);
+    f3 bc = barycentric(a.m, b.m, c.m, tn * t.w);
+    f3 pA = bc.x * a.a + bc.y * b.a + bc.z * c.a;
+    f3 pB = bc.x * a.b + bc.y * b.b + bc.z * c.b;
+    outPoint = 0.5f * (pA + pB);
+    outNormal = tn;
+    outDepth = t.w;
+    __syncwarp();
+}
+
 B200_D void storeSimplex(float4* __restrict__ pl, uint32_t cap, uint32_t e, const SimplexD& s)
 {
     const SupPt* pt[4] = { &s.a, &s.b, &s.c, &s.d };
@@ -690,7 +908,8 @@ B200_D bool gjkEpa(const SupportD& A, const SupportD& B, Man& m, NC& nc)
     }
     loadSimplex(nc.sxPlanes, nc.sxCap, nc.sxEntry, s);
     f3 p, n; float d;
-    epa(s, A, B, p, n, d, nc);
+    if (NC::phase == 3) epaWarp(*nc.epaShared, s, A, B, p, n, d, nc);
+    else epa(s, A, B, p, n, d, nc);
     m.n = n; m.cnt = 1; m.d[0] = d; m.p[0] = p;
     return true;
 }
