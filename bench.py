@@ -143,7 +143,7 @@ def rooflines(kernels, counts, n_bodies, n_colliders, n_joints, peak):
     """Algorithmic bytes (SURVEY 8d model) / measured time for the kernel groups that move the data; -> {group: {...}}."""
     P, K = counts["pairs"], counts["contacts"]
     model = {
-        "broad_phase": (n_colliders * B_GRID + P * B_PAIR_OUT, ["bp_build", "bp_query"]),
+        "broad_phase": (n_colliders * B_GRID + P * B_PAIR_OUT, ["bp_build", "bp_tiles", "bp_emit"]),
         "narrow_phase": (P * B_PAIR_NARROW + K * B_CONTACT_OUT, ["np_classify_sort", "np_closed_form_sat", "np_gjk", "np_epa", "np_compact"]),
         "solver_rows": (K * B_KINIT, ["solver_rows"]),
         "solve": (K * ITERATIONS * B_KITER + n_joints * ITERATIONS * B_JITER, ["solve"]),
@@ -416,11 +416,11 @@ def main():
 
     if rank == 0:
         dom = max(kernels, key=lambda k: kernels[k])
-        group_of = {"bp_build": "broad_phase", "bp_query": "broad_phase", "np_classify_sort": "narrow_phase", "np_closed_form_sat": "narrow_phase", "np_gjk": "narrow_phase",
+        group_of = {"bp_build": "broad_phase", "bp_tiles": "broad_phase", "bp_emit": "broad_phase", "np_classify_sort": "narrow_phase", "np_closed_form_sat": "narrow_phase", "np_gjk": "narrow_phase",
                     "np_epa": "narrow_phase", "np_compact": "narrow_phase", "solver_rows": "solver_rows", "solver_order": "solver_rows", "solve": "solve"}
         # per-kernel algorithmic bytes for the dominant kernel group (same model, split by what that kernel touches)
         P, Kc = counts["pairs"], counts["contacts"]
-        dom_bytes = {"solve": Kc * ITERATIONS * B_KITER, "bp_query": n_col * 24.0 + P * B_PAIR_OUT, "bp_build": n_col * (B_GRID - 24.0), "solver_rows": Kc * B_KINIT,
+        dom_bytes = {"solve": Kc * ITERATIONS * B_KITER, "bp_tiles": n_col * (24.0 + 128.0), "bp_emit": n_col * 128.0 + P * B_PAIR_OUT, "bp_build": n_col * (B_GRID - 24.0), "solver_rows": Kc * B_KINIT,
                      "np_epa": counts["manifolds"] * (152.0 + 128.0 + 80.0), "np_gjk": P * B_PAIR_NARROW, "np_closed_form_sat": P * B_PAIR_NARROW,
                      "np_compact": counts["manifolds"] * 80.0 + Kc * B_CONTACT_OUT + P * 16.0, "np_classify_sort": P * (8.0 + 32.0 + 1.0 + 4.0 + 16.0)}.get(dom, 0.0)
         dom_gbs = dom_bytes / (kernels[dom] * 1e-3) / 1e9 if kernels[dom] > 0 else 0.0

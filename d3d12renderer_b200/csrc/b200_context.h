@@ -27,7 +27,10 @@ struct GridParams
     float origin[3];
     int32_t dims[3];
     uint32_t numCells;
-    float bigThreshold;
+    float bigThreshold;                 // extent above which a collider skips the grid; derived by one step for the next one
+    uint32_t cellDiv, reach;            // cells per largest small extent; how many cells a query can reach beyond the centre cell
+    uint32_t segX, numSegs, numTiles;   // tile = segX consecutive cells of one grid row
+    uint32_t useTiles;                  // 1: staged tiles (dense cells), 0: direct per-collider traversal (about one collider per cell)
 };
 
 // device-resident scalars produced and consumed by kernels
@@ -54,6 +57,10 @@ struct DeviceCounts
     uint32_t epaOverflows, gjkIterationCaps, assertCount;
     unsigned long long extentSumFixed;  // sum of AABB extents, 2^-16 fixed point (deterministic mean)
     uint32_t extentCount;
+    unsigned long long smallSumFixed; uint32_t smallCount;      // the same over the colliders that go into the grid
+    uint32_t numBigNow;                 // big colliders of THIS step (numBig accumulates for the next classify pass)
+    float halfSmallExtent;              // half the largest small extent: how far a partner's centre can lie outside a query box
+    uint32_t numOverflowRows;           // colliders with more partners than the traversal keeps per row
     uint32_t maxSmallExtentBits;        // float bits (non-negative floats order like uints)
     uint32_t centreMinBits[3], centreMaxBits[3]; // sortable-uint encoded floats
     GridParams grid;
@@ -109,8 +116,10 @@ struct Context
     uint32_t* rankInCell = nullptr;
     uint32_t* cellCount = nullptr;    // maxGridCells + 1
     uint32_t* cellStart = nullptr;    // maxGridCells + 1
-    float4* sortedMin = nullptr;      // AABBs in cell order: (min.xyz, collider id bits)
-    float4* sortedMax = nullptr;
+    float4* bpRec = nullptr;          // AABBs in cell order, 32-byte records: (min.xyz, collider id bits), (max.xyz, 0)
+    uint32_t* bpRows = nullptr;       // per cell-ordered collider: up to 32 partners with a larger index, ascending
+    uint32_t* bpBigChunks = nullptr;  // pairs of big collider k inside collider chunk c: [k * numChunks + c]
+    bool bpPrimed = false;            // the big / small threshold of the previous step is valid
     uint32_t* bigList = nullptr;
     uint32_t* pairCount = nullptr;    // per collider
     uint32_t* pairStart = nullptr;    // C + 1
@@ -217,7 +226,7 @@ void launchPackAabbs(Context* c, float* devOut);
 
 // utilities (b200_util.cu)
 void launchCollisionEvents(Context* c);
-void scanExclusiveU32(Context* c, const uint32_t* in, uint32_t* out, const uint32_t* devCount, uint32_t maxCount, uint32_t* totalOut /*device, may be null*/);
+void scanExclusiveU32(Context* c, const uint32_t* in, uint32_t* out, const uint32_t* devCount, uint32_t maxCount, uint32_t* totalOut /*device, may be null*/, bool clearInput = false /* leave the scanned part of `in` zeroed */);
 void scanExclusiveU64(Context* c, const unsigned long long* in, unsigned long long* out, const uint32_t* devCount, uint32_t maxCount, unsigned long long* totalOut);
 // stable counting sort of n (device count) elements by small keys (< numKeys <= 64): dst[i] = destination slot, keyStart[k] = ranges
 void stableSmallKeySort(Context* c, const uint8_t* keys, const uint32_t* devCount, uint32_t maxCount, uint32_t numKeys, uint32_t* dst, uint32_t* keyStart);

@@ -69,8 +69,8 @@ __global__ void __launch_bounds__(1024) scanSpineKernel(T* __restrict__ blockSum
 }
 
 template <typename T>
-__global__ void __launch_bounds__(kScanThreads) scanApplyKernel(const T* __restrict__ in, T* __restrict__ out, const uint32_t* __restrict__ devCount, uint32_t hostCount,
-                                                                const T* __restrict__ blockSums, const T* __restrict__ total)
+__global__ void __launch_bounds__(kScanThreads) scanApplyKernel(T* __restrict__ in, T* __restrict__ out, const uint32_t* __restrict__ devCount, uint32_t hostCount,
+                                                                const T* __restrict__ blockSums, const T* __restrict__ total, bool clearInput)
 {
     __shared__ T warpSums[kScanThreads / 32];
     __shared__ T carryS;
@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(kScanThreads) scanApplyKernel(const T* __restr
         const uint32_t base = tile + threadIdx.x * kScanItems;
         T v[kScanItems]; T local = 0;
 #pragma unroll
-        for (int k = 0; k < kScanItems; ++k) { v[k] = (base + k < end) ? in[base + k] : (T)0; local += v[k]; }
+        for (int k = 0; k < kScanItems; ++k) { v[k] = (base + k < end) ? in[base + k] : (T)0; local += v[k]; if (clearInput && base + k < end) in[base + k] = (T)0; }
         // warp inclusive scan of the per-thread sums
         T incl = local;
 #pragma unroll
@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(kScanThreads) scanApplyKernel(const T* __restr
 }
 
 template <typename T>
-static void scanExclusive(Context* c, const T* in, T* out, const uint32_t* devCount, uint32_t maxCount, T* tmp, T* totalOut)
+static void scanExclusive(Context* c, const T* in, T* out, const uint32_t* devCount, uint32_t maxCount, T* tmp, T* totalOut, bool clearInput = false)
 {
     if (maxCount == 0) return;
     int blocks = gridFor(c, 8);
@@ -121,7 +121,7 @@ static void scanExclusive(Context* c, const T* in, T* out, const uint32_t* devCo
     T* total = tmp + 2048;
     scanReduceKernel<T><<<blocks, kScanThreads, 0, c->stream>>>(in, devCount, maxCount, tmp);
     scanSpineKernel<T><<<1, 1024, 0, c->stream>>>(tmp, (uint32_t)blocks, total);
-    scanApplyKernel<T><<<blocks, kScanThreads, 0, c->stream>>>(in, out, devCount, maxCount, tmp, total);
+    scanApplyKernel<T><<<blocks, kScanThreads, 0, c->stream>>>(const_cast<T*>(in), out, devCount, maxCount, tmp, total, clearInput);
     if (totalOut) cudaMemcpyAsync(totalOut, total, sizeof(T), cudaMemcpyDeviceToDevice, c->stream);
     c->launches += 3;
 }
@@ -133,8 +133,8 @@ static void scanExclusive(Context* c, const T* in, T* out, const uint32_t* devCo
 static const int kLbThreads = 256, kLbItems = 8, kLbTile = kLbThreads * kLbItems;
 struct ScanLbState { unsigned int ticket, done; };
 
-__global__ void __launch_bounds__(kLbThreads) scanLookbackKernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, const uint32_t* __restrict__ devCount, uint32_t hostCount,
-                                                                 unsigned long long* __restrict__ status, ScanLbState* __restrict__ state, uint32_t epoch, uint32_t* __restrict__ totalOut)
+__global__ void __launch_bounds__(kLbThreads) scanLookbackKernel(uint32_t* __restrict__ in, uint32_t* __restrict__ out, const uint32_t* __restrict__ devCount, uint32_t hostCount,
+                                                                 unsigned long long* __restrict__ status, ScanLbState* __restrict__ state, uint32_t epoch, uint32_t* __restrict__ totalOut, bool clearInput)
 {
     __shared__ uint32_t warpSums[kLbThreads / 32];
     __shared__ uint32_t sTile, sPrefix, sTileTotal;
@@ -153,11 +153,12 @@ __global__ void __launch_bounds__(kLbThreads) scanLookbackKernel(const uint32_t*
         {
             const uint4 a = *reinterpret_cast<const uint4*>(in + base), b = *reinterpret_cast<const uint4*>(in + base + 4);
             v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+            if (clearInput) { const uint4 z = make_uint4(0, 0, 0, 0); *reinterpret_cast<uint4*>(in + base) = z; *reinterpret_cast<uint4*>(in + base + 4) = z; }
         }
         else
         {
 #pragma unroll
-            for (int k = 0; k < kLbItems; ++k) v[k] = (base + k < n) ? in[base + k] : 0u;
+            for (int k = 0; k < kLbItems; ++k) { v[k] = (base + k < n) ? in[base + k] : 0u; if (clearInput && base + k < n) in[base + k] = 0u; }
         }
 #pragma unroll
         for (int k = 0; k < kLbItems; ++k) local += v[k];
@@ -231,19 +232,19 @@ __global__ void __launch_bounds__(kLbThreads) scanLookbackKernel(const uint32_t*
     }
 }
 
-void scanExclusiveU32(Context* c, const uint32_t* in, uint32_t* out, const uint32_t* devCount, uint32_t maxCount, uint32_t* totalOut)
+void scanExclusiveU32(Context* c, const uint32_t* in, uint32_t* out, const uint32_t* devCount, uint32_t maxCount, uint32_t* totalOut, bool clearInput)
 {
     if (maxCount == 0) return;
     const uint32_t maxTiles = (maxCount + kLbTile - 1) / kLbTile;
     if (maxTiles > c->scanStatusTiles || (((uintptr_t)in | (uintptr_t)out) & 15u))
     {   // unaligned buffers or more tiles than the status array holds: the three-kernel version
-        scanExclusive<uint32_t>(c, in, out, devCount, maxCount, c->scanTmp, totalOut);
+        scanExclusive<uint32_t>(c, in, out, devCount, maxCount, c->scanTmp, totalOut, clearInput);
         return;
     }
     int blocks = gridFor(c, 4);
     if ((uint32_t)blocks > maxTiles) blocks = (int)maxTiles;
     c->scanEpoch = (c->scanEpoch + 1u) & 0x3FFFFFFFu; if (c->scanEpoch == 0) c->scanEpoch = 1;
-    scanLookbackKernel<<<blocks, kLbThreads, 0, c->stream>>>(in, out, devCount, maxCount, c->scanStatus, (ScanLbState*)c->scanState, c->scanEpoch, totalOut);
+    scanLookbackKernel<<<blocks, kLbThreads, 0, c->stream>>>(const_cast<uint32_t*>(in), out, devCount, maxCount, c->scanStatus, (ScanLbState*)c->scanState, c->scanEpoch, totalOut, clearInput);
     c->launches += 1;
 }
 // 64-bit variant (two packed 32-bit sums per element): the tile status is two self-validating words, (tag | low half) and

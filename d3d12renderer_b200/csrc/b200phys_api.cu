@@ -37,12 +37,13 @@ int allocateAll(Context& c)
     CK(devAlloc(c.colorQueue, (M > J ? M : J) + 32));
     for (int k = 0; k < 6; ++k) CK(devAlloc(c.refColorsJoint[k], J + 2));
     CK(devAlloc(c.refKeys[0], M + 2)); CK(devAlloc(c.refKeys[1], M + 2)); CK(devAlloc(c.refColors, M + 2)); CK(devAlloc(c.colorKey, M + 2));
-    c.scanStatusTiles = (uint32_t)((16 * P + 2047) / 2048 + 64); CK(devAlloc(c.scanStatus, c.scanStatusTiles)); CK(devAlloc(c.scanState, 4));
+    c.scanStatusTiles = (uint32_t)((std::max<size_t>(16 * P, (size_t)c.maxCells + 2) + 2047) / 2048 + 64); CK(devAlloc(c.scanStatus, c.scanStatusTiles)); CK(devAlloc(c.scanState, 4));
     CK(cudaMemset(c.scanStatus, 0, sizeof(unsigned long long) * c.scanStatusTiles)); CK(cudaMemset(c.scanState, 0, 16));
     CK(devAlloc(c.cLocal, 4 * C)); CK(devAlloc(c.xforms, 2 * T)); CK(devAlloc(c.wCol, 4 * C)); CK(devAlloc(c.aabbMin, C)); CK(devAlloc(c.aabbMax, C));
     CK(devAlloc(c.hullVerts, 1)); CK(devAlloc(c.hullOffsets, 2)); CK(devAlloc(c.hullAabb, 2));
     CK(devAlloc(c.cellOf, C)); CK(devAlloc(c.rankInCell, C)); CK(devAlloc(c.cellCount, (size_t)c.maxCells + 2)); CK(devAlloc(c.cellStart, (size_t)c.maxCells + 2));
-    CK(devAlloc(c.sortedMin, C)); CK(devAlloc(c.sortedMax, C)); CK(devAlloc(c.bigList, kMaxBig));
+    CK(devAlloc(c.bpRec, 2 * C)); CK(devAlloc(c.bpRows, 32 * C)); CK(devAlloc(c.bpBigChunks, (size_t)kMaxBig * ((C + 2047) / 2048 + 1))); CK(devAlloc(c.bigList, kMaxBig));
+    CK(cudaMemset(c.cellCount, 0, sizeof(uint32_t) * ((size_t)c.maxCells + 2)));      // the cell scan leaves the counts cleared for the next step
     CK(devAlloc(c.pairCount, C + 2)); CK(devAlloc(c.pairStart, C + 2)); CK(devAlloc(c.pairs, P));
     CK(devAlloc(c.pairKey, P)); CK(devAlloc(c.pairsTyped, P)); CK(devAlloc(c.pairDst, P + 2)); CK(devAlloc(c.pairsSorted, P));
     CK(devAlloc(c.manTmp, 5 * P)); CK(devAlloc(c.manScan, P + 2)); CK(devAlloc(c.manScanOut, P + 2));
@@ -88,7 +89,7 @@ int allocateAll(Context& c)
 void freeAll(Context& c)
 {
     void* ptrs[] = { c.bRot, c.bPos, c.bCog, c.bInvI, c.bVel, c.bAng, c.bForce, c.bTorque, c.gVel, c.gPos, c.gInvI, c.bodyMask, c.bodyBase, c.refKeys[0], c.refKeys[1], c.refColors, c.colorKey, c.colorQueue, c.scanStatus, c.scanState, c.cLocal, c.xforms, c.wCol, c.aabbMin, c.aabbMax,
-        c.hullVerts, c.hullOffsets, c.hullAabb, c.cellOf, c.rankInCell, c.cellCount, c.cellStart, c.sortedMin, c.sortedMax, c.bigList, c.pairCount, c.pairStart, c.pairs,
+        c.hullVerts, c.hullOffsets, c.hullAabb, c.cellOf, c.rankInCell, c.cellCount, c.cellStart, c.bpRec, c.bpRows, c.bpBigChunks, c.bigList, c.pairCount, c.pairStart, c.pairs,
         c.pairKey, c.pairsTyped, c.pairDst, c.pairsSorted, c.manTmp, c.manScan, c.manScanOut, c.epaSimplex, c.epaWork, c.collisions, c.manifolds, c.contacts, c.contactBodies,
         c.unitPending, c.unitForbid, c.nbrCount, c.nbrList, c.adjStart, c.adjFill, c.adjList, c.levelStart, c.levelFill, c.slotOfContact, c.unitSlotStart, c.unitInfo, c.rows, c.rowImp, c.scanTmp, c.scanTmp64, c.sortHist, c.staging, c.counts, c.haloBuf };
     for (void* p : ptrs) if (p) cudaFree(p);
@@ -274,6 +275,7 @@ int b200phys_upload_colliders(b200phys_context* ctx, const b200phys_collider* co
     Context& c = ctx->c; CK(cudaSetDevice(c.device));
     if (count) CK(cudaMemcpyAsync(c.cLocal, colliders, sizeof(b200phys_collider) * (size_t)count, cudaMemcpyHostToDevice, c.stream));
     c.numColliders = c.numOwnedColliders = count;
+    c.bpPrimed = false;
     c.numNonCollisionColliders = 0;
     for (uint32_t i = 0; i < count; ++i) if (colliders[i].objectType == B200PHYS_OBJ_FORCE_FIELD || colliders[i].objectType == B200PHYS_OBJ_TRIGGER) ++c.numNonCollisionColliders;
     if (c.numNonCollisionColliders && !c.interactions) { c.maxInteractions = 4u * c.cfg.maxColliders + 1024u; CK(devAlloc(c.interactions, c.maxInteractions)); }
@@ -454,7 +456,7 @@ int b200phys_get_stats(b200phys_context* ctx, b200phys_stats* out)
     memset(out, 0, sizeof(*out));
     out->numBodies = c.numBodies; out->numColliders = c.numColliders; out->reserved[1] = c.numOwnedBodies; out->reserved[2] = c.numOwnedColliders; out->reserved[3] = c.numNonCollisionColliders ? d.numInteractions : 0u;
     out->numBroadphaseOverlaps = d.numPairs; out->numCollisions = d.numManifolds; out->numContacts = d.numContacts;
-    out->numBigColliders = d.numBig; out->numGridCells = d.grid.numCells;
+    out->numBigColliders = d.numBigNow; out->numGridCells = d.grid.numCells;
     for (int g = 0; g < 7; ++g) out->numColors[g] = d.numColors[g];
     out->overflowPairs = d.overflowPairs; out->overflowManifolds = d.overflowManifolds; out->overflowGrid = d.overflowGrid | d.overflowBig | (d.overflowColors << 8) | (d.overflowHalo << 16);
     out->epaOverflows = d.epaOverflows; out->gjkIterationCaps = d.gjkIterationCaps; out->assertCount = d.assertCount;

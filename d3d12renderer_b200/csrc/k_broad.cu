@@ -1,23 +1,42 @@
 // k_broad.cu -- uniform-grid broad phase. Replaces the reference's single-axis sweep-and-prune
 // (src/physics/collision_broad.cpp:87-166,297-447) but emits the SAME SET: every collider pair whose world AABBs overlap
 // under the inclusive predicate of bounding_volumes.h:352-358 (same-body and static-static pairs included; the narrow
-// phase prunes them, collision_narrow.cpp:2358-2369). Output is canonical: a < b, sorted by (a, b), built in order by a
-// count -> scan -> fill scheme (no atomics on the output, no global sort), so it is bit-reproducible run to run.
+// phase prunes them, collision_narrow.cpp:2358-2369). Output is canonical: a < b, sorted by (a, b), and bit-reproducible
+// run to run (no order-dependent atomics reach the output).
 //
-// Build:  extent statistics -> classify (grid vs "big" list) -> grid set-up on device -> bin by AABB-centre cell
-//         (count, scan, scatter a cell-ordered copy of the AABBs: 2 x 128-bit per collider).
-// Query:  one thread per cell-ordered collider walks the cell rows its expanded AABB can reach (each row is ONE contiguous
-//         range of the cell-ordered copy), tests 128-bit AABBs, keeps partners with a larger index; big colliders are
-//         tested from a shared-memory list, and each big collider sweeps all colliders with one CTA.
+// Eight launches per step (round 1: ~20, two grid traversals):
+//   classify : one pass over the AABBs: "big" colliders (extent above the threshold the PREVIOUS step derived from the mean extent)
+//              go to a brute-force list, the rest contribute to the grid statistics (max small extent, centre bounds, mean)
+//   setup    : one thread: grid resolution, reach, tile shape and the threshold for the next step
+//   bin      : cell of every small collider's AABB centre, rank inside the cell
+//   scan     : cell counts -> cell starts (the scan also clears the counts for the next step)
+//   scatter  : cell-ordered copy of the AABBs as 32-byte records (min.xyz, id | max.xyz, -)
+//   tile     : ONE traversal. A CTA owns a run of cells of one grid row; the candidate records of the neighbouring rows are contiguous
+//              runs of the cell-ordered array and are staged in shared memory by TMA bulk copies (cp.async.bulk + mbarrier), so a
+//              record is fetched once per tile instead of once per collider; every thread tests its collider against the staged
+//              records, keeps the partners with a larger index in shared memory, sorts them and writes one 128-byte row.
+//              Extra CTAs count the pairs of the big colliders chunk by chunk.
+//   scan     : partners per collider -> canonical pair offsets
+//   emit     : rows -> pair list with coalesced stores; rows that overflowed, colliders whose reach left the staged window and the
+//              big colliders' rows are produced here by direct traversal.
 // Correctness does not depend on the cell size: a partner's centre lies inside the query AABB grown by half the largest
 // small extent, and cell coordinates are a monotone function of position, so no rounding can hide a pair.
 #include "b200_context.h"
 #include "b200_util.cuh"
+#include <cstdlib>
 
 namespace b200 {
 
 static const int kThreads = 256;
-static const uint32_t kLocalPartners = 48;
+static const int kTileThreads = 128;
+static const uint32_t kRowCap = 32;              // partners kept per collider by the traversal (more: the row is rebuilt by the emit kernel)
+static const uint32_t kPartStride = kRowCap + 1; // shared-memory row stride (conflict-free per thread and per row)
+static const uint32_t kMaxReach = 1;
+static const uint32_t kMaxRows = (2 * kMaxReach + 1) * (2 * kMaxReach + 1);
+static const uint32_t kMaxSegX = 32;
+static const uint32_t kMaxWin = kMaxSegX + 2 * kMaxReach;
+static const uint32_t kBigStage = 32;            // big colliders staged in shared memory per CTA
+static const uint32_t kBigChunk = 2048;          // colliders per big-row chunk
 
 B200_D bool overlapInclusive(float4 amn, float4 amx, float4 bmn, float4 bmx)
 {   // bounding_volumes.h:352-358
@@ -29,18 +48,31 @@ B200_D bool overlapInclusive(float4 amn, float4 amx, float4 bmn, float4 bmx)
 
 B200_D float maxExtent(float4 mn, float4 mx) { return fmaxf(mx.x - mn.x, fmaxf(mx.y - mn.y, mx.z - mn.z)); }
 
-// ------------------------------------------------------------------------------------------------------ statistics
-__global__ void __launch_bounds__(kThreads) bpResetKernel(DeviceCounts* cnt)
+B200_D int cellCoord(float x, float origin, float inv, int dim)
 {
-    if (threadIdx.x == 0)
-    {
-        cnt->extentSumFixed = 0ull; cnt->extentCount = 0; cnt->maxSmallExtentBits = 0; cnt->numBig = 0;
-        for (int a = 0; a < 3; ++a) { cnt->centreMinBits[a] = 0xFFFFFFFFu; cnt->centreMaxBits[a] = 0u; }
-        cnt->numPairs = 0; cnt->numPairsWanted = 0; cnt->numEpaWork = 0; cnt->epaWorkHead = 0;
-    }
+    // monotone non-decreasing in x (fp subtract, multiply by a positive constant, floor, clamp are all monotone)
+    float f = floorf((x - origin) * inv);
+    f = fminf(fmaxf(f, 0.f), (float)(dim - 1));
+    return (int)f;
 }
 
-__global__ void __launch_bounds__(kThreads) bpExtentKernel(uint32_t C, const float4* __restrict__ mn, const float4* __restrict__ mx, DeviceCounts* cnt)
+// cells that can hold the centre of a small collider overlapping the box [amn, amx]
+struct CellRange { int x0, x1, y0, y1, z0, z1; };
+B200_D CellRange queryRange(const GridParams& g, float4 amn, float4 amx, float halfE)
+{
+    const float slackX = halfE + halfE * 1e-3f + fabsf(amn.x) * 1e-6f + fabsf(amx.x) * 1e-6f;
+    const float slackY = halfE + halfE * 1e-3f + fabsf(amn.y) * 1e-6f + fabsf(amx.y) * 1e-6f;
+    const float slackZ = halfE + halfE * 1e-3f + fabsf(amn.z) * 1e-6f + fabsf(amx.z) * 1e-6f;
+    CellRange r;
+    r.x0 = cellCoord(amn.x - slackX, g.origin[0], g.invCellSize, g.dims[0]); r.x1 = cellCoord(amx.x + slackX, g.origin[0], g.invCellSize, g.dims[0]);
+    r.y0 = cellCoord(amn.y - slackY, g.origin[1], g.invCellSize, g.dims[1]); r.y1 = cellCoord(amx.y + slackY, g.origin[1], g.invCellSize, g.dims[1]);
+    r.z0 = cellCoord(amn.z - slackZ, g.origin[2], g.invCellSize, g.dims[2]); r.z1 = cellCoord(amx.z + slackZ, g.origin[2], g.invCellSize, g.dims[2]);
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------------------ statistics
+// first step (and after an upload): mean extent -> threshold, the way every later step gets it from its predecessor's setup
+__global__ void __launch_bounds__(kThreads) bpPrimeKernel(uint32_t C, const float4* __restrict__ mn, const float4* __restrict__ mx, DeviceCounts* cnt)
 {
     unsigned long long sum = 0; uint32_t n = 0;
     for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < C; i += gridDim.x * kThreads)
@@ -50,7 +82,6 @@ __global__ void __launch_bounds__(kThreads) bpExtentKernel(uint32_t C, const flo
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { sum += __shfl_down_sync(0xffffffffu, sum, o); n += __shfl_down_sync(0xffffffffu, n, o); }
-    // one pair of atomics per CTA (same-address atomics serialise at one L2 slice)
     __shared__ unsigned long long sSum[kThreads / 32]; __shared__ uint32_t sN[kThreads / 32];
     if (laneId() == 0) { sSum[threadIdx.x >> 5] = sum; sN[threadIdx.x >> 5] = n; }
     __syncthreads();
@@ -61,29 +92,37 @@ __global__ void __launch_bounds__(kThreads) bpExtentKernel(uint32_t C, const flo
         if (tn) { atomicAdd(&cnt->extentSumFixed, ts); atomicAdd(&cnt->extentCount, tn); }
     }
 }
+__global__ void bpPrimeFinishKernel(float bigFactor, float cfgCell, DeviceCounts* cnt)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const double mean = cnt->extentCount ? ((double)cnt->extentSumFixed / 65536.0 / (double)cnt->extentCount) : 1.0;
+    cnt->grid.bigThreshold = cfgCell > 0.f ? cfgCell : (float)(mean * (double)bigFactor);
+    cnt->extentSumFixed = 0ull; cnt->extentCount = 0; cnt->smallSumFixed = 0ull; cnt->smallCount = 0; cnt->maxSmallExtentBits = 0; cnt->numBig = 0;
+    for (int a = 0; a < 3; ++a) { cnt->centreMinBits[a] = 0xFFFFFFFFu; cnt->centreMaxBits[a] = 0u; }
+}
 
-__global__ void __launch_bounds__(kThreads) bpClassifyKernel(uint32_t C, float bigFactor, float cfgCell, const float4* __restrict__ mn, const float4* __restrict__ mx,
+__global__ void __launch_bounds__(kThreads) bpClassifyKernel(uint32_t C, const float4* __restrict__ mn, const float4* __restrict__ mx,
                                                              uint32_t* __restrict__ cellOf, uint32_t* __restrict__ bigList, DeviceCounts* cnt)
 {
-    const double mean = cnt->extentCount ? ((double)cnt->extentSumFixed / 65536.0 / (double)cnt->extentCount) : 1.0;
-    float threshold = (float)(mean * (double)bigFactor);
-    if (cfgCell > 0.f) threshold = cfgCell;       // explicit cell size: anything larger goes to the big list
-    if (blockIdx.x == 0 && threadIdx.x == 0) cnt->grid.bigThreshold = threshold;
+    const float threshold = cnt->grid.bigThreshold;
     uint32_t extBits = 0, lo[3] = { 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu }, hi[3] = { 0u, 0u, 0u };
+    unsigned long long sumAll = 0, sumSmall = 0; uint32_t nAll = 0, nSmall = 0;
     for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < C; i += gridDim.x * kThreads)
     {
         const float4 a = ldStream(mn + i), b = ldStream(mx + i);
         const float e = maxExtent(a, b);
         if (a.x > b.x) { cellOf[i] = 0xFFFFFFFFu; continue; }   // inverted box = halo padding slot: neither binned nor big
+        if (e >= 0.f && e < 1e12f) { sumAll += (unsigned long long)((double)e * 65536.0); ++nAll; }
         if (!(e <= threshold))
         {   // big (or non-finite): brute force
             const uint32_t k = atomicAdd(&cnt->numBig, 1u);
             if (k < kMaxBig) bigList[k] = i; else cnt->overflowBig = 1;
-            cellOf[i] = 0xFFFFFFFFu;
+            cellOf[i] = 0xFFFFFFFEu;
         }
         else
         {
             cellOf[i] = 0;
+            sumSmall += (unsigned long long)((double)fmaxf(e, 0.f) * 65536.0); ++nSmall;
             extBits = max(extBits, __float_as_uint(fmaxf(e, 0.f)));
             const float cx = (a.x + b.x) * 0.5f, cy = (a.y + b.y) * 0.5f, cz = (a.z + b.z) * 0.5f;
             const uint32_t sx = floatToSortable(cx), sy = floatToSortable(cy), sz = floatToSortable(cz);
@@ -94,33 +133,71 @@ __global__ void __launch_bounds__(kThreads) bpClassifyKernel(uint32_t C, float b
     extBits = __reduce_max_sync(0xffffffffu, extBits);
 #pragma unroll
     for (int a = 0; a < 3; ++a) { lo[a] = __reduce_min_sync(0xffffffffu, lo[a]); hi[a] = __reduce_max_sync(0xffffffffu, hi[a]); }
-    __shared__ uint32_t sRed[kThreads / 32][7];
-    if (laneId() == 0) { sRed[threadIdx.x >> 5][0] = extBits; for (int a = 0; a < 3; ++a) { sRed[threadIdx.x >> 5][1 + a] = lo[a]; sRed[threadIdx.x >> 5][4 + a] = hi[a]; } }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+    {
+        sumAll += __shfl_down_sync(0xffffffffu, sumAll, o); sumSmall += __shfl_down_sync(0xffffffffu, sumSmall, o);
+        nAll += __shfl_down_sync(0xffffffffu, nAll, o); nSmall += __shfl_down_sync(0xffffffffu, nSmall, o);
+    }
+    __shared__ uint32_t sRed[kThreads / 32][9]; __shared__ unsigned long long sSum[kThreads / 32][2];
+    if (laneId() == 0)
+    {
+        uint32_t* r = sRed[threadIdx.x >> 5];
+        r[0] = extBits; for (int a = 0; a < 3; ++a) { r[1 + a] = lo[a]; r[4 + a] = hi[a]; } r[7] = nAll; r[8] = nSmall;
+        sSum[threadIdx.x >> 5][0] = sumAll; sSum[threadIdx.x >> 5][1] = sumSmall;
+    }
     __syncthreads();
     if (threadIdx.x == 0)
-    {   // one set of atomics per CTA
+    {   // one set of atomics per CTA (integer: the totals do not depend on the order)
         for (int w = 1; w < kThreads / 32; ++w)
         {
             extBits = max(extBits, sRed[w][0]);
             for (int a = 0; a < 3; ++a) { lo[a] = min(lo[a], sRed[w][1 + a]); hi[a] = max(hi[a], sRed[w][4 + a]); }
+            nAll += sRed[w][7]; nSmall += sRed[w][8]; sumAll += sSum[w][0]; sumSmall += sSum[w][1];
         }
         if (extBits) atomicMax(&cnt->maxSmallExtentBits, extBits);
         for (int a = 0; a < 3; ++a) { if (lo[a] != 0xFFFFFFFFu) atomicMin(&cnt->centreMinBits[a], lo[a]); if (hi[a]) atomicMax(&cnt->centreMaxBits[a], hi[a]); }
+        if (nAll) { atomicAdd(&cnt->extentSumFixed, sumAll); atomicAdd(&cnt->extentCount, nAll); }
+        if (nSmall) { atomicAdd(&cnt->smallSumFixed, sumSmall); atomicAdd(&cnt->smallCount, nSmall); }
     }
 }
 
-// single thread: derive the grid from the statistics (all on device, no host round trip)
-__global__ void bpSetupKernel(uint32_t maxCells, DeviceCounts* cnt)
+// single thread: derive the grid from the statistics (all on device, no host round trip), leave the accumulators ready for the next step
+__global__ void bpSetupKernel(uint32_t maxCells, float bigFactor, float cfgCell, uint32_t cfgCellDiv, uint32_t tileCand, uint32_t tilesMode, DeviceCounts* cnt)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     GridParams g;
-    float E = __uint_as_float(cnt->maxSmallExtentBits);
-    float s = E * 1.001f + 1e-6f;
-    if (!(s > 1e-6f)) s = 1.f;
+    const float E = __uint_as_float(cnt->maxSmallExtentBits);
+    const float meanSmall = cnt->smallCount ? (float)((double)cnt->smallSumFixed / 65536.0 / (double)cnt->smallCount) : E;
+    // cells per largest small extent: 1 when the colliders are about the same size (a sphere pile), 2 when the typical collider is
+    // clearly smaller than the largest (mixed shapes: fewer candidates per query at the price of more, emptier cells)
+    // cells per largest small extent: 1 when the colliders are about the same size (a sphere pile: 30 candidates for 25 partners), 2 when
+    // the typical collider is clearly smaller than the largest (mixed shapes: 146 -> 79 candidates per query, measured 842 -> 643 us at 1 M)
     float lo[3], hi[3];
-    bool any = cnt->centreMinBits[0] != 0xFFFFFFFFu;
+    const bool any = cnt->centreMinBits[0] != 0xFFFFFFFFu;
     for (int a = 0; a < 3; ++a) { lo[a] = any ? sortableToFloat(cnt->centreMinBits[a]) : 0.f; hi[a] = any ? sortableToFloat(cnt->centreMaxBits[a]) : 0.f; }
-    // shrink the resolution until the dense grid fits the cell budget (a coarser grid is slower, never wrong)
+    // ... and only where the coarse cells are crowded (>= 2 colliders per cell): a sparse scene (ragdolls over a wide floor) would pay for
+    // eight times as many, mostly empty cells in the cell scan
+    double cells1 = 1.0;
+    { const float s1 = E * 1.001f + 1e-6f; if (s1 > 1e-6f) for (int a = 0; a < 3; ++a) cells1 *= floor(((double)hi[a] - (double)lo[a]) / (double)s1) + 2.0; }
+    const bool crowded = (double)cnt->smallCount >= 2.0 * cells1;
+    uint32_t div = cfgCellDiv ? cfgCellDiv : ((E > 0.f && meanSmall < 0.8f * E && crowded) ? 2u : 1u);
+    if (div > 3u) div = 3u;
+    float s = 1.f;
+    for (;; --div)
+    {
+        s = (E * 1.001f + 1e-6f) / (float)div;
+        if (!(s > 1e-6f)) s = 1.f;
+        double total = 1.0; bool ok = true;
+        for (int a = 0; a < 3; ++a)
+        {
+            double d = floor(((double)hi[a] - (double)lo[a]) / (double)s) + 2.0;
+            if (d > 1048576.0) ok = false;
+            total *= d;
+        }
+        if ((ok && total <= (double)maxCells) || div == 1) break;
+    }
+    // still too many cells at one cell per extent: coarsen until the dense grid fits the budget (a coarser grid is slower, never wrong)
     for (int it = 0; it < 64; ++it)
     {
         double total = 1.0; bool ok = true;
@@ -138,22 +215,32 @@ __global__ void bpSetupKernel(uint32_t maxCells, DeviceCounts* cnt)
     for (int a = 0; a < 3; ++a) g.origin[a] = lo[a];
     g.numCells = (uint32_t)g.dims[0] * (uint32_t)g.dims[1] * (uint32_t)g.dims[2];
     if (g.numCells > maxCells) { cnt->overflowGrid = 1; g.dims[0] = g.dims[1] = g.dims[2] = 1; g.numCells = 1; }
-    g.bigThreshold = cnt->grid.bigThreshold;
+    // reach of a query in cells: the query box is at most (1 + 2 * 0.5005) E long, i.e. it ends at most E * 1.0005 / s < div + 1 cells from
+    // the centre cell (colliders at huge coordinates can exceed it: the tile kernel checks and falls back to a direct traversal)
+    const uint32_t reachNeeded = max((uint32_t)ceilf(E * 1.0006f / s), 1u);
+    g.reach = min(reachNeeded, kMaxReach);
+    // a tile is one warp's work: about 32 colliders, and the (2 reach + 1)^2 neighbouring runs should fit the staging buffer in one phase
+    const double perCell = (double)cnt->smallCount / (double)(g.numCells ? g.numCells : 1u);
+    const double rowsN = (double)((2u * g.reach + 1u) * (2u * g.reach + 1u));
+    double sx = perCell > 0.0 ? 32.0 / perCell : (double)kMaxSegX;       // (candidate runs beyond the staging buffer are staged in phases)
+    (void)rowsN; (void)tileCand;
+    g.segX = (uint32_t)fmin(fmax(sx, 1.0), (double)kMaxSegX);
+    if (g.segX > (uint32_t)g.dims[0]) g.segX = (uint32_t)g.dims[0];
+    g.numSegs = ((uint32_t)g.dims[0] + g.segX - 1u) / g.segX;
+    g.numTiles = g.numSegs * (uint32_t)g.dims[1] * (uint32_t)g.dims[2];
+    g.cellDiv = div;
+    // staging pays when a cell holds several colliders (long candidate runs); around one collider per cell the direct traversal wins
+    g.useTiles = tilesMode == 1u ? 1u : (tilesMode == 2u ? 0u : (perCell >= 2.0 ? 1u : 0u));
+    if (reachNeeded > kMaxReach) g.useTiles = 0u;       // the staged window covers kMaxReach cells each way
+    // threshold for the next step from this step's mean extent; accumulators cleared
+    const double mean = cnt->extentCount ? ((double)cnt->extentSumFixed / 65536.0 / (double)cnt->extentCount) : 1.0;
+    g.bigThreshold = cfgCell > 0.f ? cfgCell : (float)(mean * (double)bigFactor);
     cnt->grid = g;
-}
-
-B200_D int cellCoord(float x, float origin, float inv, int dim)
-{
-    // monotone non-decreasing in x (fp subtract, multiply by a positive constant, floor, clamp are all monotone)
-    float f = floorf((x - origin) * inv);
-    f = fminf(fmaxf(f, 0.f), (float)(dim - 1));
-    return (int)f;
-}
-
-__global__ void __launch_bounds__(kThreads) bpZeroCellsKernel(uint32_t* __restrict__ cellCount, const DeviceCounts* __restrict__ cnt)
-{
-    const uint32_t n = cnt->grid.numCells + 1;
-    for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads) cellCount[i] = 0;
+    cnt->halfSmallExtent = 0.5f * E;
+    cnt->numBigNow = min(cnt->numBig, kMaxBig);
+    cnt->extentSumFixed = 0ull; cnt->extentCount = 0; cnt->smallSumFixed = 0ull; cnt->smallCount = 0; cnt->maxSmallExtentBits = 0; cnt->numBig = 0;
+    for (int a = 0; a < 3; ++a) { cnt->centreMinBits[a] = 0xFFFFFFFFu; cnt->centreMaxBits[a] = 0u; }
+    cnt->numPairs = 0; cnt->numPairsWanted = 0; cnt->numEpaWork = 0; cnt->epaWorkHead = 0; cnt->numOverflowRows = 0;
 }
 
 __global__ void __launch_bounds__(kThreads) bpBinKernel(uint32_t C, const float4* __restrict__ mn, const float4* __restrict__ mx,
@@ -162,202 +249,470 @@ __global__ void __launch_bounds__(kThreads) bpBinKernel(uint32_t C, const float4
     const GridParams g = cnt->grid;
     for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < C; i += gridDim.x * kThreads)
     {
-        if (cellOf[i] == 0xFFFFFFFFu) continue;
+        if (cellOf[i] >= 0xFFFFFFFEu) continue;
         const float4 a = ldStream(mn + i), b = ldStream(mx + i);
         const int cx = cellCoord((a.x + b.x) * 0.5f, g.origin[0], g.invCellSize, g.dims[0]);
         const int cy = cellCoord((a.y + b.y) * 0.5f, g.origin[1], g.invCellSize, g.dims[1]);
         const int cz = cellCoord((a.z + b.z) * 0.5f, g.origin[2], g.invCellSize, g.dims[2]);
         const uint32_t cell = ((uint32_t)cz * (uint32_t)g.dims[1] + (uint32_t)cy) * (uint32_t)g.dims[0] + (uint32_t)cx;
         cellOf[i] = cell;
-        rankInCell[i] = atomicAdd(&cellCount[cell], 1u);
+        rankInCell[i] = atomicAdd(&cellCount[cell], 1u);   // the rank decides the position inside the cell only: pairs are sorted later
     }
 }
 
+// cell-ordered records: rec[2 e] = (min.xyz, collider id), rec[2 e + 1] = (max.xyz, 0); slotOf[id] = e. Colliders outside the grid
+// (big, padding) get an empty row here; the big ones are counted by the tile kernel's extra CTAs.
 __global__ void __launch_bounds__(kThreads) bpScatterKernel(uint32_t C, const float4* __restrict__ mn, const float4* __restrict__ mx, const uint32_t* __restrict__ cellOf,
-                                                            const uint32_t* __restrict__ rankInCell, const uint32_t* __restrict__ cellStart, float4* __restrict__ sortedMin, float4* __restrict__ sortedMax)
+                                                            uint32_t* __restrict__ rankToSlot, const uint32_t* __restrict__ cellStart, float4* __restrict__ rec, uint32_t* __restrict__ pairCount)
 {
     for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < C; i += gridDim.x * kThreads)
     {
         const uint32_t cell = cellOf[i];
-        if (cell == 0xFFFFFFFFu) continue;
-        const uint32_t pos = cellStart[cell] + rankInCell[i];
+        if (cell >= 0xFFFFFFFEu) { pairCount[i] = 0; rankToSlot[i] = 0xFFFFFFFFu; continue; }
+        const uint32_t pos = cellStart[cell] + rankToSlot[i];
         float4 a = ldStream(mn + i), b = ldStream(mx + i);
-        a.w = __uint_as_float(i);
-        sortedMin[pos] = a; sortedMax[pos] = b;
+        a.w = __uint_as_float(i); b.w = 0.f;
+        rec[2 * (size_t)pos] = a; rec[2 * (size_t)pos + 1] = b;
+        rankToSlot[i] = pos;
     }
 }
 
-// ----------------------------------------------------------------------------------------------------------- query
-// FILL == false: pairCount[id] = number of partners with a larger index.  FILL == true: write them, ascending.
-template <bool FILL>
-__global__ void __launch_bounds__(kThreads) bpQueryKernel(const float4* __restrict__ sortedMin, const float4* __restrict__ sortedMax, const uint32_t* __restrict__ cellStart,
-    const float4* __restrict__ aabbMin, const float4* __restrict__ aabbMax, const uint32_t* __restrict__ bigList,
-    uint32_t* __restrict__ pairCount, const uint32_t* __restrict__ pairStart, uint2* __restrict__ pairs, uint32_t maxPairs, DeviceCounts* cnt)
+// ------------------------------------------------------------------------------------------------- TMA / mbarrier
+B200_D uint32_t smemAddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+B200_D void mbarInit(uint64_t* bar, uint32_t count)
 {
-    __shared__ float4 sBigMin[kMaxBig / 4], sBigMax[kMaxBig / 4];   // staged in chunks of 256 big colliders
-    __shared__ uint32_t sBigId[kMaxBig / 4];
-    const GridParams g = cnt->grid;
-    const uint32_t numBinned = cellStart[g.numCells];
-    const uint32_t numBig = min(cnt->numBig, kMaxBig);
-    const float halfE = 0.5f * __uint_as_float(cnt->maxSmallExtentBits);
-    const uint32_t rounds = (numBinned + gridDim.x * kThreads - 1) / (gridDim.x * kThreads);
-    for (uint32_t r = 0; r < rounds; ++r)
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smemAddr(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+B200_D void mbarExpectTx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smemAddr(bar)), "r"(bytes) : "memory");
+}
+B200_D void mbarWait(uint64_t* bar, uint32_t parity)
+{
+    uint32_t ok;
+    do
     {
-        const uint32_t e = (r * gridDim.x + blockIdx.x) * kThreads + threadIdx.x;
-        const bool active = e < numBinned;
-        float4 amn = make_float4(0, 0, 0, 0), amx = amn; uint32_t id = 0, count = 0, base = 0, expected = 0;
-        uint32_t part[kLocalPartners];   // FILL: partners are collected and sorted in thread-local memory, then written once
-        if (active)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smemAddr(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+// contiguous global -> shared bulk copy (the 1-D TMA path: SASS UBLKCP); 16-byte aligned, size a multiple of 16
+B200_D void bulkCopyG2S(void* dstSmem, const void* srcGlobal, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smemAddr(dstSmem)), "l"(srcGlobal), "r"(bytes), "r"(smemAddr(bar)) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------ direct traversal
+// every small partner with a larger index (cells read straight from global memory) + every big partner; used where the tiled path
+// does not apply: a reach beyond the staged window, rows longer than kRowCap. F is called with each partner id.
+template <typename F>
+B200_D void traverseDirect(const GridParams& g, float halfE, uint32_t id, float4 amn, float4 amx, const float4* __restrict__ rec, const uint32_t* __restrict__ cellStart,
+                           const float4* __restrict__ aabbMin, const float4* __restrict__ aabbMax, const uint32_t* __restrict__ bigList, uint32_t numBig, F&& f)
+{
+    const CellRange r = queryRange(g, amn, amx, halfE);
+    for (int z = r.z0; z <= r.z1; ++z)
+        for (int y = r.y0; y <= r.y1; ++y)
         {
-            amn = sortedMin[e]; amx = sortedMax[e]; id = __float_as_uint(amn.w);
-            if (FILL) { base = pairStart[id]; expected = pairStart[id + 1] - base; }
-            // cells that can hold the centre of an overlapping small collider
-            const float slackX = halfE + halfE * 1e-3f + fabsf(amn.x) * 1e-6f + fabsf(amx.x) * 1e-6f;
-            const float slackY = halfE + halfE * 1e-3f + fabsf(amn.y) * 1e-6f + fabsf(amx.y) * 1e-6f;
-            const float slackZ = halfE + halfE * 1e-3f + fabsf(amn.z) * 1e-6f + fabsf(amx.z) * 1e-6f;
-            const int x0 = cellCoord(amn.x - slackX, g.origin[0], g.invCellSize, g.dims[0]), x1 = cellCoord(amx.x + slackX, g.origin[0], g.invCellSize, g.dims[0]);
-            const int y0 = cellCoord(amn.y - slackY, g.origin[1], g.invCellSize, g.dims[1]), y1 = cellCoord(amx.y + slackY, g.origin[1], g.invCellSize, g.dims[1]);
-            const int z0 = cellCoord(amn.z - slackZ, g.origin[2], g.invCellSize, g.dims[2]), z1 = cellCoord(amx.z + slackZ, g.origin[2], g.invCellSize, g.dims[2]);
-            for (int z = z0; z <= z1; ++z)
-                for (int y = y0; y <= y1; ++y)
+            const uint32_t row = ((uint32_t)z * (uint32_t)g.dims[1] + (uint32_t)y) * (uint32_t)g.dims[0];
+            const uint32_t f0 = cellStart[row + r.x0], f1 = cellStart[row + r.x1 + 1];
+            for (uint32_t e = f0; e < f1; ++e)
+            {
+                const float4 bmn = rec[2 * (size_t)e];
+                const uint32_t jd = __float_as_uint(bmn.w);
+                if (jd <= id) continue;
+                if (overlapInclusive(amn, amx, bmn, rec[2 * (size_t)e + 1])) f(jd);
+            }
+        }
+    for (uint32_t k = 0; k < numBig; ++k)
+    {
+        const uint32_t jd = bigList[k];
+        if (jd <= id) continue;
+        if (overlapInclusive(amn, amx, aabbMin[jd], aabbMax[jd])) f(jd);
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------------- tiles
+// A tile = a run of consecutive cells of one grid row; ONE WARP works on it from start to finish (no block-level barrier anywhere):
+// the lanes own up to 32 colliders of the run, lane j plans and issues the bulk copy of neighbouring row j, everybody waits on the
+// warp's own mbarrier, tests, sorts, writes rows. Sixteen or so such warps are resident per SM, each at a different point of its
+// tile, so the copy latency of one warp is covered by the tests of the others.
+static const int kWarpsPerCta = 4;
+static const uint32_t kBulkMin = 2048;           // bytes from which a staged run is worth a TMA bulk copy
+static const uint32_t kWarpCand = 256;           // candidate records staged per warp and phase (8 KB)
+struct WarpTile
+{
+    float4 rec[2 * kWarpCand];                      // staged candidate records
+    uint32_t part[32 * kPartStride];                // partners per lane
+    uint32_t start[kMaxRows * (kMaxWin + 1)];       // cell starts of the staged window, per neighbouring row
+    uint32_t pcG0[kMaxRows], pcLen[kMaxRows], pcS0[kMaxRows];     // piece of row j staged in the current phase (len 0: none)
+    alignas(8) uint64_t bar;
+};
+struct TileCtaShared { WarpTile w[kWarpsPerCta]; float4 bigMin[kBigStage], bigMax[kBigStage]; uint32_t bigId[kBigStage]; };
+
+__global__ void __launch_bounds__(kTileThreads) bpTileKernel(uint32_t C, uint32_t tileCtas, uint32_t numChunks, const float4* __restrict__ rec, const uint32_t* __restrict__ cellStart,
+    const float4* __restrict__ aabbMin, const float4* __restrict__ aabbMax, const uint32_t* __restrict__ bigList,
+    uint32_t* __restrict__ pairCount, uint32_t* __restrict__ rows, uint32_t* __restrict__ ovList, uint32_t* __restrict__ bigChunkCount, DeviceCounts* cnt)
+{
+    extern __shared__ __align__(128) unsigned char tileSmem[];
+    TileCtaShared& CS = *reinterpret_cast<TileCtaShared*>(tileSmem);
+    const GridParams g = cnt->grid;
+    const uint32_t numBig = cnt->numBigNow;
+    const uint32_t tid = threadIdx.x;
+
+    if (blockIdx.x >= tileCtas)
+    {   // ---- rows of the big colliders, counting pass: chunk c of the collider array against every big collider
+        __shared__ uint32_t sWarp[kTileThreads / 32];
+        for (uint32_t chunk = blockIdx.x - tileCtas; chunk < numChunks; chunk += gridDim.x - tileCtas)
+        {
+            const uint32_t j0 = chunk * kBigChunk;
+            for (uint32_t k = 0; k < numBig; ++k)
+            {
+                const uint32_t id = bigList[k];
+                const float4 amn = aabbMin[id], amx = aabbMax[id];
+                uint32_t n = 0;
+                for (uint32_t j = j0 + tid; j < min(C, j0 + kBigChunk); j += kTileThreads)
+                    if (j > id && overlapInclusive(amn, amx, ldStream(aabbMin + j), ldStream(aabbMax + j))) ++n;
+                n = __reduce_add_sync(0xffffffffu, n);
+                if (laneId() == 0) sWarp[tid >> 5] = n;
+                __syncthreads();
+                if (tid == 0)
                 {
-                    const uint32_t row = ((uint32_t)z * (uint32_t)g.dims[1] + (uint32_t)y) * (uint32_t)g.dims[0];
-                    const uint32_t f0 = cellStart[row + x0], f1 = cellStart[row + x1 + 1];   // one contiguous candidate range per row
-                    for (uint32_t f = f0; f < f1; ++f)
+                    uint32_t t = 0; for (int w = 0; w < kTileThreads / 32; ++w) t += sWarp[w];
+                    bigChunkCount[(size_t)k * numChunks + chunk] = t;
+                    if (t) atomicAdd(&pairCount[id], t);
+                }
+                __syncthreads();
+            }
+        }
+        return;
+    }
+
+    if (!g.useTiles) return;
+    const float halfE = cnt->halfSmallExtent;
+    const uint32_t R = g.reach, side = 2u * R + 1u, nRows = side * side, nx = (uint32_t)g.dims[0], ny = (uint32_t)g.dims[1], nz = (uint32_t)g.dims[2];
+    const uint32_t lane = tid & 31u, warpInCta = tid >> 5;
+    WarpTile& S = CS.w[warpInCta];
+    if (lane == 0) mbarInit(&S.bar, 1);
+    // big colliders staged once per CTA
+    const uint32_t nBigS = min(numBig, kBigStage);
+    if (tid < nBigS) { const uint32_t b = bigList[tid]; CS.bigId[tid] = b; CS.bigMin[tid] = aabbMin[b]; CS.bigMax[tid] = aabbMax[b]; }
+    __syncthreads();
+    uint32_t parity = 0;
+    const uint32_t numWarps = tileCtas * kWarpsPerCta;
+
+    for (uint32_t tile = blockIdx.x * kWarpsPerCta + warpInCta; tile < g.numTiles; tile += numWarps)
+    {
+        const uint32_t seg = tile % g.numSegs, rowId = tile / g.numSegs;
+        const uint32_t y = rowId % ny, z = rowId / ny;
+        const uint32_t xa = seg * g.segX, xb = min(xa + g.segX, nx);
+        const uint32_t rowBase = rowId * nx;
+        const uint32_t o0 = cellStart[rowBase + xa], o1 = cellStart[rowBase + xb];
+        if (o0 == o1) continue;                               // empty tile (uniform across the warp)
+        const uint32_t wx0 = xa > R ? xa - R : 0u, wx1 = min(xb + R, nx), W = wx1 - wx0;
+        // cell starts of the window in every neighbouring row
+        {
+            uint32_t j = 0;
+            for (int dz = -(int)R; dz <= (int)R; ++dz)
+                for (int dy = -(int)R; dy <= (int)R; ++dy, ++j)
+                {
+                    const int yy = (int)y + dy, zz = (int)z + dz;
+                    const bool valid = yy >= 0 && yy < (int)ny && zz >= 0 && zz < (int)nz;
+                    const uint32_t* src = cellStart + ((uint32_t)(valid ? zz : 0) * ny + (uint32_t)(valid ? yy : 0)) * nx + wx0;
+                    for (uint32_t xi = lane; xi <= W; xi += 32u) S.start[j * (kMaxWin + 1u) + xi] = valid ? src[xi] : 0u;
+                }
+        }
+        __syncwarp();
+        // lane j < nRows looks after neighbouring row j: its staged range in global record indices
+        uint32_t rowG0 = 0, rowLen = 0;
+        if (lane < nRows) { rowG0 = S.start[lane * (kMaxWin + 1u)]; rowLen = S.start[lane * (kMaxWin + 1u) + W] - rowG0; }
+
+        for (uint32_t ob = o0; ob < o1; ob += 32u)
+        {
+            const uint32_t e = ob + lane;
+            const bool active = e < o1;
+            float4 amn = make_float4(0, 0, 0, 0), amx = amn; uint32_t id = 0, count = 0; bool direct = false;
+            CellRange q = { 0, -1, 0, -1, 0, -1 };
+            if (active)
+            {
+                amn = rec[2 * (size_t)e]; amx = rec[2 * (size_t)e + 1]; id = __float_as_uint(amn.w);
+                q = queryRange(g, amn, amx, halfE);
+                // the staged window covers cells [wx0, wx1) of the rows within R of this row; anything else is traversed directly
+                direct = q.x0 < (int)wx0 || q.x1 >= (int)wx1 || q.y0 + (int)R < (int)y || q.y1 > (int)(y + R) || q.z0 + (int)R < (int)z || q.z1 > (int)(z + R);
+            }
+            uint32_t doneOff = 0;      // lane j: records of its row already staged in earlier phases
+            for (;;)
+            {
+                // ---- plan one phase: rows in order, as many records as the staging buffer holds (prefix sum over the lanes)
+                const uint32_t remaining = rowLen - doneOff;
+                uint32_t incl = remaining;
+#pragma unroll
+                for (int o = 1; o < 16; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (uint32_t)o) incl += t; }
+                const uint32_t excl = incl - remaining;
+                const uint32_t take = excl >= kWarpCand ? 0u : min(remaining, kWarpCand - excl);
+                const uint32_t total = min(__shfl_sync(0xffffffffu, incl, 15), kWarpCand);
+                if (total == 0) break;
+                if (lane < nRows) { S.pcG0[lane] = rowG0 + doneOff; S.pcLen[lane] = take; S.pcS0[lane] = excl; }
+                // Staging. A run of at least kBulkMin bytes goes through the TMA unit (one cp.async.bulk, completion on the warp's
+                // mbarrier); shorter runs are copied by the lanes with 16-byte cp.async: measured, a bulk copy costs the SM's single
+                // TMA unit ~150 ns whatever its size, so thousands of sub-kilobyte copies per SM serialise there.
+                const bool bulk = take * 32u >= kBulkMin;
+                const uint32_t bulkBytes = __reduce_add_sync(0xffffffffu, bulk ? take * 32u : 0u);
+                if (bulkBytes && lane == 0) mbarExpectTx(&S.bar, bulkBytes);
+                __syncwarp();
+                if (bulk) bulkCopyG2S(&S.rec[2 * excl], rec + 2 * (size_t)(rowG0 + doneOff), take * 32u, &S.bar);
+                for (uint32_t j = 0; j < nRows; ++j)
+                {
+                    const uint32_t len = S.pcLen[j];
+                    if (!len || len * 32u >= kBulkMin) continue;                      // (uniform)
+                    const float4* src = rec + 2 * (size_t)S.pcG0[j]; float4* dst = &S.rec[2 * S.pcS0[j]];
+                    for (uint32_t u = lane; u < 2u * len; u += 32u)
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"(smemAddr(dst + u)), "l"(src + u) : "memory");
+                }
+                asm volatile("cp.async.wait_all;" ::: "memory");
+                doneOff += take;
+                if (bulkBytes) { mbarWait(&S.bar, parity); parity ^= 1u; }
+                __syncwarp();
+                if (active && !direct)
+                {
+                    for (uint32_t j = 0; j < nRows; ++j)
                     {
-                        const float4 bmn = sortedMin[f];
-                        const uint32_t jd = __float_as_uint(bmn.w);
-                        if (jd <= id) continue;
-                        if (!overlapInclusive(amn, amx, bmn, sortedMax[f])) continue;
-                        if (FILL) { if (expected <= kLocalPartners) part[count] = jd; else if (base + count < maxPairs) pairs[base + count] = make_uint2(id, jd); else cnt->overflowPairs = 1; }
+                        const uint32_t len = S.pcLen[j];
+                        if (!len) continue;
+                        const int yy = (int)y + (int)(j % side) - (int)R, zz = (int)z + (int)(j / side) - (int)R;
+                        if (yy < q.y0 || yy > q.y1 || zz < q.z0 || zz > q.z1) continue;
+                        const uint32_t* st = &S.start[j * (kMaxWin + 1u)];
+                        const uint32_t g0 = S.pcG0[j];
+                        const uint32_t f0 = max(st[(uint32_t)q.x0 - wx0], g0), f1 = min(st[(uint32_t)q.x1 + 1u - wx0], g0 + len);
+                        const uint32_t sBase = S.pcS0[j] - g0;
+                        // four candidates per trip (eight independent shared-memory loads in flight); the last trip re-reads the final record
+                        // for the slots beyond the range and ignores them
+                        for (uint32_t f = f0; f < f1; f += 4u)
+                        {
+                            float4 bmn[4], bmx[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) { const uint32_t fi = min(f + (uint32_t)u, f1 - 1u) + sBase; bmn[u] = S.rec[2 * fi]; bmx[u] = S.rec[2 * fi + 1]; }
+#pragma unroll
+                            for (int u = 0; u < 4; ++u)
+                            {
+                                const uint32_t jd = __float_as_uint(bmn[u].w);
+                                if (f + (uint32_t)u < f1 && jd > id && overlapInclusive(amn, amx, bmn[u], bmx[u])) { if (count < kRowCap) S.part[lane * kPartStride + count] = jd; ++count; }
+                            }
+                        }
+                    }
+                }
+                __syncwarp();                                           // every lane is done with the staged records
+            }
+            if (active)
+            {
+                if (!direct)
+                {   // big colliders (staged; beyond kBigStage from global memory)
+                    for (uint32_t k = 0; k < numBig; ++k)
+                    {
+                        uint32_t jd; float4 bmn, bmx;
+                        if (k < nBigS) { jd = CS.bigId[k]; bmn = CS.bigMin[k]; bmx = CS.bigMax[k]; } else { jd = bigList[k]; bmn = aabbMin[jd]; bmx = aabbMax[jd]; }
+                        if (jd <= id || !overlapInclusive(amn, amx, bmn, bmx)) continue;
+                        if (count < kRowCap) S.part[lane * kPartStride + count] = jd;
                         ++count;
                     }
                 }
-        }
-        // big colliders, staged through shared memory 256 at a time
-        for (uint32_t b0 = 0; b0 < numBig; b0 += kMaxBig / 4)
-        {
-            __syncthreads();
-            const uint32_t nb = min(kMaxBig / 4, numBig - b0);
-            if (threadIdx.x < nb) { const uint32_t b = bigList[b0 + threadIdx.x]; sBigId[threadIdx.x] = b; sBigMin[threadIdx.x] = aabbMin[b]; sBigMax[threadIdx.x] = aabbMax[b]; }
-            __syncthreads();
-            if (active)
-                for (uint32_t k = 0; k < nb; ++k)
+                else
                 {
-                    const uint32_t jd = sBigId[k];
-                    if (jd <= id) continue;
-                    if (!overlapInclusive(amn, amx, sBigMin[k], sBigMax[k])) continue;
-                    if (FILL) { if (expected <= kLocalPartners) part[count] = jd; else if (base + count < maxPairs) pairs[base + count] = make_uint2(id, jd); else cnt->overflowPairs = 1; }
-                    ++count;
+                    count = 0;
+                    traverseDirect(g, halfE, id, amn, amx, rec, cellStart, aabbMin, aabbMax, bigList, numBig,
+                                   [&](uint32_t jd) { if (count < kRowCap) S.part[lane * kPartStride + count] = jd; ++count; });
                 }
-        }
-        if (active)
-        {
-            if (!FILL) pairCount[id] = count;
-            else if (expected <= kLocalPartners)
-            {   // ascending partner order: insertion sort in local memory, then one sequential write of the segment
-                for (uint32_t a = 1; a < count; ++a)
-                {
-                    const uint32_t key = part[a];
-                    uint32_t b = a;
-                    while (b > 0 && part[b - 1] > key) { part[b] = part[b - 1]; --b; }
-                    part[b] = key;
-                }
-                for (uint32_t a = 0; a < count; ++a) { if (base + a < maxPairs) pairs[base + a] = make_uint2(id, part[a]); else cnt->overflowPairs = 1; }
-            }
-            else
-            {   // rare: more partners than the local buffer -> insertion sort in place in global memory
-                const uint32_t n = (base + count <= maxPairs) ? count : (base < maxPairs ? maxPairs - base : 0);
+                pairCount[id] = count;
+                if (count > kRowCap) { const uint32_t k = atomicAdd(&cnt->numOverflowRows, 1u); if (k < C) ovList[k] = id; }    // rebuilt by the emit kernel
+                // ascending partner order (the canonical pair order)
+                const uint32_t n = min(count, kRowCap);
+                uint32_t* P = &S.part[lane * kPartStride];
                 for (uint32_t a = 1; a < n; ++a)
                 {
-                    const uint2 key = pairs[base + a];
-                    uint32_t b = a;
-                    while (b > 0 && pairs[base + b - 1].y > key.y) { pairs[base + b] = pairs[base + b - 1]; --b; }
-                    pairs[base + b] = key;
+                    const uint32_t key = P[a]; uint32_t b = a;
+                    while (b > 0 && P[b - 1] > key) { P[b] = P[b - 1]; --b; }
+                    P[b] = key;
                 }
+            }
+            if (active)
+            {   // the lane's 128-byte row, 16 bytes at a time
+                const uint32_t n = min(count, kRowCap);
+                const uint32_t* P = &S.part[lane * kPartStride];
+                uint4* dst = reinterpret_cast<uint4*>(rows + (size_t)e * kRowCap);
+                for (uint32_t k = 0; k < n; k += 4u) dst[k >> 2] = make_uint4(P[k], P[k + 1], P[k + 2], P[k + 3]);     // (the row buffer is 33 words: k + 3 <= 32)
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// The same traversal without staging: one thread per cell-ordered collider reads its candidate runs straight from global memory (L1 / L2).
+// Wins where a cell holds about one collider (sphere piles, ragdoll fields): too few records per run for staging to pay.
+static const int kDirectThreads = 256;
+__global__ void __launch_bounds__(kDirectThreads) bpRowsDirectKernel(uint32_t C, const float4* __restrict__ rec, const uint32_t* __restrict__ cellStart,
+    const float4* __restrict__ aabbMin, const float4* __restrict__ aabbMax, const uint32_t* __restrict__ bigList,
+    uint32_t* __restrict__ pairCount, uint32_t* __restrict__ rows, uint32_t* __restrict__ ovList, DeviceCounts* cnt)
+{
+    __shared__ uint32_t sPart[kDirectThreads * kPartStride];
+    __shared__ float4 sBigMin[kBigStage], sBigMax[kBigStage]; __shared__ uint32_t sBigId[kBigStage];
+    const GridParams g = cnt->grid;
+    if (g.useTiles) return;
+    const uint32_t numBig = cnt->numBigNow, nBigS = min(numBig, kBigStage);
+    const float halfE = cnt->halfSmallExtent;
+    if (threadIdx.x < nBigS) { const uint32_t b = bigList[threadIdx.x]; sBigId[threadIdx.x] = b; sBigMin[threadIdx.x] = aabbMin[b]; sBigMax[threadIdx.x] = aabbMax[b]; }
+    __syncthreads();
+    const uint32_t numBinned = cellStart[g.numCells];
+    uint32_t* P = &sPart[threadIdx.x * kPartStride];
+    for (uint32_t e = blockIdx.x * kDirectThreads + threadIdx.x; e < numBinned; e += gridDim.x * kDirectThreads)
+    {
+        const float4 amn = rec[2 * (size_t)e], amx = rec[2 * (size_t)e + 1];
+        const uint32_t id = __float_as_uint(amn.w);
+        uint32_t count = 0;
+        const CellRange r = queryRange(g, amn, amx, halfE);
+        for (int z = r.z0; z <= r.z1; ++z)
+            for (int y = r.y0; y <= r.y1; ++y)
+            {
+                const uint32_t row = ((uint32_t)z * (uint32_t)g.dims[1] + (uint32_t)y) * (uint32_t)g.dims[0];
+                const uint32_t f0 = cellStart[row + r.x0], f1 = cellStart[row + r.x1 + 1];
+                for (uint32_t f = f0; f < f1; f += 2u)
+                {   // two candidates per trip: four independent loads
+                    const uint32_t fb = min(f + 1u, f1 - 1u);
+                    const float4 mn0 = rec[2 * (size_t)f], mx0 = rec[2 * (size_t)f + 1], mn1 = rec[2 * (size_t)fb], mx1 = rec[2 * (size_t)fb + 1];
+                    const uint32_t j0 = __float_as_uint(mn0.w), j1 = __float_as_uint(mn1.w);
+                    if (j0 > id && overlapInclusive(amn, amx, mn0, mx0)) { if (count < kRowCap) P[count] = j0; ++count; }
+                    if (f + 1u < f1 && j1 > id && overlapInclusive(amn, amx, mn1, mx1)) { if (count < kRowCap) P[count] = j1; ++count; }
+                }
+            }
+        for (uint32_t k = 0; k < numBig; ++k)
+        {
+            uint32_t jd; float4 bmn, bmx;
+            if (k < nBigS) { jd = sBigId[k]; bmn = sBigMin[k]; bmx = sBigMax[k]; } else { jd = bigList[k]; bmn = aabbMin[jd]; bmx = aabbMax[jd]; }
+            if (jd <= id || !overlapInclusive(amn, amx, bmn, bmx)) continue;
+            if (count < kRowCap) P[count] = jd;
+            ++count;
+        }
+        pairCount[id] = count;
+        if (count > kRowCap) { const uint32_t k = atomicAdd(&cnt->numOverflowRows, 1u); if (k < C) ovList[k] = id; }
+        const uint32_t n = min(count, kRowCap);
+        for (uint32_t a = 1; a < n; ++a)
+        {
+            const uint32_t key = P[a]; uint32_t b = a;
+            while (b > 0 && P[b - 1] > key) { P[b] = P[b - 1]; --b; }
+            P[b] = key;
+        }
+        uint4* dst = reinterpret_cast<uint4*>(rows + (size_t)e * kRowCap);
+        for (uint32_t k = 0; k < n; k += 4u) dst[k >> 2] = make_uint4(P[k], P[k + 1], P[k + 2], P[k + 3]);
+    }
+}
+
+// -------------------------------------------------------------------------------------------------------- emit
+// rows -> canonical pair list. One warp per 32 consecutive collider ids: their pairs are one contiguous run of the output, written
+// with coalesced 8-byte stores; each output position finds its row by a search over the warp's 32 row starts.
+__global__ void __launch_bounds__(kThreads) bpEmitKernel(uint32_t C, uint32_t emitCtas, uint32_t numChunks, const uint32_t* __restrict__ slotOf, const uint32_t* __restrict__ rows,
+    const uint32_t* __restrict__ pairCount, const uint32_t* __restrict__ pairStart, const float4* __restrict__ rec, const uint32_t* __restrict__ cellStart,
+    const float4* __restrict__ aabbMin, const float4* __restrict__ aabbMax, const uint32_t* __restrict__ bigList, const uint32_t* __restrict__ ovList,
+    const uint32_t* __restrict__ bigChunkCount, uint2* __restrict__ pairs, uint32_t maxPairs, DeviceCounts* cnt)
+{
+    const GridParams g = cnt->grid;
+    const uint32_t numBig = cnt->numBigNow;
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+    {
+        const uint32_t total = pairStart[C];
+        cnt->numPairsWanted = total; cnt->numPairs = min(total, maxPairs);
+        if (total > maxPairs) cnt->overflowPairs = 1;
+    }
+    if (blockIdx.x < emitCtas)
+    {
+        const uint32_t lane = laneId();
+        const uint32_t warpsTotal = emitCtas * (kThreads / 32), warp = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+        for (uint32_t id0 = warp * 32u; id0 < C; id0 += warpsTotal * 32u)
+        {
+            const uint32_t id = id0 + lane;
+            const uint32_t start = id < C ? pairStart[id] : 0xFFFFFFFFu;
+            uint32_t cntI = id < C ? pairCount[id] : 0u;
+            const uint32_t slot = id < C ? slotOf[id] : 0xFFFFFFFFu;
+            if (cntI > kRowCap || slot == 0xFFFFFFFFu) cntI = 0;      // written by the paths below (overflow rows, big colliders)
+            const uint32_t base = __shfl_sync(0xffffffffu, start, 0);
+            const uint32_t endId = min(id0 + 32u, C);
+            const uint32_t end = pairStart[endId];
+            for (uint32_t p0 = base; p0 < end; p0 += 32u)
+            {
+                const uint32_t p = p0 + lane;                                   // (all lanes take part in the shuffles below)
+                // row i = last lane whose start <= p
+                uint32_t i = 0;
+#pragma unroll
+                for (int step = 16; step > 0; step >>= 1)
+                {
+                    const uint32_t cand = i + (uint32_t)step;
+                    const uint32_t s = __shfl_sync(0xffffffffu, start, (int)min(cand, 31u));
+                    if (cand < 32u && s <= p) i = cand;
+                }
+                const uint32_t si = __shfl_sync(0xffffffffu, start, (int)i), ci = __shfl_sync(0xffffffffu, cntI, (int)i), sl = __shfl_sync(0xffffffffu, slot, (int)i);
+                const uint32_t k = p - si;
+                if (p < end && k < ci && p < maxPairs) pairs[p] = make_uint2(id0 + i, rows[(size_t)sl * kRowCap + k]);
+            }
+        }
+        return;
+    }
+    const float halfE = cnt->halfSmallExtent;
+    const uint32_t extra = blockIdx.x - emitCtas, numExtra = gridDim.x - emitCtas;
+    // ---- rows with more than kRowCap partners: direct traversal straight into the pair list, then sorted in place (rare)
+    {
+        const uint32_t nOv = min(cnt->numOverflowRows, C);
+        for (uint32_t o = extra * kThreads + threadIdx.x; o < nOv; o += numExtra * kThreads)
+        {
+            const uint32_t id = ovList[o];
+            const uint32_t base = pairStart[id];
+            const float4 amn = aabbMin[id], amx = aabbMax[id];
+            uint32_t count = 0;
+            traverseDirect(g, halfE, id, amn, amx, rec, cellStart, aabbMin, aabbMax, bigList, numBig,
+                           [&](uint32_t jd) { if (base + count < maxPairs) pairs[base + count] = make_uint2(id, jd); ++count; });
+            const uint32_t n = (base + count <= maxPairs) ? count : (base < maxPairs ? maxPairs - base : 0);
+            for (uint32_t a = 1; a < n; ++a)
+            {
+                const uint2 key = pairs[base + a];
+                uint32_t b = a;
+                while (b > 0 && pairs[base + b - 1].y > key.y) { pairs[base + b] = pairs[base + b - 1]; --b; }
+                pairs[base + b] = key;
             }
         }
     }
-}
-
-// one CTA per big collider: sweep every collider with a larger index, ordered compaction
-template <bool FILL>
-__global__ void __launch_bounds__(kThreads) bpBigKernel(uint32_t C, uint32_t firstSlot, const float4* __restrict__ aabbMin, const float4* __restrict__ aabbMax, const uint32_t* __restrict__ bigList,
-    uint32_t* __restrict__ pairCount, const uint32_t* __restrict__ pairStart, uint2* __restrict__ pairs, uint32_t maxPairs, DeviceCounts* cnt)
-{
-    __shared__ uint32_t warpCnt[kThreads / 32];
-    __shared__ uint32_t running;
-    const uint32_t numBig = min(cnt->numBig, kMaxBig);
-    for (uint32_t k = firstSlot + blockIdx.x; k < numBig; k += gridDim.x)
+    // ---- rows of the big colliders: chunk by chunk in collider order, positions from the chunk counts
     {
-        const uint32_t id = bigList[k];
-        const float4 amn = aabbMin[id], amx = aabbMax[id];
-        const uint32_t base = FILL ? pairStart[id] : 0;
-        if (threadIdx.x == 0) running = 0;
-        __syncthreads();
-        for (uint32_t j0 = id + 1; j0 < C; j0 += kThreads)
+        __shared__ uint32_t sWarp[kThreads / 32]; __shared__ uint32_t sOffset;
+        for (uint32_t chunk = extra; chunk < numChunks; chunk += numExtra)
         {
-            const uint32_t j = j0 + threadIdx.x;
-            const bool hit = (j < C) && overlapInclusive(amn, amx, ldStream(aabbMin + j), ldStream(aabbMax + j));
-            const uint32_t ballot = __ballot_sync(0xffffffffu, hit);
-            if (laneId() == 0) warpCnt[threadIdx.x >> 5] = __popc(ballot);
-            __syncthreads();
-            uint32_t off = running;
-            for (uint32_t w = 0; w < (threadIdx.x >> 5); ++w) off += warpCnt[w];
-            off += __popc(ballot & laneMaskLt());
-            if (FILL && hit) { if (base + off < maxPairs) pairs[base + off] = make_uint2(id, j); else cnt->overflowPairs = 1; }
-            __syncthreads();
-            if (threadIdx.x == 0) { uint32_t t = 0; for (int w = 0; w < kThreads / 32; ++w) t += warpCnt[w]; running += t; }
-            __syncthreads();
+            const uint32_t j0 = chunk * kBigChunk;
+            for (uint32_t k = 0; k < numBig; ++k)
+            {
+                if (bigChunkCount[(size_t)k * numChunks + chunk] == 0) continue;      // uniform
+                const uint32_t id = bigList[k];
+                const float4 amn = aabbMin[id], amx = aabbMax[id];
+                if (threadIdx.x < 32)
+                {   // pairs of this row in earlier chunks
+                    uint32_t s = 0;
+                    for (uint32_t c2 = threadIdx.x; c2 < chunk; c2 += 32u) s += bigChunkCount[(size_t)k * numChunks + c2];
+                    s = __reduce_add_sync(0xffffffffu, s);
+                    if (threadIdx.x == 0) sOffset = pairStart[id] + s;
+                }
+                __syncthreads();
+                uint32_t running = sOffset;
+                for (uint32_t jb = j0; jb < min(C, j0 + kBigChunk); jb += kThreads)
+                {
+                    const uint32_t j = jb + threadIdx.x;
+                    const bool hit = j < C && j > id && overlapInclusive(amn, amx, ldStream(aabbMin + j), ldStream(aabbMax + j));
+                    const uint32_t ballot = __ballot_sync(0xffffffffu, hit);
+                    if (laneId() == 0) sWarp[threadIdx.x >> 5] = (uint32_t)__popc(ballot);
+                    __syncthreads();
+                    uint32_t off = running, tot = 0;
+                    for (uint32_t w = 0; w < kThreads / 32; ++w) { if (w < (threadIdx.x >> 5)) off += sWarp[w]; tot += sWarp[w]; }
+                    off += (uint32_t)__popc(ballot & laneMaskLt());
+                    if (hit) { if (off < maxPairs) pairs[off] = make_uint2(id, j); else cnt->overflowPairs = 1; }
+                    running += tot;
+                    __syncthreads();
+                }
+            }
         }
-        if (!FILL && threadIdx.x == 0) pairCount[id] = running;
-        __syncthreads();
-    }
-}
-
-// Big colliders, parallel path (numBig * C <= scratch): flag matrix [slot][j] = (j > id_slot && overlap), ONE exclusive scan over
-// the flattened matrix gives every pair its ordered position inside the big collider's segment.
-__global__ void __launch_bounds__(kThreads) bpBigFlagKernel(uint32_t C, const float4* __restrict__ aabbMin, const float4* __restrict__ aabbMax, const uint32_t* __restrict__ bigList,
-                                                            uint32_t* __restrict__ flags, const DeviceCounts* __restrict__ cnt)
-{
-    __shared__ float4 sMin[16], sMax[16]; __shared__ uint32_t sId[16];
-    const uint32_t nb = min(cnt->numBig, 16u);
-    if (threadIdx.x < nb) { const uint32_t b = bigList[threadIdx.x]; sId[threadIdx.x] = b; sMin[threadIdx.x] = aabbMin[b]; sMax[threadIdx.x] = aabbMax[b]; }
-    __syncthreads();
-    for (uint32_t j = blockIdx.x * kThreads + threadIdx.x; j < C; j += gridDim.x * kThreads)
-    {
-        const float4 mn = ldStream(aabbMin + j), mx = ldStream(aabbMax + j);
-        for (uint32_t k = 0; k < nb; ++k) flags[(size_t)k * C + j] = (j > sId[k] && overlapInclusive(sMin[k], sMax[k], mn, mx)) ? 1u : 0u;
-    }
-}
-__global__ void bpBigCountKernel(uint32_t C, const uint32_t* __restrict__ bigList, const uint32_t* __restrict__ offs, uint32_t* __restrict__ pairCount, DeviceCounts* cnt)
-{
-    const uint32_t nb = min(cnt->numBig, 16u);
-    if (threadIdx.x < nb) pairCount[bigList[threadIdx.x]] = offs[(size_t)(threadIdx.x + 1) * C] - offs[(size_t)threadIdx.x * C];
-}
-__global__ void __launch_bounds__(kThreads) bpBigFillKernel(uint32_t C, const uint32_t* __restrict__ bigList, const uint32_t* __restrict__ flags, const uint32_t* __restrict__ offs,
-                                                            const uint32_t* __restrict__ pairStart, uint2* __restrict__ pairs, uint32_t maxPairs, DeviceCounts* cnt)
-{
-    const uint32_t nb = min(cnt->numBig, 16u);
-    const size_t total = (size_t)nb * C;
-    for (size_t idx = (size_t)blockIdx.x * kThreads + threadIdx.x; idx < total; idx += (size_t)gridDim.x * kThreads)
-    {
-        if (!flags[idx]) continue;
-        const uint32_t k = (uint32_t)(idx / C), j = (uint32_t)(idx - (size_t)k * C), id = bigList[k];
-        const uint32_t pos = pairStart[id] + (offs[idx] - offs[(size_t)k * C]);
-        if (pos < maxPairs) pairs[pos] = make_uint2(id, j); else cnt->overflowPairs = 1;
-    }
-}
-__global__ void bpBigCountDeviceKernel(uint32_t C, DeviceCounts* cnt) { if (threadIdx.x == 0) cnt->bigMatrixCount = min(cnt->numBig, 16u) * C; }
-
-__global__ void bpFinishKernel(uint32_t C, const uint32_t* __restrict__ pairStart, uint32_t maxPairs, DeviceCounts* cnt)
-{
-    if (threadIdx.x == 0 && blockIdx.x == 0)
-    {
-        const uint32_t total = pairStart[C];
-        cnt->numPairsWanted = total;
-        cnt->numPairs = min(total, maxPairs);
-        if (total > maxPairs) cnt->overflowPairs = 1;
     }
 }
 
@@ -367,41 +722,48 @@ void launchBroadphase(Context* c)
     DeviceCounts* cnt = c->counts;
     const float bigFactor = c->cfg.bigFactor > 0.f ? c->cfg.bigFactor : 3.f;
     const int G = gridFor(c, 8);
-    bpResetKernel<<<1, 32, 0, c->stream>>>(cnt);
-    if (C == 0) { c->launches += 1; return; }
-    bpExtentKernel<<<G, kThreads, 0, c->stream>>>(C, c->aabbMin, c->aabbMax, cnt);
-    bpClassifyKernel<<<G, kThreads, 0, c->stream>>>(C, bigFactor, c->cfg.cellSize, c->aabbMin, c->aabbMax, c->cellOf, c->bigList, cnt);
-    bpSetupKernel<<<1, 32, 0, c->stream>>>(c->maxCells, cnt);
-    bpZeroCellsKernel<<<G, kThreads, 0, c->stream>>>(c->cellCount, cnt);
-    bpBinKernel<<<G, kThreads, 0, c->stream>>>(C, c->aabbMin, c->aabbMax, c->cellOf, c->rankInCell, c->cellCount, cnt);
-    c->launches += 6;
-    scanExclusiveU32(c, c->cellCount, c->cellStart, &cnt->grid.numCells, c->maxCells, nullptr);
-    bpScatterKernel<<<G, kThreads, 0, c->stream>>>(C, c->aabbMin, c->aabbMax, c->cellOf, c->rankInCell, c->cellStart, c->sortedMin, c->sortedMax);
-    timelineMark(c, "bp_build");
-    cudaMemsetAsync(c->pairCount, 0, sizeof(uint32_t) * (C + 1), c->stream);
-    bpQueryKernel<false><<<G, kThreads, 0, c->stream>>>(c->sortedMin, c->sortedMax, c->cellStart, c->aabbMin, c->aabbMax, c->bigList, c->pairCount, c->pairStart, c->pairs, c->maxPairs, cnt);
-    // big colliders: parallel flag-matrix path for up to 16 of them (scratch: pair-sized buffers that are free until the narrow
-    // phase); beyond that one CTA per big collider sweeps all colliders (bpBigKernel, skips the first 16)
-    uint32_t* bigFlags = c->pairDst; uint32_t* bigOffs = (uint32_t*)c->manScan;
-    const bool matrixFits = (size_t)16 * C <= (size_t)c->maxPairs;   // both scratch buffers hold maxPairs + 2 words
-    if (matrixFits)
+    static int cellDivEnv = -1;
+    if (cellDivEnv < 0) { const char* e = getenv("B200PHYS_CELL_DIV"); cellDivEnv = e ? atoi(e) : 0; }     // tuning override
+    const uint32_t cellDiv = cellDivEnv > 0 ? (uint32_t)cellDivEnv : c->cfg.reserved[1];
+    const uint32_t numChunks = (C + kBigChunk - 1) / kBigChunk;
+    static int tilesEnv = -1;
+    if (tilesEnv < 0) { const char* e = getenv("B200PHYS_BP_TILES"); tilesEnv = e ? (atoi(e) ? 1 : 2) : 0; }    // tuning override: 1 always staged tiles, 0 never
+    const uint32_t tilesMode = (uint32_t)tilesEnv;
+    if (C == 0)
     {
-        bpBigCountDeviceKernel<<<1, 32, 0, c->stream>>>(C, cnt);
-        bpBigFlagKernel<<<G, kThreads, 0, c->stream>>>(C, c->aabbMin, c->aabbMax, c->bigList, bigFlags, cnt);
-        c->launches += 2;
-        scanExclusiveU32(c, bigFlags, bigOffs, &cnt->bigMatrixCount, 16u * C, nullptr);
-        bpBigCountKernel<<<1, 32, 0, c->stream>>>(C, c->bigList, bigOffs, c->pairCount, cnt);
-        c->launches += 1;
+        bpPrimeFinishKernel<<<1, 32, 0, c->stream>>>(bigFactor, c->cfg.cellSize, cnt);
+        bpSetupKernel<<<1, 32, 0, c->stream>>>(c->maxCells, bigFactor, c->cfg.cellSize, cellDiv, kWarpCand, tilesMode, cnt);
+        c->launches += 2; c->bpPrimed = false;
+        return;
     }
-    bpBigKernel<false><<<c->numSMs, kThreads, 0, c->stream>>>(C, matrixFits ? 16u : 0u, c->aabbMin, c->aabbMax, c->bigList, c->pairCount, c->pairStart, c->pairs, c->maxPairs, cnt);
+    if (!c->bpPrimed)
+    {   // no threshold from a previous step yet (first step, or colliders were uploaded)
+        bpPrimeFinishKernel<<<1, 32, 0, c->stream>>>(bigFactor, c->cfg.cellSize, cnt);       // clears the accumulators
+        bpPrimeKernel<<<G, kThreads, 0, c->stream>>>(C, c->aabbMin, c->aabbMax, cnt);
+        bpPrimeFinishKernel<<<1, 32, 0, c->stream>>>(bigFactor, c->cfg.cellSize, cnt);
+        c->launches += 3; c->bpPrimed = true;
+    }
+    bpClassifyKernel<<<G, kThreads, 0, c->stream>>>(C, c->aabbMin, c->aabbMax, c->cellOf, c->bigList, cnt);
+    bpSetupKernel<<<1, 32, 0, c->stream>>>(c->maxCells, bigFactor, c->cfg.cellSize, cellDiv, kWarpCand, tilesMode, cnt);
+    bpBinKernel<<<G, kThreads, 0, c->stream>>>(C, c->aabbMin, c->aabbMax, c->cellOf, c->rankInCell, c->cellCount, cnt);
     c->launches += 3;
+    scanExclusiveU32(c, c->cellCount, c->cellStart, &cnt->grid.numCells, c->maxCells, nullptr, /*clearInput*/ true);
+    bpScatterKernel<<<G, kThreads, 0, c->stream>>>(C, c->aabbMin, c->aabbMax, c->cellOf, c->rankInCell, c->cellStart, c->bpRec, c->pairCount);
+    timelineMark(c, "bp_build");
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(bpTileKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileCtaShared)); attr = true; }
+    const uint32_t tileCtas = (uint32_t)c->numSMs * 4u, bigCtas = (uint32_t)c->numSMs;
+    bpTileKernel<<<tileCtas + bigCtas, kTileThreads, sizeof(TileCtaShared), c->stream>>>(C, tileCtas, numChunks, c->bpRec, c->cellStart, c->aabbMin, c->aabbMax, c->bigList,
+                                                                                      c->pairCount, c->bpRows, c->cellOf, c->bpBigChunks, cnt);
+    bpRowsDirectKernel<<<gridFor(c, 6), kDirectThreads, 0, c->stream>>>(C, c->bpRec, c->cellStart, c->aabbMin, c->aabbMax, c->bigList, c->pairCount, c->bpRows, c->cellOf, cnt);
+    c->launches += 3;
+    timelineMark(c, "bp_tiles");
     scanExclusiveU32(c, c->pairCount, c->pairStart, nullptr, C, nullptr);
-    bpQueryKernel<true><<<G, kThreads, 0, c->stream>>>(c->sortedMin, c->sortedMax, c->cellStart, c->aabbMin, c->aabbMax, c->bigList, c->pairCount, c->pairStart, c->pairs, c->maxPairs, cnt);
-    if (matrixFits) { bpBigFillKernel<<<G, kThreads, 0, c->stream>>>(C, c->bigList, bigFlags, bigOffs, c->pairStart, c->pairs, c->maxPairs, cnt); c->launches += 1; }
-    bpBigKernel<true><<<c->numSMs, kThreads, 0, c->stream>>>(C, matrixFits ? 16u : 0u, c->aabbMin, c->aabbMax, c->bigList, c->pairCount, c->pairStart, c->pairs, c->maxPairs, cnt);
-    bpFinishKernel<<<1, 32, 0, c->stream>>>(C, c->pairStart, c->maxPairs, cnt);
-    c->launches += 3;
-    timelineMark(c, "bp_query");
+    const uint32_t emitCtas = (uint32_t)c->numSMs * 6u, extraCtas = (uint32_t)c->numSMs * 2u;
+    bpEmitKernel<<<emitCtas + extraCtas, kThreads, 0, c->stream>>>(C, emitCtas, numChunks, c->rankInCell, c->bpRows, c->pairCount, c->pairStart, c->bpRec, c->cellStart,
+                                                                  c->aabbMin, c->aabbMax, c->bigList, c->cellOf, c->bpBigChunks, c->pairs, c->maxPairs, cnt);
+    c->launches += 1;
+    timelineMark(c, "bp_emit");
 }
 
 } // namespace b200
