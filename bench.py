@@ -290,7 +290,13 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # NCCL prints its version banner on stdout when the first communicator comes up: keep stdout to the one JSON line
+        sys.stdout.flush(); saved = os.dup(1); os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            t = torch.zeros(1, device="cuda"); dist.all_reduce(t); torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush(); os.dup2(saved, 1); os.close(saved)
     W = max(3, args.warmup); K = args.steps
     peak, peak_src = measured_hbm_peak()
     stream = torch.cuda.Stream()          # a real (non-default) stream: every kernel of the context and the timing events share it
