@@ -109,11 +109,11 @@ def mixed_slab(rank, world, dims=MIXED_DIMS):
     return host.build_mixed_slab(nx * world, dims[1], dims[2], nx * rank, nx * (rank + 1), seed=MIXED_SEED, spacing=MIXED_SPACING)
 
 
-def make_stepper(sc, device=0, ghost_cap=0, **kw):
+def make_stepper(sc, device=0, **kw):
     from d3d12renderer_b200 import abi
     nb, nc = len(sc["bodies"]), len(sc["colliders"])
     nj = max([len(j[0]) for j in sc.get("joints", {}).values()] + [1])
-    st = abi.Stepper(max_bodies=nb + 2 * ghost_cap, max_colliders=nc + 2 * ghost_cap, max_transforms=max(4, len(sc["transforms"])), max_joints=nj, device=device, **kw)
+    st = abi.Stepper(max_bodies=nb, max_colliders=nc, max_transforms=max(4, len(sc["transforms"])), max_joints=nj, device=device, **kw)
     if "hull_vertices" in sc:
         st.set_hulls(sc["hull_vertices"], sc["hull_offsets"])
     st.upload_transforms(np.ascontiguousarray(sc["transforms"])); st.upload_colliders(np.ascontiguousarray(sc["colliders"])); st.upload_bodies(np.ascontiguousarray(sc["bodies"]))
@@ -317,32 +317,41 @@ def main():
             t = torch.tensor([x], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.SUM); return float(t.item())
         return x
 
+    nccl_id = [None]
+    if world > 1:
+        nccl_id = [abi.dist_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(nccl_id, src=0)      # the library owns its own NCCL communicator (b200phys_create_distributed)
+
     def sharded(sc, ghost_layers=3.0):
-        """Stepper + slab shard for this rank's part of a slab-decomposed scene."""
+        """Stepper for this rank's part of a slab-decomposed scene; with N > 1 the context is created by b200phys_create_distributed and
+        b200phys_step_distributed exchanges the ghost halo with the slab neighbours (ncclSend / ncclRecv on the context's stream)."""
         n_bodies = len(sc["bodies"])
         per_layer = max(1, n_bodies // max(1, int(round((sc["slab"][1] - sc["slab"][0]) / MIXED_SPACING))))
         ghost_cap = 0 if world == 1 else int(ghost_layers * per_layer)
-        st = make_stepper(sc, device=local_rank, ghost_cap=ghost_cap)
-        st.set_stream(stream.cuda_stream)
         planes = [None] * world
         if world > 1:
             dist.all_gather_object(planes, sc["slab"])
         else:
             planes = [sc["slab"]]
         bounds = np.array([-parallel.BIG] + [0.5 * (planes[r][1] + planes[r + 1][0]) for r in range(world - 1)] + [parallel.BIG])
-        shard = parallel.SlabShard(st, rank, world, bounds, axis=0, ghost_width=1.05, max_ghost_bodies=max(1, ghost_cap), max_ghost_colliders=max(1, ghost_cap),
-                                   device=torch.device("cuda", local_rank))
-        return st, shard
+        dc = None
+        if world > 1:
+            dc = abi.DistConfig(); dc.rank = rank; dc.nranks = world; dc.axis = 0; dc.slabLo = float(bounds[rank]); dc.slabHi = float(bounds[rank + 1]); dc.ghostWidth = 1.05
+            dc.maxGhostBodies = ghost_cap; dc.maxGhostColliders = ghost_cap
+        st = make_stepper(sc, device=local_rank, dist=(dc, nccl_id[0]) if dc is not None else None)
+        st.set_stream(stream.cuda_stream)
+        return st
 
     # ================================================================ headline: mixed pile, 1 048 576 bodies per GPU (weak scaling)
     sc = mixed_slab(rank, world)
     n_bodies = len(sc["bodies"]); n_col = len(sc["colliders"])
-    st, shard = sharded(sc)
+    st = sharded(sc)
 
     def do_step(flags=abi.STEP_FAST):
         if world > 1:
-            shard.refresh_ghosts()      # pack (device) -> one batched NCCL send/recv of fixed-size messages with the slab neighbours -> unpack (device); no host sync
-        st.step(DT, ITERATIONS, flags)
+            st.step_distributed(DT, ITERATIONS, flags)      # pack (device) -> ncclSend / ncclRecv of fixed-size messages with the slab neighbours -> unpack (device) -> step; no host sync
+        else:
+            st.step(DT, ITERATIONS, flags)
 
     for _ in range(W):
         do_step()
@@ -380,7 +389,7 @@ def main():
     barrier()
     ms_e2e = max_over_ranks((time.perf_counter() - t0) * 1e3) / K2
     checksum = float(np.sum(hs["position"][:, 1].astype(np.float64)))
-    ghosts = shard.ghost_counts()[0] if world > 1 else 0
+    ghosts = st.dist_ghost_counts()[0] if world > 1 else 0
     st.close(); host_states.free(); host_forces.free()
 
     total_bodies = n_bodies * world
@@ -392,10 +401,10 @@ def main():
     if world > 1 and not args.no_side_configs:
         nx = MIXED_DIMS[0] // world
         sc2 = host.build_mixed_slab(MIXED_DIMS[0], MIXED_DIMS[1], MIXED_DIMS[2], nx * rank, nx * (rank + 1), seed=MIXED_SEED, spacing=MIXED_SPACING)
-        st2, shard2 = sharded(sc2)
+        st2 = sharded(sc2)
 
         def step2():
-            shard2.refresh_ghosts(); st2.step(DT, ITERATIONS, abi.STEP_FAST)
+            st2.step_distributed(DT, ITERATIONS, abi.STEP_FAST)
         ms2 = max_over_ranks(time_steps(step2, barrier, stream, W, K))
         st2.close()
         strong = {"workload": "ONE 1048576-body mixed pile (128 x 64 x 128) slab-decomposed over %d GPUs (fixed total: strong scaling)" % world, "bodies": MIXED_DIMS[0] * MIXED_DIMS[1] * MIXED_DIMS[2],
@@ -438,7 +447,7 @@ def main():
                                    % (MIXED_DIMS[0] * world, world),
                        "bodies": total_bodies, "bodies_per_gpu": n_bodies, "iterations": ITERATIONS, "contacts_per_gpu": counts["contacts"], "pairs_per_gpu": counts["pairs"], "manifolds_per_gpu": counts["manifolds"],
                        "steps_per_s": K / (ms_dev * 1e-3), "ms_per_step_exact_order": ms_exact,
-                       "parallelism": ("slab decomposition along x, %d slabs, ghost-body halo over NCCL (%d ghost bodies on rank 0)" % (world, ghosts)) if world > 1 else "single GPU",
+                       "parallelism": ("slab decomposition along x, %d slabs, ghost-body halo: ncclSend / ncclRecv inside the C library (%d ghost bodies on rank 0)" % (world, ghosts)) if world > 1 else "single GPU",
                        "l2_policy": "per-step working set (rows, pair and manifold scratch, body planes: > 1 GB) >> 126 MB L2; no explicit flush",
                        "state_checksum_y": checksum, "overflow": overflow},
             "e2e": {"value": e2e_value, "unit": "body-steps/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(n_bodies * (abi.body_state_dtype.itemsize + 24)),

@@ -59,6 +59,11 @@ class Config(C.Structure):
                 ("cellSize", C.c_float), ("bigFactor", C.c_float), ("maxContacts", C.c_uint32), ("reserved", C.c_uint32 * 5)]
 
 
+class DistConfig(C.Structure):
+    _fields_ = [("rank", C.c_int32), ("nranks", C.c_int32), ("axis", C.c_int32), ("slabLo", C.c_float), ("slabHi", C.c_float), ("ghostWidth", C.c_float),
+                ("maxGhostBodies", C.c_uint32), ("maxGhostColliders", C.c_uint32)]
+
+
 class Stats(C.Structure):
     _fields_ = [("numBodies", C.c_uint32), ("numColliders", C.c_uint32), ("numBroadphaseOverlaps", C.c_uint32), ("numCollisions", C.c_uint32),
                 ("numContacts", C.c_uint32), ("numBigColliders", C.c_uint32), ("numGridCells", C.c_uint32), ("numColors", C.c_uint32 * 7),
@@ -82,11 +87,19 @@ EXPORTS = [
     "b200phys_set_hulls", "b200phys_upload_bodies", "b200phys_upload_transforms", "b200phys_upload_colliders", "b200phys_upload_joints",
     "b200phys_upload_forces", "b200phys_upload_body_states", "b200phys_step", "b200phys_synchronize", "b200phys_download_bodies", "b200phys_get_stats",
     "b200phys_download_aabbs", "b200phys_download_pairs", "b200phys_download_contacts", "b200phys_download_collisions",
-    "b200phys_download_solve_order", "b200phys_get_timeline", "b200phys_halo_pack", "b200phys_halo_unpack", "b200phys_halo_clear", "b200phys_halo_record_bytes",
+    "b200phys_download_solve_order", "b200phys_get_timeline", "b200phys_dist_unique_id", "b200phys_create_distributed", "b200phys_step_distributed", "b200phys_dist_ghost_counts", "b200phys_halo_pack", "b200phys_halo_unpack", "b200phys_halo_clear", "b200phys_halo_record_bytes",
     "b200phys_halo_message_bytes", "b200phys_halo_pack_message", "b200phys_halo_unpack_message", "b200phys_migrate_pack", "b200phys_migrate_unpack", "b200phys_enable_events", "b200phys_download_events", "b200phys_upload_force_fields", "b200phys_set_global_force_field", "b200phys_download_trigger_events",
 ]
 
 _lib = None
+
+
+def dist_unique_id():
+    """128-byte NCCL id from rank 0 (b200phys_dist_unique_id); hand it to every rank's Stepper(dist=...)."""
+    lib = load_library()
+    buf = (C.c_uint8 * 128)()
+    _check(lib, lib.b200phys_dist_unique_id(buf), "b200phys_dist_unique_id")
+    return bytes(buf)
 
 
 def load_library():
@@ -118,6 +131,10 @@ def load_library():
     lib.b200phys_download_bodies.argtypes = [vp, vp, u32]
     lib.b200phys_get_stats.argtypes = [vp, C.POINTER(Stats)]
     lib.b200phys_get_timeline.argtypes = [vp, vp, u32, vp, u32, C.POINTER(u32)]
+    lib.b200phys_dist_unique_id.argtypes = [vp]
+    lib.b200phys_create_distributed.argtypes = [C.POINTER(Config), C.POINTER(DistConfig), vp, C.POINTER(vp)]
+    lib.b200phys_step_distributed.argtypes = [vp, f32, u32, u32]
+    lib.b200phys_dist_ghost_counts.argtypes = [vp, C.POINTER(u32), C.POINTER(u32)]
     lib.b200phys_download_aabbs.argtypes = [vp, vp, C.POINTER(u32)]
     lib.b200phys_download_pairs.argtypes = [vp, vp, C.POINTER(u32)]
     lib.b200phys_download_contacts.argtypes = [vp, vp, vp, C.POINTER(u32)]
@@ -177,14 +194,19 @@ class Stepper:
     """Thin object wrapper over one b200phys_context (one per GPU / rank)."""
 
     def __init__(self, max_bodies, max_colliders, max_transforms=16, device=0, max_pairs=0, max_manifolds=0, max_contacts=0,
-                 max_joints=0, max_grid_cells=0, cell_size=0.0, big_factor=0.0):
+                 max_joints=0, max_grid_cells=0, cell_size=0.0, big_factor=0.0, dist=None):
         self.lib = load_library()
         cfg = Config()
         cfg.device = device; cfg.maxBodies = max_bodies; cfg.maxColliders = max_colliders; cfg.maxTransforms = max_transforms
         cfg.maxPairs = max_pairs; cfg.maxManifolds = max_manifolds; cfg.maxContacts = max_contacts; cfg.maxJointsPerKind = max_joints
         cfg.maxGridCells = max_grid_cells; cfg.cellSize = cell_size; cfg.bigFactor = big_factor
         self.ctx = C.c_void_p()
-        _check(self.lib, self.lib.b200phys_create(C.byref(cfg), C.byref(self.ctx)), "b200phys_create")
+        if dist is None:
+            _check(self.lib, self.lib.b200phys_create(C.byref(cfg), C.byref(self.ctx)), "b200phys_create")
+        else:       # dist = (DistConfig, 128-byte NCCL id): the library owns the NCCL communicator and the halo exchange (k_dist.cu)
+            dc, uid = dist
+            buf = (C.c_uint8 * 128).from_buffer_copy(bytes(uid))
+            _check(self.lib, self.lib.b200phys_create_distributed(C.byref(cfg), C.byref(dc), buf, C.byref(self.ctx)), "b200phys_create_distributed")
         self.num_bodies = 0
 
     def close(self):
@@ -235,6 +257,15 @@ class Stepper:
 
     def step(self, dt, iterations, flags=STEP_FAST):
         _check(self.lib, self.lib.b200phys_step(self.ctx, dt, iterations, flags), "step")
+
+    def step_distributed(self, dt, iterations, flags=STEP_FAST):
+        """Ghost exchange with the slab neighbours (NCCL inside the library) + the step."""
+        _check(self.lib, self.lib.b200phys_step_distributed(self.ctx, dt, iterations, flags), "step_distributed")
+
+    def dist_ghost_counts(self):
+        b, c = C.c_uint32(0), C.c_uint32(0)
+        _check(self.lib, self.lib.b200phys_dist_ghost_counts(self.ctx, C.byref(b), C.byref(c)), "dist_ghost_counts")
+        return b.value, c.value
 
     def synchronize(self):
         _check(self.lib, self.lib.b200phys_synchronize(self.ctx), "synchronize")

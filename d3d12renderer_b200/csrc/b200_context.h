@@ -195,6 +195,7 @@ struct Context
     uint32_t maxPairs = 0, maxManifolds = 0, maxContacts = 0, maxJoints = 0, maxCells = 0;
 
     // halo (multi-GPU)
+    void* dist = nullptr;               // NCCL communicator + slab + message buffers of a context made by b200phys_create_distributed (k_dist.cu)
     uint8_t* haloBuf = nullptr; uint32_t haloCap = 0;
     uint32_t numGhostBodies = 0, numGhostColliders = 0;
 };
@@ -209,6 +210,8 @@ static inline void timelineMark(Context* c, const char* name)
 
 // launch geometry shared by every grid-stride kernel: a multiple of the SM count (148 on B200)
 static inline int gridFor(const Context* c, int blocksPerSM = 8) { return c->numSMs * blocksPerSM; }
+
+void destroyDist(Context* c);   // k_dist.cu
 
 // ---- stage launchers (one per .cu file) ------------------------------------------------------------------------
 void launchUnpackBodies(Context* c, const void* devStaging, uint32_t count);

@@ -169,6 +169,7 @@ int b200phys_destroy(b200phys_context* ctx)
     if (!ctx) return B200PHYS_E_INVALID;
     cudaSetDevice(ctx->c.device);
     cudaDeviceSynchronize();
+    destroyDist(&ctx->c);
     freeAll(ctx->c);
     delete ctx;
     return 0;

@@ -310,6 +310,23 @@ int b200phys_migrate_pack(b200phys_context* ctx, int axis, float lo, float hi, v
 int b200phys_migrate_unpack(b200phys_context* ctx, const void* srcMessageDev, uint32_t capBodies, uint32_t capColliders, uint32_t* outCounts);
 int b200phys_halo_clear(b200phys_context* ctx);
 
+/* Multi-GPU with the transport inside the library (what a C++ host uses; SURVEY 8b `_create_distributed`): one process / thread and one
+ * context per GPU, bodies sharded by slab along `axis`, this rank owning [slabLo, slabHi); ranks are ordered along the axis (rank r's
+ * upper neighbour is r + 1). The ghost halo is exchanged with ncclSend / ncclRecv on the context's stream inside b200phys_step_distributed.
+ * Rank 0 obtains the 128-byte NCCL id with b200phys_dist_unique_id and the host hands it to every rank (MPI_Bcast, a file, a socket).
+ * NCCL (libnccl.so.2) is loaded at run time; without it these calls return B200PHYS_E_NOT_READY. */
+typedef struct b200phys_dist_config {
+    int32_t  rank, nranks;
+    int32_t  axis;                          /* 0 x, 1 y, 2 z */
+    float    slabLo, slabHi;                /* -3e38 / +3e38 on the outermost ranks */
+    float    ghostWidth;                    /* >= the largest collider extent (+ the distance a body travels between two migrations) */
+    uint32_t maxGhostBodies, maxGhostColliders;   /* per neighbour; maxBodies / maxColliders of the config count the OWNED ones */
+} b200phys_dist_config;
+int b200phys_dist_unique_id(uint8_t* out128);
+int b200phys_create_distributed(const b200phys_config* config, const b200phys_dist_config* dist, const uint8_t* uniqueId128, b200phys_context** out);
+int b200phys_step_distributed(b200phys_context* ctx, float dt, uint32_t numSolverIterations, uint32_t flags);
+int b200phys_dist_ghost_counts(b200phys_context* ctx, uint32_t* outBodies, uint32_t* outColliders);
+
 #ifdef __cplusplus
 }
 #endif

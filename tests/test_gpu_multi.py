@@ -44,3 +44,10 @@ def test_slab_sharding_pair_set_identical_and_states_within_order_noise():
 def test_migration_hands_bodies_over_consistently():
     rc, out = _run("mgpu_migrate_check.py", 29521)
     assert rc == 0 and "MGPU_MIGRATE_CHECK PASS" in out, out[-3000:]
+
+
+@pytest.mark.skipif(_gpus() < 2, reason="needs 2 GPUs on one box")
+def test_library_owned_nccl_transport_matches_python_driven_halo():
+    """b200phys_create_distributed / b200phys_step_distributed (NCCL inside the C library) give bit-identical states to the Python-driven halo."""
+    rc, out = _run("mgpu_cabi_check.py", 29531)
+    assert rc == 0 and "MGPU_CABI_CHECK PASS" in out, out[-3000:]
