@@ -144,7 +144,7 @@ def rooflines(kernels, counts, n_bodies, n_colliders, n_joints, peak):
     P, K = counts["pairs"], counts["contacts"]
     model = {
         "broad_phase": (n_colliders * B_GRID + P * B_PAIR_OUT, ["bp_build", "bp_tiles", "bp_emit"]),
-        "narrow_phase": (P * B_PAIR_NARROW + K * B_CONTACT_OUT, ["np_classify_sort", "np_closed_form_sat", "np_gjk", "np_epa", "np_compact"]),
+        "narrow_phase": (P * B_PAIR_NARROW + K * B_CONTACT_OUT, ["np_classify_sort", "np_closed_form_sat", "np_gjk", "np_epa", "np_epa_redo", "np_compact"]),
         "solver_rows": (K * B_KINIT, ["solver_rows"]),
         "solve": (K * ITERATIONS * B_KITER + n_joints * ITERATIONS * B_JITER, ["solve"]),
         "bodies": (n_bodies * B_BODY, ["world_colliders", "integrate_forces", "integrate_velocities"]),
@@ -432,7 +432,7 @@ def main():
     if rank == 0:
         dom = max(kernels, key=lambda k: kernels[k])
         group_of = {"bp_build": "broad_phase", "bp_tiles": "broad_phase", "bp_emit": "broad_phase", "np_classify_sort": "narrow_phase", "np_closed_form_sat": "narrow_phase", "np_gjk": "narrow_phase",
-                    "np_epa": "narrow_phase", "np_compact": "narrow_phase", "solver_rows": "solver_rows", "solver_order": "solver_rows", "solve": "solve"}
+                    "np_epa": "narrow_phase", "np_epa_redo": "narrow_phase", "np_compact": "narrow_phase", "solver_rows": "solver_rows", "solver_order": "solver_rows", "solve": "solve"}
         # per-kernel algorithmic bytes for the dominant kernel group (same model, split by what that kernel touches)
         P, Kc = counts["pairs"], counts["contacts"]
         dom_bytes = {"solve": Kc * ITERATIONS * B_KITER, "bp_tiles": n_col * (24.0 + 128.0), "bp_emit": n_col * 128.0 + P * B_PAIR_OUT, "bp_build": n_col * (B_GRID - 24.0), "solver_rows": Kc * B_KINIT,

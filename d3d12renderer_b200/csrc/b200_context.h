@@ -37,7 +37,10 @@ struct GridParams
 struct DeviceCounts
 {
     uint32_t numEpaWork;                // GJK hits waiting for EPA this step
-    uint32_t epaWorkHead;               // next work-list entry to hand out (warp-cooperative EPA kernel)
+    uint32_t epaWorkHead;               // next work-list entry to hand out (EPA kernels with dynamic distribution)
+    uint32_t numEpaRedo;                // entries the small-polytope EPA kernel handed to the large-capacity one
+    uint32_t epaRedoHead;               // next redo entry to hand out
+    uint32_t gjkCursor[11];             // per GJK bucket: next pair to hand out (npGjkKernel)
     uint32_t numPairs;                  // broad-phase overlaps (clamped to capacity)
     uint32_t numPairsWanted;            // what the scan produced (overflow detection)
     uint32_t keyStart[kNumPairKeys + 1];// bucket ranges of the classified pair list
@@ -132,6 +135,7 @@ struct Context
     uint2* pairsSorted = nullptr;     // bucketed, stable
     float4* epaSimplex = nullptr;     // 9 planes x maxEpaWork: GJK terminal simplices parked for the EPA kernel
     uint2* epaWork = nullptr;         // (sorted pair slot, bucket)
+    uint32_t* epaRedo = nullptr;      // work-list entries that outgrew the small polytope
     uint32_t maxEpaWork = 0;
     float4* manTmp = nullptr;         // 5 planes x maxPairs: (normal, count), 4 x (point, depth)
     unsigned long long* manScan = nullptr; // per pair (contacts << 32 | collided) and its exclusive scan

@@ -142,60 +142,151 @@ __global__ void __launch_bounds__(CLASS == 0 ? 256 : 128) npCollideKernel(const 
     flushCounters(nc, cnt);
 }
 
-// GJK/EPA-based buckets (5,8,9,10,11,12,13,14,17,19,20), shared by both phases
-template <class NC>
-B200_D bool collideGjkBucket(uint32_t bucket, const ColRec& A, const ColRec& B, const float4* __restrict__ hullVerts, const uint32_t* __restrict__ hullOffsets, Man& m, NC& nc)
+// GJK/EPA-based buckets (5,8,9,10,11,12,13,14,17,19,20). gjkPrep = the routine up to gjkIntersectionTest: 0 no contact, 1 manifold
+// complete (cylinder-cylinder with parallel axes), 2 job ready.
+B200_D int gjkPrep(uint32_t bucket, const ColRec& A, const ColRec& B, const float4* __restrict__ hullVerts, const uint32_t* __restrict__ hullOffsets, Man& m, NarrowCounters& nc, GjkJob& job)
 {
     switch (bucket)
     {
-    case 8:  return segmentShapeBox(asCap(A), false, asBox(B), m, nc);
-    case 9:  return segmentShapeObb(asCap(A), false, asObb(B), m, nc);
-    case 11: return cylinderCylinder(asCap(A), asCap(B), m, nc);
-    case 12: return segmentShapeBox(asCap(A), true, asBox(B), m, nc);
-    case 13: return segmentShapeObb(asCap(A), true, asObb(B), m, nc);
+    case 8:  segmentShapeBoxPre(asCap(A), false, asBox(B), job); return 2;
+    case 9:  segmentShapeObbPre(asCap(A), false, asObb(B), job); return 2;
+    case 11: return cylinderCylinderPre(asCap(A), asCap(B), m, nc, job);
+    case 12: segmentShapeBoxPre(asCap(A), true, asBox(B), job); return 2;
+    case 13: segmentShapeObbPre(asCap(A), true, asObb(B), job); return 2;
     default:
     {   // anything vs hull: 5 sphere, 10 capsule, 14 cylinder, 17 aabb, 19 obb, 20 hull (:496-520,792-818,1045-1071,1150-1176,1529-1584)
         const uint32_t ta = __float_as_uint(A.r3.x) & 0xFFu;
-        return gjkEpa(supportFor(ta, A, hullVerts, hullOffsets), supHull(asHull(B, hullVerts, hullOffsets)), m, nc);
+        job.A = supportFor(ta, A, hullVerts, hullOffsets); job.B = supHull(asHull(B, hullVerts, hullOffsets)); job.tail = 0;
+        return 2;
     }
     }
 }
+// the whole routine for one pair in the phase NC stands for (one thread, or one warp in phase 3)
+template <class NC>
+B200_D bool collideGjkBucket(uint32_t bucket, const ColRec& A, const ColRec& B, const float4* __restrict__ hullVerts, const uint32_t* __restrict__ hullOffsets, Man& m, NC& nc)
+{
+    GjkJob job;
+    const int st = gjkPrep(bucket, A, B, hullVerts, hullOffsets, m, nc, job);
+    if (st != 2) return st == 1;
+    if (!gjkEpa(job.A, job.B, m, nc)) return false;
+    gjkTail(job, m);
+    return true;
+}
 
-// phase 1: GJK for every pair of the GJK buckets; misses (and the closed-form exits of cylinder-cylinder) are final, hits are
-// parked with their simplex in the EPA work list
+// Work distribution of the lane-refill kernels below: a warp owns a private range [next, end) of a global cursor and takes a new
+// chunk when it runs dry; idle lanes take consecutive items of the range. Returns this lane's item or 0xFFFFFFFF (none this pass).
+struct WarpRange
+{
+    uint32_t next = 0, end = 0; bool dry = false;       // warp-uniform
+    B200_D uint32_t take(bool want, uint32_t* cursor, uint32_t total, uint32_t chunk)
+    {
+        const uint32_t lane = threadIdx.x & 31u;
+        const uint32_t mask = __ballot_sync(0xffffffffu, want);
+        if (!mask) return 0xFFFFFFFFu;
+        if (next >= end && !dry)
+        {
+            uint32_t base = 0;
+            if (lane == 0u) base = atomicAdd(cursor, chunk);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (base >= total) { dry = true; next = end = total; }
+            else { next = base; end = min(base + chunk, total); }
+        }
+        const uint32_t rank = (uint32_t)__popc(mask & ((1u << lane) - 1u));
+        const uint32_t avail = end - next, n = min((uint32_t)__popc(mask), avail);
+        const uint32_t item = (want && rank < avail) ? next + rank : 0xFFFFFFFFu;
+        next += n;
+        return item;
+    }
+};
+
+// phase 1: GJK (collision_gjk.h:184-238) for every pair of the GJK buckets. Misses (and the closed-form exits of cylinder-cylinder) are
+// final; hits are parked with their terminal simplex in the EPA work list. Most pairs leave after one or two support evaluations and
+// the rest take 3-10 rounds, so the lanes of a warp are NOT tied to one pair each for a whole test: the loop below performs one
+// support evaluation per pass for every lane and a lane whose pair is decided takes the next pair of the bucket at once.
 __global__ void __launch_bounds__(128) npGjkKernel(const uint2* __restrict__ sorted, const float4* __restrict__ wCol, const float4* __restrict__ hullVerts,
     const uint32_t* __restrict__ hullOffsets, float4* __restrict__ manTmp, unsigned long long* __restrict__ manScan, uint32_t maxPairs,
     float4* __restrict__ sxPlanes, uint2* __restrict__ epaWork, uint32_t sxCap, DeviceCounts* cnt)
 {
     constexpr uint32_t list2[11] = { 5, 8, 9, 10, 11, 12, 13, 14, 17, 19, 20 };
-    NarrowCtx<1> nc; nc.epaOverflow = nc.gjkCap = nc.asserts = 0; nc.sxPlanes = sxPlanes; nc.sxCap = sxCap; nc.sxCounter = &cnt->numEpaWork;
+    NarrowCounters nc; nc.epaOverflow = nc.gjkCap = nc.asserts = 0;
+    const uint32_t lane = threadIdx.x & 31u;
     for (int li = 0; li < 11; ++li)
     {
         const uint32_t bucket = list2[li];
-        const uint32_t q0 = cnt->keyStart[bucket], q1 = cnt->keyStart[bucket + 1];
-        for (uint32_t q = q0 + blockIdx.x * blockDim.x + threadIdx.x; q < q1; q += gridDim.x * blockDim.x)
+        const uint32_t q0 = cnt->keyStart[bucket], total = cnt->keyStart[bucket + 1] - q0;
+        if (!total) continue;
+        WarpRange range;
+        bool busy = false; uint32_t q = 0; int stage = 0, round = 0;
+        GjkJob job; SimplexD s; f3 dir = mk3(0.f);
+        for (;;)
         {
-            const uint2 pr = sorted[q];
-            const ColRec A = loadCol(wCol, pr.x), B = loadCol(wCol, pr.y);
-            Man m; m.cnt = 0;
-            nc.deferred = false;
-            const bool hit = collideGjkBucket(bucket, A, B, hullVerts, hullOffsets, m, nc);
-            storeManifold(manTmp, manScan, q, maxPairs, hit, m);
-            if (nc.deferred) { if (nc.sxEntry < sxCap) epaWork[nc.sxEntry] = make_uint2(q, bucket); else cnt->overflowManifolds = 1; }
+            const uint32_t item = range.take(!busy, &cnt->gjkCursor[li], total, 128u);
+            if (item != 0xFFFFFFFFu)
+            {
+                q = q0 + item;
+                const uint2 pr = sorted[q];
+                const ColRec A = loadCol(wCol, pr.x), B = loadCol(wCol, pr.y);
+                Man m; m.cnt = 0;
+                const int st = gjkPrep(bucket, A, B, hullVerts, hullOffsets, m, nc, job);
+                if (st != 2) storeManifold(manTmp, manScan, q, maxPairs, st == 1, m);
+                else { busy = true; stage = 0; dir = mk3(1.f, 0.1f, -0.2f); }        // collision_gjk.h:190
+            }
+            if (!__any_sync(0xffffffffu, busy)) { if (range.dry) break; else continue; }
+            if (busy)
+            {
+                bool done = false, hit = false;
+                if (stage == 2)
+                {
+                    if (round >= B200_GJK_MAX_ROUNDS) { ++nc.gjkCap; done = true; }
+                    else if (sqLen(dir) < 0.0001f) done = true;
+                }
+                if (!done)
+                {
+                    const SupPt a = minkowski(job.A, job.B, dir);
+                    if (dot(a.m, dir) < 0.f) done = true;
+                    else if (stage == 0) { s.c = a; dir = -a.m; stage = 1; }
+                    else if (stage == 1) { s.b = a; dir = crossABA(s.c.m - s.b.m, -s.b.m); s.n = 2; stage = 2; round = 0; }
+                    else
+                    {
+                        const int r = updateSimplex(s, a, dir);
+                        if (r == B200_GJK_STOP) { s.a = a; s.n = 4; done = hit = true; }
+                        else if (r == B200_GJK_ERROR) done = true;
+                        else ++round;
+                    }
+                }
+                if (done)
+                {
+                    if (hit)
+                    {   // warp-aggregated append to the EPA work list
+                        const uint32_t mask = __activemask();
+                        const uint32_t leader = (uint32_t)__ffs((int)mask) - 1u;
+                        uint32_t base = 0;
+                        if (lane == leader) base = atomicAdd(&cnt->numEpaWork, (uint32_t)__popc(mask));
+                        base = __shfl_sync(mask, base, (int)leader);
+                        const uint32_t e = base + (uint32_t)__popc(mask & ((1u << lane) - 1u));
+                        if (e < sxCap) { storeSimplex(sxPlanes, sxCap, e, s); epaWork[e] = make_uint2(q, bucket); }
+                        else cnt->overflowManifolds = 1;
+                    }
+                    manScan[q] = 0ull;            // no manifold (yet)
+                    busy = false;
+                }
+            }
         }
     }
     flushCounters(nc, cnt);
 }
 
-// phase 2: EPA (and the routine's tail: clipping, transform back) for the parked pairs -- every lane has work
+// phase 2: EPA (and the routine's tail: clipping, transform back) for the parked pairs in the large thread-local polytope.
+// redo == nullptr: the whole work list; else only the entries the small-polytope kernel handed back
 __global__ void __launch_bounds__(128) npEpaKernel(const uint2* __restrict__ sorted, const float4* __restrict__ wCol, const float4* __restrict__ hullVerts,
     const uint32_t* __restrict__ hullOffsets, float4* __restrict__ manTmp, unsigned long long* __restrict__ manScan, uint32_t maxPairs,
-    float4* __restrict__ sxPlanes, const uint2* __restrict__ epaWork, uint32_t sxCap, DeviceCounts* cnt)
+    float4* __restrict__ sxPlanes, const uint2* __restrict__ epaWork, uint32_t sxCap, DeviceCounts* cnt, const uint32_t* __restrict__ redo)
 {
     NarrowCtx<2> nc; nc.epaOverflow = nc.gjkCap = nc.asserts = 0; nc.sxPlanes = sxPlanes; nc.sxCap = sxCap; nc.sxCounter = nullptr; nc.deferred = false;
-    const uint32_t n = min(cnt->numEpaWork, sxCap);
-    for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x)
+    const uint32_t n = redo ? min(cnt->numEpaRedo, sxCap) : min(cnt->numEpaWork, sxCap);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
     {
+        const uint32_t e = redo ? redo[i] : i;
         const uint2 w = epaWork[e];
         const uint2 pr = sorted[w.x];
         const ColRec A = loadCol(wCol, pr.x), B = loadCol(wCol, pr.y);
@@ -207,23 +298,87 @@ __global__ void __launch_bounds__(128) npEpaKernel(const uint2* __restrict__ sor
     flushCounters(nc, cnt);
 }
 
+// phase 2, small polytope in shared memory (k_narrow_shapes.cuh, EpaSmall): thread per pair, 6 warps per SM. Runs take 0..20
+// expansions (most 1-4), so like the GJK kernel the loop performs ONE expansion per pass for every lane and a finished lane takes the
+// next work list entry at once. The few pairs that outgrow the small polytope go to the redo list (large polytope kernels).
+static const int kEpaSmallWarps = 6;
+__global__ void __launch_bounds__(kEpaSmallWarps * 32, 1) npEpaSmallKernel(const uint2* __restrict__ sorted, const float4* __restrict__ wCol, const float4* __restrict__ hullVerts,
+    const uint32_t* __restrict__ hullOffsets, float4* __restrict__ manTmp, unsigned long long* __restrict__ manScan, uint32_t maxPairs,
+    float4* __restrict__ sxPlanes, const uint2* __restrict__ epaWork, uint32_t sxCap, DeviceCounts* cnt, uint32_t* __restrict__ redo)
+{
+    extern __shared__ uint32_t epaColumns[];
+    const uint32_t lane = threadIdx.x & 31u;
+    NarrowCounters nc; nc.epaOverflow = nc.gjkCap = nc.asserts = 0;
+    EpaSmall P; P.w = epaColumns + (size_t)(threadIdx.x >> 5) * (B200_EPAS_WORDS * 32) + lane; P.active = 0; P.nT = P.nP = P.nE = 0;
+    const uint32_t total = min(cnt->numEpaWork, sxCap);
+    WarpRange range;
+    bool busy = false; uint32_t e = 0, q = 0, it = 0; GjkJob job;
+    for (;;)
+    {
+        const uint32_t item = range.take(!busy, &cnt->epaWorkHead, total, 64u);
+        if (item != 0xFFFFFFFFu)
+        {
+            e = item;
+            const uint2 w = epaWork[e];
+            q = w.x;
+            const uint2 pr = sorted[q];
+            const ColRec A = loadCol(wCol, pr.x), B = loadCol(wCol, pr.y);
+            Man m; m.cnt = 0;
+            if (gjkPrep(w.y, A, B, hullVerts, hullOffsets, m, nc, job) == 2)      // always: the pair was parked by the GJK kernel
+            {
+                SimplexD g; loadSimplex(sxPlanes, sxCap, e, g);
+                P.init(g);
+                busy = true; it = 0;
+            }
+        }
+        if (!__any_sync(0xffffffffu, busy)) { if (range.dry) break; else continue; }
+        if (busy)
+        {   // one pass of the loop of collision_epa.h:118-146
+            bool done = false, over = false;
+            uint32_t ci = P.closest();
+            if (ci == 0xFFFFFFFFu) { ++nc.asserts; ci = 0; done = true; }
+            else
+            {
+                const uint32_t k = EpaSmall::kTri + 6 * ci;
+                const f3 tn = mk3(P.ldf(k), P.ldf(k + 1), P.ldf(k + 2));
+                const SupPt a = minkowski(job.A, job.B, tn);
+                if (dot(a.m, tn) - P.ldf(k + 3) < 0.01f) done = true;
+                else if (!P.addPoint(a)) over = true;
+                else if (++it == 20u) done = true;
+            }
+            if (done)
+            {
+                Man m; f3 p;
+                P.result(ci, p, m.n, m.d[0]); m.p[0] = p; m.cnt = 1;
+                gjkTail(job, m);
+                storeManifold(manTmp, manScan, q, maxPairs, true, m);
+                busy = false;
+            }
+            else if (over) { redo[atomicAdd(&cnt->numEpaRedo, 1u)] = e; busy = false; }
+        }
+    }
+    flushCounters(nc, cnt);
+}
+
 // phase 2, warp-cooperative: one warp per parked pair, polytope in shared memory (k_narrow_shapes.cuh, EpaWarp). All lanes run the
 // routine's scalar parts uniformly (same loads: broadcast), the EPA loops are split across the lanes; lane 0 writes the manifold.
 static const int kEpaWarpsPerCta = 4;
 __global__ void __launch_bounds__(kEpaWarpsPerCta * 32) npEpaWarpKernel(const uint2* __restrict__ sorted, const float4* __restrict__ wCol, const float4* __restrict__ hullVerts,
     const uint32_t* __restrict__ hullOffsets, float4* __restrict__ manTmp, unsigned long long* __restrict__ manScan, uint32_t maxPairs,
-    float4* __restrict__ sxPlanes, const uint2* __restrict__ epaWork, uint32_t sxCap, DeviceCounts* cnt)
+    float4* __restrict__ sxPlanes, const uint2* __restrict__ epaWork, uint32_t sxCap, DeviceCounts* cnt, const uint32_t* __restrict__ redo)
 {
     extern __shared__ __align__(16) unsigned char epaSmem[];
     EpaWarpShared* sh = reinterpret_cast<EpaWarpShared*>(epaSmem) + (threadIdx.x >> 5);
     NarrowCtx<3> nc; nc.epaOverflow = nc.gjkCap = nc.asserts = 0; nc.sxPlanes = sxPlanes; nc.sxCap = sxCap; nc.sxCounter = nullptr; nc.deferred = false; nc.epaShared = sh;
-    const uint32_t n = min(cnt->numEpaWork, sxCap);
+    // redo == nullptr: the whole work list; else only the entries the small-polytope kernel handed back
+    const uint32_t n = redo ? min(cnt->numEpaRedo, sxCap) : min(cnt->numEpaWork, sxCap);
     for (;;)
     {   // pairs take 1..20 expansions: hand the work list out dynamically, one entry per warp at a time
         uint32_t e = 0;
-        if ((threadIdx.x & 31u) == 0u) e = atomicAdd(&cnt->epaWorkHead, 1u);
+        if ((threadIdx.x & 31u) == 0u) e = atomicAdd(redo ? &cnt->epaRedoHead : &cnt->epaWorkHead, 1u);
         e = __shfl_sync(0xffffffffu, e, 0);
         if (e >= n) break;
+        if (redo) e = redo[e];
         const uint2 w = epaWork[e];
         const uint2 pr = sorted[w.x];
         const ColRec A = loadCol(wCol, pr.x), B = loadCol(wCol, pr.y);
@@ -375,21 +530,44 @@ void launchNarrowphase(Context* c)
     timelineMark(c, "np_closed_form_sat");
     npGjkKernel<<<gridFor(c, 8), 128, 0, c->stream>>>(c->pairsSorted, c->wCol, c->hullVerts, c->hullOffsets, c->manTmp, c->manScan, c->maxPairs, c->epaSimplex, c->epaWork, c->maxEpaWork, cnt);
     timelineMark(c, "np_gjk");
+    static int epaMode = -1, epaBps = 0;
     {
-        static int epaMode = -1, epaBps = 0;       // B200PHYS_EPA=warp selects the warp-cooperative kernel (measured slower); B200PHYS_EPA_BPS = resident CTAs per SM (tuning)
-        if (epaMode < 0) { const char* e = getenv("B200PHYS_EPA"); epaMode = (e && e[0] == 'w') ? 1 : 0; const char* b = getenv("B200PHYS_EPA_BPS"); epaBps = b ? atoi(b) : 0; }
-        if (epaMode == 0)
-            npEpaKernel<<<gridFor(c, epaBps > 0 ? epaBps : 8), 128, 0, c->stream>>>(c->pairsSorted, c->wCol, c->hullVerts, c->hullOffsets, c->manTmp, c->manScan, c->maxPairs, c->epaSimplex, c->epaWork, c->maxEpaWork, cnt);
+        // default: small shared-memory polytope + redo of the few that outgrow it. B200PHYS_EPA=thread: every pair in the thread-local
+        // kernel (the round-1 path); =warp: the warp-cooperative kernel (measured slower). B200PHYS_EPA_BPS = CTAs per SM (tuning)
+        if (epaMode < 0) { const char* e = getenv("B200PHYS_EPA"); epaMode = !e ? 2 : e[0] == 'w' ? 1 : e[0] == 't' ? 0 : 2; const char* b = getenv("B200PHYS_EPA_BPS"); epaBps = b ? atoi(b) : 0; }
+        if (epaMode == 2)
+        {
+            const size_t smem = (size_t)kEpaSmallWarps * B200_EPAS_WORDS * 32 * sizeof(uint32_t);
+            static bool attr = false;
+            if (!attr) { cudaFuncSetAttribute(npEpaSmallKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+            npEpaSmallKernel<<<c->numSMs, kEpaSmallWarps * 32, smem, c->stream>>>(c->pairsSorted, c->wCol, c->hullVerts, c->hullOffsets, c->manTmp, c->manScan, c->maxPairs, c->epaSimplex, c->epaWork, c->maxEpaWork, cnt, c->epaRedo);
+            timelineMark(c, "np_epa");
+            // the ones that outgrew it are the long runs (up to 20 expansions, ~100 triangles): a warp per pair (exact, see EpaWarp)
+            static int redoThread = -1;
+            if (redoThread < 0) { const char* e = getenv("B200PHYS_EPA_REDO"); redoThread = (e && e[0] == 't') ? 1 : 0; }
+            if (redoThread)
+                npEpaKernel<<<gridFor(c, 2), 64, 0, c->stream>>>(c->pairsSorted, c->wCol, c->hullVerts, c->hullOffsets, c->manTmp, c->manScan, c->maxPairs, c->epaSimplex, c->epaWork, c->maxEpaWork, cnt, c->epaRedo);
+            else
+            {
+                const size_t wsmem = sizeof(EpaWarpShared) * kEpaWarpsPerCta;
+                static bool wattr = false;
+                if (!wattr) { cudaFuncSetAttribute(npEpaWarpKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem); wattr = true; }
+                npEpaWarpKernel<<<gridFor(c, 6), kEpaWarpsPerCta * 32, wsmem, c->stream>>>(c->pairsSorted, c->wCol, c->hullVerts, c->hullOffsets, c->manTmp, c->manScan, c->maxPairs, c->epaSimplex, c->epaWork, c->maxEpaWork, cnt, c->epaRedo);
+            }
+            c->launches += 1;
+        }
+        else if (epaMode == 0)
+            npEpaKernel<<<gridFor(c, epaBps > 0 ? epaBps : 8), 128, 0, c->stream>>>(c->pairsSorted, c->wCol, c->hullVerts, c->hullOffsets, c->manTmp, c->manScan, c->maxPairs, c->epaSimplex, c->epaWork, c->maxEpaWork, cnt, nullptr);
         else
         {
             const size_t smem = sizeof(EpaWarpShared) * kEpaWarpsPerCta;
             static bool attr = false;
             if (!attr) { cudaFuncSetAttribute(npEpaWarpKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
-            npEpaWarpKernel<<<gridFor(c, epaBps > 0 ? epaBps : 6), kEpaWarpsPerCta * 32, smem, c->stream>>>(c->pairsSorted, c->wCol, c->hullVerts, c->hullOffsets, c->manTmp, c->manScan, c->maxPairs, c->epaSimplex, c->epaWork, c->maxEpaWork, cnt);
+            npEpaWarpKernel<<<gridFor(c, epaBps > 0 ? epaBps : 6), kEpaWarpsPerCta * 32, smem, c->stream>>>(c->pairsSorted, c->wCol, c->hullVerts, c->hullOffsets, c->manTmp, c->manScan, c->maxPairs, c->epaSimplex, c->epaWork, c->maxEpaWork, cnt, nullptr);
         }
     }
     c->launches += 1;
-    timelineMark(c, "np_epa");
+    timelineMark(c, epaMode == 2 ? "np_epa_redo" : "np_epa");
     npClearTailKernel<<<G, kThreads, 0, c->stream>>>(c->manScan, cnt);
     c->launches += 5;
     scanExclusiveU64(c, c->manScan, c->manScanOut, &cnt->numPairs, c->maxPairs, nullptr);

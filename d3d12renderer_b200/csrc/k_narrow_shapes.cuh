@@ -676,6 +676,154 @@ B200_D void epa(const SimplexD& g, const SupportD& A, const SupportD& B, f3& out
     outDepth = t.dist;
 }
 
+// ---- small polytope in shared memory (PHASE 4). Still one thread per pair, but the polytope lives in a word-interleaved shared
+// memory column (word k of lane l at [k * 32 + l]: whatever triangle a lane indexes, it stays in its own bank) instead of 7.7 KB of
+// thread-local memory that 1024 resident threads per SM turn into DRAM traffic. Measured on the settled mixed pile (oracle
+// histogram, tests/epa_histogram.py): 98.6 % of all EPA runs end with <= 10 points and <= 30 triangles (edges = triangles + 2), so the
+// column holds exactly that much (272 words = 1088 B per pair, 6 warps per SM); a run that needs more is abandoned and re-run from
+// its simplex by the large-capacity kernel, which gives the same result because the expansion is deterministic.
+// Indices are bytes (0xFF stands for the 0xFFFF a degenerate horizon leaves behind), the activity flags one register, the per-edge
+// reference counts of collision_epa.cpp:114-139 two register bit masks (seen once / seen more often).
+#define B200_EPAS_MAX_POINTS 10
+#define B200_EPAS_MAX_TRIS 30
+#define B200_EPAS_MAX_EDGES 32
+#define B200_EPAS_WORDS (B200_EPAS_MAX_POINTS * 6 + B200_EPAS_MAX_TRIS * 6 + B200_EPAS_MAX_EDGES)
+struct EpaSmall
+{
+    uint32_t* w;             // this lane's column
+    uint32_t active, nT, nP, nE;
+    static constexpr uint32_t kTri = B200_EPAS_MAX_POINTS * 6, kEdge = kTri + B200_EPAS_MAX_TRIS * 6;
+    B200_D float ldf(uint32_t k) const { return __uint_as_float(w[k << 5]); }
+    B200_D uint32_t ldu(uint32_t k) const { return w[k << 5]; }
+    B200_D void stf(uint32_t k, float v) { w[k << 5] = __float_as_uint(v); }
+    B200_D void stu(uint32_t k, uint32_t v) { w[k << 5] = v; }
+    B200_D static uint32_t wide(uint32_t b) { return b == 0xFFu ? 0xFFFFu : b; }           // byte -> the reference's uint16 index
+    B200_D bool isActive(uint32_t i) const { return i < nT && ((active >> i) & 1u); }
+    B200_D SupPt pt(uint32_t i) const
+    {
+        SupPt p; const uint32_t k = 6 * i;
+        p.a = mk3(ldf(k), ldf(k + 1), ldf(k + 2)); p.b = mk3(ldf(k + 3), ldf(k + 4), ldf(k + 5)); p.m = p.a - p.b;      // m = a - b as minkowski() computed it
+        return p;
+    }
+    B200_D f3 ptM(uint32_t i) const { const uint32_t k = 6 * i; return mk3(ldf(k), ldf(k + 1), ldf(k + 2)) - mk3(ldf(k + 3), ldf(k + 4), ldf(k + 5)); }
+    B200_D bool pushPoint(const SupPt& p)
+    {
+        if (nP >= B200_EPAS_MAX_POINTS) return false;
+        const uint32_t k = 6 * nP; stf(k, p.a.x); stf(k + 1, p.a.y); stf(k + 2, p.a.z); stf(k + 3, p.b.x); stf(k + 4, p.b.y); stf(k + 5, p.b.z);
+        ++nP; return true;
+    }
+    B200_D bool pushTri(uint32_t a, uint32_t b, uint32_t c, uint32_t eA, uint32_t eB, uint32_t eC, f3 n, float d)
+    {
+        if (nT >= B200_EPAS_MAX_TRIS) return false;
+        const uint32_t k = kTri + 6 * nT;
+        stf(k, n.x); stf(k + 1, n.y); stf(k + 2, n.z); stf(k + 3, d); stu(k + 4, a | (b << 8) | (c << 16)); stu(k + 5, (eA & 0xFFu) | ((eB & 0xFFu) << 8) | ((eC & 0xFFu) << 16));
+        active |= 1u << nT; ++nT; return true;
+    }
+    B200_D bool pushEdge(uint32_t a, uint32_t b, uint32_t t0, uint32_t t1)
+    {
+        if (nE >= B200_EPAS_MAX_EDGES) return false;
+        stu(kEdge + nE, a | (b << 8) | ((t0 & 0xFFu) << 16) | ((t1 & 0xFFu) << 24));
+        ++nE; return true;
+    }
+    B200_D uint32_t closest() const
+    {   // collision_epa.cpp:94-112
+        uint32_t best = 0xFFFFFFFFu; float mind = FLT_MAX;
+        for (uint32_t rest = active; rest; rest &= rest - 1u)
+        {
+            const uint32_t i = (uint32_t)__ffs((int)rest) - 1u;
+            const float d = ldf(kTri + 6 * i + 3);
+            if (d < mind) { mind = d; best = i; }
+        }
+        return best;
+    }
+    // the tetrahedron GJK ended with (collision_epa.h:98-116)
+    B200_D void init(const SimplexD& g)
+    {
+        active = 0; nT = nP = nE = 0;
+        pushPoint(g.a); pushPoint(g.b); pushPoint(g.c); pushPoint(g.d);
+        f3 n; float d;
+        EpaPoly::triInfo(g.a, g.b, g.d, n, d); pushTri(0, 1, 3, 4, 3, 0, n, d);
+        EpaPoly::triInfo(g.b, g.c, g.d, n, d); pushTri(1, 2, 3, 5, 4, 1, n, d);
+        EpaPoly::triInfo(g.c, g.a, g.d, n, d); pushTri(2, 0, 3, 3, 5, 2, n, d);
+        EpaPoly::triInfo(g.a, g.c, g.b, n, d); pushTri(0, 2, 1, 1, 0, 2, n, d);
+        pushEdge(0, 1, 0, 3); pushEdge(1, 2, 1, 3); pushEdge(2, 0, 2, 3);
+        pushEdge(0, 3, 2, 0); pushEdge(1, 3, 0, 1); pushEdge(2, 3, 1, 2);
+    }
+    // collision_epa.h:148-167: contact from the closest triangle
+    B200_D void result(uint32_t ci, f3& outPoint, f3& outNormal, float& outDepth) const
+    {
+        const uint32_t k = kTri + 6 * ci;
+        const f3 tn = mk3(ldf(k), ldf(k + 1), ldf(k + 2));
+        const float tdist = ldf(k + 3);
+        const uint32_t idx = ldu(k + 4);
+        const SupPt a = pt(idx & 0xFFu), b = pt((idx >> 8) & 0xFFu), c = pt((idx >> 16) & 0xFFu);
+        f3 bc = barycentric(a.m, b.m, c.m, tn * tdist);
+        f3 pA = bc.x * a.a + bc.y * b.a + bc.z * c.a;
+        f3 pB = bc.x * a.b + bc.y * b.b + bc.z * c.b;
+        outPoint = 0.5f * (pA + pB);
+        outNormal = tn;
+        outDepth = tdist;
+    }
+    // collision_epa.cpp:114-239 ; false = a capacity of the SMALL polytope was hit (the caller hands the pair to the large kernel)
+    B200_D bool addPoint(const SupPt& np)
+    {
+        uint32_t once = 0, more = 0;
+        for (uint32_t rest = active; rest; rest &= rest - 1u)
+        {
+            const uint32_t i = (uint32_t)__ffs((int)rest) - 1u, k = kTri + 6 * i;
+            const uint32_t idx = ldu(k + 4);
+            const float d = dot(mk3(ldf(k), ldf(k + 1), ldf(k + 2)), np.m - ptM(idx & 0xFFu));
+            if (d > 0.f)
+            {
+                const uint32_t e = ldu(k + 5);
+#pragma unroll
+                for (int j = 0; j < 3; ++j)
+                {
+                    const uint32_t ei = (e >> (8 * j)) & 0xFFu;
+                    if (ei < nE) { const uint32_t bit = 1u << ei; more |= once & bit; once |= bit; }
+                }
+                active &= ~(1u << i);
+            }
+        }
+        const uint32_t border = once & ~more;                    // refs == 1, ascending edge index
+        unsigned long long newEdgePerPoint = ~0ull;              // 6 bits per point, 63 = none
+        const uint32_t npi = nP;
+        if (!pushPoint(np)) return false;
+        const uint32_t triOffset = nT;
+        for (uint32_t rest = border; rest; rest &= rest - 1u)
+        {
+            const uint32_t ei = (uint32_t)__ffs((int)rest) - 1u;
+            const uint32_t e = ldu(kEdge + ei);
+            const uint32_t ea = e & 0xFFu, eb = (e >> 8) & 0xFFu;
+            const bool aAct = isActive((e >> 16) & 0xFFu), bAct = isActive(e >> 24);
+            const uint32_t connect = bAct ? ea : eb;
+            const uint32_t triIndex = nT, ne = nE;
+            if (!pushEdge(connect, npi, 0xFFu, triIndex)) return false;
+            newEdgePerPoint = (newEdgePerPoint & ~(63ull << (6 * connect))) | ((unsigned long long)ne << (6 * connect));
+            const uint32_t bI = connect, cI = bAct ? eb : ea;
+            f3 n; float d; EpaPoly::triInfo(np, pt(bI), pt(cI), n, d);
+            if (!pushTri(npi, bI, cI, ei, 0xFFu, ne, n, d)) return false;
+            const uint32_t e2 = ldu(kEdge + ei);
+            stu(kEdge + ei, aAct ? ((e2 & 0x00FFFFFFu) | (triIndex << 24)) : ((e2 & 0xFF00FFFFu) | (triIndex << 16)));
+        }
+        uint32_t i = 0;
+        for (uint32_t rest = border; rest; rest &= rest - 1u, ++i)
+        {
+            const uint32_t ei = (uint32_t)__ffs((int)rest) - 1u;
+            const uint32_t e = ldu(kEdge + ei);
+            const bool bNew = wide(e >> 24) >= triOffset;
+            const uint32_t connect = bNew ? (e & 0xFFu) : ((e >> 8) & 0xFFu);
+            const uint32_t other = (uint32_t)(newEdgePerPoint >> (6 * connect)) & 63u;
+            const uint32_t triIndex = i + triOffset;
+            if (other == 63u) continue;
+            const uint32_t kt = kTri + 6 * triIndex + 5;
+            stu(kt, (ldu(kt) & 0xFFFF00FFu) | (other << 8));
+            stu(kEdge + other, (ldu(kEdge + other) & 0xFF00FFFFu) | (triIndex << 16));
+        }
+        return true;
+    }
+};
+
 // ---- warp-cooperative EPA (PHASE 3). One warp expands ONE polytope that lives in shared memory; all 32 lanes execute the calling
 // routine uniformly (same pair, same data) and split the per-triangle / per-edge loops of collision_epa.cpp:94-239 among themselves.
 // Every step reproduces the sequential result exactly: the closest triangle is the first minimum (ties -> lowest index), horizon edges
@@ -915,51 +1063,34 @@ B200_D bool gjkEpa(const SupportD& A, const SupportD& B, Man& m, NC& nc)
 }
 
 // ------------------------------------------------------------------------------------- GJK/EPA-based shape pairs
-// capsule-aabb (:705-769) / cylinder-aabb (:953-1022)
-template <class NC>
-B200_D bool segmentShapeBox(const CapS& c, bool isCylinder, const BoxS& a, Man& m, NC& nc)
+// Every GJK based routine of the reference is "set up two support mappings -> gjkIntersectionTest -> epaCollisionInfo -> routine
+// specific tail". The three parts are separate functions here so that a kernel has ONE copy of GJK / EPA (the per-routine copies
+// made the kernels 200-300 KB of code and instruction fetch their top stall) and can run them as a loop over lanes that are at
+// different stages of different pairs (k_narrow.cu).
+struct GjkJob
 {
-    SupportD A = isCylinder ? supCylinder(c) : supCapsule(c);
-    SupportD B = supBox(a);
-    if (!gjkEpa(A, B, m, nc)) return false;
-    f3 normal = m.n;
-    if (fabsf(normal.x) > 0.99f || fabsf(normal.y) > 0.99f || fabsf(normal.z) > 0.99f)
-    {
-        f3 axis = normalize(c.b - c.a);
-        if (fabsf(dot(normal, axis)) < 0.01f)
-        {
-            f3 cpp[4], cpn[4]; PlaneS planes[4];
-            f3 boxNormal = -normal;
-            PlaneS ref = boxReferencePlane(a, boxNormal);
-            PolyD poly; poly.n = 2;
-            f3 pa = c.a + normal * c.r, pb = c.b + normal * c.r;
-            poly.p[0].v = pa; poly.p[0].depth = -signedDistance(pa, ref);
-            poly.p[1].v = pb; poly.p[1].depth = -signedDistance(pb, ref);
-            f3 ac = boxCenter(a);
-            boxClipPlanes(boxRadius(a), boxNormal, cpp, cpn);
-            for (int i = 0; i < 4; ++i) { cpp[i] = cpp[i] + ac; planes[i] = createPlane(cpp[i], cpn[i]); }
-            clipAndBuild(poly, planes, 4, ref, m);
-        }
-    }
-    return true;
+    SupportD A, B;
+    uint32_t tail;      // 0 none; 1 segment shape vs box: 2-point clip against the box face; 2 the same, then back out of the OBB frame
+    q4 oq; f3 oc;       // tail 2: the OBB frame
+};
+
+// capsule-aabb (:705-769) / cylinder-aabb (:953-1022): before GJK
+B200_D void segmentShapeBoxPre(const CapS& c, bool isCylinder, const BoxS& a, GjkJob& job)
+{
+    job.A = isCylinder ? supCylinder(c) : supCapsule(c);
+    job.B = supBox(a);
+    job.tail = 1;
 }
-// capsule-obb (:771-790) / cylinder-obb (:1024-1043)
-template <class NC>
-B200_D bool segmentShapeObb(const CapS& c, bool isCylinder, const ObbS& o, Man& m, NC& nc)
+// capsule-obb (:771-790) / cylinder-obb (:1024-1043): the segment shape moves into the OBB's frame
+B200_D void segmentShapeObbPre(const CapS& c, bool isCylinder, const ObbS& o, GjkJob& job)
 {
     BoxS bb; bb.mn = o.c - o.r; bb.mx = o.c + o.r;
     CapS c_; c_.a = conjugate(o.q) * (c.a - o.c) + o.c; c_.b = conjugate(o.q) * (c.b - o.c) + o.c; c_.r = c.r;
-    if (segmentShapeBox(c_, isCylinder, bb, m, nc))
-    {
-        m.n = o.q * m.n;
-        for (uint32_t i = 0; i < m.cnt; ++i) m.p[i] = o.q * (m.p[i] - o.c) + o.c;
-        return true;
-    }
-    return false;
+    segmentShapeBoxPre(c_, isCylinder, bb, job);
+    job.tail = 2; job.oq = o.q; job.oc = o.c;
 }
-// collision_narrow.cpp:821-951
-template <class NC>
-B200_D bool cylinderCylinder(const CapS& a, const CapS& b, Man& m, NC& nc)
+// collision_narrow.cpp:821-951 before GJK: 0 = no contact, 1 = manifold complete (parallel axes: closed form), 2 = GJK job ready
+B200_D int cylinderCylinderPre(const CapS& a, const CapS& b, Man& m, NarrowCounters& nc, GjkJob& job)
 {
     f3 aDir = a.b - a.a;
     f3 bDir = normalize(b.b - b.a);
@@ -975,7 +1106,7 @@ B200_D bool cylinderCylinder(const CapS& a, const CapS& b, Man& m, NC& nc)
         float b0 = dot(aDir, pBa - ref), b1 = dot(aDir, pBb - ref);
         if (!(b1 > b0)) ++nc.asserts;
         float left = fmax2(a0, b0), right = fmin2(a1, b1);
-        if (right < left) return false;
+        if (right < left) return 0;
         f3 cA0 = ref + left * aDir, cA1 = ref + right * aDir;
         f3 cB0 = closestPointSegment(cA0, pBa, pBb);
         f3 cB1 = cB0 + (right - left) * aDir;
@@ -983,7 +1114,7 @@ B200_D bool cylinderCylinder(const CapS& a, const CapS& b, Man& m, NC& nc)
         float d = len(normal);
         float rs = a.r + b.r;
         float pen = rs - d;
-        if (pen < 0.f) return false;
+        if (pen < 0.f) return 0;
         float capPen = right - left;
         if (!(capPen > 0.f)) ++nc.asserts;
         if (capPen < pen)
@@ -999,9 +1130,43 @@ B200_D bool cylinderCylinder(const CapS& a, const CapS& b, Man& m, NC& nc)
             m.d[0] = pen; m.p[0] = (cA0 + cB0) * 0.5f;
             m.d[1] = pen; m.p[1] = (cA1 + cB1) * 0.5f;
         }
-        return true;
+        return 1;
     }
-    return gjkEpa(supCylinder(a), supCylinder(b), m, nc);
+    job.A = supCylinder(a); job.B = supCylinder(b); job.tail = 0;
+    return 2;
+}
+// after EPA (m holds its one contact): the routine's own tail
+B200_D void gjkTail(const GjkJob& job, Man& m)
+{
+    if (job.tail == 0) return;
+    {   // :728-766 / :976-1019: an axis aligned normal and the segment parallel to the face -> two clipped points instead of one
+        CapS c; c.a = job.A.a; c.b = job.A.b; c.r = job.A.r;
+        BoxS a; a.mn = job.B.a; a.mx = job.B.b;
+        f3 normal = m.n;
+        if (fabsf(normal.x) > 0.99f || fabsf(normal.y) > 0.99f || fabsf(normal.z) > 0.99f)
+        {
+            f3 axis = normalize(c.b - c.a);
+            if (fabsf(dot(normal, axis)) < 0.01f)
+            {
+                f3 cpp[4], cpn[4]; PlaneS planes[4];
+                f3 boxNormal = -normal;
+                PlaneS ref = boxReferencePlane(a, boxNormal);
+                PolyD poly; poly.n = 2;
+                f3 pa = c.a + normal * c.r, pb = c.b + normal * c.r;
+                poly.p[0].v = pa; poly.p[0].depth = -signedDistance(pa, ref);
+                poly.p[1].v = pb; poly.p[1].depth = -signedDistance(pb, ref);
+                f3 ac = boxCenter(a);
+                boxClipPlanes(boxRadius(a), boxNormal, cpp, cpn);
+                for (int i = 0; i < 4; ++i) { cpp[i] = cpp[i] + ac; planes[i] = createPlane(cpp[i], cpn[i]); }
+                clipAndBuild(poly, planes, 4, ref, m);
+            }
+        }
+    }
+    if (job.tail == 2)
+    {
+        m.n = job.oq * m.n;
+        for (uint32_t i = 0; i < m.cnt; ++i) m.p[i] = job.oq * (m.p[i] - job.oc) + job.oc;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------ OBB - OBB

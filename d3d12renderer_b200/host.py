@@ -174,6 +174,8 @@ class LocomotionEnv:
         lib.b200env_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.b200env_ranges.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         lib.b200env_set_push_probability.argtypes = [C.c_void_p, C.c_float]
+        lib.b200env_set_seed.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64]
+        lib.b200env_set_exact_order.argtypes = [C.c_void_p, C.c_int]
         self.num_envs = int(num_envs)
         self.state_size = int(lib.b200env_state_size()); self.action_size = int(lib.b200env_action_size())
         self.ptr = C.c_void_p(lib.b200env_create(self.num_envs, spacing))
@@ -190,6 +192,14 @@ class LocomotionEnv:
     def set_push_probability(self, p):
         """Chance per environment and step of a random sideways push (0.02 in the reference, learned_locomotion.cpp:448)."""
         self.lib.b200env_set_push_probability(self.ptr, float(p))
+
+    def set_exact_order(self, on=True):
+        """Canonical Gauss-Seidel order (the reference's scalar solver order) instead of the fast colour-sorted one."""
+        self.lib.b200env_set_exact_order(self.ptr, 1 if on else 0)
+
+    def set_seed(self, index, seed):
+        """Seed of environment `index`'s push generator (the reference's xorshift64)."""
+        self.lib.b200env_set_seed(self.ptr, int(index), int(seed))
 
     def reward(self, index):
         return float(self.lib.b200env_reward(self.ptr, int(index)))

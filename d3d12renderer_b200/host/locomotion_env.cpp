@@ -44,6 +44,7 @@ struct locomotion_env_batch
 {
     game_scene scene; std::vector<Env> envs; float physicsTimer = 0.f;
     float pushProbability = 0.02f;      // learned_locomotion.cpp:448
+    bool exactOrder = false;            // canonical Gauss-Seidel order (B200PHYS_STEP_EXACT_ORDER) instead of the colour-sorted fast order
 
     static uint64_t nextRandom(uint64_t& state) { uint64_t x = state; x ^= x << 13; x ^= x >> 7; x ^= x << 17; state = x; return x; }          // core/random.h:14-24
     static float random01(uint64_t& state) { return (uint32_t)nextRandom(state) / (float)0xFFFFFFFFu; }
@@ -53,12 +54,17 @@ struct locomotion_env_batch
         if (!(random01(e.rngState) < pushProbability)) return;
         const uint32_t part = (uint32_t)nextRandom(e.rngState) % (kParts - 1);                 // randomUint32Between(0, NUM_BODY_PARTS - 1)
         const vec3 target = partTransform(e, (int)part).position + b200::mk3(0.f, 0.2f, 0.f);
-        const float dx = -1.f + 2.f * random01(e.rngState), dz = -1.f + 2.f * random01(e.rngState);
+        // vec3(rng.randomFloatBetween(-1, 1), 0, rng.randomFloatBetween(-1, 1)) (:455): the order of the two draws is unspecified in C++;
+        // g++ (which compiles the reference for the parity tests) and MSVC x64 both evaluate constructor arguments right to left, so z is drawn first
+        const float dz = -1.f + 2.f * random01(e.rngState), dx = -1.f + 2.f * random01(e.rngState);
         const vec3 direction = b200::normalize(b200::mk3(dx, 0.f, dz));
         testPhysicsInteraction(scene, target - direction * 5.f, direction, 1000.f, e.firstBody, kParts);
     }
 
-    const trs& partTransform(const Env& e, int part) const { return scene.physicsTransform1[e.firstBody + part]; }
+    // The reference reads transform_component everywhere in the environment (learned_locomotion.cpp:113-129, :284-311, :452), not
+    // physics_transform1: with the fixed 60 Hz step and exactly one sub-step per call the render transform is interpolated with t = 0,
+    // i.e. it shows the pose BEFORE the step just taken (physics.cpp:1396-1402), while velocities are current. Reproduced.
+    const trs& partTransform(const Env& e, int part) const { return scene.entities[scene.rigidBodyEntity[e.firstBody + part]].transform; }
     const rigid_body_component& partBody(const Env& e, int part) const { return scene.rigidBodies[e.firstBody + part]; }
     vec3 globalCOG(const Env& e, int part) const { const trs& t = partTransform(e, part); return t.position + t.rotation * partBody(e, part).localCOGPosition; }   // rigid_body.cpp:83-86
 
@@ -199,7 +205,7 @@ struct locomotion_env_batch
         parallelFor((uint32_t)envs.size(), [&](uint32_t i) { applyAction(envs[i], actions + (size_t)i * kActionFloats); }, 256u);
         scene.jointsDirty = true;
         if (pushProbability > 0.f) for (Env& e : envs) maybePush(e);
-        physics_settings settings; settings.frameRate = 60;
+        physics_settings settings; settings.frameRate = 60; settings.exactConstraintOrder = exactOrder;
         memory_arena arena; physicsTimer = 0.f;
         const int rc = physicsStep(scene, arena, physicsTimer, settings, 1.f / (float)settings.frameRate);
         if (rc) return rc;
@@ -225,6 +231,9 @@ void b200env_destroy(void* env) { delete (locomotion_env_batch*)env; }
 uint32_t b200env_state_size(void) { return kStateFloats; }
 uint32_t b200env_action_size(void) { return kActionFloats; }
 void b200env_set_push_probability(void* env, float p) { ((locomotion_env_batch*)env)->pushProbability = p; }
+void b200env_set_exact_order(void* env, int on) { ((locomotion_env_batch*)env)->exactOrder = on != 0; }
+// seed of one environment's push generator (xorshift64 state, core/random.h: the reference seeds its single generator with the wall clock)
+void b200env_set_seed(void* env, uint32_t index, uint64_t seed) { locomotion_env_batch& b = *(locomotion_env_batch*)env; if (index < b.envs.size()) b.envs[index].rngState = seed; }
 uint32_t b200env_num_envs(void* env) { return (uint32_t)((locomotion_env_batch*)env)->envs.size(); }
 // index < 0: every environment; writes the state(s) after the reset
 void b200env_reset(void* env, int index, float* outStates)

@@ -164,6 +164,13 @@ def patch(rel, t):
         # give the test harness (ref_api.cpp) access to two file-local items: the hull geometry list and getWorldSpaceColliders
         t = t.replace("static std::vector<bounding_hull_geometry> boundingHullGeometries;", "std::vector<bounding_hull_geometry> boundingHullGeometries;", 1)
         t = t.replace("static void getWorldSpaceColliders(", "void getWorldSpaceColliders(", 1)
+    if rel == "learning/learned_locomotion.cpp":
+        # the environment seeds its push generator with the wall clock and hard-codes the push probability: make both settable by the harness
+        t = t.replace("static random_number_generator rng = { (uint32)time(0) };", "random_number_generator rng = { 1 }; float refPushProbability = 0.02f;", 1)
+        t = t.replace("rng.randomFloat01() < 0.02f", "rng.randomFloat01() < refPushProbability", 1)
+        # ... and let it choose between the scalar path (the parity path) and the AVX2 path the DLL uses by default (physics.h:394-396)
+        t = t.replace("float refPushProbability = 0.02f;", "float refPushProbability = 0.02f; bool refEnvSimd = true;", 1)
+        t = t.replace("physicsSettings.frameRate = 60;", "physicsSettings.frameRate = 60; physicsSettings.simdBroadPhase = physicsSettings.simdNarrowPhase = physicsSettings.simdConstraintSolver = refEnvSimd;", 1)
     if rel == "core/random.h":
         t = re.sub(r"\bn\.yzw\b", "vec3(n.y, n.z, n.w)", t)
         t = re.sub(r"\bn\.yz\b", "vec2(n.y, n.z)", t)

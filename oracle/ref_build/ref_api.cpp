@@ -357,6 +357,20 @@ int ref_collide_pair(const b200phys_collider* a, const b200phys_collider* b, int
     return (int)r.numContacts;
 }
 
+// The reference's RL environment exactly as its Physics-Lib DLL exports it (learned_locomotion.cpp:395-488); seed and push probability
+// of its generator are made settable by patch_reference.py (the reference seeds with time(0) and hard-codes 0.02)
+extern "C" { int getPhysicsStateSize(); int getPhysicsActionSize(); void getPhysicsRanges(float*, float*, float*, float*); void resetPhysics(float*); int updatePhysics(float*, float*, float*); }
+extern random_number_generator rng; extern float refPushProbability; extern bool refEnvSimd;
+int ref_env_sizes(int* stateSize, int* actionSize) { *stateSize = getPhysicsStateSize(); *actionSize = getPhysicsActionSize(); return 0; }
+void ref_env_ranges(float* actionMin, float* actionMax) { std::vector<float> smin(getPhysicsStateSize()), smax(getPhysicsStateSize()); getPhysicsRanges(smin.data(), smax.data(), actionMin, actionMax); }
+void ref_env_reset(uint64 seed, float pushProbability, int simd, float* outState)
+{
+    rng = random_number_generator(seed); refPushProbability = pushProbability; refEnvSimd = simd != 0;
+    boundingHullGeometries.clear();
+    resetPhysics(outState);
+}
+int ref_env_update(float* action, float* outState, float* outReward) { return updatePhysics(action, outState, outReward); }
+
 // random_number_generator (core/random.h): n floats of randomFloat01 from a seed (pins the scene generators' stream)
 void ref_random_floats01(uint64 seed, float* out, uint32 n) { random_number_generator rng = { seed }; for (uint32 i = 0; i < n; ++i) out[i] = rng.randomFloat01(); }
 

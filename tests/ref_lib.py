@@ -44,6 +44,8 @@ def load(fast=False):
     lib.ref_scene_detect.argtypes = [vp, i32, i32, vp, vp, vp, u32, vp, vp, vp, vp, u32, vp]
     lib.ref_collide_pair.argtypes = [vp, vp, i32, vp, vp]; lib.ref_collide_pair.restype = i32
     lib.ref_random_floats01.argtypes = [C.c_uint64, vp, u32]
+    lib.ref_env_sizes.argtypes = [vp, vp]; lib.ref_env_ranges.argtypes = [vp, vp]
+    lib.ref_env_reset.argtypes = [C.c_uint64, f32, i32, vp]; lib.ref_env_update.argtypes = [vp, vp, vp]; lib.ref_env_update.restype = i32
     lib.ref_mass_properties.argtypes = [vp, vp, vp, vp]
     lib.ref_assert_count.argtypes = [i32]; lib.ref_assert_count.restype = u32
     _libs[key] = lib
@@ -171,3 +173,27 @@ def mass_properties(collider):
     inertia = np.zeros(9, dtype=np.float32); cog = np.zeros(3, dtype=np.float32); mass = np.zeros(1, dtype=np.float32)
     load().ref_mass_properties(_p(c), _p(inertia), _p(cog), _p(mass))
     return inertia, cog, float(mass[0])
+
+
+class RefEnv:
+    """The reference's RL environment (learned_locomotion.cpp:395-488: resetPhysics / updatePhysics, one ragdoll, 60 Hz, 30 solver iterations),
+    process-global like the original DLL."""
+
+    def __init__(self, fast=False):
+        self.lib = load(fast)
+        a, b = C.c_int(0), C.c_int(0)
+        self.lib.ref_env_sizes(C.byref(a), C.byref(b)); self.state_size, self.action_size = a.value, b.value
+
+    def ranges(self):
+        lo = np.zeros(self.action_size, dtype=np.float32); hi = np.zeros(self.action_size, dtype=np.float32)
+        self.lib.ref_env_ranges(_p(lo), _p(hi)); return lo, hi
+
+    def reset(self, seed=1, push_probability=0.0, simd=False):
+        """simd=True is what the reference DLL does (AVX2 path); False = its scalar path, the parity path."""
+        out = np.zeros(self.state_size, dtype=np.float32)
+        self.lib.ref_env_reset(seed, push_probability, 1 if simd else 0, _p(out)); return out
+
+    def step(self, action):
+        a = np.ascontiguousarray(action, dtype=np.float32); out = np.zeros(self.state_size, dtype=np.float32); rew = np.zeros(1, dtype=np.float32)
+        failed = self.lib.ref_env_update(_p(a), _p(out), _p(rew))
+        return out, float(rew[0]), bool(failed)

@@ -207,3 +207,39 @@ def test_contact_and_manifold_capacity_overflow_is_safe():
         assert int(k.sum()) == len(c), "manifold and contact lists must be cut together"
         assert np.array_equal(p, fp[:len(p)]) and np.array_equal(k, fk[:len(k)]) and np.array_equal(b, fb[:len(b)])
         assert np.array_equal(c["point"], fc["point"][:len(c)])
+
+
+# ------------------------------------------------------------------------------------------------ RL environment (f.3)
+def test_locomotion_env_matches_the_reference_environment():
+    """The batched environment (host/locomotion_env.cpp over the CUDA step) against the reference's OWN environment, compiled from
+    learned_locomotion.cpp (oracle/_ref: resetPhysics / updatePhysics, one ragdoll): same action ranges; with the same random actions
+    the 66-float state, the reward and the failure flag agree step by step, also with pushes forced on (probability 1, same generator
+    seed: same body part, same ray, same impulse through testPhysicsInteraction)."""
+    import ref_lib
+    if not ref_lib.available():
+        pytest.skip("oracle/_ref not built")
+    ref = ref_lib.RefEnv()
+    env = host.LocomotionEnv(4, spacing=6.0)
+    env.set_exact_order(True)                  # joints in array order like the reference's scalar solver (the DLL's default AVX2 path re-orders them)
+    assert (ref.state_size, ref.action_size) == (env.state_size, env.action_size) == (66, 27)
+    lo, hi = env.action_ranges(); rlo, rhi = ref.ranges()
+    assert np.allclose(lo, rlo, atol=1e-6) and np.allclose(hi, rhi, atol=1e-6)
+    rng = np.random.default_rng(12)
+    # The ragdoll starts 0.16 above the ground and lands on its toes in step 10. Until then the two environments agree to 1e-6 (no
+    # actions) / 3e-4 (position motors: device vs glibc trigonometry times the motor gains); once it stands on its feet the stacked
+    # contacts amplify that by about 2x per step (measured, tools/env_pin_probe.py: 1e-6 at landing, 5e-4 twelve steps later), and the
+    # reference's DLL interface offers no way to re-synchronise. So: (1) no actions, 20 steps = fall, landing and ten steps of standing;
+    # (2) random actions for the 8 steps of the fall; (3) the same with a push in every step (same generator seed on both sides).
+    # The reward compares looser: it contains acos(w) of rotation differences near identity, where one ulp of w is 3e-4 of angle.
+    for scale, push, steps, tol in ((0.0, 0.0, 20, 1e-3), (0.05, 0.0, 8, 1e-3), (0.05, 1.0, 8, 2e-3)):
+        env.set_push_probability(push); env.set_seed(0, 77)
+        env.reset(); ref.reset(seed=77, push_probability=push, simd=False)
+        for step in range(steps):
+            a = (scale * rng.uniform(lo, hi)).astype(np.float32)
+            states, rewards, failed = env.step(np.tile(a, (4, 1)))
+            rs, rr, rf = ref.step(a)
+            assert bool(failed[0]) == rf, "failure flag differs at step %d" % step
+            err = float(np.max(np.abs(states[0] - rs) / np.maximum(1.0, np.abs(rs))))
+            assert err <= tol, "state differs at step %d (action scale %g, push %g): %g" % (step, scale, push, err)
+            assert abs(rewards[0] - rr) <= 4e-3, "reward differs at step %d: %g vs %g" % (step, rewards[0], rr)
+    env.close()

@@ -9,10 +9,11 @@ st = abi.Stepper(max_bodies=len(sc["bodies"]), max_colliders=len(sc["colliders"]
 st.set_hulls(sc["hull_vertices"], sc["hull_offsets"]); st.upload_bodies(sc["bodies"]); st.upload_transforms(sc["transforms"]); st.upload_colliders(sc["colliders"])
 st.enable_timing(True)
 acc = {}
-for s in range(8):
+nsteps = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+for s in range(nsteps):
     st.step(np.float32(1 / 120.), 10, 0)
-    if s >= 3:
+    if s >= nsteps - 5:
         for k, v in st.timeline(): acc[k] = acc.get(k, 0.0) + v / 5
 s = st.stats(check=False)
-print("EPA=%s BPS=%s  N=%d manifolds=%d epaOvf=%d | " % (os.environ.get("B200PHYS_EPA", "warp"), os.environ.get("B200PHYS_EPA_BPS", "-"), len(sc["bodies"]), s.numCollisions, s.epaOverflows) +
+print("EPA=%s BPS=%s  N=%d manifolds=%d epaOvf=%d epaRuns=%d redo=%d | " % (os.environ.get("B200PHYS_EPA", "small"), os.environ.get("B200PHYS_EPA_BPS", "-"), len(sc["bodies"]), s.numCollisions, s.epaOverflows, s.reserved[4], s.reserved[5]) +
       " ".join("%s %.3f" % (k, v) for k, v in acc.items() if k.startswith("np_")) + " | total %.3f" % sum(acc.values()))
