@@ -203,73 +203,89 @@ struct WarpRange
 // final; hits are parked with their terminal simplex in the EPA work list. Most pairs leave after one or two support evaluations and
 // the rest take 3-10 rounds, so the lanes of a warp are NOT tied to one pair each for a whole test: the loop below performs one
 // support evaluation per pass for every lane and a lane whose pair is decided takes the next pair of the bucket at once.
-__global__ void __launch_bounds__(128) npGjkKernel(const uint2* __restrict__ sorted, const float4* __restrict__ wCol, const float4* __restrict__ hullVerts,
+__global__ void __launch_bounds__(128, 4) npGjkKernel(const uint2* __restrict__ sorted, const float4* __restrict__ wCol, const float4* __restrict__ hullVerts,
     const uint32_t* __restrict__ hullOffsets, float4* __restrict__ manTmp, unsigned long long* __restrict__ manScan, uint32_t maxPairs,
-    float4* __restrict__ sxPlanes, uint2* __restrict__ epaWork, uint32_t sxCap, DeviceCounts* cnt)
+    float4* __restrict__ sxPlanes, uint2* __restrict__ epaWork, uint32_t sxCap, DeviceCounts* cnt, uint32_t refillAt)
 {
     constexpr uint32_t list2[11] = { 5, 8, 9, 10, 11, 12, 13, 14, 17, 19, 20 };
     NarrowCounters nc; nc.epaOverflow = nc.gjkCap = nc.asserts = 0;
     const uint32_t lane = threadIdx.x & 31u;
-    for (int li = 0; li < 11; ++li)
+    // the 11 GJK buckets as one index space (a warp that drains bucket by bucket idles most of its lanes 11 times): lane l < 11 holds
+    // the first pair slot of bucket l and the running total in front of it
+    uint32_t myStart = 0, mySize = 0;
+    if (lane < 11u) { myStart = cnt->keyStart[list2[lane]]; mySize = cnt->keyStart[list2[lane] + 1] - myStart; }
+    uint32_t myPre = mySize;
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, myPre, o); if (lane >= (uint32_t)o) myPre += v; }
+    const uint32_t total = __shfl_sync(0xffffffffu, myPre, 10);
+    myPre -= mySize;                                         // exclusive
+    WarpRange range;
+    bool busy = false; uint32_t q = 0, bucket = 0; int stage = 0, round = 0;
+    GjkJob job; SimplexD s; f3 dir = mk3(0.f);
+    for (;;)
     {
-        const uint32_t bucket = list2[li];
-        const uint32_t q0 = cnt->keyStart[bucket], total = cnt->keyStart[bucket + 1] - q0;
-        if (!total) continue;
-        WarpRange range;
-        bool busy = false; uint32_t q = 0; int stage = 0, round = 0;
-        GjkJob job; SimplexD s; f3 dir = mk3(0.f);
-        for (;;)
+        // idle lanes take new pairs together (the set-up below runs with at least refillAt lanes, or when nothing else is left to do)
+        const uint32_t idle = __ballot_sync(0xffffffffu, !busy);
+        const bool batch = (uint32_t)__popc(idle) >= refillAt || idle == 0xffffffffu;
+        const uint32_t item = range.take(!busy && batch, &cnt->gjkCursor[0], total, 256u);
+        uint32_t li = 0;
+#pragma unroll
+        for (int k = 1; k < 11; ++k) { const uint32_t pk = __shfl_sync(0xffffffffu, myPre, k); if (item != 0xFFFFFFFFu && item >= pk) li = (uint32_t)k; }
+        const uint32_t bStart = __shfl_sync(0xffffffffu, myStart, (int)li), bPre = __shfl_sync(0xffffffffu, myPre, (int)li);
+        if (item != 0xFFFFFFFFu)
         {
-            const uint32_t item = range.take(!busy, &cnt->gjkCursor[li], total, 128u);
-            if (item != 0xFFFFFFFFu)
+            bucket = list2[li];
+            q = bStart + (item - bPre);
+            const uint2 pr = sorted[q];
+            const ColRec A = loadCol(wCol, pr.x), B = loadCol(wCol, pr.y);
+            Man m; m.cnt = 0;
+            const int st = gjkPrep(bucket, A, B, hullVerts, hullOffsets, m, nc, job);
+            if (st != 2) storeManifold(manTmp, manScan, q, maxPairs, st == 1, m);
+            else { busy = true; stage = 0; dir = mk3(1.f, 0.1f, -0.2f); }        // collision_gjk.h:190
+        }
+        const uint32_t busyMask = __ballot_sync(0xffffffffu, busy);
+        if (!busyMask) { if (range.dry) break; else continue; }
+        if (busy)
+        {
+            bool done = false, hit = false;
+            if (stage == 2)
             {
-                q = q0 + item;
-                const uint2 pr = sorted[q];
-                const ColRec A = loadCol(wCol, pr.x), B = loadCol(wCol, pr.y);
-                Man m; m.cnt = 0;
-                const int st = gjkPrep(bucket, A, B, hullVerts, hullOffsets, m, nc, job);
-                if (st != 2) storeManifold(manTmp, manScan, q, maxPairs, st == 1, m);
-                else { busy = true; stage = 0; dir = mk3(1.f, 0.1f, -0.2f); }        // collision_gjk.h:190
+                if (round >= B200_GJK_MAX_ROUNDS) { ++nc.gjkCap; done = true; }
+                else if (sqLen(dir) < 0.0001f) done = true;
             }
-            if (!__any_sync(0xffffffffu, busy)) { if (range.dry) break; else continue; }
-            if (busy)
+            // lanes arrive here over different paths: bring them back together for the expensive part (without this the support
+            // evaluation below was issued ~twice per pass for two halves of the warp, ncu: 15 of 32 lanes active)
+            const uint32_t evalMask = __ballot_sync(busyMask, !done);
+            if (!done)
             {
-                bool done = false, hit = false;
-                if (stage == 2)
+                __syncwarp(evalMask);
+                const SupPt a = minkowski(job.A, job.B, dir);
+                if (dot(a.m, dir) < 0.f) done = true;
+                else if (stage == 0) { s.c = a; dir = -a.m; stage = 1; }
+                else if (stage == 1) { s.b = a; dir = crossABA(s.c.m - s.b.m, -s.b.m); s.n = 2; stage = 2; round = 0; }
+                else
                 {
-                    if (round >= B200_GJK_MAX_ROUNDS) { ++nc.gjkCap; done = true; }
-                    else if (sqLen(dir) < 0.0001f) done = true;
+                    const int r = updateSimplex(s, a, dir);
+                    if (r == B200_GJK_STOP) { s.a = a; s.n = 4; done = hit = true; }
+                    else if (r == B200_GJK_ERROR) done = true;
+                    else ++round;
                 }
-                if (!done)
-                {
-                    const SupPt a = minkowski(job.A, job.B, dir);
-                    if (dot(a.m, dir) < 0.f) done = true;
-                    else if (stage == 0) { s.c = a; dir = -a.m; stage = 1; }
-                    else if (stage == 1) { s.b = a; dir = crossABA(s.c.m - s.b.m, -s.b.m); s.n = 2; stage = 2; round = 0; }
-                    else
-                    {
-                        const int r = updateSimplex(s, a, dir);
-                        if (r == B200_GJK_STOP) { s.a = a; s.n = 4; done = hit = true; }
-                        else if (r == B200_GJK_ERROR) done = true;
-                        else ++round;
-                    }
+            }
+            if (done)
+            {
+                if (hit)
+                {   // warp-aggregated append to the EPA work list
+                    const uint32_t mask = __activemask();
+                    const uint32_t leader = (uint32_t)__ffs((int)mask) - 1u;
+                    uint32_t base = 0;
+                    if (lane == leader) base = atomicAdd(&cnt->numEpaWork, (uint32_t)__popc(mask));
+                    base = __shfl_sync(mask, base, (int)leader);
+                    const uint32_t e = base + (uint32_t)__popc(mask & ((1u << lane) - 1u));
+                    if (e < sxCap) { storeSimplex(sxPlanes, sxCap, e, s); epaWork[e] = make_uint2(q, bucket); }
+                    else cnt->overflowManifolds = 1;
                 }
-                if (done)
-                {
-                    if (hit)
-                    {   // warp-aggregated append to the EPA work list
-                        const uint32_t mask = __activemask();
-                        const uint32_t leader = (uint32_t)__ffs((int)mask) - 1u;
-                        uint32_t base = 0;
-                        if (lane == leader) base = atomicAdd(&cnt->numEpaWork, (uint32_t)__popc(mask));
-                        base = __shfl_sync(mask, base, (int)leader);
-                        const uint32_t e = base + (uint32_t)__popc(mask & ((1u << lane) - 1u));
-                        if (e < sxCap) { storeSimplex(sxPlanes, sxCap, e, s); epaWork[e] = make_uint2(q, bucket); }
-                        else cnt->overflowManifolds = 1;
-                    }
-                    manScan[q] = 0ull;            // no manifold (yet)
-                    busy = false;
-                }
+                manScan[q] = 0ull;            // no manifold (yet)
+                busy = false;
             }
         }
     }
@@ -304,7 +320,7 @@ __global__ void __launch_bounds__(128) npEpaKernel(const uint2* __restrict__ sor
 static const int kEpaSmallWarps = 6;
 __global__ void __launch_bounds__(kEpaSmallWarps * 32, 1) npEpaSmallKernel(const uint2* __restrict__ sorted, const float4* __restrict__ wCol, const float4* __restrict__ hullVerts,
     const uint32_t* __restrict__ hullOffsets, float4* __restrict__ manTmp, unsigned long long* __restrict__ manScan, uint32_t maxPairs,
-    float4* __restrict__ sxPlanes, const uint2* __restrict__ epaWork, uint32_t sxCap, DeviceCounts* cnt, uint32_t* __restrict__ redo)
+    float4* __restrict__ sxPlanes, const uint2* __restrict__ epaWork, uint32_t sxCap, DeviceCounts* cnt, uint32_t* __restrict__ redo, uint32_t refillAt)
 {
     extern __shared__ uint32_t epaColumns[];
     const uint32_t lane = threadIdx.x & 31u;
@@ -312,10 +328,22 @@ __global__ void __launch_bounds__(kEpaSmallWarps * 32, 1) npEpaSmallKernel(const
     EpaSmall P; P.w = epaColumns + (size_t)(threadIdx.x >> 5) * (B200_EPAS_WORDS * 32) + lane; P.active = 0; P.nT = P.nP = P.nE = 0;
     const uint32_t total = min(cnt->numEpaWork, sxCap);
     WarpRange range;
-    bool busy = false; uint32_t e = 0, q = 0, it = 0; GjkJob job;
+    // lane states: 0 idle, 1 expanding, 2 converged (contact still to be written). Finishing and starting a run cost about as much
+    // as an expansion and a run is ~2.5 expansions, so both are done by many lanes together: when refillAt lanes are not expanding.
+    int state = 0; uint32_t e = 0, q = 0, it = 0, ci = 0; GjkJob job;
     for (;;)
     {
-        const uint32_t item = range.take(!busy, &cnt->epaWorkHead, total, 64u);
+        const uint32_t waiting = __ballot_sync(0xffffffffu, state != 1);
+        const bool batch = (uint32_t)__popc(waiting) >= refillAt || waiting == 0xffffffffu;
+        if (batch && state == 2)
+        {
+            Man m; f3 p;
+            P.result(ci, p, m.n, m.d[0]); m.p[0] = p; m.cnt = 1;
+            gjkTail(job, m);
+            storeManifold(manTmp, manScan, q, maxPairs, true, m);
+            state = 0;
+        }
+        const uint32_t item = range.take(batch && state == 0, &cnt->epaWorkHead, total, 64u);
         if (item != 0xFFFFFFFFu)
         {
             e = item;
@@ -328,33 +356,26 @@ __global__ void __launch_bounds__(kEpaSmallWarps * 32, 1) npEpaSmallKernel(const
             {
                 SimplexD g; loadSimplex(sxPlanes, sxCap, e, g);
                 P.init(g);
-                busy = true; it = 0;
+                state = 1; it = 0;
             }
         }
-        if (!__any_sync(0xffffffffu, busy)) { if (range.dry) break; else continue; }
-        if (busy)
+        if (!__any_sync(0xffffffffu, state != 0)) { if (range.dry) break; else continue; }
+        const uint32_t expandMask = __ballot_sync(0xffffffffu, state == 1);
+        if (state == 1)
         {   // one pass of the loop of collision_epa.h:118-146
-            bool done = false, over = false;
-            uint32_t ci = P.closest();
-            if (ci == 0xFFFFFFFFu) { ++nc.asserts; ci = 0; done = true; }
+            ci = P.closest();
+            const uint32_t evalMask = __ballot_sync(expandMask, ci != 0xFFFFFFFFu);      // lanes leave closest() at different times: together again
+            if (ci == 0xFFFFFFFFu) { ++nc.asserts; ci = 0; state = 2; }
             else
             {
+                __syncwarp(evalMask);
                 const uint32_t k = EpaSmall::kTri + 6 * ci;
                 const f3 tn = mk3(P.ldf(k), P.ldf(k + 1), P.ldf(k + 2));
                 const SupPt a = minkowski(job.A, job.B, tn);
-                if (dot(a.m, tn) - P.ldf(k + 3) < 0.01f) done = true;
-                else if (!P.addPoint(a)) over = true;
-                else if (++it == 20u) done = true;
+                if (dot(a.m, tn) - P.ldf(k + 3) < 0.01f) state = 2;
+                else if (!P.addPoint(a)) { redo[atomicAdd(&cnt->numEpaRedo, 1u)] = e; state = 0; }
+                else if (++it == 20u) state = 2;
             }
-            if (done)
-            {
-                Man m; f3 p;
-                P.result(ci, p, m.n, m.d[0]); m.p[0] = p; m.cnt = 1;
-                gjkTail(job, m);
-                storeManifold(manTmp, manScan, q, maxPairs, true, m);
-                busy = false;
-            }
-            else if (over) { redo[atomicAdd(&cnt->numEpaRedo, 1u)] = e; busy = false; }
         }
     }
     flushCounters(nc, cnt);
@@ -528,7 +549,9 @@ void launchNarrowphase(Context* c)
     npCollideKernel<0><<<G, 256, 0, c->stream>>>(c->pairsSorted, c->wCol, c->manTmp, c->manScan, c->maxPairs, cnt);
     npCollideKernel<1><<<gridFor(c, 4), 128, 0, c->stream>>>(c->pairsSorted, c->wCol, c->manTmp, c->manScan, c->maxPairs, cnt);
     timelineMark(c, "np_closed_form_sat");
-    npGjkKernel<<<gridFor(c, 8), 128, 0, c->stream>>>(c->pairsSorted, c->wCol, c->hullVerts, c->hullOffsets, c->manTmp, c->manScan, c->maxPairs, c->epaSimplex, c->epaWork, c->maxEpaWork, cnt);
+    static int gjkRefill = -1, epaRefill = -1;     // lanes that must be idle before a warp sets up new pairs (tuning: B200PHYS_GJK_REFILL / B200PHYS_EPA_REFILL)
+    if (gjkRefill < 0) { const char* e = getenv("B200PHYS_GJK_REFILL"); gjkRefill = e ? atoi(e) : 16; e = getenv("B200PHYS_EPA_REFILL"); epaRefill = e ? atoi(e) : 16; }
+    npGjkKernel<<<gridFor(c, 8), 128, 0, c->stream>>>(c->pairsSorted, c->wCol, c->hullVerts, c->hullOffsets, c->manTmp, c->manScan, c->maxPairs, c->epaSimplex, c->epaWork, c->maxEpaWork, cnt, (uint32_t)gjkRefill);
     timelineMark(c, "np_gjk");
     static int epaMode = -1, epaBps = 0;
     {
@@ -540,7 +563,7 @@ void launchNarrowphase(Context* c)
             const size_t smem = (size_t)kEpaSmallWarps * B200_EPAS_WORDS * 32 * sizeof(uint32_t);
             static bool attr = false;
             if (!attr) { cudaFuncSetAttribute(npEpaSmallKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
-            npEpaSmallKernel<<<c->numSMs, kEpaSmallWarps * 32, smem, c->stream>>>(c->pairsSorted, c->wCol, c->hullVerts, c->hullOffsets, c->manTmp, c->manScan, c->maxPairs, c->epaSimplex, c->epaWork, c->maxEpaWork, cnt, c->epaRedo);
+            npEpaSmallKernel<<<c->numSMs, kEpaSmallWarps * 32, smem, c->stream>>>(c->pairsSorted, c->wCol, c->hullVerts, c->hullOffsets, c->manTmp, c->manScan, c->maxPairs, c->epaSimplex, c->epaWork, c->maxEpaWork, cnt, c->epaRedo, (uint32_t)epaRefill);
             timelineMark(c, "np_epa");
             // the ones that outgrew it are the long runs (up to 20 expansions, ~100 triangles): a warp per pair (exact, see EpaWarp)
             static int redoThread = -1;
