@@ -198,11 +198,45 @@ struct Context
     // capacities
     uint32_t maxPairs = 0, maxManifolds = 0, maxContacts = 0, maxJoints = 0, maxCells = 0;
 
+    // CUDA graph replay of the step (b200phys_api.cu): 0 = launch, 1 = dry run that only hashes what would be launched
+    int graphMode = 0; unsigned long long graphHash = 0; void* graphCache = nullptr; bool graphFailed = false; uint32_t graphReplays = 0, graphCaptures = 0;
+
     // halo (multi-GPU)
     void* dist = nullptr;               // NCCL communicator + slab + message buffers of a context made by b200phys_create_distributed (k_dist.cu)
     uint8_t* haloBuf = nullptr; uint32_t haloCap = 0;
     uint32_t numGhostBodies = 0, numGhostColliders = 0;
 };
+
+// ---- every stream operation of the step goes through these wrappers: in a dry run (graphMode 1) nothing is enqueued, the kernel, its
+// launch geometry and the VALUES of its arguments are hashed instead; the hash of a whole step identifies a captured CUDA graph.
+static inline void graphHashBytes(Context* c, const void* p, size_t n)
+{
+    unsigned long long h = c->graphHash; const unsigned char* b = (const unsigned char*)p;
+    for (size_t i = 0; i < n; ++i) { h ^= b[i]; h *= 1099511628211ull; }
+    c->graphHash = h;
+}
+template <class T> static inline void graphHashValue(Context* c, T v) { graphHashBytes(c, &v, sizeof(T)); }
+template <class... KArgs, class... Args>
+static inline void launchK(Context* c, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, Args&&... args)
+{
+    if (c->graphMode == 1)
+    {
+        graphHashValue(c, (const void*)kernel); graphHashValue(c, grid.x); graphHashValue(c, grid.y); graphHashValue(c, block.x); graphHashValue(c, smem);
+        (graphHashValue<KArgs>(c, static_cast<KArgs>(args)), ...);
+        return;
+    }
+    kernel<<<grid, block, smem, c->stream>>>(static_cast<KArgs>(args)...);
+}
+static inline void memsetK(Context* c, void* p, int value, size_t bytes)
+{
+    if (c->graphMode == 1) { graphHashValue(c, p); graphHashValue(c, value); graphHashValue(c, bytes); return; }
+    cudaMemsetAsync(p, value, bytes, c->stream);
+}
+static inline void memcpyD2DK(Context* c, void* dst, const void* src, size_t bytes)
+{
+    if (c->graphMode == 1) { graphHashValue(c, dst); graphHashValue(c, src); graphHashValue(c, bytes); return; }
+    cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, c->stream);
+}
 
 // records the end of a kernel group on the context's stream when timing is enabled (no-op otherwise)
 static inline void timelineMark(Context* c, const char* name)

@@ -119,10 +119,10 @@ static void scanExclusive(Context* c, const T* in, T* out, const uint32_t* devCo
     if ((uint32_t)blocks > maxBlocks) blocks = (int)maxBlocks;
     if (blocks < 1) blocks = 1;
     T* total = tmp + 2048;
-    scanReduceKernel<T><<<blocks, kScanThreads, 0, c->stream>>>(in, devCount, maxCount, tmp);
-    scanSpineKernel<T><<<1, 1024, 0, c->stream>>>(tmp, (uint32_t)blocks, total);
-    scanApplyKernel<T><<<blocks, kScanThreads, 0, c->stream>>>(const_cast<T*>(in), out, devCount, maxCount, tmp, total, clearInput);
-    if (totalOut) cudaMemcpyAsync(totalOut, total, sizeof(T), cudaMemcpyDeviceToDevice, c->stream);
+    launchK(c, scanReduceKernel<T>, blocks, kScanThreads, 0, in, devCount, maxCount, tmp);
+    launchK(c, scanSpineKernel<T>, 1, 1024, 0, tmp, (uint32_t)blocks, total);
+    launchK(c, scanApplyKernel<T>, blocks, kScanThreads, 0, const_cast<T*>(in), out, devCount, maxCount, tmp, total, clearInput);
+    if (totalOut) memcpyD2DK(c, totalOut, total, sizeof(T));
     c->launches += 3;
 }
 
@@ -131,11 +131,20 @@ static void scanExclusive(Context* c, const T* in, T* out, const uint32_t* devCo
 // in one 64-bit word, the epoch (a per-context launch counter) makes clearing the status array unnecessary; the last CTA to leave
 // resets the ticket counter for the next launch.
 static const int kLbThreads = 256, kLbItems = 8, kLbTile = kLbThreads * kLbItems;
-struct ScanLbState { unsigned int ticket, done; };
+struct ScanLbState { unsigned int ticket, done, epoch, pad; };      // epoch lives on the device so that a replayed CUDA graph sees a fresh one
+
+// the epoch of this launch (1 .. 2^30-1): read before the CTA takes a ticket, advanced by the last CTA to leave (nobody of this launch
+// can read it afterwards)
+B200_D uint32_t scanEpochOf(const ScanLbState* state) { uint32_t e; asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(e) : "l"(&state->epoch) : "memory"); return e + 1u; }
+B200_D void scanLeave(ScanLbState* state, uint32_t epoch)
+{
+    if (atomicAdd(&state->done, 1u) == gridDim.x - 1) { state->ticket = 0; state->done = 0; state->epoch = (epoch >= 0x3FFFFFFEu) ? 0u : epoch; }     // last one out: ready for the next launch
+}
 
 __global__ void __launch_bounds__(kLbThreads) scanLookbackKernel(uint32_t* __restrict__ in, uint32_t* __restrict__ out, const uint32_t* __restrict__ devCount, uint32_t hostCount,
-                                                                 unsigned long long* __restrict__ status, ScanLbState* __restrict__ state, uint32_t epoch, uint32_t* __restrict__ totalOut, bool clearInput)
+                                                                 unsigned long long* __restrict__ status, ScanLbState* __restrict__ state, uint32_t* __restrict__ totalOut, bool clearInput)
 {
+    const uint32_t epoch = scanEpochOf(state);
     __shared__ uint32_t warpSums[kLbThreads / 32];
     __shared__ uint32_t sTile, sPrefix, sTileTotal;
     const uint32_t n = devCount ? *devCount : hostCount;
@@ -228,7 +237,7 @@ __global__ void __launch_bounds__(kLbThreads) scanLookbackKernel(uint32_t* __res
     if (threadIdx.x == 0)
     {
         if (n == 0 && blockIdx.x == 0) { out[0] = 0; if (totalOut) *totalOut = 0; }
-        if (atomicAdd(&state->done, 1u) == gridDim.x - 1) { state->ticket = 0; state->done = 0; }     // last one out: ready for the next launch
+        scanLeave(state, epoch);
     }
 }
 
@@ -243,16 +252,16 @@ void scanExclusiveU32(Context* c, const uint32_t* in, uint32_t* out, const uint3
     }
     int blocks = gridFor(c, 4);
     if ((uint32_t)blocks > maxTiles) blocks = (int)maxTiles;
-    c->scanEpoch = (c->scanEpoch + 1u) & 0x3FFFFFFFu; if (c->scanEpoch == 0) c->scanEpoch = 1;
-    scanLookbackKernel<<<blocks, kLbThreads, 0, c->stream>>>(const_cast<uint32_t*>(in), out, devCount, maxCount, c->scanStatus, (ScanLbState*)c->scanState, c->scanEpoch, totalOut, clearInput);
+    launchK(c, scanLookbackKernel, blocks, kLbThreads, 0, const_cast<uint32_t*>(in), out, devCount, maxCount, c->scanStatus, (ScanLbState*)c->scanState, totalOut, clearInput);
     c->launches += 1;
 }
 // 64-bit variant (two packed 32-bit sums per element): the tile status is two self-validating words, (tag | low half) and
 // (tag | high half); a reader accepts a tile only when both words carry the same tag
 static const int kLb64Items = 4, kLb64Tile = kLbThreads * kLb64Items;
 __global__ void __launch_bounds__(kLbThreads) scanLookbackKernel64(const unsigned long long* __restrict__ in, unsigned long long* __restrict__ out, const uint32_t* __restrict__ devCount, uint32_t hostCount,
-                                                                   unsigned long long* __restrict__ status /* 2 words per tile */, ScanLbState* __restrict__ state, uint32_t epoch)
+                                                                   unsigned long long* __restrict__ status /* 2 words per tile */, ScanLbState* __restrict__ state)
 {
+    const uint32_t epoch = scanEpochOf(state);
     __shared__ unsigned long long warpSums[kLbThreads / 32];
     __shared__ unsigned long long sPrefix, sTileTotal; __shared__ uint32_t sTile;
     const uint32_t n = devCount ? *devCount : hostCount;
@@ -328,7 +337,7 @@ __global__ void __launch_bounds__(kLbThreads) scanLookbackKernel64(const unsigne
     if (threadIdx.x == 0)
     {
         if (n == 0 && blockIdx.x == 0) out[0] = 0ull;
-        if (atomicAdd(&state->done, 1u) == gridDim.x - 1) { state->ticket = 0; state->done = 0; }
+        scanLeave(state, epoch);
     }
 }
 
@@ -343,8 +352,7 @@ void scanExclusiveU64(Context* c, const unsigned long long* in, unsigned long lo
     }
     int blocks = gridFor(c, 4);
     if ((uint32_t)blocks > maxTiles) blocks = (int)maxTiles;
-    c->scanEpoch = (c->scanEpoch + 1u) & 0x3FFFFFFFu; if (c->scanEpoch == 0) c->scanEpoch = 1;
-    scanLookbackKernel64<<<blocks, kLbThreads, 0, c->stream>>>(in, out, devCount, maxCount, c->scanStatus, (ScanLbState*)c->scanState, c->scanEpoch);
+    launchK(c, scanLookbackKernel64, blocks, kLbThreads, 0, in, out, devCount, maxCount, c->scanStatus, (ScanLbState*)c->scanState);
     c->launches += 1;
 }
 
@@ -419,11 +427,11 @@ void stableSmallKeySort(Context* c, const uint8_t* keys, const uint32_t* devCoun
     const uint32_t totalWarps = (uint32_t)blocks * kSortWarps;
     uint32_t* hist = c->sortHist;                       // numKeys * totalWarps (+1)
     uint32_t* histScan = hist + 64 * totalWarps + 64;
-    sksHistKernel<<<blocks, kSortThreads, 0, c->stream>>>(keys, devCount, numKeys, hist);
+    launchK(c, sksHistKernel, blocks, kSortThreads, 0, keys, devCount, numKeys, hist);
     c->launches += 1;
     scanExclusiveU32(c, hist, histScan, nullptr, numKeys * totalWarps, nullptr);
-    sksScatterKernel<<<blocks, kSortThreads, 0, c->stream>>>(keys, devCount, numKeys, histScan, dst);
-    sksKeyStartKernel<<<1, 64, 0, c->stream>>>(histScan, numKeys, totalWarps, devCount, keyStart);
+    launchK(c, sksScatterKernel, blocks, kSortThreads, 0, keys, devCount, numKeys, histScan, dst);
+    launchK(c, sksKeyStartKernel, 1, 64, 0, histScan, numKeys, totalWarps, devCount, keyStart);
     c->launches += 2;
 }
 

@@ -3,6 +3,7 @@
 // enqueue the fixed kernel sequence of one physicsStepInternal (physics.cpp:1180-1362) on the context's stream, copy results.
 // There is no CPU implementation of any stage in this library: without a CUDA device b200phys_create fails.
 #include <algorithm>
+#include <unordered_map>
 #include "b200_context.h"
 #include <cstdio>
 #include <cstring>
@@ -164,11 +165,13 @@ int b200phys_create(const b200phys_config* config, b200phys_context** out)
     return 0;
 }
 
+static void dropGraphs(Context& c);
 int b200phys_destroy(b200phys_context* ctx)
 {
     if (!ctx) return B200PHYS_E_INVALID;
     cudaSetDevice(ctx->c.device);
     cudaDeviceSynchronize();
+    dropGraphs(ctx->c);
     destroyDist(&ctx->c);
     freeAll(ctx->c);
     delete ctx;
@@ -302,10 +305,10 @@ int b200phys_upload_joints(b200phys_context* ctx, int kind, const void* joints, 
     return 0;
 }
 
-int b200phys_step(b200phys_context* ctx, float dt, uint32_t numSolverIterations, uint32_t flags)
+// the stream operations of one step; every launch goes through launchK / memsetK (b200_context.h), so this body can be executed for
+// real, captured into a CUDA graph, or as a dry run that only hashes what it would enqueue
+static void enqueueStep(Context& c, float dt, uint32_t numSolverIterations, uint32_t flags)
 {
-    if (!ctx || !(dt > 0.f)) return B200PHYS_E_INVALID;
-    Context& c = ctx->c; CK(cudaSetDevice(c.device));
     c.launches = 0; c.numMarks = 0;
     if (c.timing) cudaEventRecord(c.ev[0], c.stream);
     timelineMark(&c, "begin");
@@ -327,7 +330,84 @@ int b200phys_step(b200phys_context* ctx, float dt, uint32_t numSolverIterations,
     timelineMark(&c, "integrate_velocities");
     if (c.timing) cudaEventRecord(c.ev[6], c.stream);
     c.stepped = true;
-    CK(cudaGetLastError());
+}
+
+// CUDA graph replay. A step is ~40-50 small launches; at 1 024 bodies the host cannot issue them as fast as the GPU retires them.
+// The launch sequence depends on host state with a period of a few steps (colour inheritance age, ping-pong buffers, event parity),
+// so a step is first run DRY: the same code advances the host state and hashes every kernel / geometry / argument value it would
+// enqueue. A hash seen for the second time is captured (the host state is rewound for that), later occurrences are replayed with one
+// cudaGraphLaunch. Nothing is assumed about what the step depends on: whatever changes an argument changes the hash.
+struct GraphEntry { cudaGraphExec_t exec = nullptr; uint32_t seen = 0; uint32_t launches = 0; };
+typedef std::unordered_map<unsigned long long, GraphEntry> GraphCache;
+static const size_t kMaxGraphs = 256;
+
+static void dropGraphs(Context& c)
+{
+    GraphCache* cache = (GraphCache*)c.graphCache;
+    if (!cache) return;
+    for (auto& kv : *cache) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    delete cache; c.graphCache = nullptr;
+}
+
+int b200phys_step(b200phys_context* ctx, float dt, uint32_t numSolverIterations, uint32_t flags)
+{
+    if (!ctx || !(dt > 0.f)) return B200PHYS_E_INVALID;
+    Context& c = ctx->c; CK(cudaSetDevice(c.device));
+    static int graphsWanted = -1;
+    if (graphsWanted < 0) { const char* e = getenv("B200PHYS_GRAPH"); graphsWanted = (e && e[0] == '0') ? 0 : 1; }
+    if (!graphsWanted || c.graphFailed || c.timing)
+    {
+        enqueueStep(c, dt, numSolverIterations, flags);
+        CK(cudaGetLastError());
+        return 0;
+    }
+    // cross-stream dependency of the accumulator upload: taken up front (a graph is captured from one stream)
+    if (c.forcesPending) waitPendingForceUpload(&c);
+    const Context saved = c;
+    c.graphMode = 1; c.graphHash = 1469598103934665603ull;
+    graphHashValue(&c, dt); graphHashValue(&c, numSolverIterations); graphHashValue(&c, flags); graphHashValue(&c, (const void*)c.stream);
+    enqueueStep(c, dt, numSolverIterations, flags);
+    const unsigned long long key = c.graphHash;
+    c.graphMode = 0;
+    if (!c.graphCache) c.graphCache = new GraphCache();
+    if (((GraphCache*)c.graphCache)->size() > kMaxGraphs) { dropGraphs(c); c.graphCache = new GraphCache(); }      // scenes that keep changing: start over
+    GraphEntry& entry = (*(GraphCache*)c.graphCache)[key];
+    if (entry.exec)
+    {   // the host state has already advanced past this step
+        CK(cudaGraphLaunch(entry.exec, c.stream));
+        ++c.graphReplays;
+        return 0;
+    }
+    // not captured yet: rewind the host state and enqueue for real
+    const uint32_t replays = c.graphReplays, captures = c.graphCaptures; void* const cachePtr = c.graphCache;
+    c = saved; c.graphReplays = replays; c.graphCaptures = captures; c.graphCache = cachePtr;
+    if (++entry.seen < 2)
+    {
+        enqueueStep(c, dt, numSolverIterations, flags);
+        CK(cudaGetLastError());
+        return 0;
+    }
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamBeginCapture(c.stream, cudaStreamCaptureModeRelaxed);
+    if (e == cudaSuccess)
+    {
+        enqueueStep(c, dt, numSolverIterations, flags);
+        e = cudaStreamEndCapture(c.stream, &graph);
+    }
+    if (e == cudaSuccess && graph) e = cudaGraphInstantiate(&entry.exec, graph, 0);
+    if (graph) cudaGraphDestroy(graph);
+    if (e != cudaSuccess || !entry.exec)
+    {   // capture is not possible here (e.g. a cooperative launch the driver refuses to capture): plain launches from now on
+        cudaGetLastError();
+        entry.exec = nullptr; c.graphFailed = true;
+        const uint32_t r2 = c.graphReplays, c2 = c.graphCaptures;
+        c = saved; c.graphReplays = r2; c.graphCaptures = c2; c.graphCache = cachePtr; c.graphFailed = true;
+        enqueueStep(c, dt, numSolverIterations, flags);
+        CK(cudaGetLastError());
+        return 0;
+    }
+    ++c.graphCaptures;
+    CK(cudaGraphLaunch(entry.exec, c.stream));
     return 0;
 }
 
@@ -456,7 +536,7 @@ int b200phys_get_stats(b200phys_context* ctx, b200phys_stats* out)
     const DeviceCounts& d = *c.hostCounts;
     memset(out, 0, sizeof(*out));
     out->numBodies = c.numBodies; out->numColliders = c.numColliders; out->reserved[1] = c.numOwnedBodies; out->reserved[2] = c.numOwnedColliders; out->reserved[3] = c.numNonCollisionColliders ? d.numInteractions : 0u;
-    out->reserved[4] = d.numEpaWork; out->reserved[5] = d.numEpaRedo;
+    out->reserved[4] = d.numEpaWork; out->reserved[5] = d.numEpaRedo; out->reserved[6] = c.graphReplays; out->reserved[0] = c.graphCaptures;
     out->numBroadphaseOverlaps = d.numPairs; out->numCollisions = d.numManifolds; out->numContacts = d.numContacts;
     out->numBigColliders = d.numBigNow; out->numGridCells = d.grid.numCells;
     for (int g = 0; g < 7; ++g) out->numColors[g] = d.numColors[g];

@@ -290,7 +290,7 @@ void launchUnpackBodies(Context* c, const void* dev, uint32_t count)
 {
     if (!count) return;
     const uint32_t stride = c->cfg.maxBodies + 1;
-    unpackBodiesKernel<<<gridFor(c, 4), kThreads, 0, c->stream>>>((const float*)dev, count, c->bRot, c->bPos, c->bCog, c->bInvI, c->bVel, c->bAng, c->bForce, c->bTorque, stride);
+    launchK(c, unpackBodiesKernel, gridFor(c, 4), kThreads, 0, (const float*)dev, count, c->bRot, c->bPos, c->bCog, c->bInvI, c->bVel, c->bAng, c->bForce, c->bTorque, stride);
     c->launches++;
 }
 void waitPendingForceUpload(Context* c)
@@ -306,37 +306,37 @@ void launchUnpackForces(Context* c, const void* dev, uint32_t count, cudaStream_
 void launchUnpackBodyStates(Context* c, const void* dev, uint32_t count)
 {
     if (!count) return;
-    unpackBodyStatesKernel<<<gridFor(c, 4), kThreads, 0, c->stream>>>((const float*)dev, count, c->bRot, c->bPos, c->bVel, c->bAng);
+    launchK(c, unpackBodyStatesKernel, gridFor(c, 4), kThreads, 0, (const float*)dev, count, c->bRot, c->bPos, c->bVel, c->bAng);
     c->launches++;
 }
 void launchPackBodyStates(Context* c, void* dev, uint32_t count)
 {
     if (!count) return;
-    packBodyStatesKernel<<<gridFor(c, 4), kThreads, 0, c->stream>>>((float*)dev, count, c->bRot, c->bPos, c->bVel, c->bAng);
+    launchK(c, packBodyStatesKernel, gridFor(c, 4), kThreads, 0, (float*)dev, count, c->bRot, c->bPos, c->bVel, c->bAng);
     c->launches++;
 }
 void launchIntegrateForces(Context* c, float dt)
 {
     const uint32_t stride = c->cfg.maxBodies + 1;
-    integrateForcesKernel<<<gridFor(c, 8), kThreads, 0, c->stream>>>(c->numBodies, dt, stride, c->globalForce[0], c->globalForce[1], c->globalForce[2], c->bRot, c->bPos, c->bCog, c->bInvI, c->bVel, c->bAng, c->bForce, c->bTorque, c->gVel, c->gPos, c->gInvI);
+    launchK(c, integrateForcesKernel, gridFor(c, 8), kThreads, 0, c->numBodies, dt, stride, c->globalForce[0], c->globalForce[1], c->globalForce[2], c->bRot, c->bPos, c->bCog, c->bInvI, c->bVel, c->bAng, c->bForce, c->bTorque, c->gVel, c->gPos, c->gInvI);
     c->launches++;
 }
 void launchWorldColliders(Context* c)
 {
     if (!c->numColliders) return;
-    worldCollidersKernel<<<gridFor(c, 8), kThreads, 0, c->stream>>>(c->numColliders, c->numBodies, c->cLocal, c->xforms, c->bRot, c->bPos, c->hullAabb, c->wCol, c->aabbMin, c->aabbMax);
+    launchK(c, worldCollidersKernel, gridFor(c, 8), kThreads, 0, c->numColliders, c->numBodies, c->cLocal, c->xforms, c->bRot, c->bPos, c->hullAabb, c->wCol, c->aabbMin, c->aabbMax);
     c->launches++;
 }
 void launchIntegrateVelocities(Context* c, float dt)
 {
     if (!c->numBodies) return;
-    integrateVelocitiesKernel<<<gridFor(c, 8), kThreads, 0, c->stream>>>(c->numBodies, dt, c->gVel, c->gPos, c->bCog, c->bRot, c->bPos, c->bVel, c->bAng, c->bForce, c->bTorque);
+    launchK(c, integrateVelocitiesKernel, gridFor(c, 8), kThreads, 0, c->numBodies, dt, c->gVel, c->gPos, c->bCog, c->bRot, c->bPos, c->bVel, c->bAng, c->bForce, c->bTorque);
     c->launches++;
 }
 void launchPackAabbs(Context* c, float* devOut)
 {
     if (!c->numColliders) return;
-    packAabbsKernel<<<gridFor(c, 4), kThreads, 0, c->stream>>>(c->numColliders, c->aabbMin, c->aabbMax, devOut);
+    launchK(c, packAabbsKernel, gridFor(c, 4), kThreads, 0, c->numColliders, c->aabbMin, c->aabbMax, devOut);
     c->launches++;
 }
 

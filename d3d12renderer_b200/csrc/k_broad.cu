@@ -732,36 +732,36 @@ void launchBroadphase(Context* c)
     const uint32_t tilesMode = (uint32_t)tilesEnv;
     if (C == 0)
     {
-        bpPrimeFinishKernel<<<1, 32, 0, c->stream>>>(bigFactor, c->cfg.cellSize, cnt);
-        bpSetupKernel<<<1, 32, 0, c->stream>>>(c->maxCells, bigFactor, c->cfg.cellSize, cellDiv, kWarpCand, tilesMode, cnt);
+        launchK(c, bpPrimeFinishKernel, 1, 32, 0, bigFactor, c->cfg.cellSize, cnt);
+        launchK(c, bpSetupKernel, 1, 32, 0, c->maxCells, bigFactor, c->cfg.cellSize, cellDiv, kWarpCand, tilesMode, cnt);
         c->launches += 2; c->bpPrimed = false;
         return;
     }
     if (!c->bpPrimed)
     {   // no threshold from a previous step yet (first step, or colliders were uploaded)
-        bpPrimeFinishKernel<<<1, 32, 0, c->stream>>>(bigFactor, c->cfg.cellSize, cnt);       // clears the accumulators
-        bpPrimeKernel<<<G, kThreads, 0, c->stream>>>(C, c->aabbMin, c->aabbMax, cnt);
-        bpPrimeFinishKernel<<<1, 32, 0, c->stream>>>(bigFactor, c->cfg.cellSize, cnt);
+        launchK(c, bpPrimeFinishKernel, 1, 32, 0, bigFactor, c->cfg.cellSize, cnt);       // clears the accumulators
+        launchK(c, bpPrimeKernel, G, kThreads, 0, C, c->aabbMin, c->aabbMax, cnt);
+        launchK(c, bpPrimeFinishKernel, 1, 32, 0, bigFactor, c->cfg.cellSize, cnt);
         c->launches += 3; c->bpPrimed = true;
     }
-    bpClassifyKernel<<<G, kThreads, 0, c->stream>>>(C, c->aabbMin, c->aabbMax, c->cellOf, c->bigList, cnt);
-    bpSetupKernel<<<1, 32, 0, c->stream>>>(c->maxCells, bigFactor, c->cfg.cellSize, cellDiv, kWarpCand, tilesMode, cnt);
-    bpBinKernel<<<G, kThreads, 0, c->stream>>>(C, c->aabbMin, c->aabbMax, c->cellOf, c->rankInCell, c->cellCount, cnt);
+    launchK(c, bpClassifyKernel, G, kThreads, 0, C, c->aabbMin, c->aabbMax, c->cellOf, c->bigList, cnt);
+    launchK(c, bpSetupKernel, 1, 32, 0, c->maxCells, bigFactor, c->cfg.cellSize, cellDiv, kWarpCand, tilesMode, cnt);
+    launchK(c, bpBinKernel, G, kThreads, 0, C, c->aabbMin, c->aabbMax, c->cellOf, c->rankInCell, c->cellCount, cnt);
     c->launches += 3;
     scanExclusiveU32(c, c->cellCount, c->cellStart, &cnt->grid.numCells, c->maxCells, nullptr, /*clearInput*/ true);
-    bpScatterKernel<<<G, kThreads, 0, c->stream>>>(C, c->aabbMin, c->aabbMax, c->cellOf, c->rankInCell, c->cellStart, c->bpRec, c->pairCount);
+    launchK(c, bpScatterKernel, G, kThreads, 0, C, c->aabbMin, c->aabbMax, c->cellOf, c->rankInCell, c->cellStart, c->bpRec, c->pairCount);
     timelineMark(c, "bp_build");
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(bpTileKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileCtaShared)); attr = true; }
     const uint32_t tileCtas = (uint32_t)c->numSMs * 4u, bigCtas = (uint32_t)c->numSMs;
-    bpTileKernel<<<tileCtas + bigCtas, kTileThreads, sizeof(TileCtaShared), c->stream>>>(C, tileCtas, numChunks, c->bpRec, c->cellStart, c->aabbMin, c->aabbMax, c->bigList,
+    launchK(c, bpTileKernel, tileCtas + bigCtas, kTileThreads, sizeof(TileCtaShared), C, tileCtas, numChunks, c->bpRec, c->cellStart, c->aabbMin, c->aabbMax, c->bigList,
                                                                                       c->pairCount, c->bpRows, c->cellOf, c->bpBigChunks, cnt);
-    bpRowsDirectKernel<<<gridFor(c, 6), kDirectThreads, 0, c->stream>>>(C, c->bpRec, c->cellStart, c->aabbMin, c->aabbMax, c->bigList, c->pairCount, c->bpRows, c->cellOf, cnt);
+    launchK(c, bpRowsDirectKernel, gridFor(c, 6), kDirectThreads, 0, C, c->bpRec, c->cellStart, c->aabbMin, c->aabbMax, c->bigList, c->pairCount, c->bpRows, c->cellOf, cnt);
     c->launches += 3;
     timelineMark(c, "bp_tiles");
     scanExclusiveU32(c, c->pairCount, c->pairStart, nullptr, C, nullptr);
     const uint32_t emitCtas = (uint32_t)c->numSMs * 6u, extraCtas = (uint32_t)c->numSMs * 2u;
-    bpEmitKernel<<<emitCtas + extraCtas, kThreads, 0, c->stream>>>(C, emitCtas, numChunks, c->rankInCell, c->bpRows, c->pairCount, c->pairStart, c->bpRec, c->cellStart,
+    launchK(c, bpEmitKernel, emitCtas + extraCtas, kThreads, 0, C, emitCtas, numChunks, c->rankInCell, c->bpRows, c->pairCount, c->pairStart, c->bpRec, c->cellStart,
                                                                   c->aabbMin, c->aabbMax, c->bigList, c->cellOf, c->bpBigChunks, c->pairs, c->maxPairs, cnt);
     c->launches += 1;
     timelineMark(c, "bp_emit");

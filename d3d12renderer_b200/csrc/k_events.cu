@@ -97,14 +97,14 @@ void launchCollisionEvents(Context* c)
     const int G = gridFor(c, 4);
     unsigned long long* keysCur = c->evKeys[c->evParity]; unsigned long long* keysPrev = c->evKeys[c->evParity ^ 1];
     uint2* pairsCur = c->evPairs[c->evParity]; uint2* pairsPrev = c->evPairs[c->evParity ^ 1];
-    evKeysKernel<<<G, kThreads, 0, c->stream>>>(c->collisions, c->wCol, keysCur, pairsCur, cnt);
-    evDiffKernel<<<G, kThreads, 0, c->stream>>>(keysCur, keysPrev, c->evFlag[0], c->evFlag[1], cnt);
+    launchK(c, evKeysKernel, G, kThreads, 0, c->collisions, c->wCol, keysCur, pairsCur, cnt);
+    launchK(c, evDiffKernel, G, kThreads, 0, keysCur, keysPrev, c->evFlag[0], c->evFlag[1], cnt);
     c->launches += 2;
     scanExclusiveU32(c, c->evFlag[0], c->evSlot[0], &cnt->numManifolds, c->maxManifolds, nullptr);
     scanExclusiveU32(c, c->evFlag[1], c->evSlot[1], &cnt->numPrevCollisions, c->maxManifolds, nullptr);
-    evEmitKernel<<<G, kThreads, 0, c->stream>>>(c->evFlag[0], c->evSlot[0], c->evFlag[1], c->evSlot[1], c->collisions, pairsPrev, c->manifolds, c->contacts, c->gVel, c->gPos,
+    launchK(c, evEmitKernel, G, kThreads, 0, c->evFlag[0], c->evSlot[0], c->evFlag[1], c->evSlot[1], c->collisions, pairsPrev, c->manifolds, c->contacts, c->gVel, c->gPos,
                                                 c->evBegin, c->evEnd, cnt);
-    evFinishKernel<<<1, 32, 0, c->stream>>>(c->evSlot[0], c->evSlot[1], cnt);
+    launchK(c, evFinishKernel, 1, 32, 0, c->evSlot[0], c->evSlot[1], cnt);
     c->launches += 2;
     c->evParity ^= 1;
 }

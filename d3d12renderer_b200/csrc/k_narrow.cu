@@ -541,17 +541,17 @@ void launchNarrowphase(Context* c)
 {
     DeviceCounts* cnt = c->counts;
     const int G = gridFor(c, 8);
-    npClassifyKernel<<<G, kThreads, 0, c->stream>>>(c->pairs, c->wCol, c->pairKey, c->pairsTyped, cnt);
+    launchK(c, npClassifyKernel, G, kThreads, 0, c->pairs, c->wCol, c->pairKey, c->pairsTyped, cnt);
     c->launches += 1;
     stableSmallKeySort(c, c->pairKey, &cnt->numPairs, c->maxPairs, kNumPairKeys, c->pairDst, cnt->keyStart);
-    npPermuteKernel<<<G, kThreads, 0, c->stream>>>(c->pairsTyped, c->pairDst, c->pairsSorted, cnt);
+    launchK(c, npPermuteKernel, G, kThreads, 0, c->pairsTyped, c->pairDst, c->pairsSorted, cnt);
     timelineMark(c, "np_classify_sort");
-    npCollideKernel<0><<<G, 256, 0, c->stream>>>(c->pairsSorted, c->wCol, c->manTmp, c->manScan, c->maxPairs, cnt);
-    npCollideKernel<1><<<gridFor(c, 4), 128, 0, c->stream>>>(c->pairsSorted, c->wCol, c->manTmp, c->manScan, c->maxPairs, cnt);
+    launchK(c, npCollideKernel<0>, G, 256, 0, c->pairsSorted, c->wCol, c->manTmp, c->manScan, c->maxPairs, cnt);
+    launchK(c, npCollideKernel<1>, gridFor(c, 4), 128, 0, c->pairsSorted, c->wCol, c->manTmp, c->manScan, c->maxPairs, cnt);
     timelineMark(c, "np_closed_form_sat");
     static int gjkRefill = -1, epaRefill = -1;     // lanes that must be idle before a warp sets up new pairs (tuning: B200PHYS_GJK_REFILL / B200PHYS_EPA_REFILL)
     if (gjkRefill < 0) { const char* e = getenv("B200PHYS_GJK_REFILL"); gjkRefill = e ? atoi(e) : 16; e = getenv("B200PHYS_EPA_REFILL"); epaRefill = e ? atoi(e) : 16; }
-    npGjkKernel<<<gridFor(c, 8), 128, 0, c->stream>>>(c->pairsSorted, c->wCol, c->hullVerts, c->hullOffsets, c->manTmp, c->manScan, c->maxPairs, c->epaSimplex, c->epaWork, c->maxEpaWork, cnt, (uint32_t)gjkRefill);
+    launchK(c, npGjkKernel, gridFor(c, 8), 128, 0, c->pairsSorted, c->wCol, c->hullVerts, c->hullOffsets, c->manTmp, c->manScan, c->maxPairs, c->epaSimplex, c->epaWork, c->maxEpaWork, cnt, (uint32_t)gjkRefill);
     timelineMark(c, "np_gjk");
     static int epaMode = -1, epaBps = 0;
     {
@@ -563,50 +563,50 @@ void launchNarrowphase(Context* c)
             const size_t smem = (size_t)kEpaSmallWarps * B200_EPAS_WORDS * 32 * sizeof(uint32_t);
             static bool attr = false;
             if (!attr) { cudaFuncSetAttribute(npEpaSmallKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
-            npEpaSmallKernel<<<c->numSMs, kEpaSmallWarps * 32, smem, c->stream>>>(c->pairsSorted, c->wCol, c->hullVerts, c->hullOffsets, c->manTmp, c->manScan, c->maxPairs, c->epaSimplex, c->epaWork, c->maxEpaWork, cnt, c->epaRedo, (uint32_t)epaRefill);
+            launchK(c, npEpaSmallKernel, c->numSMs, kEpaSmallWarps * 32, smem, c->pairsSorted, c->wCol, c->hullVerts, c->hullOffsets, c->manTmp, c->manScan, c->maxPairs, c->epaSimplex, c->epaWork, c->maxEpaWork, cnt, c->epaRedo, (uint32_t)epaRefill);
             timelineMark(c, "np_epa");
             // the ones that outgrew it are the long runs (up to 20 expansions, ~100 triangles): a warp per pair (exact, see EpaWarp)
             static int redoThread = -1;
             if (redoThread < 0) { const char* e = getenv("B200PHYS_EPA_REDO"); redoThread = (e && e[0] == 't') ? 1 : 0; }
             if (redoThread)
-                npEpaKernel<<<gridFor(c, 2), 64, 0, c->stream>>>(c->pairsSorted, c->wCol, c->hullVerts, c->hullOffsets, c->manTmp, c->manScan, c->maxPairs, c->epaSimplex, c->epaWork, c->maxEpaWork, cnt, c->epaRedo);
+                launchK(c, npEpaKernel, gridFor(c, 2), 64, 0, c->pairsSorted, c->wCol, c->hullVerts, c->hullOffsets, c->manTmp, c->manScan, c->maxPairs, c->epaSimplex, c->epaWork, c->maxEpaWork, cnt, c->epaRedo);
             else
             {
                 const size_t wsmem = sizeof(EpaWarpShared) * kEpaWarpsPerCta;
                 static bool wattr = false;
                 if (!wattr) { cudaFuncSetAttribute(npEpaWarpKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem); wattr = true; }
-                npEpaWarpKernel<<<gridFor(c, 6), kEpaWarpsPerCta * 32, wsmem, c->stream>>>(c->pairsSorted, c->wCol, c->hullVerts, c->hullOffsets, c->manTmp, c->manScan, c->maxPairs, c->epaSimplex, c->epaWork, c->maxEpaWork, cnt, c->epaRedo);
+                launchK(c, npEpaWarpKernel, gridFor(c, 6), kEpaWarpsPerCta * 32, wsmem, c->pairsSorted, c->wCol, c->hullVerts, c->hullOffsets, c->manTmp, c->manScan, c->maxPairs, c->epaSimplex, c->epaWork, c->maxEpaWork, cnt, c->epaRedo);
             }
             c->launches += 1;
         }
         else if (epaMode == 0)
-            npEpaKernel<<<gridFor(c, epaBps > 0 ? epaBps : 8), 128, 0, c->stream>>>(c->pairsSorted, c->wCol, c->hullVerts, c->hullOffsets, c->manTmp, c->manScan, c->maxPairs, c->epaSimplex, c->epaWork, c->maxEpaWork, cnt, nullptr);
+            launchK(c, npEpaKernel, gridFor(c, epaBps > 0 ? epaBps : 8), 128, 0, c->pairsSorted, c->wCol, c->hullVerts, c->hullOffsets, c->manTmp, c->manScan, c->maxPairs, c->epaSimplex, c->epaWork, c->maxEpaWork, cnt, nullptr);
         else
         {
             const size_t smem = sizeof(EpaWarpShared) * kEpaWarpsPerCta;
             static bool attr = false;
             if (!attr) { cudaFuncSetAttribute(npEpaWarpKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
-            npEpaWarpKernel<<<gridFor(c, epaBps > 0 ? epaBps : 6), kEpaWarpsPerCta * 32, smem, c->stream>>>(c->pairsSorted, c->wCol, c->hullVerts, c->hullOffsets, c->manTmp, c->manScan, c->maxPairs, c->epaSimplex, c->epaWork, c->maxEpaWork, cnt, nullptr);
+            launchK(c, npEpaWarpKernel, gridFor(c, epaBps > 0 ? epaBps : 6), kEpaWarpsPerCta * 32, smem, c->pairsSorted, c->wCol, c->hullVerts, c->hullOffsets, c->manTmp, c->manScan, c->maxPairs, c->epaSimplex, c->epaWork, c->maxEpaWork, cnt, nullptr);
         }
     }
     c->launches += 1;
     timelineMark(c, epaMode == 2 ? "np_epa_redo" : "np_epa");
-    npClearTailKernel<<<G, kThreads, 0, c->stream>>>(c->manScan, cnt);
+    launchK(c, npClearTailKernel, G, kThreads, 0, c->manScan, cnt);
     c->launches += 5;
     scanExclusiveU64(c, c->manScan, c->manScanOut, &cnt->numPairs, c->maxPairs, nullptr);
     // rigid body vs trigger / force field: boolean overlap tests, compaction, force-field push (physics.cpp:1255, before the force integration)
     if (c->numNonCollisionColliders)
     {
         uint32_t* ovFlags = c->pairDst; uint32_t* ovSlots = (uint32_t*)c->pairsTyped;   // both free between the bucket sort and the solver
-        npOverlapKernel<<<gridFor(c, 4), 128, 0, c->stream>>>(c->pairsSorted, c->wCol, c->hullVerts, c->hullOffsets, ovFlags, cnt);
+        launchK(c, npOverlapKernel, gridFor(c, 4), 128, 0, c->pairsSorted, c->wCol, c->hullVerts, c->hullOffsets, ovFlags, cnt);
         c->launches++;
         scanExclusiveU32(c, ovFlags, ovSlots, &cnt->numOverlapPairs, c->maxPairs, nullptr);
-        npInteractionKernel<<<G, kThreads, 0, c->stream>>>(c->pairsSorted, c->wCol, ovFlags, ovSlots, c->interactions, c->maxInteractions, c->forceFields, c->numForceFields,
+        launchK(c, npInteractionKernel, G, kThreads, 0, c->pairsSorted, c->wCol, ovFlags, ovSlots, c->interactions, c->maxInteractions, c->forceFields, c->numForceFields,
                                                            c->bForce, c->numBodies, cnt);
         c->launches++;
     }
-    npTotalsKernel<<<1, 32, 0, c->stream>>>(c->manScanOut, c->maxManifolds, c->maxContacts, cnt);
-    npCompactKernel<<<G, kThreads, 0, c->stream>>>(c->pairsSorted, c->wCol, c->manTmp, c->manScan, c->manScanOut, c->maxPairs, c->maxManifolds, c->maxContacts,
+    launchK(c, npTotalsKernel, 1, 32, 0, c->manScanOut, c->maxManifolds, c->maxContacts, cnt);
+    launchK(c, npCompactKernel, G, kThreads, 0, c->pairsSorted, c->wCol, c->manTmp, c->manScan, c->manScanOut, c->maxPairs, c->maxManifolds, c->maxContacts,
                                                    c->collisions, c->manifolds, c->contacts, c->contactBodies, cnt);
     c->launches += 2;
     timelineMark(c, "np_compact");

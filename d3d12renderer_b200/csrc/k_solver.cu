@@ -16,6 +16,7 @@
 // HBM traffic per contact and iteration: one 128-byte row (8 coalesced 128-bit planes) + 8 B impulses read/written +
 // two 32-byte body records gathered and scattered (the only per-body data the iterations touch).
 #include "b200_context.h"
+#include <cstring>
 #include "b200_util.cuh"
 #include "k_joints.cuh"
 #include <cstdlib>
@@ -694,14 +695,14 @@ static void colorGroup(Context* c, uint32_t group, const uint2* unitBodies, cons
     uint32_t* posOf = c->unitPending;      // scratch, one word per unit
     const uint32_t N = c->numBodies;
     const int G = gridFor(c, 8);
-    cudaMemsetAsync(c->adjFill, 0, sizeof(uint32_t) * (N + 2), c->stream);
-    cudaMemsetAsync(c->adjStart, 0, sizeof(uint32_t) * (N + 2), c->stream);
+    memsetK(c, c->adjFill, 0, sizeof(uint32_t) * (N + 2));
+    memsetK(c, c->adjStart, 0, sizeof(uint32_t) * (N + 2));
     uint32_t* adjCount = c->adjFill;   // counts are built in adjFill, scanned into adjStart, then adjFill is re-zeroed as the fill cursor
-    adjCountKernel<<<G, kThreads, 0, c->stream>>>(unitBodies, numUnitsDev, c->gPos, N, adjCount);
+    launchK(c, adjCountKernel, G, kThreads, 0, unitBodies, numUnitsDev, c->gPos, N, adjCount);
     c->launches++;
     scanExclusiveU32(c, adjCount, c->adjStart, nullptr, N + 1, nullptr);
-    cudaMemsetAsync(c->adjFill, 0, sizeof(uint32_t) * (N + 2), c->stream);
-    adjFillKernel<<<G, kThreads, 0, c->stream>>>(unitBodies, numUnitsDev, c->gPos, N, c->adjStart, c->adjFill, c->adjList);
+    memsetK(c, c->adjFill, 0, sizeof(uint32_t) * (N + 2));
+    launchK(c, adjFillKernel, G, kThreads, 0, unitBodies, numUnitsDev, c->gPos, N, c->adjStart, c->adjFill, c->adjList);
     c->launches++;
 
     DeviceCounts* cnt = c->counts;
@@ -709,7 +710,7 @@ static void colorGroup(Context* c, uint32_t group, const uint2* unitBodies, cons
     if (mode == 3)
     {   // colours inherited from the previous step (colorInheritKernel ran before): stable sort by colour, rank by position
         stableSmallKeySort(c, c->colorKey, numUnitsDev, maxUnits, kMaxColors, posOf, cnt->colorStart[group]);
-        orderFromPosKernel<<<G, kThreads, 0, c->stream>>>(numUnitsDev, posOf, order);
+        launchK(c, orderFromPosKernel, G, kThreads, 0, numUnitsDev, posOf, order);
         c->launches++;
     }
     else if (mode == 0)
@@ -717,23 +718,23 @@ static void colorGroup(Context* c, uint32_t group, const uint2* unitBodies, cons
         uint32_t* colorCount = c->levelFill + (kMaxLevels + 1);   // kMaxColors entries used
         uint32_t* colorFill = c->levelFill + 2 * (kMaxLevels + 1);
         uint32_t* queue = c->colorQueue;
-        cudaMemsetAsync(colorCount, 0, sizeof(uint32_t) * kMaxColors, c->stream);
-        cudaMemsetAsync(colorFill, 0, sizeof(uint32_t) * kMaxColors, c->stream);
-        colorQueueResetKernel<<<G, kThreads, 0, c->stream>>>(numUnitsDev, queue, cnt);
-        colorInitKernel<<<G, kThreads, 0, c->stream>>>(unitBodies, numUnitsDev, c->gPos, N, c->adjStart, c->adjList, color, c->unitForbid, c->nbrCount, c->nbrList, queue, cnt);
-        colorRunKernel<<<c->numSMs * 4, kColorRunThreads, 0, c->stream>>>(group, unitBodies, numUnitsDev, c->gPos, N, c->adjStart, c->adjList, color, c->unitForbid, c->nbrCount, c->nbrList, queue, colorCount, cnt);
-        colorScanKernel<<<1, 32, 0, c->stream>>>(group, colorCount, colorStartOut, cnt);
-        colorScatterKernel<<<G, kThreads, 0, c->stream>>>(unitBodies, numUnitsDev, color, c->gPos, N, colorStartOut, colorFill, order, c->bodyMask);
+        memsetK(c, colorCount, 0, sizeof(uint32_t) * kMaxColors);
+        memsetK(c, colorFill, 0, sizeof(uint32_t) * kMaxColors);
+        launchK(c, colorQueueResetKernel, G, kThreads, 0, numUnitsDev, queue, cnt);
+        launchK(c, colorInitKernel, G, kThreads, 0, unitBodies, numUnitsDev, c->gPos, N, c->adjStart, c->adjList, color, c->unitForbid, c->nbrCount, c->nbrList, queue, cnt);
+        launchK(c, colorRunKernel, c->numSMs * 4, kColorRunThreads, 0, group, unitBodies, numUnitsDev, c->gPos, N, c->adjStart, c->adjList, color, c->unitForbid, c->nbrCount, c->nbrList, queue, colorCount, cnt);
+        launchK(c, colorScanKernel, 1, 32, 0, group, colorCount, colorStartOut, cnt);
+        launchK(c, colorScatterKernel, G, kThreads, 0, unitBodies, numUnitsDev, color, c->gPos, N, colorStartOut, colorFill, order, c->bodyMask);
         c->launches += 5;
     }
     else
     {
-        orderKernel<<<G, kThreads, 0, c->stream>>>(mode, numUnitsDev, order);
+        launchK(c, orderKernel, G, kThreads, 0, mode, numUnitsDev, order);
         c->launches++;
     }
     // dataflow records of this group (rank / degree of every unit at its bodies), then fold the group into the per-body totals
-    depRankKernel<<<G, kThreads, 0, c->stream>>>(mode, posOf, unitBodies, numUnitsDev, color, order, c->gPos, N, c->bodyMask, c->bodyBase, c->adjStart, c->adjList, c->unitDep[group]);
-    bodyBaseAddKernel<<<G, kThreads, 0, c->stream>>>(mode != 0, N, c->bodyMask, c->adjStart, c->bodyBase, cnt);
+    launchK(c, depRankKernel, G, kThreads, 0, mode, posOf, unitBodies, numUnitsDev, color, order, c->gPos, N, c->bodyMask, c->bodyBase, c->adjStart, c->adjList, c->unitDep[group]);
+    launchK(c, bodyBaseAddKernel, G, kThreads, 0, mode != 0, N, c->bodyMask, c->adjStart, c->bodyBase, cnt);
     c->launches += 2;
     (void)maxUnits;
 }
@@ -744,15 +745,15 @@ void launchSolver(Context* c, float dt, uint32_t iterations, uint32_t flags)
     const int G = gridFor(c, 8);
     const bool exact = (flags & B200PHYS_STEP_EXACT_ORDER) != 0;
     const bool permuted = !exact && (flags & B200PHYS_STEP_PERMUTED) != 0;
-    JointCounts jc; for (int k = 0; k < 6; ++k) jc.n[k] = c->numJoints[k];
-    solverResetKernel<<<1, 32, 0, c->stream>>>(cnt, jc);
+    JointCounts jc; memset(&jc, 0, sizeof(jc)); for (int k = 0; k < 6; ++k) jc.n[k] = c->numJoints[k];
+    launchK(c, solverResetKernel, 1, 32, 0, cnt, jc);
     c->launches++;
-    cudaMemsetAsync(c->bodyMask, 0, sizeof(unsigned long long) * (c->numBodies + 2), c->stream);
-    cudaMemsetAsync(c->bodyBase, 0, sizeof(uint32_t) * (c->numBodies + 2), c->stream);
+    memsetK(c, c->bodyMask, 0, sizeof(unsigned long long) * (c->numBodies + 2));
+    memsetK(c, c->bodyBase, 0, sizeof(uint32_t) * (c->numBodies + 2));
 
     // ---- joints: colour each kind, initialise rows
-    JointSolveArgs ja;
-    JointInitArgs ji;
+    JointSolveArgs ja; memset(&ja, 0, sizeof(ja));      // padding bytes are part of the step hash (launchK)
+    JointInitArgs ji; memset(&ji, 0, sizeof(ji));
     bool anyJoint = false;
     for (int k = 0; k < 6; ++k)
     {
@@ -764,23 +765,23 @@ void launchSolver(Context* c, float dt, uint32_t iterations, uint32_t flags)
             // the joint graph only changes when joints are uploaded with a different count: colour it once, then inherit
             const bool fast = !exact && !permuted;
             const bool inheritJ = fast && c->jointColorCount[k] == c->numJoints[k] && c->jointColorAge[k] > 0 && c->jointColorAge[k] < 64;
-            if (inheritJ) { jointColorCopyKernel<<<G, kThreads, 0, c->stream>>>(0, &cnt->numJoints[k], c->unitColor[k], c->colorKey, c->refColorsJoint[k]); c->launches++; }
+            if (inheritJ) { launchK(c, jointColorCopyKernel, G, kThreads, 0, 0, &cnt->numJoints[k], c->unitColor[k], c->colorKey, c->refColorsJoint[k]); c->launches++; }
             colorGroup(c, (uint32_t)k, c->jointBodies[k], &cnt->numJoints[k], c->numJoints[k], exact, permuted, inheritJ, c->unitColor[k], c->unitOrder[k],
                        c->levelStart + (size_t)k * (kMaxLevels + 1), (uint32_t)k);
-            if (fast && !inheritJ) { jointColorCopyKernel<<<G, kThreads, 0, c->stream>>>(1, &cnt->numJoints[k], c->unitColor[k], c->colorKey, c->refColorsJoint[k]); c->launches++; c->jointColorCount[k] = c->numJoints[k]; c->jointColorAge[k] = 0; }
+            if (fast && !inheritJ) { launchK(c, jointColorCopyKernel, G, kThreads, 0, 1, &cnt->numJoints[k], c->unitColor[k], c->colorKey, c->refColorsJoint[k]); c->launches++; c->jointColorCount[k] = c->numJoints[k]; c->jointColorAge[k] = 0; }
             if (fast) ++c->jointColorAge[k]; else c->jointColorAge[k] = 0;
         }
     }
     if (anyJoint)
     {
         ji.bRot = c->bRot; ji.bCog = c->bCog; ji.gPos = c->gPos; ji.gVel = c->gVel; ji.gInvI = c->gInvI; ji.N = c->numBodies; ji.dt = dt; ji.cnt = cnt;
-        initJointsKernel<<<gridFor(c, 4), 128, 0, c->stream>>>(ji);
+        launchK(c, initJointsKernel, gridFor(c, 4), 128, 0, ji);
         c->launches++;
     }
 
     // ---- contacts
     uint2* unitBodies = (uint2*)c->pairsTyped;     // scratch reuse: the typed pair list is dead after the bucket sort
-    manifoldBodiesKernel<<<G, kThreads, 0, c->stream>>>(c->manifolds, unitBodies, cnt);
+    launchK(c, manifoldBodiesKernel, G, kThreads, 0, c->manifolds, unitBodies, cnt);
     c->launches++;
     uint32_t* contactColorStart = c->levelStart + (size_t)6 * (kMaxLevels + 1);
     // colour reuse: a full colouring every `recolorEvery` steps, inherited colours in between (fast mode only)
@@ -792,15 +793,15 @@ void launchSolver(Context* c, float dt, uint32_t iterations, uint32_t flags)
     bool inherit = false;
     if (fastColored)
     {
-        manifoldKeysKernel<<<G, kThreads, 0, c->stream>>>(c->collisions, c->wCol, keysCur, cnt);
+        launchK(c, manifoldKeysKernel, G, kThreads, 0, c->collisions, c->wCol, keysCur, cnt);
         c->launches++;
         inherit = c->colorAge > 0 && c->colorAge < every;
-        if (inherit) { colorInheritKernel<<<G, kThreads, 0, c->stream>>>(keysCur, keysRef, c->refColors, c->colorKey, c->unitColor[6], cnt); c->launches++; }
+        if (inherit) { launchK(c, colorInheritKernel, G, kThreads, 0, keysCur, keysRef, c->refColors, c->colorKey, c->unitColor[6], cnt); c->launches++; }
     }
     colorGroup(c, 6, unitBodies, &cnt->numManifolds, c->maxManifolds, exact, permuted, inherit, c->unitColor[6], c->unitOrder[6], contactColorStart, 6);
     if (fastColored)
     {
-        colorRememberKernel<<<G, kThreads, 0, c->stream>>>(c->unitColor[6], c->refColors, cnt);
+        launchK(c, colorRememberKernel, G, kThreads, 0, c->unitColor[6], c->refColors, cnt);
         c->launches++;
         c->refParity ^= 1;
         c->colorAge = (c->colorAge + 1 >= every) ? 0 : c->colorAge + 1;
@@ -808,27 +809,27 @@ void launchSolver(Context* c, float dt, uint32_t iterations, uint32_t flags)
     else c->colorAge = 0;       // another mode ran: the remembered colours are stale
     timelineMark(c, "solver_order");
     uint32_t* slotCount = c->pairDst;              // scratch reuse
-    slotCountKernel<<<G, kThreads, 0, c->stream>>>(c->unitOrder[6], c->manifolds, slotCount, cnt);
+    launchK(c, slotCountKernel, G, kThreads, 0, c->unitOrder[6], c->manifolds, slotCount, cnt);
     c->launches++;
     scanExclusiveU32(c, slotCount, c->unitSlotStart, &cnt->numManifolds, c->maxManifolds, nullptr);
-    initContactRowsKernel<<<G, kThreads, 0, c->stream>>>(c->unitOrder[6], c->unitSlotStart, c->manifolds, c->contacts, c->gVel, c->gPos, c->gInvI,
+    launchK(c, initContactRowsKernel, G, kThreads, 0, c->unitOrder[6], c->unitSlotStart, c->manifolds, c->contacts, c->gVel, c->gPos, c->gInvI,
                                                          c->rows, c->rowImp, c->slotOfContact, c->unitInfo, c->maxContacts, dt, cnt);
     c->launches++;
 
     // ---- iterations
     if (anyJoint)
     {   // several groups: the degrees in the records of the earlier groups are partial until now
-        DepFinalizeArgs F;
+        DepFinalizeArgs F; memset(&F, 0, sizeof(F));
         for (uint32_t g = 0; g < kNumGroups; ++g)
         {
             const bool used = g == 6 || c->numJoints[g] != 0;
             F.unitBodies[g] = g == 6 ? unitBodies : c->jointBodies[g]; F.order[g] = c->unitOrder[g]; F.dep[g] = c->unitDep[g];
             F.numUnits[g] = !used ? nullptr : (g == 6 ? &cnt->numManifolds : &cnt->numJoints[g]);
         }
-        depFinalizeKernel<<<G, kThreads, 0, c->stream>>>(F, c->bodyBase);
+        launchK(c, depFinalizeKernel, G, kThreads, 0, F, c->bodyBase);
         c->launches++;
     }
-    SolveArgs A;
+    SolveArgs A; memset(&A, 0, sizeof(A));
     A.unitInfo = c->unitInfo; A.unitDep = c->unitDep[6]; A.rows = c->rows; A.rowImp = c->rowImp; A.maxContacts = c->maxContacts;
     A.joints = ja; A.gVel = c->gVel; A.gPos = c->gPos; A.gInvI = c->gInvI; A.cnt = cnt; A.iterations = iterations;
     void* args[] = { &A };
@@ -839,7 +840,8 @@ void launchSolver(Context* c, float dt, uint32_t iterations, uint32_t flags)
     void* fn = anyJoint ? (void*)solveKernel<true> : (void*)solveKernel<false>;
     if (!solveBlocksPerSM[variant]) { cudaOccupancyMaxActiveBlocksPerMultiprocessor(&solveBlocksPerSM[variant], fn, kSolveThreads, 0); if (solveBlocksPerSM[variant] < 1) solveBlocksPerSM[variant] = 1; if (solveBlocksPerSM[variant] > 1) solveBlocksPerSM[variant] = 1; }
     const int bps = solveBlocksPerSM[variant];
-    cudaLaunchCooperativeKernel(fn, dim3(c->numSMs * bps), dim3(kSolveThreads), args, 0, c->stream);
+    if (c->graphMode == 1) { graphHashValue(c, (const void*)fn); graphHashValue(c, c->numSMs * bps); graphHashBytes(c, &A, sizeof(A)); }
+    else cudaLaunchCooperativeKernel(fn, dim3(c->numSMs * bps), dim3(kSolveThreads), args, 0, c->stream);
     c->launches++;
     timelineMark(c, "solve");
 }

@@ -209,7 +209,8 @@ typedef struct b200phys_stats {
     uint32_t kernelLaunches;        /* kernels launched by the last step */
     uint32_t reserved[7];           /* [1], [2]: owned bodies / colliders (the rest are ghosts); [3]: overlapping rigid body vs trigger /
                                        force field interactions of the last step; [4]: EPA runs (GJK hits) of the last step,
-                                       [5]: those that outgrew the small shared-memory polytope and were re-run in the large one */
+                                       [5]: those that outgrew the small shared-memory polytope and were re-run in the large one;
+                                       [6] / [0]: steps replayed from / captured into a CUDA graph since the context was created */
 } b200phys_stats;
 
 typedef struct b200phys_context b200phys_context;
