@@ -82,7 +82,7 @@ class Stats(C.Structure):
 
 # every symbol include/b200phys.h declares (tests check that the library exports all of them)
 EXPORTS = [
-    "b200phys_version", "b200phys_error_string", "b200phys_create", "b200phys_destroy", "b200phys_set_stream", "b200phys_enable_timing",
+    "b200phys_version", "b200phys_error_string", "b200phys_create", "b200phys_destroy", "b200phys_set_stream", "b200phys_enable_timing", "b200phys_enable_graphs",
     "b200phys_host_alloc", "b200phys_host_free",
     "b200phys_set_hulls", "b200phys_upload_bodies", "b200phys_upload_transforms", "b200phys_upload_colliders", "b200phys_upload_joints",
     "b200phys_upload_forces", "b200phys_upload_body_states", "b200phys_step", "b200phys_synchronize", "b200phys_download_bodies", "b200phys_get_stats",
@@ -117,6 +117,7 @@ def load_library():
     lib.b200phys_destroy.argtypes = [vp]
     lib.b200phys_set_stream.argtypes = [vp, vp]
     lib.b200phys_enable_timing.argtypes = [vp, i32]
+    lib.b200phys_enable_graphs.argtypes = [vp, i32]
     lib.b200phys_host_alloc.restype = vp; lib.b200phys_host_alloc.argtypes = [C.c_size_t]
     lib.b200phys_host_free.restype = None; lib.b200phys_host_free.argtypes = [vp]
     lib.b200phys_set_hulls.argtypes = [vp, vp, vp, u32]
@@ -225,6 +226,9 @@ class Stepper:
 
     def enable_timing(self, on=True):
         _check(self.lib, self.lib.b200phys_enable_timing(self.ctx, 1 if on else 0), "enable_timing")
+
+    def enable_graphs(self, on=True):
+        _check(self.lib, self.lib.b200phys_enable_graphs(self.ctx, 1 if on else 0), "enable_graphs")
 
     def set_hulls(self, vertices, offsets):
         v = np.ascontiguousarray(vertices, dtype=np.float32); o = np.ascontiguousarray(offsets, dtype=np.uint32)

@@ -199,7 +199,7 @@ struct Context
     uint32_t maxPairs = 0, maxManifolds = 0, maxContacts = 0, maxJoints = 0, maxCells = 0;
 
     // CUDA graph replay of the step (b200phys_api.cu): 0 = launch, 1 = dry run that only hashes what would be launched
-    int graphMode = 0; unsigned long long graphHash = 0; void* graphCache = nullptr; bool graphFailed = false; uint32_t graphReplays = 0, graphCaptures = 0;
+    int graphMode = 0; unsigned long long graphHash = 0; void* graphCache = nullptr; bool graphFailed = false, graphsOff = false; uint32_t graphReplays = 0, graphCaptures = 0;
 
     // halo (multi-GPU)
     void* dist = nullptr;               // NCCL communicator + slab + message buffers of a context made by b200phys_create_distributed (k_dist.cu)

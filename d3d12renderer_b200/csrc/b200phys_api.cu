@@ -186,6 +186,7 @@ int b200phys_set_stream(b200phys_context* ctx, void* cudaStream)
 }
 
 int b200phys_enable_timing(b200phys_context* ctx, int enabled) { if (!ctx) return B200PHYS_E_INVALID; ctx->c.timing = enabled != 0; return 0; }
+int b200phys_enable_graphs(b200phys_context* ctx, int enabled) { if (!ctx) return B200PHYS_E_INVALID; ctx->c.graphsOff = enabled == 0; return 0; }
 
 int b200phys_set_hulls(b200phys_context* ctx, const float* vertices, const uint32_t* vertexOffsets, uint32_t numHulls)
 {
@@ -355,7 +356,7 @@ int b200phys_step(b200phys_context* ctx, float dt, uint32_t numSolverIterations,
     Context& c = ctx->c; CK(cudaSetDevice(c.device));
     static int graphsWanted = -1;
     if (graphsWanted < 0) { const char* e = getenv("B200PHYS_GRAPH"); graphsWanted = (e && e[0] == '0') ? 0 : 1; }
-    if (!graphsWanted || c.graphFailed || c.timing)
+    if (!graphsWanted || c.graphsOff || c.graphFailed || c.timing)
     {
         enqueueStep(c, dt, numSolverIterations, flags);
         CK(cudaGetLastError());

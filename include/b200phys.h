@@ -222,6 +222,9 @@ int b200phys_create(const b200phys_config* config, b200phys_context** out);  /* 
 int b200phys_destroy(b200phys_context* ctx);
 int b200phys_set_stream(b200phys_context* ctx, void* cudaStream);            /* run on the caller's stream (0 = own stream) */
 int b200phys_enable_timing(b200phys_context* ctx, int enabled);
+/* CUDA graph replay of b200phys_step (on by default; also off while timing is enabled or with B200PHYS_GRAPH=0 in the environment).
+ * The result of a step does not depend on it. */
+int b200phys_enable_graphs(b200phys_context* ctx, int enabled);
 /* page-locked host memory: uploads / downloads from such buffers are direct DMA transfers (optional, any host memory works) */
 void* b200phys_host_alloc(size_t bytes);
 void b200phys_host_free(void* p);

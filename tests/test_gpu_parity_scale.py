@@ -209,6 +209,26 @@ def test_contact_and_manifold_capacity_overflow_is_safe():
         assert np.array_equal(c["point"], fc["point"][:len(c)])
 
 
+# ------------------------------------------------------------------------------------------------ CUDA graph replay
+@pytest.mark.parametrize("config,dims,spacing,seed", [(host.CONFIG_MIXED_PILE, (10, 6, 10), 0.8, 1578123), (host.CONFIG_RAGDOLLS, (4, 1, 4), 1.6, 20260924)])
+def test_graph_replay_is_bit_identical_to_plain_launches(config, dims, spacing, seed):
+    """b200phys_step replays captured CUDA graphs (one per launch-sequence variant: colouring step, inherit steps with either key
+    buffer). 40 steps with replay and 40 steps of plain launches from the same state must end in the same bits, and the replay must
+    actually have happened."""
+    sc = host.build_scene(config, *dims, seed=seed, mode=0, spacing=spacing)
+    out = []
+    for graphs in (True, False):
+        st = make_stepper(sc)
+        st.enable_graphs(graphs)
+        for _ in range(40):
+            st.step(DT, 10, abi.STEP_FAST)
+        out.append(st.download_bodies().copy())
+        s = st.stats(check=False)
+        assert (s.reserved[6] > 20) == graphs, "replays: %d" % s.reserved[6]
+        st.close()
+    assert out[0].tobytes() == out[1].tobytes()
+
+
 # ------------------------------------------------------------------------------------------------ RL environment (f.3)
 def test_locomotion_env_matches_the_reference_environment():
     """The batched environment (host/locomotion_env.cpp over the CUDA step) against the reference's OWN environment, compiled from
