@@ -59,6 +59,10 @@ class Config(C.Structure):
                 ("cellSize", C.c_float), ("bigFactor", C.c_float), ("maxContacts", C.c_uint32), ("reserved", C.c_uint32 * 5)]
 
 
+class HeightmapDesc(C.Structure):
+    _fields_ = [("chunksPerDim", C.c_uint32), ("chunkSize", C.c_float), ("minCorner", C.c_float * 3), ("amplitudeScale", C.c_float), ("restitution", C.c_float), ("friction", C.c_float)]
+
+
 class DistConfig(C.Structure):
     _fields_ = [("rank", C.c_int32), ("nranks", C.c_int32), ("axis", C.c_int32), ("slabLo", C.c_float), ("slabHi", C.c_float), ("ghostWidth", C.c_float),
                 ("maxGhostBodies", C.c_uint32), ("maxGhostColliders", C.c_uint32)]
@@ -82,7 +86,7 @@ class Stats(C.Structure):
 
 # every symbol include/b200phys.h declares (tests check that the library exports all of them)
 EXPORTS = [
-    "b200phys_version", "b200phys_error_string", "b200phys_create", "b200phys_destroy", "b200phys_set_stream", "b200phys_enable_timing", "b200phys_enable_graphs",
+    "b200phys_version", "b200phys_error_string", "b200phys_create", "b200phys_destroy", "b200phys_set_stream", "b200phys_enable_timing", "b200phys_enable_graphs", "b200phys_upload_heightmap",
     "b200phys_host_alloc", "b200phys_host_free",
     "b200phys_set_hulls", "b200phys_upload_bodies", "b200phys_upload_transforms", "b200phys_upload_colliders", "b200phys_upload_joints",
     "b200phys_upload_forces", "b200phys_upload_body_states", "b200phys_step", "b200phys_synchronize", "b200phys_download_bodies", "b200phys_get_stats",
@@ -118,6 +122,7 @@ def load_library():
     lib.b200phys_set_stream.argtypes = [vp, vp]
     lib.b200phys_enable_timing.argtypes = [vp, i32]
     lib.b200phys_enable_graphs.argtypes = [vp, i32]
+    lib.b200phys_upload_heightmap.argtypes = [vp, vp, vp]
     lib.b200phys_host_alloc.restype = vp; lib.b200phys_host_alloc.argtypes = [C.c_size_t]
     lib.b200phys_host_free.restype = None; lib.b200phys_host_free.argtypes = [vp]
     lib.b200phys_set_hulls.argtypes = [vp, vp, vp, u32]
@@ -226,6 +231,18 @@ class Stepper:
 
     def enable_timing(self, on=True):
         _check(self.lib, self.lib.b200phys_enable_timing(self.ctx, 1 if on else 0), "enable_timing")
+
+    def upload_heightmap(self, heightmap):
+        """heightmap: dict(chunks_per_dim, chunk_size, min_corner, amplitude_scale, restitution, friction, heights uint16 [chunks, 129, 129]) or None."""
+        if heightmap is None:
+            _check(self.lib, self.lib.b200phys_upload_heightmap(self.ctx, None, None), "upload_heightmap"); return
+        d = HeightmapDesc(); d.chunksPerDim = int(heightmap["chunks_per_dim"]); d.chunkSize = float(heightmap["chunk_size"])
+        for k in range(3):
+            d.minCorner[k] = float(heightmap["min_corner"][k])
+        d.amplitudeScale = float(heightmap["amplitude_scale"]); d.restitution = float(heightmap["restitution"]); d.friction = float(heightmap["friction"])
+        h = np.ascontiguousarray(heightmap["heights"], dtype=np.uint16)
+        assert h.size == d.chunksPerDim * d.chunksPerDim * 129 * 129
+        _check(self.lib, self.lib.b200phys_upload_heightmap(self.ctx, C.byref(d), _ptr(h)), "upload_heightmap")
 
     def enable_graphs(self, on=True):
         _check(self.lib, self.lib.b200phys_enable_graphs(self.ctx, 1 if on else 0), "enable_graphs")

@@ -39,6 +39,7 @@ struct DeviceCounts
     uint32_t numEpaWork;                // GJK hits waiting for EPA this step
     uint32_t epaWorkHead;               // next work-list entry to hand out (EPA kernels with dynamic distribution)
     uint32_t numEpaRedo;                // entries the small-polytope EPA kernel handed to the large-capacity one
+    uint32_t hmBaseManifolds, hmBaseContacts, hmFitManifolds, hmFitContacts;   // heightmap pass: list sizes before it, first entries that did not fit
     uint32_t epaRedoHead;               // next redo entry to hand out
     uint32_t gjkCursor[11];             // per GJK bucket: next pair to hand out (npGjkKernel)
     uint32_t numPairs;                  // broad-phase overlaps (clamped to capacity)
@@ -198,6 +199,10 @@ struct Context
     // capacities
     uint32_t maxPairs = 0, maxManifolds = 0, maxContacts = 0, maxJoints = 0, maxCells = 0;
 
+    // heightmap (b200phys_upload_heightmap): heights + min/max mip pyramid per chunk on the device, parameters on the host
+    uint16_t* hmHeights = nullptr; void* hmMips = nullptr;
+    struct { uint32_t chunksPerDim; float chunkSize, invChunkSize, chunkScale, heightScale, invAmplitudeScale, minCorner[3], restitution, friction; } hm = {};
+
     // CUDA graph replay of the step (b200phys_api.cu): 0 = launch, 1 = dry run that only hashes what would be launched
     int graphMode = 0; unsigned long long graphHash = 0; void* graphCache = nullptr; bool graphFailed = false, graphsOff = false; uint32_t graphReplays = 0, graphCaptures = 0;
 
@@ -267,6 +272,7 @@ void launchPackAabbs(Context* c, float* devOut);
 
 // utilities (b200_util.cu)
 void launchCollisionEvents(Context* c);
+void launchHeightmap(Context* c);        // k_heightmap.cuh (compiled with k_narrow.cu)
 void scanExclusiveU32(Context* c, const uint32_t* in, uint32_t* out, const uint32_t* devCount, uint32_t maxCount, uint32_t* totalOut /*device, may be null*/, bool clearInput = false /* leave the scanned part of `in` zeroed */);
 void scanExclusiveU64(Context* c, const unsigned long long* in, unsigned long long* out, const uint32_t* devCount, uint32_t maxCount, unsigned long long* totalOut);
 // stable counting sort of n (device count) elements by small keys (< numKeys <= 64): dst[i] = destination slot, keyStart[k] = ranges

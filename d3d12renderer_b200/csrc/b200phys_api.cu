@@ -3,6 +3,7 @@
 // enqueue the fixed kernel sequence of one physicsStepInternal (physics.cpp:1180-1362) on the context's stream, copy results.
 // There is no CPU implementation of any stage in this library: without a CUDA device b200phys_create fails.
 #include <algorithm>
+#include <vector>
 #include <unordered_map>
 #include "b200_context.h"
 #include <cstdio>
@@ -97,6 +98,7 @@ void freeAll(Context& c)
     for (int k = 0; k < 6; ++k) if (c.refColorsJoint[k]) cudaFree(c.refColorsJoint[k]);
     for (int k = 0; k < 2; ++k) { if (c.evKeys[k]) cudaFree(c.evKeys[k]); if (c.evPairs[k]) cudaFree(c.evPairs[k]); if (c.evFlag[k]) cudaFree(c.evFlag[k]); if (c.evSlot[k]) cudaFree(c.evSlot[k]); }
     if (c.evBegin) cudaFree(c.evBegin); if (c.evEnd) cudaFree(c.evEnd);
+    if (c.hmHeights) cudaFree(c.hmHeights); if (c.hmMips) cudaFree(c.hmMips);
     if (c.interactions) cudaFree(c.interactions); if (c.forceFields) cudaFree(c.forceFields); delete c.prevTriggerOverlaps;
     for (uint32_t g = 0; g < kNumGroups; ++g) { if (c.unitColor[g]) cudaFree(c.unitColor[g]); if (c.unitOrder[g]) cudaFree(c.unitOrder[g]); if (c.unitDep[g]) cudaFree(c.unitDep[g]); }
     for (int k = 0; k < 6; ++k) { if (c.jointIn[k]) cudaFree(c.jointIn[k]); if (c.jointBodies[k]) cudaFree(c.jointBodies[k]); if (c.jointRows[k]) cudaFree(c.jointRows[k]); }
@@ -323,7 +325,8 @@ static void enqueueStep(Context& c, float dt, uint32_t numSolverIterations, uint
     if (c.timing) cudaEventRecord(c.ev[3], c.stream);
     waitPendingForceUpload(&c);
     launchIntegrateForces(&c, dt);                          // physics.cpp:1266-1279
-    launchCollisionEvents(&c);                              // physics.cpp:1284
+    launchCollisionEvents(&c);                              // physics.cpp:1284 (heightmap collisions carry no second collider and take no part, :1049)
+    launchHeightmap(&c);                                    // physics.cpp:1238-1248: contacts behind the narrow phase's
     timelineMark(&c, "integrate_forces");
     launchSolver(&c, dt, numSolverIterations, flags);       // physics.cpp:1316-1334 (records ev[4] before the iterations)
     if (c.timing) cudaEventRecord(c.ev[5], c.stream);
@@ -409,6 +412,56 @@ int b200phys_step(b200phys_context* ctx, float dt, uint32_t numSolverIterations,
     }
     ++c.graphCaptures;
     CK(cudaGraphLaunch(entry.exec, c.stream));
+    return 0;
+}
+
+// heightmap_collider_component (terrain/heightmap_collider.h:132-150, heightmap_collider.cpp:5-19) + heightmap_collider_chunk::setHeights
+// (:45-123): the min/max pyramid of every chunk is built here on the host (integer work, once per upload)
+int b200phys_upload_heightmap(b200phys_context* ctx, const b200phys_heightmap* desc, const uint16_t* heights)
+{
+    if (!ctx) return B200PHYS_E_INVALID;
+    Context& c = ctx->c; CK(cudaSetDevice(c.device));
+    CK(cudaStreamSynchronize(c.stream));
+    if (c.hmHeights) { cudaFree(c.hmHeights); c.hmHeights = nullptr; }
+    if (c.hmMips) { cudaFree(c.hmMips); c.hmMips = nullptr; }
+    if (!desc || !heights) return 0;                                   // no heightmap any more
+    if (!desc->chunksPerDim || desc->chunksPerDim > 256 || !(desc->chunkSize > 0.f) || !(desc->amplitudeScale > 0.f)) return B200PHYS_E_INVALID;
+    const uint32_t V = 129, nChunks = desc->chunksPerDim * desc->chunksPerDim, nodesPerChunk = 21845;
+    std::vector<ushort2> mips((size_t)nChunks * nodesPerChunk);
+    for (uint32_t ch = 0; ch < nChunks; ++ch)
+    {
+        const uint16_t* hh = heights + (size_t)ch * V * V;
+        ushort2* m = mips.data() + (size_t)ch * nodesPerChunk;
+        uint32_t seg = 128;
+        for (uint32_t z = 0; z < seg; ++z)
+            for (uint32_t x = 0; x < seg; ++x)
+            {
+                const uint16_t a = hh[V * z + x], b = hh[V * (z + 1) + x], cc = hh[V * z + x + 1], d = hh[V * (z + 1) + x + 1];
+                m[seg * z + x] = make_ushort2(std::min(a, std::min(b, std::min(cc, d))), std::max(a, std::max(b, std::max(cc, d))));
+            }
+        ushort2* rd = m;
+        for (uint32_t level = 1; level < 8; ++level)
+        {
+            const uint32_t stride = seg; seg >>= 1;
+            ushort2* wr = rd + stride * stride;
+            for (uint32_t z = 0; z < seg; ++z)
+                for (uint32_t x = 0; x < seg; ++x)
+                {
+                    const ushort2 a = rd[stride * (2 * z) + 2 * x], b = rd[stride * (2 * z + 1) + 2 * x], cc = rd[stride * (2 * z) + 2 * x + 1], d = rd[stride * (2 * z + 1) + 2 * x + 1];
+                    wr[seg * z + x] = make_ushort2(std::min(a.x, std::min(b.x, std::min(cc.x, d.x))), std::max(a.y, std::max(b.y, std::max(cc.y, d.y))));
+                }
+            rd = wr;
+        }
+    }
+    CK(devAlloc(c.hmHeights, (size_t)nChunks * V * V));
+    ushort2* dm = nullptr; CK(devAlloc(dm, mips.size())); c.hmMips = dm;
+    CK(cudaMemcpy(c.hmHeights, heights, sizeof(uint16_t) * (size_t)nChunks * V * V, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c.hmMips, mips.data(), sizeof(ushort2) * mips.size(), cudaMemcpyHostToDevice));
+    c.hm.chunksPerDim = desc->chunksPerDim; c.hm.chunkSize = desc->chunkSize; c.hm.invChunkSize = 1.f / desc->chunkSize;
+    c.hm.chunkScale = desc->chunkSize / (float)(V - 1);
+    c.hm.invAmplitudeScale = 1.f / desc->amplitudeScale; c.hm.heightScale = desc->amplitudeScale / (float)65535;
+    for (int k = 0; k < 3; ++k) c.hm.minCorner[k] = desc->minCorner[k];
+    c.hm.restitution = desc->restitution; c.hm.friction = desc->friction;
     return 0;
 }
 

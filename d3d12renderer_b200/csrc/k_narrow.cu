@@ -7,6 +7,7 @@
 #include "b200_context.h"
 #include "k_narrow_shapes.cuh"
 #include <cstdlib>
+#include <cstring>
 
 namespace b200 {
 
@@ -613,3 +614,5 @@ void launchNarrowphase(Context* c)
 }
 
 } // namespace b200
+
+#include "k_heightmap.cuh"

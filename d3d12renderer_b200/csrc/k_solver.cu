@@ -485,6 +485,7 @@ __global__ void __launch_bounds__(kThreads) manifoldKeysKernel(const uint2* __re
     for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < n; i += gridDim.x * kThreads)
     {
         const uint2 pr = collisions[i];
+        if (pr.y == 0xFFFFFFFFu) { keys[i] = (63ull << 56) | ((unsigned long long)pr.x << 28) | 0xFFFFFFFull; continue; }     // collider vs heightmap: no second collider
         const uint32_t ta = __float_as_uint(wCol[4 * pr.x + 3].x) & 0xFFu, tb = __float_as_uint(wCol[4 * pr.y + 3].x) & 0xFFu;
         keys[i] = ((unsigned long long)pairBucketOf(ta, tb) << 56) | ((unsigned long long)min(pr.x, pr.y) << 28) | (unsigned long long)max(pr.x, pr.y);
     }

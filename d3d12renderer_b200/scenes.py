@@ -348,3 +348,71 @@ def _quat_to_mat(q):
 def _quat_mul(a, b):
     ax, ay, az, aw = [float(v) for v in a]; bx, by, bz, bw = [float(v) for v in b]
     return np.array([aw * bx + ax * bw + ay * bz - az * by, aw * by - ax * bz + ay * bw + az * bx, aw * bz + ax * by - ay * bx + az * bw, aw * bw - ax * bx - ay * by - az * bz], dtype=np.float32)
+
+
+def terrain_heights(chunks_per_dim=2, chunk_size=16.0, amplitude=6.0, seed=5):
+    """uint16 heights of a smooth rolling terrain, chunks_per_dim^2 chunks of 129 x 129 vertices (the reference's terrain chunk layout,
+    terrain/heightmap_collider.h:8-11); neighbouring chunks share their border row / column."""
+    rng = np.random.default_rng(seed)
+    ph = rng.uniform(0, 6.28, size=4)
+    n = 129
+    out = np.zeros((chunks_per_dim * chunks_per_dim, n, n), dtype=np.uint16)
+    for cz in range(chunks_per_dim):
+        for cx in range(chunks_per_dim):
+            gx = (cx * 128 + np.arange(n))[None, :] * (chunk_size / 128.0)
+            gz = (cz * 128 + np.arange(n))[:, None] * (chunk_size / 128.0)
+            h = 0.45 + 0.22 * np.sin(0.35 * gx + ph[0]) * np.cos(0.27 * gz + ph[1]) + 0.12 * np.sin(0.9 * gx + 0.6 * gz + ph[2]) + 0.05 * np.cos(1.9 * gz + ph[3])
+            out[cz * chunks_per_dim + cx] = np.clip(h * 65535.0, 0, 65535).astype(np.uint16)
+    return out
+
+
+def terrain_drop(n_side=10, seed=5, chunks_per_dim=2, chunk_size=16.0, amplitude=6.0):
+    """Heightmap scene: n_side^2 bodies -- spheres, capsules, unrotated boxes (AABB colliders), rotated boxes (AABB colliders
+    that become OBBs, physics.cpp:722-734) and OBB colliders -- start just above / slightly inside a rolling terrain and fall onto it. No
+    other static geometry. The scene carries "heightmap": the arguments of b200phys_upload_heightmap."""
+    rng = np.random.default_rng(seed)
+    heights = terrain_heights(chunks_per_dim, chunk_size, amplitude, seed)
+    extent = chunks_per_dim * chunk_size
+    min_corner = np.array([-0.5 * extent, -2.0, -0.5 * extent], dtype=np.float32)
+    n = n_side * n_side
+    bodies = new_bodies(n)
+    set_sphere_bodies(bodies, np.arange(n), F(0.4), F(1.0))
+    colliders = np.zeros(n, dtype=abi.collider_dtype)
+    colliders["restitution"] = 0.1; colliders["friction"] = 0.5; colliders["density"] = 1.0
+    colliders["parentTransform"] = abi.NO_TRANSFORM
+    colliders["objectType"] = abi.OBJ_RIGID_BODY; colliders["objectIndex"] = np.arange(n)
+
+    def height(x, z):      # bilinear, like heightmap_collider_chunk::getHeightAt
+        u = (x - min_corner[0]) / chunk_size; v = (z - min_corner[2]) / chunk_size
+        cx = min(int(u), chunks_per_dim - 1); cz = min(int(v), chunks_per_dim - 1)
+        fx = (u - cx) * 128.0; fz = (v - cz) * 128.0
+        ix = min(int(fx), 127); iz = min(int(fz), 127); rx = fx - ix; rz = fz - iz
+        hh = heights[cz * chunks_per_dim + cx].astype(np.float64) * (amplitude / 65535.0)
+        a, b, c, d = hh[iz, ix], hh[iz + 1, ix], hh[iz, ix + 1], hh[iz + 1, ix + 1]
+        return (a + rx * (c - a)) * (1 - rz) + (b + rx * (d - b)) * rz + min_corner[1]
+
+    span = 0.7 * extent
+    for i in range(n):
+        kind = i % 5
+        s = colliders["shape"][i]; s[:] = 0
+        if kind == 0:
+            colliders["type"][i] = abi.SPHERE; s[3] = 0.4
+        elif kind == 1:
+            colliders["type"][i] = abi.CAPSULE; s[0:3] = (0, -0.3, 0); s[3:6] = (0, 0.3, 0); s[6] = 0.25
+        elif kind in (2, 3):
+            colliders["type"][i] = abi.AABB; s[0:3] = (-0.35, -0.3, -0.4); s[3:6] = (0.35, 0.3, 0.4)
+        else:
+            colliders["type"][i] = abi.OBB; s[0:4] = (0, 0, 0, 1); s[4:7] = (0.05, 0.0, -0.05); s[7:10] = (0.3, 0.35, 0.25)
+        x = -0.5 * span + span * ((i % n_side) + 0.5) / n_side + rng.uniform(-0.2, 0.2)
+        z = -0.5 * span + span * ((i // n_side) + 0.5) / n_side + rng.uniform(-0.2, 0.2)
+        bodies["position"][i] = (x, height(x, z) + rng.uniform(0.15, 0.7), z)
+        if kind not in (0, 2):
+            ax = rng.normal(size=3); ax /= np.linalg.norm(ax); ang = rng.uniform(0, np.pi)
+            bodies["rotation"][i] = np.concatenate([ax * np.sin(ang / 2), [np.cos(ang / 2)]]).astype(np.float32)
+        bodies["linearVelocity"][i] = (rng.uniform(-0.5, 0.5), -2.0, rng.uniform(-0.5, 0.5))
+        if kind == 2:
+            bodies["angularDamping"][i] = 0.0
+    transforms = np.zeros(1, dtype=abi.transform_dtype); transforms["rotation"][:, 3] = 1.0
+    return {"bodies": bodies, "colliders": colliders, "transforms": transforms, "joints": {}, "name": "terrain_drop",
+            "heightmap": dict(chunks_per_dim=chunks_per_dim, chunk_size=np.float32(chunk_size), min_corner=min_corner, amplitude_scale=np.float32(amplitude),
+                              restitution=np.float32(0.1), friction=np.float32(0.9), heights=heights)}

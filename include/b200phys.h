@@ -234,6 +234,21 @@ void b200phys_host_free(void* p);
  * memory is staged by the driver before the call returns and may be reused at once. PAGE-LOCKED memory (b200phys_host_alloc,
  * cudaHostAlloc) is read by DMA later: it must stay untouched until the next call that synchronises the context has returned
  * (b200phys_synchronize, any b200phys_download_*, b200phys_get_stats). */
+/* heightmap collision (reference: heightmap_collider_component, terrain/heightmap_collider.h:132-150, collided against every rigid body
+ * collider of type sphere / capsule / AABB / OBB by heightmapCollision, physics/heightmap_collision.cpp:509-618, physics.cpp:1238-1248).
+ * heights: chunksPerDim^2 chunks of 129 x 129 uint16 (TERRAIN_LOD_0_VERTICES_PER_DIMENSION), chunk (x, z) at z * chunksPerDim + x, row
+ * major in z; world height = minCorner[1] + h * amplitudeScale / 65535. desc == NULL or heights == NULL removes the heightmap. The contacts
+ * are appended behind the narrow phase's (one collision {collider, 0xFFFFFFFF} per touching collider, second body = the static dummy);
+ * a collider produces one contact per touching triangle (not de-duplicated, heightmap_collision.cpp:432; at most 255): size
+ * b200phys_config.maxContacts accordingly. */
+typedef struct b200phys_heightmap {
+    uint32_t chunksPerDim;
+    float    chunkSize;          /* metres per chunk edge (128 segments) */
+    float    minCorner[3];
+    float    amplitudeScale;
+    float    restitution, friction;
+} b200phys_heightmap;
+int b200phys_upload_heightmap(b200phys_context* ctx, const b200phys_heightmap* desc, const uint16_t* heights);
 int b200phys_set_hulls(b200phys_context* ctx, const float* vertices, const uint32_t* vertexOffsets, uint32_t numHulls);
 int b200phys_upload_bodies(b200phys_context* ctx, const b200phys_body* bodies, uint32_t count);
 int b200phys_upload_transforms(b200phys_context* ctx, const b200phys_transform* transforms, uint32_t count);

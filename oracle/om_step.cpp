@@ -422,6 +422,7 @@ void Oracle::collisionEvents()
     uint32_t contactOffset = 0;
     for (size_t i = 0; i < collisions.size(); ++i)
     {
+        if (!(collisions[i].b < wcol.size())) continue;        // heightmap collisions carry no second collider (physics.cpp:1049)
         cur.push_back(CollisionKey{ collisions[i].a, collisions[i].b, contactOffset, contactCount[i] });
         contactOffset += contactCount[i];
     }
@@ -460,7 +461,7 @@ void Oracle::step(float dt, uint32_t iterations, const uint32_t* contactOrder, c
     double t0 = nowMs();
     worldColliders();                       double t1 = nowMs();
     broadphaseSAP();                        double t2 = nowMs();
-    narrowphase();                          double t3 = nowMs();
+    narrowphase(); heightmapCollisions();   double t3 = nowMs();
     nonCollisionInteractions();             // physics.cpp:1255
     integrateForces(dt);                    double t4 = nowMs();
     collisionEvents();                      // physics.cpp:1284 (after the force integration, before the solver)

@@ -23,6 +23,19 @@ struct ContactRow
 
 enum PairOrder { ORDER_REFERENCE_SAP = 0, ORDER_CANONICAL = 1 };
 
+// heightmap_collider_component + its chunks (terrain/heightmap_collider.h:19-150), om_heightmap.cpp
+struct Heightmap
+{
+    struct MinMax { uint16_t mn, mx; };
+    bool present = false;
+    uint32_t chunksPerDim = 0; float chunkSize = 0.f, invChunkSize = 0.f, chunkScale = 0.f, heightScale = 0.f, invAmplitudeScale = 1.f;
+    V3 minCorner = v3(0.f); float restitution = 0.f, friction = 0.f;
+    std::vector<uint16_t> heights;                                  // chunksPerDim^2 chunks x 129 x 129, chunk (x, z) at z * chunksPerDim + x
+    std::vector<std::vector<std::vector<MinMax>>> mips;             // per chunk: 8 levels of (min, max), 128^2 ... 1
+    void set(uint32_t chunksPerDim, float chunkSize, V3 minCorner, float amplitudeScale, float restitution, float friction, const uint16_t* heights);
+    float heightAt(float x, float z) const;                         // -FLT_MAX outside
+};
+
 struct SapEndpoint { float value; uint32_t collider; bool start; };
 
 struct Oracle
@@ -78,6 +91,8 @@ struct Oracle
     void broadphaseSAP();                                // collision_broad.cpp:297-447 + :87-166
     void broadphaseBrute(std::vector<Pair>& out) const;  // all-pairs, same predicate
     void narrowphase();                                  // collision_narrow.cpp:2328-2603
+    Heightmap heightmap;
+    void heightmapCollisions();                          // heightmap_collision.cpp:509-618 behind the narrow phase (physics.cpp:1238-1248)
     void integrateForces(float dt);                      // rigid_body.cpp:95-124 over physics.cpp:1266-1279
     void initContacts(float dt);                         // constraints.cpp:3307-3379
     void solveContacts(const uint32_t* order, uint32_t n); // constraints.cpp:3381-3449

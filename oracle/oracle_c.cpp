@@ -49,7 +49,14 @@ void oracle_step(oracle_ctx* c, float dt, uint32_t iterations, const uint32_t* c
 }
 
 // staged entry points (tests drive stages separately, e.g. replaying the GPU's solve order on identical contacts)
-void oracle_stage_detect(oracle_ctx* c) { c->o.nstats = NarrowStats(); c->o.worldColliders(); c->o.broadphaseSAP(); c->o.narrowphase(); }
+void oracle_stage_detect(oracle_ctx* c) { c->o.nstats = NarrowStats(); c->o.worldColliders(); c->o.broadphaseSAP(); c->o.narrowphase(); c->o.heightmapCollisions(); }
+// heightmap_collider_component (terrain/heightmap_collider.h:132-150): chunksPerDim^2 chunks of 129 x 129 uint16 heights, chunk (x, z) at z * chunksPerDim + x
+void oracle_set_heightmap(oracle_ctx* c, uint32_t chunksPerDim, float chunkSize, const float* minCorner3, float amplitudeScale, float restitution, float friction, const uint16_t* heights)
+{
+    if (!heights) { c->o.heightmap = Heightmap(); return; }
+    c->o.heightmap.set(chunksPerDim, chunkSize, v3(minCorner3[0], minCorner3[1], minCorner3[2]), amplitudeScale, restitution, friction, heights);
+}
+float oracle_heightmap_height_at(oracle_ctx* c, float x, float z) { return c->o.heightmap.heightAt(x, z); }
 void oracle_stage_world_and_aabbs(oracle_ctx* c) { c->o.worldColliders(); }
 void oracle_stage_forces(oracle_ctx* c, float dt) { c->o.integrateForces(dt); }
 void oracle_stage_init(oracle_ctx* c, float dt) { c->o.initJoints(dt); c->o.initContacts(dt); }

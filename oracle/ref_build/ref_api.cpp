@@ -12,6 +12,8 @@
 #include "physics/collision_narrow.h"
 #include "physics/ragdoll.h"
 #include "physics/vehicle.h"
+#include "physics/heightmap_collision.h"
+#include "terrain/heightmap_collider.h"
 #include "scene/scene.h"
 #include "core/random.h"
 #include "b200phys.h"
@@ -32,6 +34,7 @@ struct RefScene
     std::vector<entity_handle> bodyEntities, transformEntities;
     float timer = 0.f;
     double lastStepSeconds = 0.0;
+    std::vector<uint16> heightmapHeights;   // storage behind heightmap_collider_chunk::setHeights (the chunk keeps the pointer)
     std::vector<uint32> triggerLog;          // (trigger index, rigid body index, 0 enter / 1 leave) triples of the last step, callback order
     RefScene() { arena.initialize(0, GB(8)); }
 };
@@ -233,6 +236,26 @@ uint32 ref_scene_add_ground(void* p, const float* center3, const float* radius3,
     e.addComponent<collider_component>(collider_component::asAABB(bounding_box::fromCenterRadius(v3(center3), v3(radius3)), { physics_material_type_none, restitution, friction, density }));
     return 1;
 }
+// heightmap_collider_component (terrain/heightmap_collider.h:132-150) on its own entity: chunksPerDim^2 chunks of 129 x 129 heights
+int ref_scene_add_heightmap(void* p, uint32 chunksPerDim, float chunkSize, const float* minCorner3, float amplitudeScale, float restitution, float friction, const uint16* heights)
+{
+    RefScene& R = *(RefScene*)p;
+    const size_t perChunk = (size_t)TERRAIN_LOD_0_VERTICES_PER_DIMENSION * TERRAIN_LOD_0_VERTICES_PER_DIMENSION;
+    R.heightmapHeights.assign(heights, heights + perChunk * chunksPerDim * chunksPerDim);
+    scene_entity e = R.scene.createEntity("terrain");
+    heightmap_collider_component& hm = e.addComponent<heightmap_collider_component>(chunksPerDim, chunkSize, physics_material{ physics_material_type_none, restitution, friction, 1.f }).getComponent<heightmap_collider_component>();
+    hm.update(v3(minCorner3), amplitudeScale);
+    for (uint32 z = 0; z < chunksPerDim; ++z)
+        for (uint32 x = 0; x < chunksPerDim; ++x)
+            hm.collider(x, z).setHeights(R.heightmapHeights.data() + perChunk * (z * chunksPerDim + x));
+    return 0;
+}
+float ref_scene_heightmap_height_at(void* p, float x, float z)
+{
+    RefScene& R = *(RefScene*)p;
+    for (auto [h, hm] : R.scene.view<heightmap_collider_component>().each()) return hm.getHeightAt(vec2(x, z));
+    return -FLT_MAX;
+}
 uint32 ref_scene_num_bodies(void* p) { return (uint32)((RefScene*)p)->bodyEntities.size(); }
 uint32 ref_scene_num_colliders(void* p) { return ((RefScene*)p)->scene.numberOfComponentsOfType<collider_component>(); }
 uint32 ref_scene_num_joints(void* p, int kind)
@@ -310,11 +333,17 @@ int ref_scene_detect(void* p, int simdBroad, int simdNarrow, float* outAabbs, fl
     if (outWorld16) for (uint32 i = 0; i < numColliders; ++i) writeWorldCollider(world[i], outWorld16 + 16 * i);
     if (outPairs) for (uint32 i = 0; i < numPairs && i < pairCapacity; ++i) { outPairs[2 * i] = pairs[i].colliderA; outPairs[2 * i + 1] = pairs[i].colliderB; }
     non_collision_interaction* nci = R.arena.allocate<non_collision_interaction>(numPairs);
-    collision_contact* contacts = R.arena.allocate<collision_contact>(numPairs * 4 + 5000);
-    constraint_body_pair* bodyPairs = R.arena.allocate<constraint_body_pair>(numPairs * 4 + 5000);
-    uint8* counts = R.arena.allocate<uint8>(numPairs + 5000);
-    collider_pair* outColl = R.arena.allocate<collider_pair>(numPairs + 5000);
+    collision_contact* contacts = R.arena.allocate<collision_contact>(numPairs * 4 + 5000 + numColliders * 256);
+    constraint_body_pair* bodyPairs = R.arena.allocate<constraint_body_pair>(numPairs * 4 + 5000 + numColliders * 256);
+    uint8* counts = R.arena.allocate<uint8>(numPairs + 5000 + numColliders);
+    collider_pair* outColl = R.arena.allocate<collider_pair>(numPairs + 5000 + numColliders);
     narrowphase_result r = narrowphase(world, pairs, numPairs, R.arena, contacts, bodyPairs, outColl, counts, nci, simdNarrow != 0);
+    for (auto [h, hm] : scene.view<heightmap_collider_component>().each())
+    {   // physics.cpp:1238-1248
+        narrowphase_result hr = heightmapCollision(hm, world, aabbs, numColliders, contacts + r.numContacts, bodyPairs + r.numContacts, outColl + r.numCollisions, counts + r.numCollisions,
+                                                   R.arena, (uint16)numRigidBodies);
+        r.numCollisions += hr.numCollisions; r.numContacts += hr.numContacts;
+    }
     static_assert(sizeof(collision_contact) == sizeof(b200phys_contact), "contact layout");
     for (uint32 i = 0; i < r.numContacts && i < contactCapacity; ++i)
     {

@@ -69,6 +69,8 @@ def load():
     lib.oracle_get_stage_ms.argtypes = [vp, vp]
     lib.oracle_collide_pair.argtypes = [vp, vp, vp, vp, vp]; lib.oracle_collide_pair.restype = C.c_int
     lib.oracle_mass_properties.argtypes = [vp, vp, vp, vp, vp]
+    lib.oracle_set_heightmap.argtypes = [vp, u32, f32, vp, f32, f32, f32, vp]
+    lib.oracle_heightmap_height_at.argtypes = [vp, f32, f32]; lib.oracle_heightmap_height_at.restype = f32
     lib.oracle_combine_mass.argtypes = [vp, vp, vp, u32, vp, vp, vp]
     _lib = lib
     return lib
@@ -107,6 +109,11 @@ class Oracle:
         for kind, (joints, pairs) in scene.get("joints", {}).items():
             j = np.ascontiguousarray(joints); p = np.ascontiguousarray(pairs)
             self.lib.oracle_set_joints(self.ctx, kind, _p(j), _p(p), len(j))
+        if "heightmap" in scene:
+            h = scene["heightmap"]; mc = np.ascontiguousarray(h["min_corner"], dtype=np.float32); hh = np.ascontiguousarray(h["heights"], dtype=np.uint16)
+            self.lib.oracle_set_heightmap(self.ctx, h["chunks_per_dim"], h["chunk_size"], _p(mc), h["amplitude_scale"], h["restitution"], h["friction"], _p(hh))
+
+    def heightmap_height_at(self, x, z): return float(self.lib.oracle_heightmap_height_at(self.ctx, x, z))
 
     def set_bodies(self, bodies):
         b = np.ascontiguousarray(bodies)

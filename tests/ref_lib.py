@@ -32,6 +32,8 @@ def load(fast=False):
     lib.ref_scene_add_ragdoll.argtypes = [vp, vp, f32]; lib.ref_scene_add_ragdoll.restype = u32
     lib.ref_scene_add_vehicle.argtypes = [vp, vp, f32, f32, f32]; lib.ref_scene_add_vehicle.restype = u32
     lib.ref_scene_add_ground.argtypes = [vp, vp, vp, vp, f32, f32, f32]
+    lib.ref_scene_add_heightmap.argtypes = [vp, u32, f32, vp, f32, f32, f32, vp]
+    lib.ref_scene_heightmap_height_at.argtypes = [vp, f32, f32]; lib.ref_scene_heightmap_height_at.restype = f32
     for n in ("ref_scene_num_bodies", "ref_scene_num_colliders"):
         getattr(lib, n).argtypes = [vp]; getattr(lib, n).restype = u32
     lib.ref_scene_num_joints.argtypes = [vp, i32]; lib.ref_scene_num_joints.restype = u32
@@ -91,6 +93,9 @@ class RefScene:
         for kind, (joints, pairs) in sorted(scene.get("joints", {}).items()):
             j = np.ascontiguousarray(joints); p = np.ascontiguousarray(pairs)
             self.lib.ref_scene_add_joints(self.ptr, kind, _p(j), _p(p), len(j))
+        if "heightmap" in scene:
+            h = scene["heightmap"]; mc = np.ascontiguousarray(h["min_corner"], dtype=np.float32); hh = np.ascontiguousarray(h["heights"], dtype=np.uint16)
+            self.lib.ref_scene_add_heightmap(self.ptr, h["chunks_per_dim"], h["chunk_size"], _p(mc), h["amplitude_scale"], h["restitution"], h["friction"], _p(hh))
         if "force_fields" in scene:
             f = np.ascontiguousarray(scene["force_fields"], dtype=np.float32); g = np.ascontiguousarray(scene.get("global_force", np.zeros(3)), dtype=np.float32)
             self.lib.ref_scene_set_force_fields(self.ptr, _p(f), len(f), _p(g))
@@ -107,6 +112,8 @@ class RefScene:
 
     def set_hinge_motor(self, index, motor_type, value, max_torque):
         self.lib.ref_scene_set_hinge_motor(self.ptr, index, motor_type, value, max_torque)
+
+    def heightmap_height_at(self, x, z): return float(self.lib.ref_scene_heightmap_height_at(self.ptr, x, z))
 
     def num_bodies(self): return self.lib.ref_scene_num_bodies(self.ptr)
     def num_colliders(self): return self.lib.ref_scene_num_colliders(self.ptr)
@@ -144,7 +151,7 @@ class RefScene:
         counts = np.zeros(5, dtype=np.uint32)
         s = 1 if simd else 0
         while True:
-            pairs = np.zeros((cap_p, 2), dtype=np.uint32); cap_c = 4 * cap_p
+            pairs = np.zeros((cap_p, 2), dtype=np.uint32); cap_c = 4 * cap_p + 64 * nc
             contacts = np.zeros(cap_c, dtype=abi.contact_dtype); cb = np.zeros(cap_c, dtype=abi.body_pair_dtype)
             cpairs = np.zeros((cap_c, 2), dtype=np.uint32); ccounts = np.zeros(cap_c, dtype=np.uint8)
             # detection mutates the SAP context; callers use a fresh scene per call or accept that

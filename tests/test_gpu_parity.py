@@ -26,6 +26,8 @@ def make_stepper(scene, **kw):
     st.upload_colliders(np.ascontiguousarray(scene["colliders"]))
     for kind, (joints, pairs) in scene.get("joints", {}).items():
         st.upload_joints(kind, joints, pairs)
+    if "heightmap" in scene:
+        st.upload_heightmap(scene["heightmap"])
     return st
 
 

@@ -209,6 +209,38 @@ def test_contact_and_manifold_capacity_overflow_is_safe():
         assert np.array_equal(c["point"], fc["point"][:len(c)])
 
 
+# ------------------------------------------------------------------------------------------------ heightmap (f.4)
+@pytest.mark.parametrize("flags", [abi.STEP_EXACT_ORDER, abi.STEP_FAST])
+def test_heightmap_collision_matches_oracle(flags):
+    """Spheres, capsules, AABB colliders (unrotated and rotated into OBBs) and OBB colliders fall onto a rolling 2 x 2 chunk terrain
+    (heightmap_collision.cpp:509-618; the oracle's restatement is pinned bit for bit to the compiled reference by
+    tests/test_ref_pins_oracle.py::test_heightmap_collision_equals_oracle). Every step: the contact list (terrain contacts behind the
+    body-body ones, one collision {collider, 0xFFFFFFFF} per touching collider, triangle order of the mip traversal) is bit-identical,
+    the states agree to 1e-5."""
+    sc = scenes.terrain_drop(12)
+    st = make_stepper(sc, max_contacts=128 * len(sc["colliders"])); orc = oracle_lib.Oracle(sc, canonical=True)
+    most = 0
+    for step in range(40):
+        st.step(DT, 10, flags)
+        s = st.stats()
+        assert_no_overflow(s, orc)
+        gc, gb = st.download_contacts(); gp, gn = st.download_collisions()
+        order = st.download_solve_order(6)
+        if flags == abi.STEP_EXACT_ORDER:
+            orc.step(DT, 10)
+        else:
+            orc.step(DT, 10, contact_order=order)
+        oc, ob = orc.contacts(); op, on = orc.collisions()
+        assert len(gc) == len(oc), "step %d: %d vs %d contacts" % (step, len(gc), len(oc))
+        assert np.array_equal(gc.view(np.uint32), oc.view(np.uint32)), "step %d: contacts differ" % step
+        assert np.array_equal(gb, ob) and np.array_equal(gn, on) and np.array_equal(gp, op)
+        most = max(most, int(np.sum(op["b"] == 0xFFFFFFFF)))
+        assert_states_close(st.download_bodies(), orc.body_states(), 1e-5)
+        st.upload_body_states(orc.body_states())
+    assert most > 100, "terrain collisions per step: %d" % most
+    st.close()
+
+
 # ------------------------------------------------------------------------------------------------ CUDA graph replay
 @pytest.mark.parametrize("config,dims,spacing,seed", [(host.CONFIG_MIXED_PILE, (10, 6, 10), 0.8, 1578123), (host.CONFIG_RAGDOLLS, (4, 1, 4), 1.6, 20260924)])
 def test_graph_replay_is_bit_identical_to_plain_launches(config, dims, spacing, seed):

@@ -197,3 +197,31 @@ def test_reference_avx2_path_runs_and_is_not_the_parity_path():
     assert np.all(np.isfinite(sb["position"]))
     assert float(np.max(np.abs(sa["position"] - sb["position"]))) < 1e-3
     assert not bits_equal(sa["linearVelocity"], sb["linearVelocity"])
+
+
+def test_heightmap_collision_equals_oracle():
+    """heightmapCollision (heightmap_collision.cpp:509-618) over heightmap_collider_component (terrain/heightmap_collider.*):
+    spheres, capsules, AABB colliders (unrotated and rotated into OBBs) and OBB colliders fall onto a rolling 2 x 2 chunk terrain. Height
+    lookups, the contact list of the first touching step (triangle order of the min/max mip traversal included) and 40 steps of
+    physicsStep agree bit for bit."""
+    sc = scenes.terrain_drop(10)
+    r = ref_lib.RefScene(sc); o = oracle_lib.Oracle(sc, canonical=False)
+    rng = np.random.default_rng(3)
+    for x, z in rng.uniform(-17, 17, size=(200, 2)).astype(np.float32):
+        assert np.float32(r.heightmap_height_at(x, z)).tobytes() == np.float32(o.heightmap_height_at(x, z)).tobytes()
+    touched = 0
+    for s in range(40):
+        if s in (0, 6, 15, 30):
+            d = ref_lib.RefScene(dict(sc, bodies=o.bodies())).detect()
+            oo = oracle_lib.Oracle(dict(sc, bodies=o.bodies()), canonical=False); oo.detect()
+            oc, ob = oo.contacts(); op, on = oo.collisions()
+            assert len(d["contacts"]) == len(oc) and bits_equal(d["contacts"].view(np.uint32), oc.view(np.uint32)), "contacts differ at step %d" % s
+            assert np.array_equal(d["contact_counts"], on) and np.array_equal(d["collision_pairs"][:, 0], op["a"])
+            assert np.all(d["collision_pairs"][:, 1] == 0xFFFF) and np.all(op["b"] == 0xFFFFFFFF)
+            assert np.array_equal(d["contact_bodies"]["rbA"], ob["rbA"]) and np.all(ob["rbB"] == len(sc["bodies"]))
+            touched = max(touched, len(oc))
+        r.step(DT, 10); o.step(DT, 10)
+        assert_states_bit_equal(r.body_states(), o.body_states(), "step %d" % s)
+    assert touched > 50, "the scene must actually produce terrain contacts (%d)" % touched
+    types = sc["colliders"]["type"]
+    assert set(types) == {abi.SPHERE, abi.CAPSULE, abi.AABB, abi.OBB}
