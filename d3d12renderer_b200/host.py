@@ -28,6 +28,7 @@ def load_library():
     lib.b200host_scene_destroy.argtypes = [vp]
     lib.b200host_build_config.argtypes = [vp, C.c_int, u32, u32, u32, C.c_uint64, C.c_int, C.c_float]
     lib.b200host_build_mixed_slab.argtypes = [vp, u32, u32, u32, u32, u32, C.c_uint64, C.c_float]
+    lib.b200host_set_heightmap.argtypes = [vp, u32, C.c_float, vp, C.c_float, C.c_float, C.c_float, vp]
     for n in ("b200host_num_bodies", "b200host_num_colliders", "b200host_num_hulls", "b200host_num_hull_vertices"):
         getattr(lib, n).argtypes = [vp]; getattr(lib, n).restype = u32
     lib.b200host_num_joints.argtypes = [vp, C.c_int]; lib.b200host_num_joints.restype = u32
@@ -77,6 +78,11 @@ class HostScene:
         if rc:
             raise ValueError("unknown config %d" % config)
         return self
+
+    def set_heightmap(self, h):
+        """heightmap_collider_component of the scene (dict as in scenes.terrain_drop)."""
+        mc = np.ascontiguousarray(h["min_corner"], dtype=np.float32); hh = np.ascontiguousarray(h["heights"], dtype=np.uint16)
+        self.lib.b200host_set_heightmap(self.ptr, int(h["chunks_per_dim"]), float(h["chunk_size"]), _p(mc), float(h["amplitude_scale"]), float(h["restitution"]), float(h["friction"]), _p(hh))
 
     def arrays(self):
         """Flat boundary arrays (what physicsStepInternal's gather produces)."""

@@ -270,6 +270,19 @@ int b200host_build_config(void* sp, int config, uint32_t nx, uint32_t ny, uint32
 // x-layers [ix0, ix1) of the config-3 mixed pile of nxTotal x ny x nz bodies + the static boxes of the WHOLE pile (replicated on every
 // rank): the multi-GPU slab of the bench. The random stream is advanced for every lattice site, so the union over all slabs is exactly
 // the scene b200host_build_config(3, nxTotal, ny, nz, ...) builds, whatever the number of ranks.
+// addComponent<heightmap_collider_component>(chunksPerDim, chunkSize, material) + update(minCorner, amplitudeScale) + setHeights per chunk
+int b200host_set_heightmap(void* sp, uint32_t chunksPerDim, float chunkSize, const float* minCorner3, float amplitudeScale, float restitution, float friction, const uint16_t* heights)
+{
+    game_scene& s = *(game_scene*)sp;
+    s.heightmaps.clear();
+    physics_material m; memset(&m, 0, sizeof(m)); m.restitution = restitution; m.friction = friction; m.density = 1.f;
+    s.heightmaps.emplace_back(chunksPerDim, chunkSize, m);
+    heightmap_collider_component& hm = s.heightmaps.back();
+    hm.update(b200::mk3(minCorner3[0], minCorner3[1], minCorner3[2]), amplitudeScale);
+    for (uint32_t z = 0; z < chunksPerDim; ++z) for (uint32_t x = 0; x < chunksPerDim; ++x) hm.setHeights(x, z, heights + (size_t)(z * chunksPerDim + x) * 129u * 129u);
+    return 0;
+}
+
 int b200host_build_mixed_slab(void* sp, uint32_t nxTotal, uint32_t ny, uint32_t nz, uint32_t ix0, uint32_t ix1, uint64_t seed, float spacing)
 {
     game_scene& s = *(game_scene*)sp;

@@ -752,6 +752,7 @@ static int ensureContext(game_scene& scene)
     if (scene.ctx) return 0;
     b200phys_config cfg; memset(&cfg, 0, sizeof(cfg));
     cfg.device = 0; cfg.maxBodies = nb + (nb >> 2) + 16; cfg.maxColliders = nc + (nc >> 2) + 16; cfg.maxTransforms = (uint32_t)scene.entities.size() + 1; cfg.maxJointsPerKind = (uint32_t)nj + 16;
+    if (!scene.heightmaps.empty()) cfg.maxContacts = 2u * 16u * cfg.maxColliders + 64u * cfg.maxColliders;     // one contact per touching triangle
     scene.collidersDirty = scene.jointsDirty = scene.hullsDirty = true;
     return b200phys_create(&cfg, &scene.ctx);
 }
@@ -785,6 +786,15 @@ static int physicsStepInternal(game_scene& scene, const physics_settings& settin
         r = b200phys_upload_transforms(scene.ctx, xf.data(), (uint32_t)xf.size()); if (r) return r;
         r = b200phys_upload_colliders(scene.ctx, cols.data(), (uint32_t)cols.size()); if (r) return r;
         scene.collidersDirty = false;
+    }
+    if (!scene.heightmaps.empty() && scene.heightmaps[0].dirty)
+    {   // physics.cpp:1238-1248 loops over every heightmap entity; scenes have one terrain, the device context holds one
+        heightmap_collider_component& hm = scene.heightmaps[0];
+        b200phys_heightmap d; memset(&d, 0, sizeof(d));
+        d.chunksPerDim = hm.chunksPerDim; d.chunkSize = hm.chunkSize; d.minCorner[0] = hm.minCorner.x; d.minCorner[1] = hm.minCorner.y; d.minCorner[2] = hm.minCorner.z;
+        d.amplitudeScale = hm.amplitudeScale; d.restitution = hm.material.restitution; d.friction = hm.material.friction;
+        r = b200phys_upload_heightmap(scene.ctx, &d, hm.heights.data()); if (r) return r;
+        hm.dirty = false;
     }
     {   // joint parameters (motor targets etc.) are host-mutable between steps (learned_locomotion.cpp:73-91): re-upload every step
         for (int k = 0; k < 6; ++k)

@@ -12,6 +12,7 @@
 #include <functional>
 #include <string>
 #include <vector>
+#include <cstring>
 #include <thread>
 #include <iosfwd>
 #include "../csrc/b200_math.cuh"       // the same fp32 helpers the kernels use (host + device)
@@ -128,6 +129,20 @@ struct collision_end_event
 typedef std::function<void(const collision_begin_event&)> collision_begin_event_func;
 typedef std::function<void(const collision_end_event&)> collision_end_event_func;
 
+// terrain/heightmap_collider.h:132-150: the terrain's collision representation, chunksPerDim^2 chunks of 129 x 129 uint16 heights
+// (heightmap_collider_chunk::setHeights keeps a pointer per chunk; here the component owns one contiguous copy, chunk (x, z) at
+// z * chunksPerDim + x). update() moves / rescales it like the reference (heightmap_collider.cpp:14-19).
+struct heightmap_collider_component
+{
+    heightmap_collider_component(uint32_t chunksPerDim, float chunkSize, physics_material material) : chunksPerDim(chunksPerDim), chunkSize(chunkSize), material(material)
+    { heights.assign((size_t)chunksPerDim * chunksPerDim * 129u * 129u, 0); }
+    void update(vec3 minCorner, float amplitudeScale) { this->minCorner = minCorner; this->amplitudeScale = amplitudeScale; dirty = true; }
+    void setHeights(uint32_t x, uint32_t z, const uint16_t* h) { memcpy(heights.data() + (size_t)(z * chunksPerDim + x) * 129u * 129u, h, sizeof(uint16_t) * 129u * 129u); dirty = true; }
+    uint32_t chunksPerDim; float chunkSize; physics_material material;
+    vec3 minCorner = b200::mk3(0.f); float amplitudeScale = 1.f;
+    std::vector<uint16_t> heights; bool dirty = true;
+};
+
 // physics.h:382-400
 struct physics_settings
 {
@@ -194,6 +209,7 @@ struct game_scene
     std::vector<trigger_component> triggers; std::vector<entity_handle> triggerEntity;
     std::vector<force_field_component> forceFields; std::vector<entity_handle> forceFieldEntity;
     std::vector<bounding_hull_geometry> hullGeometries;
+    std::vector<heightmap_collider_component> heightmaps;       // scene.view<heightmap_collider_component>() (physics.cpp:1238); the device holds one
     std::vector<distance_constraint> distanceConstraints; std::vector<ball_constraint> ballConstraints; std::vector<fixed_constraint> fixedConstraints;
     std::vector<hinge_constraint> hingeConstraints; std::vector<cone_twist_constraint> coneTwistConstraints; std::vector<slider_constraint> sliderConstraints;
     std::vector<b200phys_body_pair> constraintEntities[6];      // (entityA, entityB) per joint, storage order

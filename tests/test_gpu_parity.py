@@ -186,6 +186,23 @@ def test_host_mirror_physics_step_matches_abi():
     assert np.allclose(hs.render_transforms()[:, 4:7], sc["bodies"]["position"])
 
 
+def test_host_mirror_heightmap_component():
+    """heightmap_collider_component on the host mirror's scene: physicsStep() uploads it and the spheres of config 1 (ground box moved
+    far below) come to rest on the terrain exactly as through the C ABI."""
+    sc = host.build_scene(host.CONFIG_SPHERES_ON_GROUND, 6, 1, 6, seed=15681923, mode=1, spacing=1.25)
+    hm = scenes.terrain_drop(2)["heightmap"]
+    hm = dict(hm, min_corner=np.array([-16.0, -3.0, -16.0], dtype=np.float32))
+    hs = sc["host_scene"]; hs.set_heightmap(hm)
+    st = make_stepper(dict(sc, heightmap=hm), max_contacts=64 * len(sc["colliders"]) + 1024)
+    timer = 0.0
+    for _ in range(20):
+        st.step(DT, 30, abi.STEP_FAST)
+        timer = hs.physics_step(timer, float(DT), iterations=30)
+    direct = st.download_bodies(); via_host = hs.arrays()["bodies"]
+    assert st.stats().numContacts > 0
+    assert np.array_equal(via_host["position"], direct["position"]) and np.array_equal(via_host["linearVelocity"], direct["linearVelocity"])
+
+
 import golden_util
 
 
