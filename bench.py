@@ -318,10 +318,11 @@ def main():
             t = torch.tensor([x], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.SUM); return float(t.item())
         return x
 
-    nccl_id = [None]
-    if world > 1:
-        nccl_id = [abi.dist_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(nccl_id, src=0)      # the library owns its own NCCL communicator (b200phys_create_distributed)
+    def fresh_nccl_id():
+        """One ncclUniqueId per communicator (an id cannot be used twice): rank 0 creates it, torch.distributed hands it to the others."""
+        box = [abi.dist_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)          # the library owns its own NCCL communicator (b200phys_create_distributed)
+        return box[0]
 
     def sharded(sc, ghost_layers=3.0):
         """Stepper for this rank's part of a slab-decomposed scene; with N > 1 the context is created by b200phys_create_distributed and
@@ -339,7 +340,7 @@ def main():
         if world > 1:
             dc = abi.DistConfig(); dc.rank = rank; dc.nranks = world; dc.axis = 0; dc.slabLo = float(bounds[rank]); dc.slabHi = float(bounds[rank + 1]); dc.ghostWidth = 1.05
             dc.maxGhostBodies = ghost_cap; dc.maxGhostColliders = ghost_cap
-        st = make_stepper(sc, device=local_rank, dist=(dc, nccl_id[0]) if dc is not None else None)
+        st = make_stepper(sc, device=local_rank, dist=(dc, fresh_nccl_id()) if dc is not None else None)
         st.set_stream(stream.cuda_stream)
         return st
 

@@ -174,6 +174,7 @@ int b200phys_destroy(b200phys_context* ctx)
     cudaSetDevice(ctx->c.device);
     cudaDeviceSynchronize();
     dropGraphs(ctx->c);
+    destroyEnv(&ctx->c);
     destroyDist(&ctx->c);
     freeAll(ctx->c);
     delete ctx;

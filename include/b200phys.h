@@ -234,6 +234,36 @@ void b200phys_host_free(void* p);
  * memory is staged by the driver before the call returns and may be reused at once. PAGE-LOCKED memory (b200phys_host_alloc,
  * cudaHostAlloc) is read by DMA later: it must stay untouched until the next call that synchronises the context has returned
  * (b200phys_synchronize, any b200phys_download_*, b200phys_get_stats). */
+/* batched locomotion environment on the device (reference: src/learning/learned_locomotion.{h,cpp}, the RL environment its Physics-Lib
+ * DLL exports as getPhysicsStateSize / getPhysicsActionSize / getPhysicsRanges / resetPhysics / updatePhysics, :393-488). The scene
+ * (E identical articulated figures + static ground) is uploaded through the normal entry points; this table tells the library where
+ * each environment's bodies / joints / colliders are and what its training targets are. Per step only E x actionFloats go up and
+ * E x (stateFloats + 2) come down; action smoothing + motor targets, the random pushes, state, reward and failure flag are evaluated
+ * on the device (csrc/k_env.cu). actionFloats = 3 * coneTwistsPerEnv + hingesPerEnv, stateFloats = 39 + actionFloats. */
+typedef struct b200phys_locomotion_env {
+    uint32_t numEnvs, partsPerEnv /* <= 16 */, coneTwistsPerEnv, hingesPerEnv, collidersPerEnv;
+    int32_t  parentPart[16];            /* ragdoll.cpp:156-169, -1 = root */
+    uint32_t stateParts[6];             /* the body parts of learning_state in its order: left toes, right toes, torso, head, left / right lower arm */
+    uint32_t torsoPart, headPart;
+    const uint32_t* firstBody;          /* [numEnvs] first rigid body index (parts are consecutive) */
+    const uint32_t* firstConeTwist;     /* [numEnvs] first cone-twist joint index */
+    const uint32_t* firstHinge;         /* [numEnvs] */
+    const uint32_t* firstCollider;      /* [numEnvs] first (lowest) collider index of the environment's collidersPerEnv consecutive colliders */
+    const float* initialRotations;      /* [numEnvs][parts][4] reset pose */
+    const float* initialPositions;      /* [numEnvs][parts][3] */
+    const float* localPositions;        /* [parts][6][3] the six face centres of each part's local bounds (training_locomotion::getLocalPositions) */
+    const float* targetPositions;       /* [numEnvs][parts][6][3] */
+    const float* targetVelocities;      /* [numEnvs][parts][6][3] */
+    const float* targetRotations;       /* [numEnvs][parts][4] local target rotation */
+    const float* headTargetHeights;     /* [numEnvs] */
+    const unsigned long long* seeds;    /* [numEnvs] xorshift64 state of the push generator, NULL = default per-environment seeds */
+} b200phys_locomotion_env;
+int b200phys_env_create(b200phys_context* ctx, const b200phys_locomotion_env* desc);   /* after bodies / colliders / joints are uploaded */
+int b200phys_env_set_seed(b200phys_context* ctx, uint32_t env, unsigned long long seed);
+int b200phys_env_reset(b200phys_context* ctx, const uint32_t* envIndices, uint32_t count);                      /* resetPhysics for these environments */
+int b200phys_env_step(b200phys_context* ctx, const float* actions, float dt, uint32_t numSolverIterations, uint32_t flags, float pushProbability,
+                      float* outStates, float* outRewards, int32_t* outFailed);                                   /* updatePhysics for all of them */
+
 /* heightmap collision (reference: heightmap_collider_component, terrain/heightmap_collider.h:132-150, collided against every rigid body
  * collider of type sphere / capsule / AABB / OBB by heightmapCollision, physics/heightmap_collision.cpp:509-618, physics.cpp:1238-1248).
  * heights: chunksPerDim^2 chunks of 129 x 129 uint16 (TERRAIN_LOD_0_VERTICES_PER_DIMENSION), chunk (x, z) at z * chunksPerDim + x, row
