@@ -86,7 +86,7 @@ class Stats(C.Structure):
 
 # every symbol include/b200phys.h declares (tests check that the library exports all of them)
 EXPORTS = [
-    "b200phys_version", "b200phys_error_string", "b200phys_create", "b200phys_destroy", "b200phys_set_stream", "b200phys_enable_timing", "b200phys_enable_graphs", "b200phys_upload_heightmap",
+    "b200phys_version", "b200phys_error_string", "b200phys_create", "b200phys_destroy", "b200phys_set_stream", "b200phys_enable_timing", "b200phys_enable_graphs", "b200phys_upload_heightmap", "b200phys_env_create", "b200phys_env_set_seed", "b200phys_env_reset", "b200phys_env_step",
     "b200phys_host_alloc", "b200phys_host_free",
     "b200phys_set_hulls", "b200phys_upload_bodies", "b200phys_upload_transforms", "b200phys_upload_colliders", "b200phys_upload_joints",
     "b200phys_upload_forces", "b200phys_upload_body_states", "b200phys_step", "b200phys_synchronize", "b200phys_download_bodies", "b200phys_get_stats",

@@ -94,9 +94,10 @@ __global__ void __launch_bounds__(128) envPushKernel(EnvParams P, float pushProb
             {
                 const uint32_t ci = P.firstCollider[e] + (P.colliders - 1u - k);
                 const float4 c0 = cLocal[4 * ci], c1 = cLocal[4 * ci + 1], c2 = cLocal[4 * ci + 2], c3 = cLocal[4 * ci + 3];
-                const uint32_t tw = __float_as_uint(c3.x), type = tw & 0xFFu, objType = (tw >> 8) & 0xFFu;
+                // uploaded b200phys_collider record: shape[10], restitution, friction | density, (type, objectType, reserved), objectIndex, parentTransform
+                const uint32_t tw = __float_as_uint(c3.y), type = tw & 0xFFu, objType = (tw >> 8) & 0xFFu;
                 if (objType != B200PHYS_OBJ_RIGID_BODY) continue;
-                const uint32_t rb = __float_as_uint(c3.y);
+                const uint32_t rb = __float_as_uint(c3.z);
                 if (rb < fb || rb - fb >= P.parts) continue;
                 const q4 rot = asQ(bRot[rb]); const float4 p4 = bPos[rb]; const f3 pos = mk3(p4.x, p4.y, p4.z);
                 const lray local = { conjugate(rot) * (origin - pos), conjugate(rot) * direction };

@@ -182,6 +182,7 @@ class LocomotionEnv:
         lib.b200env_set_push_probability.argtypes = [C.c_void_p, C.c_float]
         lib.b200env_set_seed.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64]
         lib.b200env_set_exact_order.argtypes = [C.c_void_p, C.c_int]
+        lib.b200env_set_device_mode.argtypes = [C.c_void_p, C.c_int]
         self.num_envs = int(num_envs)
         self.state_size = int(lib.b200env_state_size()); self.action_size = int(lib.b200env_action_size())
         self.ptr = C.c_void_p(lib.b200env_create(self.num_envs, spacing))
@@ -198,6 +199,10 @@ class LocomotionEnv:
     def set_push_probability(self, p):
         """Chance per environment and step of a random sideways push (0.02 in the reference, learned_locomotion.cpp:448)."""
         self.lib.b200env_set_push_probability(self.ptr, float(p))
+
+    def set_device_mode(self, on=True):
+        """Everything per environment on the GPU (csrc/k_env.cu): actions up, states / rewards / flags down. Choose before the first step."""
+        self.lib.b200env_set_device_mode(self.ptr, 1 if on else 0)
 
     def set_exact_order(self, on=True):
         """Canonical Gauss-Seidel order (the reference's scalar solver order) instead of the fast colour-sorted one."""

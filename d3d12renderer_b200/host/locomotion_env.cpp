@@ -34,7 +34,7 @@ struct Env
     vec3 localPositions[kParts][6];
     vec3 targetPositions[kParts][6], targetVelocities[kParts][6]; quat localTargetRotation[kParts];
     trs initialTransform[kParts];
-    uint32_t firstBody, firstConeTwist, firstHinge;
+    uint32_t firstBody, firstConeTwist, firstHinge, firstColliderCreated, numColliders;
     uint64_t rngState;
 };
 
@@ -45,6 +45,7 @@ struct locomotion_env_batch
     game_scene scene; std::vector<Env> envs; float physicsTimer = 0.f;
     float pushProbability = 0.02f;      // learned_locomotion.cpp:448
     bool exactOrder = false;            // canonical Gauss-Seidel order (B200PHYS_STEP_EXACT_ORDER) instead of the colour-sorted fast order
+    bool deviceMode = false, deviceReady = false;   // everything per environment on the GPU (csrc/k_env.cu): only actions go up, states / rewards / flags come down
 
     static uint64_t nextRandom(uint64_t& state) { uint64_t x = state; x ^= x << 13; x ^= x >> 7; x ^= x << 17; state = x; return x; }          // core/random.h:14-24
     static float random01(uint64_t& state) { return (uint32_t)nextRandom(state) / (float)0xFFFFFFFFu; }
@@ -58,7 +59,7 @@ struct locomotion_env_batch
         // g++ (which compiles the reference for the parity tests) and MSVC x64 both evaluate constructor arguments right to left, so z is drawn first
         const float dz = -1.f + 2.f * random01(e.rngState), dx = -1.f + 2.f * random01(e.rngState);
         const vec3 direction = b200::normalize(b200::mk3(dx, 0.f, dz));
-        testPhysicsInteraction(scene, target - direction * 5.f, direction, 1000.f, e.firstBody, kParts);
+        testPhysicsInteraction(scene, target - direction * 5.f, direction, 1000.f, e.firstBody, kParts, e.firstColliderCreated, e.numColliders);
     }
 
     // The reference reads transform_component everywhere in the environment (learned_locomotion.cpp:113-129, :284-311, :452), not
@@ -191,7 +192,9 @@ struct locomotion_env_batch
             Env& e = envs[i];
             e.rngState = 0x9E3779B97F4A7C15ull ^ ((uint64_t)(i + 1) * 0xD1B54A32D192ED03ull);
             e.firstBody = (uint32_t)scene.rigidBodies.size(); e.firstConeTwist = (uint32_t)scene.coneTwistConstraints.size(); e.firstHinge = (uint32_t)scene.hingeConstraints.size();
+            e.firstColliderCreated = (uint32_t)scene.colliders.size();
             e.ragdoll = humanoid_ragdoll::create(scene, b200::mk3((i % side) * spacing - half, 1.25f, (i / side) * spacing - half));
+            e.numColliders = (uint32_t)scene.colliders.size() - e.firstColliderCreated;
             for (uint32_t p = 0; p < kParts; ++p) e.initialTransform[p] = scene.physicsTransform1[e.firstBody + p];
         }
         const float ext = fmaxf(20.f, half + 10.f);
@@ -200,8 +203,56 @@ struct locomotion_env_batch
     }
 
     // updatePhysics (:462-488) for all environments: apply the actions, ONE 60 Hz physics step, read state / reward / failure
+    // one-time hand-over to the device: the scene as it stands + the per-environment tables of b200phys_env_create
+    int ensureDevice()
+    {
+        if (deviceReady) return 0;
+        int r = uploadSceneToDevice(scene); if (r) return r;
+        const uint32_t E = (uint32_t)envs.size(), nC = (uint32_t)scene.colliders.size();
+        std::vector<uint32_t> fb(E), fc(E), fh(E), fcol(E); std::vector<float> rot((size_t)E * kParts * 4), pos((size_t)E * kParts * 3), lp((size_t)kParts * 18), tp((size_t)E * kParts * 18), tv((size_t)E * kParts * 18), tr((size_t)E * kParts * 4), hh(E);
+        std::vector<unsigned long long> seeds(E);
+        for (uint32_t i = 0; i < E; ++i)
+        {
+            const Env& e = envs[i];
+            fb[i] = e.firstBody; fc[i] = e.firstConeTwist; fh[i] = e.firstHinge;
+            fcol[i] = nC - e.firstColliderCreated - e.numColliders;            // device collider index = reverse creation order (physics.cpp:635-641)
+            hh[i] = e.headTargetHeight; seeds[i] = e.rngState;
+            for (uint32_t p = 0; p < kParts; ++p)
+            {
+                const size_t k = (size_t)i * kParts + p; const trs& t = e.initialTransform[p];
+                rot[4 * k] = t.rotation.x; rot[4 * k + 1] = t.rotation.y; rot[4 * k + 2] = t.rotation.z; rot[4 * k + 3] = t.rotation.w;
+                pos[3 * k] = t.position.x; pos[3 * k + 1] = t.position.y; pos[3 * k + 2] = t.position.z;
+                tr[4 * k] = e.localTargetRotation[p].x; tr[4 * k + 1] = e.localTargetRotation[p].y; tr[4 * k + 2] = e.localTargetRotation[p].z; tr[4 * k + 3] = e.localTargetRotation[p].w;
+                for (int j = 0; j < 6; ++j)
+                {
+                    const size_t q = (k * 6 + j) * 3;
+                    tp[q] = e.targetPositions[p][j].x; tp[q + 1] = e.targetPositions[p][j].y; tp[q + 2] = e.targetPositions[p][j].z;
+                    tv[q] = e.targetVelocities[p][j].x; tv[q + 1] = e.targetVelocities[p][j].y; tv[q + 2] = e.targetVelocities[p][j].z;
+                    if (i == 0) { const size_t l = ((size_t)p * 6 + j) * 3; lp[l] = e.localPositions[p][j].x; lp[l + 1] = e.localPositions[p][j].y; lp[l + 2] = e.localPositions[p][j].z; }
+                }
+            }
+        }
+        b200phys_locomotion_env d; memset(&d, 0, sizeof(d));
+        d.numEnvs = E; d.partsPerEnv = kParts; d.coneTwistsPerEnv = kConeTwists; d.hingesPerEnv = kHinges; d.collidersPerEnv = envs[0].numColliders;
+        for (uint32_t p = 0; p < 16; ++p) d.parentPart[p] = p < kParts ? kParent[p] : -1;
+        const uint32_t sp[6] = { lToes, rToes, torso, head, lLowerArm, rLowerArm }; memcpy(d.stateParts, sp, sizeof(sp));
+        d.torsoPart = torso; d.headPart = head;
+        d.firstBody = fb.data(); d.firstConeTwist = fc.data(); d.firstHinge = fh.data(); d.firstCollider = fcol.data();
+        d.initialRotations = rot.data(); d.initialPositions = pos.data(); d.localPositions = lp.data(); d.targetPositions = tp.data(); d.targetVelocities = tv.data();
+        d.targetRotations = tr.data(); d.headTargetHeights = hh.data(); d.seeds = seeds.data();
+        r = b200phys_env_create(scene.ctx, &d); if (r) return r;
+        deviceReady = true;
+        return 0;
+    }
+
     int step(const float* actions, float* outStates, float* outRewards, int* outFailed)
     {
+        if (deviceMode)
+        {
+            int r = ensureDevice(); if (r) return r;
+            return b200phys_env_step(scene.ctx, actions, 1.f / 60.f, physics_settings().numRigidSolverIterations, exactOrder ? B200PHYS_STEP_EXACT_ORDER : B200PHYS_STEP_FAST,
+                                     pushProbability, outStates, outRewards, (int32_t*)outFailed);
+        }
         parallelFor((uint32_t)envs.size(), [&](uint32_t i) { applyAction(envs[i], actions + (size_t)i * kActionFloats); }, 256u);
         scene.jointsDirty = true;
         if (pushProbability > 0.f) for (Env& e : envs) maybePush(e);
@@ -232,15 +283,27 @@ uint32_t b200env_state_size(void) { return kStateFloats; }
 uint32_t b200env_action_size(void) { return kActionFloats; }
 void b200env_set_push_probability(void* env, float p) { ((locomotion_env_batch*)env)->pushProbability = p; }
 void b200env_set_exact_order(void* env, int on) { ((locomotion_env_batch*)env)->exactOrder = on != 0; }
+// on: everything per environment runs on the GPU (csrc/k_env.cu); choose before the first step
+void b200env_set_device_mode(void* env, int on) { locomotion_env_batch& b = *(locomotion_env_batch*)env; if (!b.deviceReady) b.deviceMode = on != 0; }
 // seed of one environment's push generator (xorshift64 state, core/random.h: the reference seeds its single generator with the wall clock)
-void b200env_set_seed(void* env, uint32_t index, uint64_t seed) { locomotion_env_batch& b = *(locomotion_env_batch*)env; if (index < b.envs.size()) b.envs[index].rngState = seed; }
+void b200env_set_seed(void* env, uint32_t index, uint64_t seed)
+{
+    locomotion_env_batch& b = *(locomotion_env_batch*)env;
+    if (index >= b.envs.size()) return;
+    b.envs[index].rngState = seed;
+    if (b.deviceReady) b200phys_env_set_seed(b.scene.ctx, index, seed);
+}
 uint32_t b200env_num_envs(void* env) { return (uint32_t)((locomotion_env_batch*)env)->envs.size(); }
 // index < 0: every environment; writes the state(s) after the reset
 void b200env_reset(void* env, int index, float* outStates)
 {
     locomotion_env_batch& b = *(locomotion_env_batch*)env;
     for (uint32_t i = 0; i < b.envs.size(); ++i)
-        if (index < 0 || (uint32_t)index == i) { b.reset(i); if (outStates) b.getState(b.envs[i], outStates + (size_t)(index < 0 ? i : 0) * kStateFloats); }
+        if (index < 0 || (uint32_t)index == i)
+        {   // in device mode the host copy of an environment only ever holds its reset state: reset it too and read the state from it
+            b.reset(i); if (outStates) b.getState(b.envs[i], outStates + (size_t)(index < 0 ? i : 0) * kStateFloats);
+            if (b.deviceReady) b200phys_env_reset(b.scene.ctx, &i, 1);
+        }
 }
 float b200env_reward(void* env, uint32_t index) { locomotion_env_batch& b = *(locomotion_env_batch*)env; return b.getReward(b.envs[index]); }
 int b200env_step(void* env, const float* actions, float* outStates, float* outRewards, int* outFailed) { return ((locomotion_env_batch*)env)->step(actions, outStates, outRewards, outFailed); }

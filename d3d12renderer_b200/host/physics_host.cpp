@@ -757,10 +757,10 @@ static int ensureContext(game_scene& scene)
     return b200phys_create(&cfg, &scene.ctx);
 }
 
-// physicsStepInternal (physics.cpp:1180-1362): gather pools -> C ABI -> scatter results
-static int physicsStepInternal(game_scene& scene, const physics_settings& settings, float dt)
+// the gather half of physicsStepInternal: every pool that changed goes to the device (also used once by the device-side RL environment)
+int uploadSceneToDevice(game_scene& scene)
 {
-    if (scene.rigidBodies.empty()) return 0;   // physics.cpp:1186-1189
+    if (scene.rigidBodies.empty()) return 0;
     int r = ensureContext(scene); if (r) return r;
     if (scene.hullsDirty)
     {
@@ -820,6 +820,15 @@ static int physicsStepInternal(game_scene& scene, const physics_settings& settin
         const float g3[3] = { global.x, global.y, global.z };
         r = b200phys_set_global_force_field(scene.ctx, g3); if (r) return r;
     }
+    return 0;
+}
+
+// physicsStepInternal (physics.cpp:1180-1362): gather pools -> C ABI -> scatter results
+static int physicsStepInternal(game_scene& scene, const physics_settings& settings, float dt)
+{
+    if (scene.rigidBodies.empty()) return 0;   // physics.cpp:1186-1189
+    int r = uploadSceneToDevice(scene); if (r) return r;
+    const uint32_t numBodies = (uint32_t)scene.rigidBodies.size();
     const bool wantEvents = (bool)settings.collisionBeginCallback || (bool)settings.collisionEndCallback;
     if (wantEvents != scene.eventsEnabled) { r = b200phys_enable_events(scene.ctx, wantEvents ? 1 : 0); if (r) return r; scene.eventsEnabled = wantEvents; }
     r = b200phys_step(scene.ctx, dt, settings.numRigidSolverIterations, settings.exactConstraintOrder ? B200PHYS_STEP_EXACT_ORDER : B200PHYS_STEP_FAST); if (r) return r;

@@ -322,8 +322,10 @@ bool saveSceneYaml(const game_scene& scene, std::ostream& out, const char* scene
 int loadSceneYaml(game_scene& scene, std::istream& in);      // entities created, -1 if the input has no "Entities" list
 
 // physics.h:404: a ray pushes the first rigid body it hits (force + torque accumulators for the next step); ray_interaction.cpp
-void testPhysicsInteraction(game_scene& scene, vec3 rayOrigin, vec3 rayDirection, float strength = 1000.f, uint32_t firstBody = 0, uint32_t numBodies = 0xFFFFFFFFu);   // the body range restricts the test (batched environments)
+void testPhysicsInteraction(game_scene& scene, vec3 rayOrigin, vec3 rayDirection, float strength = 1000.f, uint32_t firstBody = 0, uint32_t numBodies = 0xFFFFFFFFu,
+                            uint32_t firstCollider = 0, uint32_t numColliders = 0xFFFFFFFFu);   // body / collider (creation order) ranges restrict the test (batched environments)
 
 int physicsStep(game_scene& scene, memory_arena& arena, float& timer, const physics_settings& settings, float dt);
+int uploadSceneToDevice(game_scene& scene);     // creates the device context if needed and uploads whatever changed, without stepping
 
 } // namespace b200host

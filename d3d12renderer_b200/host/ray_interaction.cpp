@@ -13,11 +13,14 @@ namespace b200host {
 using b200::mk3; using b200::mkq; using b200::dot; using b200::cross; using b200::len; using b200::sqLen; using b200::normalize; using b200::conjugate;
 using b200::lray; using b200::intersectSphere; using b200::intersectCapsule; using b200::intersectCylinder; using b200::intersectAABB; using b200::intersectTriangle;
 
-void testPhysicsInteraction(game_scene& scene, vec3 origin, vec3 direction, float strength, uint32_t firstBody, uint32_t numBodies)
+void testPhysicsInteraction(game_scene& scene, vec3 origin, vec3 direction, float strength, uint32_t firstBody, uint32_t numBodies, uint32_t firstCollider, uint32_t numColliders)
 {
     float minT = FLT_MAX; int32_t minRB = -1; vec3 force = mk3(0.f), torque = mk3(0.f);
-    for (const collider_component& collider : scene.colliders)
+    const size_t c0 = firstCollider < scene.colliders.size() ? firstCollider : scene.colliders.size();
+    const size_t c1 = (numColliders < scene.colliders.size() - c0) ? c0 + numColliders : scene.colliders.size();
+    for (size_t ci = c0; ci < c1; ++ci)
     {
+        const collider_component& collider = scene.colliders[ci];
         const game_scene::entity_data& parent = scene.entities[collider.parentEntity];
         if (parent.rigidBody < 0) continue;
         if ((uint32_t)parent.rigidBody < firstBody || (uint32_t)parent.rigidBody - firstBody >= numBodies) continue;

@@ -295,3 +295,37 @@ def test_locomotion_env_matches_the_reference_environment():
             assert err <= tol, "state differs at step %d (action scale %g, push %g): %g" % (step, scale, push, err)
             assert abs(rewards[0] - rr) <= 4e-3, "reward differs at step %d: %g vs %g" % (step, rewards[0], rr)
     env.close()
+
+
+def test_device_side_environment_matches_the_host_side_one():
+    """b200env in device mode (csrc/k_env.cu: action smoothing + motor targets, random pushes, state, reward, failure flag all on the GPU,
+    bodies and joints never leave it) against the host-side evaluation of the same formulas (host/locomotion_env.cpp, itself pinned
+    against the reference's own environment above): 64 environments, random actions, pushes with probability 0.3 from the same
+    generator seeds, resets whenever an environment fails. The physics is the same CUDA step on the same inputs, so the states agree
+    to rounding of the few host-vs-device libm calls; the reward goes through acos / exp."""
+    E = 64
+    envs = []
+    for device in (False, True):
+        env = host.LocomotionEnv(E, spacing=6.0)
+        env.set_device_mode(device)
+        env.set_push_probability(0.3)
+        for i in range(E):
+            env.set_seed(i, 1000 + 17 * i)
+        env.reset()
+        envs.append(env)
+    lo, hi = envs[0].action_ranges()
+    rng = np.random.default_rng(5)
+    resets = 0
+    for step in range(150):
+        a = (1.0 * rng.uniform(lo, hi, size=(E, len(lo)))).astype(np.float32)
+        sh, rh, fh = envs[0].step(a)
+        sd, rd, fd = envs[1].step(a)
+        assert np.array_equal(fh, fd), "failure flags differ at step %d" % step
+        err = float(np.max(np.abs(sh - sd) / np.maximum(1.0, np.abs(sh))))
+        assert err <= 1e-5, "states differ at step %d: %g" % (step, err)
+        assert float(np.max(np.abs(rh - rd))) <= 5e-3, "rewards differ at step %d: %g" % (step, float(np.max(np.abs(rh - rd))))
+        for i in list(np.nonzero(fh)[0]) + ([3, 7] if step == 25 else []):       # a failed environment is reset; two more once, whatever their state
+            envs[0].reset(int(i)); envs[1].reset(int(i)); resets += 1
+    assert resets > 2, "no environment ever failed: the reset path is untested"
+    for env in envs:
+        env.close()
