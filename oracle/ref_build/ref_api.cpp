@@ -13,6 +13,7 @@
 #include "physics/ragdoll.h"
 #include "physics/vehicle.h"
 #include "physics/heightmap_collision.h"
+#include "physics/cloth.h"
 #include "terrain/heightmap_collider.h"
 #include "scene/scene.h"
 #include "core/random.h"
@@ -73,6 +74,14 @@ void writeWorldCollider(const collider_union& w, float* out16)
 }
 
 } // namespace
+
+// cloth_component keeps its particles private and befriends cloth_render_component, which the PHYSICS_ONLY build does not define
+// (cloth.h:57-72): this definition only reads the particle arrays.
+struct cloth_render_component
+{
+    static const std::vector<vec3>& positions(const cloth_component& c) { return c.positions; }
+    static const std::vector<vec3>& velocities(const cloth_component& c) { return c.velocities; }
+};
 
 extern "C" {
 
@@ -255,6 +264,26 @@ float ref_scene_heightmap_height_at(void* p, float x, float z)
     RefScene& R = *(RefScene*)p;
     for (auto [h, hm] : R.scene.view<heightmap_collider_component>().each()) return hm.getHeightAt(vec2(x, z));
     return -FLT_MAX;
+}
+// cloth (physics/cloth.{h,cpp}); physicsStepInternal applies the global force field as wind and simulates (physics.cpp:1354-1358)
+void* ref_cloth_create(float width, float height, uint32 gx, uint32 gy, float totalMass, float stiffness, float damping, float gravityFactor)
+{ return new cloth_component(width, height, gx, gy, totalMass, stiffness, damping, gravityFactor); }
+void ref_cloth_destroy(void* c) { delete (cloth_component*)c; }
+void ref_cloth_set_fixed(void* c, const float* rot4, const float* pos3, const float* scale3, int moveRigid)
+{ trs t; t.rotation = q4(rot4); t.position = v3(pos3); t.scale = v3(scale3); ((cloth_component*)c)->setWorldPositionOfFixedVertices(t, moveRigid != 0); }
+void ref_cloth_set_properties(void* c, float totalMass, float stiffness, float damping, float gravityFactor)
+{ cloth_component& k = *(cloth_component*)c; k.totalMass = totalMass; k.stiffness = stiffness; k.damping = damping; k.gravityFactor = gravityFactor; }
+void ref_cloth_wind(void* c, const float* f3) { ((cloth_component*)c)->applyWindForce(v3(f3)); }
+void ref_cloth_simulate(void* c, uint32 vi, uint32 pi, uint32 di, float dt) { ((cloth_component*)c)->simulate(vi, pi, di, dt); }
+void ref_cloth_get(void* c, float* positions, float* velocities)
+{
+    const cloth_component& k = *(cloth_component*)c;
+    const std::vector<vec3>& p = cloth_render_component::positions(k); const std::vector<vec3>& v = cloth_render_component::velocities(k);
+    for (size_t i = 0; i < p.size(); ++i)
+    {
+        if (positions) { positions[3 * i] = p[i].x; positions[3 * i + 1] = p[i].y; positions[3 * i + 2] = p[i].z; }
+        if (velocities) { velocities[3 * i] = v[i].x; velocities[3 * i + 1] = v[i].y; velocities[3 * i + 2] = v[i].z; }
+    }
 }
 uint32 ref_scene_num_bodies(void* p) { return (uint32)((RefScene*)p)->bodyEntities.size(); }
 uint32 ref_scene_num_colliders(void* p) { return ((RefScene*)p)->scene.numberOfComponentsOfType<collider_component>(); }

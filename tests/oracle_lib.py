@@ -69,6 +69,9 @@ def load():
     lib.oracle_get_stage_ms.argtypes = [vp, vp]
     lib.oracle_collide_pair.argtypes = [vp, vp, vp, vp, vp]; lib.oracle_collide_pair.restype = C.c_int
     lib.oracle_mass_properties.argtypes = [vp, vp, vp, vp, vp]
+    lib.oracle_cloth_create.argtypes = [f32, f32, u32, u32, f32, f32, f32, f32]; lib.oracle_cloth_create.restype = vp
+    lib.oracle_cloth_destroy.argtypes = [vp]; lib.oracle_cloth_set_fixed.argtypes = [vp, vp, vp, vp, C.c_int]; lib.oracle_cloth_set_properties.argtypes = [vp, f32, f32, f32, f32]
+    lib.oracle_cloth_wind.argtypes = [vp, vp]; lib.oracle_cloth_simulate.argtypes = [vp, u32, u32, u32, f32]; lib.oracle_cloth_get.argtypes = [vp, vp, vp]
     lib.oracle_set_heightmap.argtypes = [vp, u32, f32, vp, f32, f32, f32, vp]
     lib.oracle_heightmap_height_at.argtypes = [vp, f32, f32]; lib.oracle_heightmap_height_at.restype = f32
     lib.oracle_combine_mass.argtypes = [vp, vp, vp, u32, vp, vp, vp]

@@ -49,6 +49,9 @@ def load(fast=False):
     lib.ref_env_sizes.argtypes = [vp, vp]; lib.ref_env_ranges.argtypes = [vp, vp]
     lib.ref_env_reset.argtypes = [C.c_uint64, f32, i32, vp]; lib.ref_env_update.argtypes = [vp, vp, vp]; lib.ref_env_update.restype = i32
     lib.ref_mass_properties.argtypes = [vp, vp, vp, vp]
+    lib.ref_cloth_create.argtypes = [f32, f32, u32, u32, f32, f32, f32, f32]; lib.ref_cloth_create.restype = vp
+    lib.ref_cloth_destroy.argtypes = [vp]; lib.ref_cloth_set_fixed.argtypes = [vp, vp, vp, vp, i32]; lib.ref_cloth_set_properties.argtypes = [vp, f32, f32, f32, f32]
+    lib.ref_cloth_wind.argtypes = [vp, vp]; lib.ref_cloth_simulate.argtypes = [vp, u32, u32, u32, f32]; lib.ref_cloth_get.argtypes = [vp, vp, vp]
     lib.ref_assert_count.argtypes = [i32]; lib.ref_assert_count.restype = u32
     _libs[key] = lib
     return lib
@@ -204,3 +207,39 @@ class RefEnv:
         a = np.ascontiguousarray(action, dtype=np.float32); out = np.zeros(self.state_size, dtype=np.float32); rew = np.zeros(1, dtype=np.float32)
         failed = self.lib.ref_env_update(_p(a), _p(out), _p(rew))
         return out, float(rew[0]), bool(failed)
+
+
+class _ClothBase:
+    """Same calls for the compiled reference's cloth_component and the oracle's restatement (prefix selects the library)."""
+
+    def __init__(self, lib, prefix, width, height, gx, gy, total_mass, stiffness=0.5, damping=0.3, gravity_factor=1.0):
+        self.lib = lib; self.prefix = prefix; self.n = gx * gy
+        self.ptr = C.c_void_p(getattr(lib, prefix + "create")(width, height, gx, gy, total_mass, stiffness, damping, gravity_factor))
+
+    def __del__(self):
+        try:
+            getattr(self.lib, self.prefix + "destroy")(self.ptr)
+        except Exception:
+            pass
+
+    def set_fixed(self, rotation, position, scale=(1, 1, 1), move_rigid=False):
+        r = np.ascontiguousarray(rotation, dtype=np.float32); p = np.ascontiguousarray(position, dtype=np.float32); s = np.ascontiguousarray(scale, dtype=np.float32)
+        getattr(self.lib, self.prefix + "set_fixed")(self.ptr, _p(r), _p(p), _p(s), 1 if move_rigid else 0)
+
+    def set_properties(self, total_mass, stiffness, damping, gravity_factor):
+        getattr(self.lib, self.prefix + "set_properties")(self.ptr, total_mass, stiffness, damping, gravity_factor)
+
+    def wind(self, force):
+        f = np.ascontiguousarray(force, dtype=np.float32); getattr(self.lib, self.prefix + "wind")(self.ptr, _p(f))
+
+    def simulate(self, vel_iters, pos_iters, drift_iters, dt):
+        getattr(self.lib, self.prefix + "simulate")(self.ptr, vel_iters, pos_iters, drift_iters, dt)
+
+    def state(self):
+        p = np.zeros((self.n, 3), dtype=np.float32); v = np.zeros((self.n, 3), dtype=np.float32)
+        getattr(self.lib, self.prefix + "get")(self.ptr, _p(p), _p(v)); return p, v
+
+
+class RefCloth(_ClothBase):
+    def __init__(self, *a, **kw):
+        super().__init__(load(), "ref_cloth_", *a, **kw)

@@ -225,3 +225,33 @@ def test_heightmap_collision_equals_oracle():
     assert touched > 50, "the scene must actually produce terrain contacts (%d)" % touched
     types = sc["colliders"]["type"]
     assert set(types) == {abi.SPHERE, abi.CAPSULE, abi.AABB, abi.OBB}
+
+
+def test_cloth_equals_oracle():
+    """cloth_component (cloth.cpp: wind, velocity / position / drift Gauss-Seidel passes in constraint creation order, damping,
+    moving the fixed row with and without the rigid move, a property change that triggers recalculateProperties): 60 steps, positions and
+    velocities bit for bit."""
+    class OracleCloth(ref_lib._ClothBase):
+        def __init__(self, *a, **kw):
+            super().__init__(oracle_lib.load(), "oracle_cloth_", *a, **kw)
+    args = (3.0, 4.0, 19, 26, 9.0, 0.6, 0.35, 0.9)
+    r = ref_lib.RefCloth(*args); o = OracleCloth(*args)
+    rng = np.random.default_rng(2)
+    q = np.array([0.0, np.sin(0.2), 0.0, np.cos(0.2)], dtype=np.float32)
+    for c in (r, o):
+        c.set_fixed(q, (0.5, 6.0, -1.0))
+    for step in range(60):
+        wind = rng.uniform(-3, 3, size=3).astype(np.float32)
+        iters = [(0, 1, 0), (2, 1, 0), (1, 2, 1), (3, 0, 2)][step % 4]
+        if step == 20:
+            for c in (r, o):
+                c.set_properties(12.0, 0.3, 0.2, 1.0)
+        if step in (30, 45):
+            ang = 0.2 + 0.01 * step; q2 = np.array([0.0, np.sin(ang), 0.0, np.cos(ang)], dtype=np.float32)
+            for c in (r, o):
+                c.set_fixed(q2, (0.5 + 0.02 * step, 6.0, -1.0), move_rigid=(step == 45))
+        for c in (r, o):
+            c.wind(wind); c.simulate(*iters, DT)
+        rp, rv = r.state(); op, ov = o.state()
+        assert bits_equal(rp, op) and bits_equal(rv, ov), "cloth differs at step %d: %g" % (step, float(np.max(np.abs(rp - op))))
+    assert float(np.max(np.abs(rv))) > 0.1
