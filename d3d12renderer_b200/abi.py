@@ -59,6 +59,11 @@ class Config(C.Structure):
                 ("cellSize", C.c_float), ("bigFactor", C.c_float), ("maxContacts", C.c_uint32), ("reserved", C.c_uint32 * 5)]
 
 
+class ClothDesc(C.Structure):
+    _fields_ = [("width", C.c_float), ("height", C.c_float), ("gridSizeX", C.c_uint32), ("gridSizeY", C.c_uint32), ("totalMass", C.c_float), ("stiffness", C.c_float),
+                ("damping", C.c_float), ("gravityFactor", C.c_float)]
+
+
 class HeightmapDesc(C.Structure):
     _fields_ = [("chunksPerDim", C.c_uint32), ("chunkSize", C.c_float), ("minCorner", C.c_float * 3), ("amplitudeScale", C.c_float), ("restitution", C.c_float), ("friction", C.c_float)]
 
@@ -86,7 +91,8 @@ class Stats(C.Structure):
 
 # every symbol include/b200phys.h declares (tests check that the library exports all of them)
 EXPORTS = [
-    "b200phys_version", "b200phys_error_string", "b200phys_create", "b200phys_destroy", "b200phys_set_stream", "b200phys_enable_timing", "b200phys_enable_graphs", "b200phys_upload_heightmap", "b200phys_env_create", "b200phys_env_set_seed", "b200phys_env_reset", "b200phys_env_step",
+    "b200phys_version", "b200phys_error_string", "b200phys_create", "b200phys_destroy", "b200phys_set_stream", "b200phys_enable_timing", "b200phys_enable_graphs", "b200phys_upload_heightmap", "b200phys_env_create", "b200phys_env_set_seed", "b200phys_env_reset", "b200phys_env_step", "b200phys_cloth_create", "b200phys_cloth_count", "b200phys_cloth_set_fixed_vertices", "b200phys_cloth_set_properties",
+    "b200phys_cloth_apply_wind", "b200phys_cloth_simulate", "b200phys_cloth_download",
     "b200phys_host_alloc", "b200phys_host_free",
     "b200phys_set_hulls", "b200phys_upload_bodies", "b200phys_upload_transforms", "b200phys_upload_colliders", "b200phys_upload_joints",
     "b200phys_upload_forces", "b200phys_upload_body_states", "b200phys_step", "b200phys_synchronize", "b200phys_download_bodies", "b200phys_get_stats",
@@ -123,6 +129,9 @@ def load_library():
     lib.b200phys_enable_timing.argtypes = [vp, i32]
     lib.b200phys_enable_graphs.argtypes = [vp, i32]
     lib.b200phys_upload_heightmap.argtypes = [vp, vp, vp]
+    lib.b200phys_cloth_create.argtypes = [vp, vp, vp]; lib.b200phys_cloth_set_fixed_vertices.argtypes = [vp, C.c_uint32, vp, vp, vp, i32]
+    lib.b200phys_cloth_set_properties.argtypes = [vp, C.c_uint32, C.c_float, C.c_float, C.c_float, C.c_float]; lib.b200phys_cloth_apply_wind.argtypes = [vp, C.c_uint32, vp]
+    lib.b200phys_cloth_simulate.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_float]; lib.b200phys_cloth_download.argtypes = [vp, C.c_uint32, vp, vp]
     lib.b200phys_host_alloc.restype = vp; lib.b200phys_host_alloc.argtypes = [C.c_size_t]
     lib.b200phys_host_free.restype = None; lib.b200phys_host_free.argtypes = [vp]
     lib.b200phys_set_hulls.argtypes = [vp, vp, vp, u32]
@@ -231,6 +240,32 @@ class Stepper:
 
     def enable_timing(self, on=True):
         _check(self.lib, self.lib.b200phys_enable_timing(self.ctx, 1 if on else 0), "enable_timing")
+
+    # ---- cloth
+    def cloth_create(self, width, height, gx, gy, total_mass, stiffness=0.5, damping=0.3, gravity_factor=1.0):
+        d = ClothDesc(width, height, gx, gy, total_mass, stiffness, damping, gravity_factor); out = C.c_uint32(0)
+        _check(self.lib, self.lib.b200phys_cloth_create(self.ctx, C.byref(d), C.byref(out)), "cloth_create")
+        self._cloth_sizes = getattr(self, "_cloth_sizes", {}); self._cloth_sizes[out.value] = gx * gy
+        return out.value
+
+    def cloth_set_fixed(self, cloth, rotation, position, scale=(1, 1, 1), move_rigid=False):
+        r = (C.c_float * 4)(*[float(x) for x in rotation]); p = (C.c_float * 3)(*[float(x) for x in position]); s = (C.c_float * 3)(*[float(x) for x in scale])
+        _check(self.lib, self.lib.b200phys_cloth_set_fixed_vertices(self.ctx, cloth, r, p, s, 1 if move_rigid else 0), "cloth_set_fixed_vertices")
+
+    def cloth_set_properties(self, cloth, total_mass, stiffness, damping, gravity_factor):
+        _check(self.lib, self.lib.b200phys_cloth_set_properties(self.ctx, cloth, C.c_float(total_mass), C.c_float(stiffness), C.c_float(damping), C.c_float(gravity_factor)), "cloth_set_properties")
+
+    def cloth_wind(self, force, cloth=0xFFFFFFFF):
+        f = (C.c_float * 3)(*[float(x) for x in force])
+        _check(self.lib, self.lib.b200phys_cloth_apply_wind(self.ctx, cloth, f), "cloth_apply_wind")
+
+    def cloth_simulate(self, vel_iters, pos_iters, drift_iters, dt):
+        _check(self.lib, self.lib.b200phys_cloth_simulate(self.ctx, vel_iters, pos_iters, drift_iters, C.c_float(dt)), "cloth_simulate")
+
+    def cloth_state(self, cloth):
+        n = self._cloth_sizes[cloth]
+        p = np.zeros((n, 3), dtype=np.float32); v = np.zeros((n, 3), dtype=np.float32)
+        _check(self.lib, self.lib.b200phys_cloth_download(self.ctx, cloth, _ptr(p), _ptr(v)), "cloth_download"); return p, v
 
     def upload_heightmap(self, heightmap):
         """heightmap: dict(chunks_per_dim, chunk_size, min_corner, amplitude_scale, restitution, friction, heights uint16 [chunks, 129, 129]) or None."""

@@ -203,6 +203,7 @@ struct Context
     uint16_t* hmHeights = nullptr; void* hmMips = nullptr;
     struct { uint32_t chunksPerDim; float chunkSize, invChunkSize, chunkScale, heightScale, invAmplitudeScale, minCorner[3], restitution, friction; } hm = {};
 
+    void* cloths = nullptr;             // cloth instances (k_cloth.cu)
     void* env = nullptr;                // device-side locomotion environment tables (k_env.cu)
 
     // CUDA graph replay of the step (b200phys_api.cu): 0 = launch, 1 = dry run that only hashes what would be launched
@@ -275,7 +276,8 @@ void launchPackAabbs(Context* c, float* devOut);
 // utilities (b200_util.cu)
 void launchCollisionEvents(Context* c);
 void launchHeightmap(Context* c);
-void destroyEnv(Context* c);             // k_env.cu        // k_heightmap.cuh (compiled with k_narrow.cu)
+void destroyEnv(Context* c);             // k_env.cu
+void destroyCloths(Context* c);          // k_cloth.cu        // k_heightmap.cuh (compiled with k_narrow.cu)
 void scanExclusiveU32(Context* c, const uint32_t* in, uint32_t* out, const uint32_t* devCount, uint32_t maxCount, uint32_t* totalOut /*device, may be null*/, bool clearInput = false /* leave the scanned part of `in` zeroed */);
 void scanExclusiveU64(Context* c, const unsigned long long* in, unsigned long long* out, const uint32_t* devCount, uint32_t maxCount, unsigned long long* totalOut);
 // stable counting sort of n (device count) elements by small keys (< numKeys <= 64): dst[i] = destination slot, keyStart[k] = ranges

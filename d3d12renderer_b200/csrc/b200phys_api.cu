@@ -175,6 +175,7 @@ int b200phys_destroy(b200phys_context* ctx)
     cudaDeviceSynchronize();
     dropGraphs(ctx->c);
     destroyEnv(&ctx->c);
+    destroyCloths(&ctx->c);
     destroyDist(&ctx->c);
     freeAll(ctx->c);
     delete ctx;

@@ -28,6 +28,8 @@ def load_library():
     lib.b200host_scene_destroy.argtypes = [vp]
     lib.b200host_build_config.argtypes = [vp, C.c_int, u32, u32, u32, C.c_uint64, C.c_int, C.c_float]
     lib.b200host_build_mixed_slab.argtypes = [vp, u32, u32, u32, u32, u32, C.c_uint64, C.c_float]
+    lib.b200host_add_cloth.argtypes = [vp, C.c_float, C.c_float, u32, u32, C.c_float, C.c_float, C.c_float, C.c_float]; lib.b200host_add_cloth.restype = u32
+    lib.b200host_cloth_set_fixed.argtypes = [vp, u32, vp, vp, C.c_int]; lib.b200host_cloth_positions.argtypes = [vp, u32, vp]; lib.b200host_cloth_positions.restype = u32
     lib.b200host_set_heightmap.argtypes = [vp, u32, C.c_float, vp, C.c_float, C.c_float, C.c_float, vp]
     for n in ("b200host_num_bodies", "b200host_num_colliders", "b200host_num_hulls", "b200host_num_hull_vertices"):
         getattr(lib, n).argtypes = [vp]; getattr(lib, n).restype = u32
@@ -78,6 +80,17 @@ class HostScene:
         if rc:
             raise ValueError("unknown config %d" % config)
         return self
+
+    def add_cloth(self, width, height, gx, gy, total_mass, stiffness=0.5, damping=0.3, gravity_factor=1.0):
+        return self.lib.b200host_add_cloth(self.ptr, width, height, gx, gy, total_mass, stiffness, damping, gravity_factor)
+
+    def cloth_set_fixed(self, cloth, rotation, position, move_rigid=False):
+        r = np.ascontiguousarray(rotation, dtype=np.float32); p = np.ascontiguousarray(position, dtype=np.float32)
+        self.lib.b200host_cloth_set_fixed(self.ptr, cloth, _p(r), _p(p), 1 if move_rigid else 0)
+
+    def cloth_positions(self, cloth):
+        n = self.lib.b200host_cloth_positions(self.ptr, cloth, None)
+        out = np.zeros((n, 3), dtype=np.float32); self.lib.b200host_cloth_positions(self.ptr, cloth, _p(out)); return out
 
     def set_heightmap(self, h):
         """heightmap_collider_component of the scene (dict as in scenes.terrain_drop)."""

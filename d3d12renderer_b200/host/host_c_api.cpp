@@ -283,6 +283,23 @@ int b200host_set_heightmap(void* sp, uint32_t chunksPerDim, float chunkSize, con
     return 0;
 }
 
+// addComponent<cloth_component>(width, height, gridSizeX, gridSizeY, totalMass, ...) -> index; setWorldPositionOfFixedVertices; particle positions after the last step
+uint32_t b200host_add_cloth(void* sp, float width, float height, uint32_t gx, uint32_t gy, float totalMass, float stiffness, float damping, float gravityFactor)
+{ game_scene& s = *(game_scene*)sp; s.cloths.emplace_back(width, height, gx, gy, totalMass, stiffness, damping, gravityFactor); return (uint32_t)s.cloths.size() - 1; }
+void b200host_cloth_set_fixed(void* sp, uint32_t cloth, const float* rot4, const float* pos3, int moveRigid)
+{
+    game_scene& s = *(game_scene*)sp; if (cloth >= s.cloths.size()) return;
+    trs t; t.rotation = b200::mkq(rot4[0], rot4[1], rot4[2], rot4[3]); t.position = b200::mk3(pos3[0], pos3[1], pos3[2]); t.scale = b200::mk3(1.f);
+    s.cloths[cloth].setWorldPositionOfFixedVertices(t, moveRigid != 0);
+}
+uint32_t b200host_cloth_positions(void* sp, uint32_t cloth, float* out3)
+{
+    game_scene& s = *(game_scene*)sp; if (cloth >= s.cloths.size()) return 0;
+    const cloth_component& c = s.cloths[cloth];
+    if (out3) memcpy(out3, c.positions.data(), sizeof(float) * 3 * c.positions.size());
+    return (uint32_t)c.positions.size();
+}
+
 int b200host_build_mixed_slab(void* sp, uint32_t nxTotal, uint32_t ny, uint32_t nz, uint32_t ix0, uint32_t ix1, uint64_t seed, float spacing)
 {
     game_scene& s = *(game_scene*)sp;

@@ -819,6 +819,7 @@ int uploadSceneToDevice(game_scene& scene)
         r = b200phys_upload_force_fields(scene.ctx, local.data(), (uint32_t)scene.forceFields.size()); if (r) return r;
         const float g3[3] = { global.x, global.y, global.z };
         r = b200phys_set_global_force_field(scene.ctx, g3); if (r) return r;
+        scene.lastGlobalForceField = global;
     }
     return 0;
 }
@@ -879,6 +880,36 @@ static int physicsStepInternal(game_scene& scene, const physics_settings& settin
             const trigger_component& t = scene.triggers[e.triggerIndex];
             if (t.callback) t.callback(trigger_event{ scene.triggerEntity[e.triggerIndex], scene.rigidBodyEntity[e.rigidBodyIndex], leave ? trigger_event_leave : trigger_event_enter });
         }
+    }
+    if (!scene.cloths.empty())
+    {   // physics.cpp:1354-1358: wind from the global force field, then simulate; creation / parameter changes / fixed-row moves first
+        for (cloth_component& cl : scene.cloths)
+        {
+            if (cl.deviceId < 0)
+            {
+                b200phys_cloth_desc d; memset(&d, 0, sizeof(d));
+                d.width = cl.width; d.height = cl.height; d.gridSizeX = cl.gridSizeX; d.gridSizeY = cl.gridSizeY; d.totalMass = cl.totalMass; d.stiffness = cl.stiffness; d.damping = cl.damping; d.gravityFactor = cl.gravityFactor;
+                uint32_t id = 0; r = b200phys_cloth_create(scene.ctx, &d, &id); if (r) return r;
+                cl.deviceId = (int32_t)id; cl.upTotalMass = cl.totalMass; cl.upStiffness = cl.stiffness; cl.upDamping = cl.damping; cl.upGravityFactor = cl.gravityFactor;
+                cl.positions.resize((size_t)cl.gridSizeX * cl.gridSizeY);
+            }
+            for (const cloth_component::fixed_update& f : cl.pendingFixed)
+            {
+                const float rot[4] = { f.transform.rotation.x, f.transform.rotation.y, f.transform.rotation.z, f.transform.rotation.w };
+                const float pos[3] = { f.transform.position.x, f.transform.position.y, f.transform.position.z }, sc[3] = { f.transform.scale.x, f.transform.scale.y, f.transform.scale.z };
+                r = b200phys_cloth_set_fixed_vertices(scene.ctx, (uint32_t)cl.deviceId, rot, pos, sc, f.moveRigid ? 1 : 0); if (r) return r;
+            }
+            cl.pendingFixed.clear();
+            if (cl.totalMass != cl.upTotalMass || cl.stiffness != cl.upStiffness || cl.damping != cl.upDamping || cl.gravityFactor != cl.upGravityFactor)
+            {
+                r = b200phys_cloth_set_properties(scene.ctx, (uint32_t)cl.deviceId, cl.totalMass, cl.stiffness, cl.damping, cl.gravityFactor); if (r) return r;
+                cl.upTotalMass = cl.totalMass; cl.upStiffness = cl.stiffness; cl.upDamping = cl.damping; cl.upGravityFactor = cl.gravityFactor;
+            }
+        }
+        const float w3[3] = { scene.lastGlobalForceField.x, scene.lastGlobalForceField.y, scene.lastGlobalForceField.z };
+        r = b200phys_cloth_apply_wind(scene.ctx, 0xFFFFFFFFu, w3); if (r) return r;
+        r = b200phys_cloth_simulate(scene.ctx, settings.numClothVelocityIterations, settings.numClothPositionIterations, settings.numClothDriftIterations, dt); if (r) return r;
+        for (cloth_component& cl : scene.cloths) { r = b200phys_cloth_download(scene.ctx, (uint32_t)cl.deviceId, &cl.positions[0].x, nullptr); if (r) return r; }
     }
     r = b200phys_download_bodies(scene.ctx, scene.stageStates, numBodies); if (r) return r;
     scene.scatterBodyStates(scene.stageStates, numBodies);

@@ -143,6 +143,21 @@ struct heightmap_collider_component
     std::vector<uint16_t> heights; bool dirty = true;
 };
 
+// cloth.h:5-55: the parameters live here, the particles on the device (b200phys_cloth_*); `positions` is refreshed after every simulate
+// (what cloth_render_component reads)
+struct cloth_component
+{
+    cloth_component(float width, float height, uint32_t gridSizeX, uint32_t gridSizeY, float totalMass, float stiffness = 0.5f, float damping = 0.3f, float gravityFactor = 1.f)
+        : totalMass(totalMass), gravityFactor(gravityFactor), damping(damping), stiffness(stiffness), gridSizeX(gridSizeX), gridSizeY(gridSizeY), width(width), height(height) {}
+    void setWorldPositionOfFixedVertices(const trs& transform, bool moveRigid = false) { pendingFixed.push_back({ transform, moveRigid }); }
+    float totalMass, gravityFactor, damping, stiffness;
+    uint32_t gridSizeX, gridSizeY; float width, height;
+    std::vector<vec3> positions;
+    struct fixed_update { trs transform; bool moveRigid; };
+    std::vector<fixed_update> pendingFixed;
+    int32_t deviceId = -1; float upTotalMass = 0.f, upStiffness = 0.f, upDamping = 0.f, upGravityFactor = 0.f;      // what the device has
+};
+
 // physics.h:382-400
 struct physics_settings
 {
@@ -209,6 +224,8 @@ struct game_scene
     std::vector<trigger_component> triggers; std::vector<entity_handle> triggerEntity;
     std::vector<force_field_component> forceFields; std::vector<entity_handle> forceFieldEntity;
     std::vector<bounding_hull_geometry> hullGeometries;
+    std::vector<cloth_component> cloths;                         // scene.view<cloth_component>() (physics.cpp:1354)
+    vec3 lastGlobalForceField = b200::mk3(0.f);                  // what applyWindForce receives
     std::vector<heightmap_collider_component> heightmaps;       // scene.view<heightmap_collider_component>() (physics.cpp:1238); the device holds one
     std::vector<distance_constraint> distanceConstraints; std::vector<ball_constraint> ballConstraints; std::vector<fixed_constraint> fixedConstraints;
     std::vector<hinge_constraint> hingeConstraints; std::vector<cone_twist_constraint> coneTwistConstraints; std::vector<slider_constraint> sliderConstraints;

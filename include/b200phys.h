@@ -264,6 +264,23 @@ int b200phys_env_reset(b200phys_context* ctx, const uint32_t* envIndices, uint32
 int b200phys_env_step(b200phys_context* ctx, const float* actions, float dt, uint32_t numSolverIterations, uint32_t flags, float pushProbability,
                       float* outStates, float* outRewards, int32_t* outFailed);                                   /* updatePhysics for all of them */
 
+/* cloth (reference: cloth_component, src/physics/cloth.{h,cpp}): a gridSizeX x gridSizeY particle grid (top row fixed) with stretch / shear /
+ * bend constraints, solved by Gauss-Seidel sweeps in the reference's constraint order; physicsStepInternal applies the global force field
+ * as wind and simulates every cloth after the rigid bodies (physics.cpp:1354-1358): b200phys_cloth_apply_wind(ctx, 0xFFFFFFFF, force) then
+ * b200phys_cloth_simulate(ctx, numClothVelocityIterations, numClothPositionIterations, numClothDriftIterations, dt). */
+typedef struct b200phys_cloth_desc {
+    float    width, height;
+    uint32_t gridSizeX, gridSizeY;
+    float    totalMass, stiffness /* 0.5 */, damping /* 0.3 */, gravityFactor /* 1 */;
+} b200phys_cloth_desc;
+int b200phys_cloth_create(b200phys_context* ctx, const b200phys_cloth_desc* desc, uint32_t* outId);
+int b200phys_cloth_count(b200phys_context* ctx, uint32_t* count);
+int b200phys_cloth_set_fixed_vertices(b200phys_context* ctx, uint32_t id, const float rotation[4], const float position[3], const float scale[3], int moveRigid); /* setWorldPositionOfFixedVertices */
+int b200phys_cloth_set_properties(b200phys_context* ctx, uint32_t id, float totalMass, float stiffness, float damping, float gravityFactor);
+int b200phys_cloth_apply_wind(b200phys_context* ctx, uint32_t id /* 0xFFFFFFFF = all */, const float force3[3]);                                                  /* applyWindForce */
+int b200phys_cloth_simulate(b200phys_context* ctx, uint32_t velocityIterations, uint32_t positionIterations, uint32_t driftIterations, float dt);                 /* simulate, all cloths */
+int b200phys_cloth_download(b200phys_context* ctx, uint32_t id, float* positions3, float* velocities3);                                                           /* gridSizeX * gridSizeY x 3 each, NULL = skip */
+
 /* heightmap collision (reference: heightmap_collider_component, terrain/heightmap_collider.h:132-150, collided against every rigid body
  * collider of type sphere / capsule / AABB / OBB by heightmapCollision, physics/heightmap_collision.cpp:509-618, physics.cpp:1238-1248).
  * heights: chunksPerDim^2 chunks of 129 x 129 uint16 (TERRAIN_LOD_0_VERTICES_PER_DIMENSION), chunk (x, z) at z * chunksPerDim + x, row

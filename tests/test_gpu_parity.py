@@ -203,6 +203,24 @@ def test_host_mirror_heightmap_component():
     assert np.array_equal(via_host["position"], direct["position"]) and np.array_equal(via_host["linearVelocity"], direct["linearVelocity"])
 
 
+def test_host_mirror_cloth_component():
+    """cloth_component in the host mirror's scene: physicsStep() creates it on the device, moves its fixed row, applies the global force
+    field as wind and simulates it after the rigid bodies (physics.cpp:1354-1358) -- same particles as the direct C-ABI calls."""
+    sc = host.build_scene(host.CONFIG_SPHERES_ON_GROUND, 2, 1, 2, seed=15681923, mode=1, spacing=1.25)
+    hs = sc["host_scene"]
+    cl = hs.add_cloth(2.0, 3.0, 15, 20, 5.0)
+    q = np.array([0.0, 0.0, 0.0, 1.0], dtype=np.float32)
+    hs.cloth_set_fixed(cl, q, (0.0, 5.0, 0.0))
+    st = make_stepper(sc)
+    cid = st.cloth_create(2.0, 3.0, 15, 20, 5.0); st.cloth_set_fixed(cid, q, (0.0, 5.0, 0.0))
+    timer = 0.0
+    for _ in range(15):
+        st.step(DT, 30, abi.STEP_FAST); st.cloth_wind((0.0, 0.0, 0.0)); st.cloth_simulate(0, 1, 0, DT)      # the settings' default iteration counts (physics.h:390-392)
+        timer = hs.physics_step(timer, float(DT), iterations=30)
+    direct, _ = st.cloth_state(cid)
+    assert np.array_equal(hs.cloth_positions(cl), direct) and float(np.max(np.abs(direct[:, 1] - 5.0))) > 0.01
+
+
 import golden_util
 
 

@@ -241,6 +241,45 @@ def test_heightmap_collision_matches_oracle(flags):
     st.close()
 
 
+# ------------------------------------------------------------------------------------------------ cloth (f.4)
+def test_cloth_matches_oracle():
+    """cloth_component on the device (csrc/k_cloth.cu: one CTA per cloth, the sequential constraint sweep kept exactly through wavefront
+    levels) against the oracle's restatement, which tests/test_ref_pins_oracle.py::test_cloth_equals_oracle pins bit for bit to the compiled
+    reference: two cloths (odd and even grid width: both pivot branches of the rigid move), wind, all three solver passes with changing
+    iteration counts, a property change (recalculateProperties), moving the fixed row with and without the rigid move. 60 steps, positions
+    and velocities bit-identical in every step."""
+    import ref_lib
+
+    class OracleCloth(ref_lib._ClothBase):
+        def __init__(self, *a, **kw):
+            super().__init__(oracle_lib.load(), "oracle_cloth_", *a, **kw)
+    sc = scenes.spheres_on_ground(2, mode="rest")
+    st = make_stepper(sc)
+    specs = [(3.0, 4.0, 19, 26, 9.0, 0.6, 0.35, 0.9), (2.0, 2.5, 24, 17, 4.0, 0.5, 0.3, 1.0)]
+    ids = [st.cloth_create(*a) for a in specs]; orc = [OracleCloth(*a) for a in specs]
+    rng = np.random.default_rng(2)
+    q = np.array([0.0, np.sin(0.2), 0.0, np.cos(0.2)], dtype=np.float32)
+    for k in range(2):
+        st.cloth_set_fixed(ids[k], q, (0.5 + 3 * k, 6.0, -1.0)); orc[k].set_fixed(q, (0.5 + 3 * k, 6.0, -1.0))
+    for step in range(60):
+        wind = rng.uniform(-3, 3, size=3).astype(np.float32)
+        iters = [(0, 1, 0), (2, 1, 0), (1, 2, 1), (3, 0, 2)][step % 4]
+        if step == 20:
+            st.cloth_set_properties(ids[0], 12.0, 0.3, 0.2, 1.0); orc[0].set_properties(12.0, 0.3, 0.2, 1.0)
+        if step in (30, 45):
+            ang = 0.2 + 0.01 * step; q2 = np.array([0.0, np.sin(ang), 0.0, np.cos(ang)], dtype=np.float32)
+            for k in range(2):
+                st.cloth_set_fixed(ids[k], q2, (0.5 + 3 * k + 0.02 * step, 6.0, -1.0), move_rigid=(step == 45))
+                orc[k].set_fixed(q2, (0.5 + 3 * k + 0.02 * step, 6.0, -1.0), move_rigid=(step == 45))
+        st.cloth_wind(wind); st.cloth_simulate(*iters, DT)
+        for k in range(2):
+            orc[k].wind(wind); orc[k].simulate(*iters, DT)
+            gp, gv = st.cloth_state(ids[k]); op, ov = orc[k].state()
+            assert np.array_equal(gp.view(np.uint32), op.view(np.uint32)) and np.array_equal(gv.view(np.uint32), ov.view(np.uint32)), \
+                "cloth %d differs at step %d: %g" % (k, step, float(np.max(np.abs(gp - op))))
+    st.close()
+
+
 # ------------------------------------------------------------------------------------------------ CUDA graph replay
 @pytest.mark.parametrize("config,dims,spacing,seed", [(host.CONFIG_MIXED_PILE, (10, 6, 10), 0.8, 1578123), (host.CONFIG_RAGDOLLS, (4, 1, 4), 1.6, 20260924)])
 def test_graph_replay_is_bit_identical_to_plain_launches(config, dims, spacing, seed):
