@@ -40,6 +40,7 @@ struct DeviceCounts
     uint32_t epaWorkHead;               // next work-list entry to hand out (EPA kernels with dynamic distribution)
     uint32_t numEpaRedo;                // entries the small-polytope EPA kernel handed to the large-capacity one
     uint32_t hmBaseManifolds, hmBaseContacts, hmFitManifolds, hmFitContacts;   // heightmap pass: list sizes before it, first entries that did not fit
+    uint32_t numEpaRedo2, epaRedo2Head;  // entries the medium polytope handed on to the warp-cooperative kernel
     uint32_t epaRedoHead;               // next redo entry to hand out
     uint32_t gjkCursor[11];             // per GJK bucket: next pair to hand out (npGjkKernel)
     uint32_t numPairs;                  // broad-phase overlaps (clamped to capacity)
@@ -137,6 +138,7 @@ struct Context
     float4* epaSimplex = nullptr;     // 9 planes x maxEpaWork: GJK terminal simplices parked for the EPA kernel
     uint2* epaWork = nullptr;         // (sorted pair slot, bucket)
     uint32_t* epaRedo = nullptr;      // work-list entries that outgrew the small polytope
+    uint32_t* epaRedo2 = nullptr;     // ... and the medium one
     uint32_t maxEpaWork = 0;
     float4* manTmp = nullptr;         // 5 planes x maxPairs: (normal, count), 4 x (point, depth)
     unsigned long long* manScan = nullptr; // per pair (contacts << 32 | collided) and its exclusive scan

@@ -49,7 +49,7 @@ int allocateAll(Context& c)
     CK(devAlloc(c.pairCount, C + 2)); CK(devAlloc(c.pairStart, C + 2)); CK(devAlloc(c.pairs, P));
     CK(devAlloc(c.pairKey, P)); CK(devAlloc(c.pairsTyped, P)); CK(devAlloc(c.pairDst, P + 2)); CK(devAlloc(c.pairsSorted, P));
     CK(devAlloc(c.manTmp, 5 * P)); CK(devAlloc(c.manScan, P + 2)); CK(devAlloc(c.manScanOut, P + 2));
-    c.maxEpaWork = (uint32_t)M; CK(devAlloc(c.epaSimplex, 9 * M)); CK(devAlloc(c.epaWork, M)); CK(devAlloc(c.epaRedo, M));
+    c.maxEpaWork = (uint32_t)M; CK(devAlloc(c.epaSimplex, 9 * M)); CK(devAlloc(c.epaWork, M)); CK(devAlloc(c.epaRedo, M)); CK(devAlloc(c.epaRedo2, M));
     CK(devAlloc(c.collisions, M)); CK(devAlloc(c.manifolds, M)); CK(devAlloc(c.contacts, 2 * K)); CK(devAlloc(c.contactBodies, K));
     for (uint32_t gI = 0; gI < kNumGroups; ++gI)
     {
@@ -92,7 +92,7 @@ void freeAll(Context& c)
 {
     void* ptrs[] = { c.bRot, c.bPos, c.bCog, c.bInvI, c.bVel, c.bAng, c.bForce, c.bTorque, c.gVel, c.gPos, c.gInvI, c.bodyMask, c.bodyBase, c.refKeys[0], c.refKeys[1], c.refColors, c.colorKey, c.colorQueue, c.scanStatus, c.scanState, c.cLocal, c.xforms, c.wCol, c.aabbMin, c.aabbMax,
         c.hullVerts, c.hullOffsets, c.hullAabb, c.cellOf, c.rankInCell, c.cellCount, c.cellStart, c.bpRec, c.bpRows, c.bpBigChunks, c.bigList, c.pairCount, c.pairStart, c.pairs,
-        c.pairKey, c.pairsTyped, c.pairDst, c.pairsSorted, c.manTmp, c.manScan, c.manScanOut, c.epaSimplex, c.epaWork, c.epaRedo, c.collisions, c.manifolds, c.contacts, c.contactBodies,
+        c.pairKey, c.pairsTyped, c.pairDst, c.pairsSorted, c.manTmp, c.manScan, c.manScanOut, c.epaSimplex, c.epaWork, c.epaRedo, c.epaRedo2, c.collisions, c.manifolds, c.contacts, c.contactBodies,
         c.unitPending, c.unitForbid, c.nbrCount, c.nbrList, c.adjStart, c.adjFill, c.adjList, c.levelStart, c.levelFill, c.slotOfContact, c.unitSlotStart, c.unitInfo, c.rows, c.rowImp, c.scanTmp, c.scanTmp64, c.sortHist, c.staging, c.counts, c.haloBuf };
     for (void* p : ptrs) if (p) cudaFree(p);
     for (int k = 0; k < 6; ++k) if (c.refColorsJoint[k]) cudaFree(c.refColorsJoint[k]);
@@ -592,7 +592,7 @@ int b200phys_get_stats(b200phys_context* ctx, b200phys_stats* out)
     const DeviceCounts& d = *c.hostCounts;
     memset(out, 0, sizeof(*out));
     out->numBodies = c.numBodies; out->numColliders = c.numColliders; out->reserved[1] = c.numOwnedBodies; out->reserved[2] = c.numOwnedColliders; out->reserved[3] = c.numNonCollisionColliders ? d.numInteractions : 0u;
-    out->reserved[4] = d.numEpaWork; out->reserved[5] = d.numEpaRedo; out->reserved[6] = c.graphReplays; out->reserved[0] = c.graphCaptures;
+    out->reserved[4] = d.numEpaWork; out->reserved[5] = d.numEpaRedo | (d.numEpaRedo2 << 20); out->reserved[6] = c.graphReplays; out->reserved[0] = c.graphCaptures;
     out->numBroadphaseOverlaps = d.numPairs; out->numCollisions = d.numManifolds; out->numContacts = d.numContacts;
     out->numBigColliders = d.numBigNow; out->numGridCells = d.grid.numCells;
     for (int g = 0; g < 7; ++g) out->numColors[g] = d.numColors[g];

@@ -240,7 +240,7 @@ __global__ void bpSetupKernel(uint32_t maxCells, float bigFactor, float cfgCell,
     cnt->numBigNow = min(cnt->numBig, kMaxBig);
     cnt->extentSumFixed = 0ull; cnt->extentCount = 0; cnt->smallSumFixed = 0ull; cnt->smallCount = 0; cnt->maxSmallExtentBits = 0; cnt->numBig = 0;
     for (int a = 0; a < 3; ++a) { cnt->centreMinBits[a] = 0xFFFFFFFFu; cnt->centreMaxBits[a] = 0u; }
-    cnt->numPairs = 0; cnt->numPairsWanted = 0; cnt->numEpaWork = 0; cnt->epaWorkHead = 0; cnt->numEpaRedo = 0; cnt->epaRedoHead = 0;
+    cnt->numPairs = 0; cnt->numPairsWanted = 0; cnt->numEpaWork = 0; cnt->epaWorkHead = 0; cnt->numEpaRedo = 0; cnt->epaRedoHead = 0; cnt->numEpaRedo2 = 0; cnt->epaRedo2Head = 0;
     for (int i = 0; i < 11; ++i) cnt->gjkCursor[i] = 0; cnt->numOverflowRows = 0;
 }
 

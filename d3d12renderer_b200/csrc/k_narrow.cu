@@ -318,16 +318,20 @@ __global__ void __launch_bounds__(128) npEpaKernel(const uint2* __restrict__ sor
 // phase 2, small polytope in shared memory (k_narrow_shapes.cuh, EpaSmall): thread per pair, 6 warps per SM. Runs take 0..20
 // expansions (most 1-4), so like the GJK kernel the loop performs ONE expansion per pass for every lane and a finished lane takes the
 // next work list entry at once. The few pairs that outgrow the small polytope go to the redo list (large polytope kernels).
-static const int kEpaSmallWarps = 6;
-__global__ void __launch_bounds__(kEpaSmallWarps * 32, 1) npEpaSmallKernel(const uint2* __restrict__ sorted, const float4* __restrict__ wCol, const float4* __restrict__ hullVerts,
+// POLY = EpaSmall (6 warps per SM, every parked pair) or EpaMedium (3 warps, the entries of `inList` = what the small one handed back);
+// entries that outgrow POLY are appended to outList.
+static const int kEpaSmallWarps = 6, kEpaMediumWarps = 3;
+template <class POLY, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1) npEpaSmKernel(const uint2* __restrict__ sorted, const float4* __restrict__ wCol, const float4* __restrict__ hullVerts,
     const uint32_t* __restrict__ hullOffsets, float4* __restrict__ manTmp, unsigned long long* __restrict__ manScan, uint32_t maxPairs,
-    float4* __restrict__ sxPlanes, const uint2* __restrict__ epaWork, uint32_t sxCap, DeviceCounts* cnt, uint32_t* __restrict__ redo, uint32_t refillAt)
+    float4* __restrict__ sxPlanes, const uint2* __restrict__ epaWork, uint32_t sxCap, DeviceCounts* cnt,
+    const uint32_t* __restrict__ inList, const uint32_t* __restrict__ inCount, uint32_t* cursor, uint32_t* __restrict__ outList, uint32_t* outCount, uint32_t refillAt)
 {
     extern __shared__ uint32_t epaColumns[];
     const uint32_t lane = threadIdx.x & 31u;
     NarrowCounters nc; nc.epaOverflow = nc.gjkCap = nc.asserts = 0;
-    EpaSmall P; P.w = epaColumns + (size_t)(threadIdx.x >> 5) * (B200_EPAS_WORDS * 32) + lane; P.active = 0; P.nT = P.nP = P.nE = 0;
-    const uint32_t total = min(cnt->numEpaWork, sxCap);
+    POLY P; P.w = epaColumns + (size_t)(threadIdx.x >> 5) * (POLY::kWords * 32) + lane; P.active = 0; P.nT = P.nP = P.nE = 0;
+    const uint32_t total = min(*inCount, sxCap);
     WarpRange range;
     // lane states: 0 idle, 1 expanding, 2 converged (contact still to be written). Finishing and starting a run cost about as much
     // as an expansion and a run is ~2.5 expansions, so both are done by many lanes together: when refillAt lanes are not expanding.
@@ -344,10 +348,10 @@ __global__ void __launch_bounds__(kEpaSmallWarps * 32, 1) npEpaSmallKernel(const
             storeManifold(manTmp, manScan, q, maxPairs, true, m);
             state = 0;
         }
-        const uint32_t item = range.take(batch && state == 0, &cnt->epaWorkHead, total, 64u);
+        const uint32_t item = range.take(batch && state == 0, cursor, total, 64u);
         if (item != 0xFFFFFFFFu)
         {
-            e = item;
+            e = inList ? inList[item] : item;
             const uint2 w = epaWork[e];
             q = w.x;
             const uint2 pr = sorted[q];
@@ -370,11 +374,11 @@ __global__ void __launch_bounds__(kEpaSmallWarps * 32, 1) npEpaSmallKernel(const
             else
             {
                 __syncwarp(evalMask);
-                const uint32_t k = EpaSmall::kTri + 6 * ci;
+                const uint32_t k = POLY::kTri + 6 * ci;
                 const f3 tn = mk3(P.ldf(k), P.ldf(k + 1), P.ldf(k + 2));
                 const SupPt a = minkowski(job.A, job.B, tn);
                 if (dot(a.m, tn) - P.ldf(k + 3) < 0.01f) state = 2;
-                else if (!P.addPoint(a)) { redo[atomicAdd(&cnt->numEpaRedo, 1u)] = e; state = 0; }
+                else if (!P.addPoint(a)) { outList[atomicAdd(outCount, 1u)] = e; state = 0; }
                 else if (++it == 20u) state = 2;
             }
         }
@@ -387,17 +391,17 @@ __global__ void __launch_bounds__(kEpaSmallWarps * 32, 1) npEpaSmallKernel(const
 static const int kEpaWarpsPerCta = 4;
 __global__ void __launch_bounds__(kEpaWarpsPerCta * 32) npEpaWarpKernel(const uint2* __restrict__ sorted, const float4* __restrict__ wCol, const float4* __restrict__ hullVerts,
     const uint32_t* __restrict__ hullOffsets, float4* __restrict__ manTmp, unsigned long long* __restrict__ manScan, uint32_t maxPairs,
-    float4* __restrict__ sxPlanes, const uint2* __restrict__ epaWork, uint32_t sxCap, DeviceCounts* cnt, const uint32_t* __restrict__ redo)
+    float4* __restrict__ sxPlanes, const uint2* __restrict__ epaWork, uint32_t sxCap, DeviceCounts* cnt, const uint32_t* __restrict__ redo, const uint32_t* __restrict__ redoCount, uint32_t* redoHead)
 {
     extern __shared__ __align__(16) unsigned char epaSmem[];
     EpaWarpShared* sh = reinterpret_cast<EpaWarpShared*>(epaSmem) + (threadIdx.x >> 5);
     NarrowCtx<3> nc; nc.epaOverflow = nc.gjkCap = nc.asserts = 0; nc.sxPlanes = sxPlanes; nc.sxCap = sxCap; nc.sxCounter = nullptr; nc.deferred = false; nc.epaShared = sh;
     // redo == nullptr: the whole work list; else only the entries the small-polytope kernel handed back
-    const uint32_t n = redo ? min(cnt->numEpaRedo, sxCap) : min(cnt->numEpaWork, sxCap);
+    const uint32_t n = redo ? min(*redoCount, sxCap) : min(cnt->numEpaWork, sxCap);
     for (;;)
     {   // pairs take 1..20 expansions: hand the work list out dynamically, one entry per warp at a time
         uint32_t e = 0;
-        if ((threadIdx.x & 31u) == 0u) e = atomicAdd(redo ? &cnt->epaRedoHead : &cnt->epaWorkHead, 1u);
+        if ((threadIdx.x & 31u) == 0u) e = atomicAdd(redo ? redoHead : &cnt->epaWorkHead, 1u);
         e = __shfl_sync(0xffffffffu, e, 0);
         if (e >= n) break;
         if (redo) e = redo[e];
@@ -561,22 +565,40 @@ void launchNarrowphase(Context* c)
         if (epaMode < 0) { const char* e = getenv("B200PHYS_EPA"); epaMode = !e ? 2 : e[0] == 'w' ? 1 : e[0] == 't' ? 0 : 2; const char* b = getenv("B200PHYS_EPA_BPS"); epaBps = b ? atoi(b) : 0; }
         if (epaMode == 2)
         {
-            const size_t smem = (size_t)kEpaSmallWarps * B200_EPAS_WORDS * 32 * sizeof(uint32_t);
+            const size_t smem = (size_t)kEpaSmallWarps * EpaSmall::kWords * 32 * sizeof(uint32_t), msmem = (size_t)kEpaMediumWarps * EpaMedium::kWords * 32 * sizeof(uint32_t);
             static bool attr = false;
-            if (!attr) { cudaFuncSetAttribute(npEpaSmallKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
-            launchK(c, npEpaSmallKernel, c->numSMs, kEpaSmallWarps * 32, smem, c->pairsSorted, c->wCol, c->hullVerts, c->hullOffsets, c->manTmp, c->manScan, c->maxPairs, c->epaSimplex, c->epaWork, c->maxEpaWork, cnt, c->epaRedo, (uint32_t)epaRefill);
+            if (!attr)
+            {
+                cudaFuncSetAttribute(npEpaSmKernel<EpaSmall, kEpaSmallWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                cudaFuncSetAttribute(npEpaSmKernel<EpaMedium, kEpaMediumWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem);
+                attr = true;
+            }
+            launchK(c, npEpaSmKernel<EpaSmall, kEpaSmallWarps>, c->numSMs, kEpaSmallWarps * 32, smem, c->pairsSorted, c->wCol, c->hullVerts, c->hullOffsets, c->manTmp, c->manScan, c->maxPairs, c->epaSimplex,
+                    c->epaWork, c->maxEpaWork, cnt, nullptr, &cnt->numEpaWork, &cnt->epaWorkHead, c->epaRedo, &cnt->numEpaRedo, (uint32_t)epaRefill);
             timelineMark(c, "np_epa");
-            // the ones that outgrew it are the long runs (up to 20 expansions, ~100 triangles): a warp per pair (exact, see EpaWarp)
-            static int redoThread = -1;
-            if (redoThread < 0) { const char* e = getenv("B200PHYS_EPA_REDO"); redoThread = (e && e[0] == 't') ? 1 : 0; }
-            if (redoThread)
+            // the ones that outgrew it are the long runs (up to 20 expansions, ~100 triangles): a warp per pair (exact, see EpaWarp).
+            // B200PHYS_EPA_REDO=medium puts a 16-point / 62-triangle shared-memory tier (3 warps per SM) in between -- measured: 1.28 -> 1.07 ms
+            // while the pile is still falling (74 k redo entries) but 0.12 -> 0.32 ms once it has settled (7 k entries: too few threads, each
+            // with a long run), so it is off by default; =thread uses the thread-local kernel for the redo entries (0.43 ms settled).
+            static int redoMode = -1;
+            if (redoMode < 0) { const char* e = getenv("B200PHYS_EPA_REDO"); redoMode = !e ? 2 : e[0] == 't' ? 1 : e[0] == 'm' ? 0 : 2; }
+            const uint32_t* lastList = c->epaRedo; uint32_t* lastCount = &cnt->numEpaRedo; uint32_t* lastHead = &cnt->epaRedoHead;
+            if (redoMode == 0)
+            {
+                launchK(c, npEpaSmKernel<EpaMedium, kEpaMediumWarps>, c->numSMs, kEpaMediumWarps * 32, msmem, c->pairsSorted, c->wCol, c->hullVerts, c->hullOffsets, c->manTmp, c->manScan, c->maxPairs, c->epaSimplex,
+                        c->epaWork, c->maxEpaWork, cnt, c->epaRedo, &cnt->numEpaRedo, &cnt->epaRedoHead, c->epaRedo2, &cnt->numEpaRedo2, (uint32_t)epaRefill);
+                c->launches += 1;
+                lastList = c->epaRedo2; lastCount = &cnt->numEpaRedo2; lastHead = &cnt->epaRedo2Head;
+            }
+            if (redoMode == 1)
                 launchK(c, npEpaKernel, gridFor(c, 2), 64, 0, c->pairsSorted, c->wCol, c->hullVerts, c->hullOffsets, c->manTmp, c->manScan, c->maxPairs, c->epaSimplex, c->epaWork, c->maxEpaWork, cnt, c->epaRedo);
             else
             {
                 const size_t wsmem = sizeof(EpaWarpShared) * kEpaWarpsPerCta;
                 static bool wattr = false;
                 if (!wattr) { cudaFuncSetAttribute(npEpaWarpKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem); wattr = true; }
-                launchK(c, npEpaWarpKernel, gridFor(c, 6), kEpaWarpsPerCta * 32, wsmem, c->pairsSorted, c->wCol, c->hullVerts, c->hullOffsets, c->manTmp, c->manScan, c->maxPairs, c->epaSimplex, c->epaWork, c->maxEpaWork, cnt, c->epaRedo);
+                launchK(c, npEpaWarpKernel, gridFor(c, 6), kEpaWarpsPerCta * 32, wsmem, c->pairsSorted, c->wCol, c->hullVerts, c->hullOffsets, c->manTmp, c->manScan, c->maxPairs, c->epaSimplex, c->epaWork, c->maxEpaWork, cnt,
+                        lastList, lastCount, lastHead);
             }
             c->launches += 1;
         }
@@ -587,7 +609,7 @@ void launchNarrowphase(Context* c)
             const size_t smem = sizeof(EpaWarpShared) * kEpaWarpsPerCta;
             static bool attr = false;
             if (!attr) { cudaFuncSetAttribute(npEpaWarpKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
-            launchK(c, npEpaWarpKernel, gridFor(c, epaBps > 0 ? epaBps : 6), kEpaWarpsPerCta * 32, smem, c->pairsSorted, c->wCol, c->hullVerts, c->hullOffsets, c->manTmp, c->manScan, c->maxPairs, c->epaSimplex, c->epaWork, c->maxEpaWork, cnt, nullptr);
+            launchK(c, npEpaWarpKernel, gridFor(c, epaBps > 0 ? epaBps : 6), kEpaWarpsPerCta * 32, smem, c->pairsSorted, c->wCol, c->hullVerts, c->hullOffsets, c->manTmp, c->manScan, c->maxPairs, c->epaSimplex, c->epaWork, c->maxEpaWork, cnt, nullptr, nullptr, nullptr);
         }
     }
     c->launches += 1;

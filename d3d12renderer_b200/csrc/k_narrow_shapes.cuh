@@ -5,6 +5,7 @@
 // the reference so that contacts agree with the CPU oracle to the last bits (the library is built with -fmad=false).
 #pragma once
 #include "b200_util.cuh"
+#include <type_traits>
 #include "../../include/b200phys.h"
 
 namespace b200 {
@@ -684,21 +685,25 @@ B200_D void epa(const SimplexD& g, const SupportD& A, const SupportD& B, f3& out
 // its simplex by the large-capacity kernel, which gives the same result because the expansion is deterministic.
 // Indices are bytes (0xFF stands for the 0xFFFF a degenerate horizon leaves behind), the activity flags one register, the per-edge
 // reference counts of collision_epa.cpp:114-139 two register bit masks (seen once / seen more often).
-#define B200_EPAS_MAX_POINTS 10
-#define B200_EPAS_MAX_TRIS 30
-#define B200_EPAS_MAX_EDGES 32
-#define B200_EPAS_WORDS (B200_EPAS_MAX_POINTS * 6 + B200_EPAS_MAX_TRIS * 6 + B200_EPAS_MAX_EDGES)
-struct EpaSmall
+// Two sizes are instantiated (k_narrow.cu): <10, 30, 32> for everybody (272 words, 6 warps per SM, masks in 32-bit registers) and
+// <16, 62, 64> for the runs that outgrow it (532 words, 3 warps per SM, 64-bit masks); what outgrows that too goes to the warp-cooperative kernel.
+template <uint32_t MAXP, uint32_t MAXT, uint32_t MAXE>
+struct EpaSm
 {
+    static_assert(MAXT <= 64 && MAXE <= 64 && MAXP <= 16 && MAXE < 127, "masks are one machine word, indices bytes");
+    typedef typename std::conditional<(MAXT > 32 || MAXE > 32), unsigned long long, uint32_t>::type Mask;
+    static constexpr uint32_t kWords = MAXP * 6 + MAXT * 6 + MAXE;
     uint32_t* w;             // this lane's column
-    uint32_t active, nT, nP, nE;
-    static constexpr uint32_t kTri = B200_EPAS_MAX_POINTS * 6, kEdge = kTri + B200_EPAS_MAX_TRIS * 6;
+    Mask active; uint32_t nT, nP, nE;
+    static constexpr uint32_t kTri = MAXP * 6, kEdge = kTri + MAXT * 6;
+    B200_D static uint32_t lowest(Mask m) { return sizeof(Mask) == 8 ? (uint32_t)__ffsll((long long)m) - 1u : (uint32_t)__ffs((int)(uint32_t)m) - 1u; }
+    B200_D static Mask bit(uint32_t i) { return (Mask)1 << i; }
     B200_D float ldf(uint32_t k) const { return __uint_as_float(w[k << 5]); }
     B200_D uint32_t ldu(uint32_t k) const { return w[k << 5]; }
     B200_D void stf(uint32_t k, float v) { w[k << 5] = __float_as_uint(v); }
     B200_D void stu(uint32_t k, uint32_t v) { w[k << 5] = v; }
     B200_D static uint32_t wide(uint32_t b) { return b == 0xFFu ? 0xFFFFu : b; }           // byte -> the reference's uint16 index
-    B200_D bool isActive(uint32_t i) const { return i < nT && ((active >> i) & 1u); }
+    B200_D bool isActive(uint32_t i) const { return i < nT && ((active >> i) & (Mask)1); }
     B200_D SupPt pt(uint32_t i) const
     {
         SupPt p; const uint32_t k = 6 * i;
@@ -708,29 +713,29 @@ struct EpaSmall
     B200_D f3 ptM(uint32_t i) const { const uint32_t k = 6 * i; return mk3(ldf(k), ldf(k + 1), ldf(k + 2)) - mk3(ldf(k + 3), ldf(k + 4), ldf(k + 5)); }
     B200_D bool pushPoint(const SupPt& p)
     {
-        if (nP >= B200_EPAS_MAX_POINTS) return false;
+        if (nP >= MAXP) return false;
         const uint32_t k = 6 * nP; stf(k, p.a.x); stf(k + 1, p.a.y); stf(k + 2, p.a.z); stf(k + 3, p.b.x); stf(k + 4, p.b.y); stf(k + 5, p.b.z);
         ++nP; return true;
     }
     B200_D bool pushTri(uint32_t a, uint32_t b, uint32_t c, uint32_t eA, uint32_t eB, uint32_t eC, f3 n, float d)
     {
-        if (nT >= B200_EPAS_MAX_TRIS) return false;
+        if (nT >= MAXT) return false;
         const uint32_t k = kTri + 6 * nT;
         stf(k, n.x); stf(k + 1, n.y); stf(k + 2, n.z); stf(k + 3, d); stu(k + 4, a | (b << 8) | (c << 16)); stu(k + 5, (eA & 0xFFu) | ((eB & 0xFFu) << 8) | ((eC & 0xFFu) << 16));
-        active |= 1u << nT; ++nT; return true;
+        active |= bit(nT); ++nT; return true;
     }
     B200_D bool pushEdge(uint32_t a, uint32_t b, uint32_t t0, uint32_t t1)
     {
-        if (nE >= B200_EPAS_MAX_EDGES) return false;
+        if (nE >= MAXE) return false;
         stu(kEdge + nE, a | (b << 8) | ((t0 & 0xFFu) << 16) | ((t1 & 0xFFu) << 24));
         ++nE; return true;
     }
     B200_D uint32_t closest() const
     {   // collision_epa.cpp:94-112
         uint32_t best = 0xFFFFFFFFu; float mind = FLT_MAX;
-        for (uint32_t rest = active; rest; rest &= rest - 1u)
+        for (Mask rest = active; rest; rest &= rest - 1)
         {
-            const uint32_t i = (uint32_t)__ffs((int)rest) - 1u;
+            const uint32_t i = lowest(rest);
             const float d = ldf(kTri + 6 * i + 3);
             if (d < mind) { mind = d; best = i; }
         }
@@ -767,10 +772,10 @@ struct EpaSmall
     // collision_epa.cpp:114-239 ; false = a capacity of the SMALL polytope was hit (the caller hands the pair to the large kernel)
     B200_D bool addPoint(const SupPt& np)
     {
-        uint32_t once = 0, more = 0;
-        for (uint32_t rest = active; rest; rest &= rest - 1u)
+        Mask once = 0, more = 0;
+        for (Mask rest = active; rest; rest &= rest - 1)
         {
-            const uint32_t i = (uint32_t)__ffs((int)rest) - 1u, k = kTri + 6 * i;
+            const uint32_t i = lowest(rest), k = kTri + 6 * i;
             const uint32_t idx = ldu(k + 4);
             const float d = dot(mk3(ldf(k), ldf(k + 1), ldf(k + 2)), np.m - ptM(idx & 0xFFu));
             if (d > 0.f)
@@ -780,26 +785,26 @@ struct EpaSmall
                 for (int j = 0; j < 3; ++j)
                 {
                     const uint32_t ei = (e >> (8 * j)) & 0xFFu;
-                    if (ei < nE) { const uint32_t bit = 1u << ei; more |= once & bit; once |= bit; }
+                    if (ei < nE) { const Mask b = bit(ei); more |= once & b; once |= b; }
                 }
-                active &= ~(1u << i);
+                active &= ~bit(i);
             }
         }
-        const uint32_t border = once & ~more;                    // refs == 1, ascending edge index
-        unsigned long long newEdgePerPoint = ~0ull;              // 6 bits per point, 63 = none
+        const Mask border = once & ~more;                    // refs == 1, ascending edge index
+        unsigned long long nepp0 = ~0ull, nepp1 = ~0ull;         // newEdgePerPoint: 7 bits per point (8 points per word), 127 = none
         const uint32_t npi = nP;
         if (!pushPoint(np)) return false;
         const uint32_t triOffset = nT;
-        for (uint32_t rest = border; rest; rest &= rest - 1u)
+        for (Mask rest = border; rest; rest &= rest - 1)
         {
-            const uint32_t ei = (uint32_t)__ffs((int)rest) - 1u;
+            const uint32_t ei = lowest(rest);
             const uint32_t e = ldu(kEdge + ei);
             const uint32_t ea = e & 0xFFu, eb = (e >> 8) & 0xFFu;
             const bool aAct = isActive((e >> 16) & 0xFFu), bAct = isActive(e >> 24);
             const uint32_t connect = bAct ? ea : eb;
             const uint32_t triIndex = nT, ne = nE;
             if (!pushEdge(connect, npi, 0xFFu, triIndex)) return false;
-            newEdgePerPoint = (newEdgePerPoint & ~(63ull << (6 * connect))) | ((unsigned long long)ne << (6 * connect));
+            { const uint32_t sh = 7u * (connect & 7u); unsigned long long& word = connect < 8u ? nepp0 : nepp1; word = (word & ~(127ull << sh)) | ((unsigned long long)ne << sh); }
             const uint32_t bI = connect, cI = bAct ? eb : ea;
             f3 n; float d; EpaPoly::triInfo(np, pt(bI), pt(cI), n, d);
             if (!pushTri(npi, bI, cI, ei, 0xFFu, ne, n, d)) return false;
@@ -807,15 +812,15 @@ struct EpaSmall
             stu(kEdge + ei, aAct ? ((e2 & 0x00FFFFFFu) | (triIndex << 24)) : ((e2 & 0xFF00FFFFu) | (triIndex << 16)));
         }
         uint32_t i = 0;
-        for (uint32_t rest = border; rest; rest &= rest - 1u, ++i)
+        for (Mask rest = border; rest; rest &= rest - 1, ++i)
         {
-            const uint32_t ei = (uint32_t)__ffs((int)rest) - 1u;
+            const uint32_t ei = lowest(rest);
             const uint32_t e = ldu(kEdge + ei);
             const bool bNew = wide(e >> 24) >= triOffset;
             const uint32_t connect = bNew ? (e & 0xFFu) : ((e >> 8) & 0xFFu);
-            const uint32_t other = (uint32_t)(newEdgePerPoint >> (6 * connect)) & 63u;
+            const uint32_t other = (uint32_t)((connect < 8u ? nepp0 : nepp1) >> (7u * (connect & 7u))) & 127u;
             const uint32_t triIndex = i + triOffset;
-            if (other == 63u) continue;
+            if (other == 127u) continue;
             const uint32_t kt = kTri + 6 * triIndex + 5;
             stu(kt, (ldu(kt) & 0xFFFF00FFu) | (other << 8));
             stu(kEdge + other, (ldu(kEdge + other) & 0xFF00FFFFu) | (triIndex << 16));
@@ -823,6 +828,10 @@ struct EpaSmall
         return true;
     }
 };
+
+typedef EpaSm<10, 30, 32> EpaSmall;
+typedef EpaSm<16, 62, 64> EpaMedium;
+#define B200_EPAS_WORDS (EpaSmall::kWords)
 
 // ---- warp-cooperative EPA (PHASE 3). One warp expands ONE polytope that lives in shared memory; all 32 lanes execute the calling
 // routine uniformly (same pair, same data) and split the per-triangle / per-edge loops of collision_epa.cpp:94-239 among themselves.

@@ -15,5 +15,5 @@ for s in range(nsteps):
     if s >= nsteps - 5:
         for k, v in st.timeline(): acc[k] = acc.get(k, 0.0) + v / 5
 s = st.stats(check=False)
-print("EPA=%s BPS=%s  N=%d manifolds=%d epaOvf=%d epaRuns=%d redo=%d | " % (os.environ.get("B200PHYS_EPA", "small"), os.environ.get("B200PHYS_EPA_BPS", "-"), len(sc["bodies"]), s.numCollisions, s.epaOverflows, s.reserved[4], s.reserved[5]) +
+print("EPA=%s BPS=%s  N=%d manifolds=%d epaOvf=%d epaRuns=%d redo=%d redo2=%d | " % (os.environ.get("B200PHYS_EPA", "small"), os.environ.get("B200PHYS_EPA_BPS", "-"), len(sc["bodies"]), s.numCollisions, s.epaOverflows, s.reserved[4], s.reserved[5] & 0xFFFFF, s.reserved[5] >> 20) +
       " ".join("%s %.3f" % (k, v) for k, v in acc.items() if k.startswith("np_")) + " | total %.3f" % sum(acc.values()))
