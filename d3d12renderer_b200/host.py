@@ -30,6 +30,9 @@ def load_library():
     lib.b200host_build_mixed_slab.argtypes = [vp, u32, u32, u32, u32, u32, C.c_uint64, C.c_float]
     lib.b200host_add_cloth.argtypes = [vp, C.c_float, C.c_float, u32, u32, C.c_float, C.c_float, C.c_float, C.c_float]; lib.b200host_add_cloth.restype = u32
     lib.b200host_cloth_set_fixed.argtypes = [vp, u32, vp, vp, C.c_int]; lib.b200host_cloth_positions.argtypes = [vp, u32, vp]; lib.b200host_cloth_positions.restype = u32
+    lib.b200host_serialize_entity.argtypes = [vp, u32, vp, C.c_uint64]; lib.b200host_serialize_entity.restype = C.c_uint64
+    lib.b200host_deserialize_entity.argtypes = [vp, vp, C.c_uint64]; lib.b200host_deserialize_entity.restype = u32
+    lib.b200host_entity_of_body.argtypes = [vp, u32]; lib.b200host_entity_of_body.restype = u32; lib.b200host_num_entities.argtypes = [vp]; lib.b200host_num_entities.restype = u32
     lib.b200host_set_heightmap.argtypes = [vp, u32, C.c_float, vp, C.c_float, C.c_float, C.c_float, vp]
     for n in ("b200host_num_bodies", "b200host_num_colliders", "b200host_num_hulls", "b200host_num_hull_vertices"):
         getattr(lib, n).argtypes = [vp]; getattr(lib, n).restype = u32
@@ -91,6 +94,18 @@ class HostScene:
     def cloth_positions(self, cloth):
         n = self.lib.b200host_cloth_positions(self.ptr, cloth, None)
         out = np.zeros((n, 3), dtype=np.float32); self.lib.b200host_cloth_positions(self.ptr, cloth, _p(out)); return out
+
+    def serialize_entity(self, entity):
+        """serializeEntityToMemory -> bytes"""
+        buf = np.zeros(1 << 16, dtype=np.uint8); n = self.lib.b200host_serialize_entity(self.ptr, entity, _p(buf), buf.size)
+        return buf[:n].tobytes()
+
+    def deserialize_entity(self, data):
+        """deserializeEntityFromMemory into a new entity -> its handle (None on failure)"""
+        b = np.frombuffer(data, dtype=np.uint8).copy(); h = self.lib.b200host_deserialize_entity(self.ptr, _p(b), b.size)
+        return None if h == 0xFFFFFFFF else h
+
+    def entity_of_body(self, body): return self.lib.b200host_entity_of_body(self.ptr, body)
 
     def set_heightmap(self, h):
         """heightmap_collider_component of the scene (dict as in scenes.terrain_drop)."""

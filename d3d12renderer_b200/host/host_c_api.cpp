@@ -300,6 +300,14 @@ uint32_t b200host_cloth_positions(void* sp, uint32_t cloth, float* out3)
     return (uint32_t)c.positions.size();
 }
 
+// binary entity stream (scene/serialization_binary.h): entity -> bytes; bytes -> a NEW entity of this scene (returns its handle, 0xFFFFFFFF on failure)
+uint64_t b200host_serialize_entity(void* sp, uint32_t entity, uint8_t* out, uint64_t cap)
+{ game_scene& s = *(game_scene*)sp; if (entity >= s.entities.size()) return 0; scene_entity e = { entity, &s }; return serializeEntityToMemory(e, out, cap); }
+uint32_t b200host_deserialize_entity(void* sp, const uint8_t* bytes, uint64_t size)
+{ game_scene& s = *(game_scene*)sp; scene_entity e = s.createEntity(""); return deserializeEntityFromMemory(e, bytes, size) ? e.handle : 0xFFFFFFFFu; }
+uint32_t b200host_entity_of_body(void* sp, uint32_t body) { game_scene& s = *(game_scene*)sp; return body < s.rigidBodyEntity.size() ? s.rigidBodyEntity[body] : 0xFFFFFFFFu; }
+uint32_t b200host_num_entities(void* sp) { return (uint32_t)((game_scene*)sp)->entities.size(); }
+
 int b200host_build_mixed_slab(void* sp, uint32_t nxTotal, uint32_t ny, uint32_t nz, uint32_t ix0, uint32_t ix1, uint64_t seed, float spacing)
 {
     game_scene& s = *(game_scene*)sp;

@@ -343,6 +343,9 @@ void testPhysicsInteraction(game_scene& scene, vec3 rayOrigin, vec3 rayDirection
                             uint32_t firstCollider = 0, uint32_t numColliders = 0xFFFFFFFFu);   // body / collider (creation order) ranges restrict the test (batched environments)
 
 int physicsStep(game_scene& scene, memory_arena& arena, float& timer, const physics_settings& settings, float dt);
+// scene/serialization_binary.h: the binary entity stream (physics components), scene_binary.cpp
+uint64_t serializeEntityToMemory(scene_entity entity, void* memory, uint64_t maxSize);
+bool deserializeEntityFromMemory(scene_entity entity, const void* memory, uint64_t size);
 int uploadSceneToDevice(game_scene& scene);     // creates the device context if needed and uploads whatever changed, without stepping
 
 } // namespace b200host

@@ -285,6 +285,62 @@ void ref_cloth_get(void* c, float* positions, float* velocities)
         if (velocities) { velocities[3 * i] = v[i].x; velocities[3 * i + 1] = v[i].y; velocities[3 * i + 2] = v[i].z; }
     }
 }
+// ---- binary entity stream (scene/serialization_binary.cpp:137-513). That file itself cannot be compiled here (asset registry, meshes,
+// terrain); what IS reference-owned are the component structs it memcpy's. This restates the stream framing -- one bool per component
+// type of serialized_components in order, then the payload -- over the reference's real components: the struct layouts (g++ build of
+// the patched headers; sizes checked against SURVEY 8's MSVC sizes by ref_layout_info) pin the byte layout of every physics payload.
+void ref_layout_info(uint32* out)
+{
+    out[0] = (uint32)sizeof(trs); out[1] = (uint32)sizeof(rigid_body_component); out[2] = (uint32)sizeof(collider_union); out[3] = (uint32)offsetof(collider_union, material);
+    out[4] = (uint32)offsetof(collider_union, type); out[5] = (uint32)offsetof(collider_union, objectIndex); out[6] = (uint32)sizeof(tag_component);
+    out[7] = (uint32)sizeof(distance_constraint); out[8] = (uint32)sizeof(ball_constraint); out[9] = (uint32)sizeof(fixed_constraint); out[10] = (uint32)sizeof(hinge_constraint);
+    out[11] = (uint32)sizeof(cone_twist_constraint); out[12] = (uint32)sizeof(slider_constraint); out[13] = (uint32)sizeof(physics_material); out[14] = (uint32)sizeof(constraint_type);
+    out[15] = (uint32)sizeof(entity_handle);
+}
+uint64 ref_scene_serialize_body_entity(void* p, uint32 bodyIndex, uint8* out, uint64 cap)
+{
+    RefScene& R = *(RefScene*)p;
+    scene_entity entity = { R.bodyEntities[bodyIndex], R.scene };
+    uint64 n = 0;
+    auto put = [&](const void* src, uint64 bytes) { if (n + bytes <= cap) memcpy(out + n, src, bytes); n += bytes; };
+    auto flag = [&](bool b) { put(&b, 1); };
+    auto whole = [&](auto* comp) { flag(comp != nullptr); if (comp) put(comp, sizeof(*comp)); };
+    whole(entity.getComponentIfExists<tag_component>());
+    whole(entity.getComponentIfExists<transform_component>());
+    flag(false); flag(false); flag(false);                                   // position / position_rotation / position_scale
+    flag(entity.hasComponent<dynamic_transform_component>());                // empty payload (:148-149)
+    flag(false); flag(false); flag(false);                                   // mesh, point light, spot light
+    whole(entity.getComponentIfExists<rigid_body_component>());
+    whole(entity.getComponentIfExists<force_field_component>());
+    flag(false);                                                             // cloth_component: a stand-alone entity in the tests
+    flag(false);                                                             // cloth_render_component
+    if (physics_reference_component* ref = entity.getComponentIfExists<physics_reference_component>())
+    {   // :207-234
+        flag(true);
+        put(&ref->numColliders, 4);
+        for (collider_component& collider : collider_component_iterator(entity)) put((collider_union*)&collider, sizeof(collider_union));
+        put(&ref->numConstraints, 4);
+        for (auto [constraintEntity, constraintType] : constraint_entity_iterator(entity))
+        {
+            auto& cref = constraintEntity.getComponent<constraint_entity_reference_component>();
+            put(&constraintType, sizeof(constraintType)); put(&cref.entityA, sizeof(entity_handle)); put(&cref.entityB, sizeof(entity_handle));
+            switch (constraintType)
+            {
+                case constraint_type_distance: put(&constraintEntity.getComponent<distance_constraint>(), sizeof(distance_constraint)); break;
+                case constraint_type_ball: put(&constraintEntity.getComponent<ball_constraint>(), sizeof(ball_constraint)); break;
+                case constraint_type_fixed: put(&constraintEntity.getComponent<fixed_constraint>(), sizeof(fixed_constraint)); break;
+                case constraint_type_hinge: put(&constraintEntity.getComponent<hinge_constraint>(), sizeof(hinge_constraint)); break;
+                case constraint_type_cone_twist: put(&constraintEntity.getComponent<cone_twist_constraint>(), sizeof(cone_twist_constraint)); break;
+                case constraint_type_slider: put(&constraintEntity.getComponent<slider_constraint>(), sizeof(slider_constraint)); break;
+                default: break;
+            }
+        }
+    }
+    else flag(false);
+    flag(false); flag(false); flag(false); flag(false); flag(false);         // terrain, heightmap collider, grass, proc placement, water
+    return n;
+}
+uint32 ref_scene_entity_of_body(void* p, uint32 bodyIndex) { return (uint32)((RefScene*)p)->bodyEntities[bodyIndex]; }
 uint32 ref_scene_num_bodies(void* p) { return (uint32)((RefScene*)p)->bodyEntities.size(); }
 uint32 ref_scene_num_colliders(void* p) { return ((RefScene*)p)->scene.numberOfComponentsOfType<collider_component>(); }
 uint32 ref_scene_num_joints(void* p, int kind)

@@ -49,6 +49,8 @@ def load(fast=False):
     lib.ref_env_sizes.argtypes = [vp, vp]; lib.ref_env_ranges.argtypes = [vp, vp]
     lib.ref_env_reset.argtypes = [C.c_uint64, f32, i32, vp]; lib.ref_env_update.argtypes = [vp, vp, vp]; lib.ref_env_update.restype = i32
     lib.ref_mass_properties.argtypes = [vp, vp, vp, vp]
+    lib.ref_layout_info.argtypes = [vp]; lib.ref_scene_serialize_body_entity.argtypes = [vp, u32, vp, C.c_uint64]; lib.ref_scene_serialize_body_entity.restype = C.c_uint64
+    lib.ref_scene_entity_of_body.argtypes = [vp, u32]; lib.ref_scene_entity_of_body.restype = u32
     lib.ref_cloth_create.argtypes = [f32, f32, u32, u32, f32, f32, f32, f32]; lib.ref_cloth_create.restype = vp
     lib.ref_cloth_destroy.argtypes = [vp]; lib.ref_cloth_set_fixed.argtypes = [vp, vp, vp, vp, i32]; lib.ref_cloth_set_properties.argtypes = [vp, f32, f32, f32, f32]
     lib.ref_cloth_wind.argtypes = [vp, vp]; lib.ref_cloth_simulate.argtypes = [vp, u32, u32, u32, f32]; lib.ref_cloth_get.argtypes = [vp, vp, vp]
@@ -117,6 +119,13 @@ class RefScene:
         self.lib.ref_scene_set_hinge_motor(self.ptr, index, motor_type, value, max_torque)
 
     def heightmap_height_at(self, x, z): return float(self.lib.ref_scene_heightmap_height_at(self.ptr, x, z))
+
+    def serialize_body_entity(self, body):
+        """the binary entity stream of the entity that owns rigid body `body` (restated framing over the reference's own component structs)"""
+        buf = np.zeros(1 << 16, dtype=np.uint8); n = self.lib.ref_scene_serialize_body_entity(self.ptr, body, _p(buf), buf.size)
+        return buf[:n].tobytes()
+
+    def entity_of_body(self, body): return self.lib.ref_scene_entity_of_body(self.ptr, body)
 
     def num_bodies(self): return self.lib.ref_scene_num_bodies(self.ptr)
     def num_colliders(self): return self.lib.ref_scene_num_colliders(self.ptr)
