@@ -5,7 +5,7 @@
 // physics_reference_component the entity's colliders as collider_union structs and its constraints as (type, entityA, entityB, struct)
 // (:207-266). Payload byte layouts are the reference's struct layouts (trs 48, rigid_body_component 112, collider_union 80 with the material
 // at 48 and type / objectType / objectIndex at 64 / 65 / 66, the six constraint structs 28 / 24 / 48 / 104 / 120 / 80 bytes): verified against
-// the compiled reference (oracle/_ref, ref_layout_info) by tests/test_ref_pins_oracle.py. Rendering / terrain components are written as
+// the compiled reference by tests/test_ref_pins_oracle.py (ref_layout_info). Rendering / terrain components are written as
 // "absent"; a stream that contains one cannot be read here (their sizes are not part of the stream).
 #include "physics_host.h"
 #include <cstring>
