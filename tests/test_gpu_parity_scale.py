@@ -368,3 +368,50 @@ def test_device_side_environment_matches_the_host_side_one():
     assert resets > 2, "no environment ever failed: the reset path is untested"
     for env in envs:
         env.close()
+
+
+# ------------------------------------------------------------------------------------------------ full-size properties
+def _full_size_properties(sc, steps, sample=1500, seed=0):
+    """Size-independent checks at a BASELINE size the oracle cannot step in seconds: canonical pair list, soundness of every pair and
+    completeness on a random sample of colliders (numpy all-pairs AABB test, the oracle's predicate collision_broad.cpp:316-340), contact
+    sanity, counters, and run-to-run determinism."""
+    results = []
+    for run in range(2):
+        st = make_stepper(sc)
+        for _ in range(steps):
+            st.step(DT, 10, abi.STEP_FAST)
+        s = st.stats()
+        assert s.overflowPairs == 0 and s.overflowManifolds == 0 and s.overflowGrid == 0 and s.epaOverflows <= 4
+        pairs = st.download_pairs(); aabbs = st.download_aabbs(); contacts, cb = st.download_contacts(); bodies = st.download_bodies()
+        results.append((pairs, contacts, bodies))
+        if run == 0:
+            a, b = pairs[:, 0].astype(np.int64), pairs[:, 1].astype(np.int64)
+            assert np.all(a < b), "pairs are stored (low, high)"
+            key = a * (1 << 32) + b
+            assert np.all(np.diff(key) > 0), "pair list sorted and free of duplicates"
+            mn, mx = aabbs[:, :3], aabbs[:, 3:]
+            assert np.all(mn[a] <= mx[b]) and np.all(mn[b] <= mx[a]), "every reported pair overlaps (inclusive, like aabbVsAABB)"
+            rng = np.random.default_rng(seed)
+            pick = rng.choice(len(aabbs), size=sample, replace=False)
+            for i in pick:
+                hit = np.nonzero(np.all(mn <= mx[i], axis=1) & np.all(mn[i] <= mx, axis=1))[0]
+                hit = hit[hit != i]
+                lo, hi = np.searchsorted(a, i, "left"), np.searchsorted(a, i, "right")
+                mine = set(b[lo:hi].tolist()) | set(a[b == i].tolist())
+                assert mine == set(hit.tolist()), "collider %d: %d reported vs %d overlapping" % (i, len(mine), len(hit))
+            n = np.linalg.norm(contacts["normal"], axis=1)
+            assert len(contacts) == s.numContacts and np.all(np.abs(n - 1.0) < 1e-3) and np.all(contacts["penetrationDepth"] >= 0.0)
+            assert np.all(np.isfinite(bodies["position"])) and np.all(np.isfinite(bodies["linearVelocity"]))
+        st.close()
+    assert np.array_equal(results[0][0], results[1][0]) and results[0][1].tobytes() == results[1][1].tobytes() and results[0][2].tobytes() == results[1][2].tobytes(), "two runs differ"
+
+
+def test_full_size_config2_properties():
+    """BASELINE configs[1] at its full size: 262 144 spheres settling in the open box (5 oversized static boxes: the big-collider path)."""
+    _full_size_properties(scenes.sphere_pile_settled(64, 64, 64), steps=6)
+
+
+def test_full_size_config3_eighth_properties():
+    """BASELINE configs[2] lattice at 131 072 mixed primitives (spheres, capsules, OBBs, hulls): grid with two cells per extent, overflow rows,
+    every GJK / EPA kernel incl. the redo path."""
+    _full_size_properties(host.build_scene(host.CONFIG_MIXED_PILE, 64, 32, 64, seed=1578123, spacing=0.8), steps=6, sample=800)
