@@ -200,35 +200,13 @@ struct WarpRange
     }
 };
 
-// A pair whose shapes are more than a millimetre apart along the line between their centres cannot be reported as touching by
-// gjkIntersectionTest (its Minkowski points all lie beyond a plane that excludes the origin; a millimetre is far above the rounding of
-// the support points), and a miss carries no data: such pairs are answered by ONE support evaluation along a direction that is good by
-// construction, instead of the 2-4 the reference needs from its fixed start direction (1, 0.1, -0.2). Hits are unaffected (bit-exact).
-B200_D f3 supportCentre(const SupportD& S)
-{
-    switch (S.type)
-    {
-    case B200PHYS_SPHERE: return S.a;
-    case B200PHYS_CAPSULE: case B200PHYS_CYLINDER: case B200PHYS_AABB: return (S.a + S.b) * 0.5f;
-    default: return S.c;
-    }
-}
-B200_D bool separatedAlongCentres(const SupportD& A, const SupportD& B)
-{
-    const f3 d = supportCentre(B) - supportCentre(A);
-    const float l2 = sqLen(d);
-    if (!(l2 > 1e-6f)) return false;
-    const f3 pa = A.eval(d), pb = B.eval(-d);
-    return dot(pb, d) - dot(pa, d) > 1e-3f * sqrtf(l2);
-}
-
 // phase 1: GJK (collision_gjk.h:184-238) for every pair of the GJK buckets. Misses (and the closed-form exits of cylinder-cylinder) are
 // final; hits are parked with their terminal simplex in the EPA work list. Most pairs leave after one or two support evaluations and
 // the rest take 3-10 rounds, so the lanes of a warp are NOT tied to one pair each for a whole test: the loop below performs one
 // support evaluation per pass for every lane and a lane whose pair is decided takes the next pair of the bucket at once.
 __global__ void __launch_bounds__(128, 4) npGjkKernel(const uint2* __restrict__ sorted, const float4* __restrict__ wCol, const float4* __restrict__ hullVerts,
     const uint32_t* __restrict__ hullOffsets, float4* __restrict__ manTmp, unsigned long long* __restrict__ manScan, uint32_t maxPairs,
-    float4* __restrict__ sxPlanes, uint2* __restrict__ epaWork, uint32_t sxCap, DeviceCounts* cnt, uint32_t refillAt, int preTest)
+    float4* __restrict__ sxPlanes, uint2* __restrict__ epaWork, uint32_t sxCap, DeviceCounts* cnt, uint32_t refillAt)
 {
     constexpr uint32_t list2[11] = { 5, 8, 9, 10, 11, 12, 13, 14, 17, 19, 20 };
     NarrowCounters nc; nc.epaOverflow = nc.gjkCap = nc.asserts = 0;
@@ -264,7 +242,6 @@ __global__ void __launch_bounds__(128, 4) npGjkKernel(const uint2* __restrict__ 
             Man m; m.cnt = 0;
             const int st = gjkPrep(bucket, A, B, hullVerts, hullOffsets, m, nc, job);
             if (st != 2) storeManifold(manTmp, manScan, q, maxPairs, st == 1, m);
-            else if (preTest && separatedAlongCentres(job.A, job.B)) manScan[q] = 0ull;    // provably apart: GJK could only say "no"
             else { busy = true; stage = 0; dir = mk3(1.f, 0.1f, -0.2f); }        // collision_gjk.h:190
         }
         const uint32_t busyMask = __ballot_sync(0xffffffffu, busy);
@@ -577,11 +554,9 @@ void launchNarrowphase(Context* c)
     launchK(c, npCollideKernel<0>, G, 256, 0, c->pairsSorted, c->wCol, c->manTmp, c->manScan, c->maxPairs, cnt);
     launchK(c, npCollideKernel<1>, gridFor(c, 4), 128, 0, c->pairsSorted, c->wCol, c->manTmp, c->manScan, c->maxPairs, cnt);
     timelineMark(c, "np_closed_form_sat");
-    static int gjkPreTest = -1;      // B200PHYS_GJK_PRETEST=0: every pair goes through the reference's GJK iteration (tuning / comparison)
-    if (gjkPreTest < 0) { const char* e = getenv("B200PHYS_GJK_PRETEST"); gjkPreTest = (e && e[0] == '0') ? 0 : 1; }
     static int gjkRefill = -1, epaRefill = -1;     // lanes that must be idle before a warp sets up new pairs (tuning: B200PHYS_GJK_REFILL / B200PHYS_EPA_REFILL)
     if (gjkRefill < 0) { const char* e = getenv("B200PHYS_GJK_REFILL"); gjkRefill = e ? atoi(e) : 16; e = getenv("B200PHYS_EPA_REFILL"); epaRefill = e ? atoi(e) : 16; }
-    launchK(c, npGjkKernel, gridFor(c, 8), 128, 0, c->pairsSorted, c->wCol, c->hullVerts, c->hullOffsets, c->manTmp, c->manScan, c->maxPairs, c->epaSimplex, c->epaWork, c->maxEpaWork, cnt, (uint32_t)gjkRefill, gjkPreTest);
+    launchK(c, npGjkKernel, gridFor(c, 8), 128, 0, c->pairsSorted, c->wCol, c->hullVerts, c->hullOffsets, c->manTmp, c->manScan, c->maxPairs, c->epaSimplex, c->epaWork, c->maxEpaWork, cnt, (uint32_t)gjkRefill);
     timelineMark(c, "np_gjk");
     static int epaMode = -1, epaBps = 0;
     {

@@ -385,7 +385,7 @@ def _full_size_properties(sc, steps, sample=1500, seed=0):
         pairs = st.download_pairs(); aabbs = st.download_aabbs(); contacts, cb = st.download_contacts(); bodies = st.download_bodies()
         results.append((pairs, contacts, bodies))
         if run == 0:
-            a, b = pairs[:, 0].astype(np.int64), pairs[:, 1].astype(np.int64)
+            a, b = pairs["a"].astype(np.int64), pairs["b"].astype(np.int64)
             assert np.all(a < b), "pairs are stored (low, high)"
             key = a * (1 << 32) + b
             assert np.all(np.diff(key) > 0), "pair list sorted and free of duplicates"
