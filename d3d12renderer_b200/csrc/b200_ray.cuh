@@ -77,7 +77,7 @@ B200_HD bool intersectCylinder(const lray& r, f3 posA, f3 posB, float radius, fl
 }
 B200_HD bool intersectCapsule(const lray& r, f3 a, f3 b, float radius, float& outT)
 {
-    outT = FLT_MAX; float t; bool result = false;
+    outT = FLT_MAX; float t = 0.f; bool result = false;
     if (intersectCylinder(r, a, b, radius, t)) { outT = t; result = true; }
     if (intersectSphere(r, a, radius, t)) { outT = fminf(outT, t); result = true; }
     if (intersectSphere(r, b, radius, t)) { outT = fminf(outT, t); result = true; }
