@@ -301,7 +301,8 @@ def test_graph_replay_is_bit_identical_to_plain_launches(config, dims, spacing, 
 
 
 # ------------------------------------------------------------------------------------------------ RL environment (f.3)
-def test_locomotion_env_matches_the_reference_environment():
+@pytest.mark.parametrize("device_mode", [False, True])
+def test_locomotion_env_matches_the_reference_environment(device_mode):
     """The batched environment (host/locomotion_env.cpp over the CUDA step) against the reference's OWN environment, compiled from
     learned_locomotion.cpp (oracle/_ref: resetPhysics / updatePhysics, one ragdoll): same action ranges; with the same random actions
     the 66-float state, the reward and the failure flag agree step by step, also with pushes forced on (probability 1, same generator
@@ -311,6 +312,7 @@ def test_locomotion_env_matches_the_reference_environment():
         pytest.skip("oracle/_ref not built")
     ref = ref_lib.RefEnv()
     env = host.LocomotionEnv(4, spacing=6.0)
+    env.set_device_mode(device_mode)           # the formulas evaluated on the host from downloaded poses, or everything on the GPU (k_env.cu)
     env.set_exact_order(True)                  # joints in array order like the reference's scalar solver (the DLL's default AVX2 path re-orders them)
     assert (ref.state_size, ref.action_size) == (env.state_size, env.action_size) == (66, 27)
     lo, hi = env.action_ranges(); rlo, rhi = ref.ranges()
