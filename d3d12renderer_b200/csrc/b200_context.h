@@ -163,6 +163,10 @@ struct Context
     unsigned long long* scanStatus = nullptr; uint32_t* scanState = nullptr; uint32_t scanStatusTiles = 0, scanEpoch = 0;   // single-pass scan
     unsigned long long* refKeys[2] = {}; uint8_t* refColors = nullptr; uint8_t* colorKey = nullptr; int refParity = 0, colorAge = 0;   // colour reuse across steps
     uint8_t* refColorsJoint[6] = {}; uint32_t jointColorCount[6] = {}; int jointColorAge[6] = {};
+    // the joint graph is static between uploads: solve order, dataflow ranks and the per-body unit counts of the joint groups are kept
+    // (fast mode) as long as neither the joints' body pairs nor the body set changed
+    uint32_t* bodyBaseJoints = nullptr; uint32_t bodiesEpoch = 1, jointsEpoch = 1, jointCacheBodiesEpoch = 0, jointCacheJointsEpoch = 0, jointCacheNumBodies = 0;
+    std::vector<b200phys_body_pair>* jointPairsHost = nullptr;      // [6] last uploaded pairs (to tell a parameter refresh from a topology change)
     // the per-step accumulator upload runs on its own stream so that it overlaps the collision detection (b200phys_upload_forces)
     cudaStream_t copyStream = nullptr; cudaEvent_t evCopyGate = nullptr, evForcesDone = nullptr; bool forcesPending = false; void* forceStaging = nullptr;
     uint32_t* colorQueue = nullptr;         // ready queue of the colouring (max units of any group)

@@ -35,7 +35,7 @@ int allocateAll(Context& c)
     CK(devAlloc(c.bRot, N1)); CK(devAlloc(c.bPos, N1)); CK(devAlloc(c.bCog, N1)); CK(devAlloc(c.bInvI, 3 * N1));
     CK(devAlloc(c.bVel, N1)); CK(devAlloc(c.bAng, N1)); CK(devAlloc(c.bForce, N1)); CK(devAlloc(c.bTorque, N1));
     CK(devAlloc(c.gVel, 2 * N1)); CK(devAlloc(c.gPos, N1)); CK(devAlloc(c.gInvI, 3 * N1));
-    CK(devAlloc(c.bodyMask, N1 + 1)); CK(devAlloc(c.bodyBase, N1 + 1));
+    CK(devAlloc(c.bodyMask, N1 + 1)); CK(devAlloc(c.bodyBase, N1 + 1)); CK(devAlloc(c.bodyBaseJoints, N1 + 1));
     CK(devAlloc(c.colorQueue, (M > J ? M : J) + 32));
     for (int k = 0; k < 6; ++k) CK(devAlloc(c.refColorsJoint[k], J + 2));
     CK(devAlloc(c.refKeys[0], M + 2)); CK(devAlloc(c.refKeys[1], M + 2)); CK(devAlloc(c.refColors, M + 2)); CK(devAlloc(c.colorKey, M + 2));
@@ -99,6 +99,7 @@ void freeAll(Context& c)
     for (int k = 0; k < 2; ++k) { if (c.evKeys[k]) cudaFree(c.evKeys[k]); if (c.evPairs[k]) cudaFree(c.evPairs[k]); if (c.evFlag[k]) cudaFree(c.evFlag[k]); if (c.evSlot[k]) cudaFree(c.evSlot[k]); }
     if (c.evBegin) cudaFree(c.evBegin); if (c.evEnd) cudaFree(c.evEnd);
     if (c.hmHeights) cudaFree(c.hmHeights); if (c.hmMips) cudaFree(c.hmMips);
+    if (c.bodyBaseJoints) cudaFree(c.bodyBaseJoints); delete[] c.jointPairsHost;
     if (c.interactions) cudaFree(c.interactions); if (c.forceFields) cudaFree(c.forceFields); delete c.prevTriggerOverlaps;
     for (uint32_t g = 0; g < kNumGroups; ++g) { if (c.unitColor[g]) cudaFree(c.unitColor[g]); if (c.unitOrder[g]) cudaFree(c.unitOrder[g]); if (c.unitDep[g]) cudaFree(c.unitDep[g]); }
     for (int k = 0; k < 6; ++k) { if (c.jointIn[k]) cudaFree(c.jointIn[k]); if (c.jointBodies[k]) cudaFree(c.jointBodies[k]); if (c.jointRows[k]) cudaFree(c.jointRows[k]); }
@@ -231,7 +232,7 @@ int b200phys_upload_bodies(b200phys_context* ctx, const b200phys_body* bodies, u
         CK(cudaMemcpyAsync(c.staging, bodies, sizeof(b200phys_body) * (size_t)count, cudaMemcpyHostToDevice, c.stream));
         launchUnpackBodies(&c, c.staging, count);
     }
-    c.numBodies = c.numOwnedBodies = count;
+    c.numBodies = c.numOwnedBodies = count; ++c.bodiesEpoch;
     CK(cudaGetLastError());
     return 0;
 }
@@ -306,6 +307,10 @@ int b200phys_upload_joints(b200phys_context* ctx, int kind, const void* joints, 
         CK(cudaMemcpyAsync(c.jointIn[kind], joints, inBytes[kind] * (size_t)count, cudaMemcpyHostToDevice, c.stream));
         CK(cudaMemcpyAsync(c.jointBodies[kind], pairs, sizeof(b200phys_body_pair) * (size_t)count, cudaMemcpyHostToDevice, c.stream));
     }
+    // topology change? (the host mirror re-uploads the structs every step for the motor targets; the pairs rarely change)
+    if (!c.jointPairsHost) c.jointPairsHost = new std::vector<b200phys_body_pair>[6];
+    std::vector<b200phys_body_pair>& prev = c.jointPairsHost[kind];
+    if (prev.size() != count || (count && memcmp(prev.data(), pairs, sizeof(b200phys_body_pair) * (size_t)count) != 0)) { prev.assign(pairs, pairs + count); ++c.jointsEpoch; }
     c.numJoints[kind] = count;
     return 0;
 }

@@ -396,7 +396,7 @@ int b200phys_migrate_pack(b200phys_context* ctx, int axis, float lo, float hi, v
     }
     CK(cudaStreamSynchronize(c.stream));
     CK(cudaGetLastError());
-    c.numBodies = c.numOwnedBodies = keptB; c.numColliders = c.numOwnedColliders = keptC;
+    c.numBodies = c.numOwnedBodies = keptB; c.numColliders = c.numOwnedColliders = keptC; ++c.bodiesEpoch;
     outCounts[0] = counts[0]; outCounts[1] = counts[1]; outCounts[2] = counts[2]; outCounts[3] = counts[3];
     return 0;
 }
