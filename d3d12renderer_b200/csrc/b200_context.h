@@ -179,6 +179,8 @@ struct Context
     uint32_t* adjStart = nullptr;           // N + 2
     uint32_t* adjFill = nullptr;
     uint32_t* adjList = nullptr;            // 2 * max units
+    uint32_t* adjPos = nullptr;             // 2 * max units: solve position of the unit behind each adjList entry (inherit mode)
+    uint2* unitSlots = nullptr;             // max units: the unit's slots in its two bodies' lists
     uint32_t* levelStart = nullptr;         // 7 x (kMaxLevels + 1): colour ranges per group
     uint32_t* levelFill = nullptr;          // 3 x (kMaxLevels + 1): per-round progress, colour histogram, scatter cursors
     uint32_t* slotOfContact = nullptr;      // solve slot -> canonical contact index

@@ -57,7 +57,7 @@ int allocateAll(Context& c)
         CK(devAlloc(c.unitColor[gI], units)); CK(devAlloc(c.unitOrder[gI], units)); CK(devAlloc(c.unitDep[gI], units));
     }
     CK(devAlloc(c.unitPending, (M > J ? M : J))); CK(devAlloc(c.nbrCount, (M > J ? M : J))); CK(devAlloc(c.nbrList, 16 * (M > J ? M : J))); CK(devAlloc(c.unitForbid, (M > J ? M : J)));
-    CK(devAlloc(c.adjStart, N1 + 2)); CK(devAlloc(c.adjFill, N1 + 2)); CK(devAlloc(c.adjList, 2 * (M > J ? M : J)));
+    CK(devAlloc(c.adjStart, N1 + 2)); CK(devAlloc(c.adjFill, N1 + 2)); CK(devAlloc(c.adjList, 2 * (M > J ? M : J))); CK(devAlloc(c.adjPos, 2 * (M > J ? M : J))); CK(devAlloc(c.unitSlots, (M > J ? M : J)));
     CK(devAlloc(c.levelStart, (size_t)kNumGroups * (kMaxLevels + 1))); CK(devAlloc(c.levelFill, (size_t)3 * (kMaxLevels + 1)));
     CK(devAlloc(c.slotOfContact, K)); CK(devAlloc(c.unitSlotStart, M + 2)); CK(devAlloc(c.unitInfo, M)); CK(devAlloc(c.rows, 8 * K)); CK(devAlloc(c.rowImp, K));
     static const size_t inBytes[6] = { sizeof(b200phys_distance_joint), sizeof(b200phys_ball_joint), sizeof(b200phys_fixed_joint),
@@ -93,7 +93,7 @@ void freeAll(Context& c)
     void* ptrs[] = { c.bRot, c.bPos, c.bCog, c.bInvI, c.bVel, c.bAng, c.bForce, c.bTorque, c.gVel, c.gPos, c.gInvI, c.bodyMask, c.bodyBase, c.refKeys[0], c.refKeys[1], c.refColors, c.colorKey, c.colorQueue, c.scanStatus, c.scanState, c.cLocal, c.xforms, c.wCol, c.aabbMin, c.aabbMax,
         c.hullVerts, c.hullOffsets, c.hullAabb, c.cellOf, c.rankInCell, c.cellCount, c.cellStart, c.bpRec, c.bpRows, c.bpBigChunks, c.bigList, c.pairCount, c.pairStart, c.pairs,
         c.pairKey, c.pairsTyped, c.pairDst, c.pairsSorted, c.manTmp, c.manScan, c.manScanOut, c.epaSimplex, c.epaWork, c.epaRedo, c.epaRedo2, c.collisions, c.manifolds, c.contacts, c.contactBodies,
-        c.unitPending, c.unitForbid, c.nbrCount, c.nbrList, c.adjStart, c.adjFill, c.adjList, c.levelStart, c.levelFill, c.slotOfContact, c.unitSlotStart, c.unitInfo, c.rows, c.rowImp, c.scanTmp, c.scanTmp64, c.sortHist, c.staging, c.counts, c.haloBuf };
+        c.unitPending, c.unitForbid, c.nbrCount, c.nbrList, c.adjStart, c.adjFill, c.adjList, c.adjPos, c.unitSlots, c.levelStart, c.levelFill, c.slotOfContact, c.unitSlotStart, c.unitInfo, c.rows, c.rowImp, c.scanTmp, c.scanTmp64, c.sortHist, c.staging, c.counts, c.haloBuf };
     for (void* p : ptrs) if (p) cudaFree(p);
     for (int k = 0; k < 6; ++k) if (c.refColorsJoint[k]) cudaFree(c.refColorsJoint[k]);
     for (int k = 0; k < 2; ++k) { if (c.evKeys[k]) cudaFree(c.evKeys[k]); if (c.evPairs[k]) cudaFree(c.evPairs[k]); if (c.evFlag[k]) cudaFree(c.evFlag[k]); if (c.evSlot[k]) cudaFree(c.evSlot[k]); }
