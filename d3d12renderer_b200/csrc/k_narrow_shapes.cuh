@@ -843,8 +843,8 @@ typedef EpaSm<16, 62, 64> EpaMedium;
 // Capacities follow the reference where it has a real bound (<= 128 border edges, collision_epa.cpp:141; 4 + 20 points) and are sized
 // for the observed maxima elsewhere (the reference's arrays hold 1024).
 #define B200_EPAW_MAX_POINTS 24
-#define B200_EPAW_MAX_TRIS 160
-#define B200_EPAW_MAX_EDGES 240
+#define B200_EPAW_MAX_TRIS 320
+#define B200_EPAW_MAX_EDGES 480
 #define B200_EPAW_MAX_BORDER 128
 struct EpaWarpShared
 {

@@ -383,7 +383,7 @@ def _full_size_properties(sc, steps, sample=1500, seed=0):
         for _ in range(steps):
             st.step(DT, 10, abi.STEP_FAST)
         s = st.stats()
-        assert s.overflowPairs == 0 and s.overflowManifolds == 0 and s.overflowGrid == 0 and s.epaOverflows <= 4
+        assert s.overflowPairs == 0 and s.overflowManifolds == 0 and s.overflowGrid == 0 and s.epaOverflows == 0
         pairs = st.download_pairs(); aabbs = st.download_aabbs(); contacts, cb = st.download_contacts(); bodies = st.download_bodies()
         results.append((pairs, contacts, bodies))
         if run == 0:
