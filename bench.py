@@ -143,7 +143,7 @@ def rooflines(kernels, counts, n_bodies, n_colliders, n_joints, peak):
     """Algorithmic bytes (SURVEY 8d model) / measured time for the kernel groups that move the data; -> {group: {...}}."""
     P, K = counts["pairs"], counts["contacts"]
     model = {
-        "broad_phase": (n_colliders * B_GRID + P * B_PAIR_OUT, ["bp_build", "bp_tiles", "bp_emit"]),
+        "broad_phase": (n_colliders * B_GRID + P * B_PAIR_OUT, ["bp_check", "bp_build", "bp_tiles", "bp_emit", "bp_filter"]),
         "narrow_phase": (P * B_PAIR_NARROW + K * B_CONTACT_OUT, ["np_classify_sort", "np_closed_form_sat", "np_gjk", "np_epa", "np_epa_redo", "np_compact"]),
         "solver_rows": (K * B_KINIT, ["solver_rows"]),
         "solve": (K * ITERATIONS * B_KITER + n_joints * ITERATIONS * B_JITER, ["solve"]),
@@ -189,7 +189,7 @@ def side_config(name, sc, peak, steps, warmup=5, iterations=ITERATIONS):
            "ms_per_step": ms / steps, "steps_per_s": steps / (ms * 1e-3), "body_steps_per_s": len(sc["bodies"]) * steps / (ms * 1e-3),
            "ms_per_step_exact_order": ms_exact / max(4, steps // 4), "kernel_ms": kernels, "launches_per_step": int(s.kernelLaunches),
            "roofline": {k: {"frac": v["frac"], "achieved_gbs": v["achieved"], "ms": v["ms"]} for k, v in rf.items() if k in ("broad_phase", "solve")},
-           "overflow": [int(s.overflowPairs), int(s.overflowManifolds), int(s.overflowGrid), int(s.epaOverflows)]}
+           "overflow": [int(s.overflowPairs), int(s.overflowManifolds), int(s.overflowGrid), int(s.epaOverflows)], "broadphase_reuse": st.broadphase_reuse()}
     st.close()
     return out
 
@@ -364,12 +364,13 @@ def main():
     ms_dev = max_over_ranks(time_steps(do_step, barrier, stream, 0, K))
     clock_info = clocks.stop() if rank == 0 else None
     stats = st.stats(check=False)
+    reuse = st.broadphase_reuse()              # over warm-up + timed steps: how many of them ran the grid pipeline (the others filtered the candidate list)
     launches_per_step = stats.kernelLaunches
     overflow = [int(stats.overflowPairs), int(stats.overflowManifolds), int(stats.overflowGrid)]
 
     if args.timed_only:
         if rank == 0:
-            print(json.dumps({"timed_only": True, "ms_per_step": ms_dev / K, "n_gpus": world, "steps": K, "warmup": W, "launches_per_step": int(launches_per_step), "overflow": overflow}))
+            print(json.dumps({"timed_only": True, "ms_per_step": ms_dev / K, "n_gpus": world, "steps": K, "warmup": W, "launches_per_step": int(launches_per_step), "overflow": overflow, "broadphase_reuse": reuse}))
         st.close()
         if world > 1:
             dist.destroy_process_group()
@@ -440,7 +441,7 @@ def main():
 
     if rank == 0:
         dom = max(kernels, key=lambda k: kernels[k])
-        group_of = {"bp_build": "broad_phase", "bp_tiles": "broad_phase", "bp_emit": "broad_phase", "np_classify_sort": "narrow_phase", "np_closed_form_sat": "narrow_phase", "np_gjk": "narrow_phase",
+        group_of = {"bp_check": "broad_phase", "bp_filter": "broad_phase", "bp_build": "broad_phase", "bp_tiles": "broad_phase", "bp_emit": "broad_phase", "np_classify_sort": "narrow_phase", "np_closed_form_sat": "narrow_phase", "np_gjk": "narrow_phase",
                     "np_epa": "narrow_phase", "np_epa_redo": "narrow_phase", "np_compact": "narrow_phase", "solver_rows": "solver_rows", "solver_order": "solver_rows", "solve": "solve"}
         # per-kernel algorithmic bytes for the dominant kernel group (same model, split by what that kernel touches)
         P, Kc = counts["pairs"], counts["contacts"]
@@ -458,7 +459,8 @@ def main():
                        "steps_per_s": K / (ms_dev * 1e-3), "ms_per_step_exact_order": ms_exact,
                        "parallelism": ("slab decomposition along x, %d slabs, ghost-body halo: ncclSend / ncclRecv inside the C library (%d ghost bodies on rank 0)" % (world, ghosts)) if world > 1 else "single GPU",
                        "l2_policy": "per-step working set (rows, pair and manifold scratch, body planes: > 1 GB) >> 126 MB L2; no explicit flush",
-                       "state_checksum_y": checksum, "overflow": overflow},
+                       "state_checksum_y": checksum, "overflow": overflow,
+                       "broadphase_reuse": dict(reuse, note="warm-up + timed steps; 'rebuilds' of them ran the grid pipeline, the others filtered the candidate list of grown AABBs (same pair list either way)")},
             "e2e": {"value": e2e_value, "unit": "body-steps/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(n_bodies * (abi.body_state_dtype.itemsize + 24)),
                     "d2h_bytes_per_step": int(n_bodies * abi.body_state_dtype.itemsize)},
             "gpu_launches": int(launches_per_step * K),

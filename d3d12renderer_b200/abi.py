@@ -95,7 +95,7 @@ EXPORTS = [
     "b200phys_cloth_apply_wind", "b200phys_cloth_simulate", "b200phys_cloth_download",
     "b200phys_host_alloc", "b200phys_host_free",
     "b200phys_set_hulls", "b200phys_upload_bodies", "b200phys_upload_transforms", "b200phys_upload_colliders", "b200phys_upload_joints",
-    "b200phys_upload_forces", "b200phys_upload_body_states", "b200phys_step", "b200phys_synchronize", "b200phys_download_bodies", "b200phys_get_stats",
+    "b200phys_upload_forces", "b200phys_upload_body_states", "b200phys_step", "b200phys_synchronize", "b200phys_download_bodies", "b200phys_get_stats", "b200phys_get_broadphase_reuse",
     "b200phys_download_aabbs", "b200phys_download_pairs", "b200phys_download_contacts", "b200phys_download_collisions",
     "b200phys_download_solve_order", "b200phys_get_timeline", "b200phys_dist_unique_id", "b200phys_create_distributed", "b200phys_step_distributed", "b200phys_dist_ghost_counts", "b200phys_halo_pack", "b200phys_halo_unpack", "b200phys_halo_clear", "b200phys_halo_record_bytes",
     "b200phys_halo_message_bytes", "b200phys_halo_pack_message", "b200phys_halo_unpack_message", "b200phys_migrate_pack", "b200phys_migrate_unpack", "b200phys_enable_events", "b200phys_download_events", "b200phys_upload_force_fields", "b200phys_set_global_force_field", "b200phys_download_trigger_events",
@@ -145,6 +145,7 @@ def load_library():
     lib.b200phys_synchronize.argtypes = [vp]
     lib.b200phys_download_bodies.argtypes = [vp, vp, u32]
     lib.b200phys_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    lib.b200phys_get_broadphase_reuse.argtypes = [vp, C.POINTER(u32)]
     lib.b200phys_get_timeline.argtypes = [vp, vp, u32, vp, u32, C.POINTER(u32)]
     lib.b200phys_dist_unique_id.argtypes = [vp]
     lib.b200phys_create_distributed.argtypes = [C.POINTER(Config), C.POINTER(DistConfig), vp, C.POINTER(vp)]
@@ -209,12 +210,14 @@ class Stepper:
     """Thin object wrapper over one b200phys_context (one per GPU / rank)."""
 
     def __init__(self, max_bodies, max_colliders, max_transforms=16, device=0, max_pairs=0, max_manifolds=0, max_contacts=0,
-                 max_joints=0, max_grid_cells=0, cell_size=0.0, big_factor=0.0, dist=None):
+                 max_joints=0, max_grid_cells=0, cell_size=0.0, big_factor=0.0, dist=None, bp_reuse=True):
         self.lib = load_library()
         cfg = Config()
         cfg.device = device; cfg.maxBodies = max_bodies; cfg.maxColliders = max_colliders; cfg.maxTransforms = max_transforms
         cfg.maxPairs = max_pairs; cfg.maxManifolds = max_manifolds; cfg.maxContacts = max_contacts; cfg.maxJointsPerKind = max_joints
         cfg.maxGridCells = max_grid_cells; cfg.cellSize = cell_size; cfg.bigFactor = big_factor
+        if not bp_reuse:
+            cfg.reserved[2] = 1          # the grid pipeline runs in every step (no candidate reuse)
         self.ctx = C.c_void_p()
         if dist is None:
             _check(self.lib, self.lib.b200phys_create(C.byref(cfg), C.byref(self.ctx)), "b200phys_create")
@@ -338,6 +341,14 @@ class Stepper:
         if check:
             _check(self.lib, code, "get_stats")
         return st
+
+    def broadphase_reuse(self):
+        """Candidate reuse of the broad phase: dict(steps, rebuilds, candidates, pairs, margin, age) (b200phys_get_broadphase_reuse)."""
+        out = (C.c_uint32 * 8)()
+        _check(self.lib, self.lib.b200phys_get_broadphase_reuse(self.ctx, out), "get_broadphase_reuse")
+        f = np.frombuffer(np.array(list(out), dtype=np.uint32).tobytes(), dtype=np.float32)
+        return dict(steps=int(out[0]), rebuilds=int(out[1]), candidates=int(out[2]), pairs=int(out[3]), margin=float(f[4]), age=int(out[5]),
+                    moved_per_step=float(f[6]), mean_extent=float(f[7]))
 
     def timeline(self):
         """[(kernel group name, ms)] of the last step (enable_timing(True) first)."""

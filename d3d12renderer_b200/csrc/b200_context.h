@@ -69,6 +69,20 @@ struct DeviceCounts
     uint32_t maxSmallExtentBits;        // float bits (non-negative floats order like uints)
     uint32_t centreMinBits[3], centreMaxBits[3]; // sortable-uint encoded floats
     GridParams grid;
+    // ---- candidate reuse across steps (k_broad.cu, "fattened boxes"): the grid pipeline runs on AABBs grown by a margin and leaves a CANDIDATE
+    // list; while every collider's true AABB stays inside its grown box the step's pair list is that list filtered by the exact predicate
+    uint32_t bpRebuild;                 // this step runs the grid pipeline (always 1 in contexts without reuse)
+    uint32_t bpEmitToCand;              // the pipeline of this step / the last build wrote the candidate list (margin > 0) rather than the pair list itself
+    uint32_t bpViolations;              // colliders found outside their grown box by this step's check
+    uint32_t bpExcessBits;              // sortable-uint float: largest distance by which a true AABB face lies outside (+) / inside (-) its grown box
+    uint32_t bpMarginBits;              // float bits: margin of the current list (0: the list is the exact pair list of its step, not reusable)
+    uint32_t bpAge;                     // steps since the list was built
+    uint32_t numCand, numCandWanted;    // candidate list size (clamped / as scanned)
+    uint32_t bpScanCells, bpScanColliders;   // sizes of this step's two scans (0 when the list is reused)
+    uint32_t bpRebuildCount, bpStepCount;    // statistics
+    uint32_t bpMarginOff;               // a candidate list outgrew its buffer: no margins any more until the colliders are uploaded again
+    float meanSmallExtent;              // mean AABB extent of the colliders that went into the grid at the last build
+    float bpMovedPerStep;               // how far a box face moved per step since the last build (largest over all colliders), as of the last check
 };
 
 template <typename T> struct DevBuf { T* p = nullptr; size_t n = 0; };
@@ -125,6 +139,10 @@ struct Context
     uint32_t* bpRows = nullptr;       // per cell-ordered collider: up to 32 partners with a larger index, ascending
     uint32_t* bpBigChunks = nullptr;  // pairs of big collider k inside collider chunk c: [k * numChunks + c]
     bool bpPrimed = false;            // the big / small threshold of the previous step is valid
+    // candidate reuse: grown boxes of the last build, the candidate list, and what the host knows about it
+    float4* bpInflMin = nullptr; float4* bpInflMax = nullptr; uint2* bpCand = nullptr; uint32_t maxCand = 0;
+    bool bpReuse = false;             // this context keeps a candidate list (B200PHYS_BP_REUSE=0 turns it off)
+    uint32_t bpListColliders = 0;     // collider count the list was built for (0: none)
     uint32_t* bigList = nullptr;
     uint32_t* pairCount = nullptr;    // per collider
     uint32_t* pairStart = nullptr;    // C + 1

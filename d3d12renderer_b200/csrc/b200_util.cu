@@ -131,15 +131,7 @@ static void scanExclusive(Context* c, const T* in, T* out, const uint32_t* devCo
 // in one 64-bit word, the epoch (a per-context launch counter) makes clearing the status array unnecessary; the last CTA to leave
 // resets the ticket counter for the next launch.
 static const int kLbThreads = 256, kLbItems = 8, kLbTile = kLbThreads * kLbItems;
-struct ScanLbState { unsigned int ticket, done, epoch, pad; };      // epoch lives on the device so that a replayed CUDA graph sees a fresh one
-
-// the epoch of this launch (1 .. 2^30-1): read before the CTA takes a ticket, advanced by the last CTA to leave (nobody of this launch
-// can read it afterwards)
-B200_D uint32_t scanEpochOf(const ScanLbState* state) { uint32_t e; asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(e) : "l"(&state->epoch) : "memory"); return e + 1u; }
-B200_D void scanLeave(ScanLbState* state, uint32_t epoch)
-{
-    if (atomicAdd(&state->done, 1u) == gridDim.x - 1) { state->ticket = 0; state->done = 0; state->epoch = (epoch >= 0x3FFFFFFEu) ? 0u : epoch; }     // last one out: ready for the next launch
-}
+// (ScanLbState, scanEpochOf, scanLeave: b200_util.cuh -- the broad phase's candidate filter runs the same look-back protocol)
 
 __global__ void __launch_bounds__(kLbThreads) scanLookbackKernel(uint32_t* __restrict__ in, uint32_t* __restrict__ out, const uint32_t* __restrict__ devCount, uint32_t hostCount,
                                                                  unsigned long long* __restrict__ status, ScanLbState* __restrict__ state, uint32_t* __restrict__ totalOut, bool clearInput)

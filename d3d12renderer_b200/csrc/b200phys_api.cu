@@ -47,6 +47,15 @@ int allocateAll(Context& c)
     CK(devAlloc(c.bpRec, 2 * C)); CK(devAlloc(c.bpRows, 32 * C)); CK(devAlloc(c.bpBigChunks, (size_t)kMaxBig * ((C + 2047) / 2048 + 1))); CK(devAlloc(c.bigList, kMaxBig));
     CK(cudaMemset(c.cellCount, 0, sizeof(uint32_t) * ((size_t)c.maxCells + 2)));      // the cell scan leaves the counts cleared for the next step
     CK(devAlloc(c.pairCount, C + 2)); CK(devAlloc(c.pairStart, C + 2)); CK(devAlloc(c.pairs, P));
+    {   // candidate reuse across steps (k_broad.cu): grown boxes + a candidate list half as large again as the pair list
+        const char* e = getenv("B200PHYS_BP_REUSE");
+        c.bpReuse = !(e && e[0] == '0') && g.reserved[2] != 1u;
+        if (c.bpReuse)
+        {
+            c.maxCand = (uint32_t)std::min<size_t>(P + P / 2, 0xFFFFFFF0u);
+            CK(devAlloc(c.bpInflMin, C)); CK(devAlloc(c.bpInflMax, C)); CK(devAlloc(c.bpCand, (size_t)c.maxCand + 2));
+        }
+    }
     CK(devAlloc(c.pairKey, P)); CK(devAlloc(c.pairsTyped, P)); CK(devAlloc(c.pairDst, P + 2)); CK(devAlloc(c.pairsSorted, P));
     CK(devAlloc(c.manTmp, 5 * P)); CK(devAlloc(c.manScan, P + 2)); CK(devAlloc(c.manScanOut, P + 2));
     c.maxEpaWork = (uint32_t)M; CK(devAlloc(c.epaSimplex, 9 * M)); CK(devAlloc(c.epaWork, M)); CK(devAlloc(c.epaRedo, M)); CK(devAlloc(c.epaRedo2, M));
@@ -78,6 +87,7 @@ int allocateAll(Context& c)
     { float* fs = nullptr; CK(devAlloc(fs, (size_t)g.maxBodies * 6 + 8)); c.forceStaging = fs; }
     CK(devAlloc(c.counts, 1));
     CK(cudaMemset(c.counts, 0, sizeof(DeviceCounts)));
+    { const uint32_t one = 1u; CK(cudaMemcpy(&c.counts->bpRebuild, &one, sizeof(one), cudaMemcpyHostToDevice)); }     // without candidate reuse the grid pipeline runs in every step
     CK(cudaHostAlloc((void**)&c.hostCounts, sizeof(DeviceCounts), cudaHostAllocDefault));
     memset(c.hostCounts, 0, sizeof(DeviceCounts));
     // the dummy body slot and all planes start zeroed
@@ -93,7 +103,7 @@ void freeAll(Context& c)
     void* ptrs[] = { c.bRot, c.bPos, c.bCog, c.bInvI, c.bVel, c.bAng, c.bForce, c.bTorque, c.gVel, c.gPos, c.gInvI, c.bodyMask, c.bodyBase, c.refKeys[0], c.refKeys[1], c.refColors, c.colorKey, c.colorQueue, c.scanStatus, c.scanState, c.cLocal, c.xforms, c.wCol, c.aabbMin, c.aabbMax,
         c.hullVerts, c.hullOffsets, c.hullAabb, c.cellOf, c.rankInCell, c.cellCount, c.cellStart, c.bpRec, c.bpRows, c.bpBigChunks, c.bigList, c.pairCount, c.pairStart, c.pairs,
         c.pairKey, c.pairsTyped, c.pairDst, c.pairsSorted, c.manTmp, c.manScan, c.manScanOut, c.epaSimplex, c.epaWork, c.epaRedo, c.epaRedo2, c.collisions, c.manifolds, c.contacts, c.contactBodies,
-        c.unitPending, c.unitForbid, c.nbrCount, c.nbrList, c.adjStart, c.adjFill, c.adjList, c.adjPos, c.unitSlots, c.levelStart, c.levelFill, c.slotOfContact, c.unitSlotStart, c.unitInfo, c.rows, c.rowImp, c.scanTmp, c.scanTmp64, c.sortHist, c.staging, c.counts, c.haloBuf };
+        c.unitPending, c.unitForbid, c.nbrCount, c.nbrList, c.adjStart, c.adjFill, c.adjList, c.adjPos, c.unitSlots, c.levelStart, c.levelFill, c.slotOfContact, c.unitSlotStart, c.unitInfo, c.rows, c.rowImp, c.scanTmp, c.scanTmp64, c.sortHist, c.staging, c.counts, c.haloBuf, c.bpInflMin, c.bpInflMax, c.bpCand };
     for (void* p : ptrs) if (p) cudaFree(p);
     for (int k = 0; k < 6; ++k) if (c.refColorsJoint[k]) cudaFree(c.refColorsJoint[k]);
     for (int k = 0; k < 2; ++k) { if (c.evKeys[k]) cudaFree(c.evKeys[k]); if (c.evPairs[k]) cudaFree(c.evPairs[k]); if (c.evFlag[k]) cudaFree(c.evFlag[k]); if (c.evSlot[k]) cudaFree(c.evSlot[k]); }
@@ -586,6 +596,17 @@ int b200phys_download_bodies(b200phys_context* ctx, b200phys_body_state* out, ui
     launchPackBodyStates(&c, c.staging, count);
     CK(cudaMemcpyAsync(out, c.staging, sizeof(b200phys_body_state) * (size_t)count, cudaMemcpyDeviceToHost, c.stream));
     CK(cudaStreamSynchronize(c.stream));
+    return 0;
+}
+
+int b200phys_get_broadphase_reuse(b200phys_context* ctx, uint32_t out[8])
+{
+    if (!ctx || !out) return B200PHYS_E_INVALID;
+    Context& c = ctx->c; CK(cudaSetDevice(c.device));
+    int r = fetchCounts(c); if (r) return r;
+    const DeviceCounts& d = *c.hostCounts;
+    out[0] = d.bpStepCount; out[1] = d.bpRebuildCount; out[2] = d.bpEmitToCand ? d.numCand : 0u; out[3] = d.numPairs; out[4] = c.bpReuse ? d.bpMarginBits : 0u; out[5] = d.bpAge;
+    memcpy(&out[6], &d.bpMovedPerStep, 4); memcpy(&out[7], &d.meanSmallExtent, 4);
     return 0;
 }
 

@@ -101,15 +101,24 @@ __global__ void bpPrimeFinishKernel(float bigFactor, float cfgCell, DeviceCounts
     for (int a = 0; a < 3; ++a) { cnt->centreMinBits[a] = 0xFFFFFFFFu; cnt->centreMaxBits[a] = 0u; }
 }
 
-__global__ void __launch_bounds__(kThreads) bpClassifyKernel(uint32_t C, const float4* __restrict__ mn, const float4* __restrict__ mx,
+// With candidate reuse (inflMin != nullptr) the pipeline works on boxes grown by the step's margin: they are produced here, stored for the
+// later stages (which only ever see the grown boxes) and for the containment checks of the following steps.
+__global__ void __launch_bounds__(kThreads) bpClassifyKernel(uint32_t C, const float4* __restrict__ mn, const float4* __restrict__ mx, float4* __restrict__ inflMin, float4* __restrict__ inflMax,
                                                              uint32_t* __restrict__ cellOf, uint32_t* __restrict__ bigList, DeviceCounts* cnt)
 {
+    if (!cnt->bpRebuild) return;
+    const float margin = inflMin ? __uint_as_float(cnt->bpMarginBits) : 0.f;
     const float threshold = cnt->grid.bigThreshold;
     uint32_t extBits = 0, lo[3] = { 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu }, hi[3] = { 0u, 0u, 0u };
     unsigned long long sumAll = 0, sumSmall = 0; uint32_t nAll = 0, nSmall = 0;
     for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < C; i += gridDim.x * kThreads)
     {
-        const float4 a = ldStream(mn + i), b = ldStream(mx + i);
+        float4 a = ldStream(mn + i), b = ldStream(mx + i);
+        if (inflMin)
+        {
+            if (!(a.x > b.x)) { a.x -= margin; a.y -= margin; a.z -= margin; b.x += margin; b.y += margin; b.z += margin; }
+            inflMin[i] = a; inflMax[i] = b;
+        }
         const float e = maxExtent(a, b);
         if (a.x > b.x) { cellOf[i] = 0xFFFFFFFFu; continue; }   // inverted box = halo padding slot: neither binned nor big
         if (e >= 0.f && e < 1e12f) { sumAll += (unsigned long long)((double)e * 65536.0); ++nAll; }
@@ -166,6 +175,7 @@ __global__ void __launch_bounds__(kThreads) bpClassifyKernel(uint32_t C, const f
 __global__ void bpSetupKernel(uint32_t maxCells, float bigFactor, float cfgCell, uint32_t cfgCellDiv, uint32_t tileCand, uint32_t tilesMode, DeviceCounts* cnt)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (!cnt->bpRebuild) return;        // the candidate list is reused: grid, statistics and threshold stay as the last build left them (bpDecideKernel did the per-step resets)
     GridParams g;
     const float E = __uint_as_float(cnt->maxSmallExtentBits);
     const float meanSmall = cnt->smallCount ? (float)((double)cnt->smallSumFixed / 65536.0 / (double)cnt->smallCount) : E;
@@ -236,6 +246,7 @@ __global__ void bpSetupKernel(uint32_t maxCells, float bigFactor, float cfgCell,
     const double mean = cnt->extentCount ? ((double)cnt->extentSumFixed / 65536.0 / (double)cnt->extentCount) : 1.0;
     g.bigThreshold = cfgCell > 0.f ? cfgCell : (float)(mean * (double)bigFactor);
     cnt->grid = g;
+    cnt->meanSmallExtent = meanSmall; cnt->bpScanCells = g.numCells;
     cnt->halfSmallExtent = 0.5f * E;
     cnt->numBigNow = min(cnt->numBig, kMaxBig);
     cnt->extentSumFixed = 0ull; cnt->extentCount = 0; cnt->smallSumFixed = 0ull; cnt->smallCount = 0; cnt->maxSmallExtentBits = 0; cnt->numBig = 0;
@@ -247,6 +258,7 @@ __global__ void bpSetupKernel(uint32_t maxCells, float bigFactor, float cfgCell,
 __global__ void __launch_bounds__(kThreads) bpBinKernel(uint32_t C, const float4* __restrict__ mn, const float4* __restrict__ mx,
                                                         uint32_t* __restrict__ cellOf, uint32_t* __restrict__ rankInCell, uint32_t* __restrict__ cellCount, const DeviceCounts* __restrict__ cnt)
 {
+    if (!cnt->bpRebuild) return;
     const GridParams g = cnt->grid;
     for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < C; i += gridDim.x * kThreads)
     {
@@ -264,8 +276,9 @@ __global__ void __launch_bounds__(kThreads) bpBinKernel(uint32_t C, const float4
 // cell-ordered records: rec[2 e] = (min.xyz, collider id), rec[2 e + 1] = (max.xyz, 0); slotOf[id] = e. Colliders outside the grid
 // (big, padding) get an empty row here; the big ones are counted by the tile kernel's extra CTAs.
 __global__ void __launch_bounds__(kThreads) bpScatterKernel(uint32_t C, const float4* __restrict__ mn, const float4* __restrict__ mx, const uint32_t* __restrict__ cellOf,
-                                                            uint32_t* __restrict__ rankToSlot, const uint32_t* __restrict__ cellStart, float4* __restrict__ rec, uint32_t* __restrict__ pairCount)
+                                                            uint32_t* __restrict__ rankToSlot, const uint32_t* __restrict__ cellStart, float4* __restrict__ rec, uint32_t* __restrict__ pairCount, const DeviceCounts* __restrict__ cnt)
 {
+    if (!cnt->bpRebuild) return;
     for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < C; i += gridDim.x * kThreads)
     {
         const uint32_t cell = cellOf[i];
@@ -357,6 +370,7 @@ __global__ void __launch_bounds__(kTileThreads) bpTileKernel(uint32_t C, uint32_
 {
     extern __shared__ __align__(128) unsigned char tileSmem[];
     TileCtaShared& CS = *reinterpret_cast<TileCtaShared*>(tileSmem);
+    if (!cnt->bpRebuild) return;
     const GridParams g = cnt->grid;
     const uint32_t numBig = cnt->numBigNow;
     const uint32_t tid = threadIdx.x;
@@ -557,7 +571,7 @@ __global__ void __launch_bounds__(kDirectThreads) bpRowsDirectKernel(uint32_t C,
     __shared__ uint32_t sPart[kDirectThreads * kPartStride];
     __shared__ float4 sBigMin[kBigStage], sBigMax[kBigStage]; __shared__ uint32_t sBigId[kBigStage];
     const GridParams g = cnt->grid;
-    if (g.useTiles) return;
+    if (g.useTiles || !cnt->bpRebuild) return;
     const uint32_t numBig = cnt->numBigNow, nBigS = min(numBig, kBigStage);
     const float halfE = cnt->halfSmallExtent;
     if (threadIdx.x < nBigS) { const uint32_t b = bigList[threadIdx.x]; sBigId[threadIdx.x] = b; sBigMin[threadIdx.x] = aabbMin[b]; sBigMax[threadIdx.x] = aabbMax[b]; }
@@ -612,15 +626,28 @@ __global__ void __launch_bounds__(kDirectThreads) bpRowsDirectKernel(uint32_t C,
 __global__ void __launch_bounds__(kThreads) bpEmitKernel(uint32_t C, uint32_t emitCtas, uint32_t numChunks, const uint32_t* __restrict__ slotOf, const uint32_t* __restrict__ rows,
     const uint32_t* __restrict__ pairCount, const uint32_t* __restrict__ pairStart, const float4* __restrict__ rec, const uint32_t* __restrict__ cellStart,
     const float4* __restrict__ aabbMin, const float4* __restrict__ aabbMax, const uint32_t* __restrict__ bigList, const uint32_t* __restrict__ ovList,
-    const uint32_t* __restrict__ bigChunkCount, uint2* __restrict__ pairs, uint32_t maxPairs, DeviceCounts* cnt)
+    const uint32_t* __restrict__ bigChunkCount, uint2* __restrict__ pairList, uint32_t maxPairList, uint2* __restrict__ candList, uint32_t maxCandList, DeviceCounts* cnt)
 {
+    if (!cnt->bpRebuild) return;
     const GridParams g = cnt->grid;
     const uint32_t numBig = cnt->numBigNow;
+    // with a margin the rows hold CANDIDATES (pairs of grown boxes): they go to the candidate list and bpFilterKernel derives the step's pairs
+    const bool toCand = cnt->bpEmitToCand != 0u;
+    uint2* __restrict__ pairs = toCand ? candList : pairList;
+    const uint32_t maxPairs = toCand ? maxCandList : maxPairList;
     if (blockIdx.x == 0 && threadIdx.x == 0)
     {
         const uint32_t total = pairStart[C];
-        cnt->numPairsWanted = total; cnt->numPairs = min(total, maxPairs);
-        if (total > maxPairs) cnt->overflowPairs = 1;
+        if (toCand)
+        {
+            cnt->numCandWanted = total; cnt->numCand = min(total, maxPairs);
+            if (total > maxPairs) { cnt->overflowPairs = 1; cnt->bpMarginOff = 1; }    // candidates lost: reported like a pair overflow; no margins from now on
+        }
+        else
+        {
+            cnt->numPairsWanted = total; cnt->numPairs = min(total, maxPairs);
+            if (total > maxPairs) cnt->overflowPairs = 1;
+        }
     }
     if (blockIdx.x < emitCtas)
     {
@@ -717,6 +744,177 @@ __global__ void __launch_bounds__(kThreads) bpEmitKernel(uint32_t C, uint32_t em
     }
 }
 
+// ------------------------------------------------------------------------------------------- candidate reuse
+// The pair set is a function of the collider indices and their world AABBs only. The grid pipeline above therefore may run on boxes grown
+// by a margin m and leave a CANDIDATE list (canonical order, like the pair list); as long as every collider's true AABB lies inside its
+// grown box, every overlapping pair of true boxes is a pair of overlapping grown boxes, i.e. a candidate, and the step's pair list is the
+// candidate list filtered -- in order -- by the reference's predicate on the true boxes: the SAME list the pipeline would have produced,
+// bit for bit (tests compare it with the oracle's sweep in every step). In a settled pile the list survives hundreds of steps; a falling
+// or thrown scene rebuilds every step with margin 0 and pays one extra pass over the AABBs.
+//   check  : every collider: is the true box inside the grown one? (+ how far the faces have moved: the policy's input)
+//   decide : one thread: rebuild or reuse, the margin of a new list, the sizes of this step's scans, the per-step counter resets
+//   filter : candidates -> pairs, single pass (decoupled look-back over 2048-candidate tiles), stable
+// margin policy (bpDecideKernel): a new list gets the margin that lets it live about kTargetLife steps at the speed the box faces moved since the
+// last build, between kMinMarginFraction and maxFraction of the mean small extent; no margin (exact build, no filter pass) when even the largest
+// margin would not survive kMinReuseSteps steps
+static const float kMaxMarginFraction = 0.06f, kMinMarginFraction = 0.02f;
+static const float kTargetLife = 6.f, kMinReuseSteps = 2.5f;
+
+__global__ void __launch_bounds__(kThreads) bpCheckKernel(uint32_t force, uint32_t C, const float4* __restrict__ mn, const float4* __restrict__ mx,
+                                                          const float4* __restrict__ inflMin, const float4* __restrict__ inflMax, DeviceCounts* cnt)
+{
+    if (force) return;
+    uint32_t viol = 0; float exc = -3.0e38f;
+    for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < C; i += gridDim.x * kThreads)
+    {
+        const float4 a = ldStream(mn + i), b = ldStream(mx + i);
+        if (a.x > b.x) continue;                                  // padding slot now: takes part in no pair
+        const float4 p = ldStream(inflMin + i), q = ldStream(inflMax + i);
+        if (p.x > q.x) { ++viol; continue; }                      // was a padding slot when the list was built
+        const bool inside = a.x >= p.x && a.y >= p.y && a.z >= p.z && b.x <= q.x && b.y <= q.y && b.z <= q.z;      // (false for NaN)
+        if (!inside) ++viol;
+        exc = fmaxf(exc, fmaxf(fmaxf(p.x - a.x, fmaxf(p.y - a.y, p.z - a.z)), fmaxf(b.x - q.x, fmaxf(b.y - q.y, b.z - q.z))));
+    }
+    viol = __reduce_add_sync(0xffffffffu, viol);
+    uint32_t excBits = __reduce_max_sync(0xffffffffu, floatToSortable(exc));
+    __shared__ uint32_t sV[kThreads / 32], sE[kThreads / 32];
+    if (laneId() == 0) { sV[threadIdx.x >> 5] = viol; sE[threadIdx.x >> 5] = excBits; }
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        for (int w = 1; w < kThreads / 32; ++w) { viol += sV[w]; excBits = max(excBits, sE[w]); }
+        if (viol) atomicAdd(&cnt->bpViolations, viol);
+        atomicMax(&cnt->bpExcessBits, excBits);
+    }
+}
+
+__global__ void bpDecideKernel(uint32_t force, uint32_t C, uint32_t maxCand, float maxFraction, float targetLife, DeviceCounts* cnt)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const float lastMargin = __uint_as_float(cnt->bpMarginBits);
+    if (force) cnt->bpMarginOff = 0;
+    // a list built without margin was written straight into the pair list of its step: nothing to reuse
+    const bool rebuild = force || cnt->bpViolations != 0u || !(lastMargin > 0.f) || !cnt->bpEmitToCand;
+    // how far did the box faces move per step since the last build? (the check's excess is relative to the grown box)
+    const float moved = force ? 0.f : fmaxf(sortableToFloat(cnt->bpExcessBits) + fmaxf(lastMargin, 0.f), 0.f);
+    const float perStep = moved / (float)max(cnt->bpAge, 1u);
+    if (!force) cnt->bpMovedPerStep = perStep;
+    if (rebuild)
+    {
+        float margin = 0.f;
+        if (!force && !cnt->bpMarginOff)
+        {
+            const float ext = cnt->meanSmallExtent;
+            const float mMax = maxFraction * ext, mMin = kMinMarginFraction * ext;
+            // room for the extra candidates? (the last step's exact count is the yardstick)
+            const bool room = (double)cnt->numPairsWanted * 1.4 < (double)maxCand;
+            if (mMax > 0.f && mMax < 1e30f && perStep * kMinReuseSteps <= mMax && room) margin = fminf(fmaxf(perStep * targetLife, mMin), mMax);
+        }
+        cnt->bpMarginBits = __float_as_uint(margin);
+        cnt->bpEmitToCand = margin > 0.f ? 1u : 0u;
+        cnt->bpAge = 0; ++cnt->bpRebuildCount;
+        cnt->bpScanColliders = C;          // (bpScanCells: bpSetupKernel, once the grid is known)
+    }
+    else { cnt->bpScanCells = 0; cnt->bpScanColliders = 0; }
+    cnt->bpRebuild = rebuild ? 1u : 0u;
+    ++cnt->bpAge; ++cnt->bpStepCount;
+    cnt->bpViolations = 0; cnt->bpExcessBits = 0;
+    // per-step resets (bpSetupKernel does them when it runs; it does not on a reuse step)
+    cnt->numPairs = 0; cnt->numPairsWanted = 0; cnt->numEpaWork = 0; cnt->epaWorkHead = 0; cnt->numEpaRedo = 0; cnt->epaRedoHead = 0; cnt->numEpaRedo2 = 0; cnt->epaRedo2Head = 0;
+    for (int i = 0; i < 11; ++i) cnt->gjkCursor[i] = 0; cnt->numOverflowRows = 0;
+}
+
+// candidates -> pairs. A tile is 2048 consecutive candidates; warp w takes 256 of them in four coalesced 512-byte loads (lane l: candidates
+// 2 l and 2 l + 1 of each 64), tests them against the true AABBs (the first collider repeats along the list: broadcast loads; the second is a
+// gather into the L2-resident AABB planes), ranks the survivors with two ballots per load and writes them at the tile's offset, which comes
+// from the look-back chain. Order is preserved, so the output is the canonical pair list.
+static const int kFilterThreads = 256;
+static const uint32_t kFilterTile = 2048;
+B200_D bool trueBoxesOverlap(uint32_t ia, uint32_t ib, const float4* __restrict__ mn, const float4* __restrict__ mx)
+{
+    const float4 amn = mn[ia], amx = mx[ia], bmn = mn[ib], bmx = mx[ib];
+    if (amn.x > amx.x || bmn.x > bmx.x) return false;            // padding slots are in no pair (bpClassifyKernel never bins them)
+    return overlapInclusive(amn, amx, bmn, bmx);
+}
+__global__ void __launch_bounds__(kFilterThreads) bpFilterKernel(const uint2* __restrict__ cand, const float4* __restrict__ mn, const float4* __restrict__ mx,
+    uint2* __restrict__ pairs, uint32_t maxPairs, unsigned long long* __restrict__ status, ScanLbState* __restrict__ state, DeviceCounts* cnt)
+{
+    if (cnt->bpRebuild && !cnt->bpEmitToCand) return;          // this step's pipeline wrote the pair list itself (margin 0)
+    const uint32_t epoch = scanEpochOf(state);
+    __shared__ uint32_t warpSums[kFilterThreads / 32];
+    __shared__ uint32_t sTile, sPrefix, sTileTotal;
+    const uint32_t n = cnt->numCand;
+    const uint32_t numTiles = (n + kFilterTile - 1) / kFilterTile;
+    const uint32_t lane = laneId(), warp = threadIdx.x >> 5, lt = laneMaskLt();
+    for (;;)
+    {
+        if (threadIdx.x == 0) sTile = atomicAdd(&state->ticket, 1u);
+        __syncthreads();
+        const uint32_t tile = sTile;
+        if (tile >= numTiles) break;
+        const uint32_t warpBase = tile * kFilterTile + warp * 256u;
+        uint4 c4[4]; uint32_t rank[4], keep[4], warpTotal = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+        {
+            const uint32_t idx = warpBase + (uint32_t)j * 64u + 2u * lane;
+            c4[j] = make_uint4(0, 0, 0, 0);
+            if (idx + 1u < n) c4[j] = *reinterpret_cast<const uint4*>(cand + idx);
+            else if (idx < n) { const uint2 t = cand[idx]; c4[j].x = t.x; c4[j].y = t.y; }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+        {
+            const uint32_t idx = warpBase + (uint32_t)j * 64u + 2u * lane;
+            const bool k0 = idx < n && trueBoxesOverlap(c4[j].x, c4[j].y, mn, mx);
+            const bool k1 = idx + 1u < n && trueBoxesOverlap(c4[j].z, c4[j].w, mn, mx);
+            const uint32_t b0 = __ballot_sync(0xffffffffu, k0), b1 = __ballot_sync(0xffffffffu, k1);
+            rank[j] = warpTotal + (uint32_t)__popc(b0 & lt) + (uint32_t)__popc(b1 & lt);       // of this lane's first candidate inside the warp's 256
+            keep[j] = (k0 ? 1u : 0u) | (k1 ? 2u : 0u);
+            warpTotal += (uint32_t)__popc(b0) + (uint32_t)__popc(b1);
+        }
+        if (lane == 0) warpSums[warp] = warpTotal;
+        __syncthreads();
+        if (threadIdx.x < 32)
+        {
+            const uint32_t w = (threadIdx.x < kFilterThreads / 32) ? warpSums[threadIdx.x] : 0u;
+            uint32_t wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= (uint32_t)o) wi += t; }
+            if (threadIdx.x < kFilterThreads / 32) warpSums[threadIdx.x] = wi - w;
+            const uint32_t total = __shfl_sync(0xffffffffu, wi, kFilterThreads / 32 - 1);
+            const uint32_t prefix = scanLookbackPrefix(status, tile, total, epoch);
+            if (threadIdx.x == 0)
+            {
+                sPrefix = prefix; sTileTotal = total;
+                if (tile == numTiles - 1)
+                {
+                    const uint32_t all = prefix + total;
+                    // a truncated candidate list may have lost pairs: what it wanted bounds what the pair list can want
+                    const uint32_t wanted = cnt->numCandWanted > cnt->numCand ? max(all, cnt->numCandWanted) : all;
+                    cnt->numPairsWanted = wanted; cnt->numPairs = min(all, maxPairs);
+                    if (wanted > maxPairs) cnt->overflowPairs = 1;
+                }
+            }
+        }
+        __syncthreads();
+        const uint32_t base = sPrefix + warpSums[warp];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+        {
+            uint32_t pos = base + rank[j];
+            if (keep[j] & 1u) { if (pos < maxPairs) pairs[pos] = make_uint2(c4[j].x, c4[j].y); ++pos; }
+            if (keep[j] & 2u) { if (pos < maxPairs) pairs[pos] = make_uint2(c4[j].z, c4[j].w); }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0)
+    {
+        if (n == 0 && blockIdx.x == 0) { cnt->numPairsWanted = cnt->numCandWanted > cnt->numCand ? cnt->numCandWanted : 0u; cnt->numPairs = 0; }
+        scanLeave(state, epoch);
+    }
+}
+
 void launchBroadphase(Context* c)
 {
     const uint32_t C = c->numColliders;
@@ -730,13 +928,24 @@ void launchBroadphase(Context* c)
     static int tilesEnv = -1;
     if (tilesEnv < 0) { const char* e = getenv("B200PHYS_BP_TILES"); tilesEnv = e ? (atoi(e) ? 1 : 2) : 0; }    // tuning override: 1 always staged tiles, 0 never
     const uint32_t tilesMode = (uint32_t)tilesEnv;
+    const bool reuse = c->bpReuse;
+    static float maxFraction = -1.f, targetLife = -1.f;
+    if (maxFraction < 0.f)
+    {   // tuning overrides
+        const char* e = getenv("B200PHYS_BP_MARGIN"); maxFraction = e ? (float)atof(e) : kMaxMarginFraction;
+        const char* l = getenv("B200PHYS_BP_LIFE"); targetLife = l ? (float)atof(l) : kTargetLife;
+    }
     if (C == 0)
     {
+        if (reuse) { launchK(c, bpDecideKernel, 1, 32, 0, 1u, 0u, c->maxCand, maxFraction, targetLife, cnt); c->launches++; c->bpListColliders = 0; }
         launchK(c, bpPrimeFinishKernel, 1, 32, 0, bigFactor, c->cfg.cellSize, cnt);
         launchK(c, bpSetupKernel, 1, 32, 0, c->maxCells, bigFactor, c->cfg.cellSize, cellDiv, kWarpCand, tilesMode, cnt);
         c->launches += 2; c->bpPrimed = false;
         return;
     }
+    // candidate reuse: a list exists for exactly this collider count and no upload happened since -> the device decides (check + decide);
+    // otherwise this step builds (force)
+    const uint32_t force = (!c->bpPrimed || c->bpListColliders != C) ? 1u : 0u;
     if (!c->bpPrimed)
     {   // no threshold from a previous step yet (first step, or colliders were uploaded)
         launchK(c, bpPrimeFinishKernel, 1, 32, 0, bigFactor, c->cfg.cellSize, cnt);       // clears the accumulators
@@ -744,27 +953,43 @@ void launchBroadphase(Context* c)
         launchK(c, bpPrimeFinishKernel, 1, 32, 0, bigFactor, c->cfg.cellSize, cnt);
         c->launches += 3; c->bpPrimed = true;
     }
-    launchK(c, bpClassifyKernel, G, kThreads, 0, C, c->aabbMin, c->aabbMax, c->cellOf, c->bigList, cnt);
+    // the pipeline's view of the boxes: grown copies with reuse, the world AABBs themselves without
+    const float4* boxMin = reuse ? c->bpInflMin : c->aabbMin; const float4* boxMax = reuse ? c->bpInflMax : c->aabbMax;
+    if (reuse)
+    {
+        launchK(c, bpCheckKernel, G, kThreads, 0, force, C, c->aabbMin, c->aabbMax, c->bpInflMin, c->bpInflMax, cnt);
+        launchK(c, bpDecideKernel, 1, 32, 0, force, C, c->maxCand, maxFraction, targetLife, cnt);
+        c->launches += 2; c->bpListColliders = C;
+        timelineMark(c, "bp_check");
+    }
+    launchK(c, bpClassifyKernel, G, kThreads, 0, C, c->aabbMin, c->aabbMax, reuse ? c->bpInflMin : (float4*)nullptr, reuse ? c->bpInflMax : (float4*)nullptr, c->cellOf, c->bigList, cnt);
     launchK(c, bpSetupKernel, 1, 32, 0, c->maxCells, bigFactor, c->cfg.cellSize, cellDiv, kWarpCand, tilesMode, cnt);
-    launchK(c, bpBinKernel, G, kThreads, 0, C, c->aabbMin, c->aabbMax, c->cellOf, c->rankInCell, c->cellCount, cnt);
+    launchK(c, bpBinKernel, G, kThreads, 0, C, boxMin, boxMax, c->cellOf, c->rankInCell, c->cellCount, cnt);
     c->launches += 3;
-    scanExclusiveU32(c, c->cellCount, c->cellStart, &cnt->grid.numCells, c->maxCells, nullptr, /*clearInput*/ true);
-    launchK(c, bpScatterKernel, G, kThreads, 0, C, c->aabbMin, c->aabbMax, c->cellOf, c->rankInCell, c->cellStart, c->bpRec, c->pairCount);
+    scanExclusiveU32(c, c->cellCount, c->cellStart, reuse ? &cnt->bpScanCells : &cnt->grid.numCells, c->maxCells, nullptr, /*clearInput*/ true);
+    launchK(c, bpScatterKernel, G, kThreads, 0, C, boxMin, boxMax, c->cellOf, c->rankInCell, c->cellStart, c->bpRec, c->pairCount, cnt);
     timelineMark(c, "bp_build");
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(bpTileKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileCtaShared)); attr = true; }
     const uint32_t tileCtas = (uint32_t)c->numSMs * 4u, bigCtas = (uint32_t)c->numSMs;
-    launchK(c, bpTileKernel, tileCtas + bigCtas, kTileThreads, sizeof(TileCtaShared), C, tileCtas, numChunks, c->bpRec, c->cellStart, c->aabbMin, c->aabbMax, c->bigList,
+    launchK(c, bpTileKernel, tileCtas + bigCtas, kTileThreads, sizeof(TileCtaShared), C, tileCtas, numChunks, c->bpRec, c->cellStart, boxMin, boxMax, c->bigList,
                                                                                       c->pairCount, c->bpRows, c->cellOf, c->bpBigChunks, cnt);
-    launchK(c, bpRowsDirectKernel, gridFor(c, 6), kDirectThreads, 0, C, c->bpRec, c->cellStart, c->aabbMin, c->aabbMax, c->bigList, c->pairCount, c->bpRows, c->cellOf, cnt);
+    launchK(c, bpRowsDirectKernel, gridFor(c, 6), kDirectThreads, 0, C, c->bpRec, c->cellStart, boxMin, boxMax, c->bigList, c->pairCount, c->bpRows, c->cellOf, cnt);
     c->launches += 3;
     timelineMark(c, "bp_tiles");
-    scanExclusiveU32(c, c->pairCount, c->pairStart, nullptr, C, nullptr);
+    scanExclusiveU32(c, c->pairCount, c->pairStart, reuse ? &cnt->bpScanColliders : (const uint32_t*)nullptr, C, nullptr);
     const uint32_t emitCtas = (uint32_t)c->numSMs * 6u, extraCtas = (uint32_t)c->numSMs * 2u;
     launchK(c, bpEmitKernel, emitCtas + extraCtas, kThreads, 0, C, emitCtas, numChunks, c->rankInCell, c->bpRows, c->pairCount, c->pairStart, c->bpRec, c->cellStart,
-                                                                  c->aabbMin, c->aabbMax, c->bigList, c->cellOf, c->bpBigChunks, c->pairs, c->maxPairs, cnt);
+                                                                  boxMin, boxMax, c->bigList, c->cellOf, c->bpBigChunks, c->pairs, c->maxPairs, c->bpCand, c->maxCand, cnt);
     c->launches += 1;
     timelineMark(c, "bp_emit");
+    if (reuse)
+    {
+        int blocks = gridFor(c, 4);
+        launchK(c, bpFilterKernel, blocks, kFilterThreads, 0, c->bpCand, c->aabbMin, c->aabbMax, c->pairs, c->maxPairs, c->scanStatus, (ScanLbState*)c->scanState, cnt);
+        c->launches += 1;
+        timelineMark(c, "bp_filter");
+    }
 }
 
 } // namespace b200

@@ -315,12 +315,12 @@ __global__ void __launch_bounds__(128) npEpaKernel(const uint2* __restrict__ sor
     flushCounters(nc, cnt);
 }
 
-// phase 2, small polytope in shared memory (k_narrow_shapes.cuh, EpaSmall): thread per pair, 6 warps per SM. Runs take 0..20
+// phase 2, small polytope in shared memory (k_narrow_shapes.cuh, EpaSmall): thread per pair, 7 warps per SM. Runs take 0..20
 // expansions (most 1-4), so like the GJK kernel the loop performs ONE expansion per pass for every lane and a finished lane takes the
 // next work list entry at once. The few pairs that outgrow the small polytope go to the redo list (large polytope kernels).
-// POLY = EpaSmall (6 warps per SM, every parked pair) or EpaMedium (3 warps, the entries of `inList` = what the small one handed back);
+// POLY = EpaSmall (7 warps per SM, every parked pair) or EpaMedium (3 warps, the entries of `inList` = what the small one handed back);
 // entries that outgrow POLY are appended to outList.
-static const int kEpaSmallWarps = 6, kEpaMediumWarps = 3;
+static const int kEpaSmallWarps = 7, kEpaMediumWarps = 3;      // 7 x 242 words x 128 B = 212 KB of the 227 KB a CTA may have
 template <class POLY, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 1) npEpaSmKernel(const uint2* __restrict__ sorted, const float4* __restrict__ wCol, const float4* __restrict__ hullVerts,
     const uint32_t* __restrict__ hullOffsets, float4* __restrict__ manTmp, unsigned long long* __restrict__ manScan, uint32_t maxPairs,
@@ -374,7 +374,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) npEpaSmKernel(const uint2* __re
             else
             {
                 __syncwarp(evalMask);
-                const uint32_t k = POLY::kTri + 6 * ci;
+                const uint32_t k = POLY::triAt(ci);
                 const f3 tn = mk3(P.ldf(k), P.ldf(k + 1), P.ldf(k + 2));
                 const SupPt a = minkowski(job.A, job.B, tn);
                 if (dot(a.m, tn) - P.ldf(k + 3) < 0.01f) state = 2;

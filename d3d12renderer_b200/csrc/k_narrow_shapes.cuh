@@ -681,21 +681,26 @@ B200_D void epa(const SimplexD& g, const SupportD& A, const SupportD& B, f3& out
 // memory column (word k of lane l at [k * 32 + l]: whatever triangle a lane indexes, it stays in its own bank) instead of 7.7 KB of
 // thread-local memory that 1024 resident threads per SM turn into DRAM traffic. Measured on the settled mixed pile (oracle
 // histogram, tests/epa_histogram.py): 98.6 % of all EPA runs end with <= 10 points and <= 30 triangles (edges = triangles + 2), so the
-// column holds exactly that much (272 words = 1088 B per pair, 6 warps per SM); a run that needs more is abandoned and re-run from
+// column holds exactly that much (242 words = 968 B per pair, 7 warps per SM); a run that needs more is abandoned and re-run from
 // its simplex by the large-capacity kernel, which gives the same result because the expansion is deterministic.
 // Indices are bytes (0xFF stands for the 0xFFFF a degenerate horizon leaves behind), the activity flags one register, the per-edge
 // reference counts of collision_epa.cpp:114-139 two register bit masks (seen once / seen more often).
-// Two sizes are instantiated (k_narrow.cu): <10, 30, 32> for everybody (272 words, 6 warps per SM, masks in 32-bit registers) and
+// Two sizes are instantiated (k_narrow.cu): <10, 30, 32> for everybody (242 words, 7 warps per SM, masks in 32-bit registers) and
 // <16, 62, 64> for the runs that outgrow it (532 words, 3 warps per SM, 64-bit masks); what outgrows that too goes to the warp-cooperative kernel.
 template <uint32_t MAXP, uint32_t MAXT, uint32_t MAXE>
 struct EpaSm
 {
     static_assert(MAXT <= 64 && MAXE <= 64 && MAXP <= 16 && MAXE < 127, "masks are one machine word, indices bytes");
     typedef typename std::conditional<(MAXT > 32 || MAXE > 32), unsigned long long, uint32_t>::type Mask;
-    static constexpr uint32_t kWords = MAXP * 6 + MAXT * 6 + MAXE;
+    // a triangle is normal.xyz, distance and its three point + three edge indices: with <= 16 points and <= 32 edges the six indices fit ONE word
+    // (4 bits per point, 6 bits per edge, 63 = none), which makes the small polytope 242 words per pair instead of 272: 7 warps per SM instead of 6
+    static constexpr bool kPacked = MAXP <= 16 && MAXE <= 32;
+    static constexpr uint32_t kTriW = kPacked ? 5u : 6u;
+    static constexpr uint32_t kWords = MAXP * 6 + MAXT * kTriW + MAXE;
     uint32_t* w;             // this lane's column
     Mask active; uint32_t nT, nP, nE;
-    static constexpr uint32_t kTri = MAXP * 6, kEdge = kTri + MAXT * 6;
+    static constexpr uint32_t kTri = MAXP * 6, kEdge = kTri + MAXT * kTriW;
+    B200_D static uint32_t triAt(uint32_t i) { return kTri + kTriW * i; }
     B200_D static uint32_t lowest(Mask m) { return sizeof(Mask) == 8 ? (uint32_t)__ffsll((long long)m) - 1u : (uint32_t)__ffs((int)(uint32_t)m) - 1u; }
     B200_D static Mask bit(uint32_t i) { return (Mask)1 << i; }
     B200_D float ldf(uint32_t k) const { return __uint_as_float(w[k << 5]); }
@@ -704,6 +709,23 @@ struct EpaSm
     B200_D void stu(uint32_t k, uint32_t v) { w[k << 5] = v; }
     B200_D static uint32_t wide(uint32_t b) { return b == 0xFFu ? 0xFFFFu : b; }           // byte -> the reference's uint16 index
     B200_D bool isActive(uint32_t i) const { return i < nT && ((active >> i) & (Mask)1); }
+    // point indices as bytes a | b << 8 | c << 16; edge indices as bytes eA | eB << 8 | eC << 16 (anything >= nE: none)
+    B200_D uint32_t triIdx(uint32_t i) const
+    {
+        const uint32_t v = ldu(triAt(i) + 4);
+        return kPacked ? ((v & 0xFu) | ((v & 0xF0u) << 4) | ((v & 0xF00u) << 8)) : v;
+    }
+    B200_D uint32_t triEdges(uint32_t i) const
+    {
+        if (!kPacked) return ldu(triAt(i) + 5);
+        const uint32_t v = ldu(triAt(i) + 4) >> 12;
+        return (v & 63u) | ((v & (63u << 6)) << 2) | ((v & (63u << 12)) << 4);
+    }
+    B200_D void setTriEdgeB(uint32_t i, uint32_t e)
+    {
+        if (kPacked) { const uint32_t k = triAt(i) + 4; stu(k, (ldu(k) & ~(63u << 18)) | ((e & 63u) << 18)); }
+        else { const uint32_t k = triAt(i) + 5; stu(k, (ldu(k) & 0xFFFF00FFu) | (e << 8)); }
+    }
     B200_D SupPt pt(uint32_t i) const
     {
         SupPt p; const uint32_t k = 6 * i;
@@ -720,8 +742,10 @@ struct EpaSm
     B200_D bool pushTri(uint32_t a, uint32_t b, uint32_t c, uint32_t eA, uint32_t eB, uint32_t eC, f3 n, float d)
     {
         if (nT >= MAXT) return false;
-        const uint32_t k = kTri + 6 * nT;
-        stf(k, n.x); stf(k + 1, n.y); stf(k + 2, n.z); stf(k + 3, d); stu(k + 4, a | (b << 8) | (c << 16)); stu(k + 5, (eA & 0xFFu) | ((eB & 0xFFu) << 8) | ((eC & 0xFFu) << 16));
+        const uint32_t k = triAt(nT);
+        stf(k, n.x); stf(k + 1, n.y); stf(k + 2, n.z); stf(k + 3, d);
+        if (kPacked) stu(k + 4, (a & 0xFu) | ((b & 0xFu) << 4) | ((c & 0xFu) << 8) | ((eA & 63u) << 12) | ((eB & 63u) << 18) | ((eC & 63u) << 24));
+        else { stu(k + 4, a | (b << 8) | (c << 16)); stu(k + 5, (eA & 0xFFu) | ((eB & 0xFFu) << 8) | ((eC & 0xFFu) << 16)); }
         active |= bit(nT); ++nT; return true;
     }
     B200_D bool pushEdge(uint32_t a, uint32_t b, uint32_t t0, uint32_t t1)
@@ -736,7 +760,7 @@ struct EpaSm
         for (Mask rest = active; rest; rest &= rest - 1)
         {
             const uint32_t i = lowest(rest);
-            const float d = ldf(kTri + 6 * i + 3);
+            const float d = ldf(triAt(i) + 3);
             if (d < mind) { mind = d; best = i; }
         }
         return best;
@@ -757,10 +781,10 @@ struct EpaSm
     // collision_epa.h:148-167: contact from the closest triangle
     B200_D void result(uint32_t ci, f3& outPoint, f3& outNormal, float& outDepth) const
     {
-        const uint32_t k = kTri + 6 * ci;
+        const uint32_t k = triAt(ci);
         const f3 tn = mk3(ldf(k), ldf(k + 1), ldf(k + 2));
         const float tdist = ldf(k + 3);
-        const uint32_t idx = ldu(k + 4);
+        const uint32_t idx = triIdx(ci);
         const SupPt a = pt(idx & 0xFFu), b = pt((idx >> 8) & 0xFFu), c = pt((idx >> 16) & 0xFFu);
         f3 bc = barycentric(a.m, b.m, c.m, tn * tdist);
         f3 pA = bc.x * a.a + bc.y * b.a + bc.z * c.a;
@@ -775,12 +799,12 @@ struct EpaSm
         Mask once = 0, more = 0;
         for (Mask rest = active; rest; rest &= rest - 1)
         {
-            const uint32_t i = lowest(rest), k = kTri + 6 * i;
-            const uint32_t idx = ldu(k + 4);
+            const uint32_t i = lowest(rest), k = triAt(i);
+            const uint32_t idx = triIdx(i);
             const float d = dot(mk3(ldf(k), ldf(k + 1), ldf(k + 2)), np.m - ptM(idx & 0xFFu));
             if (d > 0.f)
             {
-                const uint32_t e = ldu(k + 5);
+                const uint32_t e = triEdges(i);
 #pragma unroll
                 for (int j = 0; j < 3; ++j)
                 {
@@ -821,8 +845,7 @@ struct EpaSm
             const uint32_t other = (uint32_t)((connect < 8u ? nepp0 : nepp1) >> (7u * (connect & 7u))) & 127u;
             const uint32_t triIndex = i + triOffset;
             if (other == 127u) continue;
-            const uint32_t kt = kTri + 6 * triIndex + 5;
-            stu(kt, (ldu(kt) & 0xFFFF00FFu) | (other << 8));
+            setTriEdgeB(triIndex, other);
             stu(kEdge + other, (ldu(kEdge + other) & 0xFF00FFFFu) | (triIndex << 16));
         }
         return true;

@@ -195,7 +195,9 @@ typedef struct b200phys_config {
     float    bigFactor;             /* colliders whose AABB extent exceeds bigFactor * mean extent skip the grid (0: 3) */
     uint32_t maxContacts;           /* contact capacity            (0: 2 * maxManifolds + 1024) */
     uint32_t reserved[5];           /* reserved[0]: fast mode colours the contact graph afresh every this many steps and lets the
-                                       manifolds inherit their colour in between (0: 8; 1: colour every step) */
+                                       manifolds inherit their colour in between (0: 8; 1: colour every step);
+                                       reserved[1]: grid cells per largest small extent (0: automatic);
+                                       reserved[2]: 1 = no broad-phase candidate reuse (b200phys_get_broadphase_reuse) */
 } b200phys_config;
 
 /* the five counters the reference publishes (physics.cpp:1258-1262) + capacities + per-stage device times */
@@ -335,6 +337,14 @@ int b200phys_enable_events(b200phys_context* ctx, int enable);
 int b200phys_download_events(b200phys_context* ctx, b200phys_collision_begin_event* beginOut, uint32_t beginCapacity, uint32_t* numBegin,
                              b200phys_collider_pair* endOut, uint32_t endCapacity, uint32_t* numEnd);
 int b200phys_get_stats(b200phys_context* ctx, b200phys_stats* out);
+/* Broad-phase candidate reuse (no counterpart in the reference, whose sweep-and-prune sorts afresh every step, collision_broad.cpp:87-166;
+ * the OUTPUT is the same pair list either way). The grid pipeline runs on AABBs grown by a margin and leaves a candidate list; while every
+ * collider's AABB stays inside its grown box a step only filters that list by the exact overlap predicate. On by default;
+ * b200phys_config.reserved[2] = 1 or B200PHYS_BP_REUSE=0 turns it off (the pipeline then runs in every step).
+ * out[0] steps, out[1] steps that ran the grid pipeline, out[2] candidates in the current list, out[3] pairs of the last step,
+ * out[4] margin of the current list (float bits; 0: the last build was exact), out[5] age of the list in steps, out[6] largest movement of
+ * an AABB face per step since the last build (float bits), out[7] mean AABB extent of the grid colliders (float bits). Synchronises the stream. */
+int b200phys_get_broadphase_reuse(b200phys_context* ctx, uint32_t out[8]);
 /* Per-kernel-group device times of the LAST step (timing must be enabled): *count intervals in launch order; names are written as one
  * '\n'-separated string (kernel group names such as "bp_query", "np_epa", "solve"), msOut[i] is the CUDA-event time of interval i.
  * The analogue of the reference's CPU_PROFILE_BLOCK tree (physics.cpp:1182, collision_broad.cpp:299, ...), per kernel group. */

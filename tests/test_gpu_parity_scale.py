@@ -417,3 +417,56 @@ def test_full_size_config3_eighth_properties():
     """BASELINE configs[2] lattice at 131 072 mixed primitives (spheres, capsules, OBBs, hulls): grid with two cells per extent, overflow rows,
     every GJK / EPA kernel incl. the redo path."""
     _full_size_properties(host.build_scene(host.CONFIG_MIXED_PILE, 64, 32, 64, seed=1578123, spacing=0.8), steps=6, sample=800)
+
+
+def _reuse_vs_rebuild(sc, steps, flags=abi.STEP_FAST, kick=None):
+    """The same scene in a context that keeps a candidate list between steps and in one that runs the grid pipeline every step: pair
+    lists and body states must agree bit for bit in every step (the pair set is a function of indices and AABBs only)."""
+    a = make_stepper(sc); b = make_stepper(sc, bp_reuse=False)
+    for step in range(steps):
+        if kick is not None and step == kick:
+            for st in (a, b):      # throw a few bodies across the scene between two steps: their boxes leave the grown ones
+                s = st.download_bodies()
+                s["position"][::97] += np.array([3.0, 1.5, -2.0], dtype=np.float32); s["linearVelocity"][::97] = np.array([0.0, 4.0, 0.0], dtype=np.float32)
+                st.upload_body_states(np.ascontiguousarray(s))
+        a.step(DT, 10, flags); b.step(DT, 10, flags)
+        pa, pb = a.download_pairs(), b.download_pairs()
+        assert np.array_equal(pa, pb), "pair lists differ at step %d (%d vs %d)" % (step, len(pa), len(pb))
+        assert a.download_bodies().tobytes() == b.download_bodies().tobytes(), "body states differ at step %d" % step
+    ra, rb = a.broadphase_reuse(), b.broadphase_reuse()
+    sa, sb = a.stats(), b.stats()
+    assert sa.overflowPairs == 0 and sb.overflowPairs == 0 and sa.numBroadphaseOverlaps == sb.numBroadphaseOverlaps
+    assert ra["steps"] == steps and rb["steps"] == 0 and rb["margin"] == 0.0
+    a.close(); b.close()
+    return ra
+
+
+def test_broadphase_candidate_reuse_resting_scene():
+    """1 024 spheres at rest on the ground: after the two opening builds the candidate list survives, the filtered list is the pair list."""
+    r = _reuse_vs_rebuild(scenes.spheres_on_ground(32, mode="rest"), steps=30)
+    print("reuse (resting spheres):", r)
+    assert r["rebuilds"] <= 6 and r["margin"] > 0.0 and r["candidates"] >= r["pairs"]
+
+
+def test_broadphase_candidate_reuse_settling_pile_with_kick():
+    """16 K spheres settling (fast at first: exact builds; slow later: grown boxes), some bodies teleported at step 20: the containment check
+    must notice and rebuild; both solve orders."""
+    r = _reuse_vs_rebuild(scenes.sphere_pile_settled(32, 16, 32), steps=36, kick=20)
+    print("reuse (settling pile, kick at 20):", r)
+    assert r["rebuilds"] < 36
+    r = _reuse_vs_rebuild(scenes.sphere_pile_settled(16, 16, 16), steps=8, flags=abi.STEP_EXACT_ORDER)
+
+
+def test_broadphase_candidate_reuse_mixed_pile():
+    """8 K mixed primitives (tumbling boxes and hulls change their AABB extents without moving far): reuse vs rebuild contexts bit for bit over
+    24 steps; the reuse context against the oracle's sweep-and-prune over the first steps (GPU and oracle states agree to ~1e-6, not bit for bit,
+    once GJK / EPA contacts are involved, so a borderline pair may differ later on: the comparison that holds for any number of steps is GPU vs GPU)."""
+    sc = host.build_scene(host.CONFIG_MIXED_PILE, 16, 32, 16, seed=1578123, spacing=0.8)
+    r = _reuse_vs_rebuild(sc, steps=24)
+    print("reuse (mixed pile):", r)
+    st = make_stepper(sc); orc = oracle_lib.Oracle(sc, canonical=True)
+    for step in range(4):
+        st.step(DT, 10, abi.STEP_FAST)
+        orc.step(DT, 10, contact_order=st.download_solve_order(6))
+        assert np.array_equal(st.download_pairs(), orc.pairs()), "pairs differ at step %d" % step
+    assert st.stats().overflowPairs == 0
