@@ -126,6 +126,7 @@ struct Context
     float4* wCol = nullptr;     // world colliders, AoS 64 B (gather target of the narrow phase)
     float4* aabbMin = nullptr;  // world AABB min.xyz
     float4* aabbMax = nullptr;  // world AABB max.xyz
+    float4* bSphere = nullptr;  // world bounding sphere of the shape (centre.xyz, radius; radius < 0: padding slot): the narrow phase's cheap separation proof
     float4* hullVerts = nullptr;   // all hull vertices (xyz, 0)
     uint32_t* hullOffsets = nullptr;
     float4* hullAabb = nullptr;    // 2 per hull

@@ -8,6 +8,7 @@
 #include "b200_context.h"
 #include <cstdio>
 #include <cstring>
+#include <cmath>
 #include <new>
 
 using namespace b200;
@@ -41,7 +42,7 @@ int allocateAll(Context& c)
     CK(devAlloc(c.refKeys[0], M + 2)); CK(devAlloc(c.refKeys[1], M + 2)); CK(devAlloc(c.refColors, M + 2)); CK(devAlloc(c.colorKey, M + 2));
     c.scanStatusTiles = (uint32_t)((std::max<size_t>(16 * P, (size_t)c.maxCells + 2) + 2047) / 2048 + 64); CK(devAlloc(c.scanStatus, c.scanStatusTiles)); CK(devAlloc(c.scanState, 4));
     CK(cudaMemset(c.scanStatus, 0, sizeof(unsigned long long) * c.scanStatusTiles)); CK(cudaMemset(c.scanState, 0, 16));
-    CK(devAlloc(c.cLocal, 4 * C)); CK(devAlloc(c.xforms, 2 * T)); CK(devAlloc(c.wCol, 4 * C)); CK(devAlloc(c.aabbMin, C)); CK(devAlloc(c.aabbMax, C));
+    CK(devAlloc(c.cLocal, 4 * C)); CK(devAlloc(c.xforms, 2 * T)); CK(devAlloc(c.wCol, 4 * C)); CK(devAlloc(c.aabbMin, C)); CK(devAlloc(c.aabbMax, C)); CK(devAlloc(c.bSphere, C));
     CK(devAlloc(c.hullVerts, 1)); CK(devAlloc(c.hullOffsets, 2)); CK(devAlloc(c.hullAabb, 2));
     CK(devAlloc(c.cellOf, C)); CK(devAlloc(c.rankInCell, C)); CK(devAlloc(c.cellCount, (size_t)c.maxCells + 2)); CK(devAlloc(c.cellStart, (size_t)c.maxCells + 2));
     CK(devAlloc(c.bpRec, 2 * C)); CK(devAlloc(c.bpRows, 32 * C)); CK(devAlloc(c.bpBigChunks, (size_t)kMaxBig * ((C + 2047) / 2048 + 1))); CK(devAlloc(c.bigList, kMaxBig));
@@ -103,7 +104,7 @@ void freeAll(Context& c)
     void* ptrs[] = { c.bRot, c.bPos, c.bCog, c.bInvI, c.bVel, c.bAng, c.bForce, c.bTorque, c.gVel, c.gPos, c.gInvI, c.bodyMask, c.bodyBase, c.refKeys[0], c.refKeys[1], c.refColors, c.colorKey, c.colorQueue, c.scanStatus, c.scanState, c.cLocal, c.xforms, c.wCol, c.aabbMin, c.aabbMax,
         c.hullVerts, c.hullOffsets, c.hullAabb, c.cellOf, c.rankInCell, c.cellCount, c.cellStart, c.bpRec, c.bpRows, c.bpBigChunks, c.bigList, c.pairCount, c.pairStart, c.pairs,
         c.pairKey, c.pairsTyped, c.pairDst, c.pairsSorted, c.manTmp, c.manScan, c.manScanOut, c.epaSimplex, c.epaWork, c.epaRedo, c.epaRedo2, c.collisions, c.manifolds, c.contacts, c.contactBodies,
-        c.unitPending, c.unitForbid, c.nbrCount, c.nbrList, c.adjStart, c.adjFill, c.adjList, c.adjPos, c.unitSlots, c.levelStart, c.levelFill, c.slotOfContact, c.unitSlotStart, c.unitInfo, c.rows, c.rowImp, c.scanTmp, c.scanTmp64, c.sortHist, c.staging, c.counts, c.haloBuf, c.bpInflMin, c.bpInflMax, c.bpCand };
+        c.unitPending, c.unitForbid, c.nbrCount, c.nbrList, c.adjStart, c.adjFill, c.adjList, c.adjPos, c.unitSlots, c.levelStart, c.levelFill, c.slotOfContact, c.unitSlotStart, c.unitInfo, c.rows, c.rowImp, c.scanTmp, c.scanTmp64, c.sortHist, c.staging, c.counts, c.haloBuf, c.bpInflMin, c.bpInflMax, c.bpCand, c.bSphere };
     for (void* p : ptrs) if (p) cudaFree(p);
     for (int k = 0; k < 6; ++k) if (c.refColorsJoint[k]) cudaFree(c.refColorsJoint[k]);
     for (int k = 0; k < 2; ++k) { if (c.evKeys[k]) cudaFree(c.evKeys[k]); if (c.evPairs[k]) cudaFree(c.evPairs[k]); if (c.evFlag[k]) cudaFree(c.evFlag[k]); if (c.evSlot[k]) cudaFree(c.evSlot[k]); }
@@ -221,7 +222,16 @@ int b200phys_set_hulls(b200phys_context* ctx, const float* vertices, const uint3
             hv[v] = make_float4(p[0], p[1], p[2], 0.f);
             for (int a = 0; a < 3; ++a) { mn[a] = mn[a] < p[a] ? mn[a] : p[a]; mx[a] = mx[a] < p[a] ? p[a] : mx[a]; }
         }
-        ha[2 * h] = make_float4(mn[0], mn[1], mn[2], 0.f); ha[2 * h + 1] = make_float4(mx[0], mx[1], mx[2], 0.f);
+        // .w of the min corner: radius of the sphere around the box centre that holds every vertex (rounded up; the narrow phase's bounding sphere)
+        double r2 = 0.0;
+        for (uint32_t v = vertexOffsets[h]; v < vertexOffsets[h + 1]; ++v)
+        {
+            const float* p = vertices + 3 * (size_t)v; double d2 = 0.0;
+            for (int a = 0; a < 3; ++a) { const double d = (double)p[a] - 0.5 * ((double)mn[a] + (double)mx[a]); d2 += d * d; }
+            if (d2 > r2) r2 = d2;
+        }
+        const float radius = vertexOffsets[h + 1] > vertexOffsets[h] ? (float)(sqrt(r2) * 1.00001 + 1e-7) : 0.f;
+        ha[2 * h] = make_float4(mn[0], mn[1], mn[2], radius); ha[2 * h + 1] = make_float4(mx[0], mx[1], mx[2], 0.f);
     }
     cudaError_t e1 = cudaMemcpy(c.hullVerts, hv, sizeof(float4) * nv, cudaMemcpyHostToDevice);
     cudaError_t e2 = cudaMemcpy(c.hullOffsets, vertexOffsets, sizeof(uint32_t) * ((size_t)numHulls + (numHulls ? 1 : 0)), cudaMemcpyHostToDevice);

@@ -164,7 +164,7 @@ B200_D BoxMM transformToAABB(f3 mn, f3 mx, q4 q, f3 t)
 
 __global__ void __launch_bounds__(kThreads) worldCollidersKernel(uint32_t C, uint32_t N,
     const float4* __restrict__ cLocal, const float4* __restrict__ xforms, const float4* __restrict__ bRot, const float4* __restrict__ bPos,
-    const float4* __restrict__ hullAabb, float4* __restrict__ wCol, float4* __restrict__ aabbMin, float4* __restrict__ aabbMax)
+    const float4* __restrict__ hullAabb, float4* __restrict__ wCol, float4* __restrict__ aabbMin, float4* __restrict__ aabbMax, float4* __restrict__ bSphere)
 {
     for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < C; i += gridDim.x * kThreads)
     {
@@ -178,6 +178,7 @@ __global__ void __launch_bounds__(kThreads) worldCollidersKernel(uint32_t C, uin
         {   // padding slot of a fixed-size halo message: an inverted box overlaps nothing and is never binned
             wCol[4 * i] = wCol[4 * i + 1] = wCol[4 * i + 2] = make_float4(0.f, 0.f, 0.f, 0.f); wCol[4 * i + 3] = make_float4(__uint_as_float(tw & 0xFFFFu), __uint_as_float(0xFFFFFFFFu), 0.f, 0.f);
             aabbMin[i] = make_float4(FLT_MAX, FLT_MAX, FLT_MAX, 0.f); aabbMax[i] = make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, 0.f);
+            bSphere[i] = make_float4(0.f, 0.f, 0.f, -1.f);
             continue;
         }
 
@@ -189,6 +190,8 @@ __global__ void __launch_bounds__(kThreads) worldCollidersKernel(uint32_t C, uin
         float o[10] = { 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f };
         uint32_t geom = 0;
         BoxMM bb;
+        // a sphere around the shape (centre, radius): npClassifyKernel drops pairs whose spheres are clearly apart before any routine runs
+        f3 bsC; float bsR;
         switch (type)
         {
         case B200PHYS_SPHERE:
@@ -196,6 +199,7 @@ __global__ void __launch_bounds__(kThreads) worldCollidersKernel(uint32_t C, uin
             const f3 c = pos + rot * mk3(s[0], s[1], s[2]);
             bb.mn = c - mk3(s[3]); bb.mx = c + mk3(s[3]);
             o[0] = c.x; o[1] = c.y; o[2] = c.z; o[3] = s[3];
+            bsC = c; bsR = s[3];
         } break;
         case B200PHYS_CAPSULE:
         {
@@ -204,6 +208,7 @@ __global__ void __launch_bounds__(kThreads) worldCollidersKernel(uint32_t C, uin
             bb.mn = mk3(FLT_MAX); bb.mx = mk3(-FLT_MAX);
             growBox(bb, a + r3); growBox(bb, a - r3); growBox(bb, b + r3); growBox(bb, b - r3);
             o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = b.x; o[4] = b.y; o[5] = b.z; o[6] = s[6];
+            bsC = (a + b) * 0.5f; bsR = 0.5f * sqrtf(dot(b - a, b - a)) + s[6];
         } break;
         case B200PHYS_CYLINDER:
         {
@@ -216,6 +221,7 @@ __global__ void __launch_bounds__(kThreads) worldCollidersKernel(uint32_t C, uin
             const f3 e = radius * mk3(x, y, z);
             bb.mn = vmin(a - e, b - e); bb.mx = vmax(a + e, b + e);
             o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = b.x; o[4] = b.y; o[5] = b.z; o[6] = radius;
+            bsC = (a + b) * 0.5f; bsR = sqrtf(0.25f * aa + radius * radius);
         } break;
         case B200PHYS_AABB:
         {
@@ -228,6 +234,7 @@ __global__ void __launch_bounds__(kThreads) worldCollidersKernel(uint32_t C, uin
                 const f3 c = rot * ((mn + mx) * 0.5f) + pos, r = (mx - mn) * 0.5f;
                 o[0] = rot.x; o[1] = rot.y; o[2] = rot.z; o[3] = rot.w; o[4] = c.x; o[5] = c.y; o[6] = c.z; o[7] = r.x; o[8] = r.y; o[9] = r.z;
             }
+            bsC = (bb.mn + bb.mx) * 0.5f; bsR = 0.5f * sqrtf(dot(bb.mx - bb.mn, bb.mx - bb.mn));      // (around the world box: contains the shape in both cases)
         } break;
         case B200PHYS_OBB:
         {
@@ -235,6 +242,7 @@ __global__ void __launch_bounds__(kThreads) worldCollidersKernel(uint32_t C, uin
             const q4 q = rot * oq; const f3 c = rot * oc + pos;
             bb = transformToAABB(-rad, rad, q, c);
             o[0] = q.x; o[1] = q.y; o[2] = q.z; o[3] = q.w; o[4] = c.x; o[5] = c.y; o[6] = c.z; o[7] = rad.x; o[8] = rad.y; o[9] = rad.z;
+            bsC = c; bsR = sqrtf(dot(rad, rad));
         } break;
         default:
         {
@@ -242,6 +250,9 @@ __global__ void __launch_bounds__(kThreads) worldCollidersKernel(uint32_t C, uin
             const q4 q = rot * mkq(s[0], s[1], s[2], s[3]); const f3 p = rot * mk3(s[4], s[5], s[6]) + pos;
             bb = transformToAABB(xyz(hullAabb[2 * geom]), xyz(hullAabb[2 * geom + 1]), q, p);
             o[0] = q.x; o[1] = q.y; o[2] = q.z; o[3] = q.w; o[4] = p.x; o[5] = p.y; o[6] = p.z;
+            // hullAabb[2 g].w = largest distance of a vertex from the centre of the local box (b200phys_set_hulls)
+            const float4 hmn = hullAabb[2 * geom], hmx = hullAabb[2 * geom + 1];
+            bsC = q * ((xyz(hmn) + xyz(hmx)) * 0.5f) + p; bsR = hmn.w;
         } break;
         }
         const uint32_t bodyIndex = (objType == B200PHYS_OBJ_STATIC) ? N : objIndex;   // dummy for static colliders (physics.cpp:669)
@@ -251,6 +262,7 @@ __global__ void __launch_bounds__(kThreads) worldCollidersKernel(uint32_t C, uin
         wCol[4 * i + 3] = make_float4(__uint_as_float(type | (objType << 8)), __uint_as_float(bodyIndex), __uint_as_float(geom), 0.f);
         aabbMin[i] = mk4(bb.mn, 0.f);
         aabbMax[i] = mk4(bb.mx, 0.f);
+        bSphere[i] = mk4(bsC, bsR);
     }
 }
 
@@ -324,7 +336,7 @@ void launchIntegrateForces(Context* c, float dt)
 void launchWorldColliders(Context* c)
 {
     if (!c->numColliders) return;
-    launchK(c, worldCollidersKernel, gridFor(c, 8), kThreads, 0, c->numColliders, c->numBodies, c->cLocal, c->xforms, c->bRot, c->bPos, c->hullAabb, c->wCol, c->aabbMin, c->aabbMax);
+    launchK(c, worldCollidersKernel, gridFor(c, 8), kThreads, 0, c->numColliders, c->numBodies, c->cLocal, c->xforms, c->bRot, c->bPos, c->hullAabb, c->wCol, c->aabbMin, c->aabbMax, c->bSphere);
     c->launches++;
 }
 void launchIntegrateVelocities(Context* c, float dt)
