@@ -27,8 +27,28 @@ B200_D bool spheresApart(float4 a, float4 b)
     return dx * dx + dy * dy + dz * dz > reach * reach;         // (false for NaN: the pair goes to its routine)
 }
 
-__global__ void __launch_bounds__(kThreads) npClassifyKernel(const uint2* __restrict__ pairs, const float4* __restrict__ wCol, const float4* __restrict__ bSphere, uint8_t* __restrict__ pairKey, uint2* __restrict__ typed,
-                                                             const DeviceCounts* __restrict__ cnt)
+// Second proof for the pairs whose spheres are not apart: the other shape's sphere against THIS shape's box when it has one (world AABB, OBB,
+// or the box of a hull's vertices in the hull's frame): closest point of the box to the sphere centre, in the box frame. Same slack.
+B200_D bool sphereBoxApart(float4 s, const float4* __restrict__ wCol, const float4* __restrict__ hullAabb, uint32_t i, uint32_t type, uint32_t geom)
+{
+    const float4 r0 = wCol[4 * i], r1 = wCol[4 * i + 1];
+    f3 p, lo, hi; float ref;
+    if (type == B200PHYS_AABB) { p = xyz(s); lo = mk3(r0.x, r0.y, r0.z); hi = mk3(r0.w, r1.x, r1.y); ref = 0.f; }
+    else
+    {
+        const q4 q = toq(r0); const f3 c = mk3(r1.x, r1.y, r1.z);
+        p = conjugate(q) * (xyz(s) - c);
+        ref = fabsf(c.x) + fabsf(c.y) + fabsf(c.z);
+        if (type == B200PHYS_OBB) { const float4 r2 = wCol[4 * i + 2]; hi = mk3(r1.w, r2.x, r2.y); lo = -hi; }
+        else { lo = xyz(hullAabb[2 * geom]); hi = xyz(hullAabb[2 * geom + 1]); }
+    }
+    const float dx = p.x - clampf(p.x, lo.x, hi.x), dy = p.y - clampf(p.y, lo.y, hi.y), dz = p.z - clampf(p.z, lo.z, hi.z);
+    const float reach = s.w * 1.002f + 1e-4f + 1e-5f * (fabsf(s.x) + fabsf(s.y) + fabsf(s.z) + ref);
+    return dx * dx + dy * dy + dz * dz > reach * reach;
+}
+
+__global__ void __launch_bounds__(kThreads) npClassifyKernel(const uint2* __restrict__ pairs, const float4* __restrict__ wCol, const float4* __restrict__ bSphere, const float4* __restrict__ hullAabb,
+                                                             uint8_t* __restrict__ pairKey, uint2* __restrict__ typed, const DeviceCounts* __restrict__ cnt)
 {
     const uint32_t n = cnt->numPairs;
     for (uint32_t p = blockIdx.x * kThreads + threadIdx.x; p < n; p += gridDim.x * kThreads)
@@ -43,10 +63,20 @@ __global__ void __launch_bounds__(kThreads) npClassifyKernel(const uint2* __rest
         else if (oa == B200PHYS_OBJ_RIGID_BODY && ob == B200PHYS_OBJ_RIGID_BODY && ba == bb) key = kBucketDropped;      // :2364-2369
         else
         {
-            if (!(ta < tb)) { uint32_t t = pr.x; pr.x = pr.y; pr.y = t; t = ta; ta = tb; tb = t; }                     // equal types swap too (:2374)
+            float oa_geom = ma.z, ob_geom = mb.z;                                                                   // hull geometry index bits (worldCollidersKernel)
+            if (!(ta < tb)) { uint32_t t = pr.x; pr.x = pr.y; pr.y = t; t = ta; ta = tb; tb = t; const float g = oa_geom; oa_geom = ob_geom; ob_geom = g; }   // equal types swap too (:2374)
             const bool collision = (oa == B200PHYS_OBJ_RIGID_BODY && ob == B200PHYS_OBJ_RIGID_BODY) || oa == B200PHYS_OBJ_STATIC || ob == B200PHYS_OBJ_STATIC; // :2378-2379
             key = collision ? bucketOf(ta, tb) : kBucketOverlap;
-            if (collision && bSphere && spheresApart(bSphere[pr.x], bSphere[pr.y])) key = kBucketDropped;
+            if (collision && bSphere)
+            {
+                const float4 sa = bSphere[pr.x], sb = bSphere[pr.y];
+                bool apart = spheresApart(sa, sb);
+                if (!apart && ta >= B200PHYS_AABB && !(ta == B200PHYS_AABB && tb == B200PHYS_AABB))     // (box vs box in world axes: the broad phase already knows)
+                    apart = sphereBoxApart(sb, wCol, hullAabb, pr.x, ta, __float_as_uint(oa_geom));
+                if (!apart && tb >= B200PHYS_AABB && !(ta == B200PHYS_AABB && tb == B200PHYS_AABB))
+                    apart = sphereBoxApart(sa, wCol, hullAabb, pr.y, tb, __float_as_uint(ob_geom));
+                if (apart) key = kBucketDropped;
+            }
         }
         pairKey[p] = (uint8_t)key;
         typed[p] = pr;
@@ -561,7 +591,7 @@ void launchNarrowphase(Context* c)
     const int G = gridFor(c, 8);
     static int sphereCull = -1;
     if (sphereCull < 0) { const char* e = getenv("B200PHYS_SPHERE_CULL"); sphereCull = (e && e[0] == '0') ? 0 : 1; }       // tuning / A-B override
-    launchK(c, npClassifyKernel, G, kThreads, 0, c->pairs, c->wCol, sphereCull ? c->bSphere : (const float4*)nullptr, c->pairKey, c->pairsTyped, cnt);
+    launchK(c, npClassifyKernel, G, kThreads, 0, c->pairs, c->wCol, sphereCull ? c->bSphere : (const float4*)nullptr, c->hullAabb, c->pairKey, c->pairsTyped, cnt);
     c->launches += 1;
     stableSmallKeySort(c, c->pairKey, &cnt->numPairs, c->maxPairs, kNumPairKeys, c->pairDst, cnt->keyStart);
     launchK(c, npPermuteKernel, G, kThreads, 0, c->pairsTyped, c->pairDst, c->pairsSorted, cnt);
