@@ -528,18 +528,11 @@ __global__ void __launch_bounds__(kThreads) npInteractionKernel(const uint2* __r
     }
 }
 
-// pruned / overlap-only slots produce no manifold
-__global__ void __launch_bounds__(kThreads) npClearTailKernel(unsigned long long* __restrict__ manScan, const DeviceCounts* __restrict__ cnt)
-{
-    const uint32_t q0 = cnt->keyStart[kBucketDropped], q1 = cnt->numPairs;
-    for (uint32_t q = q0 + blockIdx.x * kThreads + threadIdx.x; q < q1; q += gridDim.x * kThreads) manScan[q] = 0ull;
-}
-
 __global__ void npTotalsKernel(const unsigned long long* __restrict__ scanOut, uint32_t maxManifolds, uint32_t maxContacts, DeviceCounts* cnt)
 {
     if (threadIdx.x == 0 && blockIdx.x == 0)
     {
-        const unsigned long long t = scanOut[cnt->numPairs];
+        const unsigned long long t = scanOut[cnt->keyStart[kBucketDropped]];
         const uint32_t nm = (uint32_t)(t & 0xFFFFFFFFull), nk = (uint32_t)(t >> 32);
         cnt->numManifoldsWanted = nm;
         cnt->numManifolds = min(nm, maxManifolds);
@@ -659,9 +652,9 @@ void launchNarrowphase(Context* c)
     }
     c->launches += 1;
     timelineMark(c, epaMode == 2 ? "np_epa_redo" : "np_epa");
-    launchK(c, npClearTailKernel, G, kThreads, 0, c->manScan, cnt);
-    c->launches += 5;
-    scanExclusiveU64(c, c->manScan, c->manScanOut, &cnt->numPairs, c->maxPairs, nullptr);
+    c->launches += 4;
+    // manifold / contact offsets: only the collision buckets can hold manifolds (the pruned and overlap-only pairs are sorted behind them)
+    scanExclusiveU64(c, c->manScan, c->manScanOut, &cnt->keyStart[kBucketDropped], c->maxPairs, nullptr);
     // rigid body vs trigger / force field: boolean overlap tests, compaction, force-field push (physics.cpp:1255, before the force integration)
     if (c->numNonCollisionColliders)
     {

@@ -51,3 +51,10 @@ def test_library_owned_nccl_transport_matches_python_driven_halo():
     """b200phys_create_distributed / b200phys_step_distributed (NCCL inside the C library) give bit-identical states to the Python-driven halo."""
     rc, out = _run("mgpu_cabi_check.py", 29531)
     assert rc == 0 and "MGPU_CABI_CHECK PASS" in out, out[-3000:]
+
+
+@pytest.mark.skipif(_gpus() < 2, reason="needs 2 GPUs on one box")
+def test_broadphase_candidate_reuse_with_ghosts_is_bit_identical():
+    """tests/mgpu_reuse_check.py: 120 distributed steps of a pile coming to rest, candidate reuse vs per-step rebuild, ghosts included."""
+    rc, out = _run("mgpu_reuse_check.py", 29541)
+    assert rc == 0 and "MGPU_REUSE_CHECK PASS" in out, out[-3000:]

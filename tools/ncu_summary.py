@@ -10,7 +10,7 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio", "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
         "smsp__inst_executed_op_local_ld.sum", "smsp__inst_executed_op_local_st.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active"]
 # kernel -> the timeline group bench.py reports it under (b200phys_get_timeline)
-GROUP = {"solveKernel": "solve", "npGjkKernel": "np_gjk", "npEpaSmallKernel": "np_epa", "npEpaWarpKernel": "np_epa_redo", "npEpaKernel": "np_epa_redo",
+GROUP = {"solveKernel": "solve", "npGjkKernel": "np_gjk", "npEpaSmallKernel": "np_epa", "npEpaSmKernel": "np_epa", "npClassifyKernel": "np_classify_sort", "bpFilterKernel": "bp_filter", "depRankKernel": "solver_order", "npEpaWarpKernel": "np_epa_redo", "npEpaKernel": "np_epa_redo",
          "bpRowsDirectKernel": "bp_tiles", "bpTileKernel": "bp_tiles", "bpEmitKernel": "bp_emit", "initContactRowsKernel": "solver_rows",
          "npCollideKernel": "np_closed_form_sat", "npCompactKernel": "np_compact"}
 SCALE = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
