@@ -660,24 +660,27 @@ __global__ void __launch_bounds__(kThreads) bpEmitKernel(uint32_t C, uint32_t em
             uint32_t cntI = id < C ? pairCount[id] : 0u;
             const uint32_t slot = id < C ? slotOf[id] : 0xFFFFFFFFu;
             if (cntI > kRowCap || slot == 0xFFFFFFFFu) cntI = 0;      // written by the paths below (overflow rows, big colliders)
-            const uint32_t base = __shfl_sync(0xffffffffu, start, 0);
-            const uint32_t endId = min(id0 + 32u, C);
-            const uint32_t end = pairStart[endId];
-            for (uint32_t p0 = base; p0 < end; p0 += 32u)
+            // the warp's rows as one run of `total` entries (prefix over the lanes' counts): rows written elsewhere (overflow rows, big colliders --
+            // a ground box with a low index has a row of 10^5 pairs) contribute nothing and are not walked over
+            uint32_t incl = cntI;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (uint32_t)o) incl += t; }
+            const uint32_t excl = incl - cntI, total = __shfl_sync(0xffffffffu, incl, 31);
+            for (uint32_t t0 = 0; t0 < total; t0 += 32u)
             {
-                const uint32_t p = p0 + lane;                                   // (all lanes take part in the shuffles below)
-                // row i = last lane whose start <= p
+                const uint32_t t = t0 + lane;                                   // (all lanes take part in the shuffles below)
+                // row i = last lane whose first entry is at or before t (empty rows share their successor's offset and lose against it)
                 uint32_t i = 0;
 #pragma unroll
                 for (int step = 16; step > 0; step >>= 1)
                 {
                     const uint32_t cand = i + (uint32_t)step;
-                    const uint32_t s = __shfl_sync(0xffffffffu, start, (int)min(cand, 31u));
-                    if (cand < 32u && s <= p) i = cand;
+                    const uint32_t e = __shfl_sync(0xffffffffu, excl, (int)min(cand, 31u));
+                    if (cand < 32u && e <= t) i = cand;
                 }
-                const uint32_t si = __shfl_sync(0xffffffffu, start, (int)i), ci = __shfl_sync(0xffffffffu, cntI, (int)i), sl = __shfl_sync(0xffffffffu, slot, (int)i);
-                const uint32_t k = p - si;
-                if (p < end && k < ci && p < maxPairs) pairs[p] = make_uint2(id0 + i, rows[(size_t)sl * kRowCap + k]);
+                const uint32_t si = __shfl_sync(0xffffffffu, start, (int)i), ei = __shfl_sync(0xffffffffu, excl, (int)i), sl = __shfl_sync(0xffffffffu, slot, (int)i);
+                const uint32_t k = t - ei, p = si + k;
+                if (t < total && p < maxPairs) pairs[p] = make_uint2(id0 + i, rows[(size_t)sl * kRowCap + k]);
             }
         }
         return;
@@ -971,14 +974,14 @@ void launchBroadphase(Context* c)
     timelineMark(c, "bp_build");
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(bpTileKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileCtaShared)); attr = true; }
-    const uint32_t tileCtas = (uint32_t)c->numSMs * 4u, bigCtas = (uint32_t)c->numSMs;
+    const uint32_t tileCtas = (uint32_t)c->numSMs * 4u, bigCtas = (uint32_t)c->numSMs * 4u;      // (big rows: one 2048-collider chunk per CTA at 1 M colliders; with one CTA per SM the counting pass was a 0.1 ms latency chain)
     launchK(c, bpTileKernel, tileCtas + bigCtas, kTileThreads, sizeof(TileCtaShared), C, tileCtas, numChunks, c->bpRec, c->cellStart, boxMin, boxMax, c->bigList,
                                                                                       c->pairCount, c->bpRows, c->cellOf, c->bpBigChunks, cnt);
     launchK(c, bpRowsDirectKernel, gridFor(c, 6), kDirectThreads, 0, C, c->bpRec, c->cellStart, boxMin, boxMax, c->bigList, c->pairCount, c->bpRows, c->cellOf, cnt);
     c->launches += 3;
     timelineMark(c, "bp_tiles");
     scanExclusiveU32(c, c->pairCount, c->pairStart, reuse ? &cnt->bpScanColliders : (const uint32_t*)nullptr, C, nullptr);
-    const uint32_t emitCtas = (uint32_t)c->numSMs * 6u, extraCtas = (uint32_t)c->numSMs * 2u;
+    const uint32_t emitCtas = (uint32_t)c->numSMs * 6u, extraCtas = (uint32_t)c->numSMs * 4u;
     launchK(c, bpEmitKernel, emitCtas + extraCtas, kThreads, 0, C, emitCtas, numChunks, c->rankInCell, c->bpRows, c->pairCount, c->pairStart, c->bpRec, c->cellStart,
                                                                   boxMin, boxMax, c->bigList, c->cellOf, c->bpBigChunks, c->pairs, c->maxPairs, c->bpCand, c->maxCand, cnt);
     c->launches += 1;
