@@ -797,7 +797,8 @@ __global__ void bpDecideKernel(uint32_t force, uint32_t C, uint32_t maxCand, flo
     const float lastMargin = __uint_as_float(cnt->bpMarginBits);
     if (force) cnt->bpMarginOff = 0;
     // a list built without margin was written straight into the pair list of its step: nothing to reuse
-    const bool rebuild = force || cnt->bpViolations != 0u || !(lastMargin > 0.f) || !cnt->bpEmitToCand;
+    // ... and a list that did not fit its buffer (reported as a pair overflow when it happened) is not complete
+    const bool rebuild = force || cnt->bpViolations != 0u || !(lastMargin > 0.f) || !cnt->bpEmitToCand || cnt->numCandWanted > cnt->numCand;
     // how far did the box faces move per step since the last build? (the check's excess is relative to the grown box)
     const float moved = force ? 0.f : fmaxf(sortableToFloat(cnt->bpExcessBits) + fmaxf(lastMargin, 0.f), 0.f);
     const float perStep = moved / (float)max(cnt->bpAge, 1u);
