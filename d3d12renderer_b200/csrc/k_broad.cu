@@ -19,6 +19,8 @@
 //   scan     : partners per collider -> canonical pair offsets
 //   emit     : rows -> pair list with coalesced stores; rows that overflowed, colliders whose reach left the staged window and the
 //              big colliders' rows are produced here by direct traversal.
+// With candidate reuse (default, see "candidate reuse" below) three more launches frame the pipeline: check (are all boxes still inside the grown
+// boxes of the last build?), decide (one thread: rebuild or reuse; every kernel above is gated by its flag) and filter (candidates -> pairs).
 // Correctness does not depend on the cell size: a partner's centre lies inside the query AABB grown by half the largest
 // small extent, and cell coordinates are a monotone function of position, so no rounding can hide a pair.
 #include "b200_context.h"
