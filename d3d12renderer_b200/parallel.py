@@ -173,21 +173,62 @@ class SlabShard:
         self.st.step(dt, iterations, flags)
 
 
+def articulated_groups(n_bodies, joints):
+    """Connected components of the joint graph: group[b] = smallest body index of b's mechanism (bodies without joints are their own group).
+    `joints`: {kind: (structs, pairs)} as in the scene dicts; pairs carry rbA / rbB. A joint to a body index >= n_bodies (the static dummy)
+    connects nothing."""
+    parent = np.arange(n_bodies, dtype=np.int64)
+
+    def find(x):
+        while parent[x] != x:
+            parent[x] = parent[parent[x]]; x = parent[x]
+        return x
+    for _, (_, pairs) in sorted(joints.items()):
+        for a, b in zip(pairs["rbA"].tolist(), pairs["rbB"].tolist()):
+            if a >= n_bodies or b >= n_bodies:
+                continue
+            ra, rb = find(a), find(b)
+            if ra != rb:
+                parent[max(ra, rb)] = min(ra, rb)
+    return np.array([find(i) for i in range(n_bodies)], dtype=np.int64)
+
+
 def shard_scene(scene, rank, world, bounds, axis=0):
-    """Splits a single-GPU scene dict into this rank's shard: owned bodies (centre inside the slab) with their colliders,
-    static colliders replicated on every rank. Returns (shard_scene, global_body_ids, global_collider_ids)."""
+    """Splits a single-GPU scene dict into this rank's shard: owned bodies with their colliders, static colliders replicated on every rank.
+    A body without joints is owned by the slab that holds its centre. Jointed mechanisms (ragdolls, vehicles: the connected components of the
+    joint graph) are sharded WHOLE: every body of a mechanism goes, with all its joints, to the slab that holds the mechanism's mean position,
+    so no joint ever spans two ranks (a limb that sticks out into the neighbour's slab is still owned here and reaches the neighbour as a ghost,
+    where it takes part in contacts only). Joint body indices are remapped to the shard; a joint's partner >= len(bodies) (the static dummy)
+    becomes the shard's own dummy index. Returns (shard_scene, global_body_ids, global_collider_ids)."""
     bodies, colliders = scene["bodies"], scene["colliders"]
-    if any(len(j[0]) for j in scene.get("joints", {}).values()):
-        raise ValueError("joint chains are not sharded across GPUs yet (shard whole ragdolls instead)")
-    owner = owner_of(bodies["position"][:, axis].astype(np.float64), bounds)
+    n = len(bodies)
+    joints = {k: v for k, v in (scene.get("joints") or {}).items() if len(v[0])}
+    x = bodies["position"][:, axis].astype(np.float64)
+    if joints:
+        group = articulated_groups(n, joints)
+        sums = np.bincount(group, weights=x, minlength=n); counts = np.bincount(group, minlength=n)
+        x = (sums / np.maximum(counts, 1))[group]                 # every body votes with its mechanism's mean position
+    owner = owner_of(x, bounds)
     mine = np.nonzero(owner == rank)[0]
-    remap = np.full(len(bodies), -1, dtype=np.int64); remap[mine] = np.arange(len(mine))
+    remap = np.full(n, -1, dtype=np.int64); remap[mine] = np.arange(len(mine))
     is_body = colliders["objectType"] == 0
-    keep = np.nonzero(~is_body | (remap[np.minimum(colliders["objectIndex"], len(bodies) - 1)] >= 0))[0]
+    keep = np.nonzero(~is_body | (remap[np.minimum(colliders["objectIndex"], n - 1)] >= 0))[0]
     sub_c = colliders[keep].copy()
     bsel = sub_c["objectType"] == 0
     sub_c["objectIndex"][bsel] = remap[sub_c["objectIndex"][bsel]].astype(np.uint32)
-    out = {"bodies": np.ascontiguousarray(bodies[mine]), "colliders": np.ascontiguousarray(sub_c), "transforms": scene["transforms"], "joints": {}}
+    sub_j = {}
+    for k, (structs, pairs) in joints.items():
+        a = pairs["rbA"].astype(np.int64); b = pairs["rbB"].astype(np.int64)
+        anchor = np.where(a < n, a, b)                                # the dynamic end decides (both ends share a mechanism otherwise)
+        sel = np.nonzero((anchor < n) & (remap[np.minimum(anchor, n - 1)] >= 0))[0]
+        p = pairs[sel].copy()
+        for f, src in (("rbA", a), ("rbB", b)):
+            v = src[sel]
+            loc = np.where(v < n, remap[np.minimum(v, n - 1)], len(mine))
+            assert np.all(loc >= 0), "a joint spans two mechanisms' owners"      # cannot happen: connected components are sharded whole
+            p[f] = loc.astype(p[f].dtype)
+        sub_j[k] = (np.ascontiguousarray(structs[sel]), np.ascontiguousarray(p))
+    out = {"bodies": np.ascontiguousarray(bodies[mine]), "colliders": np.ascontiguousarray(sub_c), "transforms": scene["transforms"], "joints": sub_j}
     for k in ("hull_vertices", "hull_offsets", "hull_triangles"):
         if k in scene:
             out[k] = scene[k]

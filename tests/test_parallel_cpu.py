@@ -8,7 +8,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from d3d12renderer_b200 import parallel, scenes
+from d3d12renderer_b200 import abi, parallel, scenes
 
 
 def _free_port():
@@ -86,3 +86,51 @@ def test_shard_scene_covers_every_body_once_and_replicates_statics():
         # the remapped collider still points at the same global body
         assert np.array_equal(body_ids[sub["colliders"]["objectIndex"][dyn]], sc["colliders"]["objectIndex"][col_ids][dyn])
     assert np.all(seen == 1)
+
+
+def test_articulated_groups_are_the_connected_components_of_the_joint_graph():
+    pairs = np.zeros(4, dtype=abi.body_pair_dtype)
+    pairs["rbA"] = [0, 1, 5, 7]; pairs["rbB"] = [1, 2, 6, 9]          # 0-1-2, 5-6, 7-(9 = the static dummy of an 9-body scene)
+    g = parallel.articulated_groups(9, {3: (np.zeros(4), pairs)})
+    assert g.tolist() == [0, 0, 0, 3, 4, 5, 5, 7, 8]
+
+
+def test_shard_scene_keeps_jointed_mechanisms_whole_and_remaps_their_joints():
+    """BASELINE config 4 (ragdolls) can be sharded: every ragdoll goes whole -- bodies, colliders, hinge and cone-twist joints -- to the slab that
+    holds its mean position. With the ragdolls far enough apart not to touch each other the shards are independent islands on a shared static
+    ground, so stepping each shard with the oracle must reproduce the full scene's body states BIT FOR BIT (the canonical contact and joint
+    order of a sub-scene is the restriction of the full scene's order): that pins the body / collider / joint index remapping."""
+    import oracle_lib
+    from d3d12renderer_b200 import host
+    sc = host.build_scene(host.CONFIG_RAGDOLLS, 4, 1, 3, seed=7, spacing=4.0)
+    n = len(sc["bodies"]); assert n == 12 * 14
+    xs = sc["bodies"]["position"][:, 0]
+    full = oracle_lib.Oracle(sc, canonical=True)
+    DT = np.float32(1.0 / 120.0)
+    for _ in range(30):
+        full.step(DT, 10)
+    ref = full.body_states()
+    for world in (2, 3):
+        bounds = parallel.slab_bounds(world, float(xs.min()) - 0.5, float(xs.max()) + 0.5)
+        seen = np.zeros(n, dtype=int); joints_seen = {k: 0 for k in sc["joints"]}
+        for rank in range(world):
+            sub, ids, cids = parallel.shard_scene(sc, rank, world, bounds)
+            seen[ids] += 1
+            assert len(ids) % 14 == 0 and np.array_equal(ids.reshape(-1, 14)[:, 0] % 14, np.zeros(len(ids) // 14, dtype=int))     # whole ragdolls, order kept
+            nb = len(sub["bodies"])
+            for k, (structs, pairs) in sub["joints"].items():
+                joints_seen[k] += len(structs)
+                assert np.all(pairs["rbA"] < nb) and np.all(pairs["rbB"] < nb)
+                # mapped back to global ids every kept joint is one of the original joints, in the original order
+                orig = sc["joints"][k][1]
+                glob = np.stack([ids[pairs["rbA"]], ids[pairs["rbB"]]], 1)
+                sel = np.nonzero(np.isin(orig["rbA"], ids))[0]
+                assert np.array_equal(glob, np.stack([orig["rbA"][sel], orig["rbB"][sel]], 1)) and structs.tobytes() == sc["joints"][k][0][sel].tobytes()
+            if nb == 0:
+                continue
+            orc = oracle_lib.Oracle(sub, canonical=True)
+            for _ in range(30):
+                orc.step(DT, 10)
+            got = orc.body_states()
+            assert got.tobytes() == ref[ids].tobytes(), "shard %d of %d does not reproduce the full scene" % (rank, world)
+        assert np.all(seen == 1) and all(joints_seen[k] == len(sc["joints"][k][0]) for k in joints_seen)
